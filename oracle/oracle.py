@@ -1,0 +1,351 @@
+"""ctypes view of the CPU oracle (oracle/mml_oracle.c).
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs -- never from mymedialite_b200/ (the product).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libmmloracle.so")
+
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+LOSS_RMSE, LOSS_MAE, LOSS_LOGISTIC = 0, 1, 2
+
+
+class RngState(C.Structure):
+    _fields_ = [("seed_array", C.c_int32 * 56), ("inext", C.c_int32), ("inextp", C.c_int32)]
+
+
+class MFParams(C.Structure):
+    _fields_ = [
+        ("num_factors", C.c_int32), ("learn_rate", C.c_float), ("decay", C.c_float),
+        ("regularization", C.c_float), ("num_iter", C.c_int32),
+        ("init_mean", C.c_double), ("init_stddev", C.c_double),
+        ("bias_learn_rate", C.c_float), ("bias_reg", C.c_float),
+        ("reg_u", C.c_float), ("reg_i", C.c_float),
+        ("frequency_regularization", C.c_int32), ("loss", C.c_int32),
+        ("max_threads", C.c_int32), ("bold_driver", C.c_int32),
+        ("naive_parallelization", C.c_int32), ("omp_threads", C.c_int32),
+    ]
+
+
+def build(force=False):
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "mml_oracle.c")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(_SO)
+    R = C.POINTER(RngState)
+    P = C.POINTER(MFParams)
+    vp = C.c_void_p
+    sig = {
+        "mo_rng_init": (None, [R, C.c_int32]),
+        "mo_rng_next": (C.c_int32, [R]),
+        "mo_rng_next_double": (C.c_double, [R]),
+        "mo_rng_next_max": (C.c_int32, [R, C.c_int32]),
+        "mo_shuffle_i32": (None, [R, i32p, C.c_int64]),
+        "mo_shuffle_targets": (None, [R, i32p, C.c_int64]),
+        "mo_shuffle_apply": (None, [i32p, i32p, C.c_int64]),
+        "mo_normal_sample": (C.c_double, [R, C.c_double, C.c_double]),
+        "mo_init_normal": (None, [R, f32p, C.c_int64, C.c_double, C.c_double]),
+        "mo_count_by": (None, [i32p, C.c_int64, C.c_int32, i32p]),
+        "mo_build_index": (None, [i32p, C.c_int64, C.c_int32, i64p, i32p]),
+        "mo_average": (C.c_float, [f32p, C.c_int64]),
+        "mo_scale": (None, [f32p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "mo_random_index": (None, [R, i32p, C.c_int64]),
+        "mo_partition_users_and_items": (C.c_int32, [R, i32p, i32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, i64p, i32p, vp, vp]),
+        "mo_partition_blocks_given": (None, [i32p, i32p, C.c_int64, i32p, i32p, C.c_int32, i64p, i32p]),
+        "mo_partition_indices": (C.c_int32, [i32p, C.c_int64, C.c_int32, i64p, i32p]),
+        "mo_mf_params_default": (None, [P]),
+        "mo_model_create": (vp, [C.c_int, P, i32p, i32p, f32p, C.c_int64, C.c_int32, C.c_int32]),
+        "mo_model_destroy": (None, [vp]),
+        "mo_model_init": (None, [vp, R]),
+        "mo_model_train": (None, [vp, R]),
+        "mo_model_iterate": (None, [vp, R]),
+        "mo_model_predict": (C.c_float, [vp, C.c_int32, C.c_int32]),
+        "mo_model_predict_many": (None, [vp, i32p, i32p, C.c_int64, f32p]),
+        "mo_model_evaluate": (None, [vp, i32p, i32p, f32p, C.c_int64, f32p]),
+        "mo_model_objective": (C.c_float, [vp]),
+        "mo_model_learnrate": (C.c_float, [vp]),
+        "mo_model_global_bias": (C.c_float, [vp]),
+        "mo_model_user_factors": (C.POINTER(C.c_float), [vp]),
+        "mo_model_item_factors": (C.POINTER(C.c_float), [vp]),
+        "mo_model_user_bias": (C.POINTER(C.c_float), [vp]),
+        "mo_model_item_bias": (C.POINTER(C.c_float), [vp]),
+        "mo_model_random_index": (C.POINTER(C.c_int32), [vp]),
+        "mo_model_iterate_indices": (None, [vp, i32p, C.c_int64, C.c_int, C.c_int]),
+        "mo_bmf_replay_runs": (None, [vp, i32p, i64p, C.c_int64, i32p, f32p, C.c_int32]),
+        "mo_wrmf_optimize": (None, [i64p, i32p, C.c_int32, f32p, f32p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int]),
+        "mo_wrmf_gram": (None, [f32p, C.c_int32, C.c_int32, f64p]),
+        "mo_feedback_csr": (C.c_int64, [i32p, i32p, C.c_int64, C.c_int32, i64p, i32p]),
+        "mo_recommend_mf": (C.c_int64, [f32p, f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, i32p, C.c_int64, i32p, C.c_int64, i32p, f32p]),
+        "mo_recommend_model": (C.c_int64, [vp, C.c_int32, C.c_int32, i32p, C.c_int64, i32p, C.c_int64, i32p, f32p]),
+        "mo_row_scalar_product": (C.c_float, [f32p, f32p, C.c_int32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+class Random:
+    """System.Random as used through MyMediaLite.Random (Random.cs:23-64)."""
+
+    def __init__(self, seed):
+        self.state = RngState()
+        lib().mo_rng_init(C.byref(self.state), int(seed))
+
+    @property
+    def ref(self):
+        return C.byref(self.state)
+
+    def next(self):
+        return lib().mo_rng_next(self.ref)
+
+    def next_max(self, m):
+        return lib().mo_rng_next_max(self.ref, int(m))
+
+    def next_double(self):
+        return lib().mo_rng_next_double(self.ref)
+
+    def shuffle(self, a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        lib().mo_shuffle_i32(self.ref, a, a.size)
+        return a
+
+    def shuffle_targets(self, n):
+        h = np.empty(n, dtype=np.int32)
+        lib().mo_shuffle_targets(self.ref, h, n)
+        return h
+
+    def init_normal(self, n, mean=0.0, stddev=0.1):
+        d = np.empty(n, dtype=np.float32)
+        lib().mo_init_normal(self.ref, d, n, mean, stddev)
+        return d
+
+
+def default_params(**kw):
+    p = MFParams()
+    lib().mo_mf_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    if "regularization" in kw:           # BiasedMatrixFactorization.cs:97-104: setter fans out
+        if "reg_u" not in kw:
+            p.reg_u = kw["regularization"]
+        if "reg_i" not in kw:
+            p.reg_i = kw["regularization"]
+    return p
+
+
+class Model:
+    """MatrixFactorization / BiasedMatrixFactorization restated (see mml_oracle.c)."""
+
+    def __init__(self, users, items, values, biased=True, max_user=None, max_item=None, **params):
+        self.users = np.ascontiguousarray(users, dtype=np.int32)
+        self.items = np.ascontiguousarray(items, dtype=np.int32)
+        self.values = np.ascontiguousarray(values, dtype=np.float32)
+        self.max_user = int(self.users.max()) if max_user is None else int(max_user)
+        self.max_item = int(self.items.max()) if max_item is None else int(max_item)
+        self.params = default_params(**params)
+        self.k = self.params.num_factors
+        self.biased = biased
+        self.h = lib().mo_model_create(int(biased), C.byref(self.params), self.users, self.items, self.values,
+                                       self.users.size, self.max_user, self.max_item)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().mo_model_destroy(self.h)
+            self.h = None
+
+    def init(self, rng):
+        lib().mo_model_init(self.h, rng.ref)
+
+    def train(self, rng):
+        lib().mo_model_train(self.h, rng.ref)
+
+    def iterate(self, rng):
+        lib().mo_model_iterate(self.h, rng.ref)
+
+    def iterate_indices(self, idx, update_user=True, update_item=True):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        lib().mo_model_iterate_indices(self.h, idx, idx.size, int(update_user), int(update_item))
+
+    def replay_runs(self, run_item, run_ptr, ent_user, ent_value, batch):
+        run_item = np.ascontiguousarray(run_item, dtype=np.int32)
+        run_ptr = np.ascontiguousarray(run_ptr, dtype=np.int64)
+        ent_user = np.ascontiguousarray(ent_user, dtype=np.int32)
+        ent_value = np.ascontiguousarray(ent_value, dtype=np.float32)
+        lib().mo_bmf_replay_runs(self.h, run_item, run_ptr, run_item.size, ent_user, ent_value, int(batch))
+
+    def predict(self, u, i):
+        return lib().mo_model_predict(self.h, int(u), int(i))
+
+    def predict_many(self, u, i):
+        u = np.ascontiguousarray(u, dtype=np.int32)
+        i = np.ascontiguousarray(i, dtype=np.int32)
+        out = np.empty(u.size, dtype=np.float32)
+        lib().mo_model_predict_many(self.h, u, i, u.size, out)
+        return out
+
+    def evaluate(self, u, i, v):
+        u = np.ascontiguousarray(u, dtype=np.int32)
+        i = np.ascontiguousarray(i, dtype=np.int32)
+        v = np.ascontiguousarray(v, dtype=np.float32)
+        out = np.empty(4, dtype=np.float32)
+        lib().mo_model_evaluate(self.h, u, i, v, u.size, out)
+        return {"RMSE": float(out[0]), "MAE": float(out[1]), "NMAE": float(out[2]), "CBD": float(out[3])}
+
+    def objective(self):
+        return lib().mo_model_objective(self.h)
+
+    @property
+    def learnrate(self):
+        return lib().mo_model_learnrate(self.h)
+
+    @property
+    def global_bias(self):
+        return lib().mo_model_global_bias(self.h)
+
+    def _arr(self, ptr, shape):
+        return np.ctypeslib.as_array(ptr, shape=shape)
+
+    @property
+    def user_factors(self):
+        return self._arr(lib().mo_model_user_factors(self.h), (self.max_user + 1, self.k))
+
+    @property
+    def item_factors(self):
+        return self._arr(lib().mo_model_item_factors(self.h), (self.max_item + 1, self.k))
+
+    @property
+    def user_bias(self):
+        return self._arr(lib().mo_model_user_bias(self.h), (self.max_user + 1,))
+
+    @property
+    def item_bias(self):
+        return self._arr(lib().mo_model_item_bias(self.h), (self.max_item + 1,))
+
+    @property
+    def random_index(self):
+        p = lib().mo_model_random_index(self.h)
+        if not p:
+            return None
+        return self._arr(p, (self.users.size,))
+
+
+def count_by(ids, max_id):
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    out = np.empty(max_id + 1, dtype=np.int32)
+    lib().mo_count_by(ids, ids.size, max_id, out)
+    return out
+
+
+def build_index(ids, max_id):
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    ptr = np.empty(max_id + 2, dtype=np.int64)
+    idx = np.empty(ids.size, dtype=np.int32)
+    lib().mo_build_index(ids, ids.size, max_id, ptr, idx)
+    return ptr, idx
+
+
+def partition_users_and_items(rng, users, items, max_user, max_item, num_groups):
+    users = np.ascontiguousarray(users, dtype=np.int32)
+    items = np.ascontiguousarray(items, dtype=np.int32)
+    g = min(num_groups, max_user + 1, max_item + 1)
+    ptr = np.empty(g * g + 1, dtype=np.int64)
+    idx = np.empty(users.size, dtype=np.int32)
+    up = np.empty(max_user + 1, dtype=np.int32)
+    ip = np.empty(max_item + 1, dtype=np.int32)
+    g2 = lib().mo_partition_users_and_items(rng.ref, users, items, users.size, max_user, max_item, num_groups,
+                                            ptr, idx, up.ctypes.data, ip.ctypes.data)
+    assert g2 == g
+    return g, ptr, idx, up, ip
+
+
+def partition_blocks_given(users, items, user_perm, item_perm, g):
+    users = np.ascontiguousarray(users, dtype=np.int32)
+    items = np.ascontiguousarray(items, dtype=np.int32)
+    ptr = np.empty(g * g + 1, dtype=np.int64)
+    idx = np.empty(users.size, dtype=np.int32)
+    lib().mo_partition_blocks_given(users, items, users.size, np.ascontiguousarray(user_perm, dtype=np.int32),
+                                    np.ascontiguousarray(item_perm, dtype=np.int32), g, ptr, idx)
+    return ptr, idx
+
+
+def partition_indices(random_index, num_groups):
+    ri = np.ascontiguousarray(random_index, dtype=np.int32)
+    g = min(num_groups, ri.size)
+    ptr = np.empty(g + 1, dtype=np.int64)
+    idx = np.empty(ri.size, dtype=np.int32)
+    g2 = lib().mo_partition_indices(ri, ri.size, num_groups, ptr, idx)
+    assert g2 == g
+    return g, ptr, idx
+
+
+def feedback_csr(rows, cols, max_row):
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    ptr = np.empty(max_row + 2, dtype=np.int64)
+    out = np.empty(rows.size, dtype=np.int32)
+    nnz = lib().mo_feedback_csr(rows, cols, rows.size, max_row, ptr, out)
+    return ptr, out[:nnz].copy()
+
+
+def wrmf_optimize(row_ptr, cols, W, H, alpha=1.0, regularization=0.015, omp_threads=1):
+    """In-place ALS half-sweep on W (WRMF.cs:79-156)."""
+    assert W.dtype == np.float32 and H.dtype == np.float32
+    lib().mo_wrmf_optimize(np.ascontiguousarray(row_ptr, dtype=np.int64), np.ascontiguousarray(cols, dtype=np.int32),
+                           W.shape[0], W, H, H.shape[0], W.shape[1], float(alpha), float(regularization), int(omp_threads))
+
+
+def wrmf_gram(H):
+    k = H.shape[1]
+    out = np.empty((k, k), dtype=np.float64)
+    lib().mo_wrmf_gram(np.ascontiguousarray(H, dtype=np.float32), H.shape[0], k, out)
+    return out
+
+
+def recommend_mf(U, V, user, n=-1, candidates=None, ignore=None):
+    U = np.ascontiguousarray(U, dtype=np.float32)
+    V = np.ascontiguousarray(V, dtype=np.float32)
+    if candidates is None:
+        candidates = np.arange(V.shape[0], dtype=np.int32)
+    candidates = np.ascontiguousarray(candidates, dtype=np.int32)
+    ignore = np.ascontiguousarray(ignore if ignore is not None else [], dtype=np.int32)
+    oi = np.empty(max(candidates.size, 1), dtype=np.int32)
+    os_ = np.empty(max(candidates.size, 1), dtype=np.float32)
+    cnt = lib().mo_recommend_mf(U, V, U.shape[1], V.shape[0], U.shape[0], int(user), int(n), candidates, candidates.size,
+                                ignore, ignore.size, oi, os_)
+    return oi[:cnt].copy(), os_[:cnt].copy()
+
+
+def recommend_model(model, user, n=-1, candidates=None, ignore=None):
+    if candidates is None:
+        candidates = np.arange(model.max_item + 1, dtype=np.int32)
+    candidates = np.ascontiguousarray(candidates, dtype=np.int32)
+    ignore = np.ascontiguousarray(ignore if ignore is not None else [], dtype=np.int32)
+    oi = np.empty(max(candidates.size, 1), dtype=np.int32)
+    os_ = np.empty(max(candidates.size, 1), dtype=np.float32)
+    cnt = lib().mo_recommend_model(model.h, int(user), int(n), candidates, candidates.size, ignore, ignore.size, oi, os_)
+    return oi[:cnt].copy(), os_[:cnt].copy()
