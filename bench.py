@@ -1,0 +1,252 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: BiasedMatrixFactorization SGD epochs (ratings/s) on synthetic data of the shapes
+BASELINE.json names.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ml10m|netflix|...]
+
+A step is one Iterate() (one full SGD epoch over the resident training ratings). `value` is whole-job ratings/s
+with the ratings resident in HBM, timed with CUDA events on the library's stream; `e2e` is the same metric
+through the find-iter loop a MyMediaLite user runs (Iterate() + Evaluate(test) with HOST test arrays, section 3.2 of
+SURVEY.md), host<->device copies inside the timed region. `--impl reference` times the CPU restatement of the
+reference's own loops (oracle/, the C# original cannot run here: no Mono/.NET) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_users, n_items, n_ratings, levels, k, seed, description)
+    "ml10m": (71_500, 10_700, 10_000_000, "half", 64, 20260102,
+              "BiasedMatrixFactorization k=64 SGD, synthetic MovieLens-10M shape (71.5k x 10.7k, 10M ratings)"),
+    "netflix": (480_000, 17_800, 100_000_000, "int", 128, 20260104,
+                "BiasedMatrixFactorization k=128 DSGD, synthetic Netflix shape (480k x 17.8k, 100M ratings)"),
+    "tiny": (3_000, 800, 300_000, "half", 64, 7, "debug-sized"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle-reason samples during the timed region (profiling recipe's clocks line)."""
+
+    def __init__(self, gpu_index=0):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[c] for r in self.rows if len(r) >= 7 for c in range(4) if r[3 + c].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_data(name, rank=0, world=1):
+    from mymedialite_b200 import synthetic
+    nu, ni, n, levels, k, seed, desc = WORKLOADS[name]
+    cache = os.path.join("/tmp", "mmlb200_%s_%d_of_%d.npz" % (name, rank, world))
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return dict(train=(z["u"], z["i"], z["v"]), test=(z["tu"], z["ti"], z["tv"]), n_users=nu, n_items=ni), k, desc
+    # n ratings in the TRAINING set (the shape the metric is quoted on) + 10 % test ratings on top
+    d = synthetic.ratings(nu, ni, int(n / 0.9), levels, seed)
+    u, i, v = d["train"]
+    if u.size > n:
+        u, i, v = u[:n], i[:n], v[:n]
+    d["train"] = (u, i, v)
+    try:
+        np.savez(cache, u=u, i=i, v=v, tu=d["test"][0], ti=d["test"][1], tv=d["test"][2])
+    except Exception:
+        pass
+    return d, k, desc
+
+
+def run_ours(args):
+    from mymedialite_b200 import engine
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        raise SystemExit("multi-GPU DSGD ring is not wired into bench.py yet")
+    d, k, desc = make_data(args.workload)
+    u, i, v = d["train"]; tu, ti, tv = d["test"]
+    n = int(u.size)
+    ctx = engine.Context(local_rank)
+    t0 = time.time()
+    ratings = engine.DeviceRatings(ctx, u, i, v, max_user=d["n_users"] - 1, max_item=d["n_items"] - 1)
+    params = engine.default_params(biased=1, num_factors=k, num_groups=args.groups, num_subgroups=args.subgroups,
+                                   persistent=args.persistent)
+    model = engine.SgdModel(ctx, ratings, params)
+    model.init_model(1, 0.0, 0.1)
+    ctx.synchronize()
+    build_s = time.time() - t0
+    info = model.strata_info()
+    rs = np.random.RandomState(1)
+
+    def seq():
+        return rs.permutation(info["G"]).astype(np.int32)
+
+    for _ in range(args.warmup):
+        model.iterate(seq())
+    ctx.synchronize()
+    launches0, _ = model.stats()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # --- device-resident: K epochs, each timed by CUDA events on the library's stream, L2 flushed in between
+    ms = []
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        model.iterate(seq())
+        ms.append(model.stats()[1])
+    launches1, _ = model.stats()
+    dev_ms = float(np.sum(ms))
+    # --- end to end: the find-iter loop (Iterate + Evaluate on host test arrays), wall clock around synchronous calls
+    ctx.synchronize()
+    t0 = time.time()
+    rmse = None
+    for _ in range(args.steps):
+        model.iterate(seq())
+        rmse = model.evaluate(tu, ti, tv)["RMSE"]
+    e2e_s = time.time() - t0
+    sampler.stop_flag.set(); sampler.join()
+    train_rmse = model.evaluate_train()["RMSE"]
+
+    pk, pk_kind = peaks()
+    bytes_per_rating = 16 * k + 28
+    ms_per_step = dev_ms / args.steps
+    value = n * args.steps / (dev_ms * 1e-3)
+    achieved = bytes_per_rating * n / (ms_per_step * 1e-3) / 1e9
+    out = {
+        "metric": "BiasedMF SGD ratings/sec", "value": value, "unit": "ratings/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "n_ratings": n, "num_factors": k, "schedule": "DSGD G=%d W=%d%s" % (
+            info["G"], info["W"], " persistent" if params.persistent != 0 else ""),
+            "item_group_smem_bytes": info["staged_bytes"], "l2": "flushed between timed epochs (384 MB memset)",
+            "strata_build_s": round(build_s, 3)},
+        "e2e": {"value": n * args.steps / e2e_s, "unit": "ratings/s",
+                "h2d_bytes_per_step": int(12 * tu.size + 4 * info["G"]), "d2h_bytes_per_step": 16 + 8 * 4 * 1184,
+                "what": "Iterate() + Evaluate(test) per step through the C ABI with host test arrays"},
+        "gpu_launches": int(launches1 - launches0),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
+                     "bytes_per_rating": bytes_per_rating},
+        "clocks": sampler.summary(),
+        "rmse": {"train": train_rmse, "test": rmse, "epochs": args.warmup + 2 * args.steps},
+        "ms_each": [round(x, 3) for x in ms],
+    }
+    if not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(args, d, k, sample_only=True)
+    print(json.dumps(out))
+
+
+def cpu_baseline(args, d, k, sample_only):
+    """The oracle's restatement of BiasedMatrixFactorization.Iterate timed on this box's host cores:
+    single-threaded (MaxThreads=1) on a bounded prefix of the workload."""
+    from oracle import oracle as O
+    u, i, v = d["train"]
+    m = min(u.size, args.cpu_sample)
+    us, is_, vs = u[:m].copy(), i[:m].copy(), v[:m].copy()
+    om = O.Model(us, is_, vs, biased=True, num_factors=k, max_user=d["n_users"] - 1, max_item=d["n_items"] - 1)
+    rng = O.Random(1)
+    om.init(rng)
+    t0 = time.time()
+    om.iterate(rng)
+    dt = time.time() - t0
+    return {"value": m / dt, "unit": "ratings/s", "cores": 1, "kind": "port",
+            "sample": "one single-threaded epoch (MaxThreads=1 order) over the first %d ratings of the workload, "
+                      "C restatement of the reference loop (no Mono/.NET in this image)" % m,
+            "seconds": dt}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU algorithm (oracle port) with all host threads: DSGD blocks on
+    OpenMP threads as BiasedMatrixFactorization does with MaxThreads = cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    d, k, desc = make_data(args.workload)
+    u, i, v = d["train"]
+    cores = os.cpu_count() or 1
+    m = min(u.size, args.cpu_sample)
+    us, is_, vs = u[:m].copy(), i[:m].copy(), v[:m].copy()
+    om = O.Model(us, is_, vs, biased=True, num_factors=k, max_user=d["n_users"] - 1, max_item=d["n_items"] - 1,
+                 max_threads=cores, omp_threads=cores)
+    rng = O.Random(1)
+    om.init(rng)
+    for _ in range(args.warmup):
+        om.iterate(rng)
+    t0 = time.time()
+    for _ in range(args.steps):
+        om.iterate(rng)
+    dt = time.time() - t0
+    value = m * args.steps / dt
+    sample = ("%d-rating prefix of the workload per step, DSGD block schedule (MultiCore.cs:43-73) on %d OpenMP threads, "
+              "C restatement of the reference loop (no Mono/.NET in this image)" % (m, cores))
+    out = {
+        "impl": "reference", "metric": "BiasedMF SGD ratings/sec", "value": value, "unit": "ratings/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "n_ratings": int(m), "num_factors": k},
+        "cpu_baseline": {"value": value, "unit": "ratings/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "ratings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ml10m", choices=sorted(WORKLOADS))
+    ap.add_argument("--groups", type=int, default=0)
+    ap.add_argument("--subgroups", type=int, default=0)
+    ap.add_argument("--persistent", type=int, default=-1)
+    ap.add_argument("--cpu-sample", type=int, default=10_000_000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,164 @@
+/*
+ * mmlb200.h -- C ABI of libmmlb200.so, the B200-native matrix-factorization engine that the
+ * CUDA-backed MyMediaLite recommender classes (CudaBiasedMatrixFactorization,
+ * CudaMatrixFactorization, CudaWRMF) bind through P/Invoke.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only; every pointer argument is HOST memory owned by the caller
+ *     and is only read/written during the call (the library copies to/from the device);
+ *   - every function returns an int32 status (MML_OK = 0) and never throws;
+ *     mml_last_error() returns a thread-local message for the last failure;
+ *   - handles are library-owned, released by the matching *_destroy;
+ *   - there is NO CPU fallback: without a CUDA device mml_ctx_create fails with MML_ERR_CUDA.
+ *
+ * Each entry point cites the reference code (relative to src/MyMediaLite/ of
+ * jordansilva/MyMediaLite) whose work it takes over.
+ */
+#ifndef MMLB200_H
+#define MMLB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MML_OK            0
+#define MML_ERR_CUDA      1   /* CUDA runtime / launch failure (sticky for the context) */
+#define MML_ERR_ARG       2   /* invalid argument */
+#define MML_ERR_STATE     3   /* call order violated (e.g. iterate before a model exists) */
+#define MML_ERR_NCCL      4
+#define MML_ERR_UNSUPPORTED 5
+
+typedef struct mml_ctx     mml_ctx;      /* device, stream (and NCCL communicator when n_gpus > 1) */
+typedef struct mml_ratings mml_ratings;  /* COO rating set resident in HBM */
+typedef struct mml_sgd     mml_sgd;      /* MatrixFactorization / BiasedMatrixFactorization model */
+typedef struct mml_feedback mml_feedback;/* implicit feedback (CSR by user and by item) in HBM */
+typedef struct mml_wrmf    mml_wrmf;     /* WRMF model */
+
+const char* mml_last_error(void);
+/* Library build info: "mmlb200 <version> sm_100a". */
+const char* mml_version(void);
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* device_ids may be NULL (device 0..n_gpus-1). One context per process per GPU. */
+int32_t mml_ctx_create(int32_t n_gpus, const int32_t* device_ids, mml_ctx** out);
+int32_t mml_ctx_destroy(mml_ctx* ctx);
+int32_t mml_ctx_synchronize(mml_ctx* ctx);
+/* Benchmark hygiene: overwrites a 384 MB scratch buffer so the 126 MB L2 holds none of the model. */
+int32_t mml_ctx_flush_l2(mml_ctx* ctx);
+/* SM count of the device (used by hosts to pick the number of worker groups). */
+int32_t mml_ctx_sm_count(mml_ctx* ctx, int32_t* out);
+
+/* ---- rating matrix build -------------------------------------------------------------------- */
+/* Replaces StaticRatings/Ratings storage (Data/StaticRatings.cs:47-84, Data/Ratings.cs:150-190):
+ * uploads the COO triples, computes CountByUser/CountByItem (Data/DataSet.cs:134-169), Average
+ * (Data/Ratings.cs:76-84) and the rating scale min/max (Data/RatingScale.cs:104-117) on device. */
+int32_t mml_ratings_create(mml_ctx* ctx, const int32_t* users, const int32_t* items, const float* values,
+                           int64_t n, int32_t max_user, int32_t max_item, mml_ratings** out);
+int32_t mml_ratings_destroy(mml_ratings* r);
+/* CountByUser (by_item = 0) / CountByItem (by_item = 1): counts_out has max_id + 1 entries. */
+int32_t mml_ratings_counts(mml_ratings* r, int32_t by_item, int32_t* counts_out);
+/* ByUser / ByItem (Data/DataSet.cs:171-191) as CSR: row_ptr[max_id + 2], idx[n] holds rating
+ * indices in ascending order inside each row (bit-exact with the reference's forward pass). */
+int32_t mml_ratings_csr(mml_ratings* r, int32_t by_item, int64_t* row_ptr, int32_t* idx);
+/* Average, Scale.Min, Scale.Max. */
+int32_t mml_ratings_stats(mml_ratings* r, float* average, float* min_rating, float* max_rating);
+/* Applies the Fisher-Yates swap targets H (H[i] = random.Next(i+1), drawn for i = n-1..0 by the
+ * host's RNG) to perm in place: for i = n-1..0 swap(perm[i], perm[H[i]]) -- the permutation
+ * Utils.Shuffle (Utils.cs:52-64) produces for DataSet.RandomIndex (Data/DataSet.cs:193-202). */
+int32_t mml_shuffle_apply(mml_ctx* ctx, int32_t* perm, const int32_t* H, int64_t n);
+/* MultiCore.PartitionUsersAndItems (MultiCore.cs:43-73) without the per-block shuffle: block
+ * (user_perm[u] % g, item_perm[i] % g), rating indices ascending inside a block.
+ * block_ptr[g*g + 1] (row-major), idx[n]. */
+int32_t mml_partition_blocks(mml_ratings* r, const int32_t* user_perm, const int32_t* item_perm, int32_t g,
+                             int64_t* block_ptr, int32_t* idx);
+
+/* ---- MatrixFactorization / BiasedMatrixFactorization ------------------------------------------ */
+enum { MML_LOSS_RMSE = 0, MML_LOSS_MAE = 1, MML_LOSS_LOGISTIC = 2 };
+enum {
+    MML_SCHEDULE_SERIAL = 0,   /* MaxThreads = 1: one pass over RandomIndex in the reference's order */
+    MML_SCHEDULE_DSGD   = 1    /* stratified DSGD block schedule (BiasedMatrixFactorization.cs:205-215) */
+};
+enum {
+    MML_GROUPS_PERM_MOD = 0,   /* group = perm[id] % groups, the reference rule (MultiCore.cs:64) */
+    MML_GROUPS_BALANCED = 1    /* same stratification, ids dealt to groups balanced by rating count */
+};
+
+/* Hyper-parameters: names and defaults are those of the reference properties
+ * (MatrixFactorization.cs:87-96, BiasedMatrixFactorization.cs:85-141). */
+typedef struct mml_mf_params {
+    int32_t biased;               /* 1 = BiasedMatrixFactorization, 0 = MatrixFactorization */
+    int32_t num_factors;          /* NumFactors = 10 */
+    float   learn_rate;           /* LearnRate = 0.01 */
+    float   decay;                /* Decay = 1.0 */
+    float   regularization;       /* Regularization = 0.015 (plain MF) */
+    float   bias_learn_rate;      /* BiasLearnRate = 1.0 */
+    float   bias_reg;             /* BiasReg = 0.01 */
+    float   reg_u, reg_i;         /* RegU = RegI = Regularization */
+    int32_t frequency_regularization;
+    int32_t loss;                 /* MML_LOSS_* */
+    int32_t bold_driver;
+    int32_t max_threads;          /* MaxThreads: 1 = UpdateLearnRate once per Iterate(); > 1 = the reference's
+                                     multi-threaded semantics (learn rate updated twice per epoch, :216/:221) */
+    /* engine knobs (not reference options) */
+    int32_t schedule;             /* MML_SCHEDULE_* */
+    int32_t num_groups;           /* G: DSGD worker groups on this GPU (one CTA each); 0 = one per SM */
+    int32_t num_subgroups;        /* W: second-level groups inside a worker group (one warp each); 0 = auto */
+    int32_t group_rule;           /* MML_GROUPS_* */
+    int32_t persistent;           /* 1 = one cooperative launch per epoch with neighbour flags instead of
+                                     one launch per sub-epoch; 0 = per-sub-epoch launches; -1 = auto */
+} mml_mf_params;
+
+void mml_mf_params_default(mml_mf_params* p);
+
+/* Train() part 1 (BiasedMatrixFactorization.cs:173-190 / MatrixFactorization.cs:119-126): allocates
+ * the model for `ratings`, sets rating_range_size and global_bias, builds the DSGD strata when
+ * schedule = MML_SCHEDULE_DSGD. user_perm/item_perm (host, may be NULL = identity) are the
+ * permutations PartitionUsersAndItems would draw (MultiCore.cs:51-52). */
+int32_t mml_sgd_create(mml_ctx* ctx, mml_ratings* ratings, const mml_mf_params* p,
+                       const int32_t* user_perm, const int32_t* item_perm, mml_sgd** out);
+int32_t mml_sgd_destroy(mml_sgd* m);
+/* InitModel (MatrixFactorization.cs:99-116, BiasedMatrixFactorization.cs:161-170) with factors
+ * supplied by the host's RNG (user matrix first, then item matrix, row-major, num_factors columns).
+ * Rows of entities without ratings are zeroed; biases (may be NULL) default to zero;
+ * current_learnrate = LearnRate. */
+int32_t mml_sgd_set_model(mml_sgd* m, const float* user_factors, const float* item_factors,
+                          const float* user_bias, const float* item_bias);
+/* Same InitModel, factors drawn on device ~ N(mean, stddev) from a counter-based generator. */
+int32_t mml_sgd_init_model(mml_sgd* m, uint64_t seed, double init_mean, double init_stddev);
+/* Any output pointer may be NULL. */
+int32_t mml_sgd_get_model(mml_sgd* m, float* user_factors, float* item_factors,
+                          float* user_bias, float* item_bias, float* global_bias, float* current_learnrate);
+int32_t mml_sgd_set_learnrate(mml_sgd* m, float current_learnrate);
+/* Iterate() (BiasedMatrixFactorization.cs:197-222 / MatrixFactorization.cs:135-138): one epoch +
+ * UpdateLearnRate. DSGD schedule: subepoch_sequence (host, G entries, may be NULL = 0..G-1) is the
+ * shuffled sub-epoch order of :210-211. Serial schedule: random_index (host, n_index entries) is
+ * ratings.RandomIndex; it is uploaded once and cached until a different length is passed or
+ * mml_sgd_invalidate_index is called. */
+int32_t mml_sgd_iterate(mml_sgd* m, const int32_t* subepoch_sequence, const int32_t* random_index, int64_t n_index);
+int32_t mml_sgd_invalidate_index(mml_sgd* m);
+/* Iterate(IList<int>, bool, bool) (BiasedMatrixFactorization.cs:264-310, MatrixFactorization.cs:166-196)
+ * in the reference's exact order and mixed precision; no learn-rate update for the biased model,
+ * plain MF decays as the reference does (:195). */
+int32_t mml_sgd_iterate_indices(mml_sgd* m, const int32_t* indices, int64_t n, int32_t update_user, int32_t update_item);
+/* Predict (BiasedMatrixFactorization.cs:313-325 / MatrixFactorization.cs:251-259), batched. */
+int32_t mml_sgd_predict(mml_sgd* m, const int32_t* users, const int32_t* items, int64_t n, float* out);
+/* Eval.Ratings.Evaluate (Eval/Ratings.cs:96-139): out4 = {RMSE, MAE, NMAE, CBD}. */
+int32_t mml_sgd_evaluate(mml_sgd* m, const int32_t* users, const int32_t* items, const float* values, int64_t n, float* out4);
+/* Same on the training set already resident in HBM (ComputeFit, Eval/Ratings.cs:164-170). */
+int32_t mml_sgd_evaluate_train(mml_sgd* m, float* out4);
+/* ComputeObjective (BiasedMatrixFactorization.cs:515-552). */
+int32_t mml_sgd_objective(mml_sgd* m, double* out);
+/* Number of kernels this model launched so far and the device time of the last iterate (ms). */
+int32_t mml_sgd_stats(mml_sgd* m, int64_t* kernel_launches, float* last_iterate_ms);
+/* Strata shape: G, W, number of sub-blocks, staged item block bytes (0 = item rows stay in global memory). */
+int32_t mml_sgd_strata_info(mml_sgd* m, int32_t* G, int32_t* W, int64_t* n_subblocks, int64_t* staged_bytes);
+/* The serial-equivalent order of one DSGD epoch with the given sub-epoch sequence (NULL = 0..G-1):
+ * order[n] receives rating indices such that processing them one after the other gives the same
+ * model as the conflict-free parallel schedule (tests replay it through the oracle). */
+int32_t mml_sgd_schedule_dump(mml_sgd* m, const int32_t* subepoch_sequence, int32_t* order);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMLB200_H */

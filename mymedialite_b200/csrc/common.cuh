@@ -1,0 +1,99 @@
+// common.cuh -- shared declarations of libmmlb200 (sm_100a only; no CPU fallback anywhere).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <mutex>
+
+#include "../../include/mmlb200.h"
+
+namespace mml {
+
+// ---- error handling: every ABI entry point returns a status, never throws -----------------
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define MML_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            mml::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return MML_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define MML_CHECK(cond, code, ...)                                                             \
+    do {                                                                                       \
+        if (!(cond)) { mml::set_error(__VA_ARGS__); return (code); }                          \
+    } while (0)
+
+#define MML_TRY(expr)                                                                          \
+    do { int32_t _s = (expr); if (_s != MML_OK) return _s; } while (0)
+
+// ---- a device buffer that frees itself --------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    int32_t alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        MML_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+        n = count;
+        return MML_OK;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- primitives (prims.cu) ---------------------------------------------------------------------
+// counts[ids[t]]++ for t < n (counts must be zeroed by the caller)
+int32_t histogram_i32(const int32_t* ids, int64_t n, uint32_t* counts, cudaStream_t s);
+// out[i] = sum_{j<i} in[j]; out has n+1 entries (out[n] = total). in/out may not alias.
+int32_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, cudaStream_t s);
+// Stable LSD radix sort of (key,value) pairs on key bits [0, key_bits). Result ends in keys/vals
+// (ping-pong through keys_tmp/vals_tmp is handled inside; all four buffers hold n entries).
+int32_t radix_sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_tmp, uint32_t* vals_tmp,
+                         int64_t n, int key_bits, cudaStream_t s);
+// vals[i] = i
+int32_t iota_u32(uint32_t* vals, int64_t n, cudaStream_t s);
+// out[i] = src[idx[i]]
+int32_t gather_u32(const uint32_t* src, const uint32_t* idx, uint32_t* out, int64_t n, cudaStream_t s);
+int bits_for(uint32_t max_value);
+
+// ---- objects -----------------------------------------------------------------------------------
+struct Ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    int n_gpus = 1;
+    void* flush_buf = nullptr;   // mml_ctx_flush_l2
+    int flush_val = 0;
+};
+
+struct Ratings {
+    Ctx* ctx = nullptr;
+    int64_t n = 0;
+    int32_t max_user = -1, max_item = -1;
+    DevBuf<int32_t> users, items;
+    DevBuf<float> values;
+    DevBuf<uint32_t> count_by_user, count_by_item;
+    float average = 0.f, min_rating = 0.f, max_rating = 0.f;
+    int32_t n_users() const { return max_user + 1; }
+    int32_t n_items() const { return max_item + 1; }
+};
+
+Ratings* ratings_of(mml_ratings* h);
+Ctx* ctx_of(mml_ctx* h);
+
+}  // namespace mml

@@ -1,0 +1,201 @@
+"""Thin object layer over the C ABI (handle lifetimes, numpy marshalling). The recommender classes in
+recommenders.py -- the mirror of the reference's IRecommender surface -- are built on these."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import MFParams, check
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Context:
+    """One GPU (one process per GPU). Raises MmlError without a CUDA device: there is no CPU path."""
+
+    def __init__(self, device=0):
+        self.lib = _capi.load()
+        h = C.c_void_p()
+        dev = np.array([device], dtype=np.int32)
+        check(self.lib.mml_ctx_create(1, dev, C.byref(h)))
+        self.h = h
+
+    def sm_count(self):
+        v = C.c_int32()
+        check(self.lib.mml_ctx_sm_count(self.h, C.byref(v)))
+        return v.value
+
+    def flush_l2(self):
+        check(self.lib.mml_ctx_flush_l2(self.h))
+
+    def synchronize(self):
+        check(self.lib.mml_ctx_synchronize(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.mml_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceRatings:
+    """COO rating set resident in HBM (StaticRatings / DataSet of the reference)."""
+
+    def __init__(self, ctx, users, items, values, max_user=None, max_item=None):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        users, items, values = _i32(users), _i32(items), _f32(values)
+        self.n = int(users.shape[0])
+        self.max_user = int(users.max()) if max_user is None and self.n else (-1 if max_user is None else int(max_user))
+        self.max_item = int(items.max()) if max_item is None and self.n else (-1 if max_item is None else int(max_item))
+        h = C.c_void_p()
+        check(self.lib.mml_ratings_create(ctx.h, users, items, values, self.n, self.max_user, self.max_item, C.byref(h)))
+        self.h = h
+
+    def counts(self, by_item=False):
+        out = np.zeros((self.max_item if by_item else self.max_user) + 1, dtype=np.int32)
+        check(self.lib.mml_ratings_counts(self.h, 1 if by_item else 0, out))
+        return out
+
+    def csr(self, by_item=False):
+        rows = (self.max_item if by_item else self.max_user) + 1
+        ptr = np.zeros(rows + 1, dtype=np.int64)
+        idx = np.zeros(max(self.n, 1), dtype=np.int32)
+        check(self.lib.mml_ratings_csr(self.h, 1 if by_item else 0, ptr, idx))
+        return ptr, idx[:self.n]
+
+    def stats(self):
+        a, mn, mx = C.c_float(), C.c_float(), C.c_float()
+        check(self.lib.mml_ratings_stats(self.h, C.byref(a), C.byref(mn), C.byref(mx)))
+        return a.value, mn.value, mx.value
+
+    def partition_blocks(self, user_perm, item_perm, g):
+        ptr = np.zeros(g * g + 1, dtype=np.int64)
+        idx = np.zeros(max(self.n, 1), dtype=np.int32)
+        check(self.lib.mml_partition_blocks(self.h, _i32(user_perm), _i32(item_perm), int(g), ptr, idx))
+        return ptr, idx[:self.n]
+
+    def close(self):
+        if self.h:
+            self.lib.mml_ratings_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def default_params(**kw):
+    p = MFParams()
+    _capi.load().mml_mf_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError("mml_mf_params has no field %r" % k)
+        setattr(p, k, v)
+    return p
+
+
+class SgdModel:
+    """MatrixFactorization / BiasedMatrixFactorization state on the device."""
+
+    def __init__(self, ctx, ratings, params, user_perm=None, item_perm=None):
+        self.ctx, self.ratings, self.lib = ctx, ratings, ctx.lib
+        self.params = params
+        self.k = params.num_factors
+        h = C.c_void_p()
+        check(self.lib.mml_sgd_create(ctx.h, ratings.h, C.byref(params), _i32(user_perm), _i32(item_perm), C.byref(h)))
+        self.h = h
+        self.n_users, self.n_items = ratings.max_user + 1, ratings.max_item + 1
+
+    def set_model(self, U, V, bu=None, bi=None):
+        U, V = _f32(U), _f32(V)
+        assert U.shape == (self.n_users, self.k) and V.shape == (self.n_items, self.k)
+        check(self.lib.mml_sgd_set_model(self.h, U, V, _f32(bu), _f32(bi)))
+
+    def init_model(self, seed, mean=0.0, stddev=0.1):
+        check(self.lib.mml_sgd_init_model(self.h, int(seed), float(mean), float(stddev)))
+
+    def get_model(self, factors=True, biases=True):
+        U = np.zeros((self.n_users, self.k), np.float32) if factors else None
+        V = np.zeros((self.n_items, self.k), np.float32) if factors else None
+        bu = np.zeros(self.n_users, np.float32) if biases else None
+        bi = np.zeros(self.n_items, np.float32) if biases else None
+        gb, lr = C.c_float(), C.c_float()
+        check(self.lib.mml_sgd_get_model(self.h, U, V, bu, bi, C.byref(gb), C.byref(lr)))
+        return dict(U=U, V=V, bu=bu, bi=bi, global_bias=gb.value, learnrate=lr.value)
+
+    @property
+    def learnrate(self):
+        return self.get_model(False, False)["learnrate"]
+
+    def set_learnrate(self, lr):
+        check(self.lib.mml_sgd_set_learnrate(self.h, float(lr)))
+
+    def iterate(self, subepoch_sequence=None, random_index=None):
+        ri = _i32(random_index)
+        check(self.lib.mml_sgd_iterate(self.h, _i32(subepoch_sequence), ri, 0 if ri is None else ri.shape[0]))
+
+    def iterate_indices(self, indices, update_user=True, update_item=True):
+        idx = _i32(indices)
+        check(self.lib.mml_sgd_iterate_indices(self.h, idx, idx.shape[0], int(update_user), int(update_item)))
+
+    def predict(self, users, items):
+        users, items = _i32(users), _i32(items)
+        out = np.zeros(users.shape[0], np.float32)
+        check(self.lib.mml_sgd_predict(self.h, users, items, users.shape[0], out))
+        return out
+
+    def evaluate(self, users, items, values):
+        users, items, values = _i32(users), _i32(items), _f32(values)
+        out = np.zeros(4, np.float32)
+        check(self.lib.mml_sgd_evaluate(self.h, users, items, values, users.shape[0], out))
+        return dict(RMSE=float(out[0]), MAE=float(out[1]), NMAE=float(out[2]), CBD=float(out[3]))
+
+    def evaluate_train(self):
+        out = np.zeros(4, np.float32)
+        check(self.lib.mml_sgd_evaluate_train(self.h, out))
+        return dict(RMSE=float(out[0]), MAE=float(out[1]), NMAE=float(out[2]), CBD=float(out[3]))
+
+    def objective(self):
+        v = C.c_double()
+        check(self.lib.mml_sgd_objective(self.h, C.byref(v)))
+        return v.value
+
+    def stats(self):
+        n, ms = C.c_int64(), C.c_float()
+        check(self.lib.mml_sgd_stats(self.h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def strata_info(self):
+        G, W, ns, sb = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
+        check(self.lib.mml_sgd_strata_info(self.h, C.byref(G), C.byref(W), C.byref(ns), C.byref(sb)))
+        return dict(G=G.value, W=W.value, n_subblocks=ns.value, staged_bytes=sb.value)
+
+    def schedule(self, subepoch_sequence=None):
+        order = np.zeros(max(self.ratings.n, 1), np.int32)
+        check(self.lib.mml_sgd_schedule_dump(self.h, _i32(subepoch_sequence), order))
+        return order[:self.ratings.n]
+
+    def close(self):
+        if self.h:
+            self.lib.mml_sgd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,89 @@
+"""Deterministic synthetic data of the shapes BASELINE.json names.
+
+Planted model: rank-16 factors ~ N(0, 0.35^2), biases ~ N(0, 0.3^2), mu = 3.6, noise N(0, 0.5^2); user activity
+is log-normal, item popularity Zipf(0.8); (user, item) pairs are distinct; ids are dense (every user and item
+appears at least once when n is large enough). The same bytes feed the GPU engine and the CPU oracle."""
+import numpy as np
+
+SHAPES = {
+    # name: (n_users, n_items, n_ratings, levels, k, seed)
+    "ml10m": (71_500, 10_700, 10_000_000, "half", 64, 20260102),
+    "ml20m_implicit": (138_000, 27_000, 20_000_000, None, 128, 20260103),
+    "netflix": (480_000, 17_800, 100_000_000, "int", 128, 20260104),
+}
+
+
+def _pairs(rng, n_users, n_items, n):
+    act = rng.lognormal(0.0, 1.0, n_users)
+    pop = 1.0 / np.arange(1, n_items + 1) ** 0.8
+    pop = pop[rng.permutation(n_items)]
+    pop /= pop.sum()
+    cdf = np.cumsum(pop)
+    cdf[-1] = 1.0
+    users_out, items_out = [], []
+    have = 0
+    want = n
+    # guarantee every user and item once, then fill by the activity / popularity laws and de-duplicate
+    base_u = np.concatenate([np.arange(n_users, dtype=np.int64), rng.integers(0, n_users, n_items)])
+    base_i = np.concatenate([rng.integers(0, n_items, n_users), np.arange(n_items, dtype=np.int64)])
+    keys = np.unique(base_u * n_items + base_i)
+    while True:
+        need = want - keys.size
+        if need <= 0:
+            break
+        draw = int(need * 1.15) + 1024
+        cnt = rng.multinomial(draw, act / act.sum())
+        u = np.repeat(np.arange(n_users, dtype=np.int64), cnt)
+        i = np.searchsorted(cdf, rng.random(u.size), side="right").astype(np.int64)
+        np.minimum(i, n_items - 1, out=i)
+        keys = np.unique(np.concatenate([keys, u * n_items + i]))
+    if keys.size > want:
+        # drop random surplus pairs, never one of the "every id once" pairs' ids entirely: surplus is tiny (<15 %)
+        drop = rng.choice(keys.size, keys.size - want, replace=False)
+        mask = np.ones(keys.size, bool)
+        mask[drop] = False
+        keys = keys[mask]
+    perm = rng.permutation(keys.size)
+    keys = keys[perm]
+    return (keys // n_items).astype(np.int32), (keys % n_items).astype(np.int32)
+
+
+def ratings(n_users, n_items, n, levels="half", seed=1, test_fraction=0.1):
+    """Returns dict(train=(u, i, v), test=(u, i, v), n_users, n_items)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    u, i = _pairs(rng, n_users, n_items, n)
+    rank = 16
+    Pu = rng.normal(0, 0.35, (n_users, rank)).astype(np.float32)
+    Qi = rng.normal(0, 0.35, (n_items, rank)).astype(np.float32)
+    bu = rng.normal(0, 0.3, n_users).astype(np.float32)
+    bi = rng.normal(0, 0.3, n_items).astype(np.float32)
+    v = np.empty(u.size, np.float32)
+    step = 1 << 22
+    for s in range(0, u.size, step):
+        uu, ii = u[s:s + step], i[s:s + step]
+        v[s:s + step] = 3.6 + bu[uu] + bi[ii] + np.einsum("nk,nk->n", Pu[uu], Qi[ii]) + rng.normal(0, 0.5, uu.size)
+    if levels == "half":
+        v = np.clip(np.round(v * 2) / 2, 0.5, 5.0).astype(np.float32)
+    elif levels == "int":
+        v = np.clip(np.round(v), 1.0, 5.0).astype(np.float32)
+    # 90/10 split by a hash of (u, i, seed)
+    h = (u.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15) ^ i.astype(np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F)
+         ^ np.uint64(seed)) >> np.uint64(33)
+    is_test = (h % np.uint64(1000)) < np.uint64(int(test_fraction * 1000))
+    tr, te = ~is_test, is_test
+    return dict(train=(u[tr].copy(), i[tr].copy(), v[tr].copy()), test=(u[te].copy(), i[te].copy(), v[te].copy()),
+                n_users=n_users, n_items=n_items)
+
+
+def implicit(n_users, n_items, n, seed=1):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return _pairs(rng, n_users, n_items, n)
+
+
+def named(name, scale=1.0):
+    nu, ni, n, levels, k, seed = SHAPES[name]
+    if scale != 1.0:
+        nu, ni, n = max(int(nu * scale), 8), max(int(ni * scale), 8), max(int(n * scale * scale), 64)
+    if levels is None:
+        return implicit(nu, ni, n, seed), k
+    return ratings(nu, ni, n, levels, seed), k
