@@ -107,7 +107,8 @@ def run_ours(args):
     t0 = time.time()
     ratings = engine.DeviceRatings(ctx, u, i, v, max_user=d["n_users"] - 1, max_item=d["n_items"] - 1)
     params = engine.default_params(biased=1, num_factors=k, num_groups=args.groups, num_subgroups=args.subgroups,
-                                   persistent=args.persistent)
+                                   persistent=args.persistent, hot_item_factor=args.hot, hot_copies=args.copies, intra_block=args.intra,
+                                   hot_merge_average=args.hot_avg)
     model = engine.SgdModel(ctx, ratings, params)
     model.init_model(1, 0.0, 0.1)
     ctx.synchronize()
@@ -153,9 +154,9 @@ def run_ours(args):
         "metric": "BiasedMF SGD ratings/sec", "value": value, "unit": "ratings/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "n_ratings": n, "num_factors": k, "schedule": "DSGD G=%d W=%d%s" % (
-            info["G"], info["W"], " persistent" if params.persistent != 0 else ""),
-            "item_group_smem_bytes": info["staged_bytes"], "l2": "flushed between timed epochs (384 MB memset)",
+        "config": {"workload": desc, "n_ratings": n, "num_factors": k, "schedule": "DSGD G=%d W=%d %s%s" % (
+            info["G"], info["W"], "async" if args.intra else "rounds", " persistent" if params.persistent != 0 else ""),
+            "item_group_smem_bytes": info["staged_bytes"], "rounds": info["n_rounds"], "hot_items": model.hot_items(), "l2": "flushed between timed epochs (384 MB memset)",
             "strata_build_s": round(build_s, 3)},
         "e2e": {"value": n * args.steps / e2e_s, "unit": "ratings/s",
                 "h2d_bytes_per_step": int(12 * tu.size + 4 * info["G"]), "d2h_bytes_per_step": 16 + 8 * 4 * 1184,
@@ -239,6 +240,10 @@ def main():
     ap.add_argument("--groups", type=int, default=0)
     ap.add_argument("--subgroups", type=int, default=0)
     ap.add_argument("--persistent", type=int, default=-1)
+    ap.add_argument("--hot", type=float, default=1.0)
+    ap.add_argument("--copies", type=int, default=0)
+    ap.add_argument("--hot-avg", type=int, default=1)
+    ap.add_argument("--intra", type=int, default=1, help="0 = conflict-free rounds, 1 = async (default)")
     ap.add_argument("--cpu-sample", type=int, default=10_000_000)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -84,6 +84,13 @@ enum {
     MML_GROUPS_BALANCED = 1    /* same stratification, ids dealt to groups balanced by rating count */
 };
 
+enum {
+    MML_INTRA_ROUNDS = 0,      /* inside a block: rounds of mutually independent ratings (conflict-free, deterministic:
+                                  the epoch equals a serial pass in the order mml_sgd_schedule_dump reports) */
+    MML_INTRA_ASYNC  = 1       /* inside a block: user rows exclusive per worker, item rows updated without ordering
+                                  (lock-free, as the reference's NaiveParallelization, but confined to a block) */
+};
+
 /* Hyper-parameters: names and defaults are those of the reference properties
  * (MatrixFactorization.cs:87-96, BiasedMatrixFactorization.cs:85-141). */
 typedef struct mml_mf_params {
@@ -103,10 +110,19 @@ typedef struct mml_mf_params {
     /* engine knobs (not reference options) */
     int32_t schedule;             /* MML_SCHEDULE_* */
     int32_t num_groups;           /* G: DSGD worker groups on this GPU (one CTA each); 0 = one per SM */
-    int32_t num_subgroups;        /* W: second-level groups inside a worker group (one warp each); 0 = auto */
+    int32_t num_subgroups;        /* warps per worker group (a warp runs 32/L ratings of a round at once); 0 = 8 */
     int32_t group_rule;           /* MML_GROUPS_* */
     int32_t persistent;           /* 1 = one cooperative launch per epoch with neighbour flags instead of
                                      one launch per sub-epoch; 0 = per-sub-epoch launches; -1 = auto */
+    float   hot_item_factor;      /* an item whose ratings per block reach factor x (ratings per block / workers)
+                                     is "hot": inside a block its updates run on hot_copies private copies of the
+                                     row and the copies' deltas are summed at the end of the block (they would
+                                     otherwise form one serial chain); 0 = off, default 1.0 */
+    int32_t hot_copies;           /* private copies per hot item and block; 0 = 8 */
+    int32_t intra_block;          /* MML_INTRA_*; default MML_INTRA_ASYNC */
+    int32_t hot_merge_average;    /* hot-item copies are merged by averaging (1, default) or summing (0) their steps */
+    int32_t async_workers;        /* async mode: workers per worker group that take part; 0 = all, 1 = serial
+                                     inside a block (deterministic; used by the parity tests) */
 } mml_mf_params;
 
 void mml_mf_params_default(mml_mf_params* p);
@@ -151,12 +167,19 @@ int32_t mml_sgd_evaluate_train(mml_sgd* m, float* out4);
 int32_t mml_sgd_objective(mml_sgd* m, double* out);
 /* Number of kernels this model launched so far and the device time of the last iterate (ms). */
 int32_t mml_sgd_stats(mml_sgd* m, int64_t* kernel_launches, float* last_iterate_ms);
-/* Strata shape: G, W, number of sub-blocks, staged item block bytes (0 = item rows stay in global memory). */
-int32_t mml_sgd_strata_info(mml_sgd* m, int32_t* G, int32_t* W, int64_t* n_subblocks, int64_t* staged_bytes);
+/* Strata shape: G, warps per group, number of rounds, staged item block bytes (0 = item rows stay in global memory). */
+int32_t mml_sgd_strata_info(mml_sgd* m, int32_t* G, int32_t* W, int64_t* n_rounds, int64_t* staged_bytes);
+/* Strata shape: ..., number of hot items. */
+int32_t mml_sgd_hot_items(mml_sgd* m, int64_t* n_hot);
 /* The serial-equivalent order of one DSGD epoch with the given sub-epoch sequence (NULL = 0..G-1):
  * order[n] receives rating indices such that processing them one after the other gives the same
- * model as the conflict-free parallel schedule (tests replay it through the oracle). */
-int32_t mml_sgd_schedule_dump(mml_sgd* m, const int32_t* subepoch_sequence, int32_t* order);
+ * model as the conflict-free parallel schedule (tests replay it through the oracle).
+ * block[n] (may be NULL) = id of the (sub-epoch, worker group) block each entry belongs to;
+ * copy[n] (may be NULL) = -1 for ordinary items, else the private copy of the hot item's row the entry
+ * updates (copies start from the row at block start and their deltas are summed at block end);
+ * round[n] (may be NULL) = id of the round (set of mutually independent ratings) the entry runs in. */
+int32_t mml_sgd_schedule_dump(mml_sgd* m, const int32_t* subepoch_sequence, int32_t* order,
+                              int32_t* block, int32_t* copy, int32_t* round);
 
 #ifdef __cplusplus
 }

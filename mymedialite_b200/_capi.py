@@ -16,6 +16,7 @@ vp = C.c_void_p
 LOSS_RMSE, LOSS_MAE, LOSS_LOGISTIC = 0, 1, 2
 SCHEDULE_SERIAL, SCHEDULE_DSGD = 0, 1
 GROUPS_PERM_MOD, GROUPS_BALANCED = 0, 1
+INTRA_ROUNDS, INTRA_ASYNC = 0, 1
 
 
 class MmlError(RuntimeError):
@@ -33,7 +34,7 @@ class MFParams(C.Structure):
         ("reg_u", C.c_float), ("reg_i", C.c_float), ("frequency_regularization", C.c_int32),
         ("loss", C.c_int32), ("bold_driver", C.c_int32), ("max_threads", C.c_int32),
         ("schedule", C.c_int32), ("num_groups", C.c_int32), ("num_subgroups", C.c_int32),
-        ("group_rule", C.c_int32), ("persistent", C.c_int32),
+        ("group_rule", C.c_int32), ("persistent", C.c_int32), ("hot_item_factor", C.c_float), ("hot_copies", C.c_int32), ("intra_block", C.c_int32), ("hot_merge_average", C.c_int32), ("async_workers", C.c_int32),
     ]
 
 
@@ -88,7 +89,8 @@ SIGNATURES = {
     "mml_sgd_objective": (C.c_int32, [vp, C.POINTER(C.c_double)]),
     "mml_sgd_stats": (C.c_int32, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "mml_sgd_strata_info": (C.c_int32, [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
-    "mml_sgd_schedule_dump": (C.c_int32, [vp, oi32p, i32p]),
+    "mml_sgd_hot_items": (C.c_int32, [vp, C.POINTER(C.c_int64)]),
+    "mml_sgd_schedule_dump": (C.c_int32, [vp, oi32p, i32p, oi32p, oi32p, oi32p]),
 }
 
 _lib = None

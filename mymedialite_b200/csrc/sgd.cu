@@ -5,21 +5,28 @@
 // MultiCore.cs:43-73 (the user x item block stratification the DSGD schedule mirrors).
 //
 // Schedule. The reference's DSGD mode cuts the rating matrix into g x g blocks by
-// (user_perm[u] % g, item_perm[i] % g) and runs g sub-epochs of g mutually disjoint blocks. Here the
-// same stratification is applied at two levels on one GPU:
-//   level 1: G worker groups = CTAs.   CTA j owns user group j for the whole epoch; in sub-epoch
-//            ("slot") s it holds item group (s + j) mod G, staged in shared memory.
-//   level 2: W sub-groups  = warps.    Inside block (j, b) warp w owns user sub-group w; in step t
-//            it works on item sub-group (t + w) mod W; __syncthreads() separates the steps.
-// At any moment no two warps of the GPU touch the same user row or the same item row, so the
-// parallel epoch equals a serial pass over the ratings in the order (slot, step, j, w, entry) --
-// the order mml_sgd_schedule_dump returns and the tests replay through the CPU oracle.
+// (user_perm[u] % g, item_perm[i] % g) and runs g sub-epochs of g mutually disjoint blocks, one
+// thread per block. Here:
+//   level 1: G worker groups = CTAs (the reference's threads). CTA j owns user group j for the
+//            whole epoch; in sub-epoch ("slot") s it holds item group (s + j) mod G, staged in
+//            shared memory -- exactly the reference's block schedule with g = G.
+//   level 2: inside block (j, b), where the reference's thread walks the block serially, the CTA
+//            walks it in ROUNDS: a round is a set of ratings with pairwise distinct users and
+//            distinct item rows (a matching of the block's bipartite graph, found at build time
+//            by greedy edge colouring). The ratings of a round are independent, so the CTA's
+//            workers (sub-warps of L lanes, one rating each) take them in parallel;
+//            __syncthreads() separates rounds.
+// No two workers of the GPU ever touch the same user row or item row at the same time, so the
+// parallel epoch equals a serial pass over the ratings in the order (slot, block, round, entry)
+// -- the order mml_sgd_schedule_dump returns and the tests replay through the CPU oracle.
+// Hot items (an item with d ratings in a block forces d rounds) get `hot_copies` private copies of
+// their row per block; the copies' deltas are summed when the block ends (see sgd_block).
 //
 // Data layout in HBM. Factor rows are renumbered group-major (all rows of one group are contiguous)
-// and padded with zeros to kp = 32 * kpl floats, so a warp moves a row with one 128-bit (64/32-bit)
-// access per lane and an item group is one contiguous region (bulk-copied to shared memory).
-// Ratings are stored as entries (internal user row, internal item row, value) sorted by the
-// consumption order above; sub_ptr[] delimits the (j, slot, w, step) sub-blocks.
+// and padded with zeros to kp floats (32, 64, 128 or 256), so a worker moves a row with 128-bit
+// accesses and an item group is one contiguous region. Ratings are stored as entries (internal
+// user row, item row inside the staged group image, value) sorted by (block, round);
+// round_ptr[] delimits the rounds and blk_round_ptr[] the rounds of each block.
 #include "sgd.cuh"
 #include <algorithm>
 #include <cmath>
@@ -35,50 +42,98 @@ namespace mml {
 // Deals ids to n_blocks * G * W groups and numbers them group-major.
 //   level 0 (GPU block)  : perm[id] % R          (the reference rule, MultiCore.cs:64)
 //   level 1/2, PERM_MOD  : (perm[id] / R) % (G*W) -> g = x % G, w = x / G
-//   level 1/2, BALANCED  : ids of a block sorted by rating count (desc) and dealt boustrophedon
+//   level 1/2, BALANCED  : ids of a block in descending rating count, each to the lightest group so far
+// Hot ids (items only, hot_min > 0): an id with at least hot_min ratings would serialise its whole
+// group (its updates form one dependence chain), so it gets no sub-group: it belongs to CTA-level
+// group g only and every warp works on a private copy of its row (see sgd_block). At most
+// MAX_HOT per CTA-level group; hot rows are numbered first inside their group.
+constexpr int32_t HOT_BIT = 1 << 30;
+constexpr int32_t MAX_HOT = 8;
+
 static void build_group_map(GroupMap& m, int32_t n_ext, const uint32_t* counts, const int32_t* perm,
-                            int32_t R, int32_t only_block /* -1 = all blocks */, int32_t G, int32_t W, int32_t rule)
+                            int32_t R, int32_t only_block /* -1 = all blocks */, int32_t G, int32_t W, int32_t rule,
+                            int64_t hot_min, std::vector<int32_t>* hot_cnt /* [n_blocks * G] or NULL */)
 {
     m.n_ext = n_ext;
     m.n_blocks = only_block >= 0 ? 1 : R;
     const int32_t T = G * W;
     m.grp.assign(n_ext, -1);
+    if (hot_cnt) hot_cnt->assign((size_t)m.n_blocks * G, 0);
     std::vector<std::vector<int32_t>> by_block(m.n_blocks);
     for (int32_t id = 0; id < n_ext; id++) {
         const int32_t pid = perm ? perm[id] : id;
         const int32_t blk = pid % R;
         if (only_block >= 0 && blk != only_block) continue;
-        const int32_t bi = only_block >= 0 ? 0 : blk;
+        by_block[only_block >= 0 ? 0 : blk].push_back(id);
+    }
+    for (int32_t bi = 0; bi < m.n_blocks; bi++) {
+        auto& ids = by_block[bi];
         if (rule == MML_GROUPS_PERM_MOD) {
-            const int32_t x = (pid / R) % T;
-            m.grp[id] = (bi * G + (x % G)) * W + (x / G);
-        } else {
-            by_block[bi].push_back(id);
-        }
-    }
-    if (rule != MML_GROUPS_PERM_MOD) {
-        for (int32_t bi = 0; bi < m.n_blocks; bi++) {
-            auto& ids = by_block[bi];
-            std::stable_sort(ids.begin(), ids.end(), [&](int32_t a, int32_t b) { return counts[a] > counts[b]; });
-            for (size_t pos = 0; pos < ids.size(); pos++) {
-                const size_t round = pos / T, r = pos % T;
-                const int32_t x = (int32_t)((round & 1) ? (T - 1 - r) : r);
-                m.grp[ids[pos]] = (bi * G + (x % G)) * W + (x / G);
+            for (int32_t id : ids) {
+                const int32_t pid = perm ? perm[id] : id;
+                const int32_t x = (pid / R) % T, g = x % G;
+                if (hot_cnt && hot_min > 0 && (int64_t)counts[id] >= hot_min && (*hot_cnt)[(size_t)bi * G + g] < MAX_HOT) {
+                    (*hot_cnt)[(size_t)bi * G + g]++;
+                    m.grp[id] = ((bi * G + g) * W) | HOT_BIT;
+                } else {
+                    m.grp[id] = (bi * G + g) * W + (x / G);
+                }
             }
+            continue;
+        }
+        std::stable_sort(ids.begin(), ids.end(), [&](int32_t a, int32_t b) { return counts[a] > counts[b]; });
+        // loads: per CTA-level group and per packed group; a min-heap of packed groups by (load, index)
+        std::vector<int64_t> gload(G, 0), load(T, 0);
+        size_t pos = 0;
+        if (hot_cnt && hot_min > 0) {
+            // hot ids, heaviest first, each to the lightest CTA-level group that still has a hot slot
+            for (; pos < ids.size() && (int64_t)counts[ids[pos]] >= hot_min; pos++) {
+                int32_t best = -1;
+                for (int32_t g = 0; g < G; g++)
+                    if ((*hot_cnt)[(size_t)bi * G + g] < MAX_HOT && (best < 0 || gload[g] < gload[best])) best = g;
+                if (best < 0) break;
+                (*hot_cnt)[(size_t)bi * G + best]++;
+                gload[best] += counts[ids[pos]];
+                m.grp[ids[pos]] = ((bi * G + best) * W) | HOT_BIT;
+            }
+            for (int32_t x = 0; x < T; x++) load[x] = gload[x % G] / W;
+        }
+        std::vector<std::pair<int64_t, int32_t>> heap(T);
+        for (int32_t x = 0; x < T; x++) heap[x] = std::make_pair(load[x], x);
+        auto cmp = [](const std::pair<int64_t, int32_t>& a, const std::pair<int64_t, int32_t>& b) { return a > b; };
+        std::make_heap(heap.begin(), heap.end(), cmp);
+        for (; pos < ids.size(); pos++) {
+            std::pop_heap(heap.begin(), heap.end(), cmp);
+            auto& top = heap.back();
+            const int32_t x = top.second;
+            m.grp[ids[pos]] = (bi * G + (x % G)) * W + (x / G);
+            top.first += std::max<uint32_t>(counts[ids[pos]], 1u);   // ids without ratings still spread evenly
+            std::push_heap(heap.begin(), heap.end(), cmp);
         }
     }
-    // group-major numbering (counting sort, ascending id inside a group)
+    // group-major numbering (counting sort, ascending id inside a group); hot rows first in their CTA group
     const int32_t n_grp = m.n_blocks * T;
     m.grp_ptr.assign((size_t)n_grp + 1, 0);
-    for (int32_t id = 0; id < n_ext; id++) if (m.grp[id] >= 0) m.grp_ptr[m.grp[id] + 1]++;
+    auto slot_of = [&](int32_t g) { return (g & HOT_BIT) ? (g & ~HOT_BIT) : g; };   // hot rows share slot (bi*G+g)*W
+    // two keys per id: (packed slot, hot first). Count hot separately so they precede the cold rows of sub-group 0.
+    std::vector<int32_t> n_hot_in((size_t)m.n_blocks * G, 0);
+    for (int32_t id = 0; id < n_ext; id++) {
+        const int32_t g = m.grp[id];
+        if (g < 0) continue;
+        m.grp_ptr[slot_of(g) + 1]++;
+        if (g & HOT_BIT) n_hot_in[slot_of(g) / W]++;
+    }
     for (int32_t g = 0; g < n_grp; g++) m.grp_ptr[g + 1] += m.grp_ptr[g];
     m.n_int = m.grp_ptr[n_grp];
     m.to_int.assign(n_ext, -1);
     m.to_ext.assign(std::max(m.n_int, 1), 0);
-    std::vector<int32_t> cursor(m.grp_ptr.begin(), m.grp_ptr.end() - 1);
+    std::vector<int32_t> cur_hot((size_t)m.n_blocks * G), cur_cold(n_grp);
+    for (int32_t g = 0; g < n_grp; g++) cur_cold[g] = m.grp_ptr[g] + ((g % W) == 0 ? n_hot_in[g / W] : 0);
+    for (int32_t cg = 0; cg < m.n_blocks * G; cg++) cur_hot[cg] = m.grp_ptr[(size_t)cg * W];
     for (int32_t id = 0; id < n_ext; id++) {
-        if (m.grp[id] < 0) continue;
-        const int32_t r = cursor[m.grp[id]]++;
+        const int32_t g = m.grp[id];
+        if (g < 0) continue;
+        const int32_t r = (g & HOT_BIT) ? cur_hot[slot_of(g) / W]++ : cur_cold[g]++;
         m.to_int[id] = r;
         m.to_ext[r] = id;
     }
@@ -105,75 +160,298 @@ static inline int grid_n(int64_t n, int threads = 256)
     return (int)std::min<int64_t>(std::max<int64_t>(ceil_div(n, threads), 1), 148 * 16);
 }
 
-// key = ((((B*G + j)*G + slot)*W + w)*W + step ; bad[0] counts ratings whose user/item is not mapped
-__global__ void strata_key_kernel(const int32_t* __restrict__ users, const int32_t* __restrict__ items, int64_t n,
-                                  const int32_t* __restrict__ user_grp, const int32_t* __restrict__ item_grp,
-                                  int32_t G, int32_t W, uint32_t* __restrict__ key, uint32_t* __restrict__ bad)
+__device__ __forceinline__ uint32_t mix32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+// blk = (B*G + j)*G + slot ; bad[0] counts ratings whose user/item is not mapped to this rank
+__global__ void strata_block_kernel(const int32_t* __restrict__ users, const int32_t* __restrict__ items, int64_t n,
+                                    const int32_t* __restrict__ user_grp, const int32_t* __restrict__ item_grp,
+                                    int32_t G, uint32_t* __restrict__ key, uint32_t* __restrict__ bad)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; t < n; t += stride) {
-        const int32_t ug = user_grp[users[t]], ig = item_grp[items[t]];
-        if (ug < 0 || ig < 0) { atomicAdd(bad, 1u); key[t] = 0; continue; }
-        const int32_t j = ug / W, w = ug % W;
-        const int32_t Bb = ig / W, c = ig % W;
-        const int32_t B = Bb / G, b = Bb % G;
+        const int32_t j = user_grp[users[t]];
+        int32_t ig = item_grp[items[t]];
+        if (j < 0 || ig < 0) { atomicAdd(bad, 1u); key[t] = 0; continue; }
+        ig &= ~HOT_BIT;
+        const int32_t B = ig / G, b = ig % G;
         int32_t slot = b - j; if (slot < 0) slot += G;
-        int32_t step = c - w; if (step < 0) step += W;
-        key[t] = (uint32_t)((((B * G + j) * G + slot) * W + w) * W + step);
+        key[t] = (uint32_t)((B * G + j) * G + slot);
     }
 }
 
+// Per entry (in block order): user row local to its group, item row inside the staged image of its group
+// (cold items and copy 0 of hot items: internal row - first row of the group; copy c >= 1 of hot item x:
+// n_it + x * (C - 1) + (c - 1)), value, source index, copy.
 __global__ void strata_entries_kernel(const uint32_t* __restrict__ order, const int32_t* __restrict__ users,
                                       const int32_t* __restrict__ items, const float* __restrict__ values, int64_t n,
                                       const int32_t* __restrict__ user_int, const int32_t* __restrict__ item_int,
-                                      int32_t* __restrict__ ent_u, int32_t* __restrict__ ent_i,
-                                      float* __restrict__ ent_v, int32_t* __restrict__ ent_idx)
+                                      const int32_t* __restrict__ item_grp, const int32_t* __restrict__ item_ptr,
+                                      int32_t C, int32_t* __restrict__ ent_u, int32_t* __restrict__ ent_i,
+                                      float* __restrict__ ent_v, int32_t* __restrict__ ent_idx, int8_t* __restrict__ ent_copy)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; t < n; t += stride) {
         const uint32_t src = order[t];
-        ent_u[t] = user_int[users[src]];
-        ent_i[t] = item_int[items[src]];
+        const int32_t u = users[src], it = items[src];
+        const int32_t ig = item_grp[it];
+        const int32_t Bb = ig & ~HOT_BIT;
+        const int32_t i_lo = item_ptr[Bb], n_it = item_ptr[Bb + 1] - i_lo;
+        int32_t row = item_int[it] - i_lo;
+        int8_t copy = -1;
+        if (ig & HOT_BIT) {
+            const int32_t c = (int32_t)(mix32(src) % (uint32_t)C);
+            copy = (int8_t)c;
+            if (c > 0) row = n_it + row * (C - 1) + (c - 1);
+        }
+        ent_u[t] = user_int[u];
+        ent_i[t] = row;
         ent_v[t] = values[src];
         ent_idx[t] = (int32_t)src;
+        ent_copy[t] = copy;
     }
 }
 
-static int32_t build_strata(Sgd& m)
+// Greedy edge colouring, one thread per block: entry e gets the smallest round not yet used by its user or its
+// item row inside this block (128-bit masks per node in `scratch`); entries beyond 128 rounds go to rounds of
+// their own. Rounds are therefore matchings: no user and no item row appears twice in a round.
+constexpr int COLOR_BITS = 12;
+__global__ void strata_color_kernel(const uint32_t* __restrict__ blk_ptr, int32_t n_blk, int32_t G,
+                                    const int32_t* __restrict__ ent_u, const int32_t* __restrict__ ent_i,
+                                    const int32_t* __restrict__ user_ptr, int32_t nu_max, int32_t nr_max,
+                                    unsigned long long* __restrict__ scratch, uint32_t* __restrict__ color,
+                                    uint32_t* __restrict__ overflow_flag)
+{
+    const int32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk >= n_blk) return;
+    const int32_t j = (blk / G) % G;
+    const int32_t u_lo = user_ptr[j];
+    unsigned long long* mu = scratch + (size_t)blk * (size_t)(nu_max + nr_max) * 2;
+    unsigned long long* mi = mu + (size_t)nu_max * 2;
+    uint32_t extra = 128;
+    for (uint32_t e = blk_ptr[blk]; e < blk_ptr[blk + 1]; e++) {
+        const int32_t u = ent_u[e] - u_lo, r = ent_i[e];
+        const unsigned long long lo = mu[2 * u] | mi[2 * r];
+        uint32_t c;
+        if (~lo) {
+            c = (uint32_t)__ffsll((long long)~lo) - 1u;
+            mu[2 * u] |= 1ull << c; mi[2 * r] |= 1ull << c;
+        } else {
+            const unsigned long long hi = mu[2 * u + 1] | mi[2 * r + 1];
+            if (~hi) {
+                const uint32_t b = (uint32_t)__ffsll((long long)~hi) - 1u;
+                c = 64u + b;
+                mu[2 * u + 1] |= 1ull << b; mi[2 * r + 1] |= 1ull << b;
+            } else {
+                c = extra++;
+            }
+        }
+        if (c >= (1u << COLOR_BITS)) { atomicExch(overflow_flag, 1u); c = (1u << COLOR_BITS) - 1u; }
+        color[e] = c;
+    }
+}
+
+__global__ void strata_key2_kernel(const uint32_t* __restrict__ blk_sorted, const uint32_t* __restrict__ color, int64_t n,
+                                   uint32_t* __restrict__ key2)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) key2[t] = (blk_sorted[t] << COLOR_BITS) | color[t];
+}
+
+// head[t] = 1 where a new round starts; rounds_in_blk[blk]++ for every head
+__global__ void strata_heads_kernel(const uint32_t* __restrict__ key2, int64_t n, uint32_t* __restrict__ head,
+                                    uint32_t* __restrict__ rounds_in_blk)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) {
+        const bool h = t == 0 || key2[t] != key2[t - 1];
+        head[t] = h ? 1u : 0u;
+        if (h) atomicAdd(&rounds_in_blk[key2[t] >> COLOR_BITS], 1u);
+    }
+}
+
+__global__ void strata_round_ptr_kernel(const uint32_t* __restrict__ head, const uint32_t* __restrict__ round_id, int64_t n,
+                                        uint32_t n_rounds, uint32_t* __restrict__ round_ptr)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) if (head[t]) round_ptr[round_id[t]] = (uint32_t)t;
+    if (blockIdx.x == 0 && threadIdx.x == 0) round_ptr[n_rounds] = (uint32_t)n;
+}
+
+__global__ void gather_entries_kernel(const uint32_t* __restrict__ perm, int64_t n,
+                                      const int32_t* __restrict__ u0, const int32_t* __restrict__ i0, const float* __restrict__ v0,
+                                      const int32_t* __restrict__ x0, const int8_t* __restrict__ c0,
+                                      int32_t* __restrict__ u1, int32_t* __restrict__ i1, float* __restrict__ v1,
+                                      int32_t* __restrict__ x1, int8_t* __restrict__ c1)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) {
+        const uint32_t s = perm[t];
+        u1[t] = u0[s]; i1[t] = i0[s]; v1[t] = v0[s]; x1[t] = x0[s]; c1[t] = c0[s];
+    }
+}
+
+// Async mode: worker w of the CTA gets the w-th of n_workers equal slices of the block's entries (sorted by
+// user), cut at user boundaries so that every user row of the block belongs to exactly one worker.
+__global__ void strata_split_kernel(const uint32_t* __restrict__ blk_ptr, int32_t n_blk, int32_t n_workers,
+                                    const int32_t* __restrict__ ent_u, uint32_t* __restrict__ wptr)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n_blk * (n_workers + 1)) return;
+    const int32_t blk = (int32_t)(t / (n_workers + 1)), w = (int32_t)(t % (n_workers + 1));
+    const uint32_t beg = blk_ptr[blk], end = blk_ptr[blk + 1];
+    uint32_t cut = beg + (uint32_t)(((uint64_t)(end - beg) * (uint64_t)w) / (uint64_t)n_workers);
+    if (w == n_workers) cut = end;
+    while (cut > beg && cut < end && ent_u[cut] == ent_u[cut - 1]) cut++;
+    wptr[t] = cut;
+}
+
+__global__ void gather_key_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, int64_t n, uint32_t* __restrict__ out)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) out[t] = src[idx[t]];
+}
+
+__global__ void user_key_kernel(const int32_t* __restrict__ users, const int32_t* __restrict__ user_int, int64_t n, uint32_t* __restrict__ key)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) { const int32_t r = user_int[users[t]]; key[t] = r < 0 ? 0u : (uint32_t)r; }
+}
+
+static int32_t build_strata_async(Sgd& m, int32_t n_workers)
 {
     Ratings& r = *m.ratings;
     cudaStream_t s = m.ctx->stream;
     const int64_t n = r.n;
-    m.n_sub = (int64_t)m.R * m.G * m.G * m.W * m.W;
-    MML_CHECK(m.n_sub < ((int64_t)1 << 31), MML_ERR_ARG, "strata: %lld sub-blocks is too many (G=%d W=%d)",
-              (long long)m.n_sub, m.G, m.W);
-    DevBuf<uint32_t> key, vals, ktmp, vtmp, cnt, bad;
-    MML_TRY(key.alloc(n)); MML_TRY(vals.alloc(n)); MML_TRY(ktmp.alloc(n)); MML_TRY(vtmp.alloc(n));
-    MML_TRY(cnt.alloc(m.n_sub)); MML_TRY(bad.alloc(1));
+    const int64_t n_blk64 = (int64_t)m.R * m.G * m.G;
+    MML_CHECK(n_blk64 * (n_workers + 1) < ((int64_t)1 << 31), MML_ERR_ARG, "strata: %lld blocks is too many (G=%d)", (long long)n_blk64, m.G);
+    const int32_t n_blk = (int32_t)n_blk64;
+    m.n_blk = n_blk;
+    m.n_workers = n_workers;
+    DevBuf<uint32_t> blk, key, vals, ktmp, vtmp, cnt, bad, blk_ptr;
+    MML_TRY(blk.alloc(n)); MML_TRY(key.alloc(n)); MML_TRY(vals.alloc(n)); MML_TRY(ktmp.alloc(n)); MML_TRY(vtmp.alloc(n));
+    MML_TRY(cnt.alloc(n_blk)); MML_TRY(bad.alloc(1)); MML_TRY(blk_ptr.alloc((size_t)n_blk + 1));
     MML_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(uint32_t), s));
     MML_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), s));
-    strata_key_kernel<<<grid_n(n), 256, 0, s>>>(r.users.p, r.items.p, n, m.users.d_grp.p, m.items.d_grp.p,
-                                                m.G, m.W, key.p, bad.p);
+    strata_block_kernel<<<grid_n(n), 256, 0, s>>>(r.users.p, r.items.p, n, m.users.d_grp.p, m.items.d_grp.p, m.G, blk.p, bad.p);
     MML_CUDA(cudaGetLastError());
     uint32_t h_bad = 0;
     MML_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     MML_CUDA(cudaStreamSynchronize(s));
     MML_CHECK(h_bad == 0, MML_ERR_ARG,
               "strata: %u ratings belong to users of another GPU block (pass each rank the ratings of its own users)", h_bad);
-    MML_TRY(histogram_i32((const int32_t*)key.p, n, cnt.p, s));
-    MML_TRY(m.sub_ptr.alloc((size_t)m.n_sub + 1));
-    MML_TRY(exclusive_scan_u32(cnt.p, m.sub_ptr.p, m.n_sub, s));
+    MML_TRY(histogram_i32((const int32_t*)blk.p, n, cnt.p, s));
+    MML_TRY(exclusive_scan_u32(cnt.p, blk_ptr.p, n_blk, s));
+    // order by (block, user row, rating index): stable LSD over the user key, then over the block key
+    user_key_kernel<<<grid_n(n), 256, 0, s>>>(r.users.p, m.users.d_to_int.p, n, key.p);
+    MML_CUDA(cudaGetLastError());
     MML_TRY(iota_u32(vals.p, n, s));
-    MML_TRY(radix_sort_pairs(key.p, vals.p, ktmp.p, vtmp.p, n, bits_for((uint32_t)(m.n_sub - 1)), s));
+    MML_TRY(radix_sort_pairs(key.p, vals.p, ktmp.p, vtmp.p, n, bits_for((uint32_t)std::max(m.users.n_int - 1, 1)), s));
+    gather_key_kernel<<<grid_n(n), 256, 0, s>>>(blk.p, vals.p, n, key.p);
+    MML_CUDA(cudaGetLastError());
+    MML_TRY(radix_sort_pairs(key.p, vals.p, ktmp.p, vtmp.p, n, bits_for((uint32_t)std::max(n_blk - 1, 1)), s));
     MML_TRY(m.ent_u.alloc(n)); MML_TRY(m.ent_i.alloc(n)); MML_TRY(m.ent_v.alloc(n)); MML_TRY(m.ent_idx.alloc(n));
+    MML_TRY(m.ent_copy.alloc(n));
     strata_entries_kernel<<<grid_n(n), 256, 0, s>>>(vals.p, r.users.p, r.items.p, r.values.p, n,
-                                                    m.users.d_to_int.p, m.items.d_to_int.p,
-                                                    m.ent_u.p, m.ent_i.p, m.ent_v.p, m.ent_idx.p);
+                                                    m.users.d_to_int.p, m.items.d_to_int.p, m.items.d_grp.p, m.d_item_ptr.p,
+                                                    1, m.ent_u.p, m.ent_i.p, m.ent_v.p, m.ent_idx.p, m.ent_copy.p);
+    MML_CUDA(cudaGetLastError());
+    MML_TRY(m.wptr.alloc((size_t)n_blk * (n_workers + 1)));
+    const int64_t nt = (int64_t)n_blk * (n_workers + 1);
+    strata_split_kernel<<<(unsigned)ceil_div(nt, 256), 256, 0, s>>>(blk_ptr.p, n_blk, n_workers, m.ent_u.p, m.wptr.p);
     MML_CUDA(cudaGetLastError());
     MML_CUDA(cudaStreamSynchronize(s));
-    m.launches += 8;
+    m.launches += 14;
+    return MML_OK;
+}
+
+static int32_t build_strata(Sgd& m, int32_t nu_max, int32_t nr_max)
+{
+    Ratings& r = *m.ratings;
+    cudaStream_t s = m.ctx->stream;
+    const int64_t n = r.n;
+    const int64_t n_blk64 = (int64_t)m.R * m.G * m.G;
+    MML_CHECK(n_blk64 < ((int64_t)1 << (32 - COLOR_BITS)), MML_ERR_ARG, "strata: %lld blocks is too many (G=%d)", (long long)n_blk64, m.G);
+    const int32_t n_blk = (int32_t)n_blk64;
+    m.n_blk = n_blk;
+    DevBuf<uint32_t> key, vals, ktmp, vtmp, cnt, bad, color;
+    MML_TRY(key.alloc(n)); MML_TRY(vals.alloc(n)); MML_TRY(ktmp.alloc(n)); MML_TRY(vtmp.alloc(n));
+    MML_TRY(cnt.alloc(n_blk)); MML_TRY(bad.alloc(2)); MML_TRY(color.alloc(n));
+    MML_CUDA(cudaMemsetAsync(bad.p, 0, 2 * sizeof(uint32_t), s));
+    MML_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), s));
+    // 1. entries in block order (stable: ascending rating index inside a block)
+    strata_block_kernel<<<grid_n(n), 256, 0, s>>>(r.users.p, r.items.p, n, m.users.d_grp.p, m.items.d_grp.p, m.G, key.p, bad.p);
+    MML_CUDA(cudaGetLastError());
+    uint32_t h_bad[2] = {0, 0};
+    MML_CUDA(cudaMemcpyAsync(h_bad, bad.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    MML_CUDA(cudaStreamSynchronize(s));
+    MML_CHECK(h_bad[0] == 0, MML_ERR_ARG,
+              "strata: %u ratings belong to users of another GPU block (pass each rank the ratings of its own users)", h_bad[0]);
+    DevBuf<uint32_t> blk_ptr;
+    MML_TRY(blk_ptr.alloc((size_t)n_blk + 1));
+    MML_TRY(histogram_i32((const int32_t*)key.p, n, cnt.p, s));
+    MML_TRY(exclusive_scan_u32(cnt.p, blk_ptr.p, n_blk, s));
+    MML_TRY(iota_u32(vals.p, n, s));
+    MML_TRY(radix_sort_pairs(key.p, vals.p, ktmp.p, vtmp.p, n, bits_for((uint32_t)std::max(n_blk - 1, 1)), s));
+    DevBuf<int32_t> u0, i0, x0; DevBuf<float> v0; DevBuf<int8_t> c0;
+    MML_TRY(u0.alloc(n)); MML_TRY(i0.alloc(n)); MML_TRY(x0.alloc(n)); MML_TRY(v0.alloc(n)); MML_TRY(c0.alloc(n));
+    strata_entries_kernel<<<grid_n(n), 256, 0, s>>>(vals.p, r.users.p, r.items.p, r.values.p, n,
+                                                    m.users.d_to_int.p, m.items.d_to_int.p, m.items.d_grp.p, m.d_item_ptr.p,
+                                                    m.hot_copies, u0.p, i0.p, v0.p, x0.p, c0.p);
+    MML_CUDA(cudaGetLastError());
+    // 2. rounds: greedy edge colouring per block
+    {
+        DevBuf<unsigned long long> scratch;
+        const size_t words = (size_t)n_blk * (size_t)(nu_max + nr_max) * 2;
+        MML_TRY(scratch.alloc(words));
+        MML_CUDA(cudaMemsetAsync(scratch.p, 0, scratch.bytes(), s));
+        strata_color_kernel<<<(unsigned)ceil_div(n_blk, 64), 64, 0, s>>>(blk_ptr.p, n_blk, m.G, u0.p, i0.p, m.d_user_ptr.p,
+                                                                          nu_max, nr_max, scratch.p, color.p, bad.p + 1);
+        MML_CUDA(cudaGetLastError());
+        MML_CUDA(cudaMemcpyAsync(h_bad + 1, bad.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaStreamSynchronize(s));
+        MML_CHECK(h_bad[1] == 0, MML_ERR_UNSUPPORTED, "strata: a block needs more than %d rounds (one user or item dominates it); use more groups", 1 << COLOR_BITS);
+    }
+    // 3. entries in (block, round) order; key currently holds the sorted block ids
+    strata_key2_kernel<<<grid_n(n), 256, 0, s>>>(key.p, color.p, n, ktmp.p);
+    MML_CUDA(cudaGetLastError());
+    MML_CUDA(cudaMemcpyAsync(key.p, ktmp.p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    MML_TRY(iota_u32(vals.p, n, s));
+    MML_TRY(radix_sort_pairs(key.p, vals.p, ktmp.p, vtmp.p, n, bits_for((uint32_t)std::max(n_blk - 1, 1)) + COLOR_BITS, s));
+    MML_TRY(m.ent_u.alloc(n)); MML_TRY(m.ent_i.alloc(n)); MML_TRY(m.ent_v.alloc(n)); MML_TRY(m.ent_idx.alloc(n));
+    MML_TRY(m.ent_copy.alloc(n));
+    gather_entries_kernel<<<grid_n(n), 256, 0, s>>>(vals.p, n, u0.p, i0.p, v0.p, x0.p, c0.p,
+                                                    m.ent_u.p, m.ent_i.p, m.ent_v.p, m.ent_idx.p, m.ent_copy.p);
+    MML_CUDA(cudaGetLastError());
+    // 4. round boundaries
+    DevBuf<uint32_t> head, round_id, rounds_in_blk;
+    MML_TRY(head.alloc(n)); MML_TRY(round_id.alloc((size_t)n + 1)); MML_TRY(rounds_in_blk.alloc(n_blk));
+    MML_CUDA(cudaMemsetAsync(rounds_in_blk.p, 0, rounds_in_blk.bytes(), s));
+    strata_heads_kernel<<<grid_n(n), 256, 0, s>>>(key.p, n, head.p, rounds_in_blk.p);
+    MML_CUDA(cudaGetLastError());
+    MML_TRY(exclusive_scan_u32(head.p, round_id.p, n, s));
+    uint32_t n_rounds = 0;
+    MML_CUDA(cudaMemcpyAsync(&n_rounds, round_id.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    MML_CUDA(cudaStreamSynchronize(s));
+    m.n_rounds = n_rounds;
+    MML_TRY(m.round_ptr.alloc((size_t)n_rounds + 1));
+    strata_round_ptr_kernel<<<grid_n(n), 256, 0, s>>>(head.p, round_id.p, n, n_rounds, m.round_ptr.p);
+    MML_CUDA(cudaGetLastError());
+    MML_TRY(m.blk_round_ptr.alloc((size_t)n_blk + 1));
+    MML_TRY(exclusive_scan_u32(rounds_in_blk.p, m.blk_round_ptr.p, n_blk, s));
+    MML_CUDA(cudaStreamSynchronize(s));
+    m.launches += 16;
     return MML_OK;
 }
 
@@ -183,66 +461,74 @@ static int32_t build_strata(Sgd& m)
 struct SgdArgs {
     float* P; float* Q; float* bu; float* bi;
     const int32_t* ent_u; const int32_t* ent_i; const float* ent_v;
-    const uint32_t* sub_ptr;      // offset to the GPU-level item block B
-    const int32_t* item_ptr;      // offset to B: [G + 1] internal item row range per item group
+    const uint32_t* wptr;           // async mode, offset to B: [G*G][n_workers + 1] worker slices of each block
+    const uint32_t* round_ptr;      // [n_rounds + 1]
+    const uint32_t* blk_round_ptr;  // offset to the GPU-level item block B: [G*G + 1]
+    const int32_t* item_ptr;        // offset to B: [G + 1] internal item row range per item group
+    const int32_t* hot_cnt;         // offset to B: [G] hot items per item group (their rows come first)
     const float* regw_u; const float* regw_i;   // frequency regularisation weights or NULL
-    uint32_t* flags;              // persistent kernel: progress counter per CTA
-    const int32_t* seq;           // persistent kernel: sub-epoch sequence [G] (device)
+    uint32_t* flags;                // persistent kernel: progress counter per CTA
+    const int32_t* seq;             // persistent kernel: sub-epoch sequence [G] (device)
     uint32_t epoch_base;
-    int32_t G, W;
+    int32_t G, C;                   // worker groups, copies per hot item
+    int32_t n_workers;              // async mode: workers per CTA the slices were cut for
+    float hot_scale;                // merge of hot-item copies: 1 = sum of the chains' steps, 1/C = average
     float lr, gb, minr, range, reg_u, reg_i, blr, breg;
     int32_t loss;
 };
 
-// A factor row as seen by one lane: kpl floats, 128-bit accesses where the row is long enough.
-template <int KPL> struct Row;
-template <> struct Row<1> {
-    static __device__ __forceinline__ void load(float (&r)[1], const float* row, int lane) { r[0] = row[lane]; }
-    static __device__ __forceinline__ void store(const float (&r)[1], float* row, int lane) { row[lane] = r[0]; }
-};
-template <> struct Row<2> {
-    static __device__ __forceinline__ void load(float (&r)[2], const float* row, int lane)
-    { const float2 v = reinterpret_cast<const float2*>(row)[lane]; r[0] = v.x; r[1] = v.y; }
-    static __device__ __forceinline__ void store(const float (&r)[2], float* row, int lane)
-    { reinterpret_cast<float2*>(row)[lane] = make_float2(r[0], r[1]); }
-};
-template <> struct Row<4> {
-    static __device__ __forceinline__ void load(float (&r)[4], const float* row, int lane)
-    { const float4 v = reinterpret_cast<const float4*>(row)[lane]; r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w; }
-    static __device__ __forceinline__ void store(const float (&r)[4], float* row, int lane)
-    { reinterpret_cast<float4*>(row)[lane] = make_float4(r[0], r[1], r[2], r[3]); }
-};
-template <> struct Row<8> {
-    static __device__ __forceinline__ void load(float (&r)[8], const float* row, int lane)
+// A factor row as seen by one lane of an L-lane worker: KPL = kp / L floats as KPL/4 128-bit pieces;
+// piece v of lane sl is float4 number v*L + sl of the row (consecutive lanes -> consecutive 16 bytes).
+template <int L, int KPL>
+struct Row {
+    static_assert(KPL % 4 == 0, "rows move in 128-bit pieces");
+    static __device__ __forceinline__ void load(float (&r)[KPL], const float* row, int sl)
     {
-        const float4 a = reinterpret_cast<const float4*>(row)[lane];
-        const float4 b = reinterpret_cast<const float4*>(row)[32 + lane];
-        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+#pragma unroll
+        for (int v = 0; v < KPL / 4; v++) {
+            const float4 x = reinterpret_cast<const float4*>(row)[v * L + sl];
+            r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+        }
     }
-    static __device__ __forceinline__ void store(const float (&r)[8], float* row, int lane)
+    static __device__ __forceinline__ void store(const float (&r)[KPL], float* row, int sl)
     {
-        reinterpret_cast<float4*>(row)[lane] = make_float4(r[0], r[1], r[2], r[3]);
-        reinterpret_cast<float4*>(row)[32 + lane] = make_float4(r[4], r[5], r[6], r[7]);
+#pragma unroll
+        for (int v = 0; v < KPL / 4; v++)
+            reinterpret_cast<float4*>(row)[v * L + sl] = make_float4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+    }
+    // L1-bypassing load (rows other SMs or the L2 atomic unit modify)
+    static __device__ __forceinline__ void load_cg(float (&r)[KPL], const float* row, int sl)
+    {
+#pragma unroll
+        for (int v = 0; v < KPL / 4; v++) {
+            float4 x;
+            asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                         : "l"(reinterpret_cast<const float4*>(row) + (v * L + sl)) : "memory");
+            r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+        }
     }
 };
 
-__device__ __forceinline__ float warp_sum(float v)
+template <int L>
+__device__ __forceinline__ float worker_sum(float v)
 {
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    for (int d = L / 2; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
     return v;
 }
 
+__device__ __forceinline__ float warp_sum(float v) { return worker_sum<32>(v); }
+
 // BiasedMatrixFactorization.cs:264-310 (BIASED) / MatrixFactorization.cs:166-196 for one rating, fp32.
 // p and q are updated from their pre-update values; the biases before the factors.
-template <int KPL, bool BIASED>
+template <int L, int KPL, bool BIASED>
 __device__ __forceinline__ void sgd_update(const SgdArgs& a, float (&p)[KPL], float (&q)[KPL],
                                            float& bu, float& bi, float v, float regu, float regi)
 {
     float dot = 0.f;
 #pragma unroll
     for (int f = 0; f < KPL; f++) dot = fmaf(p[f], q[f], dot);
-    dot = warp_sum(dot);
+    dot = worker_sum<L>(dot);
     float gc;
     if (BIASED) {
         const float score = ((a.gb + bu) + bi) + dot;
@@ -291,93 +577,284 @@ __device__ __forceinline__ float ld_cg_f(const float* p)
     return v;
 }
 
-// Work of CTA j on block (j, b): stage item group b, W conflict-free steps, write the group back.
-// STAGE = item group lives in shared memory while the CTA holds it; otherwise item rows are
-// updated in global memory (groups too large for shared memory, e.g. very small G).
-template <int KPL, bool BIASED, bool STAGE>
+// Stage item group rows [i_lo, i_lo + n_it) (+ biases) into shared memory; hot items (the first n_hot rows)
+// additionally get copies 1..C-1 at rows n_it + x*(C-1) + (c-1) and a snapshot at rows n_it + n_hot*(C-1) + x.
+// Lock words (async mode) are cleared. Ends with a barrier.
+template <int KP, bool BIASED>
+__device__ __forceinline__ void stage_group(const SgdArgs& a, int i_lo, int n_it, int n_hot, int C,
+                                            float* sQ, float* sB, unsigned* sLock)
+{
+    const float4* src = reinterpret_cast<const float4*>(a.Q + (size_t)i_lo * KP);
+    float4* dst = reinterpret_cast<float4*>(sQ);
+    const int n4 = n_it * (KP / 4);
+    for (int t = threadIdx.x; t < n4; t += blockDim.x) dst[t] = ld_cg_f4(src + t);
+    if (BIASED) for (int t = threadIdx.x; t < n_it; t += blockDim.x) sB[t] = ld_cg_f(a.bi + i_lo + t);
+    if (sLock) for (int t = threadIdx.x; t < n_it + n_hot * C; t += blockDim.x) sLock[t] = 0u;
+    if (n_hot > 0) {
+        __syncthreads();
+        constexpr int per = KP / 4;
+        for (int t = threadIdx.x; t < n_hot * C * per; t += blockDim.x) {
+            const int x = t / (C * per), c = (t / per) % C, f = t % per;
+            const int row = (c < C - 1) ? (n_it + x * (C - 1) + c) : (n_it + n_hot * (C - 1) + x);
+            dst[(size_t)row * per + f] = dst[(size_t)x * per + f];
+        }
+        if (BIASED) for (int t = threadIdx.x; t < n_hot * C; t += blockDim.x) {
+            const int x = t / C, c = t % C;
+            const int row = (c < C - 1) ? (n_it + x * (C - 1) + c) : (n_it + n_hot * (C - 1) + x);
+            sB[row] = sB[x];
+        }
+    }
+    __syncthreads();
+}
+
+// Merge the hot items' copies (row = old + scale * sum_c (copy_c - old), copy 0 being the row itself; scale = 1
+// sums the chains' steps, scale = 1/C averages them) and write the group back. Call after a barrier.
+template <int KP, bool BIASED>
+__device__ __forceinline__ void unstage_group(const SgdArgs& a, int i_lo, int n_it, int n_hot, int C,
+                                              float* sQ, float* sB)
+{
+    if (n_hot > 0) {
+        const int old0 = n_it + n_hot * (C - 1);
+        const float scale = a.hot_scale;
+        for (int t = threadIdx.x; t < n_hot * KP; t += blockDim.x) {
+            const int x = t / KP, f = t % KP;
+            const float old = sQ[(size_t)(old0 + x) * KP + f];
+            float acc = sQ[(size_t)x * KP + f] - old;
+            for (int c = 1; c < C; c++) acc += sQ[(size_t)(n_it + x * (C - 1) + (c - 1)) * KP + f] - old;
+            sQ[(size_t)x * KP + f] = old + scale * acc;
+        }
+        if (BIASED) for (int x = threadIdx.x; x < n_hot; x += blockDim.x) {
+            const float old = sB[old0 + x];
+            float acc = sB[x] - old;
+            for (int c = 1; c < C; c++) acc += sB[n_it + x * (C - 1) + (c - 1)] - old;
+            sB[x] = old + scale * acc;
+        }
+        __syncthreads();
+    }
+    float4* dst = reinterpret_cast<float4*>(a.Q + (size_t)i_lo * KP);
+    const float4* src = reinterpret_cast<const float4*>(sQ);
+    const int n4 = n_it * (KP / 4);
+    for (int t = threadIdx.x; t < n4; t += blockDim.x) dst[t] = src[t];
+    if (BIASED) for (int t = threadIdx.x; t < n_it; t += blockDim.x) a.bi[i_lo + t] = sB[t];
+}
+
+// Work of CTA j on block (j, b): stage item group b, walk the block's rounds, write the group back.
+//
+// Shared-memory image of the item group (STAGE): rows [0, n_it) are the group's item rows (hot items
+// first); rows [n_it, n_it + h*(C-1)) are private copies 1..C-1 of the h hot items (copy 0 is the row
+// itself); rows [n_it + h*(C-1), n_it + h*C) keep the hot rows as they were at block start. Each copy is
+// a separate node for the round colouring, so a hot item's updates in this block run as C independent
+// chains, merged at the end: row = copy0 + sum_{c>=1} (copy_c - old). The item biases mirror the rows in sB.
+// Without STAGE (item group too large for shared memory) item rows are updated in global memory
+// and there are no hot items.
+//
+// A worker is L consecutive lanes (kp = L * KPL): 32 / L ratings per warp instruction.
+template <int L, int KPL, bool BIASED, bool STAGE>
 __device__ __forceinline__ void sgd_block(const SgdArgs& a, const int j, const int slot, float* smem)
 {
-    constexpr int KP = 32 * KPL;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    constexpr int KP = L * KPL;
+    constexpr int WPW = 32 / L;                        // workers per warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sl = lane % L;                           // lane inside the worker
+    const int wid = warp * WPW + lane / L;             // worker inside the CTA
+    const int n_workers = (blockDim.x >> 5) * WPW;
+    const int C = a.C;
     int b = slot + j; if (b >= a.G) b -= a.G;
     const int i_lo = a.item_ptr[b], i_hi = a.item_ptr[b + 1];
     const int n_it = i_hi - i_lo;
+    const int n_hot = STAGE ? a.hot_cnt[b] : 0;
+    const int n_rows = n_it + n_hot * C;
     float* sQ = smem;
-    float* sB = smem + (size_t)n_it * KP;
-    if (STAGE) {
-        const float4* src = reinterpret_cast<const float4*>(a.Q + (size_t)i_lo * KP);
-        float4* dst = reinterpret_cast<float4*>(sQ);
-        const int n4 = n_it * (KP / 4);
-        for (int t = threadIdx.x; t < n4; t += blockDim.x) dst[t] = ld_cg_f4(src + t);
-        if (BIASED) for (int t = threadIdx.x; t < n_it; t += blockDim.x) sB[t] = ld_cg_f(a.bi + i_lo + t);
-        __syncthreads();
-    }
-    const uint32_t* sp = a.sub_ptr + ((size_t)(j * a.G + slot) * a.W + w) * a.W;
+    float* sB = smem + (size_t)n_rows * KP;
+    const uint32_t r0 = a.blk_round_ptr[j * a.G + slot], r1 = a.blk_round_ptr[j * a.G + slot + 1];
+    if (STAGE) stage_group<KP, BIASED>(a, i_lo, n_it, n_hot, C, sQ, sB, nullptr);
 
-    int cur_u = -1;
-    float p[KPL];
-    float bu_v = 0.f, regu = a.reg_u;
-    for (int step = 0; step < a.W; step++) {
-        const uint32_t beg = sp[step], end = sp[step + 1];
-        for (uint32_t base = beg; base < end; base += 32) {
-            const int cnt = min(32u, end - base);
-            int mu = 0, mi = 0; float mv = 0.f;
-            if (lane < cnt) { mu = a.ent_u[base + lane]; mi = a.ent_i[base + lane]; mv = a.ent_v[base + lane]; }
-            for (int e = 0; e < cnt; e++) {
-                const int u = __shfl_sync(0xffffffffu, mu, e);
-                const int i = __shfl_sync(0xffffffffu, mi, e);
-                const float v = __shfl_sync(0xffffffffu, mv, e);
-                if (u != cur_u) {   // warp-uniform; the user row is owned by this warp for the whole block
-                    if (cur_u >= 0) {
-                        Row<KPL>::store(p, a.P + (size_t)cur_u * KP, lane);
-                        if (BIASED && lane == 0) a.bu[cur_u] = bu_v;
-                    }
-                    Row<KPL>::load(p, a.P + (size_t)u * KP, lane);
-                    if (BIASED) bu_v = a.bu[u];
-                    if (a.regw_u) regu = a.regw_u[u];
-                    cur_u = u;
-                }
-                float* qrow = STAGE ? (sQ + (size_t)(i - i_lo) * KP) : (a.Q + (size_t)i * KP);
-                float* bip = STAGE ? (sB + (i - i_lo)) : (a.bi + i);
-                float q[KPL];
-                Row<KPL>::load(q, qrow, lane);
-                float bi_v = BIASED ? *bip : 0.f;
-                const float regi = a.regw_i ? a.regw_i[i] : a.reg_i;
-                sgd_update<KPL, BIASED>(a, p, q, bu_v, bi_v, v, regu, regi);
-                Row<KPL>::store(q, qrow, lane);
-                if (BIASED && lane == 0) *bip = bi_v;
-                __syncwarp();
+    // round boundaries 32 at a time: lane l holds round_ptr[rbase + l]
+    uint32_t rbase = r0;
+    uint32_t my_ptr = (rbase + lane <= r1) ? a.round_ptr[rbase + lane] : 0u;
+    // entry of this worker for the first sub-round of the next round, fetched one round ahead
+    int nu = 0, ni = 0; float nv = 0.f;
+    if (r0 < r1) {
+        const uint32_t e = __shfl_sync(0xffffffffu, my_ptr, 0) + (uint32_t)wid;
+        const uint32_t eb = __shfl_sync(0xffffffffu, my_ptr, 1);
+        if (e < eb) { nu = a.ent_u[e]; ni = a.ent_i[e]; nv = a.ent_v[e]; }
+    }
+    for (uint32_t r = r0; r < r1; r++) {
+        int ridx = (int)(r - rbase);
+        if (ridx == 31) {   // slot 31 holds this round's start; reload so that both bounds are in registers
+            rbase = r; ridx = 0;
+            my_ptr = (rbase + lane <= r1) ? a.round_ptr[rbase + lane] : 0u;
+        }
+        const uint32_t ea = __shfl_sync(0xffffffffu, my_ptr, ridx);
+        const uint32_t eb = __shfl_sync(0xffffffffu, my_ptr, ridx + 1);
+        int cu = nu, ci = ni; float cv = nv;
+        if (r + 1 < r1) {   // next round's first entry (read-only data: safe before the barrier)
+            const uint32_t en_b = (ridx + 2 <= 31) ? __shfl_sync(0xffffffffu, my_ptr, ridx + 2) : a.round_ptr[r + 2];
+            const uint32_t en = eb + (uint32_t)wid;
+            if (en < en_b) { nu = a.ent_u[en]; ni = a.ent_i[en]; nv = a.ent_v[en]; }
+        }
+        // sub-rounds: the warp iterates while its first worker still has an entry
+        for (uint32_t e0 = ea + (uint32_t)(warp * WPW); e0 < eb; e0 += (uint32_t)n_workers) {
+            const uint32_t e = e0 + (uint32_t)(lane / L);
+            const bool active = e < eb;
+            if (e0 != ea + (uint32_t)(warp * WPW)) {   // later sub-rounds fetch their entry here
+                if (active) { cu = a.ent_u[e]; ci = a.ent_i[e]; cv = a.ent_v[e]; }
+            }
+            float p[KPL], q[KPL];
+            float bu_v = 0.f, bi_v = 0.f, regu = a.reg_u, regi = a.reg_i;
+            float* prow = a.P + (size_t)(active ? cu : 0) * KP;
+            float* qrow = STAGE ? (sQ + (size_t)(active ? ci : 0) * KP) : (a.Q + (size_t)(i_lo + (active ? ci : 0)) * KP);
+            float* bip = STAGE ? (sB + (active ? ci : 0)) : (a.bi + i_lo + (active ? ci : 0));
+            Row<L, KPL>::load(p, prow, sl);
+            Row<L, KPL>::load(q, qrow, sl);
+            if (BIASED) { bu_v = a.bu[active ? cu : 0]; bi_v = *bip; }
+            if (a.regw_u) {
+                regu = a.regw_u[active ? cu : 0];
+                const int it = active ? ci : 0;
+                regi = a.regw_i[i_lo + (it < n_it ? it : (it - n_it) / (C - 1))];
+            }
+            sgd_update<L, KPL, BIASED>(a, p, q, bu_v, bi_v, cv, regu, regi);
+            if (active) {
+                Row<L, KPL>::store(p, prow, sl);
+                Row<L, KPL>::store(q, qrow, sl);
+                if (BIASED && sl == 0) { a.bu[cu] = bu_v; *bip = bi_v; }
             }
         }
         __syncthreads();
     }
-    if (cur_u >= 0) {
-        Row<KPL>::store(p, a.P + (size_t)cur_u * KP, lane);
-        if (BIASED && lane == 0) a.bu[cur_u] = bu_v;
+    // the last __syncthreads() above (or the staging barrier, for an empty block) ordered all shared-memory updates
+    if (STAGE) unstage_group<KP, BIASED>(a, i_lo, n_it, n_hot, C, sQ, sB);
+}
+
+__device__ __forceinline__ void red_add_f4(float* p, float x, float y, float z, float w)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void red_add_f(float* p, float x)
+{
+    asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(x) : "memory");
+}
+
+// Async mode of block (j, b): the block's entries are sorted by user and cut into one slice per worker (whole
+// user runs), so user rows stay exclusive to a worker -- kept in registers across a user's run, the next
+// user's row fetched while the current rating is computed. Item rows stay in global memory (they are
+// L2-resident: n_items * kp * 4 bytes is a few MB): a worker reads the row (L1 bypassed, one rating ahead),
+// takes the gradient, and applies its step  q += lr * (g * p - reg * q)  as a vector atomic add executed by
+// the L2 (red.global.add.v4.f32). Steps of different workers on the same item row are therefore all applied,
+// in some order, none lost -- only the gradient may have been taken at a q that is a few updates old, as in
+// the reference's lock-free NaiveParallelization mode (BiasedMatrixFactorization.cs:136-141, :201-204), but
+// confined to a block: blocks of a sub-epoch stay disjoint as in the reference's DSGD mode. A popular item's
+// chain of updates is serialised by the L2 atomic unit, not by the SM. No barriers inside the block.
+template <int L, int KPL, bool BIASED>
+__device__ __forceinline__ void sgd_block_async(const SgdArgs& a, const int j, const int slot)
+{
+    constexpr int KP = L * KPL;
+    constexpr int WPW = 32 / L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sl = lane % L;
+    const int wid = warp * WPW + lane / L;
+    const int n_workers = a.n_workers;                 // <= workers in the CTA; the rest idle (1 = serial, for tests)
+    int b = slot + j; if (b >= a.G) b -= a.G;
+    const int i_lo = a.item_ptr[b];
+    float* Qg = a.Q + (size_t)i_lo * KP;
+    float* Bg = a.bi + i_lo;
+    const uint32_t* wp = a.wptr + (size_t)(j * a.G + slot) * (n_workers + 1) + min(wid, n_workers - 1);
+    const uint32_t e0 = wid < n_workers ? wp[0] : 0u, e1 = wid < n_workers ? wp[1] : 0u;
+    // entries two ahead, user row and item row one ahead
+    int u1 = 0, i1 = 0, u2 = 0, i2 = 0; float v1 = 0.f, v2 = 0.f;
+    if (e0 < e1) { u1 = a.ent_u[e0]; i1 = a.ent_i[e0]; v1 = a.ent_v[e0]; }
+    if (e0 + 1 < e1) { u2 = a.ent_u[e0 + 1]; i2 = a.ent_i[e0 + 1]; v2 = a.ent_v[e0 + 1]; }
+    float p[KPL], pn[KPL], qn[KPL];
+    float bu_v = 0.f, bun = 0.f, bin = 0.f, regu = a.reg_u, regun = a.reg_u;
+#pragma unroll
+    for (int f = 0; f < KPL; f++) { p[f] = 0.f; pn[f] = 0.f; qn[f] = 0.f; }
+    if (e0 < e1) {
+        Row<L, KPL>::load(pn, a.P + (size_t)u1 * KP, sl);
+        Row<L, KPL>::load_cg(qn, Qg + (size_t)i1 * KP, sl);
+        if (BIASED) { bun = a.bu[u1]; bin = ld_cg_f(Bg + i1); }
+        if (a.regw_u) regun = a.regw_u[u1];
     }
-    if (STAGE) {
-        // the last __syncthreads() above made every warp's shared-memory updates visible
-        float4* dst = reinterpret_cast<float4*>(a.Q + (size_t)i_lo * KP);
-        const float4* src = reinterpret_cast<const float4*>(sQ);
-        const int n4 = n_it * (KP / 4);
-        for (int t = threadIdx.x; t < n4; t += blockDim.x) dst[t] = src[t];
-        if (BIASED) for (int t = threadIdx.x; t < n_it; t += blockDim.x) a.bi[i_lo + t] = sB[t];
+    // the warp iterates until its longest worker is done
+    uint32_t len = e1 - e0;
+#pragma unroll
+    for (int d = L; d < 32; d <<= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, d));
+    int cur_u = -1;
+    for (uint32_t t = 0; t < len; t++) {
+        const uint32_t e = e0 + t;
+        const bool active = e < e1;
+        const int u = u1, i = i1; const float v = v1;
+        u1 = u2; i1 = i2; v1 = v2;
+        if (e + 2 < e1) { u2 = a.ent_u[e + 2]; i2 = a.ent_i[e + 2]; v2 = a.ent_v[e + 2]; }
+        if (active && u != cur_u) {   // new user run: flush the previous row, adopt the fetched one
+            if (cur_u >= 0) {
+                Row<L, KPL>::store(p, a.P + (size_t)cur_u * KP, sl);
+                if (BIASED) a.bu[cur_u] = bu_v;
+            }
+#pragma unroll
+            for (int f = 0; f < KPL; f++) p[f] = pn[f];
+            bu_v = bun; regu = regun;
+            cur_u = u;
+        }
+        float q[KPL], q0[KPL];
+#pragma unroll
+        for (int f = 0; f < KPL; f++) { q[f] = qn[f]; q0[f] = qn[f]; }
+        float bi_v = bin;
+        const float bi0 = bin;
+        const bool same_item = active && e + 1 < e1 && i1 == i;   // next rating hits the same item: forward the new row
+        if (e + 1 < e1) {   // next entry: its item row, and its user row if a new run starts (runs are contiguous)
+            if (!same_item) {
+                Row<L, KPL>::load_cg(qn, Qg + (size_t)i1 * KP, sl);
+                if (BIASED) bin = ld_cg_f(Bg + i1);
+            }
+            if (u1 != cur_u) {
+                Row<L, KPL>::load(pn, a.P + (size_t)u1 * KP, sl);
+                if (BIASED) bun = a.bu[u1];
+                if (a.regw_u) regun = a.regw_u[u1];
+            }
+        }
+        const float regi = a.regw_i ? a.regw_i[i_lo + (active ? i : 0)] : a.reg_i;
+        float pw[KPL];
+#pragma unroll
+        for (int f = 0; f < KPL; f++) pw[f] = p[f];
+        float buw = bu_v;
+        sgd_update<L, KPL, BIASED>(a, pw, q, buw, bi_v, v, regu, regi);
+        if (active) {
+#pragma unroll
+            for (int f = 0; f < KPL; f++) p[f] = pw[f];
+            bu_v = buw;
+            float* qrow = Qg + (size_t)i * KP;
+#pragma unroll
+            for (int vv = 0; vv < KPL / 4; vv++)
+                red_add_f4(qrow + 4 * (vv * L + sl), q[4 * vv] - q0[4 * vv], q[4 * vv + 1] - q0[4 * vv + 1],
+                           q[4 * vv + 2] - q0[4 * vv + 2], q[4 * vv + 3] - q0[4 * vv + 3]);
+            if (BIASED && sl == 0) red_add_f(Bg + i, bi_v - bi0);
+            if (same_item) {
+#pragma unroll
+                for (int f = 0; f < KPL; f++) qn[f] = q[f];
+                bin = bi_v;
+            }
+        }
+    }
+    if (cur_u >= 0) {
+        Row<L, KPL>::store(p, a.P + (size_t)cur_u * KP, sl);
+        if (BIASED) a.bu[cur_u] = bu_v;
     }
 }
 
-// One launch per sub-epoch: grid = G CTAs, block = W warps.
-template <int KPL, bool BIASED, bool STAGE>
-__global__ void __launch_bounds__(1024) sgd_slot_kernel(const SgdArgs a, const int slot)
+// One launch per sub-epoch: grid = G CTAs.
+template <int L, int KPL, bool BIASED, bool STAGE, bool ASYNC>
+__global__ void __launch_bounds__(512) sgd_slot_kernel(const SgdArgs a, const int slot)
 {
     extern __shared__ float4 smem4[];
-    sgd_block<KPL, BIASED, STAGE>(a, blockIdx.x, slot, reinterpret_cast<float*>(smem4));
+    if (ASYNC) sgd_block_async<L, KPL, BIASED>(a, blockIdx.x, slot);
+    else sgd_block<L, KPL, BIASED, STAGE>(a, blockIdx.x, slot, reinterpret_cast<float*>(smem4));
 }
 
 // One cooperative launch per epoch: CTA j walks the sub-epoch sequence; before it takes item group b
 // it waits (acquire) until the CTA that held b in the previous sub-epoch has published it (release).
 // All G CTAs are co-resident (cooperative launch), so the waits cannot deadlock.
-template <int KPL, bool BIASED, bool STAGE>
-__global__ void __launch_bounds__(1024) sgd_epoch_kernel(const SgdArgs a)
+template <int L, int KPL, bool BIASED, bool STAGE, bool ASYNC>
+__global__ void __launch_bounds__(512) sgd_epoch_kernel(const SgdArgs a)
 {
     extern __shared__ float4 smem4[];
     const int j = blockIdx.x;
@@ -393,7 +870,8 @@ __global__ void __launch_bounds__(1024) sgd_epoch_kernel(const SgdArgs a)
             }
             __syncthreads();
         }
-        sgd_block<KPL, BIASED, STAGE>(a, j, slot, reinterpret_cast<float*>(smem4));
+        if (ASYNC) sgd_block_async<L, KPL, BIASED>(a, j, slot);
+        else sgd_block<L, KPL, BIASED, STAGE>(a, j, slot, reinterpret_cast<float*>(smem4));
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) st_release_u32(a.flags + j, a.epoch_base + (uint32_t)t + 1u);
@@ -674,12 +1152,16 @@ static SgdArgs make_args(Sgd& m, int32_t B)
     SgdArgs a{};
     a.P = m.P.p; a.Q = m.Q.p; a.bu = m.bu.p; a.bi = m.bi.p;
     a.ent_u = m.ent_u.p; a.ent_i = m.ent_i.p; a.ent_v = m.ent_v.p;
-    a.sub_ptr = m.sub_ptr.p ? m.sub_ptr.p + (size_t)B * m.G * m.G * m.W * m.W : nullptr;
+    a.round_ptr = m.round_ptr.p;
+    a.wptr = m.wptr.p ? m.wptr.p + (size_t)B * m.G * m.G * (m.n_workers + 1) : nullptr;
+    a.blk_round_ptr = m.blk_round_ptr.p ? m.blk_round_ptr.p + (size_t)B * m.G * m.G : nullptr;
     a.item_ptr = m.d_item_ptr.p ? m.d_item_ptr.p + (size_t)B * m.G : nullptr;
+    a.hot_cnt = m.d_hot_cnt.p ? m.d_hot_cnt.p + (size_t)B * m.G : nullptr;
     a.regw_u = m.p.frequency_regularization ? m.regw_u.p : nullptr;
     a.regw_i = m.p.frequency_regularization ? m.regw_i.p : nullptr;
     a.flags = m.flags.p; a.seq = nullptr; a.epoch_base = m.epoch_base;
-    a.G = m.G; a.W = m.W;
+    a.G = m.G; a.C = m.hot_copies; a.n_workers = m.n_workers;
+    a.hot_scale = m.p.hot_merge_average ? 1.f / (float)m.hot_copies : 1.f;
     a.lr = m.lr; a.gb = m.global_bias; a.minr = m.min_rating; a.range = m.range;
     if (m.p.biased) { a.reg_u = m.p.reg_u; a.reg_i = m.p.reg_i; }
     else { a.reg_u = m.p.regularization; a.reg_i = m.p.regularization; }
@@ -690,26 +1172,34 @@ static SgdArgs make_args(Sgd& m, int32_t B)
 typedef void (*slot_fn_t)(const SgdArgs, const int);
 typedef void (*epoch_fn_t)(const SgdArgs);
 
-template <int KPL>
-static void pick_kernels(bool biased, bool stage, slot_fn_t* sf, epoch_fn_t* ef)
+template <int L, int KPL, bool ASYNC>
+static void pick_kernels2(bool biased, bool stage, slot_fn_t* sf, epoch_fn_t* ef)
 {
     if (biased) {
-        if (stage) { *sf = sgd_slot_kernel<KPL, true, true>; *ef = sgd_epoch_kernel<KPL, true, true>; }
-        else { *sf = sgd_slot_kernel<KPL, true, false>; *ef = sgd_epoch_kernel<KPL, true, false>; }
+        if (stage) { *sf = sgd_slot_kernel<L, KPL, true, true, ASYNC>; *ef = sgd_epoch_kernel<L, KPL, true, true, ASYNC>; }
+        else { *sf = sgd_slot_kernel<L, KPL, true, false, ASYNC>; *ef = sgd_epoch_kernel<L, KPL, true, false, ASYNC>; }
     } else {
-        if (stage) { *sf = sgd_slot_kernel<KPL, false, true>; *ef = sgd_epoch_kernel<KPL, false, true>; }
-        else { *sf = sgd_slot_kernel<KPL, false, false>; *ef = sgd_epoch_kernel<KPL, false, false>; }
+        if (stage) { *sf = sgd_slot_kernel<L, KPL, false, true, ASYNC>; *ef = sgd_epoch_kernel<L, KPL, false, true, ASYNC>; }
+        else { *sf = sgd_slot_kernel<L, KPL, false, false, ASYNC>; *ef = sgd_epoch_kernel<L, KPL, false, false, ASYNC>; }
     }
 }
 
+template <int L, int KPL>
+static void pick_kernels(bool async, bool biased, bool stage, slot_fn_t* sf, epoch_fn_t* ef)
+{
+    if (async) pick_kernels2<L, KPL, true>(biased, stage, sf, ef);
+    else pick_kernels2<L, KPL, false>(biased, stage, sf, ef);
+}
+
+// kp = 32: 8 lanes x 4 floats (4 ratings per warp) ; 64: 8 x 8 ; 128: 16 x 8 (2 per warp) ; 256: 32 x 8
 static int32_t get_kernels(Sgd& m, slot_fn_t* sf, epoch_fn_t* ef)
 {
-    const bool stage = m.stage_bytes > 0;
-    switch (m.kpl) {
-        case 1: pick_kernels<1>(m.p.biased != 0, stage, sf, ef); break;
-        case 2: pick_kernels<2>(m.p.biased != 0, stage, sf, ef); break;
-        case 4: pick_kernels<4>(m.p.biased != 0, stage, sf, ef); break;
-        case 8: pick_kernels<8>(m.p.biased != 0, stage, sf, ef); break;
+    const bool stage = m.stage_bytes > 0, async = m.p.intra_block == MML_INTRA_ASYNC;
+    switch (m.kp) {
+        case 32: pick_kernels<8, 4>(async, m.p.biased != 0, stage, sf, ef); break;
+        case 64: pick_kernels<8, 8>(async, m.p.biased != 0, stage, sf, ef); break;
+        case 128: pick_kernels<16, 8>(async, m.p.biased != 0, stage, sf, ef); break;
+        case 256: pick_kernels<32, 8>(async, m.p.biased != 0, stage, sf, ef); break;
         default: set_error("unsupported num_factors"); return MML_ERR_UNSUPPORTED;
     }
     if (stage) {
@@ -888,6 +1378,11 @@ extern "C" void mml_mf_params_default(mml_mf_params* p)
     p->num_groups = 0; p->num_subgroups = 0;
     p->group_rule = MML_GROUPS_BALANCED;
     p->persistent = -1;
+    p->hot_item_factor = 1.0f;
+    p->hot_copies = 8;
+    p->intra_block = MML_INTRA_ASYNC;
+    p->async_workers = 0;
+    p->hot_merge_average = 1;
 }
 
 extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_params* p,
@@ -904,24 +1399,22 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
     Sgd& m = h->m;
     m.ctx = ctx; m.ratings = r; m.p = *p;
     m.k = p->num_factors;
-    m.kpl = m.k <= 32 ? 1 : (m.k <= 64 ? 2 : (m.k <= 128 ? 4 : 8));
-    m.kp = 32 * m.kpl;
+    m.kp = m.k <= 32 ? 32 : (m.k <= 64 ? 64 : (m.k <= 128 ? 128 : 256));
+    m.kpl = m.kp / 32;
     m.R = 1; m.rank = 0;
     cudaStream_t s = ctx->stream;
     int32_t st = MML_OK;
     do {
-        // group shape
+        // group shape: G worker groups (CTAs), W warps per CTA, C private copies per hot item
         if (p->schedule == MML_SCHEDULE_DSGD) {
             int32_t G = p->num_groups > 0 ? p->num_groups : ctx->sm_count;
             G = std::min(G, std::min(r->n_users(), r->n_items()));
-            G = std::max(G, 1);
-            int32_t W = p->num_subgroups;
-            if (W <= 0) W = (r->n / ((int64_t)G * G) >= 2048) ? 16 : 8;
-            W = std::min(W, 32);
-            W = std::min(W, std::max(1, std::min(r->n_users(), r->n_items()) / G));
-            m.G = G; m.W = std::max(W, 1);
+            m.G = std::max(G, 1);
+            int32_t W = p->num_subgroups > 0 ? p->num_subgroups : 8;
+            m.W = std::max(1, std::min(W, 16));
+            m.hot_copies = p->hot_copies > 0 ? std::min(p->hot_copies, 64) : 8;
         } else {
-            m.G = 1; m.W = 1;
+            m.G = 1; m.W = 1; m.hot_copies = 1;
         }
         // counts -> host (group balancing, zero rows)
         std::vector<uint32_t> cu(r->n_users()), ci(r->n_items());
@@ -931,19 +1424,47 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
             set_error("mml_sgd_create: count download failed: %s", cudaGetErrorString(cudaGetLastError()));
             st = MML_ERR_CUDA; break;
         }
-        const int32_t rule = p->schedule == MML_SCHEDULE_DSGD ? p->group_rule : MML_GROUPS_PERM_MOD;
-        build_group_map(m.users, r->n_users(), cu.data(), p->schedule == MML_SCHEDULE_DSGD ? user_perm : nullptr,
-                        m.R, m.rank, m.G, m.W, rule);
-        build_group_map(m.items, r->n_items(), ci.data(), p->schedule == MML_SCHEDULE_DSGD ? item_perm : nullptr,
-                        m.R, -1, m.G, m.W, rule);
+        const bool dsgd = p->schedule == MML_SCHEDULE_DSGD;
+        const int32_t rule = dsgd ? p->group_rule : MML_GROUPS_PERM_MOD;
+        build_group_map(m.users, r->n_users(), cu.data(), dsgd ? user_perm : nullptr, m.R, m.rank, m.G, 1, rule, 0, nullptr);
+        // Items: an item with d ratings in a block needs d rounds there. Items whose per-block share
+        // count / G reaches hot_item_factor x the block's ideal round count (ratings per block / workers) are
+        // "hot" and get C private copies per block -- which needs the staged (shared-memory) item group, so
+        // fall back step by step when that does not fit.
+        int max_optin = 0;
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+        const int lanes = m.kp <= 64 ? 8 : (m.kp == 128 ? 16 : 32);
+        const int n_workers = m.W * (32 / lanes);
+        int64_t hot_min = 0;
+        const bool async = dsgd && p->intra_block == MML_INTRA_ASYNC;
+        if (dsgd && !async && m.hot_copies > 1 && p->hot_item_factor > 0.f) {
+            const double ideal_rounds = std::max((double)r->n / ((double)m.G * m.G) / n_workers, 4.0);
+            hot_min = std::max<int64_t>((int64_t)((double)p->hot_item_factor * ideal_rounds * m.G), 2);
+        }
+        size_t need = 0;
+        int64_t max_rows = 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            build_group_map(m.items, r->n_items(), ci.data(), dsgd ? item_perm : nullptr, m.R, -1, m.G, 1, rule, hot_min, &m.h_hot_cnt);
+            m.h_item_ptr.assign(m.items.grp_ptr.begin(), m.items.grp_ptr.end());   // [R * G + 1]
+            max_rows = 0;
+            m.n_hot = 0;
+            for (int32_t g = 0; g < m.R * m.G; g++) {
+                max_rows = std::max<int64_t>(max_rows, (int64_t)(m.h_item_ptr[g + 1] - m.h_item_ptr[g]) + (int64_t)m.h_hot_cnt[g] * m.hot_copies);
+                m.n_hot += m.h_hot_cnt[g];
+            }
+            need = (size_t)max_rows * (m.kp + 2) * sizeof(float);   // row + bias + lock word
+            if (need <= (size_t)max_optin || hot_min == 0) break;
+            hot_min = 0;   // retry without hot items
+        }
+        m.stage_bytes = (dsgd && !async && need <= (size_t)max_optin) ? ((need + 15) / 16) * 16 : 0;
+        int32_t nu_max = 1;
+        for (int32_t g = 0; g < m.G; g++) nu_max = std::max(nu_max, m.users.grp_ptr[g + 1] - m.users.grp_ptr[g]);
         if ((st = upload_group_map(m.users, s)) || (st = upload_group_map(m.items, s))) break;
-        // item group ranges (level 1): group (B, b) covers packed groups (B*G + b)*W .. +W
-        m.h_item_ptr.resize((size_t)m.R * m.G + 1);
-        int32_t max_items = 0;
-        for (int32_t g = 0; g <= m.R * m.G; g++) m.h_item_ptr[g] = m.items.grp_ptr[(size_t)g * m.W];
-        for (int32_t g = 0; g < m.R * m.G; g++) max_items = std::max(max_items, m.h_item_ptr[g + 1] - m.h_item_ptr[g]);
-        if ((st = m.d_item_ptr.alloc(m.h_item_ptr.size()))) break;
-        if (cudaMemcpyAsync(m.d_item_ptr.p, m.h_item_ptr.data(), sizeof(int32_t) * m.h_item_ptr.size(), cudaMemcpyHostToDevice, s) != cudaSuccess) {
+        if ((st = m.d_item_ptr.alloc(m.h_item_ptr.size())) || (st = m.d_hot_cnt.alloc(m.h_hot_cnt.size())) ||
+            (st = m.d_user_ptr.alloc(m.users.grp_ptr.size()))) break;
+        if (cudaMemcpyAsync(m.d_item_ptr.p, m.h_item_ptr.data(), sizeof(int32_t) * m.h_item_ptr.size(), cudaMemcpyHostToDevice, s) != cudaSuccess ||
+            cudaMemcpyAsync(m.d_hot_cnt.p, m.h_hot_cnt.data(), sizeof(int32_t) * m.h_hot_cnt.size(), cudaMemcpyHostToDevice, s) != cudaSuccess ||
+            cudaMemcpyAsync(m.d_user_ptr.p, m.users.grp_ptr.data(), sizeof(int32_t) * m.users.grp_ptr.size(), cudaMemcpyHostToDevice, s) != cudaSuccess) {
             set_error("mml_sgd_create: H2D failed"); st = MML_ERR_CUDA; break;
         }
         // model storage
@@ -970,15 +1491,15 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
         m.lr = p->learn_rate;
         // strata
         if (p->schedule == MML_SCHEDULE_DSGD) {
-            if ((st = build_strata(m))) break;
-            const size_t need = (size_t)max_items * (m.kp + 1) * sizeof(float);
-            int max_optin = 0;
-            cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-            m.stage_bytes = (need <= (size_t)max_optin) ? ((need + 15) / 16) * 16 : 0;
+            if (m.p.intra_block == MML_INTRA_ASYNC) {
+                const int32_t nw = p->async_workers > 0 ? std::min(p->async_workers, n_workers) : n_workers;
+                if ((st = build_strata_async(m, nw))) break;
+            }
+            else if ((st = build_strata(m, nu_max, (int32_t)std::max<int64_t>(max_rows, 1)))) break;
             if (m.p.persistent < 0) m.p.persistent = 1;
             // item rows that stay in global memory are read through L1, which is only coherent across
             // launches: the single-launch epoch needs the staged (shared-memory) item groups
-            if (m.stage_bytes == 0) m.p.persistent = 0;
+            if (m.stage_bytes == 0 && m.p.intra_block != MML_INTRA_ASYNC) m.p.persistent = 0;
             if (m.p.persistent) {
                 // all G CTAs must be co-resident
                 slot_fn_t sf; epoch_fn_t ef;
@@ -1261,17 +1782,25 @@ extern "C" int32_t mml_sgd_stats(mml_sgd* h, int64_t* kernel_launches, float* la
     return MML_OK;
 }
 
-extern "C" int32_t mml_sgd_strata_info(mml_sgd* h, int32_t* G, int32_t* W, int64_t* n_subblocks, int64_t* staged_bytes)
+extern "C" int32_t mml_sgd_strata_info(mml_sgd* h, int32_t* G, int32_t* W, int64_t* n_rounds, int64_t* staged_bytes)
 {
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
     if (G) *G = h->m.G;
     if (W) *W = h->m.W;
-    if (n_subblocks) *n_subblocks = h->m.n_sub;
+    if (n_rounds) *n_rounds = h->m.n_rounds;
     if (staged_bytes) *staged_bytes = (int64_t)h->m.stage_bytes;
     return MML_OK;
 }
 
-extern "C" int32_t mml_sgd_schedule_dump(mml_sgd* h, const int32_t* subepoch_sequence, int32_t* order)
+extern "C" int32_t mml_sgd_hot_items(mml_sgd* h, int64_t* n_hot)
+{
+    MML_CHECK(h && n_hot, MML_ERR_ARG, "NULL argument");
+    *n_hot = h->m.n_hot;
+    return MML_OK;
+}
+
+extern "C" int32_t mml_sgd_schedule_dump(mml_sgd* h, const int32_t* subepoch_sequence, int32_t* order,
+                                        int32_t* block, int32_t* copy, int32_t* round)
 {
     MML_CHECK(h && order, MML_ERR_ARG, "mml_sgd_schedule_dump: NULL argument");
     Sgd& m = h->m;
@@ -1279,23 +1808,45 @@ extern "C" int32_t mml_sgd_schedule_dump(mml_sgd* h, const int32_t* subepoch_seq
     MML_CUDA(cudaSetDevice(m.ctx->device));
     cudaStream_t s = m.ctx->stream;
     const int64_t n = m.ratings->n;
-    std::vector<uint32_t> sp((size_t)m.n_sub + 1);
+    const bool async = m.p.intra_block == MML_INTRA_ASYNC;
+    std::vector<uint32_t> brp((size_t)m.n_blk + 1), rp((size_t)m.n_rounds + 1), wp;
     std::vector<int32_t> idx(std::max<int64_t>(n, 1));
-    MML_CUDA(cudaMemcpyAsync(sp.data(), m.sub_ptr.p, sizeof(uint32_t) * sp.size(), cudaMemcpyDeviceToHost, s));
-    if (n > 0) MML_CUDA(cudaMemcpyAsync(idx.data(), m.ent_idx.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    if (async) {
+        wp.resize((size_t)m.n_blk * (m.n_workers + 1));
+        MML_CUDA(cudaMemcpyAsync(wp.data(), m.wptr.p, sizeof(uint32_t) * wp.size(), cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaStreamSynchronize(s));
+        // one "round" per block: its entries in worker-slice order (a serial-equivalent order only with 1 worker)
+        rp.assign((size_t)m.n_blk + 1, 0);
+        for (int32_t bk = 0; bk < m.n_blk; bk++) { brp[bk] = bk; rp[bk] = wp[(size_t)bk * (m.n_workers + 1)]; }
+        brp[m.n_blk] = m.n_blk; rp[m.n_blk] = (uint32_t)n;
+    }
+    std::vector<int8_t> cp(std::max<int64_t>(n, 1));
+    if (!async) {
+        MML_CUDA(cudaMemcpyAsync(brp.data(), m.blk_round_ptr.p, sizeof(uint32_t) * brp.size(), cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaMemcpyAsync(rp.data(), m.round_ptr.p, sizeof(uint32_t) * rp.size(), cudaMemcpyDeviceToHost, s));
+    }
+    if (n > 0) {
+        MML_CUDA(cudaMemcpyAsync(idx.data(), m.ent_idx.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaMemcpyAsync(cp.data(), m.ent_copy.p, sizeof(int8_t) * n, cudaMemcpyDeviceToHost, s));
+    }
     MML_CUDA(cudaStreamSynchronize(s));
     int64_t pos = 0;
-    const int G = m.G, W = m.W;
+    const int G = m.G;
     for (int B = 0; B < m.R; B++)
         for (int t = 0; t < G; t++) {
             const int slot = subepoch_sequence ? subepoch_sequence[t] : t;
             MML_CHECK(slot >= 0 && slot < G, MML_ERR_ARG, "subepoch_sequence[%d] out of range", t);
-            for (int step = 0; step < W; step++)
-                for (int j = 0; j < G; j++)
-                    for (int w = 0; w < W; w++) {
-                        const size_t sb = ((((size_t)B * G + j) * G + slot) * W + w) * W + step;
-                        for (uint32_t e = sp[sb]; e < sp[sb + 1]; e++) order[pos++] = idx[e];
+            for (int j = 0; j < G; j++) {
+                const size_t blk = ((size_t)B * G + j) * G + slot;
+                for (uint32_t rd = brp[blk]; rd < brp[blk + 1]; rd++)
+                    for (uint32_t e = rp[rd]; e < rp[rd + 1]; e++) {
+                        order[pos] = idx[e];
+                        if (block) block[pos] = (B * G + t) * G + j;
+                        if (copy) copy[pos] = cp[e];
+                        if (round) round[pos] = (int32_t)rd;
+                        pos++;
                     }
+            }
         }
     MML_CHECK(pos == n, MML_ERR_STATE, "schedule covers %lld of %lld ratings", (long long)pos, (long long)n);
     return MML_OK;

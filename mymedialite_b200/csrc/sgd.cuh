@@ -23,10 +23,14 @@ struct Sgd {
     mml_mf_params p{};
     int32_t k = 0, kp = 0, kpl = 0;    // factors, padded row length (32 * kpl), floats per lane
     int32_t R = 1, rank = 0;           // GPU-level blocks (world size) and own block
-    int32_t G = 1, W = 1;              // CTA-level and warp-level groups
+    int32_t G = 1, W = 1;              // worker groups (CTAs) and warps per CTA
+    int32_t hot_copies = 1;            // private copies of a hot item row inside a block
     GroupMap users, items;
     std::vector<int32_t> h_item_ptr;   // [R * G + 1] internal item row range of CTA-level item group (B, b)
     DevBuf<int32_t> d_item_ptr;
+    std::vector<int32_t> h_hot_cnt;    // [R * G] hot items of CTA-level item group (B, b) (rows first in the group)
+    DevBuf<int32_t> d_hot_cnt;
+    int64_t n_hot = 0;
 
     // model, internal order, rows padded with zeros to kp floats
     DevBuf<float> P, Q, bu, bi;
@@ -35,11 +39,17 @@ struct Sgd {
     bool has_model = false;
     double last_loss = 0.0;            // bold driver
 
-    // strata: entries ordered by (B, j, slot, w, step), see sgd.cu
-    int64_t n_sub = 0;                 // R * G * G * W * W
+    // strata: entries ordered by (block = (B, j, slot), round), see sgd.cu
+    int32_t n_blk = 0;                 // R * G * G blocks
+    int64_t n_rounds = 0;
+    int32_t n_workers = 0;             // async mode: workers per CTA the slices were cut for
+    DevBuf<uint32_t> wptr;             // async mode: [n_blk][n_workers + 1]
+    DevBuf<uint32_t> round_ptr;        // [n_rounds + 1] first entry of each round
+    DevBuf<uint32_t> blk_round_ptr;    // [n_blk + 1] first round of each block
+    DevBuf<int32_t> d_user_ptr;        // [G + 1] internal user row range of each user group
     DevBuf<int32_t> ent_u, ent_i, ent_idx;
+    DevBuf<int8_t> ent_copy;           // -1 = cold item, else the private copy of the hot item row the entry updates
     DevBuf<float> ent_v;
-    DevBuf<uint32_t> sub_ptr;          // [n_sub + 1]
     size_t stage_bytes = 0;            // shared memory for the largest item group; 0 = not staged
     DevBuf<uint32_t> flags;            // persistent kernel: per-CTA progress counters
     uint32_t epoch_base = 0;

@@ -182,12 +182,31 @@ class SgdModel:
     def strata_info(self):
         G, W, ns, sb = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
         check(self.lib.mml_sgd_strata_info(self.h, C.byref(G), C.byref(W), C.byref(ns), C.byref(sb)))
-        return dict(G=G.value, W=W.value, n_subblocks=ns.value, staged_bytes=sb.value)
+        return dict(G=G.value, W=W.value, n_rounds=ns.value, staged_bytes=sb.value)
 
-    def schedule(self, subepoch_sequence=None):
-        order = np.zeros(max(self.ratings.n, 1), np.int32)
-        check(self.lib.mml_sgd_schedule_dump(self.h, _i32(subepoch_sequence), order))
-        return order[:self.ratings.n]
+    def schedule(self, subepoch_sequence=None, detail=False, rounds=False):
+        n = self.ratings.n
+        order = np.zeros(max(n, 1), np.int32)
+        block = np.zeros(max(n, 1), np.int32) if detail else None
+        copy = np.zeros(max(n, 1), np.int32) if detail else None
+        rnd = np.zeros(max(n, 1), np.int32) if rounds else None
+        check(self.lib.mml_sgd_schedule_dump(self.h, _i32(subepoch_sequence), order, block, copy, rnd))
+        if rounds:
+            return rnd[:n]
+        return (order[:n], block[:n], copy[:n]) if detail else order[:n]
+
+    def round_sizes(self, subepoch_sequence=None):
+        """Sizes of the rounds in schedule order."""
+        rnd = self.schedule(subepoch_sequence, rounds=True)
+        if rnd.size == 0:
+            return np.zeros(0, np.int64)
+        cuts = np.flatnonzero(np.diff(rnd)) + 1
+        return np.diff(np.concatenate([[0], cuts, [rnd.size]]))
+
+    def hot_items(self):
+        v = C.c_int64()
+        check(self.lib.mml_sgd_hot_items(self.h, C.byref(v)))
+        return v.value
 
     def close(self):
         if self.h:

@@ -60,7 +60,8 @@ def test_serial_example_train_matches_oracle(eng, example_data, biased):
     om.init(rng)
     r, gm = gpu_model(eng, u, i, v, biased, 10, om, schedule=engine._capi.SCHEDULE_SERIAL)
     assert abs(gm.get_model(False, False)["global_bias"] - om.global_bias) < 1e-6
-    om.train(rng)                      # draws RandomIndex on the first Iterate, 30 epochs
+    for _ in range(30):                # Train() minus InitModel: RandomIndex is drawn on the first Iterate
+        om.iterate(rng)
     ri = om.random_index.copy()
     for _ in range(30):
         gm.iterate(random_index=ri)
@@ -106,14 +107,21 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("intra", ["rounds", "async1"])
 @pytest.mark.parametrize("k,biased,G,W,persistent,loss,freq,n_items", CASES)
-def test_dsgd_epoch_equals_oracle_replay(eng, k, biased, G, W, persistent, loss, freq, n_items):
+def test_dsgd_epoch_equals_oracle_replay(eng, k, biased, G, W, persistent, loss, freq, n_items, intra):
+    """Deterministic schedules: `rounds` (conflict-free parallel rounds) and `async` restricted to one worker per
+    block. Both equal a serial pass in the dumped order, replayed by the oracle."""
     engine, ctx = eng
+    mode = dict(intra_block=engine._capi.INTRA_ROUNDS) if intra == "rounds" else \
+        dict(intra_block=engine._capi.INTRA_ASYNC, async_workers=1)
     d = small_data(n_items=n_items, n=20000 if n_items < 1000 else 40000)
     u, i, v = d["train"]
     kw = dict(loss=loss, frequency_regularization=freq) if biased else {}
     om = oracle_model(u, i, v, biased, k, **kw)
-    r, gm = gpu_model(eng, u, i, v, biased, k, om, num_groups=G, num_subgroups=W, persistent=persistent, **kw)
+    kw.update(mode)
+    r, gm = gpu_model(eng, u, i, v, biased, k, om, num_groups=G, num_subgroups=W, persistent=persistent,
+                      hot_item_factor=0.0, **kw)
     info = gm.strata_info()
     assert info["G"] == G and info["W"] == W
     if n_items >= 1000:
@@ -125,40 +133,130 @@ def test_dsgd_epoch_equals_oracle_replay(eng, k, biased, G, W, persistent, loss,
         assert np.array_equal(np.sort(order), np.arange(u.size))
         gm.iterate(subepoch_sequence=seq)
         om.iterate_indices(order)
-    assert_model_close(gm, om, biased, 5e-5)
+    # async: the step is applied as an fp32 delta by the L2 atomic unit -> one more rounding per update
+    assert_model_close(gm, om, biased, 5e-5 if intra == "rounds" else 3e-4)
+
+
+def _emulate_epoch(model, u, i, v, order, block, copy, W, hp, average=False):
+    """fp32 numpy restatement of the kernel's semantics INCLUDING hot-item copies: inside a block a hot item's
+    entries update private copies (all starting from the row at block start); at block end
+    row = copy0 + sum_{c>=1} (copy_c - old). Everything else is the reference update (:264-310)."""
+    U, V, bu, bi = model["U"], model["V"], model["bu"], model["bi"]
+    f = np.float32
+    lr, gb, minr, rng = f(hp["lr"]), f(hp["gb"]), f(hp["minr"]), f(hp["range"])
+    reg, blr, breg = f(0.015), f(1.0), f(0.01)
+    pos_sorted = np.argsort(block, kind="stable")
+    bounds = np.flatnonzero(np.diff(block[pos_sorted])) + 1
+    for chunk in np.split(pos_sorted, bounds):
+        hot = {}
+        for pos in chunk:
+            t = order[pos]; uu, ii, c = u[t], i[t], copy[pos]
+            if c >= 0:
+                if ii not in hot:
+                    hot[ii] = ([V[ii].copy() for _ in range(W)], [f(bi[ii]) for _ in range(W)], V[ii].copy(), f(bi[ii]))
+                q, qb = hot[ii][0][c], hot[ii][1][c]
+            else:
+                q, qb = V[ii], bi[ii]
+            p = U[uu]
+            score = f(f(f(gb + bu[uu]) + qb) + f(np.dot(p, q)))
+            sig = f(1.0) / (f(1.0) + np.exp(-score, dtype=f))
+            err = f(v[t]) - (minr + sig * rng)
+            gc = f(err * sig * (f(1.0) - sig) * rng)
+            bu[uu] = bu[uu] + blr * lr * (gc - breg * reg * bu[uu])
+            qb_new = qb + blr * lr * (gc - breg * reg * qb)
+            p_new = p + lr * (gc * q - reg * p)
+            q_new = q + lr * (gc * p - reg * q)
+            U[uu] = p_new
+            if c >= 0:
+                hot[ii][0][c][:] = q_new; hot[ii][1][c] = f(qb_new)
+            else:
+                V[ii] = q_new; bi[ii] = qb_new
+        for ii, (rows, biases, old, old_b) in hot.items():
+            scale = f(1.0 / W) if average else f(1.0)
+            acc, accb = rows[0] - old, f(biases[0] - old_b)
+            for c in range(1, W):
+                acc += rows[c] - old; accb = f(accb + f(biases[c] - old_b))
+            V[ii] = old + scale * acc; bi[ii] = f(old_b + scale * accb)
+
+
+@pytest.mark.parametrize("k,G,W,persistent,hot,avg", [(64, 4, 4, 1, 0.5, 0), (128, 3, 8, 0, 0.5, 1), (10, 5, 2, 1, 0.1, 1)])
+def test_dsgd_hot_item_copies_match_emulation(eng, k, G, W, persistent, hot, avg):
+    """Hot items (whose updates would serialise a block) run as W private chains per block, merged by summing
+    deltas; the device result equals an fp32 emulation of exactly that rule."""
+    engine, ctx = eng
+    d = small_data(n_users=400, n_items=60, n=12000)
+    u, i, v = d["train"]
+    om = oracle_model(u, i, v, True, k)
+    r, gm = gpu_model(eng, u, i, v, True, k, om, num_groups=G, num_subgroups=W, persistent=persistent, hot_item_factor=hot,
+                      hot_copies=W, intra_block=engine._capi.INTRA_ROUNDS, hot_merge_average=avg)
+    assert gm.hot_items() > 0
+    state = dict(U=om.user_factors.copy(), V=om.item_factors.copy(), bu=om.user_bias.copy(), bi=om.item_bias.copy())
+    g0 = gm.get_model(False, False)
+    avg, mn, mx = r.stats()
+    hp = dict(lr=0.01, gb=g0["global_bias"], minr=mn, range=mx - mn)
+    order, block, copy = gm.schedule(detail=True)
+    assert (copy >= 0).sum() > 0 and copy.max() < W
+    gm.iterate()
+    _emulate_epoch(state, u, i, v, order, block, copy, W, hp, average=bool(avg))
+    g = gm.get_model()
+    for key in ("U", "V", "bu", "bi"):
+        np.testing.assert_allclose(g[key], state[key], rtol=1e-4, atol=1e-4, err_msg=key)
 
 
 def test_dsgd_reference_group_rule_and_schedule_is_stratified(eng):
-    """PERM_MOD rule: group = perm[id] % groups (MultiCore.cs:64); concurrent sub-blocks share no user and no item."""
+    """PERM_MOD rule: group = perm[id] % G (MultiCore.cs:64); the blocks of a sub-epoch share no user and no item,
+    and the dumped order walks sub-epochs in sequence, the reference's DSGD schedule with g = G."""
     engine, ctx = eng
     d = small_data()
     u, i, v = d["train"]
-    G, W = 4, 2
+    G = 6
     rng = O.Random(7)
     up = rng.shuffle(np.arange(u.max() + 1)); ip = rng.shuffle(np.arange(i.max() + 1))
     r = engine.DeviceRatings(ctx, u, i, v)
-    p = engine.default_params(num_factors=16, num_groups=G, num_subgroups=W, group_rule=engine._capi.GROUPS_PERM_MOD)
+    p = engine.default_params(num_factors=16, num_groups=G, num_subgroups=2, group_rule=engine._capi.GROUPS_PERM_MOD,
+                              hot_item_factor=0.0, intra_block=engine._capi.INTRA_ROUNDS)
     gm = engine.SgdModel(ctx, r, p, up, ip)
-    order = gm.schedule()
-    T = G * W
-    ug, ig = up[u[order]] % T, ip[i[order]] % T
-    j, w = ug % G, ug // G
-    b, c = ig % G, ig // G
-    slot, step = (b - j) % G, (c - w) % W
-    key = slot * W + step
-    assert np.all(np.diff(key) >= 0), "schedule is ordered by (slot, step)"
-    for s in np.unique(key):
-        sel = key == s
-        workers = j[sel] * W + w[sel]
-        # inside one (slot, step) every user and every item belongs to exactly one worker
-        for ids in (u[order][sel], i[order][sel]):
-            owner = {}
-            for x, wk in zip(ids, workers):
-                assert owner.setdefault(x, wk) == wk
+    seq = np.array([3, 0, 5, 1, 4, 2], np.int32)
+    order, block, copy = gm.schedule(seq, detail=True)
+    assert np.all(copy == -1)
+    j, b = up[u[order]] % G, ip[i[order]] % G
+    slot = (b - j) % G
+    t = block // G
+    assert np.array_equal(slot, seq[t]) and np.array_equal(block % G, j)
+    assert np.all(np.diff(t) >= 0)
+    # the reference's partition: same membership as MultiCore.PartitionUsersAndItems with these permutations
+    optr, oidx = O.partition_blocks_given(u, i, up, ip, G)
+    for jj in range(G):
+        for bb in range(G):
+            mine = np.sort(order[(j == jj) & (b == bb)])
+            assert np.array_equal(mine, oidx[optr[jj * G + bb]:optr[jj * G + bb + 1]])
 
 
-def test_dsgd_rmse_tracks_single_threaded_oracle(eng):
-    """north_star gate: per-epoch train/test RMSE within 0.5 % of the reference's own (MaxThreads=1) run."""
+def test_dsgd_rounds_are_matchings(eng):
+    """Inside a block the CTA runs rounds of ratings with pairwise distinct users and item rows."""
+    engine, ctx = eng
+    d = small_data(n_users=200, n_items=50, n=6000)
+    u, i, v = d["train"]
+    r = engine.DeviceRatings(ctx, u, i, v)
+    gm = engine.SgdModel(ctx, r, engine.default_params(num_factors=8, num_groups=3, num_subgroups=2, hot_item_factor=1.0,
+                                                       intra_block=engine._capi.INTRA_ROUNDS))
+    order, block, copy = gm.schedule(detail=True)
+    rounds = gm.round_sizes()
+    assert rounds.sum() == u.size
+    pos = 0
+    for sz in rounds:
+        sel = order[pos:pos + sz]
+        assert len(set(u[sel])) == sz, "a user appears twice in a round"
+        rows = list(zip(i[sel], copy[pos:pos + sz]))
+        assert len(set(rows)) == sz, "an item row appears twice in a round"
+        assert len(set(block[pos:pos + sz])) == 1
+        pos += sz
+
+
+@pytest.mark.parametrize("intra", ["async", "rounds"])
+def test_dsgd_rmse_tracks_single_threaded_oracle(eng, intra):
+    """north_star gate: per-epoch train/test RMSE within 0.5 % of the reference's own (MaxThreads=1) run, for the
+    default lock-free intra-block mode and for the conflict-free rounds (with hot-item copies)."""
     engine, ctx = eng
     from mymedialite_b200 import synthetic
     d = synthetic.ratings(3000, 800, 300000, "half", 11)
@@ -167,7 +265,8 @@ def test_dsgd_rmse_tracks_single_threaded_oracle(eng):
     rng = O.Random(1)
     om = O.Model(u, i, v, biased=True, num_factors=k)
     om.init(rng)
-    r, gm = gpu_model(eng, u, i, v, True, k, om, num_groups=16, num_subgroups=4)
+    r, gm = gpu_model(eng, u, i, v, True, k, om, num_groups=16, num_subgroups=4,
+                      intra_block=engine._capi.INTRA_ASYNC if intra == "async" else engine._capi.INTRA_ROUNDS)
     for epoch in range(8):
         om.iterate(rng)
         gm.iterate()
