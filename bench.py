@@ -3,12 +3,15 @@
 BASELINE.json names.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ml10m|netflix|...]
+  torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU)
 
-A step is one Iterate() (one full SGD epoch over the resident training ratings). `value` is whole-job ratings/s
-with the ratings resident in HBM, timed with CUDA events on the library's stream; `e2e` is the same metric
-through the find-iter loop a MyMediaLite user runs (Iterate() + Evaluate(test) with HOST test arrays, section 3.2 of
-SURVEY.md), host<->device copies inside the timed region. `--impl reference` times the CPU restatement of the
-reference's own loops (oracle/, the C# original cannot run here: no Mono/.NET) on the host cores.
+A step is one Iterate() = one full SGD epoch over the resident training ratings. `value` is whole-job ratings/s
+with the ratings resident in HBM, timed with CUDA events on the library's stream (max over ranks); `e2e` is the
+same metric through the find-iter loop a MyMediaLite user runs (Iterate() + Evaluate(test) with HOST test arrays,
+SURVEY.md section 3.2), host<->device copies inside the timed region. N > 1 is weak scaling: every rank brings a
+user block of the named shape (its own users, the shared item catalogue); item blocks rotate round the NCCL ring.
+`--impl reference` times the CPU restatement of the reference's own loops (oracle/; the C# original cannot run
+here: no Mono/.NET in the image) on the host cores.
 """
 import argparse
 import json
@@ -29,6 +32,8 @@ WORKLOADS = {
               "BiasedMatrixFactorization k=64 SGD, synthetic MovieLens-10M shape (71.5k x 10.7k, 10M ratings)"),
     "netflix": (480_000, 17_800, 100_000_000, "int", 128, 20260104,
                 "BiasedMatrixFactorization k=128 DSGD, synthetic Netflix shape (480k x 17.8k, 100M ratings)"),
+    "netflix10": (48_000, 17_800, 10_000_000, "int", 128, 20260104,
+                  "BiasedMatrixFactorization k=128 DSGD, 1/10 of the synthetic Netflix shape (48k x 17.8k, 10M ratings)"),
     "tiny": (3_000, 800, 300_000, "half", 64, 7, "debug-sized"),
 }
 
@@ -62,11 +67,16 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.1)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in self.rows if r and num(r[0]) is not None]
+        mx = [num(r[1]) for r in self.rows if len(r) > 1 and num(r[1]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[c] for r in self.rows if len(r) >= 7 for c in range(4) if r[3 + c].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
@@ -74,22 +84,29 @@ class ClockSampler(threading.Thread):
 
 
 def make_data(name, rank=0, world=1):
+    """The rank's user shard: n_users users of its own (global id = local * world + rank, so that
+    user % world == rank, the reference's block rule) over the shared item catalogue."""
     from mymedialite_b200 import synthetic
     nu, ni, n, levels, k, seed, desc = WORKLOADS[name]
     cache = os.path.join("/tmp", "mmlb200_%s_%d_of_%d.npz" % (name, rank, world))
     if os.path.exists(cache):
         z = np.load(cache)
-        return dict(train=(z["u"], z["i"], z["v"]), test=(z["tu"], z["ti"], z["tv"]), n_users=nu, n_items=ni), k, desc
-    # n ratings in the TRAINING set (the shape the metric is quoted on) + 10 % test ratings on top
-    d = synthetic.ratings(nu, ni, int(n / 0.9), levels, seed)
-    u, i, v = d["train"]
-    if u.size > n:
-        u, i, v = u[:n], i[:n], v[:n]
-    d["train"] = (u, i, v)
-    try:
-        np.savez(cache, u=u, i=i, v=v, tu=d["test"][0], ti=d["test"][1], tv=d["test"][2])
-    except Exception:
-        pass
+        d = dict(train=(z["u"], z["i"], z["v"]), test=(z["tu"], z["ti"], z["tv"]))
+    else:
+        # n ratings in the TRAINING set (the shape the metric is quoted on) + 10 % test ratings on top
+        d = synthetic.ratings(nu, ni, int(n / 0.9), levels, seed + 1000 * rank, item_seed=seed)
+        u, i, v = d["train"]
+        if u.size > n:
+            u, i, v = u[:n], i[:n], v[:n]
+        d["train"] = (u, i, v)
+        try:
+            np.savez(cache, u=u, i=i, v=v, tu=d["test"][0], ti=d["test"][1], tv=d["test"][2])
+        except Exception:
+            pass
+    if world > 1:
+        d["train"] = ((d["train"][0] * world + rank).astype(np.int32), d["train"][1], d["train"][2])
+        d["test"] = ((d["test"][0] * world + rank).astype(np.int32), d["test"][1], d["test"][2])
+    d["n_users"], d["n_items"] = nu * world, ni
     return d, k, desc
 
 
@@ -98,104 +115,151 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    uid = None
     if world > 1:
-        raise SystemExit("multi-GPU DSGD ring is not wired into bench.py yet")
-    d, k, desc = make_data(args.workload)
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        t = torch.from_numpy(engine.Context.unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
+        dist.broadcast(t, 0)
+        uid = t.cpu().numpy()
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return float(x)
+        import torch
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    d, k, desc = make_data(args.workload, rank, world)
     u, i, v = d["train"]; tu, ti, tv = d["test"]
     n = int(u.size)
-    ctx = engine.Context(local_rank)
+    ctx = engine.Context(local_rank, rank, world, uid)
     t0 = time.time()
     ratings = engine.DeviceRatings(ctx, u, i, v, max_user=d["n_users"] - 1, max_item=d["n_items"] - 1)
     params = engine.default_params(biased=1, num_factors=k, num_groups=args.groups, num_subgroups=args.subgroups,
-                                   persistent=args.persistent, hot_item_factor=args.hot, hot_copies=args.copies, intra_block=args.intra,
-                                   hot_merge_average=args.hot_avg)
+                                   persistent=args.persistent, hot_item_factor=args.hot, hot_copies=args.copies,
+                                   intra_block=args.intra, hot_merge_average=args.hot_avg)
     model = engine.SgdModel(ctx, ratings, params)
     model.init_model(1, 0.0, 0.1)
     ctx.synchronize()
     build_s = time.time() - t0
     info = model.strata_info()
-    rs = np.random.RandomState(1)
+    rs = np.random.RandomState(1)      # same stream on every rank: all ranks use the same sub-epoch order
 
     def seq():
         return rs.permutation(info["G"]).astype(np.int32)
 
     for _ in range(args.warmup):
         model.iterate(seq())
-    ctx.synchronize()
+    barrier()
     launches0, _ = model.stats()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # --- device-resident: K epochs, each timed by CUDA events on the library's stream, L2 flushed in between
+    # --- device-resident: K epochs, each timed by CUDA events on the library's stream (kernels + ring exchange),
+    #     L2 flushed before each
     ms = []
     for _ in range(args.steps):
         ctx.flush_l2()
+        barrier()
         model.iterate(seq())
-        ms.append(model.stats()[1])
+        ms.append(max_over_ranks(model.stats()[1]))
+    barrier()
     launches1, _ = model.stats()
     dev_ms = float(np.sum(ms))
     # --- end to end: the find-iter loop (Iterate + Evaluate on host test arrays), wall clock around synchronous calls
-    ctx.synchronize()
+    barrier()
     t0 = time.time()
     rmse = None
     for _ in range(args.steps):
         model.iterate(seq())
         rmse = model.evaluate(tu, ti, tv)["RMSE"]
-    e2e_s = time.time() - t0
+    ctx.synchronize()
+    e2e_s = max_over_ranks(time.time() - t0)
     sampler.stop_flag.set(); sampler.join()
     train_rmse = model.evaluate_train()["RMSE"]
 
+    n_total = n * world
+    if dist is not None:
+        import torch
+        t = torch.tensor([float(n)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        n_total = int(t.item())
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+        return
     pk, pk_kind = peaks()
     bytes_per_rating = 16 * k + 28
     ms_per_step = dev_ms / args.steps
-    value = n * args.steps / (dev_ms * 1e-3)
-    achieved = bytes_per_rating * n / (ms_per_step * 1e-3) / 1e9
+    value = n_total * args.steps / (dev_ms * 1e-3)
+    achieved = bytes_per_rating * n / (ms_per_step * 1e-3) / 1e9      # per GPU
     out = {
-        "metric": "BiasedMF SGD ratings/sec", "value": value, "unit": "ratings/s", "n_gpus": 1,
+        "metric": "BiasedMF SGD ratings/sec", "value": value, "unit": "ratings/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "n_ratings": n, "num_factors": k, "schedule": "DSGD G=%d W=%d %s%s" % (
-            info["G"], info["W"], "async" if args.intra else "rounds", " persistent" if params.persistent != 0 else ""),
-            "item_group_smem_bytes": info["staged_bytes"], "rounds": info["n_rounds"], "hot_items": model.hot_items(), "l2": "flushed between timed epochs (384 MB memset)",
-            "strata_build_s": round(build_s, 3)},
-        "e2e": {"value": n * args.steps / e2e_s, "unit": "ratings/s",
+        "config": {"workload": desc + (" per GPU (users sharded, item catalogue shared)" if world > 1 else ""),
+                   "n_ratings": n_total, "num_factors": k,
+                   "schedule": "DSGD G=%d W=%d %s%s%s" % (info["G"], info["W"], "async" if args.intra else "rounds",
+                                                          " persistent" if params.persistent != 0 else "",
+                                                          (", item-block ring over %d GPUs" % world) if world > 1 else ""),
+                   "l2": "flushed before every timed epoch (384 MB memset)", "strata_build_s": round(build_s, 3)},
+        "e2e": {"value": n_total * args.steps / e2e_s, "unit": "ratings/s",
                 "h2d_bytes_per_step": int(12 * tu.size + 4 * info["G"]), "d2h_bytes_per_step": 16 + 8 * 4 * 1184,
                 "what": "Iterate() + Evaluate(test) per step through the C ABI with host test arrays"},
         "gpu_launches": int(launches1 - launches0),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
-                     "bytes_per_rating": bytes_per_rating},
+                     "bytes_per_rating": bytes_per_rating, "kernel": "sgd_epoch_kernel (one launch per epoch and item block)"},
         "clocks": sampler.summary(),
         "rmse": {"train": train_rmse, "test": rmse, "epochs": args.warmup + 2 * args.steps},
         "ms_each": [round(x, 3) for x in ms],
     }
+    tr = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if os.path.exists(tr):
+        try:
+            with open(tr) as f:
+                out["roofline"]["traffic"] = json.load(f).get(args.workload)
+        except Exception:
+            pass
     if not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(args, d, k, sample_only=True)
-    print(json.dumps(out))
+        out["cpu_baseline"] = cpu_baseline(args, d, k)
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
 
 
-def cpu_baseline(args, d, k, sample_only):
+def cpu_baseline(args, d, k):
     """The oracle's restatement of BiasedMatrixFactorization.Iterate timed on this box's host cores:
-    single-threaded (MaxThreads=1) on a bounded prefix of the workload."""
+    single-threaded (MaxThreads=1) over a bounded prefix of the workload."""
     from oracle import oracle as O
     u, i, v = d["train"]
     m = min(u.size, args.cpu_sample)
     us, is_, vs = u[:m].copy(), i[:m].copy(), v[:m].copy()
-    om = O.Model(us, is_, vs, biased=True, num_factors=k, max_user=d["n_users"] - 1, max_item=d["n_items"] - 1)
+    om = O.Model(us, is_, vs, biased=True, num_factors=k, max_user=int(us.max()), max_item=d["n_items"] - 1)
     rng = O.Random(1)
     om.init(rng)
     t0 = time.time()
     om.iterate(rng)
     dt = time.time() - t0
     return {"value": m / dt, "unit": "ratings/s", "cores": 1, "kind": "port",
-            "sample": "one single-threaded epoch (MaxThreads=1 order) over the first %d ratings of the workload, "
+            "sample": "one single-threaded epoch (MaxThreads=1 order) over the first %d ratings of the workload; "
                       "C restatement of the reference loop (no Mono/.NET in this image)" % m,
-            "seconds": dt}
+            "seconds": round(dt, 2)}
 
 
 def run_reference(args):
     """Reference arm: the reference's own CPU algorithm (oracle port) with all host threads: DSGD blocks on
-    OpenMP threads as BiasedMatrixFactorization does with MaxThreads = cores."""
+    OpenMP threads, as BiasedMatrixFactorization does with MaxThreads = cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -205,7 +269,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     m = min(u.size, args.cpu_sample)
     us, is_, vs = u[:m].copy(), i[:m].copy(), v[:m].copy()
-    om = O.Model(us, is_, vs, biased=True, num_factors=k, max_user=d["n_users"] - 1, max_item=d["n_items"] - 1,
+    om = O.Model(us, is_, vs, biased=True, num_factors=k, max_user=int(us.max()), max_item=d["n_items"] - 1,
                  max_threads=cores, omp_threads=cores)
     rng = O.Random(1)
     om.init(rng)
@@ -216,7 +280,7 @@ def run_reference(args):
         om.iterate(rng)
     dt = time.time() - t0
     value = m * args.steps / dt
-    sample = ("%d-rating prefix of the workload per step, DSGD block schedule (MultiCore.cs:43-73) on %d OpenMP threads, "
+    sample = ("%d-rating prefix of the workload per step, DSGD block schedule (MultiCore.cs:43-73) on %d OpenMP threads; "
               "C restatement of the reference loop (no Mono/.NET in this image)" % (m, cores))
     out = {
         "impl": "reference", "metric": "BiasedMF SGD ratings/sec", "value": value, "unit": "ratings/s",
@@ -227,7 +291,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "ratings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
 
 
 def main():
@@ -238,7 +302,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ml10m", choices=sorted(WORKLOADS))
     ap.add_argument("--groups", type=int, default=0)
-    ap.add_argument("--subgroups", type=int, default=0)
+    ap.add_argument("--subgroups", type=int, default=16)
     ap.add_argument("--persistent", type=int, default=-1)
     ap.add_argument("--hot", type=float, default=0.0)
     ap.add_argument("--copies", type=int, default=0)
@@ -248,6 +312,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.cpu_sample == 10_000_000:
+            args.cpu_sample = 4_000_000
         run_reference(args)
     else:
         run_ours(args)

@@ -42,6 +42,12 @@ const char* mml_version(void);
 /* ---- context ------------------------------------------------------------------------------ */
 /* device_ids may be NULL (device 0..n_gpus-1). One context per process per GPU. */
 int32_t mml_ctx_create(int32_t n_gpus, const int32_t* device_ids, mml_ctx** out);
+/* Multi-GPU: one process per GPU. Rank 0 calls mml_dist_unique_id (128 bytes = ncclUniqueId), hands the bytes to
+ * the other ranks (the host's own plumbing: torch.distributed, MPI, a file ...), then every rank calls
+ * mml_ctx_create_dist. Models created on such a context shard users over ranks (user block = user_perm[u] % world,
+ * MultiCore.cs:64 lifted to GPUs) and rotate item blocks round the ring after every GPU-level sub-epoch. */
+int32_t mml_dist_unique_id(uint8_t* out128);
+int32_t mml_ctx_create_dist(int32_t rank, int32_t world, int32_t device, const uint8_t* unique_id128, mml_ctx** out);
 int32_t mml_ctx_destroy(mml_ctx* ctx);
 int32_t mml_ctx_synchronize(mml_ctx* ctx);
 /* Benchmark hygiene: overwrites a 384 MB scratch buffer so the 126 MB L2 holds none of the model. */

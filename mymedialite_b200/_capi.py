@@ -62,6 +62,8 @@ SIGNATURES = {
     "mml_last_error": (C.c_char_p, []),
     "mml_version": (C.c_char_p, []),
     "mml_ctx_create": (C.c_int32, [C.c_int32, oi32p, PP]),
+    "mml_dist_unique_id": (C.c_int32, [np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")]),
+    "mml_ctx_create_dist": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), PP]),
     "mml_ctx_destroy": (C.c_int32, [vp]),
     "mml_ctx_synchronize": (C.c_int32, [vp]),
     "mml_ctx_flush_l2": (C.c_int32, [vp]),

@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("libmmlb200 build failed")
     if force or procs or _stale(SO, objs):
-        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + objs + ["-lcudart"]
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + objs + ["-lcudart", "-lnccl"]
         subprocess.check_call(cmd)
     return SO
 

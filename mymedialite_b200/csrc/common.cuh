@@ -76,7 +76,9 @@ struct Ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    int n_gpus = 1;
+    int n_gpus = 1;              // world size: one process (context) per GPU
+    int rank = 0;
+    void* comm = nullptr;        // ncclComm_t when n_gpus > 1
     void* flush_buf = nullptr;   // mml_ctx_flush_l2
     int flush_val = 0;
 };
@@ -94,6 +96,15 @@ struct Ratings {
 };
 
 Ratings* ratings_of(mml_ratings* h);
+int32_t dist_destroy(Ctx* c);
+int32_t dist_allreduce_u32(Ctx* c, uint32_t* d_buf, size_t n);
+int32_t dist_allreduce_f64(Ctx* c, double* d_buf, size_t n);
+int32_t dist_allreduce_f64_max(Ctx* c, double* d_buf, size_t n);
+int32_t dist_ring_exchange(Ctx* c, const float* send_a, size_t n_send_a, const float* send_b, size_t n_send_b, int to,
+                           float* recv_a, size_t n_recv_a, float* recv_b, size_t n_recv_b, int from);
+int32_t dist_broadcast_f32(Ctx* c, float* d_buf, size_t n, int root);
+int32_t dist_group_start();
+int32_t dist_group_end();
 Ctx* ctx_of(mml_ctx* h);
 
 }  // namespace mml

@@ -121,15 +121,12 @@ struct mml_ratings { Ratings r; };
 extern "C" const char* mml_last_error(void) { return mml::last_error(); }
 extern "C" const char* mml_version(void) { return "mmlb200 0.1 sm_100a"; }
 
-extern "C" int32_t mml_ctx_create(int32_t n_gpus, const int32_t* device_ids, mml_ctx** out)
+namespace mml {
+int32_t ctx_create_on_device(int dev, mml_ctx** out)
 {
-    MML_CHECK(out != nullptr, MML_ERR_ARG, "mml_ctx_create: out is NULL");
-    MML_CHECK(n_gpus == 1, MML_ERR_UNSUPPORTED,
-              "mml_ctx_create: one context drives one GPU (one process per GPU); got n_gpus=%d", n_gpus);
     int count = 0;
     MML_CUDA(cudaGetDeviceCount(&count));
     MML_CHECK(count > 0, MML_ERR_CUDA, "mml_ctx_create: no CUDA device (this library has no CPU fallback)");
-    const int dev = device_ids ? device_ids[0] : 0;
     MML_CHECK(dev >= 0 && dev < count, MML_ERR_ARG, "mml_ctx_create: device %d not in [0,%d)", dev, count);
     MML_CUDA(cudaSetDevice(dev));
     mml_ctx* c = new (std::nothrow) mml_ctx();
@@ -142,11 +139,21 @@ extern "C" int32_t mml_ctx_create(int32_t n_gpus, const int32_t* device_ids, mml
     *out = c;
     return MML_OK;
 }
+}
+
+extern "C" int32_t mml_ctx_create(int32_t n_gpus, const int32_t* device_ids, mml_ctx** out)
+{
+    MML_CHECK(out != nullptr, MML_ERR_ARG, "mml_ctx_create: out is NULL");
+    MML_CHECK(n_gpus == 1, MML_ERR_UNSUPPORTED,
+              "mml_ctx_create: one context drives one GPU (one process per GPU; use mml_ctx_create_dist); got n_gpus=%d", n_gpus);
+    return ctx_create_on_device(device_ids ? device_ids[0] : 0, out);
+}
 
 extern "C" int32_t mml_ctx_destroy(mml_ctx* ctx)
 {
     if (!ctx) return MML_OK;
     cudaSetDevice(ctx->c.device);
+    dist_destroy(&ctx->c);
     if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
     if (ctx->c.flush_buf) cudaFree(ctx->c.flush_buf);
     delete ctx;

@@ -1216,6 +1216,22 @@ static int32_t get_kernels(Sgd& m, slot_fn_t* sf, epoch_fn_t* ef)
     return MML_OK;
 }
 
+// Multi-GPU: after an epoch every rank holds the current rows of its home item block only; prediction and model
+// download need all of them -> every home block is broadcast from its rank (one grouped NCCL call).
+static int32_t sync_items(Sgd& m)
+{
+    if (m.R <= 1 || !m.items_dirty) return MML_OK;
+    MML_TRY(dist_group_start());
+    for (int B = 0; B < m.R; B++) {
+        const int32_t lo = m.h_item_ptr[(size_t)B * m.G], hi = m.h_item_ptr[(size_t)(B + 1) * m.G];
+        MML_TRY(dist_broadcast_f32(m.ctx, m.Q.p + (size_t)lo * m.kp, (size_t)(hi - lo) * m.kp, B));
+        MML_TRY(dist_broadcast_f32(m.ctx, m.bi.p + lo, (size_t)(hi - lo), B));
+    }
+    MML_TRY(dist_group_end());
+    m.items_dirty = false;
+    return MML_OK;
+}
+
 static PredArgs make_pred_args(Sgd& m)
 {
     PredArgs a{};
@@ -1230,6 +1246,7 @@ static PredArgs make_pred_args(Sgd& m)
 static int32_t evaluate_device(Sgd& m, const int32_t* d_u, const int32_t* d_i, const float* d_v, int64_t n, double* sums4)
 {
     cudaStream_t s = m.ctx->stream;
+    MML_TRY(sync_items(m));
     const int blocks = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(n * 32, EV_THREADS * 4), 1), 148 * 8);
     DevBuf<double> part;
     MML_TRY(part.alloc((size_t)blocks * 4));
@@ -1241,6 +1258,20 @@ static int32_t evaluate_device(Sgd& m, const int32_t* d_u, const int32_t* d_i, c
     MML_CUDA(cudaStreamSynchronize(s));
     for (int c = 0; c < 4; c++) sums4[c] = 0;
     for (int b = 0; b < blocks; b++) for (int c = 0; c < 4; c++) sums4[c] += h[(size_t)b * 4 + c];
+    return MML_OK;
+}
+
+// Sum over ranks of per-rank partial sums (and of the rating count n)
+static int32_t reduce_over_ranks(Sgd& m, double* vals, int count)
+{
+    if (m.R <= 1) return MML_OK;
+    cudaStream_t s = m.ctx->stream;
+    DevBuf<double> d;
+    MML_TRY(d.alloc(count));
+    MML_CUDA(cudaMemcpyAsync(d.p, vals, sizeof(double) * count, cudaMemcpyHostToDevice, s));
+    MML_TRY(dist_allreduce_f64(m.ctx, d.p, count));
+    MML_CUDA(cudaMemcpyAsync(vals, d.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s));
+    MML_CUDA(cudaStreamSynchronize(s));
     return MML_OK;
 }
 
@@ -1264,7 +1295,7 @@ static int32_t regterm(Sgd& m, bool user_side, double* out)
     regterm_kernel<<<blocks, EV_THREADS, 0, s>>>(user_side ? m.P.p : m.Q.p,
                                                  m.p.biased ? (user_side ? m.bu.p : m.bi.p) : nullptr,
                                                  gm.d_to_ext.p,
-                                                 user_side ? m.ratings->count_by_user.p : m.ratings->count_by_item.p,
+                                                 user_side ? m.ratings->count_by_user.p : m.item_counts.p,
                                                  gm.n_int, m.kp, reg, m.p.bias_reg,
                                                  m.p.frequency_regularization ? 1 : 0, part.p);
     MML_CUDA(cudaGetLastError());
@@ -1285,7 +1316,9 @@ static int32_t objective(Sgd& m, double* out)
     double ru = 0, ri = 0;
     MML_TRY(regterm(m, true, &ru));
     MML_TRY(regterm(m, false, &ri));
-    *out = sums[3] + ru + ri;
+    double local[1] = { sums[3] + ru };     // loss and user terms are per rank, item terms are global
+    MML_TRY(reduce_over_ranks(m, local, 1));
+    *out = local[0] + ri;
     return MML_OK;
 }
 
@@ -1334,7 +1367,12 @@ static int32_t run_dsgd_epoch(Sgd& m, const int32_t* h_seq)
         seen[seq[t]] = 1;
     }
     const int threads = m.W * 32;
-    for (int B = 0; B < m.R; B++) {   // R = 1 unless the ring driver moves item blocks between GPUs
+    // GPU-level sub-epochs: in sub-epoch S this rank works on item block B = (S + rank) mod R, then passes the
+    // block (factor rows + biases) to rank - 1 and takes the next one from rank + 1 -- the reference's block
+    // schedule (BiasedMatrixFactorization.cs:213-214) with GPUs in place of threads. After R sub-epochs every
+    // block is back on its home rank. R = 1: one pass, no exchange.
+    for (int S = 0; S < m.R; S++) {
+        const int B = (S + m.rank) % m.R;
         SgdArgs a = make_args(m, B);
         if (m.p.persistent) {
             DevBuf<int32_t>& dseq = m.d_index;   // reuse: serial index cache is unused in DSGD mode
@@ -1352,7 +1390,17 @@ static int32_t run_dsgd_epoch(Sgd& m, const int32_t* h_seq)
             }
             MML_CUDA(cudaGetLastError());
         }
+        if (m.R > 1) {
+            const int Bn = (B + 1) % m.R;
+            const int32_t s_lo = m.h_item_ptr[(size_t)B * m.G], s_hi = m.h_item_ptr[(size_t)(B + 1) * m.G];
+            const int32_t r_lo = m.h_item_ptr[(size_t)Bn * m.G], r_hi = m.h_item_ptr[(size_t)(Bn + 1) * m.G];
+            MML_TRY(dist_ring_exchange(m.ctx, m.Q.p + (size_t)s_lo * m.kp, (size_t)(s_hi - s_lo) * m.kp, m.bi.p + s_lo, (size_t)(s_hi - s_lo),
+                                       (m.rank + m.R - 1) % m.R,
+                                       m.Q.p + (size_t)r_lo * m.kp, (size_t)(r_hi - r_lo) * m.kp, m.bi.p + r_lo, (size_t)(r_hi - r_lo),
+                                       (m.rank + 1) % m.R));
+        }
     }
+    if (m.R > 1) m.items_dirty = true;
     return MML_OK;
 }
 
@@ -1408,7 +1456,7 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
     m.k = p->num_factors;
     m.kp = m.k <= 32 ? 32 : (m.k <= 64 ? 64 : (m.k <= 128 ? 128 : 256));
     m.kpl = m.kp / 32;
-    m.R = 1; m.rank = 0;
+    m.R = std::max(ctx->n_gpus, 1); m.rank = ctx->rank;
     cudaStream_t s = ctx->stream;
     int32_t st = MML_OK;
     do {
@@ -1424,9 +1472,28 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
             m.G = 1; m.W = 1; m.hot_copies = 1;
         }
         // counts -> host (group balancing, zero rows)
+        // item counts, rating sum and scale are global quantities: reduce them over the ranks
         std::vector<uint32_t> cu(r->n_users()), ci(r->n_items());
+        if ((st = m.item_counts.alloc(r->n_items()))) break;
+        cudaMemcpyAsync(m.item_counts.p, r->count_by_item.p, sizeof(uint32_t) * ci.size(), cudaMemcpyDeviceToDevice, s);
+        if ((st = dist_allreduce_u32(ctx, m.item_counts.p, ci.size()))) break;
+        double g_avg = r->average; float g_min = r->min_rating, g_max = r->max_rating;
+        if (m.R > 1) {
+            DevBuf<double> red;
+            if ((st = red.alloc(4))) break;
+            // sum of ratings and their number (sum), then -min and max (max)
+            double h4[4] = { (double)r->average * (double)r->n, (double)r->n, -(double)r->min_rating, (double)r->max_rating };
+            if (r->n == 0) { h4[2] = -1e30; h4[3] = -1e30; }
+            cudaMemcpyAsync(red.p, h4, sizeof(h4), cudaMemcpyHostToDevice, s);
+            if ((st = dist_allreduce_f64(ctx, red.p, 2))) break;
+            if ((st = dist_allreduce_f64_max(ctx, red.p + 2, 2))) break;
+            cudaMemcpyAsync(h4, red.p, sizeof(h4), cudaMemcpyDeviceToHost, s);
+            if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("stats reduction failed"); st = MML_ERR_CUDA; break; }
+            g_avg = h4[1] > 0 ? (double)((float)h4[0] / (float)h4[1]) : 0.0;
+            g_min = (float)-h4[2]; g_max = (float)h4[3];
+        }
         if (cudaMemcpyAsync(cu.data(), r->count_by_user.p, sizeof(uint32_t) * cu.size(), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-            cudaMemcpyAsync(ci.data(), r->count_by_item.p, sizeof(uint32_t) * ci.size(), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaMemcpyAsync(ci.data(), m.item_counts.p, sizeof(uint32_t) * ci.size(), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
             cudaStreamSynchronize(s) != cudaSuccess) {
             set_error("mml_sgd_create: count download failed: %s", cudaGetErrorString(cudaGetLastError()));
             st = MML_ERR_CUDA; break;
@@ -1483,17 +1550,17 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
             if ((st = m.regw_u.alloc(m.users.n_int)) || (st = m.regw_i.alloc(m.items.n_int))) break;
             const float ru = p->biased ? p->reg_u : p->regularization, ri = p->biased ? p->reg_i : p->regularization;
             regw_kernel<<<grid_n(m.users.n_int), 256, 0, s>>>(m.users.d_to_ext.p, r->count_by_user.p, m.users.n_int, ru, m.regw_u.p);
-            regw_kernel<<<grid_n(m.items.n_int), 256, 0, s>>>(m.items.d_to_ext.p, r->count_by_item.p, m.items.n_int, ri, m.regw_i.p);
+            regw_kernel<<<grid_n(m.items.n_int), 256, 0, s>>>(m.items.d_to_ext.p, m.item_counts.p, m.items.n_int, ri, m.regw_i.p);
             m.launches += 2;
         }
         // scale and global bias (BiasedMatrixFactorization.cs:186-190 / MatrixFactorization.cs:124)
-        m.min_rating = r->min_rating; m.max_rating = r->max_rating;
+        m.min_rating = g_min; m.max_rating = g_max;
         m.range = m.max_rating - m.min_rating;
         if (p->biased) {
-            const double avg = (double)(r->average - m.min_rating) / (double)m.range;
+            const double avg = (double)((float)g_avg - m.min_rating) / (double)m.range;
             m.global_bias = (float)std::log(avg / (1 - avg));
         } else {
-            m.global_bias = r->average;
+            m.global_bias = (float)g_avg;
         }
         m.lr = p->learn_rate;
         // strata
@@ -1587,7 +1654,7 @@ extern "C" int32_t mml_sgd_set_model(mml_sgd* h, const float* user_factors, cons
     Sgd& m = h->m;
     MML_CUDA(cudaSetDevice(m.ctx->device));
     MML_TRY(rows_from_host(m, m.users, m.ratings->count_by_user.p, user_factors, m.P.p));
-    MML_TRY(rows_from_host(m, m.items, m.ratings->count_by_item.p, item_factors, m.Q.p));
+    MML_TRY(rows_from_host(m, m.items, m.item_counts.p, item_factors, m.Q.p));
     MML_TRY(vec_from_host(m, m.users, user_bias, m.bu.p));
     MML_TRY(vec_from_host(m, m.items, item_bias, m.bi.p));
     MML_CUDA(cudaStreamSynchronize(m.ctx->stream));
@@ -1602,7 +1669,7 @@ extern "C" int32_t mml_sgd_init_model(mml_sgd* h, uint64_t seed, double init_mea
     cudaStream_t s = m.ctx->stream;
     init_rows_kernel<<<grid_n((int64_t)m.users.n_int * 32), 256, 0, s>>>(m.users.d_to_ext.p, m.ratings->count_by_user.p,
         m.users.n_int, m.k, m.kp, seed, 1, (float)init_mean, (float)init_stddev, m.P.p);
-    init_rows_kernel<<<grid_n((int64_t)m.items.n_int * 32), 256, 0, s>>>(m.items.d_to_ext.p, m.ratings->count_by_item.p,
+    init_rows_kernel<<<grid_n((int64_t)m.items.n_int * 32), 256, 0, s>>>(m.items.d_to_ext.p, m.item_counts.p,
         m.items.n_int, m.k, m.kp, seed, 2, (float)init_mean, (float)init_stddev, m.Q.p);
     MML_CUDA(cudaGetLastError());
     MML_CUDA(cudaMemsetAsync(m.bu.p, 0, m.bu.bytes(), s));
@@ -1619,6 +1686,7 @@ extern "C" int32_t mml_sgd_get_model(mml_sgd* h, float* user_factors, float* ite
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_get_model: no model (call set_model / init_model first)");
     MML_CUDA(cudaSetDevice(m.ctx->device));
+    MML_TRY(sync_items(m));
     cudaStream_t s = m.ctx->stream;
     for (int side = 0; side < 2; side++) {
         GroupMap& gm = side ? m.items : m.users;
@@ -1718,8 +1786,9 @@ extern "C" int32_t mml_sgd_predict(mml_sgd* h, const int32_t* users, const int32
     MML_CHECK(h && (n == 0 || (users && items && out)), MML_ERR_ARG, "mml_sgd_predict: NULL argument");
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_predict: no model");
-    if (n == 0) return MML_OK;
     MML_CUDA(cudaSetDevice(m.ctx->device));
+    MML_TRY(sync_items(m));   // collective on a multi-GPU context: every rank calls predict
+    if (n == 0) return MML_OK;
     cudaStream_t s = m.ctx->stream;
     DevBuf<int32_t> du, di; DevBuf<float> dout;
     MML_TRY(du.alloc(n)); MML_TRY(di.alloc(n)); MML_TRY(dout.alloc(n));
@@ -1738,7 +1807,7 @@ extern "C" int32_t mml_sgd_evaluate(mml_sgd* h, const int32_t* users, const int3
     MML_CHECK(h && out4 && (n == 0 || (users && items && values)), MML_ERR_ARG, "mml_sgd_evaluate: NULL argument");
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_evaluate: no model");
-    MML_CHECK(n > 0, MML_ERR_ARG, "mml_sgd_evaluate: empty test set");   // Eval/Ratings.cs:98-99 returns null
+    MML_CHECK(n > 0 || m.R > 1, MML_ERR_ARG, "mml_sgd_evaluate: empty test set");   // Eval/Ratings.cs:98-99 returns null
     MML_CUDA(cudaSetDevice(m.ctx->device));
     cudaStream_t s = m.ctx->stream;
     DevBuf<int32_t> du, di; DevBuf<float> dv;
@@ -1746,9 +1815,12 @@ extern "C" int32_t mml_sgd_evaluate(mml_sgd* h, const int32_t* users, const int3
     MML_CUDA(cudaMemcpyAsync(du.p, users, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
     MML_CUDA(cudaMemcpyAsync(di.p, items, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
     MML_CUDA(cudaMemcpyAsync(dv.p, values, sizeof(float) * n, cudaMemcpyHostToDevice, s));
-    double sums[4];
+    double sums[5];
     MML_TRY(evaluate_device(m, du.p, di.p, dv.p, n, sums));
-    sums_to_measures(m, sums, n, out4);
+    sums[4] = (double)n;
+    MML_TRY(reduce_over_ranks(m, sums, 5));   // multi-GPU: every rank passes its own users' test ratings
+    MML_CHECK(sums[4] > 0, MML_ERR_ARG, "mml_sgd_evaluate: empty test set");
+    sums_to_measures(m, sums, (int64_t)sums[4], out4);
     return MML_OK;
 }
 
@@ -1757,11 +1829,13 @@ extern "C" int32_t mml_sgd_evaluate_train(mml_sgd* h, float* out4)
     MML_CHECK(h && out4, MML_ERR_ARG, "mml_sgd_evaluate_train: NULL argument");
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_evaluate_train: no model");
-    MML_CHECK(m.ratings->n > 0, MML_ERR_ARG, "mml_sgd_evaluate_train: empty training set");
+    MML_CHECK(m.ratings->n > 0 || m.R > 1, MML_ERR_ARG, "mml_sgd_evaluate_train: empty training set");
     MML_CUDA(cudaSetDevice(m.ctx->device));
-    double sums[4];
+    double sums[5];
     MML_TRY(evaluate_device(m, m.ratings->users.p, m.ratings->items.p, m.ratings->values.p, m.ratings->n, sums));
-    sums_to_measures(m, sums, m.ratings->n, out4);
+    sums[4] = (double)m.ratings->n;
+    MML_TRY(reduce_over_ranks(m, sums, 5));
+    sums_to_measures(m, sums, (int64_t)sums[4], out4);
     return MML_OK;
 }
 
@@ -1839,8 +1913,9 @@ extern "C" int32_t mml_sgd_schedule_dump(mml_sgd* h, const int32_t* subepoch_seq
     MML_CUDA(cudaStreamSynchronize(s));
     int64_t pos = 0;
     const int G = m.G;
-    for (int B = 0; B < m.R; B++)
+    for (int S = 0; S < m.R; S++)           // execution order of the GPU-level sub-epochs on this rank
         for (int t = 0; t < G; t++) {
+            const int B = (S + m.rank) % m.R;
             const int slot = subepoch_sequence ? subepoch_sequence[t] : t;
             MML_CHECK(slot >= 0 && slot < G, MML_ERR_ARG, "subepoch_sequence[%d] out of range", t);
             for (int j = 0; j < G; j++) {
@@ -1848,7 +1923,7 @@ extern "C" int32_t mml_sgd_schedule_dump(mml_sgd* h, const int32_t* subepoch_seq
                 for (uint32_t rd = brp[blk]; rd < brp[blk + 1]; rd++)
                     for (uint32_t e = rp[rd]; e < rp[rd + 1]; e++) {
                         order[pos] = idx[e];
-                        if (block) block[pos] = (B * G + t) * G + j;
+                        if (block) block[pos] = (S * G + t) * G + j;
                         if (copy) copy[pos] = cp[e];
                         if (round) round[pos] = (int32_t)rd;
                         pos++;

@@ -37,6 +37,8 @@ struct Sgd {
     DevBuf<float> regw_u, regw_i;      // per-row regularisation weights (frequency regularisation only)
     float global_bias = 0.f, lr = 0.f, min_rating = 0.f, max_rating = 0.f, range = 0.f;
     bool has_model = false;
+    bool items_dirty = false;          // multi-GPU: item blocks away from home were updated since the last sync
+    DevBuf<uint32_t> item_counts;      // CountByItem over all ranks
     double last_loss = 0.0;            // bold driver
 
     // strata: entries ordered by (block = (B, j, slot), round), see sgd.cu

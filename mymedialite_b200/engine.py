@@ -19,12 +19,25 @@ def _f32(a):
 class Context:
     """One GPU (one process per GPU). Raises MmlError without a CUDA device: there is no CPU path."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, rank=0, world=1, unique_id=None):
         self.lib = _capi.load()
+        self.rank, self.world = rank, world
         h = C.c_void_p()
-        dev = np.array([device], dtype=np.int32)
-        check(self.lib.mml_ctx_create(1, dev, C.byref(h)))
+        if world > 1:
+            uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+            assert uid.size == 128
+            check(self.lib.mml_ctx_create_dist(rank, world, device, uid, C.byref(h)))
+        else:
+            dev = np.array([device], dtype=np.int32)
+            check(self.lib.mml_ctx_create(1, dev, C.byref(h)))
         self.h = h
+
+    @staticmethod
+    def unique_id():
+        """ncclUniqueId bytes: rank 0 creates them and hands them to the other ranks."""
+        out = np.zeros(128, np.uint8)
+        check(_capi.load().mml_dist_unique_id(out))
+        return out
 
     def sm_count(self):
         v = C.c_int32()

@@ -13,10 +13,10 @@ SHAPES = {
 }
 
 
-def _pairs(rng, n_users, n_items, n):
+def _pairs(rng, n_users, n_items, n, item_rng=None):
     act = rng.lognormal(0.0, 1.0, n_users)
     pop = 1.0 / np.arange(1, n_items + 1) ** 0.8
-    pop = pop[rng.permutation(n_items)]
+    pop = pop[(item_rng or rng).permutation(n_items)]
     pop /= pop.sum()
     cdf = np.cumsum(pop)
     cdf[-1] = 1.0
@@ -48,15 +48,18 @@ def _pairs(rng, n_users, n_items, n):
     return (keys // n_items).astype(np.int32), (keys % n_items).astype(np.int32)
 
 
-def ratings(n_users, n_items, n, levels="half", seed=1, test_fraction=0.1):
-    """Returns dict(train=(u, i, v), test=(u, i, v), n_users, n_items)."""
+def ratings(n_users, n_items, n, levels="half", seed=1, test_fraction=0.1, item_seed=None):
+    """Returns dict(train=(u, i, v), test=(u, i, v), n_users, n_items). item_seed: the item side of the planted
+    model and the popularity law come from their own generator, so that several user shards (one per GPU, each
+    with its own `seed`) share one item catalogue."""
     rng = np.random.Generator(np.random.PCG64(seed))
-    u, i = _pairs(rng, n_users, n_items, n)
+    irng = np.random.Generator(np.random.PCG64(item_seed)) if item_seed is not None else None
+    u, i = _pairs(rng, n_users, n_items, n, irng)
     rank = 16
     Pu = rng.normal(0, 0.35, (n_users, rank)).astype(np.float32)
-    Qi = rng.normal(0, 0.35, (n_items, rank)).astype(np.float32)
+    Qi = (irng or rng).normal(0, 0.35, (n_items, rank)).astype(np.float32)
     bu = rng.normal(0, 0.3, n_users).astype(np.float32)
-    bi = rng.normal(0, 0.3, n_items).astype(np.float32)
+    bi = (irng or rng).normal(0, 0.3, n_items).astype(np.float32)
     v = np.empty(u.size, np.float32)
     step = 1 << 22
     for s in range(0, u.size, step):
