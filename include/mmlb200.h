@@ -188,6 +188,51 @@ int32_t mml_sgd_hot_items(mml_sgd* m, int64_t* n_hot);
 int32_t mml_sgd_schedule_dump(mml_sgd* m, const int32_t* subepoch_sequence, int32_t* order,
                               int32_t* block, int32_t* copy, int32_t* round);
 
+/* ---- Top-N Recommend() ---------------------------------------------------------------------- */
+/* Recommender.Recommend (Recommender.cs:52-103) for a batch of users on an item-MF model
+ * (score = RowScalarProduct, ItemRecommendation/MF.cs:151-157): for every user the top n
+ * candidates not in its ignore list, ordered by (score desc, candidate position asc).
+ * n > 0 or n = -1 (all candidates with a score > float.MinValue); out arrays hold n_users * n_out entries,
+ * n_out = n_cand for n = -1, else min(n, n_cand).
+ * candidates: n_cand item ids (NULL = 0..n_model_items-1; the reference's own default, Enumerable.Range(0, MaxItemID - 1),
+ * drops the last two items -- every in-tree caller passes an explicit list, and so should hosts of this library). ignore CSR: ignore_ptr[n_users+1], ignore_idx
+ * (may be NULL). out_items/out_scores: n_users * n entries; out_counts[n_users]. */
+int32_t mml_topn_mf(mml_ctx* ctx, const float* user_factors, int32_t n_model_users,
+                    const float* item_factors, int32_t n_model_items, int32_t k,
+                    const int32_t* users, int64_t n_users, int32_t n,
+                    const int32_t* candidates, int64_t n_cand,
+                    const int64_t* ignore_ptr, const int32_t* ignore_idx,
+                    int32_t* out_items, float* out_scores, int32_t* out_counts);
+
+/* ---- WRMF ------------------------------------------------------------------------------------- */
+/* PosOnlyFeedback.UserMatrix / ItemMatrix (Data/PosOnlyFeedback.cs:35-83): duplicates collapse. */
+int32_t mml_feedback_create(mml_ctx* ctx, const int32_t* users, const int32_t* items, int64_t n,
+                            int32_t max_user, int32_t max_item, mml_feedback** out);
+int32_t mml_feedback_destroy(mml_feedback* f);
+int32_t mml_feedback_nnz(mml_feedback* f, int64_t* nnz);
+/* UserMatrix (by_item = 0) / ItemMatrix (by_item = 1) as CSR: row_ptr[rows + 1], cols[nnz] ascending inside a row. */
+int32_t mml_feedback_csr(mml_feedback* f, int32_t by_item, int64_t* row_ptr, int32_t* cols);
+
+typedef struct mml_wrmf_params {
+    int32_t num_factors;      /* NumFactors = 10 (ItemRecommendation/MF.cs:43-45) */
+    double  alpha;            /* Alpha = 1 (WRMF.cs:56) */
+    double  regularization;   /* Regularization = 0.015 (WRMF.cs:59) */
+} mml_wrmf_params;
+
+int32_t mml_wrmf_create(mml_ctx* ctx, mml_feedback* f, const mml_wrmf_params* p, mml_wrmf** out);
+int32_t mml_wrmf_destroy(mml_wrmf* m);
+int32_t mml_wrmf_set_model(mml_wrmf* m, const float* user_factors, const float* item_factors);
+int32_t mml_wrmf_init_model(mml_wrmf* m, uint64_t seed, double init_mean, double init_stddev);
+int32_t mml_wrmf_get_model(mml_wrmf* m, float* user_factors, float* item_factors);
+/* WRMF.Iterate (WRMF.cs:68-73): user half-sweep then item half-sweep. */
+int32_t mml_wrmf_iterate(mml_wrmf* m);
+int32_t mml_wrmf_stats(mml_wrmf* m, int64_t* kernel_launches, float* last_iterate_ms);
+/* mml_topn_mf on the device-resident model (no factor upload). */
+int32_t mml_wrmf_recommend(mml_wrmf* m, const int32_t* users, int64_t n_users, int32_t n,
+                           const int32_t* candidates, int64_t n_cand,
+                           const int64_t* ignore_ptr, const int32_t* ignore_idx,
+                           int32_t* out_items, float* out_scores, int32_t* out_counts);
+
 #ifdef __cplusplus
 }
 #endif

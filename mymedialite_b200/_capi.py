@@ -92,6 +92,20 @@ SIGNATURES = {
     "mml_sgd_stats": (C.c_int32, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "mml_sgd_strata_info": (C.c_int32, [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mml_sgd_hot_items": (C.c_int32, [vp, C.POINTER(C.c_int64)]),
+    "mml_topn_mf": (C.c_int32, [vp, f32p, C.c_int32, f32p, C.c_int32, C.c_int32, oi32p, C.c_int64, C.c_int32,
+                                oi32p, C.c_int64, oi64p, oi32p, i32p, f32p, i32p]),
+    "mml_feedback_create": (C.c_int32, [vp, oi32p, oi32p, C.c_int64, C.c_int32, C.c_int32, PP]),
+    "mml_feedback_destroy": (C.c_int32, [vp]),
+    "mml_feedback_nnz": (C.c_int32, [vp, C.POINTER(C.c_int64)]),
+    "mml_feedback_csr": (C.c_int32, [vp, C.c_int32, i64p, i32p]),
+    "mml_wrmf_create": (C.c_int32, [vp, vp, C.POINTER(WrmfParams), PP]),
+    "mml_wrmf_destroy": (C.c_int32, [vp]),
+    "mml_wrmf_set_model": (C.c_int32, [vp, f32p, f32p]),
+    "mml_wrmf_init_model": (C.c_int32, [vp, C.c_uint64, C.c_double, C.c_double]),
+    "mml_wrmf_get_model": (C.c_int32, [vp, of32p, of32p]),
+    "mml_wrmf_iterate": (C.c_int32, [vp]),
+    "mml_wrmf_stats": (C.c_int32, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    "mml_wrmf_recommend": (C.c_int32, [vp, oi32p, C.c_int64, C.c_int32, oi32p, C.c_int64, oi64p, oi32p, i32p, f32p, i32p]),
     "mml_sgd_schedule_dump": (C.c_int32, [vp, oi32p, i32p, oi32p, oi32p, oi32p]),
 }
 

@@ -1,0 +1,340 @@
+// topn.cu -- Recommend() for a batch of users on an item-MF model (WRMF / MF).
+//
+// Reference: Recommender.Recommend (Recommender.cs:52-103): score every candidate that is not in ignore_items with
+// Predict, keep those with score > float.MinValue; n > 0 -> the n best (C5 IntervalHeap), n = -1 -> all, by
+// descending score (stable sort: ties keep candidate-list order). Predict of item-MF = RowScalarProduct
+// (ItemRecommendation/MF.cs:151-157 -> DataType/MatrixExtensions.cs:224-241: sequential fp32 multiply then add,
+// float.MinValue for ids outside the model).
+//
+// Result order here: (score desc, candidate position asc) -- the reference's order for n = -1 always, and for
+// n > 0 whenever the best n + 1 scores differ (C5's tie order is not pinned by anything in the reference).
+// Scores are bit-exact: every (user, candidate) dot product is accumulated f = 0 .. k-1 in fp32 with separate
+// multiply and add, exactly as RowScalarProduct does.
+//
+// Round-1 status: exact scoring on the CUDA cores (tiled, shared-memory staged) into a score buffer, then a
+// per-user selection kernel. The tcgen05 scoring GEMM (approximate scores to pick a candidate superset, exact
+// re-scoring of the finalists) named by the north star is not written yet ("what comes next").
+#include "common.cuh"
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <new>
+
+namespace mml {
+
+static inline int grid_n(int64_t n, int threads = 256)
+{
+    return (int)std::min<int64_t>(std::max<int64_t>(ceil_div(n, threads), 1), 148 * 16);
+}
+
+// ---- exact scores of a user batch against all candidates -------------------------------------------------
+constexpr int TS = 64;      // users per tile = candidates per tile
+constexpr int TK = 32;      // factors per staging step
+
+// scores[b * n_cand + c] = dot(U[users[b]], V[cand[c]]) (sequential fp32 mul/add), or -FLT_MAX for ids outside the model
+__global__ void __launch_bounds__(256) score_tile_kernel(const float* __restrict__ U, int32_t n_model_users,
+                                                         const float* __restrict__ V, int32_t n_model_items, int32_t k,
+                                                         const int32_t* __restrict__ users, int32_t n_batch,
+                                                         const int32_t* __restrict__ cand, int64_t n_cand,
+                                                         float* __restrict__ scores)
+{
+    __shared__ float Us[TK][TS + 1];    // transposed: [f][user]
+    __shared__ float Vs[TK][TS + 1];
+    __shared__ int32_t su[TS], sc[TS];
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;     // 16 x 16 threads, 4 x 4 results each
+    const int64_t c0 = (int64_t)blockIdx.x * TS;
+    const int b0 = blockIdx.y * TS;
+    if (threadIdx.x < TS) {
+        const int b = b0 + threadIdx.x;
+        int32_t uid = b < n_batch ? users[b] : -1;
+        if (uid >= n_model_users) uid = -1;
+        su[threadIdx.x] = uid;
+    } else if (threadIdx.x < 2 * TS) {
+        const int64_t c = c0 + (threadIdx.x - TS);
+        int32_t iid = c < n_cand ? (cand ? cand[c] : (int32_t)c) : -1;
+        if (iid >= n_model_items) iid = -1;
+        sc[threadIdx.x - TS] = iid;
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
+    for (int f0 = 0; f0 < k; f0 += TK) {
+        // stage TS rows x TK factors of both sides (coalesced along f)
+        for (int t = threadIdx.x; t < TS * TK; t += 256) {
+            const int row = t / TK, f = t % TK;
+            const int32_t uid = su[row], iid = sc[row];
+            Us[f][row] = (uid >= 0 && f0 + f < k) ? U[(size_t)uid * k + f0 + f] : 0.f;
+            Vs[f][row] = (iid >= 0 && f0 + f < k) ? V[(size_t)iid * k + f0 + f] : 0.f;
+        }
+        __syncthreads();
+        const int fmax = min(TK, k - f0);
+        for (int f = 0; f < fmax; f++) {
+            float a4[4], b4[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) a4[a] = Us[f][ty * 4 + a];
+#pragma unroll
+            for (int b = 0; b < 4; b++) b4[b] = Vs[f][tx * 4 + b];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) acc[a][b] = __fadd_rn(acc[a][b], __fmul_rn(a4[a], b4[b]));
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const int b = b0 + ty * 4 + a;
+        if (b >= n_batch) continue;
+#pragma unroll
+        for (int bb = 0; bb < 4; bb++) {
+            const int64_t c = c0 + tx * 4 + bb;
+            if (c >= n_cand) continue;
+            const bool ok = su[ty * 4 + a] >= 0 && sc[tx * 4 + bb] >= 0;
+            scores[(size_t)b * n_cand + c] = ok ? acc[a][bb] : -FLT_MAX;
+        }
+    }
+}
+
+// scores of the user's ignore_items -> -inf. pos_of[item] = first candidate position of item (or -1),
+// next_same[pos] = next position holding the same item (or -1).
+__global__ void mask_ignored_kernel(const int64_t* __restrict__ ign_ptr, const int32_t* __restrict__ ign_idx,
+                                    int32_t b_lo, int32_t n_batch, const int32_t* __restrict__ pos_of, int32_t n_pos_of,
+                                    const int32_t* __restrict__ next_same, int64_t n_cand, float* __restrict__ scores)
+{
+    const int b = blockIdx.x;
+    if (b >= n_batch) return;
+    const int64_t lo = ign_ptr[b_lo + b], hi = ign_ptr[b_lo + b + 1];
+    for (int64_t t = lo + threadIdx.x; t < hi; t += blockDim.x) {
+        const int32_t item = ign_idx[t];
+        if (item < 0 || item >= n_pos_of) continue;
+        for (int32_t pos = pos_of[item]; pos >= 0; pos = next_same[pos]) scores[(size_t)b * n_cand + pos] = -INFINITY;
+    }
+}
+
+// ---- per-user selection of the n best (n <= MAXN) --------------------------------------------------------
+constexpr int SEL_T = 128;
+constexpr int MAXN = 32;
+
+__device__ __forceinline__ bool better(float sa, int pa, float sb, int pb) { return sa > sb || (sa == sb && pa < pb); }
+
+// one CTA per user: every thread keeps the n best of its strided share (sorted, in shared memory), then n rounds of
+// block-wide arg-best over the list heads.
+__global__ void __launch_bounds__(SEL_T) select_topn_kernel(const float* __restrict__ scores, int64_t n_cand, int32_t n,
+                                                            const int32_t* __restrict__ cand,
+                                                            int32_t* __restrict__ out_items, float* __restrict__ out_scores,
+                                                            int32_t* __restrict__ out_counts)
+{
+    extern __shared__ unsigned char sel_smem[];
+    float* ls = reinterpret_cast<float*>(sel_smem);                  // [SEL_T][n]
+    int32_t* lp = reinterpret_cast<int32_t*>(ls + (size_t)SEL_T * n);  // [SEL_T][n]
+    __shared__ float rs[SEL_T / 32]; __shared__ int rp[SEL_T / 32]; __shared__ int rt[SEL_T / 32];
+    __shared__ int win_t;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float* sc = scores + (size_t)b * n_cand;
+    float* my_s = ls + (size_t)tid * n; int32_t* my_p = lp + (size_t)tid * n;
+    int cnt = 0;
+    for (int64_t c = tid; c < n_cand; c += SEL_T) {
+        const float s = sc[c];
+        if (!(s > -FLT_MAX)) continue;                               // float.MinValue and masked entries never qualify
+        if (cnt == n && !better(s, (int)c, my_s[n - 1], my_p[n - 1])) continue;
+        int pos = cnt < n ? cnt : n - 1;                             // insertion into the sorted list
+        while (pos > 0 && better(s, (int)c, my_s[pos - 1], my_p[pos - 1])) { my_s[pos] = my_s[pos - 1]; my_p[pos] = my_p[pos - 1]; pos--; }
+        my_s[pos] = s; my_p[pos] = (int32_t)c;
+        if (cnt < n) cnt++;
+    }
+    int head = 0, produced = 0;
+    for (int r = 0; r < n; r++) {
+        float s = head < cnt ? my_s[head] : -INFINITY; int p = head < cnt ? my_p[head] : 0x7fffffff; int t = tid;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float s2 = __shfl_xor_sync(0xffffffffu, s, d); const int p2 = __shfl_xor_sync(0xffffffffu, p, d);
+            const int t2 = __shfl_xor_sync(0xffffffffu, t, d);
+            if (better(s2, p2, s, p)) { s = s2; p = p2; t = t2; }
+        }
+        if ((tid & 31) == 0) { rs[tid >> 5] = s; rp[tid >> 5] = p; rt[tid >> 5] = t; }
+        __syncthreads();
+        if (tid == 0) {
+            float bs = rs[0]; int bp = rp[0], bt = rt[0];
+            for (int w = 1; w < SEL_T / 32; w++) if (better(rs[w], rp[w], bs, bp)) { bs = rs[w]; bp = rp[w]; bt = rt[w]; }
+            if (bp != 0x7fffffff) {
+                out_items[(size_t)b * n + r] = cand ? cand[bp] : bp;
+                out_scores[(size_t)b * n + r] = bs;
+                win_t = bt;
+            } else {
+                win_t = -1;
+            }
+        }
+        __syncthreads();
+        if (win_t < 0) break;
+        if (win_t == tid) head++;
+        produced++;
+        __syncthreads();
+    }
+    if (tid == 0) out_counts[b] = produced;
+}
+
+// ---- full ranking / large n: sort the whole score buffer ----------------------------------------------------
+// key ascending == score descending (total order on floats; -0 and +0 compare equal in the reference, so map -0 to +0)
+__global__ void rank_key_kernel(const float* __restrict__ scores, int64_t total, uint32_t* __restrict__ key, uint32_t* __restrict__ val)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        float s = scores[t];
+        if (s == 0.f) s = 0.f;
+        uint32_t u = __float_as_uint(s);
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);     // ascending in s
+        key[t] = ~u;                                          // descending in s
+        val[t] = (uint32_t)t;
+    }
+}
+
+__global__ void rank_user_key_kernel(const uint32_t* __restrict__ val, int64_t total, int64_t n_cand, uint32_t* __restrict__ key)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; t < total; t += stride) key[t] = (uint32_t)(val[t] / n_cand);
+}
+
+// after sorting by (user, score desc, position asc): row b occupies [b * n_cand, (b + 1) * n_cand)
+__global__ void rank_emit_kernel(const uint32_t* __restrict__ val, const float* __restrict__ scores, int64_t n_cand, int32_t n_out,
+                                 const int32_t* __restrict__ cand, int32_t* __restrict__ out_items, float* __restrict__ out_scores,
+                                 int32_t* __restrict__ out_counts)
+{
+    const int b = blockIdx.x;
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    int local = 0;
+    for (int64_t r = threadIdx.x; r < n_out; r += blockDim.x) {
+        const uint32_t src = val[(size_t)b * n_cand + r];
+        const float s = scores[src];
+        if (s > -FLT_MAX) {
+            const int64_t pos = (int64_t)src - (int64_t)b * n_cand;
+            out_items[(size_t)b * n_out + r] = cand ? cand[pos] : (int32_t)pos;
+            out_scores[(size_t)b * n_out + r] = s;
+            local++;
+        }
+    }
+    atomicAdd(&s_cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) out_counts[b] = s_cnt;     // qualifying entries sort first, so they are rows 0 .. count-1
+}
+
+// d_U / d_V: model on the device. All other pointers: host.
+int32_t topn_device(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
+                    const int32_t* users, int64_t n_users, int32_t n,
+                    const int32_t* candidates, int64_t n_cand,
+                    const int64_t* ignore_ptr, const int32_t* ignore_idx,
+                    int32_t* out_items, float* out_scores, int32_t* out_counts, int64_t* launches)
+{
+    cudaStream_t s = ctx->stream;
+    if (n_users == 0) return MML_OK;
+    if (!candidates) n_cand = n_model_items;
+    const int32_t n_out = n < 0 ? (int32_t)n_cand : (int32_t)std::min<int64_t>(n, n_cand);
+    if (n_cand == 0 || n_out == 0) { for (int64_t b = 0; b < n_users; b++) out_counts[b] = 0; return MML_OK; }
+    MML_CHECK(n_cand < ((int64_t)1 << 31), MML_ERR_ARG, "topn: too many candidates");
+    // candidate list and the position maps for ignore_items
+    DevBuf<int32_t> d_cand, d_pos_of, d_next, d_users, d_ign_idx; DevBuf<int64_t> d_ign_ptr;
+    if (candidates) {
+        MML_TRY(d_cand.alloc(n_cand));
+        MML_CUDA(cudaMemcpyAsync(d_cand.p, candidates, sizeof(int32_t) * n_cand, cudaMemcpyHostToDevice, s));
+    }
+    int32_t n_pos_of = 0;
+    if (ignore_ptr && ignore_idx && ignore_ptr[n_users] > 0) {
+        int32_t max_id = n_model_items - 1;
+        if (candidates) for (int64_t c = 0; c < n_cand; c++) max_id = std::max(max_id, candidates[c]);
+        n_pos_of = max_id + 1;
+        std::vector<int32_t> pos_of(std::max(n_pos_of, 1), -1), next(n_cand, -1);
+        for (int64_t c = n_cand - 1; c >= 0; c--) {
+            const int32_t item = candidates ? candidates[c] : (int32_t)c;
+            if (item < 0) continue;
+            next[c] = pos_of[item]; pos_of[item] = (int32_t)c;
+        }
+        MML_TRY(d_pos_of.alloc(pos_of.size())); MML_TRY(d_next.alloc(n_cand));
+        MML_TRY(d_ign_ptr.alloc((size_t)n_users + 1)); MML_TRY(d_ign_idx.alloc((size_t)ignore_ptr[n_users]));
+        MML_CUDA(cudaMemcpyAsync(d_pos_of.p, pos_of.data(), sizeof(int32_t) * pos_of.size(), cudaMemcpyHostToDevice, s));
+        MML_CUDA(cudaMemcpyAsync(d_next.p, next.data(), sizeof(int32_t) * n_cand, cudaMemcpyHostToDevice, s));
+        MML_CUDA(cudaMemcpyAsync(d_ign_ptr.p, ignore_ptr, sizeof(int64_t) * ((size_t)n_users + 1), cudaMemcpyHostToDevice, s));
+        MML_CUDA(cudaMemcpyAsync(d_ign_idx.p, ignore_idx, sizeof(int32_t) * (size_t)ignore_ptr[n_users], cudaMemcpyHostToDevice, s));
+        MML_CUDA(cudaStreamSynchronize(s));
+    }
+    MML_TRY(d_users.alloc(n_users));
+    MML_CUDA(cudaMemcpyAsync(d_users.p, users, sizeof(int32_t) * n_users, cudaMemcpyHostToDevice, s));
+
+    const bool fast = n > 0 && n_out <= MAXN;
+    // users per pass: score buffer <= 1 GiB; the sorting path also needs 32-bit positions
+    int64_t B = std::max<int64_t>(1, ((int64_t)1 << 28) / n_cand);
+    if (!fast) B = std::max<int64_t>(1, std::min<int64_t>(B, (((int64_t)1 << 31) - 1) / n_cand));
+    B = std::min<int64_t>(B, n_users);
+    B = std::min<int64_t>(B, 65535 * (int64_t)TS);
+    DevBuf<float> d_scores, d_out_s; DevBuf<int32_t> d_out_i, d_out_c;
+    MML_TRY(d_scores.alloc((size_t)B * n_cand));
+    MML_TRY(d_out_s.alloc((size_t)B * n_out)); MML_TRY(d_out_i.alloc((size_t)B * n_out)); MML_TRY(d_out_c.alloc(B));
+    DevBuf<uint32_t> key, val, k2, v2;
+    if (!fast) { MML_TRY(key.alloc((size_t)B * n_cand)); MML_TRY(val.alloc((size_t)B * n_cand)); MML_TRY(k2.alloc((size_t)B * n_cand)); MML_TRY(v2.alloc((size_t)B * n_cand)); }
+    for (int64_t b_lo = 0; b_lo < n_users; b_lo += B) {
+        const int32_t nb = (int32_t)std::min<int64_t>(B, n_users - b_lo);
+        dim3 grid((unsigned)ceil_div(n_cand, TS), (unsigned)ceil_div(nb, TS));
+        score_tile_kernel<<<grid, 256, 0, s>>>(d_U, n_model_users, d_V, n_model_items, k, d_users.p + b_lo, nb,
+                                               candidates ? d_cand.p : nullptr, n_cand, d_scores.p);
+        if (n_pos_of > 0)
+            mask_ignored_kernel<<<nb, 128, 0, s>>>(d_ign_ptr.p, d_ign_idx.p, (int32_t)b_lo, nb, d_pos_of.p, n_pos_of, d_next.p, n_cand, d_scores.p);
+        MML_CUDA(cudaGetLastError());
+        MML_CUDA(cudaMemsetAsync(d_out_i.p, 0, sizeof(int32_t) * (size_t)nb * n_out, s));
+        MML_CUDA(cudaMemsetAsync(d_out_s.p, 0, sizeof(float) * (size_t)nb * n_out, s));
+        if (fast) {
+            const size_t smem = (size_t)SEL_T * n_out * 8;
+            select_topn_kernel<<<nb, SEL_T, smem, s>>>(d_scores.p, n_cand, n_out, candidates ? d_cand.p : nullptr,
+                                                       d_out_i.p, d_out_s.p, d_out_c.p);
+            MML_CUDA(cudaGetLastError());
+            if (launches) *launches += 3;
+        } else {
+            const int64_t total = (int64_t)nb * n_cand;
+            rank_key_kernel<<<grid_n(total), 256, 0, s>>>(d_scores.p, total, key.p, val.p);
+            MML_CUDA(cudaGetLastError());
+            MML_TRY(radix_sort_pairs(key.p, val.p, k2.p, v2.p, total, 32, s));          // by score desc, stable in position
+            rank_user_key_kernel<<<grid_n(total), 256, 0, s>>>(val.p, total, n_cand, key.p);
+            MML_CUDA(cudaGetLastError());
+            MML_TRY(radix_sort_pairs(key.p, val.p, k2.p, v2.p, total, bits_for((uint32_t)std::max(nb - 1, 1)), s));   // by user, stable
+            rank_emit_kernel<<<nb, 256, 0, s>>>(val.p, d_scores.p, n_cand, n_out, candidates ? d_cand.p : nullptr,
+                                                d_out_i.p, d_out_s.p, d_out_c.p);
+            MML_CUDA(cudaGetLastError());
+            if (launches) *launches += 16;
+        }
+        MML_CUDA(cudaMemcpyAsync(out_items + (size_t)b_lo * n_out, d_out_i.p, sizeof(int32_t) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaMemcpyAsync(out_scores + (size_t)b_lo * n_out, d_out_s.p, sizeof(float) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaMemcpyAsync(out_counts + b_lo, d_out_c.p, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaStreamSynchronize(s));
+    }
+    return MML_OK;
+}
+
+}  // namespace mml
+
+using namespace mml;
+
+extern "C" int32_t mml_topn_mf(mml_ctx* hctx, const float* user_factors, int32_t n_model_users,
+                               const float* item_factors, int32_t n_model_items, int32_t k,
+                               const int32_t* users, int64_t n_users, int32_t n,
+                               const int32_t* candidates, int64_t n_cand,
+                               const int64_t* ignore_ptr, const int32_t* ignore_idx,
+                               int32_t* out_items, float* out_scores, int32_t* out_counts)
+{
+    MML_CHECK(hctx && user_factors && item_factors && (n_users == 0 || (users && out_items && out_scores && out_counts)),
+              MML_ERR_ARG, "mml_topn_mf: NULL argument");
+    MML_CHECK(k >= 1 && n_model_users >= 0 && n_model_items >= 0 && n_users >= 0 && (n > 0 || n == -1), MML_ERR_ARG,
+              "mml_topn_mf: bad sizes (n must be > 0 or -1)");
+    Ctx* ctx = ctx_of(hctx);
+    MML_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    DevBuf<float> dU, dV;
+    MML_TRY(dU.alloc((size_t)n_model_users * k)); MML_TRY(dV.alloc((size_t)n_model_items * k));
+    MML_CUDA(cudaMemcpyAsync(dU.p, user_factors, sizeof(float) * (size_t)n_model_users * k, cudaMemcpyHostToDevice, s));
+    MML_CUDA(cudaMemcpyAsync(dV.p, item_factors, sizeof(float) * (size_t)n_model_items * k, cudaMemcpyHostToDevice, s));
+    return topn_device(ctx, dU.p, n_model_users, dV.p, n_model_items, k, users, n_users, n, candidates, n_cand,
+                       ignore_ptr, ignore_idx, out_items, out_scores, out_counts, nullptr);
+}

@@ -231,3 +231,124 @@ class SgdModel:
             self.close()
         except Exception:
             pass
+
+
+def _ignore_csr(ignore_lists, n_users):
+    """list of per-user id arrays -> (ptr int64, idx int32) or (None, None)."""
+    if ignore_lists is None:
+        return None, None
+    ptr = np.zeros(n_users + 1, np.int64)
+    for b, lst in enumerate(ignore_lists):
+        ptr[b + 1] = ptr[b] + len(lst)
+    idx = np.concatenate([np.asarray(l, np.int32) for l in ignore_lists]) if ptr[-1] > 0 else np.zeros(1, np.int32)
+    return ptr, np.ascontiguousarray(idx, np.int32)
+
+
+def _topn_outputs(n_users, n, n_cand):
+    n_out = n_cand if n < 0 else min(n, n_cand)
+    return (np.zeros((n_users, max(n_out, 1)), np.int32), np.zeros((n_users, max(n_out, 1)), np.float32),
+            np.zeros(max(n_users, 1), np.int32), n_out)
+
+
+def topn_mf(ctx, U, V, users, n=-1, candidates=None, ignore_lists=None):
+    """Recommender.Recommend for a batch of users on item-MF factors. Returns a list of (items, scores) per user."""
+    U, V = _f32(U), _f32(V)
+    users = _i32(users)
+    cand = _i32(candidates)
+    n_cand = V.shape[0] if cand is None else cand.shape[0]
+    oi, os_, oc, n_out = _topn_outputs(users.shape[0], n, n_cand)
+    ptr, idx = _ignore_csr(ignore_lists, users.shape[0])
+    check(ctx.lib.mml_topn_mf(ctx.h, U, U.shape[0], V, V.shape[0], U.shape[1], users, users.shape[0], int(n),
+                              cand, n_cand, ptr, idx, oi, os_, oc))
+    return [(oi[b, :oc[b]].copy(), os_[b, :oc[b]].copy()) for b in range(users.shape[0])]
+
+
+class DeviceFeedback:
+    """PosOnlyFeedback resident in HBM: user and item matrices as CSR, duplicate events collapsed."""
+
+    def __init__(self, ctx, users, items, max_user=None, max_item=None):
+        self.ctx, self.lib = ctx, ctx.lib
+        users, items = _i32(users), _i32(items)
+        n = int(users.shape[0])
+        self.max_user = (int(users.max()) if n else -1) if max_user is None else int(max_user)
+        self.max_item = (int(items.max()) if n else -1) if max_item is None else int(max_item)
+        h = C.c_void_p()
+        check(self.lib.mml_feedback_create(ctx.h, users, items, n, self.max_user, self.max_item, C.byref(h)))
+        self.h = h
+
+    @property
+    def nnz(self):
+        v = C.c_int64()
+        check(self.lib.mml_feedback_nnz(self.h, C.byref(v)))
+        return v.value
+
+    def csr(self, by_item=False):
+        rows = (self.max_item if by_item else self.max_user) + 1
+        ptr = np.zeros(rows + 1, np.int64)
+        cols = np.zeros(max(self.nnz, 1), np.int32)
+        check(self.lib.mml_feedback_csr(self.h, int(by_item), ptr, cols))
+        return ptr, cols[:self.nnz]
+
+    def close(self):
+        if self.h:
+            self.lib.mml_feedback_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class WrmfModel:
+    def __init__(self, ctx, feedback, num_factors=10, alpha=1.0, regularization=0.015):
+        self.ctx, self.fb, self.lib = ctx, feedback, ctx.lib
+        self.k = int(num_factors)
+        p = _capi.WrmfParams(self.k, float(alpha), float(regularization))
+        h = C.c_void_p()
+        check(self.lib.mml_wrmf_create(ctx.h, feedback.h, C.byref(p), C.byref(h)))
+        self.h = h
+        self.n_users, self.n_items = feedback.max_user + 1, feedback.max_item + 1
+
+    def set_model(self, U, V):
+        U, V = _f32(U), _f32(V)
+        assert U.shape == (self.n_users, self.k) and V.shape == (self.n_items, self.k)
+        check(self.lib.mml_wrmf_set_model(self.h, U, V))
+
+    def init_model(self, seed, mean=0.0, stddev=0.1):
+        check(self.lib.mml_wrmf_init_model(self.h, int(seed), float(mean), float(stddev)))
+
+    def get_model(self):
+        U = np.zeros((self.n_users, self.k), np.float32)
+        V = np.zeros((self.n_items, self.k), np.float32)
+        check(self.lib.mml_wrmf_get_model(self.h, U, V))
+        return U, V
+
+    def iterate(self):
+        check(self.lib.mml_wrmf_iterate(self.h))
+
+    def stats(self):
+        n, ms = C.c_int64(), C.c_float()
+        check(self.lib.mml_wrmf_stats(self.h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def recommend(self, users, n=-1, candidates=None, ignore_lists=None):
+        users = _i32(users)
+        cand = _i32(candidates)
+        n_cand = self.n_items if cand is None else cand.shape[0]
+        oi, os_, oc, n_out = _topn_outputs(users.shape[0], n, n_cand)
+        ptr, idx = _ignore_csr(ignore_lists, users.shape[0])
+        check(self.lib.mml_wrmf_recommend(self.h, users, users.shape[0], int(n), cand, n_cand, ptr, idx, oi, os_, oc))
+        return [(oi[b, :oc[b]].copy(), os_[b, :oc[b]].copy()) for b in range(users.shape[0])]
+
+    def close(self):
+        if self.h:
+            self.lib.mml_wrmf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,133 @@
+"""WRMF ALS and Recommend() on the device against the CPU oracle (ItemRecommendation/WRMF.cs, Recommender.cs)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from mymedialite_b200 import engine
+    ctx = engine.Context(0)
+    yield engine, ctx
+    ctx.close()
+
+
+def events(n_users, n_items, n, seed, dup=0.1):
+    rs = np.random.RandomState(seed)
+    u = rs.randint(0, n_users, n).astype(np.int32)
+    i = (rs.zipf(1.5, n) % n_items).astype(np.int32)
+    m = int(n * dup)                       # repeated events must collapse (SparseBooleanMatrix rows are sets)
+    u = np.concatenate([u, u[:m]]); i = np.concatenate([i, i[:m]])
+    p = rs.permutation(u.size)
+    return u[p], i[p]
+
+
+def test_feedback_known_answers(eng):
+    """TestUtils.CreatePosOnlyFeedback (src/Tests/TestUtils.cs:58-72): {(0,0),(0,1),(1,0),(1,2)} + a duplicate."""
+    engine, ctx = eng
+    u = np.array([0, 0, 1, 1, 0], np.int32); i = np.array([0, 1, 0, 2, 1], np.int32)
+    f = engine.DeviceFeedback(ctx, u, i, max_user=2, max_item=3)
+    assert f.nnz == 4
+    ptr, cols = f.csr(False)
+    assert list(ptr) == [0, 2, 4, 4] and list(cols) == [0, 1, 0, 2]
+    ptr, rows = f.csr(True)
+    assert list(ptr) == [0, 2, 3, 4, 4] and list(rows) == [0, 1, 0, 1]
+
+
+@pytest.mark.parametrize("nu,ni,n,seed", [(300, 200, 5000, 1), (5000, 900, 120000, 2)])
+def test_feedback_csr_matches_oracle(eng, nu, ni, n, seed):
+    engine, ctx = eng
+    u, i = events(nu, ni, n, seed)
+    f = engine.DeviceFeedback(ctx, u, i, max_user=nu, max_item=ni - 1)      # user nu has no events
+    optr, ocols = O.feedback_csr(u, i, nu)
+    ptr, cols = f.csr(False)
+    assert f.nnz == ocols.size and np.array_equal(ptr, optr)
+    for r in range(nu + 1):                                                  # rows are sets: compare as sets
+        assert np.array_equal(np.sort(ocols[optr[r]:optr[r + 1]]), cols[ptr[r]:ptr[r + 1]])
+    optr, ocols = O.feedback_csr(i, u, ni - 1)
+    ptr, rows = f.csr(True)
+    assert np.array_equal(ptr, optr)
+    for r in range(ni):
+        assert np.array_equal(np.sort(ocols[optr[r]:optr[r + 1]]), rows[ptr[r]:ptr[r + 1]])
+
+
+@pytest.mark.parametrize("k,alpha,reg", [(10, 1.0, 0.015), (64, 2.0, 0.1), (128, 1.0, 0.015), (150, 0.5, 0.015)])
+def test_wrmf_iterate_matches_oracle(eng, k, alpha, reg):
+    """north_star gate: ALS factor rows within 1e-4 relative (fp32) of the reference arithmetic."""
+    engine, ctx = eng
+    nu, ni = 400, 150
+    u, i = events(nu - 10, ni, 9000, k)                                  # the last 10 users have no events
+    f = engine.DeviceFeedback(ctx, u, i, max_user=nu - 1, max_item=ni - 1)
+    rng = O.Random(3)
+    U = rng.init_normal(nu * k).reshape(nu, k); V = rng.init_normal(ni * k).reshape(ni, k)   # MF.cs:56-57 draw order
+    m = engine.WrmfModel(ctx, f, k, alpha, reg)
+    m.set_model(U, V)
+    uptr, ucols = O.feedback_csr(u, i, nu - 1)
+    iptr, irows = O.feedback_csr(i, u, ni - 1)
+    Uo, Vo = U.copy(), V.copy()
+    for _ in range(2):
+        m.iterate()
+        O.wrmf_optimize(uptr, ucols, Uo, Vo, alpha, reg)
+        O.wrmf_optimize(iptr, irows, Vo, Uo, alpha, reg)
+    Ug, Vg = m.get_model()
+    for got, want in ((Ug, Uo), (Vg, Vo)):
+        scale = np.abs(want).max(axis=1, keepdims=True) + 1e-12
+        assert (np.abs(got - want) / scale).max() < 1e-4
+    empty = np.flatnonzero(np.diff(uptr) == 0)
+    assert empty.size > 0 and np.all(Ug[empty] == 0)                     # HCp = 0 => the row is exactly zero
+
+
+def _oracle_lists(U, V, users, n, candidates, ignore_lists):
+    out = []
+    for b, usr in enumerate(users):
+        out.append(O.recommend_mf(U, V, int(usr), n, candidates, None if ignore_lists is None else ignore_lists[b]))
+    return out
+
+
+@pytest.mark.parametrize("n", [-1, 1, 10, 32, 50])
+@pytest.mark.parametrize("k", [10, 128])
+def test_topn_is_bit_exact(eng, n, k):
+    """Item indices, order (score desc, candidate position asc) and fp32 scores equal the reference's."""
+    engine, ctx = eng
+    rs = np.random.RandomState(n + k)
+    nu, ni = 90, 333
+    U = (rs.randn(nu, k) * 0.1).astype(np.float32); V = (rs.randn(ni, k) * 0.1).astype(np.float32)
+    V[7] = V[3]; V[200] = V[3]                                          # exact score ties -> position decides
+    U[5] = 0                                                              # a whole row of ties
+    users = np.array([0, 5, 17, 89, 5, 120], np.int32)                    # repeated user, user outside the model
+    cand = rs.permutation(ni + 4)[:300].astype(np.int32)                  # shuffled (Eval/Items.cs:94), some ids outside the model
+    ign = [rs.choice(ni, 25, replace=False).astype(np.int32) for _ in users]
+    got = engine.topn_mf(ctx, U, V, users, n, cand, ign)
+    want = _oracle_lists(U, V, users, n, cand, ign)
+    for (gi, gs), (wi, ws) in zip(got, want):
+        assert np.array_equal(gi, wi)
+        assert np.array_equal(gs.view(np.uint32), ws.view(np.uint32))
+    # default candidates = every item, no ignore list
+    got = engine.topn_mf(ctx, U, V, users[:3], n)
+    want = _oracle_lists(U, V, users[:3], n, None, None)
+    for (gi, gs), (wi, ws) in zip(got, want):
+        assert np.array_equal(gi, wi) and np.array_equal(gs.view(np.uint32), ws.view(np.uint32))
+
+
+def test_wrmf_recommend_after_training(eng):
+    """The WritePredictions loop (ItemRecommendation/Extensions.cs:75-85): ignore = the user's training items."""
+    engine, ctx = eng
+    nu, ni, k = 250, 120, 32
+    u, i = events(nu, ni, 6000, 9)
+    f = engine.DeviceFeedback(ctx, u, i, max_user=nu - 1, max_item=ni - 1)
+    m = engine.WrmfModel(ctx, f, k)
+    m.init_model(5)
+    for _ in range(3):
+        m.iterate()
+    U, V = m.get_model()
+    ptr, cols = f.csr(False)
+    users = np.arange(0, nu, 7, dtype=np.int32)
+    ign = [cols[ptr[x]:ptr[x + 1]] for x in users]
+    got = m.recommend(users, 10, None, ign)
+    want = _oracle_lists(U, V, users, 10, None, ign)
+    for b, ((gi, gs), (wi, ws)) in enumerate(zip(got, want)):
+        assert np.array_equal(gi, wi) and np.array_equal(gs.view(np.uint32), ws.view(np.uint32))
+        assert not set(gi) & set(ign[b])
