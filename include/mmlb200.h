@@ -153,6 +153,8 @@ int32_t mml_sgd_init_model(mml_sgd* m, uint64_t seed, double init_mean, double i
 int32_t mml_sgd_get_model(mml_sgd* m, float* user_factors, float* item_factors,
                           float* user_bias, float* item_bias, float* global_bias, float* current_learnrate);
 int32_t mml_sgd_set_learnrate(mml_sgd* m, float current_learnrate);
+/* LoadModel (BiasedMatrixFactorization.cs:353-402): the rating scale and global bias come from the model file. */
+int32_t mml_sgd_set_scale(mml_sgd* m, float min_rating, float max_rating, float global_bias);
 /* Iterate() (BiasedMatrixFactorization.cs:197-222 / MatrixFactorization.cs:135-138): one epoch +
  * UpdateLearnRate. DSGD schedule: subepoch_sequence (host, G entries, may be NULL = 0..G-1) is the
  * shuffled sub-epoch order of :210-211. Serial schedule: random_index (host, n_index entries) is

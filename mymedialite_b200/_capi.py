@@ -82,6 +82,7 @@ SIGNATURES = {
     "mml_sgd_init_model": (C.c_int32, [vp, C.c_uint64, C.c_double, C.c_double]),
     "mml_sgd_get_model": (C.c_int32, [vp, of32p, of32p, of32p, of32p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "mml_sgd_set_learnrate": (C.c_int32, [vp, C.c_float]),
+    "mml_sgd_set_scale": (C.c_int32, [vp, C.c_float, C.c_float, C.c_float]),
     "mml_sgd_iterate": (C.c_int32, [vp, oi32p, oi32p, C.c_int64]),
     "mml_sgd_invalidate_index": (C.c_int32, [vp]),
     "mml_sgd_iterate_indices": (C.c_int32, [vp, oi32p, C.c_int64, C.c_int32, C.c_int32]),

@@ -1725,6 +1725,14 @@ extern "C" int32_t mml_sgd_set_learnrate(mml_sgd* h, float lr)
     return MML_OK;
 }
 
+extern "C" int32_t mml_sgd_set_scale(mml_sgd* h, float min_rating, float max_rating, float global_bias)
+{
+    MML_CHECK(h, MML_ERR_ARG, "NULL argument");
+    h->m.min_rating = min_rating; h->m.max_rating = max_rating; h->m.range = max_rating - min_rating;
+    h->m.global_bias = global_bias;
+    return MML_OK;
+}
+
 extern "C" int32_t mml_sgd_invalidate_index(mml_sgd* h)
 {
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
