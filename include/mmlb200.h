@@ -206,6 +206,15 @@ int32_t mml_topn_mf(mml_ctx* ctx, const float* user_factors, int32_t n_model_use
                     const int64_t* ignore_ptr, const int32_t* ignore_idx,
                     int32_t* out_items, float* out_scores, int32_t* out_counts);
 
+/* Engine knob (not a reference option): which scoring path Recommend() uses. AUTO = tcgen05 TF32 scoring with the
+ * top-k selection fused into the GEMM epilogue, finalists re-scored exactly (n <= 16, num_factors <= 128, distinct
+ * candidates), exact CUDA-core scoring otherwise and for users whose candidate superset cannot be proven complete.
+ * Both paths return bit-identical results; EXACT / TENSOR force one of them (tests, benchmarks). */
+enum { MML_TOPN_AUTO = 0, MML_TOPN_EXACT = 1, MML_TOPN_TENSOR = 2 };
+int32_t mml_topn_set_mode(int32_t mode);
+/* Users served by each path in the last Recommend() call of this process and the device time of the tensor path. */
+int32_t mml_topn_last_stats(int64_t* users_tensor_path, int64_t* users_exact_path, float* tensor_path_ms);
+
 /* ---- WRMF ------------------------------------------------------------------------------------- */
 /* PosOnlyFeedback.UserMatrix / ItemMatrix (Data/PosOnlyFeedback.cs:35-83): duplicates collapse. */
 int32_t mml_feedback_create(mml_ctx* ctx, const int32_t* users, const int32_t* items, int64_t n,

@@ -95,6 +95,8 @@ SIGNATURES = {
     "mml_sgd_hot_items": (C.c_int32, [vp, C.POINTER(C.c_int64)]),
     "mml_topn_mf": (C.c_int32, [vp, f32p, C.c_int32, f32p, C.c_int32, C.c_int32, oi32p, C.c_int64, C.c_int32,
                                 oi32p, C.c_int64, oi64p, oi32p, i32p, f32p, i32p]),
+    "mml_topn_set_mode": (C.c_int32, [C.c_int32]),
+    "mml_topn_last_stats": (C.c_int32, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "mml_feedback_create": (C.c_int32, [vp, oi32p, oi32p, C.c_int64, C.c_int32, C.c_int32, PP]),
     "mml_feedback_destroy": (C.c_int32, [vp]),
     "mml_feedback_nnz": (C.c_int32, [vp, C.POINTER(C.c_int64)]),
@@ -109,6 +111,8 @@ SIGNATURES = {
     "mml_wrmf_recommend": (C.c_int32, [vp, oi32p, C.c_int64, C.c_int32, oi32p, C.c_int64, oi64p, oi32p, i32p, f32p, i32p]),
     "mml_sgd_schedule_dump": (C.c_int32, [vp, oi32p, i32p, oi32p, oi32p, oi32p]),
 }
+
+TOPN_AUTO, TOPN_EXACT, TOPN_TENSOR = 0, 1, 2
 
 _lib = None
 

@@ -1248,8 +1248,8 @@ static int32_t evaluate_device(Sgd& m, const int32_t* d_u, const int32_t* d_i, c
     cudaStream_t s = m.ctx->stream;
     MML_TRY(sync_items(m));
     const int blocks = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(n * 32, EV_THREADS * 4), 1), 148 * 8);
-    DevBuf<double> part;
-    MML_TRY(part.alloc((size_t)blocks * 4));
+    DevBuf<double>& part = m.scr_part;
+    if (part.n < (size_t)blocks * 4) MML_TRY(part.alloc((size_t)148 * 8 * 4));
     evaluate_kernel<<<blocks, EV_THREADS, 0, s>>>(make_pred_args(m), d_u, d_i, d_v, n, m.p.loss, part.p);
     MML_CUDA(cudaGetLastError());
     m.launches++;
@@ -1798,8 +1798,10 @@ extern "C" int32_t mml_sgd_predict(mml_sgd* h, const int32_t* users, const int32
     MML_TRY(sync_items(m));   // collective on a multi-GPU context: every rank calls predict
     if (n == 0) return MML_OK;
     cudaStream_t s = m.ctx->stream;
-    DevBuf<int32_t> du, di; DevBuf<float> dout;
-    MML_TRY(du.alloc(n)); MML_TRY(di.alloc(n)); MML_TRY(dout.alloc(n));
+    DevBuf<int32_t>& du = m.scr_u; DevBuf<int32_t>& di = m.scr_i; DevBuf<float>& dout = m.scr_v;
+    if (du.n < (size_t)n) MML_TRY(du.alloc(n));
+    if (di.n < (size_t)n) MML_TRY(di.alloc(n));
+    if (dout.n < (size_t)n) MML_TRY(dout.alloc(n));
     MML_CUDA(cudaMemcpyAsync(du.p, users, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
     MML_CUDA(cudaMemcpyAsync(di.p, items, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
     predict_kernel<<<grid_n(n * 32), 256, 0, s>>>(make_pred_args(m), du.p, di.p, n, dout.p);
@@ -1818,8 +1820,10 @@ extern "C" int32_t mml_sgd_evaluate(mml_sgd* h, const int32_t* users, const int3
     MML_CHECK(n > 0 || m.R > 1, MML_ERR_ARG, "mml_sgd_evaluate: empty test set");   // Eval/Ratings.cs:98-99 returns null
     MML_CUDA(cudaSetDevice(m.ctx->device));
     cudaStream_t s = m.ctx->stream;
-    DevBuf<int32_t> du, di; DevBuf<float> dv;
-    MML_TRY(du.alloc(n)); MML_TRY(di.alloc(n)); MML_TRY(dv.alloc(n));
+    DevBuf<int32_t>& du = m.scr_u; DevBuf<int32_t>& di = m.scr_i; DevBuf<float>& dv = m.scr_v;
+    if (du.n < (size_t)n) MML_TRY(du.alloc(n));
+    if (di.n < (size_t)n) MML_TRY(di.alloc(n));
+    if (dv.n < (size_t)n) MML_TRY(dv.alloc(n));
     MML_CUDA(cudaMemcpyAsync(du.p, users, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
     MML_CUDA(cudaMemcpyAsync(di.p, items, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
     MML_CUDA(cudaMemcpyAsync(dv.p, values, sizeof(float) * n, cudaMemcpyHostToDevice, s));

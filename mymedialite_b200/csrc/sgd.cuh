@@ -56,6 +56,11 @@ struct Sgd {
     DevBuf<uint32_t> flags;            // persistent kernel: per-CTA progress counters
     uint32_t epoch_base = 0;
 
+    // grow-only scratch of Evaluate()/Predict() (no cudaMalloc/cudaFree in the per-epoch find-iter loop)
+    DevBuf<int32_t> scr_u, scr_i;
+    DevBuf<float> scr_v;
+    DevBuf<double> scr_part;
+
     // serial schedule: cached RandomIndex
     DevBuf<int32_t> d_index;
     int64_t n_index = -1;

@@ -224,8 +224,8 @@ __global__ void rank_emit_kernel(const uint32_t* __restrict__ val, const float* 
     if (threadIdx.x == 0) out_counts[b] = s_cnt;     // qualifying entries sort first, so they are rows 0 .. count-1
 }
 
-// d_U / d_V: model on the device. All other pointers: host.
-int32_t topn_device(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
+// d_U / d_V: model on the device. All other pointers: host. Exact scoring on the CUDA cores.
+static int32_t topn_exact_device(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
                     const int32_t* users, int64_t n_users, int32_t n,
                     const int32_t* candidates, int64_t n_cand,
                     const int64_t* ignore_ptr, const int32_t* ignore_idx,
@@ -313,9 +313,142 @@ int32_t topn_device(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
     return MML_OK;
 }
 
+bool topn_tc_eligible(int32_t k, int32_t n, int64_t n_cand);
+int32_t topn_tc_batch(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
+                      const int32_t* d_users, int32_t n_users, int32_t n, int32_t n_out,
+                      const int32_t* d_cand, int32_t n_cand,
+                      const int64_t* d_ign_ptr, int32_t* d_ign_idx, int64_t n_ign,
+                      int32_t* d_out_items, float* d_out_scores, int32_t* d_out_counts, uint8_t* d_redo,
+                      int64_t* launches);
+
+static int g_topn_mode = 0;                         // MML_TOPN_AUTO
+static int64_t g_stat_tc = 0, g_stat_exact = 0;     // users served by each path in the last call
+static float g_stat_ms = 0.f;
+
+// Recommend() for a user batch. Tensor-core path (topn_tc.cu) when the request qualifies; users whose candidate
+// superset it cannot prove complete, and requests outside its envelope, run on the exact CUDA-core path.
+int32_t topn_device(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
+                    const int32_t* users, int64_t n_users, int32_t n,
+                    const int32_t* candidates, int64_t n_cand,
+                    const int64_t* ignore_ptr, const int32_t* ignore_idx,
+                    int32_t* out_items, float* out_scores, int32_t* out_counts, int64_t* launches)
+{
+    g_stat_tc = 0; g_stat_exact = 0; g_stat_ms = 0.f;
+    if (n_users == 0) return MML_OK;
+    if (!candidates) n_cand = n_model_items;
+    bool tc = g_topn_mode != MML_TOPN_EXACT && topn_tc_eligible(k, n, n_cand) && n_cand < ((int64_t)1 << 31);
+    if (tc && candidates) {   // a candidate listed twice is scored (and may be returned) twice: exact path only
+        std::vector<uint8_t> seen((size_t)std::max(n_model_items, 1), 0);
+        for (int64_t c = 0; c < n_cand && tc; c++) {
+            const int32_t id = candidates[c];
+            if (id < 0 || id >= n_model_items) continue;
+            if (seen[id]) tc = false;
+            seen[id] = 1;
+        }
+    }
+    MML_CHECK(tc || g_topn_mode != MML_TOPN_TENSOR, MML_ERR_UNSUPPORTED,
+              "topn: request is outside the tensor-core path (n <= 16, num_factors <= 128, distinct candidates)");
+    if (!tc) {
+        g_stat_exact = n_users;
+        return topn_exact_device(ctx, d_U, n_model_users, d_V, n_model_items, k, users, n_users, n, candidates, n_cand,
+                                 ignore_ptr, ignore_idx, out_items, out_scores, out_counts, launches);
+    }
+    cudaStream_t s = ctx->stream;
+    const int32_t n_out = (int32_t)std::min<int64_t>(n, n_cand);
+    const int64_t n_ign = (ignore_ptr && ignore_idx) ? ignore_ptr[n_users] : 0;
+    DevBuf<int32_t> d_cand, d_ign_idx; DevBuf<int64_t> d_ign_ptr;
+    if (candidates) {
+        MML_TRY(d_cand.alloc(n_cand));
+        MML_CUDA(cudaMemcpyAsync(d_cand.p, candidates, sizeof(int32_t) * n_cand, cudaMemcpyHostToDevice, s));
+    }
+    cudaEvent_t e0, e1;
+    MML_CUDA(cudaEventCreate(&e0)); MML_CUDA(cudaEventCreate(&e1));
+    MML_CUDA(cudaEventRecord(e0, s));
+    std::vector<int64_t> redo_users;
+    const int64_t B = 1 << 20;                       // users per pass (staging panels: B * 128 floats)
+    std::vector<uint8_t> h_redo;
+    std::vector<int64_t> ptr_local;
+    for (int64_t b_lo = 0; b_lo < n_users; b_lo += B) {
+        const int32_t nb = (int32_t)std::min<int64_t>(B, n_users - b_lo);
+        DevBuf<int32_t> d_users, d_oi, d_oc; DevBuf<float> d_os; DevBuf<uint8_t> d_redo;
+        MML_TRY(d_users.alloc(nb)); MML_TRY(d_oi.alloc((size_t)nb * n_out)); MML_TRY(d_os.alloc((size_t)nb * n_out));
+        MML_TRY(d_oc.alloc(nb)); MML_TRY(d_redo.alloc(nb));
+        MML_CUDA(cudaMemcpyAsync(d_users.p, users + b_lo, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s));
+        MML_CUDA(cudaMemsetAsync(d_oi.p, 0, sizeof(int32_t) * (size_t)nb * n_out, s));
+        MML_CUDA(cudaMemsetAsync(d_os.p, 0, sizeof(float) * (size_t)nb * n_out, s));
+        int64_t nib = 0;
+        if (n_ign > 0) {
+            const int64_t i_lo = ignore_ptr[b_lo];
+            nib = ignore_ptr[b_lo + nb] - i_lo;
+            ptr_local.resize((size_t)nb + 1);
+            for (int32_t t = 0; t <= nb; t++) ptr_local[t] = ignore_ptr[b_lo + t] - i_lo;
+            MML_TRY(d_ign_ptr.alloc((size_t)nb + 1)); MML_TRY(d_ign_idx.alloc(nib));
+            MML_CUDA(cudaMemcpyAsync(d_ign_ptr.p, ptr_local.data(), sizeof(int64_t) * ((size_t)nb + 1), cudaMemcpyHostToDevice, s));
+            if (nib > 0) MML_CUDA(cudaMemcpyAsync(d_ign_idx.p, ignore_idx + i_lo, sizeof(int32_t) * (size_t)nib, cudaMemcpyHostToDevice, s));
+        }
+        MML_TRY(topn_tc_batch(ctx, d_U, n_model_users, d_V, n_model_items, k, d_users.p, nb, n, n_out,
+                              candidates ? d_cand.p : nullptr, (int32_t)n_cand,
+                              nib > 0 ? d_ign_ptr.p : nullptr, d_ign_idx.p, nib,
+                              d_oi.p, d_os.p, d_oc.p, d_redo.p, launches));
+        h_redo.resize(nb);
+        MML_CUDA(cudaMemcpyAsync(out_items + (size_t)b_lo * n_out, d_oi.p, sizeof(int32_t) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaMemcpyAsync(out_scores + (size_t)b_lo * n_out, d_os.p, sizeof(float) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaMemcpyAsync(out_counts + b_lo, d_oc.p, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaMemcpyAsync(h_redo.data(), d_redo.p, nb, cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaStreamSynchronize(s));
+        for (int32_t t = 0; t < nb; t++) if (h_redo[t]) redo_users.push_back(b_lo + t);
+    }
+    MML_CUDA(cudaEventRecord(e1, s));
+    MML_CUDA(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&g_stat_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    g_stat_tc = n_users - (int64_t)redo_users.size();
+    g_stat_exact = (int64_t)redo_users.size();
+    if (redo_users.empty()) return MML_OK;
+    // users the filter could not decide: exact path on the sub-batch, results scattered back
+    const size_t nr = redo_users.size();
+    std::vector<int32_t> ru(nr), ri(nr * (size_t)n_out), rc(nr), rign;
+    std::vector<float> rs(nr * (size_t)n_out);
+    std::vector<int64_t> rptr(nr + 1, 0);
+    for (size_t t = 0; t < nr; t++) {
+        ru[t] = users[redo_users[t]];
+        if (n_ign > 0) {
+            const int64_t lo = ignore_ptr[redo_users[t]], hi = ignore_ptr[redo_users[t] + 1];
+            rign.insert(rign.end(), ignore_idx + lo, ignore_idx + hi);
+            rptr[t + 1] = rptr[t] + (hi - lo);
+        }
+    }
+    if (rign.empty()) rign.push_back(0);
+    MML_TRY(topn_exact_device(ctx, d_U, n_model_users, d_V, n_model_items, k, ru.data(), (int64_t)nr, n, candidates, n_cand,
+                              n_ign > 0 ? rptr.data() : nullptr, n_ign > 0 ? rign.data() : nullptr,
+                              ri.data(), rs.data(), rc.data(), launches));
+    for (size_t t = 0; t < nr; t++) {
+        const size_t b = (size_t)redo_users[t];
+        memcpy(out_items + b * n_out, ri.data() + t * n_out, sizeof(int32_t) * n_out);
+        memcpy(out_scores + b * n_out, rs.data() + t * n_out, sizeof(float) * n_out);
+        out_counts[b] = rc[t];
+    }
+    return MML_OK;
+}
+
 }  // namespace mml
 
 using namespace mml;
+
+extern "C" int32_t mml_topn_set_mode(int32_t mode)
+{
+    MML_CHECK(mode >= MML_TOPN_AUTO && mode <= MML_TOPN_TENSOR, MML_ERR_ARG, "mml_topn_set_mode: unknown mode %d", mode);
+    g_topn_mode = mode;
+    return MML_OK;
+}
+
+extern "C" int32_t mml_topn_last_stats(int64_t* users_tensor_path, int64_t* users_exact_path, float* tensor_path_ms)
+{
+    if (users_tensor_path) *users_tensor_path = g_stat_tc;
+    if (users_exact_path) *users_exact_path = g_stat_exact;
+    if (tensor_path_ms) *tensor_path_ms = g_stat_ms;
+    return MML_OK;
+}
 
 extern "C" int32_t mml_topn_mf(mml_ctx* hctx, const float* user_factors, int32_t n_model_users,
                                const float* item_factors, int32_t n_model_items, int32_t k,

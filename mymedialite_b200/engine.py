@@ -250,6 +250,17 @@ def _topn_outputs(n_users, n, n_cand):
             np.zeros(max(n_users, 1), np.int32), n_out)
 
 
+def topn_set_mode(mode):
+    """_capi.TOPN_AUTO (default) / TOPN_EXACT (CUDA cores only) / TOPN_TENSOR (tcgen05 path or error)."""
+    check(_capi.load().mml_topn_set_mode(int(mode)))
+
+
+def topn_last_stats():
+    a, b, ms = C.c_int64(), C.c_int64(), C.c_float()
+    check(_capi.load().mml_topn_last_stats(C.byref(a), C.byref(b), C.byref(ms)))
+    return dict(users_tensor_path=a.value, users_exact_path=b.value, tensor_path_ms=ms.value)
+
+
 def topn_mf(ctx, U, V, users, n=-1, candidates=None, ignore_lists=None):
     """Recommender.Recommend for a batch of users on item-MF factors. Returns a list of (items, scores) per user."""
     U, V = _f32(U), _f32(V)
