@@ -1,0 +1,215 @@
+// CudaBiasedMatrixFactorization.cs / CudaMatrixFactorization -- the reference's MatrixFactorization and
+// BiasedMatrixFactorization surface (RatingPrediction/MatrixFactorization.cs:35-418,
+// RatingPrediction/BiasedMatrixFactorization.cs:61-563) on libmmlb200.so. Same property names and defaults,
+// same ToString() shape, same model-file layout; one added property, NumGpus.
+// Compile into MyMediaLite.dll so that "CudaBiasedMatrixFactorization".CreateRatingPredictor() (Extensions.cs:170-182)
+// finds it. Not compiled here: no .NET/Mono toolchain in this image (INTEGRATION.md).
+using System;
+using System.Collections.Generic;
+using System.Globalization;
+using System.IO;
+using System.Linq;
+using MyMediaLite.Data;
+using MyMediaLite.DataType;
+using MyMediaLite.Eval;
+using MyMediaLite.IO;
+using MyMediaLite.Native;
+
+namespace MyMediaLite.RatingPrediction
+{
+	/// <summary>MatrixFactorization on the GPU: r = global_bias + p_u . q_i, SGD (MatrixFactorization.cs:166-196)</summary>
+	public class CudaMatrixFactorization : RatingPredictor, IIterativeModel
+	{
+		/// <summary>the device model; shared by clones, replaced (never mutated in place) by Train()</summary>
+		protected MmlHandle model, dev_ratings;
+		protected readonly object gate = new object();
+
+		public float InitMean { get; set; }
+		public float InitStdDev { get; set; }
+		public uint NumFactors { get; set; }
+		public float LearnRate { get; set; }
+		public float Decay { get; set; }
+		public virtual float Regularization { get; set; }
+		public uint NumIter { get; set; }
+		/// <summary>GPUs of one host to train on (engine property; default 1)</summary>
+		public uint NumGpus { get; set; }
+
+		protected virtual bool Biased { get { return false; } }
+
+		public CudaMatrixFactorization()
+		{
+			// MatrixFactorization.cs:87-96
+			Regularization = 0.015f; LearnRate = 0.01f; Decay = 1.0f; NumIter = 30; InitStdDev = 0.1f; NumFactors = 10; NumGpus = 1;
+		}
+
+		/// <summary>IList -> int[]/float[] of length Count (StaticRatings exposes its arrays, Ratings/RatingsProxy do not)</summary>
+		protected static T[] AsArray<T>(IList<T> list, int count)
+		{
+			var a = list as T[];
+			if (a != null && a.Length == count) return a;
+			var r = new T[count];
+			for (int i = 0; i < count; i++) r[i] = list[i];
+			return r;
+		}
+
+		protected virtual MmlMfParams Params()
+		{
+			MmlMfParams p;
+			Mml.mml_mf_params_default(out p);
+			p.biased = Biased ? 1 : 0;
+			p.num_factors = (int) NumFactors; p.learn_rate = LearnRate; p.decay = Decay; p.regularization = Regularization;
+			p.schedule = Mml.SCHEDULE_SERIAL;
+			return p;
+		}
+
+		/// <summary>InitModel (MatrixFactorization.cs:99-116): draws come from MyMediaLite.Random in the reference's order</summary>
+		protected internal virtual void InitModel()
+		{
+			IntPtr ctx = Mml.Context(), r, m;
+			int n = ratings.Count;
+			Mml.Check(Mml.mml_ratings_create(ctx, AsArray(ratings.Users, n), AsArray(ratings.Items, n), AsArray(ratings.Values, n), n, MaxUserID, MaxItemID, out r));
+			dev_ratings = new MmlHandle(r, Mml.mml_ratings_destroy);
+			var p = Params();
+			Mml.Check(Mml.mml_sgd_create(ctx, r, ref p, null, null, out m));
+			model = new MmlHandle(m, Mml.mml_sgd_destroy);
+			var user_factors = new Matrix<float>(MaxUserID + 1, (int) NumFactors);
+			var item_factors = new Matrix<float>(MaxItemID + 1, (int) NumFactors);
+			user_factors.InitNormal(InitMean, InitStdDev);
+			item_factors.InitNormal(InitMean, InitStdDev);
+			Mml.Check(Mml.mml_sgd_set_model(m, user_factors.data, item_factors.data, null, null));   // rows without ratings are zeroed by the library
+		}
+
+		public override void Train()
+		{
+			lock (gate)
+			{
+				InitModel();
+				for (uint it = 0; it < NumIter; it++) Iterate();
+			}
+		}
+
+		public virtual void Iterate()
+		{
+			lock (gate)
+			{
+				var index = AsArray(ratings.RandomIndex, ratings.Count);
+				Mml.Check(Mml.mml_sgd_iterate(model.DangerousGetHandle(), null, index, index.Length));
+			}
+		}
+
+		public override float Predict(int user_id, int item_id)
+		{
+			var res = new float[1];
+			Mml.Check(Mml.mml_sgd_predict(model.DangerousGetHandle(), new int[] { user_id }, new int[] { item_id }, 1, res));
+			return res[0];
+		}
+
+		/// <summary>Eval.Ratings.Evaluate (Eval/Ratings.cs:96-139) in one device pass: RMSE, MAE, NMAE, CBD</summary>
+		public Dictionary<string, float> Evaluate(IRatings test)
+		{
+			int n = test.Count;
+			var r = new float[4];
+			Mml.Check(Mml.mml_sgd_evaluate(model.DangerousGetHandle(), AsArray(test.Users, n), AsArray(test.Items, n), AsArray(test.Values, n), n, r));
+			return new Dictionary<string, float> { { "RMSE", r[0] }, { "MAE", r[1] }, { "NMAE", r[2] }, { "CBD", r[3] } };
+		}
+
+		public virtual float ComputeObjective()
+		{
+			double v;
+			Mml.Check(Mml.mml_sgd_objective(model.DangerousGetHandle(), out v));
+			return (float) v;
+		}
+
+		public override void SaveModel(string filename)
+		{
+			var U = new float[(MaxUserID + 1) * NumFactors]; var V = new float[(MaxItemID + 1) * NumFactors];
+			float gb, lr;
+			Mml.Check(Mml.mml_sgd_get_model(model.DangerousGetHandle(), U, V, null, null, out gb, out lr));
+			using (StreamWriter writer = Model.GetWriter(filename, this.GetType(), "2.99"))
+			{
+				writer.WriteLine(gb.ToString(CultureInfo.InvariantCulture));
+				writer.WriteMatrix(new Matrix<float>(MaxUserID + 1, (int) NumFactors) { data = U });
+				writer.WriteMatrix(new Matrix<float>(MaxItemID + 1, (int) NumFactors) { data = V });
+			}
+		}
+
+		public override string ToString()
+		{
+			return string.Format(CultureInfo.InvariantCulture,
+				"{0} num_factors={1} regularization={2} learn_rate={3} learn_rate_decay={4} num_iter={5}",
+				this.GetType().Name, NumFactors, Regularization, LearnRate, Decay, NumIter);
+		}
+	}
+
+	/// <summary>BiasedMatrixFactorization on the GPU (BiasedMatrixFactorization.cs:61-563)</summary>
+	public class CudaBiasedMatrixFactorization : CudaMatrixFactorization
+	{
+		public float BiasReg { get; set; }
+		public float BiasLearnRate { get; set; }
+		public float RegU { get; set; }
+		public float RegI { get; set; }
+		public override float Regularization { set { base.Regularization = value; RegU = value; RegI = value; } }   // :97-104
+		public bool FrequencyRegularization { get; set; }
+		public OptimizationTarget Loss { get; set; }
+		public int MaxThreads { get; set; }
+		public bool BoldDriver { get; set; }
+		public bool NaiveParallelization { get; set; }
+
+		protected override bool Biased { get { return true; } }
+
+		public CudaBiasedMatrixFactorization() : base()
+		{
+			BiasReg = 0.01f; BiasLearnRate = 1.0f; MaxThreads = 1;   // :85-141
+		}
+
+		protected override MmlMfParams Params()
+		{
+			var p = base.Params();
+			p.bias_learn_rate = BiasLearnRate; p.bias_reg = BiasReg; p.reg_u = RegU; p.reg_i = RegI;
+			p.frequency_regularization = FrequencyRegularization ? 1 : 0;
+			p.loss = Loss == OptimizationTarget.MAE ? Mml.LOSS_MAE : (Loss == OptimizationTarget.LogisticLoss ? Mml.LOSS_LOGISTIC : Mml.LOSS_RMSE);
+			p.bold_driver = BoldDriver ? 1 : 0; p.max_threads = MaxThreads;
+			// MaxThreads > 1 selects the reference's DSGD block schedule (:178-184); on the GPU the worker groups are CTAs
+			p.schedule = MaxThreads > 1 ? Mml.SCHEDULE_DSGD : Mml.SCHEDULE_SERIAL;
+			return p;
+		}
+
+		public override void Iterate()
+		{
+			if (MaxThreads <= 1) { base.Iterate(); return; }
+			lock (gate)
+			{
+				int G, W; long rounds, staged;
+				Mml.Check(Mml.mml_sgd_strata_info(model.DangerousGetHandle(), out G, out W, out rounds, out staged));
+				var subepoch_sequence = Enumerable.Range(0, G).ToList();
+				subepoch_sequence.Shuffle();   // :210-211
+				Mml.Check(Mml.mml_sgd_iterate(model.DangerousGetHandle(), subepoch_sequence.ToArray(), null, 0));
+			}
+		}
+
+		public override void SaveModel(string filename)
+		{
+			int nu = MaxUserID + 1, ni = MaxItemID + 1, k = (int) NumFactors;
+			var U = new float[nu * k]; var V = new float[ni * k]; var bu = new float[nu]; var bi = new float[ni];
+			float gb, lr;
+			Mml.Check(Mml.mml_sgd_get_model(model.DangerousGetHandle(), U, V, bu, bi, out gb, out lr));
+			using (StreamWriter writer = Model.GetWriter(filename, this.GetType(), "2.99"))   // layout of :339-351
+			{
+				writer.WriteLine(gb.ToString(CultureInfo.InvariantCulture));
+				writer.WriteLine(min_rating.ToString(CultureInfo.InvariantCulture));
+				writer.WriteLine(max_rating.ToString(CultureInfo.InvariantCulture));
+				writer.WriteVector(bu);
+				writer.WriteMatrix(new Matrix<float>(nu, k) { data = U });
+				writer.WriteVector(bi);
+				writer.WriteMatrix(new Matrix<float>(ni, k) { data = V });
+			}
+		}
+
+		public override string ToString()
+		{
+			return string.Format(CultureInfo.InvariantCulture,
+				"{0} num_factors={1} bias_reg={2} reg_u={3} reg_i={4} frequency_regularization={5} learn_rate={6} bias_learn_rate={7} learn_rate_decay={8} num_iter={9} bold_driver={10} loss={11} max_threads={12} naive_parallelization={13}",
+				this.GetType().Name, NumFactors, BiasReg, RegU, RegI, FrequencyRegularization, LearnRate, BiasLearnRate, Decay, NumIter, BoldDriver, Loss, MaxThreads, NaiveParallelization);
+		}
+	}
+}

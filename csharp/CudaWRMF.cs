@@ -1,0 +1,125 @@
+// CudaWRMF.cs -- ItemRecommendation.WRMF (ItemRecommendation/WRMF.cs:56-180, MF.cs:37-196) on libmmlb200.so.
+// Compile into MyMediaLite.dll ("CudaWRMF".CreateItemRecommender(), Extensions.cs:216-228).
+// Not compiled here: no .NET/Mono toolchain in this image (INTEGRATION.md).
+using System;
+using System.Collections.Generic;
+using System.Globalization;
+using System.IO;
+using System.Linq;
+using MyMediaLite.Data;
+using MyMediaLite.DataType;
+using MyMediaLite.IO;
+using MyMediaLite.Native;
+
+namespace MyMediaLite.ItemRecommendation
+{
+	public class CudaWRMF : ItemRecommender, IIterativeModel
+	{
+		protected MmlHandle model, dev_feedback;
+		protected readonly object gate = new object();
+
+		public uint NumFactors { get; set; }
+		public uint NumIter { get; set; }
+		public double Alpha { get; set; }
+		public double Regularization { get; set; }
+		public double InitMean { get; set; }
+		public double InitStdDev { get; set; }
+		public uint NumGpus { get; set; }
+
+		public CudaWRMF()
+		{
+			NumFactors = 10; NumIter = 15; Alpha = 1; Regularization = 0.015; InitStdDev = 0.1; NumGpus = 1;   // WRMF.cs:56-65, MF.cs:37-48
+		}
+
+		protected virtual void InitModel()
+		{
+			IntPtr ctx = Mml.Context(), f, m;
+			int n = Feedback.Count;
+			var users = new int[n]; var items = new int[n];
+			for (int t = 0; t < n; t++) { users[t] = Feedback.Users[t]; items[t] = Feedback.Items[t]; }
+			Mml.Check(Mml.mml_feedback_create(ctx, users, items, n, MaxUserID, MaxItemID, out f));
+			dev_feedback = new MmlHandle(f, Mml.mml_feedback_destroy);
+			var p = new MmlWrmfParams { num_factors = (int) NumFactors, alpha = Alpha, regularization = Regularization };
+			Mml.Check(Mml.mml_wrmf_create(ctx, f, ref p, out m));
+			model = new MmlHandle(m, Mml.mml_wrmf_destroy);
+			var user_factors = new Matrix<float>(MaxUserID + 1, (int) NumFactors);   // MF.cs:51-58: user matrix first
+			var item_factors = new Matrix<float>(MaxItemID + 1, (int) NumFactors);
+			user_factors.InitNormal(InitMean, InitStdDev);
+			item_factors.InitNormal(InitMean, InitStdDev);
+			Mml.Check(Mml.mml_wrmf_set_model(m, user_factors.data, item_factors.data));
+		}
+
+		public override void Train()
+		{
+			lock (gate)
+			{
+				InitModel();
+				for (uint i = 0; i < NumIter; i++) Iterate();
+			}
+		}
+
+		/// <summary>WRMF.Iterate (WRMF.cs:68-73): user half-sweep, then item half-sweep</summary>
+		public virtual void Iterate()
+		{
+			lock (gate) Mml.Check(Mml.mml_wrmf_iterate(model.DangerousGetHandle()));
+		}
+
+		public override float Predict(int user_id, int item_id)
+		{
+			if (user_id > MaxUserID || item_id > MaxItemID) return float.MinValue;   // MF.cs:151-157
+			var r = Recommend(user_id, 1, null, new int[] { item_id });
+			return r.Count > 0 ? r[0].Item2 : float.MinValue;
+		}
+
+		/// <summary>Recommender.Recommend (Recommender.cs:52-103) for one user</summary>
+		public override IList<Tuple<int, float>> Recommend(int user_id, int n = -1, ICollection<int> ignore_items = null, ICollection<int> candidate_items = null)
+		{
+			return RecommendMany(new int[] { user_id }, n, ignore_items == null ? null : new ICollection<int>[] { ignore_items }, candidate_items)[0];
+		}
+
+		/// <summary>The all-users loop of Extensions.WritePredictions / Eval.Items.Evaluate in ONE device call
+		/// (tcgen05 scoring GEMM with fused top-k; exact re-scoring makes the result bit-identical to per-user Predict loops)</summary>
+		public IList<Tuple<int, float>>[] RecommendMany(IList<int> users, int n, IList<ICollection<int>> ignore_items, ICollection<int> candidate_items)
+		{
+			int[] cand = candidate_items == null ? Enumerable.Range(0, Math.Max(MaxItemID - 1, 0)).ToArray() : candidate_items.ToArray();   // Recommender.cs:57-58
+			int n_out = n < 0 ? cand.Length : Math.Min(n, cand.Length);
+			var u = users.ToArray();
+			long[] ptr = null; int[] idx = null;
+			if (ignore_items != null)
+			{
+				ptr = new long[u.Length + 1];
+				for (int b = 0; b < u.Length; b++) ptr[b + 1] = ptr[b] + (ignore_items[b] == null ? 0 : ignore_items[b].Count);
+				idx = new int[Math.Max(ptr[u.Length], 1)];
+				for (int b = 0; b < u.Length; b++) if (ignore_items[b] != null) ignore_items[b].CopyTo(idx, (int) ptr[b]);
+			}
+			var items = new int[Math.Max(u.Length * n_out, 1)]; var scores = new float[items.Length]; var counts = new int[u.Length];
+			Mml.Check(Mml.mml_wrmf_recommend(model.DangerousGetHandle(), u, u.Length, n, cand, cand.Length, ptr, idx, items, scores, counts));
+			var result = new IList<Tuple<int, float>>[u.Length];
+			for (int b = 0; b < u.Length; b++)
+			{
+				var list = new List<Tuple<int, float>>(counts[b]);
+				for (int r = 0; r < counts[b]; r++) list.Add(Tuple.Create(items[b * n_out + r], scores[b * n_out + r]));
+				result[b] = list;
+			}
+			return result;
+		}
+
+		public override void SaveModel(string filename)
+		{
+			int nu = MaxUserID + 1, ni = MaxItemID + 1, k = (int) NumFactors;
+			var U = new float[nu * k]; var V = new float[ni * k];
+			Mml.Check(Mml.mml_wrmf_get_model(model.DangerousGetHandle(), U, V));
+			using (StreamWriter writer = Model.GetWriter(filename, this.GetType(), "2.99"))   // MF.cs:160-168
+			{
+				writer.WriteMatrix(new Matrix<float>(nu, k) { data = U });
+				writer.WriteMatrix(new Matrix<float>(ni, k) { data = V });
+			}
+		}
+
+		public override string ToString()
+		{
+			return string.Format(CultureInfo.InvariantCulture, "{0} num_factors={1} regularization={2} alpha={3} num_iter={4}",
+				this.GetType().Name, NumFactors, Regularization, Alpha, NumIter);
+		}
+	}
+}

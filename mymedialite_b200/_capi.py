@@ -125,6 +125,12 @@ def load():
     if not os.path.exists(SO_PATH):
         raise ImportError("libmmlb200.so is missing at %s: build it with `python -m mymedialite_b200.build` "
                           "(there is no CPU fallback)" % SO_PATH)
+    # libmmlb200 needs libnccl.so.2. PyTorch bundles a newer NCCL under the same soname than the system one; whichever
+    # is loaded first serves both, and torch does not start on the older system build -- so let torch load its own first.
+    try:
+        import torch  # noqa: F401
+    except ImportError:
+        pass
     L = C.CDLL(SO_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(L, name)   # AttributeError if the library does not export a declared symbol

@@ -314,12 +314,10 @@ static int32_t topn_exact_device(Ctx* ctx, const float* d_U, int32_t n_model_use
 }
 
 bool topn_tc_eligible(int32_t k, int32_t n, int64_t n_cand);
-int32_t topn_tc_batch(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
-                      const int32_t* d_users, int32_t n_users, int32_t n, int32_t n_out,
-                      const int32_t* d_cand, int32_t n_cand,
-                      const int64_t* d_ign_ptr, int32_t* d_ign_idx, int64_t n_ign,
-                      int32_t* d_out_items, float* d_out_scores, int32_t* d_out_counts, uint8_t* d_redo,
-                      int64_t* launches);
+int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
+                    const int32_t* users, int64_t n_users, int32_t n, int32_t n_out, const int32_t* d_cand, int32_t n_cand,
+                    bool has_invalid_cand, const int64_t* ignore_ptr, const int32_t* ignore_idx,
+                    int32_t* out_items, float* out_scores, int32_t* out_counts, std::vector<int64_t>& redo_users, int64_t* launches);
 
 static int g_topn_mode = 0;                         // MML_TOPN_AUTO
 static int64_t g_stat_tc = 0, g_stat_exact = 0;     // users served by each path in the last call
@@ -337,11 +335,12 @@ int32_t topn_device(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
     if (n_users == 0) return MML_OK;
     if (!candidates) n_cand = n_model_items;
     bool tc = g_topn_mode != MML_TOPN_EXACT && topn_tc_eligible(k, n, n_cand) && n_cand < ((int64_t)1 << 31);
+    bool has_invalid = false;
     if (tc && candidates) {   // a candidate listed twice is scored (and may be returned) twice: exact path only
         std::vector<uint8_t> seen((size_t)std::max(n_model_items, 1), 0);
         for (int64_t c = 0; c < n_cand && tc; c++) {
             const int32_t id = candidates[c];
-            if (id < 0 || id >= n_model_items) continue;
+            if (id < 0 || id >= n_model_items) { has_invalid = true; continue; }
             if (seen[id]) tc = false;
             seen[id] = 1;
         }
@@ -356,7 +355,7 @@ int32_t topn_device(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
     cudaStream_t s = ctx->stream;
     const int32_t n_out = (int32_t)std::min<int64_t>(n, n_cand);
     const int64_t n_ign = (ignore_ptr && ignore_idx) ? ignore_ptr[n_users] : 0;
-    DevBuf<int32_t> d_cand, d_ign_idx; DevBuf<int64_t> d_ign_ptr;
+    DevBuf<int32_t> d_cand;
     if (candidates) {
         MML_TRY(d_cand.alloc(n_cand));
         MML_CUDA(cudaMemcpyAsync(d_cand.p, candidates, sizeof(int32_t) * n_cand, cudaMemcpyHostToDevice, s));
@@ -365,39 +364,8 @@ int32_t topn_device(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
     MML_CUDA(cudaEventCreate(&e0)); MML_CUDA(cudaEventCreate(&e1));
     MML_CUDA(cudaEventRecord(e0, s));
     std::vector<int64_t> redo_users;
-    const int64_t B = 1 << 20;                       // users per pass (staging panels: B * 128 floats)
-    std::vector<uint8_t> h_redo;
-    std::vector<int64_t> ptr_local;
-    for (int64_t b_lo = 0; b_lo < n_users; b_lo += B) {
-        const int32_t nb = (int32_t)std::min<int64_t>(B, n_users - b_lo);
-        DevBuf<int32_t> d_users, d_oi, d_oc; DevBuf<float> d_os; DevBuf<uint8_t> d_redo;
-        MML_TRY(d_users.alloc(nb)); MML_TRY(d_oi.alloc((size_t)nb * n_out)); MML_TRY(d_os.alloc((size_t)nb * n_out));
-        MML_TRY(d_oc.alloc(nb)); MML_TRY(d_redo.alloc(nb));
-        MML_CUDA(cudaMemcpyAsync(d_users.p, users + b_lo, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s));
-        MML_CUDA(cudaMemsetAsync(d_oi.p, 0, sizeof(int32_t) * (size_t)nb * n_out, s));
-        MML_CUDA(cudaMemsetAsync(d_os.p, 0, sizeof(float) * (size_t)nb * n_out, s));
-        int64_t nib = 0;
-        if (n_ign > 0) {
-            const int64_t i_lo = ignore_ptr[b_lo];
-            nib = ignore_ptr[b_lo + nb] - i_lo;
-            ptr_local.resize((size_t)nb + 1);
-            for (int32_t t = 0; t <= nb; t++) ptr_local[t] = ignore_ptr[b_lo + t] - i_lo;
-            MML_TRY(d_ign_ptr.alloc((size_t)nb + 1)); MML_TRY(d_ign_idx.alloc(nib));
-            MML_CUDA(cudaMemcpyAsync(d_ign_ptr.p, ptr_local.data(), sizeof(int64_t) * ((size_t)nb + 1), cudaMemcpyHostToDevice, s));
-            if (nib > 0) MML_CUDA(cudaMemcpyAsync(d_ign_idx.p, ignore_idx + i_lo, sizeof(int32_t) * (size_t)nib, cudaMemcpyHostToDevice, s));
-        }
-        MML_TRY(topn_tc_batch(ctx, d_U, n_model_users, d_V, n_model_items, k, d_users.p, nb, n, n_out,
-                              candidates ? d_cand.p : nullptr, (int32_t)n_cand,
-                              nib > 0 ? d_ign_ptr.p : nullptr, d_ign_idx.p, nib,
-                              d_oi.p, d_os.p, d_oc.p, d_redo.p, launches));
-        h_redo.resize(nb);
-        MML_CUDA(cudaMemcpyAsync(out_items + (size_t)b_lo * n_out, d_oi.p, sizeof(int32_t) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, s));
-        MML_CUDA(cudaMemcpyAsync(out_scores + (size_t)b_lo * n_out, d_os.p, sizeof(float) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, s));
-        MML_CUDA(cudaMemcpyAsync(out_counts + b_lo, d_oc.p, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
-        MML_CUDA(cudaMemcpyAsync(h_redo.data(), d_redo.p, nb, cudaMemcpyDeviceToHost, s));
-        MML_CUDA(cudaStreamSynchronize(s));
-        for (int32_t t = 0; t < nb; t++) if (h_redo[t]) redo_users.push_back(b_lo + t);
-    }
+    MML_TRY(topn_tc_run(ctx, d_U, n_model_users, d_V, n_model_items, k, users, n_users, n, n_out, candidates ? d_cand.p : nullptr,
+                        (int32_t)n_cand, has_invalid, ignore_ptr, ignore_idx, out_items, out_scores, out_counts, redo_users, launches));
     MML_CUDA(cudaEventRecord(e1, s));
     MML_CUDA(cudaEventSynchronize(e1));
     cudaEventElapsedTime(&g_stat_ms, e0, e1);

@@ -28,7 +28,8 @@ constexpr int TC_ROWS = 256;                  // users per CTA: two 128-row MMA 
 constexpr int TC_N = 128;                     // candidates per MMA tile
 constexpr int TC_KC = 32;                     // floats per K chunk = one 128-byte swizzle atom
 constexpr int TC_CHUNK_BYTES = 128 * 128;     // 128 rows x 128 bytes
-constexpr int TC_CAP = 32;                    // approximate scores kept per user (and per candidate split)
+constexpr int TC_CAP = 256;                   // candidates collected per user (and per candidate split) before the user is handed to the exact path
+constexpr int TC_SAMPLE = 16384;              // target size of the candidate sample the threshold comes from
 constexpr int TC_MAX_N = 16;                  // largest n served by this path
 constexpr int TC_THREADS = 320;               // warp 0: TMA, warp 1: MMA issue + TMEM, warps 2-9: epilogue
 constexpr float TC_ERR_C = 0.0025f;           // |tf32 score - exact| <= TC_ERR_C * |u| * |v| (2^-9 truncation + slack)
@@ -104,44 +105,36 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T
 
 struct TcArgs {
     int32_t n_rows;                 // users in the batch
-    int32_t n_cand;                 // candidates (positions)
-    int32_t n_model_items;
+    int32_t stride;                 // column j of the V panel is candidate position j * stride (1 when collecting)
     int32_t kc;                     // K chunks (kp / 32)
     int32_t stages;                 // V ring depth
     int32_t n_tiles, tiles_per_split, splits;
+    int32_t n_cols;                 // real columns of the V panel (the rest is zero padding)
+    int32_t m;                      // sampling pass: length of the per-user sorted list (>= n)
     const uint8_t* row_ok;          // [n_rows] user id inside the model
-    const int32_t* cand;            // [n_cand] item id per position or NULL (identity)
+    const uint32_t* bad;            // NULL, or [n_tiles * 4]: bit c of word g set = column 32 g + c is an id outside the model
     const int64_t* ign_ptr;         // [n_rows + 1] or NULL
-    const int32_t* ign_idx;         // item ids, ascending inside a row
-    float* list_s; int32_t* list_p; // [n_rows][splits][CAP]
-    int32_t* list_n;                // [n_rows][splits]
+    const int32_t* ign_pos;         // candidate POSITIONS of the user's ignore_items, ascending inside a row
+    float* thr;                     // [n_rows] sampling pass: out, m-th best sampled score; collecting pass: in, threshold
+    float* buf_s; int32_t* buf_p;   // collecting pass: [n_rows][splits][TC_CAP] approximate score, position
+    int32_t* buf_n;                 // [n_rows][splits] entries wanted (> TC_CAP = overflow)
     uint32_t* err;
 };
 
-struct TcIns { float thr; int cnt; };
-
-// Slow path of the epilogue: candidate at position pos passed the threshold of this user's list.
-__device__ __noinline__ TcIns tc_consider(const TcArgs& a, float s, int pos, float* ls, int32_t* lp, float thr, int cnt,
-                                          int64_t ig_lo, int64_t ig_hi)
+// Sampling pass slow path: s enters the sorted list ls[0 .. m) (stride 256 floats: one column of shared memory per thread).
+__device__ __noinline__ float tc_insert(float* ls, int m, float s)
 {
-    TcIns r; r.thr = thr; r.cnt = cnt;
-    if (pos >= a.n_cand) return r;
-    const int32_t item = a.cand ? a.cand[pos] : pos;
-    if ((uint32_t)item >= (uint32_t)a.n_model_items) return r;      // Predict = float.MinValue: never qualifies
-    while (ig_lo < ig_hi) {                                          // ignore_items.Contains(item)
-        const int64_t mid = (ig_lo + ig_hi) >> 1;
-        const int32_t x = a.ign_idx[mid];
-        if (x == item) return r;
-        if (x < item) ig_lo = mid + 1; else ig_hi = mid;
-    }
-    int j = cnt < TC_CAP ? cnt : TC_CAP - 1;
-    while (j > 0 && ls[j - 1] < s) { ls[j] = ls[j - 1]; lp[j] = lp[j - 1]; j--; }
-    ls[j] = s; lp[j] = pos;
-    if (cnt < TC_CAP) r.cnt = cnt + 1;
-    if (r.cnt == TC_CAP) r.thr = ls[TC_CAP - 1];
-    return r;
+    int j = m - 1;
+    while (j > 0 && ls[(j - 1) * TC_ROWS] < s) { ls[j * TC_ROWS] = ls[(j - 1) * TC_ROWS]; j--; }
+    ls[j * TC_ROWS] = s;
+    return ls[(m - 1) * TC_ROWS];
 }
 
+// MODE 0 (sampling): every thread keeps the m best approximate scores of its user over a strided sample of the candidates;
+//                    the m-th best, minus twice the error bound, is a threshold no member of the exact top n can fall below.
+// MODE 1 (collecting): every thread appends the candidates of its user that reach the threshold (a few dozen of 10^5).
+// ignore_items are skipped with a cursor into the user's position-sorted ignore list: one register compare per 32 scores.
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_v, const TcArgs a)
 {
@@ -151,6 +144,7 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
     const uint32_t smem0 = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_u = smem0;                                               // [2][kc] chunks
     const uint32_t smem_v = smem0 + 2u * a.kc * TC_CHUNK_BYTES;                  // [stages] chunks
+    float* lists = reinterpret_cast<float*>(tc_smem_raw + (smem0 - smem_u32(tc_smem_raw)) + (size_t)(2 * a.kc + a.stages) * TC_CHUNK_BYTES);
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * 8, bar_u = bar_full + 16 * 8;
     const uint32_t bar_tfull = bar_full + 17 * 8, bar_tempty = bar_full + 19 * 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -221,47 +215,104 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
         // ===== epilogue: 8 warps, thread <-> user row =====
         const int q = warp & 3;                                // TMEM lane quarter this warp may read
         const int h = (warp - 2) >> 2;                         // row half
-        const int row = row0 + h * 128 + q * 32 + lane;
+        const int rloc = h * 128 + q * 32 + lane;
+        const int row = row0 + rloc;
         const bool ok = row < a.n_rows && a.row_ok[row];
-        float thr = ok ? -INFINITY : INFINITY;
+        float* ls = lists + rloc;
+        float thr;
+        if (MODE == 0) {
+            for (int j = 0; j < a.m; j++) ls[j * TC_ROWS] = -INFINITY;
+            thr = ok ? -INFINITY : INFINITY;
+        } else {
+            thr = ok ? a.thr[row] : INFINITY;
+        }
         int cnt = 0;
-        const size_t lbase = ((size_t)(ok ? row : 0) * a.splits + sp) * TC_CAP;
-        float* ls = a.list_s + lbase; int32_t* lp = a.list_p + lbase;
-        int64_t ig_lo = 0, ig_hi = 0;
-        if (ok && a.ign_ptr) { ig_lo = a.ign_ptr[row]; ig_hi = a.ign_ptr[row + 1]; }
-        int it = 0;
-        for (int t = t_begin; t < t_end; t++, it++) {
+        const size_t bbase = ((size_t)(ok ? row : 0) * a.splits + sp) * TC_CAP;
+        int64_t ig = 0, ig_end = 0;
+        int32_t ig_next = 0x7fffffff;
+        if (ok && a.ign_ptr) {
+            ig = a.ign_ptr[row]; ig_end = a.ign_ptr[row + 1];
+            if (ig < ig_end) ig_next = a.ign_pos[ig];
+        }
+        const long long st = a.stride;
+        const int n_groups = (t_end - t_begin) * (TC_N / 32);
+        // group gi = 32 consecutive columns; its accumulators are fetched while group gi - 1 is being examined
+        uint32_t va[32], vb[32];
+        auto fetch = [&](int gi, uint32_t (&v)[32]) {
+            const int it = gi / (TC_N / 32), j = gi % (TC_N / 32);
             const int buf = it & 1;
-            const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-            mbar_wait(bar_tfull + 8 * buf, aphase, a.err);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + h) * TC_N);
-#pragma unroll 1
-            for (int j = 0; j < TC_N / 32; j++) {
-                uint32_t v[32];
-                __syncwarp();
-                tc_ld32(taddr + j * 32, v);
-                tc_ld_wait();
-                float m = __uint_as_float(v[0]);
+            if (j == 0) {
+                mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u, a.err);
+                tc_fence_after();
+            }
+            __syncwarp();
+            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + h) * TC_N + j * 32), v);
+        };
+        auto examine = [&](int gi, uint32_t (&v)[32]) {
+            const int g = t_begin * (TC_N / 32) + gi;
+            const int col0 = g * 32;
+            uint32_t mask = a.bad ? a.bad[g] : 0u;
+            if (col0 + 32 > a.n_cols) mask |= col0 >= a.n_cols ? 0xffffffffu : (0xffffffffu << (a.n_cols - col0));
+            if ((long long)ig_next < (long long)(col0 + 32) * st) {     // some ignore_items fall into these 32 columns
+                do {
+                    const long long p = ig_next;
+                    if (p >= (long long)col0 * st && p % st == 0) mask |= 1u << (int)(p / st - col0);
+                    ++ig;
+                    ig_next = ig < ig_end ? a.ign_pos[ig] : 0x7fffffff;
+                } while ((long long)ig_next < (long long)(col0 + 32) * st);
+            }
+            if (mask) {
 #pragma unroll
-                for (int c = 1; c < 32; c++) m = fmaxf(m, __uint_as_float(v[c]));
+                for (int c = 0; c < 32; c++) if ((mask >> c) & 1u) v[c] = 0x7fc00000u;      // NaN: fails every comparison, fmaxf skips it
+            }
+            float m = __uint_as_float(v[0]);
+#pragma unroll
+            for (int c = 1; c < 32; c++) m = fmaxf(m, __uint_as_float(v[c]));
+            if (MODE == 0) {
                 if (m > thr) {
-                    const int pos0 = t * TC_N + j * 32;
 #pragma unroll
                     for (int c = 0; c < 32; c++) {
                         const float s = __uint_as_float(v[c]);
-                        if (s > thr) {
-                            const TcIns r = tc_consider(a, s, pos0 + c, ls, lp, thr, cnt, ig_lo, ig_hi);
-                            thr = r.thr; cnt = r.cnt;
+                        if (s > thr) thr = tc_insert(ls, a.m, s);
+                    }
+                }
+            } else {
+                if (m >= thr) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const float s = __uint_as_float(v[c]);
+                        if (s >= thr) {
+                            if (cnt < TC_CAP) { a.buf_s[bbase + cnt] = s; a.buf_p[bbase + cnt] = col0 + c; }
+                            cnt++;
                         }
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        };
+        auto release = [&](int gi) {      // last group of a tile examined: its TMEM buffer may be overwritten
+            if (gi % (TC_N / 32) == TC_N / 32 - 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * ((gi / (TC_N / 32)) & 1));
+            }
+        };
+        if (n_groups > 0) fetch(0, va);
+        for (int gi = 0; gi < n_groups; gi += 2) {
+            tc_ld_wait();                                   // va holds group gi
+            if (gi + 1 < n_groups) fetch(gi + 1, vb);
+            examine(gi, va);
+            release(gi);
+            if (gi + 1 < n_groups) {
+                tc_ld_wait();                               // vb holds group gi + 1
+                if (gi + 2 < n_groups) fetch(gi + 2, va);
+                examine(gi + 1, vb);
+                release(gi + 1);
+            }
         }
-        if (ok) a.list_n[(size_t)row * a.splits + sp] = cnt;
+        if (ok) {
+            if (MODE == 0) a.thr[row] = thr;
+            else a.buf_n[(size_t)row * a.splits + sp] = cnt;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -273,18 +324,19 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
 }
 
 // ---- staging: dense, zero-padded operand panels + row norms --------------------------------------------------
-// dst[r][0..kp) = src[id(r)][0..k) (zero beyond k, zero row for ids outside the model); norm[r] = |row|;
-// ok[r] = id inside the model; *max_norm_bits = max over rows (float bits; NaN sorts above +inf).
+// dst[r][0..kp) = src[id(r)][0..k) (zero beyond k, zero row for ids outside the model), id(r) = ids ? ids[r * id_stride] :
+// r * id_stride; norm[r] = |row|; ok[r] = id inside the model; *max_norm_bits = max over rows (float bits; NaN sorts
+// above +inf); bad: bit (r % 32) of word r / 32 set for rows whose id is outside the model.
 __global__ void tc_stage_rows_kernel(const float* __restrict__ src, int32_t n_src_rows, int32_t k,
-                                     const int32_t* __restrict__ ids, int32_t n, int32_t kp,
+                                     const int32_t* __restrict__ ids, int32_t id_stride, int32_t n, int32_t kp,
                                      float* __restrict__ dst, float* __restrict__ norm, uint8_t* __restrict__ ok,
-                                     uint32_t* __restrict__ max_norm_bits)
+                                     uint32_t* __restrict__ max_norm_bits, uint32_t* __restrict__ bad)
 {
     const int lane = threadIdx.x & 31;
     int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (; r < n; r += stride) {
-        const int32_t id = ids ? ids[r] : (int32_t)r;
+        const int32_t id = ids ? ids[r * id_stride] : (int32_t)(r * id_stride);
         const bool valid = (uint32_t)id < (uint32_t)n_src_rows;
         float ss = 0.f;
         for (int f = lane; f < kp; f += 32) {
@@ -299,13 +351,23 @@ __global__ void tc_stage_rows_kernel(const float* __restrict__ src, int32_t n_sr
             if (norm) norm[r] = nr;
             if (ok) ok[r] = valid ? 1 : 0;
             if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(nr));
+            if (bad && !valid) atomicOr(bad + (r >> 5), 1u << (r & 31));
         }
     }
 }
 
-// row of every ignore entry (binary search in the CSR pointers) + "rows are ascending" check
-__global__ void tc_ignore_rows_kernel(const int64_t* __restrict__ ptr, int32_t n_rows, const int32_t* __restrict__ idx, int64_t total,
-                                      uint32_t* __restrict__ row_of, uint32_t* __restrict__ unsorted)
+// pos_of[item] = candidate position (candidates are distinct)
+__global__ void tc_pos_of_kernel(const int32_t* __restrict__ cand, int32_t n_cand, int32_t n_items, int32_t* __restrict__ pos_of)
+{
+    const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_cand) { const int32_t id = cand[c]; if ((uint32_t)id < (uint32_t)n_items) pos_of[id] = c; }
+}
+
+// ignore item ids -> candidate positions (INT_MAX: not a candidate), row of every entry (binary search in the CSR
+// pointers), and an "ascending inside every row" check
+__global__ void tc_ignore_pos_kernel(const int64_t* __restrict__ ptr, int32_t n_rows, int32_t* __restrict__ idx, int64_t total,
+                                     const int32_t* __restrict__ pos_of, int32_t n_items, int32_t n_cand,
+                                     uint32_t* __restrict__ row_of)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -313,38 +375,54 @@ __global__ void tc_ignore_rows_kernel(const int64_t* __restrict__ ptr, int32_t n
         int32_t lo = 0, hi = n_rows;                  // last row with ptr[row] <= t
         while (hi - lo > 1) { const int32_t mid = (lo + hi) >> 1; if (ptr[mid] <= t) lo = mid; else hi = mid; }
         row_of[t] = (uint32_t)lo;
-        if (t + 1 < ptr[lo + 1] && idx[t] > idx[t + 1]) atomicExch(unsorted, 1u);
+        const int32_t item = idx[t];
+        int32_t pos = 0x7fffffff;
+        if (pos_of) { if ((uint32_t)item < (uint32_t)n_items && pos_of[item] >= 0) pos = pos_of[item]; }
+        else if ((uint32_t)item < (uint32_t)n_cand) pos = item;
+        idx[t] = pos;
     }
 }
 
-__global__ void tc_bias_items_kernel(const int32_t* __restrict__ idx, int64_t total, uint32_t* __restrict__ key)
+__global__ void tc_ignore_sorted_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ row_of,
+                                        const int32_t* __restrict__ pos, int64_t total, uint32_t* __restrict__ unsorted)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; t < total; t += stride) key[t] = (uint32_t)idx[t] ^ 0x80000000u;      // order-preserving for negative ids
+    for (; t < total; t += stride)
+        if (t + 1 < ptr[row_of[t] + 1] && pos[t] > pos[t + 1]) atomicExch(unsorted, 1u);
 }
-__global__ void tc_unbias_items_kernel(const uint32_t* __restrict__ key, int64_t total, int32_t* __restrict__ idx)
+
+__global__ void tc_copy_u32_kernel(const uint32_t* __restrict__ src, int64_t total, uint32_t* __restrict__ dst)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; t < total; t += stride) idx[t] = (int32_t)(key[t] ^ 0x80000000u);
+    for (; t < total; t += stride) dst[t] = src[t];
+}
+
+// thr[b] = (m-th best sampled score) - 2 d, d2[b] = 2 d, d = TC_ERR_C * |u_b| * max|v| (+ underflow slack)
+__global__ void tc_threshold_kernel(float* __restrict__ thr, float* __restrict__ d2, const float* __restrict__ unorm,
+                                    const uint32_t* __restrict__ vmax_bits, int32_t n_rows)
+{
+    const int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_rows) return;
+    const float dd = 2.f * (TC_ERR_C * unorm[b] * __uint_as_float(*vmax_bits) + 1e-30f);
+    d2[b] = dd;
+    thr[b] = (dd < INFINITY) ? thr[b] - dd : -INFINITY;
 }
 
 // ---- finalize: exact re-scoring of the candidate superset, one warp per user ---------------------------------
-constexpr int FIN_WARPS = 4;
-
 struct FinArgs {
     const float* U; const float* V; int32_t k;            // original model matrices
     const int32_t* users;                                   // [n_rows] user ids
     const int32_t* cand;                                    // or NULL
-    const float* list_s; const int32_t* list_p; const int32_t* list_n;
-    const float* unorm; const uint32_t* vmax_bits;
+    const float* buf_s; const int32_t* buf_p; const int32_t* buf_n;
+    const float* thr; const float* d2;
     const uint8_t* row_ok;
-    int32_t n_rows, splits, n, n_out;
+    int32_t n_rows, splits, n, n_out, warps;
     int32_t* out_items; float* out_scores; int32_t* out_counts; uint8_t* redo;
 };
 
-__global__ void __launch_bounds__(FIN_WARPS * 32) tc_finalize_kernel(const FinArgs a)
+__global__ void tc_finalize_kernel(const FinArgs a)
 {
     extern __shared__ uint8_t fin_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -352,24 +430,26 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) tc_finalize_kernel(const FinAr
     float* ap = reinterpret_cast<float*>(fin_smem) + (size_t)warp * E_max * 3;      // approximate scores
     int32_t* pp = reinterpret_cast<int32_t*>(ap + E_max);                            // positions
     float* ex = reinterpret_cast<float*>(pp + E_max);                                // exact scores
-    const int b = blockIdx.x * FIN_WARPS + warp;
+    const int b = blockIdx.x * a.warps + warp;
     if (b >= a.n_rows) return;
     if (!a.row_ok[b]) { if (lane == 0) { a.out_counts[b] = 0; a.redo[b] = 0; } return; }
-    // 1. gather the per-split lists; full_min = largest "smallest kept score" over the lists that are full
+    // 1. gather what the splits collected; a split that wanted more than TC_CAP entries lost some
     int E = 0;
-    float full_min = -INFINITY;
-    bool any_full = false;
+    bool overflow = false;
     for (int s = 0; s < a.splits; s++) {
-        const int c = a.list_n[(size_t)b * a.splits + s];
+        const int c = a.buf_n[(size_t)b * a.splits + s];
+        if (c > TC_CAP) { overflow = true; break; }
         const size_t base = ((size_t)b * a.splits + s) * TC_CAP;
-        for (int e = lane; e < c; e += 32) { ap[E + e] = a.list_s[base + e]; pp[E + e] = a.list_p[base + e]; }
-        if (c == TC_CAP) { any_full = true; full_min = fmaxf(full_min, a.list_s[base + TC_CAP - 1]); }
+        for (int e = lane; e < c; e += 32) { ap[E + e] = a.buf_s[base + e]; pp[E + e] = a.buf_p[base + e]; }
         E += c;
     }
     __syncwarp();
+    const float d2 = a.d2[b], thr = a.thr[b];
+    // thr = -inf: the sample held fewer than m scorable candidates and everything scorable was collected.
+    // thr > -inf: at least m >= n candidates reach it, anything else is a broken invariant -> exact path.
+    if (overflow || !(d2 < INFINITY) || (thr > -INFINITY && E < a.n)) { if (lane == 0) { a.redo[b] = 1; a.out_counts[b] = 0; } return; }
     if (E == 0) { if (lane == 0) { a.out_counts[b] = 0; a.redo[b] = 0; } return; }
-    const float delta = TC_ERR_C * a.unorm[b] * __uint_as_float(*a.vmax_bits) + 1e-30f;
-    // 2. a_n = n-th best approximate score (rank by score desc, list index asc)
+    // 2. a_n = n-th best approximate score (rank by score desc, buffer index asc)
     float a_n = -INFINITY;
     if (E >= a.n) {
         for (int e = lane; e < E; e += 32) {
@@ -381,10 +461,8 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) tc_finalize_kernel(const FinAr
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) a_n = fmaxf(a_n, __shfl_xor_sync(0xffffffffu, a_n, d));
     }
-    const float cut = a_n - 2.f * delta;        // -inf when fewer than n candidates were seen at all
-    // 3. is the superset complete? (a full list may have dropped candidates scoring up to its smallest entry)
-    if (!(delta < INFINITY) || (any_full && full_min >= cut)) { if (lane == 0) { a.redo[b] = 1; a.out_counts[b] = 0; } return; }
-    // 4. exact scores of the finalists: sequential fp32 multiply, then add (MatrixExtensions.cs:234-238)
+    const float cut = a_n - d2;        // every member of the exact top n scores >= cut approximately; cut >= thr
+    // 3. exact scores of the finalists: sequential fp32 multiply, then add (MatrixExtensions.cs:234-238)
     const float* urow = a.U + (size_t)a.users[b] * a.k;
     for (int e = lane; e < E; e += 32) {
         float s = -INFINITY;
@@ -398,7 +476,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) tc_finalize_kernel(const FinAr
         ex[e] = s;
     }
     __syncwarp();
-    // 5. order by (exact score desc, candidate position asc); the best n go out
+    // 4. order by (exact score desc, candidate position asc); the best n go out
     int qualified = 0;
     for (int e = lane; e < E; e += 32) {
         const float se = ex[e];
@@ -449,95 +527,215 @@ static inline int tc_grid(int64_t n, int threads = 256)
 
 bool topn_tc_eligible(int32_t k, int32_t n, int64_t n_cand)
 {
-    return n >= 1 && n <= TC_MAX_N && k >= 1 && k <= 128 && n_cand >= 1;
+    return n >= 1 && n <= TC_MAX_N && k >= 1 && k <= 128 && n_cand >= 1 && n_cand < ((int64_t)1 << 30);
 }
 
-// Top n of a user batch on the tensor-core path. d_users / d_cand (or NULL) / d_ign_ptr / d_ign_idx (or NULL): device.
-// d_redo[b] = 1 for users whose candidate superset could not be proven complete (caller re-runs them exactly).
-// Outputs (device): d_out_items/d_out_scores [n_users x n_out], d_out_counts [n_users].
-int32_t topn_tc_batch(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
-                      const int32_t* d_users, int32_t n_users, int32_t n, int32_t n_out,
-                      const int32_t* d_cand, int32_t n_cand,
-                      const int64_t* d_ign_ptr, int32_t* d_ign_idx, int64_t n_ign,
-                      int32_t* d_out_items, float* d_out_scores, int32_t* d_out_counts, uint8_t* d_redo,
-                      int64_t* launches)
+// Candidate-side state of one Recommend() call, shared by all user batches.
+struct TcCandidates {
+    int32_t n_cand = 0, kp = 0, kc = 0, stride = 1, n_samp = 0;
+    int64_t cand_pad = 0, samp_pad = 0;
+    bool has_bad = false;                 // some candidate id lies outside the model
+    DevBuf<float> Vb, Vs;                 // all candidates / the strided sample, zero padded panels
+    DevBuf<uint32_t> bad_b, bad_s, vmax;  // never-qualifying columns of either panel; max |v| (float bits)
+    DevBuf<int32_t> pos_of;               // explicit candidate lists only: item -> position
+    CUtensorMap map_b, map_s;
+};
+
+static int32_t tc_prepare_candidates(Ctx* ctx, TcCandidates& c, const float* d_V, int32_t n_model_items, int32_t k,
+                                     const int32_t* d_cand, int32_t n_cand, bool has_invalid, int32_t n, int64_t* launches)
 {
     cudaStream_t s = ctx->stream;
-    const int32_t kp = (int32_t)ceil_div(k, TC_KC) * TC_KC, kc = kp / TC_KC;
-    const int64_t rows_pad = ceil_div(n_users, TC_ROWS) * TC_ROWS, cand_pad = ceil_div(n_cand, TC_N) * TC_N;
-    DevBuf<float> Ub, Vb, unorm; DevBuf<uint8_t> row_ok; DevBuf<uint32_t> vmax, err;
-    MML_TRY(Ub.alloc((size_t)rows_pad * kp)); MML_TRY(Vb.alloc((size_t)cand_pad * kp));
-    MML_TRY(unorm.alloc(n_users)); MML_TRY(row_ok.alloc(n_users)); MML_TRY(vmax.alloc(1)); MML_TRY(err.alloc(1));
-    MML_CUDA(cudaMemsetAsync(vmax.p, 0, sizeof(uint32_t), s));
-    MML_CUDA(cudaMemsetAsync(err.p, 0, sizeof(uint32_t), s));
-    if (rows_pad > n_users) MML_CUDA(cudaMemsetAsync(Ub.p + (size_t)n_users * kp, 0, sizeof(float) * (size_t)(rows_pad - n_users) * kp, s));
-    if (cand_pad > n_cand) MML_CUDA(cudaMemsetAsync(Vb.p + (size_t)n_cand * kp, 0, sizeof(float) * (size_t)(cand_pad - n_cand) * kp, s));
-    tc_stage_rows_kernel<<<tc_grid((int64_t)n_users * 32), 256, 0, s>>>(d_U, n_model_users, k, d_users, n_users, kp, Ub.p, unorm.p, row_ok.p, nullptr);
-    tc_stage_rows_kernel<<<tc_grid((int64_t)n_cand * 32), 256, 0, s>>>(d_V, n_model_items, k, d_cand, n_cand, kp, Vb.p, nullptr, nullptr, vmax.p);
-    MML_CUDA(cudaGetLastError());
-    if (launches) *launches += 2;
-    // ignore lists must be ascending inside a row for the epilogue's binary search
-    if (d_ign_ptr && n_ign > 0) {
-        DevBuf<uint32_t> row_of, flag, key, t1, t2;
-        MML_TRY(row_of.alloc(n_ign)); MML_TRY(flag.alloc(1));
-        MML_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t), s));
-        tc_ignore_rows_kernel<<<tc_grid(n_ign), 256, 0, s>>>(d_ign_ptr, n_users, d_ign_idx, n_ign, row_of.p, flag.p);
-        MML_CUDA(cudaGetLastError());
-        uint32_t unsorted = 0;
-        MML_CUDA(cudaMemcpyAsync(&unsorted, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        MML_CUDA(cudaStreamSynchronize(s));
-        if (launches) *launches += 1;
-        if (unsorted) {
-            MML_TRY(key.alloc(n_ign)); MML_TRY(t1.alloc(n_ign)); MML_TRY(t2.alloc(n_ign));
-            tc_bias_items_kernel<<<tc_grid(n_ign), 256, 0, s>>>(d_ign_idx, n_ign, key.p);
-            MML_TRY(radix_sort_pairs(key.p, row_of.p, t1.p, t2.p, n_ign, 32, s));                                   // by item
-            MML_TRY(radix_sort_pairs(row_of.p, key.p, t1.p, t2.p, n_ign, bits_for((uint32_t)std::max(n_users - 1, 1)), s));   // by row, stable
-            tc_unbias_items_kernel<<<tc_grid(n_ign), 256, 0, s>>>(key.p, n_ign, d_ign_idx);
-            MML_CUDA(cudaGetLastError());
-            if (launches) *launches += 10;
-        }
+    c.n_cand = n_cand; c.has_bad = has_invalid;
+    c.kp = (int32_t)ceil_div(k, TC_KC) * TC_KC; c.kc = c.kp / TC_KC;
+    c.cand_pad = ceil_div(n_cand, TC_N) * TC_N;
+    // sample: every stride-th position; about n * stride candidates reach the threshold it yields
+    c.stride = (int32_t)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_cand, TC_SAMPLE), std::max(1, 96 / n)));
+    c.n_samp = (int32_t)ceil_div(n_cand, c.stride);
+    c.samp_pad = ceil_div(c.n_samp, TC_N) * TC_N;
+    MML_TRY(c.Vb.alloc((size_t)c.cand_pad * c.kp)); MML_TRY(c.Vs.alloc((size_t)c.samp_pad * c.kp));
+    MML_TRY(c.bad_b.alloc((size_t)c.cand_pad / 32)); MML_TRY(c.bad_s.alloc((size_t)c.samp_pad / 32)); MML_TRY(c.vmax.alloc(1));
+    MML_CUDA(cudaMemsetAsync(c.bad_b.p, 0, c.bad_b.bytes(), s)); MML_CUDA(cudaMemsetAsync(c.bad_s.p, 0, c.bad_s.bytes(), s));
+    MML_CUDA(cudaMemsetAsync(c.vmax.p, 0, sizeof(uint32_t), s));
+    if (c.cand_pad > n_cand) MML_CUDA(cudaMemsetAsync(c.Vb.p + (size_t)n_cand * c.kp, 0, sizeof(float) * (size_t)(c.cand_pad - n_cand) * c.kp, s));
+    if (c.samp_pad > c.n_samp) MML_CUDA(cudaMemsetAsync(c.Vs.p + (size_t)c.n_samp * c.kp, 0, sizeof(float) * (size_t)(c.samp_pad - c.n_samp) * c.kp, s));
+    tc_stage_rows_kernel<<<tc_grid((int64_t)n_cand * 32), 256, 0, s>>>(d_V, n_model_items, k, d_cand, 1, n_cand, c.kp, c.Vb.p, nullptr, nullptr, c.vmax.p, c.bad_b.p);
+    tc_stage_rows_kernel<<<tc_grid((int64_t)c.n_samp * 32), 256, 0, s>>>(d_V, n_model_items, k, d_cand, c.stride, c.n_samp, c.kp, c.Vs.p, nullptr, nullptr, nullptr, c.bad_s.p);
+    if (d_cand) {
+        MML_TRY(c.pos_of.alloc(std::max(n_model_items, 1)));
+        MML_CUDA(cudaMemsetAsync(c.pos_of.p, 0xff, c.pos_of.bytes(), s));
+        tc_pos_of_kernel<<<(unsigned)ceil_div(n_cand, 256), 256, 0, s>>>(d_cand, n_cand, n_model_items, c.pos_of.p);
     }
-    CUtensorMap map_u, map_v;
-    MML_TRY(make_panel_map(&map_u, Ub.p, rows_pad, kp));
-    MML_TRY(make_panel_map(&map_v, Vb.p, cand_pad, kp));
-    // candidate splits: enough CTAs to fill the GPU when the batch has few user tiles
-    const int row_tiles = (int)(rows_pad / TC_ROWS), n_tiles = (int)(cand_pad / TC_N);
+    MML_CUDA(cudaGetLastError());
+    if (launches) *launches += 3;
+    MML_TRY(make_panel_map(&c.map_b, c.Vb.p, c.cand_pad, c.kp));
+    MML_TRY(make_panel_map(&c.map_s, c.Vs.p, c.samp_pad, c.kp));
+    return MML_OK;
+}
+
+// Per-batch buffers of one Recommend() call, allocated once for the largest batch.
+struct TcWork {
+    int32_t cap_users = 0, splits = 1, tps = 1, stages = 2;
+    size_t smem = 0;
+    DevBuf<float> Ub, unorm, thr, d2, buf_s, out_s;
+    DevBuf<uint8_t> row_ok, redo;
+    DevBuf<uint32_t> err;
+    DevBuf<int32_t> buf_p, buf_n, users, out_i, out_c, ign_idx;
+    DevBuf<int64_t> ign_ptr;
+    DevBuf<uint32_t> row_of, flag, key, t1, t2;
+};
+
+static int32_t tc_alloc_work(Ctx* ctx, TcWork& w, const TcCandidates& c, int32_t cap_users, int32_t n_out, int64_t max_ign)
+{
+    w.cap_users = cap_users;
+    const int64_t rows_pad = ceil_div(cap_users, TC_ROWS) * TC_ROWS;
+    const int row_tiles = (int)(rows_pad / TC_ROWS), n_tiles = (int)(c.cand_pad / TC_N);
+    // candidate splits fill the GPU when the batch has few user tiles
     int splits = (int)std::min<int64_t>(std::min<int64_t>(ceil_div(ctx->sm_count, row_tiles), TC_MAX_SPLITS), n_tiles);
     splits = std::max(splits, 1);
-    const int tps = (int)ceil_div(n_tiles, splits);
-    splits = (int)ceil_div(n_tiles, tps);
-    DevBuf<float> list_s; DevBuf<int32_t> list_p, list_n;
-    MML_TRY(list_s.alloc((size_t)n_users * splits * TC_CAP)); MML_TRY(list_p.alloc((size_t)n_users * splits * TC_CAP));
-    MML_TRY(list_n.alloc((size_t)n_users * splits));
-    MML_CUDA(cudaMemsetAsync(list_n.p, 0, list_n.bytes(), s));
+    w.tps = (int)ceil_div(n_tiles, splits);
+    w.splits = (int)ceil_div(n_tiles, w.tps);
+    MML_TRY(w.Ub.alloc((size_t)rows_pad * c.kp));
+    MML_TRY(w.unorm.alloc(cap_users)); MML_TRY(w.thr.alloc(cap_users)); MML_TRY(w.d2.alloc(cap_users));
+    MML_TRY(w.row_ok.alloc(cap_users)); MML_TRY(w.redo.alloc(cap_users)); MML_TRY(w.err.alloc(1));
+    MML_TRY(w.buf_s.alloc((size_t)cap_users * w.splits * TC_CAP)); MML_TRY(w.buf_p.alloc((size_t)cap_users * w.splits * TC_CAP));
+    MML_TRY(w.buf_n.alloc((size_t)cap_users * w.splits));
+    MML_TRY(w.users.alloc(cap_users)); MML_TRY(w.out_i.alloc((size_t)cap_users * n_out)); MML_TRY(w.out_s.alloc((size_t)cap_users * n_out));
+    MML_TRY(w.out_c.alloc(cap_users));
+    if (max_ign > 0) {
+        MML_TRY(w.ign_ptr.alloc((size_t)cap_users + 1)); MML_TRY(w.ign_idx.alloc(max_ign));
+        MML_TRY(w.row_of.alloc(max_ign)); MML_TRY(w.flag.alloc(1));
+    }
     int max_optin = 0;
     MML_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-    const int64_t fixed = 2ll * kc * TC_CHUNK_BYTES + 1024 + 512;      // U panels + alignment slack + static barriers
-    const int stages = (int)std::min<int64_t>(8, (max_optin - fixed) / TC_CHUNK_BYTES);
-    MML_CHECK(stages >= 2, MML_ERR_UNSUPPORTED, "topn: shared memory too small for the tcgen05 path");
-    const size_t smem = (size_t)(2ll * kc + stages) * TC_CHUNK_BYTES + 1024;
-    MML_CUDA(cudaFuncSetAttribute((const void*)score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t list_bytes = (int64_t)TC_ROWS * TC_MAX_N * sizeof(float);
+    const int64_t fixed = 2ll * c.kc * TC_CHUNK_BYTES + 1024 + 512 + list_bytes;      // U panels, alignment slack, static barriers, sample lists
+    w.stages = (int)std::min<int64_t>(8, (max_optin - fixed) / TC_CHUNK_BYTES);
+    MML_CHECK(w.stages >= 2, MML_ERR_UNSUPPORTED, "topn: shared memory too small for the tcgen05 path");
+    w.smem = (size_t)(2ll * c.kc + w.stages) * TC_CHUNK_BYTES + 1024 + list_bytes;
+    MML_CUDA(cudaFuncSetAttribute((const void*)score_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+    MML_CUDA(cudaFuncSetAttribute((const void*)score_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+    return MML_OK;
+}
+
+// Top n of a user batch on the tensor-core path; users and the ignore CSR (item ids) are already in w.users / w.ign_*.
+// w.redo[b] = 1 for users whose candidate superset could not be proven complete (caller re-runs them exactly).
+// Results: w.out_i / w.out_s [n_users x n_out], w.out_c [n_users].
+static int32_t topn_tc_batch(Ctx* ctx, TcCandidates& c, TcWork& w, const float* d_U, int32_t n_model_users, const float* d_V,
+                             int32_t n_model_items, int32_t k, int32_t n_users, int32_t n, int32_t n_out, const int32_t* d_cand,
+                             int64_t n_ign, int64_t* launches)
+{
+    cudaStream_t s = ctx->stream;
+    const int32_t kp = c.kp, kc = c.kc;
+    const int64_t rows_pad = ceil_div(n_users, TC_ROWS) * TC_ROWS;
+    MML_CUDA(cudaMemsetAsync(w.err.p, 0, sizeof(uint32_t), s));
+    if (rows_pad > n_users) MML_CUDA(cudaMemsetAsync(w.Ub.p + (size_t)n_users * kp, 0, sizeof(float) * (size_t)(rows_pad - n_users) * kp, s));
+    tc_stage_rows_kernel<<<tc_grid((int64_t)n_users * 32), 256, 0, s>>>(d_U, n_model_users, k, w.users.p, 1, n_users, kp, w.Ub.p, w.unorm.p, w.row_ok.p, nullptr, nullptr);
+    MML_CUDA(cudaGetLastError());
+    if (launches) *launches += 1;
+    // ignore_items as candidate positions, ascending inside a row (the epilogue walks them with a cursor)
+    const bool have_ign = n_ign > 0;
+    if (have_ign) {
+        MML_CUDA(cudaMemsetAsync(w.flag.p, 0, sizeof(uint32_t), s));
+        tc_ignore_pos_kernel<<<tc_grid(n_ign), 256, 0, s>>>(w.ign_ptr.p, n_users, w.ign_idx.p, n_ign, d_cand ? c.pos_of.p : nullptr,
+                                                           n_model_items, c.n_cand, w.row_of.p);
+        tc_ignore_sorted_kernel<<<tc_grid(n_ign), 256, 0, s>>>(w.ign_ptr.p, w.row_of.p, w.ign_idx.p, n_ign, w.flag.p);
+        MML_CUDA(cudaGetLastError());
+        uint32_t unsorted = 0;
+        MML_CUDA(cudaMemcpyAsync(&unsorted, w.flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaStreamSynchronize(s));
+        if (launches) *launches += 2;
+        if (unsorted) {     // positions are non-negative: plain unsigned radix order
+            if (w.key.n < (size_t)n_ign) { MML_TRY(w.key.alloc(n_ign)); MML_TRY(w.t1.alloc(n_ign)); MML_TRY(w.t2.alloc(n_ign)); }
+            tc_copy_u32_kernel<<<tc_grid(n_ign), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(w.ign_idx.p), n_ign, w.key.p);
+            MML_TRY(radix_sort_pairs(w.key.p, w.row_of.p, w.t1.p, w.t2.p, n_ign, 31, s));                                              // by position
+            MML_TRY(radix_sort_pairs(w.row_of.p, w.key.p, w.t1.p, w.t2.p, n_ign, bits_for((uint32_t)std::max(n_users - 1, 1)), s));   // by row, stable
+            tc_copy_u32_kernel<<<tc_grid(n_ign), 256, 0, s>>>(w.key.p, n_ign, reinterpret_cast<uint32_t*>(w.ign_idx.p));
+            MML_CUDA(cudaGetLastError());
+            if (launches) *launches += 12;
+        }
+    }
+    CUtensorMap map_u;
+    MML_TRY(make_panel_map(&map_u, w.Ub.p, rows_pad, kp));
+    const int row_tiles = (int)(rows_pad / TC_ROWS);
     TcArgs a{};
-    a.n_rows = n_users; a.n_cand = n_cand; a.n_model_items = n_model_items; a.kc = kc; a.stages = stages;
-    a.n_tiles = n_tiles; a.tiles_per_split = tps; a.splits = splits;
-    a.row_ok = row_ok.p; a.cand = d_cand; a.ign_ptr = (d_ign_ptr && n_ign > 0) ? d_ign_ptr : nullptr; a.ign_idx = d_ign_idx;
-    a.list_s = list_s.p; a.list_p = list_p.p; a.list_n = list_n.p; a.err = err.p;
-    score_select_kernel<<<dim3(row_tiles, splits), TC_THREADS, smem, s>>>(map_u, map_v, a);
+    a.n_rows = n_users; a.kc = kc; a.stages = w.stages; a.m = n;
+    a.row_ok = w.row_ok.p; a.ign_ptr = have_ign ? w.ign_ptr.p : nullptr; a.ign_pos = w.ign_idx.p;
+    a.thr = w.thr.p; a.err = w.err.p;
+    // pass 1: threshold from the candidate sample
+    a.stride = c.stride; a.n_tiles = (int)(c.samp_pad / TC_N); a.tiles_per_split = a.n_tiles; a.splits = 1;
+    a.n_cols = c.n_samp; a.bad = c.has_bad ? c.bad_s.p : nullptr;
+    score_select_kernel<0><<<dim3(row_tiles, 1), TC_THREADS, w.smem, s>>>(map_u, c.map_s, a);
+    MML_CUDA(cudaGetLastError());
+    tc_threshold_kernel<<<(unsigned)ceil_div(n_users, 256), 256, 0, s>>>(w.thr.p, w.d2.p, w.unorm.p, c.vmax.p, n_users);
+    MML_CUDA(cudaGetLastError());
+    // pass 2: collect every candidate that reaches it
+    MML_CUDA(cudaMemsetAsync(w.buf_n.p, 0, sizeof(int32_t) * (size_t)n_users * w.splits, s));
+    a.stride = 1; a.n_tiles = (int)(c.cand_pad / TC_N); a.tiles_per_split = w.tps; a.splits = w.splits;
+    a.n_cols = c.n_cand; a.bad = c.has_bad ? c.bad_b.p : nullptr;
+    a.buf_s = w.buf_s.p; a.buf_p = w.buf_p.p; a.buf_n = w.buf_n.p;
+    score_select_kernel<1><<<dim3(row_tiles, w.splits), TC_THREADS, w.smem, s>>>(map_u, c.map_b, a);
     MML_CUDA(cudaGetLastError());
     FinArgs f{};
-    f.U = d_U; f.V = d_V; f.k = k; f.users = d_users; f.cand = d_cand;
-    f.list_s = list_s.p; f.list_p = list_p.p; f.list_n = list_n.p; f.unorm = unorm.p; f.vmax_bits = vmax.p; f.row_ok = row_ok.p;
-    f.n_rows = n_users; f.splits = splits; f.n = n; f.n_out = n_out;
-    f.out_items = d_out_items; f.out_scores = d_out_scores; f.out_counts = d_out_counts; f.redo = d_redo;
-    const size_t fsmem = (size_t)FIN_WARPS * splits * TC_CAP * 12;
+    f.U = d_U; f.V = d_V; f.k = k; f.users = w.users.p; f.cand = d_cand;
+    f.buf_s = w.buf_s.p; f.buf_p = w.buf_p.p; f.buf_n = w.buf_n.p; f.thr = w.thr.p; f.d2 = w.d2.p; f.row_ok = w.row_ok.p;
+    f.n_rows = n_users; f.splits = w.splits; f.n = n; f.n_out = n_out;
+    f.out_items = w.out_i.p; f.out_scores = w.out_s.p; f.out_counts = w.out_c.p; f.redo = w.redo.p;
+    const size_t per_warp = (size_t)w.splits * TC_CAP * 12;
+    f.warps = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)96 * 1024 / per_warp));
+    const size_t fsmem = per_warp * f.warps;
     MML_CUDA(cudaFuncSetAttribute((const void*)tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-    tc_finalize_kernel<<<(unsigned)ceil_div(n_users, FIN_WARPS), FIN_WARPS * 32, fsmem, s>>>(f);
+    tc_finalize_kernel<<<(unsigned)ceil_div(n_users, f.warps), f.warps * 32, fsmem, s>>>(f);
     MML_CUDA(cudaGetLastError());
-    if (launches) *launches += 2;
-    MML_CUDA(cudaStreamSynchronize(s));      // staging buffers are released on return
-    uint32_t h_err = 0;
-    MML_CUDA(cudaMemcpy(&h_err, err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    MML_CHECK(h_err == 0, MML_ERR_CUDA, "topn: tcgen05 pipeline timed out");
+    if (launches) *launches += 4;
+    return MML_OK;
+}
+
+// All user batches of one Recommend() call. users / ignore CSR / outputs: host. d_cand: device or NULL.
+int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
+                    const int32_t* users, int64_t n_users, int32_t n, int32_t n_out, const int32_t* d_cand, int32_t n_cand,
+                    bool has_invalid_cand, const int64_t* ignore_ptr, const int32_t* ignore_idx,
+                    int32_t* out_items, float* out_scores, int32_t* out_counts, std::vector<int64_t>& redo_users, int64_t* launches)
+{
+    cudaStream_t s = ctx->stream;
+    TcCandidates c;
+    MML_TRY(tc_prepare_candidates(ctx, c, d_V, n_model_items, k, d_cand, n_cand, has_invalid_cand, n, launches));
+    const int64_t n_ign = (ignore_ptr && ignore_idx) ? ignore_ptr[n_users] : 0;
+    const int64_t B = 1 << 18;                       // users per pass (staging panel 128 MB, collect buffers 512 MB)
+    int64_t max_ign = 0;
+    if (n_ign > 0)
+        for (int64_t b_lo = 0; b_lo < n_users; b_lo += B)
+            max_ign = std::max(max_ign, ignore_ptr[std::min(b_lo + B, n_users)] - ignore_ptr[b_lo]);
+    TcWork w;
+    MML_TRY(tc_alloc_work(ctx, w, c, (int32_t)std::min<int64_t>(B, n_users), n_out, max_ign));
+    std::vector<uint8_t> h_redo;
+    std::vector<int64_t> ptr_local;
+    for (int64_t b_lo = 0; b_lo < n_users; b_lo += B) {
+        const int32_t nb = (int32_t)std::min<int64_t>(B, n_users - b_lo);
+        MML_CUDA(cudaMemcpyAsync(w.users.p, users + b_lo, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s));
+        MML_CUDA(cudaMemsetAsync(w.out_i.p, 0, sizeof(int32_t) * (size_t)nb * n_out, s));
+        MML_CUDA(cudaMemsetAsync(w.out_s.p, 0, sizeof(float) * (size_t)nb * n_out, s));
+        int64_t nib = 0;
+        if (n_ign > 0) {
+            const int64_t i_lo = ignore_ptr[b_lo];
+            nib = ignore_ptr[b_lo + nb] - i_lo;
+            ptr_local.resize((size_t)nb + 1);
+            for (int32_t t = 0; t <= nb; t++) ptr_local[t] = ignore_ptr[b_lo + t] - i_lo;
+            MML_CUDA(cudaMemcpyAsync(w.ign_ptr.p, ptr_local.data(), sizeof(int64_t) * ((size_t)nb + 1), cudaMemcpyHostToDevice, s));
+            if (nib > 0) MML_CUDA(cudaMemcpyAsync(w.ign_idx.p, ignore_idx + i_lo, sizeof(int32_t) * (size_t)nib, cudaMemcpyHostToDevice, s));
+            MML_CUDA(cudaStreamSynchronize(s));      // ptr_local is reused by the next batch
+        }
+        MML_TRY(topn_tc_batch(ctx, c, w, d_U, n_model_users, d_V, n_model_items, k, nb, n, n_out, d_cand, nib, launches));
+        h_redo.resize(nb);
+        MML_CUDA(cudaMemcpyAsync(out_items + (size_t)b_lo * n_out, w.out_i.p, sizeof(int32_t) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaMemcpyAsync(out_scores + (size_t)b_lo * n_out, w.out_s.p, sizeof(float) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaMemcpyAsync(out_counts + b_lo, w.out_c.p, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaMemcpyAsync(h_redo.data(), w.redo.p, nb, cudaMemcpyDeviceToHost, s));
+        MML_CUDA(cudaStreamSynchronize(s));
+        uint32_t h_err = 0;
+        MML_CUDA(cudaMemcpy(&h_err, w.err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        MML_CHECK(h_err == 0, MML_ERR_CUDA, "topn: tcgen05 pipeline timed out");
+        for (int32_t t = 0; t < nb; t++) if (h_redo[t]) redo_users.push_back(b_lo + t);
+    }
     return MML_OK;
 }
 

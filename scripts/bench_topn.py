@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Times Recommend() for all users (config 5 shape by default: 1M users x 100k items, k=128, top-10, 20 ignored
+items per user) on the tcgen05 path, and the exact CUDA-core path on a user subset for comparison.
+usage: python scripts/bench_topn.py [--users N] [--items M] [--k K] [--n n] [--exact-users E] [--reps R]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--users", type=int, default=1_000_000)
+    ap.add_argument("--items", type=int, default=100_000)
+    ap.add_argument("--k", type=int, default=128)
+    ap.add_argument("--n", type=int, default=10)
+    ap.add_argument("--ignore", type=int, default=20)
+    ap.add_argument("--exact-users", type=int, default=4096)
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    from mymedialite_b200 import engine
+    ctx = engine.Context(0)
+    rs = np.random.default_rng(20260105)
+    U = (rs.standard_normal((args.users, args.k), dtype=np.float32) * np.float32(0.1))
+    V = (rs.standard_normal((args.items, args.k), dtype=np.float32) * np.float32(0.1))
+    users = np.arange(args.users, dtype=np.int32)
+    ign_idx = rs.integers(0, args.items, (args.users, args.ignore), dtype=np.int32)
+    ign_ptr = (np.arange(args.users + 1, dtype=np.int64) * args.ignore)
+    import ctypes as C
+    lib = ctx.lib
+    dU = dV = None
+    n_out = min(args.n, args.items)
+
+    def run(mode, nu):
+        engine.topn_set_mode(mode)
+        oi = np.zeros((nu, n_out), np.int32); os_ = np.zeros((nu, n_out), np.float32); oc = np.zeros(nu, np.int32)
+        t0 = time.time()
+        engine.check(lib.mml_topn_mf(ctx.h, U, args.users, V, args.items, args.k, users[:nu], nu, args.n, None, args.items,
+                                     ign_ptr[:nu + 1], np.ascontiguousarray(ign_idx[:nu]).reshape(-1), oi, os_, oc))
+        wall = time.time() - t0
+        return oi, os_, oc, wall, engine.topn_last_stats()
+
+    res = {"shape": {"users": args.users, "items": args.items, "k": args.k, "n": args.n, "ignore_per_user": args.ignore}}
+    best = None
+    for r in range(args.reps):
+        oi, os_, oc, wall, st = run(engine._capi.TOPN_AUTO, args.users)
+        if best is None or st["tensor_path_ms"] < best["tensor_path_ms"]:
+            best = dict(st, wall_s=wall)
+    flop = 2.0 * args.users * args.items * args.k
+    res["tensor"] = dict(best, tflops_tf32=flop / (best["tensor_path_ms"] * 1e-3) / 1e12,
+                         users_per_s=args.users / (best["tensor_path_ms"] * 1e-3))
+    ne = min(args.exact_users, args.users)
+    ei, es, ec, wall, st = run(engine._capi.TOPN_EXACT, ne)
+    res["exact_cuda_cores"] = {"users": ne, "wall_s": wall, "users_per_s": ne / wall}
+    res["bit_identical_on_subset"] = bool(np.array_equal(ei, oi[:ne]) and np.array_equal(es.view(np.uint32), os_[:ne].view(np.uint32))
+                                          and np.array_equal(ec, oc[:ne]))
+    engine.topn_set_mode(engine._capi.TOPN_AUTO)
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

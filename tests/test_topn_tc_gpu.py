@@ -97,7 +97,7 @@ def test_undecidable_users_fall_back_to_exact_scoring(eng):
     """Scores packed closer together than the TF32 error bound: the filter must notice and hand the users over."""
     engine, ctx = eng
     rs = np.random.RandomState(8)
-    k, nu, ni = 128, 300, 4000
+    k, nu, ni = 128, 300, 40000                                          # > 256 near-ties per candidate split
     base = rs.randn(k).astype(np.float32)
     V = (base[None, :] + 1e-5 * rs.randn(ni, k)).astype(np.float32)     # all items score within ~1e-4 relative
     U = (rs.randn(nu, k) * 0.1).astype(np.float32)
