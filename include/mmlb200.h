@@ -238,6 +238,14 @@ int32_t mml_wrmf_get_model(mml_wrmf* m, float* user_factors, float* item_factors
 /* WRMF.Iterate (WRMF.cs:68-73): user half-sweep then item half-sweep. */
 int32_t mml_wrmf_iterate(mml_wrmf* m);
 int32_t mml_wrmf_stats(mml_wrmf* m, int64_t* kernel_launches, float* last_iterate_ms);
+/* Engine knob: AUTO = per-row Gram sums sum_{i in S_u} h_i h_i^T on the tcgen05 tensor cores (3 x TF32 split, fp32-accurate)
+ * with HH, the assembly and the blocked Cholesky solve in double (num_factors a multiple of 4, <= 128), the all-double
+ * CUDA-core kernels otherwise; FP64 / TENSOR force one of them. */
+enum { MML_WRMF_AUTO = 0, MML_WRMF_FP64 = 1, MML_WRMF_TENSOR = 2 };
+int32_t mml_wrmf_set_mode(int32_t mode);
+/* Diagnostic for the parity tests: the tensor-core Gram sum (128 x 128 floats, zero beyond num_factors) of the user with
+ * the most events, and that user's id. The model is not modified. */
+int32_t mml_wrmf_debug_gram(mml_wrmf* m, float* out_gram, int32_t* out_user);
 /* mml_topn_mf on the device-resident model (no factor upload). */
 int32_t mml_wrmf_recommend(mml_wrmf* m, const int32_t* users, int64_t n_users, int32_t n,
                            const int32_t* candidates, int64_t n_cand,

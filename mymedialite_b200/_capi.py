@@ -108,11 +108,14 @@ SIGNATURES = {
     "mml_wrmf_get_model": (C.c_int32, [vp, of32p, of32p]),
     "mml_wrmf_iterate": (C.c_int32, [vp]),
     "mml_wrmf_stats": (C.c_int32, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    "mml_wrmf_set_mode": (C.c_int32, [C.c_int32]),
+    "mml_wrmf_debug_gram": (C.c_int32, [vp, f32p, C.POINTER(C.c_int32)]),
     "mml_wrmf_recommend": (C.c_int32, [vp, oi32p, C.c_int64, C.c_int32, oi32p, C.c_int64, oi64p, oi32p, i32p, f32p, i32p]),
     "mml_sgd_schedule_dump": (C.c_int32, [vp, oi32p, i32p, oi32p, oi32p, oi32p]),
 }
 
 TOPN_AUTO, TOPN_EXACT, TOPN_TENSOR = 0, 1, 2
+WRMF_AUTO, WRMF_FP64, WRMF_TENSOR = 0, 1, 2
 
 _lib = None
 

@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 
 namespace mml {
@@ -28,10 +29,10 @@ constexpr int TC_ROWS = 256;                  // users per CTA: two 128-row MMA 
 constexpr int TC_N = 128;                     // candidates per MMA tile
 constexpr int TC_KC = 32;                     // floats per K chunk = one 128-byte swizzle atom
 constexpr int TC_CHUNK_BYTES = 128 * 128;     // 128 rows x 128 bytes
-constexpr int TC_CAP = 256;                   // candidates collected per user (and per candidate split) before the user is handed to the exact path
+constexpr int TC_CAP = 128;                   // candidates collected per epilogue thread (2 threads per user and candidate split) before the user goes to the exact path
 constexpr int TC_SAMPLE = 16384;              // target size of the candidate sample the threshold comes from
 constexpr int TC_MAX_N = 16;                  // largest n served by this path
-constexpr int TC_THREADS = 320;               // warp 0: TMA, warp 1: MMA issue + TMEM, warps 2-9: epilogue
+constexpr int TC_THREADS = 576;               // warp 0: TMA, warp 1: MMA issue + TMEM, warps 2-17: epilogue (2 threads per user row)
 constexpr float TC_ERR_C = 0.0025f;           // |tf32 score - exact| <= TC_ERR_C * |u| * |v| (2^-9 truncation + slack)
 constexpr int TC_MAX_SPLITS = 32;
 
@@ -108,26 +109,28 @@ struct TcArgs {
     int32_t stride;                 // column j of the V panel is candidate position j * stride (1 when collecting)
     int32_t kc;                     // K chunks (kp / 32)
     int32_t stages;                 // V ring depth
+    int32_t list_off;               // byte offset of the sampling lists behind the aligned operand area
     int32_t n_tiles, tiles_per_split, splits;
     int32_t n_cols;                 // real columns of the V panel (the rest is zero padding)
     int32_t m;                      // sampling pass: length of the per-user sorted list (>= n)
+    int32_t dbg;                    // experiments (MMLB200_TC_DBG): 1 = epilogue does not examine, 2 = no MMAs are issued
     const uint8_t* row_ok;          // [n_rows] user id inside the model
     const uint32_t* bad;            // NULL, or [n_tiles * 4]: bit c of word g set = column 32 g + c is an id outside the model
     const int64_t* ign_ptr;         // [n_rows + 1] or NULL
     const int32_t* ign_pos;         // candidate POSITIONS of the user's ignore_items, ascending inside a row
     float* thr;                     // [n_rows] sampling pass: out, m-th best sampled score; collecting pass: in, threshold
-    float* buf_s; int32_t* buf_p;   // collecting pass: [n_rows][splits][TC_CAP] approximate score, position
-    int32_t* buf_n;                 // [n_rows][splits] entries wanted (> TC_CAP = overflow)
+    float* buf_s; int32_t* buf_p;   // collecting pass: [n_rows][splits][2][TC_CAP] approximate score, position
+    int32_t* buf_n;                 // [n_rows][splits][2] entries wanted (> TC_CAP = overflow)
     uint32_t* err;
 };
 
-// Sampling pass slow path: s enters the sorted list ls[0 .. m) (stride 256 floats: one column of shared memory per thread).
+// Sampling pass slow path: s enters the sorted list ls[0 .. m) (stride 512 floats: one column of shared memory per thread).
 __device__ __noinline__ float tc_insert(float* ls, int m, float s)
 {
     int j = m - 1;
-    while (j > 0 && ls[(j - 1) * TC_ROWS] < s) { ls[j * TC_ROWS] = ls[(j - 1) * TC_ROWS]; j--; }
-    ls[j * TC_ROWS] = s;
-    return ls[(m - 1) * TC_ROWS];
+    while (j > 0 && ls[(j - 1) * 2 * TC_ROWS] < s) { ls[j * 2 * TC_ROWS] = ls[(j - 1) * 2 * TC_ROWS]; j--; }
+    ls[j * 2 * TC_ROWS] = s;
+    return ls[(m - 1) * 2 * TC_ROWS];
 }
 
 // MODE 0 (sampling): every thread keeps the m best approximate scores of its user over a strided sample of the candidates;
@@ -144,7 +147,7 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
     const uint32_t smem0 = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_u = smem0;                                               // [2][kc] chunks
     const uint32_t smem_v = smem0 + 2u * a.kc * TC_CHUNK_BYTES;                  // [stages] chunks
-    float* lists = reinterpret_cast<float*>(tc_smem_raw + (smem0 - smem_u32(tc_smem_raw)) + (size_t)(2 * a.kc + a.stages) * TC_CHUNK_BYTES);
+    float* lists = reinterpret_cast<float*>(tc_smem_raw + (smem0 - smem_u32(tc_smem_raw)) + (size_t)a.list_off);
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * 8, bar_u = bar_full + 16 * 8;
     const uint32_t bar_tfull = bar_full + 17 * 8, bar_tempty = bar_full + 19 * 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -155,7 +158,7 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.stages; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_u, 1);
-        for (int b = 0; b < 2; b++) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 8); }
+        for (int b = 0; b < 2; b++) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 16); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {    // TMEM: 512 columns = 2 buffers x 2 row halves x 128 fp32 columns
@@ -201,6 +204,7 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
                     for (int h = 0; h < 2; h++) {
                         const uint32_t ub = smem_u + (uint32_t)(h * a.kc + c) * TC_CHUNK_BYTES;
                         const uint32_t d = tmem_base + (uint32_t)((buf * 2 + h) * TC_N);
+                        if (a.dbg & 2) continue;
 #pragma unroll
                         for (int kk = 0; kk < 4; kk++)
                             tc_mma_tf32(d, tc_smem_desc(ub + kk * 32), tc_smem_desc(vb + kk * 32), TC_IDESC, (c | kk) != 0 ? 1u : 0u);
@@ -212,22 +216,24 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
             }
         }
     } else {
-        // ===== epilogue: 8 warps, thread <-> user row =====
+        // ===== epilogue: 16 warps; two threads per user row, each examines two of the four 32-column groups of a tile =====
+        const int e = warp - 2;
         const int q = warp & 3;                                // TMEM lane quarter this warp may read
-        const int h = (warp - 2) >> 2;                         // row half
+        const int h = (e >> 2) & 1;                            // row half
+        const int part = e >> 3;                               // column groups 2 part, 2 part + 1 of every tile
         const int rloc = h * 128 + q * 32 + lane;
         const int row = row0 + rloc;
         const bool ok = row < a.n_rows && a.row_ok[row];
-        float* ls = lists + rloc;
+        float* ls = lists + part * TC_ROWS + rloc;             // entry j at ls[j * 2 * TC_ROWS]
         float thr;
         if (MODE == 0) {
-            for (int j = 0; j < a.m; j++) ls[j * TC_ROWS] = -INFINITY;
+            for (int j = 0; j < a.m; j++) ls[j * 2 * TC_ROWS] = -INFINITY;
             thr = ok ? -INFINITY : INFINITY;
         } else {
             thr = ok ? a.thr[row] : INFINITY;
         }
         int cnt = 0;
-        const size_t bbase = ((size_t)(ok ? row : 0) * a.splits + sp) * TC_CAP;
+        const size_t bbase = (((size_t)(ok ? row : 0) * a.splits + sp) * 2 + part) * TC_CAP;
         int64_t ig = 0, ig_end = 0;
         int32_t ig_next = 0x7fffffff;
         if (ok && a.ign_ptr) {
@@ -235,21 +241,23 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
             if (ig < ig_end) ig_next = a.ign_pos[ig];
         }
         const long long st = a.stride;
-        const int n_groups = (t_end - t_begin) * (TC_N / 32);
+        const int n_groups = (t_end - t_begin) * 2;
         // group gi = 32 consecutive columns; its accumulators are fetched while group gi - 1 is being examined
         uint32_t va[32], vb[32];
         auto fetch = [&](int gi, uint32_t (&v)[32]) {
-            const int it = gi / (TC_N / 32), j = gi % (TC_N / 32);
+            const int it = gi >> 1, j = part * 2 + (gi & 1);
             const int buf = it & 1;
-            if (j == 0) {
-                mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u, a.err);
+            if ((gi & 1) == 0) {      // one lane polls: 512 threads spinning on the barrier unit delay the MMA / TMA hand-overs
+                if (lane == 0) mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u, a.err);
+                __syncwarp();
                 tc_fence_after();
             }
             __syncwarp();
             tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + h) * TC_N + j * 32), v);
         };
         auto examine = [&](int gi, uint32_t (&v)[32]) {
-            const int g = t_begin * (TC_N / 32) + gi;
+            if (a.dbg & 1) return;
+            const int g = (t_begin + (gi >> 1)) * (TC_N / 32) + part * 2 + (gi & 1);
             const int col0 = g * 32;
             uint32_t mask = a.bad ? a.bad[g] : 0u;
             if (col0 + 32 > a.n_cols) mask |= col0 >= a.n_cols ? 0xffffffffu : (0xffffffffu << (a.n_cols - col0));
@@ -265,35 +273,50 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
 #pragma unroll
                 for (int c = 0; c < 32; c++) if ((mask >> c) & 1u) v[c] = 0x7fc00000u;      // NaN: fails every comparison, fmaxf skips it
             }
-            float m = __uint_as_float(v[0]);
+            float m8[4];
 #pragma unroll
-            for (int c = 1; c < 32; c++) m = fmaxf(m, __uint_as_float(v[c]));
+            for (int i = 0; i < 4; i++) {
+                m8[i] = __uint_as_float(v[8 * i]);
+#pragma unroll
+                for (int c = 1; c < 8; c++) m8[i] = fmaxf(m8[i], __uint_as_float(v[8 * i + c]));
+            }
+            const float m = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
             if (MODE == 0) {
                 if (m > thr) {
 #pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const float s = __uint_as_float(v[c]);
-                        if (s > thr) thr = tc_insert(ls, a.m, s);
+                    for (int i = 0; i < 4; i++) {
+                        if (m8[i] > thr) {
+#pragma unroll
+                            for (int c = 8 * i; c < 8 * i + 8; c++) {
+                                const float s = __uint_as_float(v[c]);
+                                if (s > thr) thr = tc_insert(ls, a.m, s);
+                            }
+                        }
                     }
                 }
             } else {
                 if (m >= thr) {
 #pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const float s = __uint_as_float(v[c]);
-                        if (s >= thr) {
-                            if (cnt < TC_CAP) { a.buf_s[bbase + cnt] = s; a.buf_p[bbase + cnt] = col0 + c; }
-                            cnt++;
+                    for (int i = 0; i < 4; i++) {
+                        if (m8[i] >= thr) {
+#pragma unroll
+                            for (int c = 8 * i; c < 8 * i + 8; c++) {
+                                const float s = __uint_as_float(v[c]);
+                                if (s >= thr) {
+                                    if (cnt < TC_CAP) { a.buf_s[bbase + cnt] = s; a.buf_p[bbase + cnt] = col0 + c; }
+                                    cnt++;
+                                }
+                            }
                         }
                     }
                 }
             }
         };
         auto release = [&](int gi) {      // last group of a tile examined: its TMEM buffer may be overwritten
-            if (gi % (TC_N / 32) == TC_N / 32 - 1) {
+            if (gi & 1) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty + 8 * ((gi / (TC_N / 32)) & 1));
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * ((gi >> 1) & 1));
             }
         };
         if (n_groups > 0) fetch(0, va);
@@ -309,9 +332,21 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
                 release(gi + 1);
             }
         }
-        if (ok) {
-            if (MODE == 0) a.thr[row] = thr;
-            else a.buf_n[(size_t)row * a.splits + sp] = cnt;
+        if (MODE == 0) {
+            // the user's two threads hold the m best of their halves of the sample (sorted): m-th best of the union
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (ok && part == 0) {
+                const float* la = lists + rloc; const float* lb = lists + TC_ROWS + rloc;
+                int ia = 0, ib = 0;
+                float t = -INFINITY;
+                for (int x = 0; x < a.m; x++) {
+                    const float fa = la[ia * 2 * TC_ROWS], fb = lb[ib * 2 * TC_ROWS];
+                    if (fa >= fb) { t = fa; ia++; } else { t = fb; ib++; }
+                }
+                a.thr[row] = t;
+            }
+        } else if (ok) {
+            a.buf_n[((size_t)row * a.splits + sp) * 2 + part] = cnt;
         }
     }
     tc_fence_before();
@@ -426,7 +461,8 @@ __global__ void tc_finalize_kernel(const FinArgs a)
 {
     extern __shared__ uint8_t fin_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int E_max = a.splits * TC_CAP;
+    const int parts = a.splits * 2;                                                  // two collecting threads per user and split
+    const int E_max = parts * TC_CAP;
     float* ap = reinterpret_cast<float*>(fin_smem) + (size_t)warp * E_max * 3;      // approximate scores
     int32_t* pp = reinterpret_cast<int32_t*>(ap + E_max);                            // positions
     float* ex = reinterpret_cast<float*>(pp + E_max);                                // exact scores
@@ -436,10 +472,10 @@ __global__ void tc_finalize_kernel(const FinArgs a)
     // 1. gather what the splits collected; a split that wanted more than TC_CAP entries lost some
     int E = 0;
     bool overflow = false;
-    for (int s = 0; s < a.splits; s++) {
-        const int c = a.buf_n[(size_t)b * a.splits + s];
+    for (int s = 0; s < parts; s++) {
+        const int c = a.buf_n[(size_t)b * parts + s];
         if (c > TC_CAP) { overflow = true; break; }
-        const size_t base = ((size_t)b * a.splits + s) * TC_CAP;
+        const size_t base = ((size_t)b * parts + s) * TC_CAP;
         for (int e = lane; e < c; e += 32) { ap[E + e] = a.buf_s[base + e]; pp[E + e] = a.buf_p[base + e]; }
         E += c;
     }
@@ -574,8 +610,8 @@ static int32_t tc_prepare_candidates(Ctx* ctx, TcCandidates& c, const float* d_V
 
 // Per-batch buffers of one Recommend() call, allocated once for the largest batch.
 struct TcWork {
-    int32_t cap_users = 0, splits = 1, tps = 1, stages = 2;
-    size_t smem = 0;
+    int32_t cap_users = 0, splits = 1, tps = 1, stages = 2, stages0 = 2;
+    size_t smem = 0, smem0 = 0;
     DevBuf<float> Ub, unorm, thr, d2, buf_s, out_s;
     DevBuf<uint8_t> row_ok, redo;
     DevBuf<uint32_t> err;
@@ -597,8 +633,8 @@ static int32_t tc_alloc_work(Ctx* ctx, TcWork& w, const TcCandidates& c, int32_t
     MML_TRY(w.Ub.alloc((size_t)rows_pad * c.kp));
     MML_TRY(w.unorm.alloc(cap_users)); MML_TRY(w.thr.alloc(cap_users)); MML_TRY(w.d2.alloc(cap_users));
     MML_TRY(w.row_ok.alloc(cap_users)); MML_TRY(w.redo.alloc(cap_users)); MML_TRY(w.err.alloc(1));
-    MML_TRY(w.buf_s.alloc((size_t)cap_users * w.splits * TC_CAP)); MML_TRY(w.buf_p.alloc((size_t)cap_users * w.splits * TC_CAP));
-    MML_TRY(w.buf_n.alloc((size_t)cap_users * w.splits));
+    MML_TRY(w.buf_s.alloc((size_t)cap_users * w.splits * 2 * TC_CAP)); MML_TRY(w.buf_p.alloc((size_t)cap_users * w.splits * 2 * TC_CAP));
+    MML_TRY(w.buf_n.alloc((size_t)cap_users * w.splits * 2));
     MML_TRY(w.users.alloc(cap_users)); MML_TRY(w.out_i.alloc((size_t)cap_users * n_out)); MML_TRY(w.out_s.alloc((size_t)cap_users * n_out));
     MML_TRY(w.out_c.alloc(cap_users));
     if (max_ign > 0) {
@@ -607,12 +643,15 @@ static int32_t tc_alloc_work(Ctx* ctx, TcWork& w, const TcCandidates& c, int32_t
     }
     int max_optin = 0;
     MML_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-    const int64_t list_bytes = (int64_t)TC_ROWS * TC_MAX_N * sizeof(float);
-    const int64_t fixed = 2ll * c.kc * TC_CHUNK_BYTES + 1024 + 512 + list_bytes;      // U panels, alignment slack, static barriers, sample lists
+    // the sampling pass keeps 2 x 256 sorted lists of up to TC_MAX_N floats behind the operand area, the collecting pass does not
+    const int64_t list_bytes = 2ll * TC_ROWS * TC_MAX_N * sizeof(float);
+    const int64_t fixed = 2ll * c.kc * TC_CHUNK_BYTES + 1024 + 512;      // U panels, alignment slack, static barriers
+    w.stages0 = (int)std::min<int64_t>(8, (max_optin - fixed - list_bytes) / TC_CHUNK_BYTES);
     w.stages = (int)std::min<int64_t>(8, (max_optin - fixed) / TC_CHUNK_BYTES);
-    MML_CHECK(w.stages >= 2, MML_ERR_UNSUPPORTED, "topn: shared memory too small for the tcgen05 path");
-    w.smem = (size_t)(2ll * c.kc + w.stages) * TC_CHUNK_BYTES + 1024 + list_bytes;
-    MML_CUDA(cudaFuncSetAttribute((const void*)score_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+    MML_CHECK(w.stages0 >= 2, MML_ERR_UNSUPPORTED, "topn: shared memory too small for the tcgen05 path");
+    w.smem0 = (size_t)(2ll * c.kc + w.stages0) * TC_CHUNK_BYTES + 1024 + list_bytes;
+    w.smem = (size_t)(2ll * c.kc + w.stages) * TC_CHUNK_BYTES + 1024;
+    MML_CUDA(cudaFuncSetAttribute((const void*)score_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem0));
     MML_CUDA(cudaFuncSetAttribute((const void*)score_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
     return MML_OK;
 }
@@ -658,18 +697,21 @@ static int32_t topn_tc_batch(Ctx* ctx, TcCandidates& c, TcWork& w, const float* 
     MML_TRY(make_panel_map(&map_u, w.Ub.p, rows_pad, kp));
     const int row_tiles = (int)(rows_pad / TC_ROWS);
     TcArgs a{};
-    a.n_rows = n_users; a.kc = kc; a.stages = w.stages; a.m = n;
+    a.n_rows = n_users; a.kc = kc; a.m = n;
+    { const char* e = getenv("MMLB200_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
     a.row_ok = w.row_ok.p; a.ign_ptr = have_ign ? w.ign_ptr.p : nullptr; a.ign_pos = w.ign_idx.p;
     a.thr = w.thr.p; a.err = w.err.p;
     // pass 1: threshold from the candidate sample
     a.stride = c.stride; a.n_tiles = (int)(c.samp_pad / TC_N); a.tiles_per_split = a.n_tiles; a.splits = 1;
+    a.stages = w.stages0; a.list_off = (2 * kc + w.stages0) * TC_CHUNK_BYTES;
     a.n_cols = c.n_samp; a.bad = c.has_bad ? c.bad_s.p : nullptr;
-    score_select_kernel<0><<<dim3(row_tiles, 1), TC_THREADS, w.smem, s>>>(map_u, c.map_s, a);
+    score_select_kernel<0><<<dim3(row_tiles, 1), TC_THREADS, w.smem0, s>>>(map_u, c.map_s, a);
     MML_CUDA(cudaGetLastError());
     tc_threshold_kernel<<<(unsigned)ceil_div(n_users, 256), 256, 0, s>>>(w.thr.p, w.d2.p, w.unorm.p, c.vmax.p, n_users);
     MML_CUDA(cudaGetLastError());
     // pass 2: collect every candidate that reaches it
-    MML_CUDA(cudaMemsetAsync(w.buf_n.p, 0, sizeof(int32_t) * (size_t)n_users * w.splits, s));
+    MML_CUDA(cudaMemsetAsync(w.buf_n.p, 0, sizeof(int32_t) * (size_t)n_users * w.splits * 2, s));
+    a.stages = w.stages; a.list_off = 0;
     a.stride = 1; a.n_tiles = (int)(c.cand_pad / TC_N); a.tiles_per_split = w.tps; a.splits = w.splits;
     a.n_cols = c.n_cand; a.bad = c.has_bad ? c.bad_b.p : nullptr;
     a.buf_s = w.buf_s.p; a.buf_p = w.buf_p.p; a.buf_n = w.buf_n.p;
@@ -680,7 +722,7 @@ static int32_t topn_tc_batch(Ctx* ctx, TcCandidates& c, TcWork& w, const float* 
     f.buf_s = w.buf_s.p; f.buf_p = w.buf_p.p; f.buf_n = w.buf_n.p; f.thr = w.thr.p; f.d2 = w.d2.p; f.row_ok = w.row_ok.p;
     f.n_rows = n_users; f.splits = w.splits; f.n = n; f.n_out = n_out;
     f.out_items = w.out_i.p; f.out_scores = w.out_s.p; f.out_counts = w.out_c.p; f.redo = w.redo.p;
-    const size_t per_warp = (size_t)w.splits * TC_CAP * 12;
+    const size_t per_warp = (size_t)w.splits * 2 * TC_CAP * 12;
     f.warps = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)96 * 1024 / per_warp));
     const size_t fsmem = per_warp * f.warps;
     MML_CUDA(cudaFuncSetAttribute((const void*)tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
@@ -690,6 +732,19 @@ static int32_t topn_tc_batch(Ctx* ctx, TcCandidates& c, TcWork& w, const float* 
     return MML_OK;
 }
 
+static bool tc_trace() { static int t = -1; if (t < 0) { const char* e = getenv("MMLB200_TRACE"); t = (e && *e && *e != '0') ? 1 : 0; } return t == 1; }
+struct TcPhase {
+    cudaStream_t s; std::chrono::steady_clock::time_point t0;
+    explicit TcPhase(cudaStream_t st) : s(st) { if (tc_trace()) { cudaStreamSynchronize(s); t0 = std::chrono::steady_clock::now(); } }
+    void mark(const char* what) {
+        if (!tc_trace()) return;
+        cudaStreamSynchronize(s);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mmlb200 topn] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 // All user batches of one Recommend() call. users / ignore CSR / outputs: host. d_cand: device or NULL.
 int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
                     const int32_t* users, int64_t n_users, int32_t n, int32_t n_out, const int32_t* d_cand, int32_t n_cand,
@@ -697,8 +752,10 @@ int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
                     int32_t* out_items, float* out_scores, int32_t* out_counts, std::vector<int64_t>& redo_users, int64_t* launches)
 {
     cudaStream_t s = ctx->stream;
+    TcPhase ph(s);
     TcCandidates c;
     MML_TRY(tc_prepare_candidates(ctx, c, d_V, n_model_items, k, d_cand, n_cand, has_invalid_cand, n, launches));
+    ph.mark("candidate panels");
     const int64_t n_ign = (ignore_ptr && ignore_idx) ? ignore_ptr[n_users] : 0;
     const int64_t B = 1 << 18;                       // users per pass (staging panel 128 MB, collect buffers 512 MB)
     int64_t max_ign = 0;
@@ -707,6 +764,7 @@ int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
             max_ign = std::max(max_ign, ignore_ptr[std::min(b_lo + B, n_users)] - ignore_ptr[b_lo]);
     TcWork w;
     MML_TRY(tc_alloc_work(ctx, w, c, (int32_t)std::min<int64_t>(B, n_users), n_out, max_ign));
+    ph.mark("workspace alloc");
     std::vector<uint8_t> h_redo;
     std::vector<int64_t> ptr_local;
     for (int64_t b_lo = 0; b_lo < n_users; b_lo += B) {
@@ -724,7 +782,9 @@ int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
             if (nib > 0) MML_CUDA(cudaMemcpyAsync(w.ign_idx.p, ignore_idx + i_lo, sizeof(int32_t) * (size_t)nib, cudaMemcpyHostToDevice, s));
             MML_CUDA(cudaStreamSynchronize(s));      // ptr_local is reused by the next batch
         }
+        ph.mark("batch H2D");
         MML_TRY(topn_tc_batch(ctx, c, w, d_U, n_model_users, d_V, n_model_items, k, nb, n, n_out, d_cand, nib, launches));
+        ph.mark("batch kernels");
         h_redo.resize(nb);
         MML_CUDA(cudaMemcpyAsync(out_items + (size_t)b_lo * n_out, w.out_i.p, sizeof(int32_t) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, s));
         MML_CUDA(cudaMemcpyAsync(out_scores + (size_t)b_lo * n_out, w.out_s.p, sizeof(float) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, s));
@@ -735,6 +795,7 @@ int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
         MML_CUDA(cudaMemcpy(&h_err, w.err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
         MML_CHECK(h_err == 0, MML_ERR_CUDA, "topn: tcgen05 pipeline timed out");
         for (int32_t t = 0; t < nb; t++) if (h_redo[t]) redo_users.push_back(b_lo + t);
+        ph.mark("batch D2H");
     }
     return MML_OK;
 }

@@ -46,6 +46,7 @@ struct Wrmf {
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
+    struct WrmfTcWork* tc_work = nullptr;  // tensor-path buffers (wrmf_tc.cu), grow-only
 };
 
 static inline int grid_n(int64_t n, int threads = 256)
@@ -297,6 +298,16 @@ __global__ void __launch_bounds__(AT) als_rows_kernel(const uint32_t* __restrict
     }
 }
 
+struct WrmfTcWork;
+WrmfTcWork* wrmf_tc_work_create();
+void wrmf_tc_work_destroy(WrmfTcWork* w);
+bool wrmf_tc_eligible(int32_t k);
+int32_t wrmf_tc_half_sweep(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_ptr, const int32_t* cols, const int32_t* order, int32_t n_rows,
+                           float* W, const float* H, int32_t k, const double* HH, double alpha, double reg, int64_t* launches,
+                           float* debug_G_row0);
+static int g_wrmf_mode = 0;            // MML_WRMF_AUTO
+static float* g_wrmf_debug_G = nullptr;
+
 typedef void (*gram_fn_t)(const float*, int32_t, int32_t, double*);
 typedef void (*als_fn_t)(const uint32_t*, const int32_t*, const int32_t*, int32_t, float*, const float*, int32_t,
                          const double*, double, double, unsigned*);
@@ -325,6 +336,16 @@ static int32_t half_sweep(Wrmf& m, const uint32_t* row_ptr, const int32_t* cols,
     gf<<<n_part, AT, sizeof(float) * HB * k, s>>>(H, n_h_rows, k, m.HH_part.p);
     gram_reduce_kernel<<<(unsigned)ceil_div(k * k, 256), 256, 0, s>>>(m.HH_part.p, n_part, k * k, m.HH.p);
     MML_CUDA(cudaGetLastError());
+    // AUTO takes the tensor path only when HH sums many more rows than it has columns: with n_h_rows ~ k the system is so
+    // ill-conditioned that the fp32-level rounding of the per-row Gram sums shows above the 1e-4 gate (double does not).
+    const bool tc = g_wrmf_mode != MML_WRMF_FP64 && wrmf_tc_eligible(k) &&
+                    (g_wrmf_mode == MML_WRMF_TENSOR || (int64_t)n_h_rows >= 16ll * k);
+    MML_CHECK(tc || g_wrmf_mode != MML_WRMF_TENSOR, MML_ERR_UNSUPPORTED, "WRMF: num_factors=%d is outside the tensor-core path (multiple of 4, <= 128)", k);
+    if (tc) {
+        m.launches += 2;
+        if (!m.tc_work) m.tc_work = wrmf_tc_work_create();
+        return wrmf_tc_half_sweep(m.ctx, m.tc_work, row_ptr, cols, order, n_rows, W, H, k, m.HH.p, m.alpha, m.reg, &m.launches, g_wrmf_debug_G);
+    }
     const size_t smem = sizeof(double) * ((size_t)k * k + k) + sizeof(float) * HB * k;
     MML_CUDA(cudaFuncSetAttribute((const void*)af, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MML_CUDA(cudaMemsetAsync(m.counter.p, 0, sizeof(unsigned), s));
@@ -429,6 +450,7 @@ extern "C" int32_t mml_wrmf_destroy(mml_wrmf* h)
     cudaStreamSynchronize(h->m.ctx->stream);
     if (h->m.ev0) cudaEventDestroy(h->m.ev0);
     if (h->m.ev1) cudaEventDestroy(h->m.ev1);
+    if (h->m.tc_work) wrmf_tc_work_destroy(h->m.tc_work);
     delete h;
     return MML_OK;
 }
@@ -503,6 +525,35 @@ extern "C" int32_t mml_wrmf_iterate(mml_wrmf* h)
     MML_TRY(half_sweep(m, f.item_ptr.p, f.item_rows.p, m.order_i.p, f.n_items(), m.V.p, m.U.p, f.n_users()));
     MML_CUDA(cudaEventRecord(m.ev1, s));
     m.timed = true;
+    return MML_OK;
+}
+
+extern "C" int32_t mml_wrmf_set_mode(int32_t mode)
+{
+    MML_CHECK(mode >= MML_WRMF_AUTO && mode <= MML_WRMF_TENSOR, MML_ERR_ARG, "mml_wrmf_set_mode: unknown mode %d", mode);
+    g_wrmf_mode = mode;
+    return MML_OK;
+}
+
+// Diagnostic: one user half-sweep on the tensor path; out_gram (128 x 128 floats, row-major, zero beyond k) receives
+// sum_{i in S_u} h_i h_i^T of the user with the most feedback events (the first row of the work queue).
+extern "C" int32_t mml_wrmf_debug_gram(mml_wrmf* h, float* out_gram, int32_t* out_user)
+{
+    MML_CHECK(h && out_gram && out_user, MML_ERR_ARG, "NULL argument");
+    Wrmf& m = h->m;
+    MML_CHECK(m.has_model, MML_ERR_STATE, "mml_wrmf_debug_gram: no model");
+    MML_CHECK(wrmf_tc_eligible(m.k), MML_ERR_UNSUPPORTED, "mml_wrmf_debug_gram: num_factors outside the tensor-core path");
+    MML_CUDA(cudaSetDevice(m.ctx->device));
+    Feedback& f = *m.fb;
+    MML_CHECK(f.n_users() > 0, MML_ERR_STATE, "no users");
+    DevBuf<float> scratch;                      // the sweep's result is discarded: the model is left untouched
+    MML_TRY(scratch.alloc((size_t)f.n_users() * m.k));
+    const int old_mode = g_wrmf_mode;
+    g_wrmf_mode = MML_WRMF_TENSOR; g_wrmf_debug_G = out_gram;
+    const int32_t st = half_sweep(m, f.user_ptr.p, f.user_cols.p, m.order_u.p, f.n_users(), scratch.p, m.V.p, f.n_items());
+    g_wrmf_mode = old_mode; g_wrmf_debug_G = nullptr;
+    MML_TRY(st);
+    MML_CUDA(cudaMemcpy(out_user, m.order_u.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
     return MML_OK;
 }
 

@@ -1,0 +1,553 @@
+// wrmf_tc.cu -- the per-row normal equations of a WRMF half-sweep on the tcgen05 tensor cores (K7 of SURVEY.md 2d).
+//
+// Reference: WRMF.Optimize(u, ...) (ItemRecommendation/WRMF.cs:110-156):
+//     A_u = HH + alpha * sum_{i in S_u} h_i h_i^T + lambda I,   b_u = (1 + alpha) * sum_{i in S_u} h_i,   w_u = A_u^-1 b_u
+//
+// Two kernels per batch of rows:
+//   wrmf_syrk_kernel   G_u = sum_{i in S_u} h_i h_i^T  (k x k) as tcgen05.mma kind::tf32 with BOTH operands taken from one
+//                      shared-memory tile of gathered factor rows (MN-major: a gathered row is contiguous along M = N).
+//                      fp32 accuracy comes from the split h = hi + lo (hi = upper 19 bits, lo = h - hi, exact):
+//                      G = hi hi^T + hi lo^T + lo hi^T  (3 MMAs per 8 rows; lo lo^T ~ 2^-22 relative is dropped).
+//                      Accumulators live in TMEM (4 x 128 columns: four rows in flight); producer warps gather rows
+//                      with 128-bit loads, split them and store both tiles in the 128-byte-swizzled canonical layout;
+//                      epilogue warps read TMEM with tcgen05.ld and write G_u (fp32) to HBM. b_u is accumulated in
+//                      double by the producer lanes on the way.
+//   wrmf_solve_kernel  A_u = HH (fp64, CUDA cores) + alpha * G_u + lambda I in fp64, blocked Cholesky (16-wide panels,
+//                      b_u carried as an extra row so the forward substitution is free), back substitution, w_u -> fp32.
+// Only G_u -- the sum over the row's own few hundred entries, a small part of A_u next to HH -- sees fp32 rounding;
+// HH, the assembly and the solve stay in the reference's double precision (the gate is 1e-4 relative on w_u).
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+namespace mml {
+
+constexpr int WS_THREADS = 288;          // warp 0: MMA issue + TMEM, warps 1-4: gather producers, warps 5-8: epilogue
+constexpr int WS_KCH = 32;               // gathered rows per stage
+constexpr int WS_TILE = WS_KCH * 512;    // one tile: 32 rows x 128 floats = 16 KB
+constexpr int WS_STAGES = 4;             // stage = hi tile + lo tile = 32 KB
+constexpr int WS_KP = 128;
+
+__device__ __forceinline__ uint32_t ws_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ws_mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_wait(uint32_t bar, uint32_t parity, uint32_t* err)
+{
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1u); __threadfence(); asm volatile("trap;"); }
+    }
+}
+__device__ __forceinline__ void ws_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ws_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ws_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void ws_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ws_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void ws_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of one 8-row group of a gathered tile. MN-major 32-bit operands have exactly one legal
+// layout, "128-byte swizzle with 32-byte base" (layout type 1): an atom is 4 K-rows x 128 bytes (32 floats along M/N), the
+// 32-byte chunks of row r are XOR-ed with r; atoms along M/N are LBO = 512 bytes apart, 4-row groups along K SBO = 2048.
+__device__ __forceinline__ uint64_t ws_smem_desc(uint32_t addr)
+{
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(512 >> 4) << 16) | ((uint64_t)(2048 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+// D = F32, A = B = TF32, A and B MN-major (bits 15, 16), N = 128, M = 128
+constexpr uint32_t WS_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct SyrkArgs {
+    const uint32_t* row_ptr; const int32_t* cols;      // CSR of the side being solved
+    const int32_t* order;                              // rows by descending length
+    int32_t q_lo, q_hi;                                // this batch = order[q_lo .. q_hi)
+    const float* H; int32_t k;                         // the fixed factor matrix [*, k], k % 4 == 0, k <= 128
+    float* G;                                          // [q_hi - q_lo][128][128]
+    double* bsum;                                      // [q_hi - q_lo][128], zeroed by the caller
+    uint32_t* err;
+};
+
+__global__ void __launch_bounds__(WS_THREADS, 1) wrmf_syrk_kernel(const SyrkArgs a)
+{
+    extern __shared__ uint8_t ws_smem_raw[];
+    __shared__ uint64_t bars[2 * WS_STAGES + 8];      // full[4], empty[4], tfull[4], tempty[4]
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t smem0 = (ws_smem_u32(ws_smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = ws_smem_raw + (smem0 - ws_smem_u32(ws_smem_raw));
+    const uint32_t bar_full = ws_smem_u32(bars), bar_empty = bar_full + 8 * WS_STAGES;
+    const uint32_t bar_tfull = bar_full + 16 * WS_STAGES, bar_tempty = bar_tfull + 8 * 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WS_STAGES; s++) { ws_mbar_init(bar_full + 8 * s, 4); ws_mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 4; b++) { ws_mbar_init(bar_tfull + 8 * b, 1); ws_mbar_init(bar_tempty + 8 * b, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(ws_smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    ws_fence_before();
+    __syncthreads();
+    ws_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    // every role walks the same row sequence: batch-local rows blockIdx.x, blockIdx.x + gridDim.x, ...; empty rows are skipped
+    if (warp == 0) {
+        if (lane == 0) {    // ===== MMA issuer =====
+            int stage = 0; uint32_t phase = 0; int it = 0;
+            for (int q = a.q_lo + blockIdx.x; q < a.q_hi; q += gridDim.x) {
+                const int u = a.order[q];
+                const uint32_t K = a.row_ptr[u + 1] - a.row_ptr[u];
+                if (K == 0) continue;
+                const int buf = it & 3;
+                ws_mbar_wait(bar_tempty + 8 * buf, ((uint32_t)(it >> 2) & 1u) ^ 1u, a.err);
+                ws_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(buf * 128);
+                bool first = true;
+                for (uint32_t base = 0; base < K; base += WS_KCH) {
+                    ws_mbar_wait(bar_full + 8 * stage, phase, a.err);
+                    ws_fence_after();
+                    const uint32_t hi = smem0 + (uint32_t)stage * 2 * WS_TILE, lo = hi + WS_TILE;
+                    const int groups = (int)min((uint32_t)4, (K - base + 7) / 8);
+                    for (int g = 0; g < groups; g++) {
+                        const uint64_t dh = ws_smem_desc(hi + g * 4096), dl = ws_smem_desc(lo + g * 4096);
+                        ws_mma_tf32(d, dh, dh, WS_IDESC, first ? 0u : 1u);
+                        ws_mma_tf32(d, dh, dl, WS_IDESC, 1u);
+                        ws_mma_tf32(d, dl, dh, WS_IDESC, 1u);
+                        first = false;
+                    }
+                    ws_commit(bar_empty + 8 * stage);
+                    if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
+                }
+                ws_commit(bar_tfull + 8 * buf);
+                it++;
+            }
+        }
+    } else if (warp <= 4) {
+        // ===== gather producers: warp pw takes rows pw, pw + 4, ... of every stage =====
+        const int pw = warp - 1;
+        const int j = lane >> 3, c = lane & 7;           // 128-byte block along M/N and 16-byte chunk inside it
+        const bool col_ok = 4 * lane < a.k;
+        int stage = 0; uint32_t phase = 0;
+        int qi = 0;
+        for (int q = a.q_lo + blockIdx.x; q < a.q_hi; q += gridDim.x, qi++) {
+            const int u = a.order[q];
+            const uint32_t beg = a.row_ptr[u], end = a.row_ptr[u + 1];
+            if (beg == end) continue;
+            double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+            for (uint32_t base = beg; base < end; base += WS_KCH) {
+                // ids of this warp's 8 rows, then all 8 row loads in flight
+                int32_t idv = -1;
+                if (lane < 8) { const uint32_t e = base + pw + 4 * lane; if (e < end) idv = a.cols[e]; }
+                float4 x[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int32_t id = __shfl_sync(0xffffffffu, idv, i);
+                    x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (id >= 0 && col_ok) x[i] = __ldg(reinterpret_cast<const float4*>(a.H + (size_t)id * a.k) + lane);
+                }
+                ws_mbar_wait(bar_empty + 8 * stage, phase ^ 1u, a.err);
+                uint8_t* hi = smem_gen + (size_t)stage * 2 * WS_TILE; uint8_t* lo = hi + WS_TILE;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int r = pw + 4 * i, kg = r >> 2, rr = r & 3;
+                    const uint32_t off = (uint32_t)(kg * 2048 + j * 512 + rr * 128 + (((c >> 1) ^ rr) << 5) + ((c & 1) << 4));
+                    float4 h4, l4;
+                    h4.x = __uint_as_float(__float_as_uint(x[i].x) & 0xFFFFE000u); l4.x = x[i].x - h4.x;
+                    h4.y = __uint_as_float(__float_as_uint(x[i].y) & 0xFFFFE000u); l4.y = x[i].y - h4.y;
+                    h4.z = __uint_as_float(__float_as_uint(x[i].z) & 0xFFFFE000u); l4.z = x[i].z - h4.z;
+                    h4.w = __uint_as_float(__float_as_uint(x[i].w) & 0xFFFFE000u); l4.w = x[i].w - h4.w;
+                    *reinterpret_cast<float4*>(hi + off) = h4;
+                    *reinterpret_cast<float4*>(lo + off) = l4;
+                    b0 += (double)x[i].x; b1 += (double)x[i].y; b2 += (double)x[i].z; b3 += (double)x[i].w;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA's async proxy
+                __syncwarp();
+                if (lane == 0) ws_mbar_arrive(bar_full + 8 * stage);
+                if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
+            }
+            if (col_ok) {
+                double* bs = a.bsum + (size_t)(q - a.q_lo) * WS_KP + 4 * lane;
+                atomicAdd(bs, b0); atomicAdd(bs + 1, b1); atomicAdd(bs + 2, b2); atomicAdd(bs + 3, b3);
+            }
+        }
+    } else {
+        // ===== epilogue: thread <-> row m of G_u =====
+        const int qd = warp & 3;
+        const int m = qd * 32 + lane;
+        int it = 0;
+        for (int q = a.q_lo + blockIdx.x; q < a.q_hi; q += gridDim.x) {
+            const int u = a.order[q];
+            if (a.row_ptr[u + 1] == a.row_ptr[u]) continue;
+            const int buf = it & 3;
+            ws_mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 2) & 1u, a.err);
+            ws_fence_after();
+            float* out = a.G + ((size_t)(q - a.q_lo) * WS_KP + m) * WS_KP;
+#pragma unroll 1
+            for (int jj = 0; jj < 4; jj++) {
+                uint32_t v[32];
+                __syncwarp();
+                ws_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * 128 + jj * 32), v);
+                ws_ld_wait();
+#pragma unroll
+                for (int c4 = 0; c4 < 8; c4++)
+                    reinterpret_cast<float4*>(out + jj * 32)[c4] = make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
+                                                                               __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
+            }
+            ws_fence_before();
+            __syncwarp();
+            if (lane == 0) ws_mbar_arrive(bar_tempty + 8 * buf);
+            it++;
+        }
+    }
+    ws_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        ws_fence_after();
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- assembly + blocked Cholesky solve + iterative refinement, one CTA per row --------------------------------------
+// A_u is held as its lower triangle in 16 x 16 blocks (rows padded to 17 doubles: conflict-free row and column access),
+// block (bi, bj), bj <= bi, at index bi (bi + 1) / 2 + bj: 78 KB at k = 128, so two rows are in flight per SM.
+//   1. A~ = HH + alpha G~ + lambda I with the tensor cores' fp32-accurate G~;   A~ = L L^T (right-looking, 16-wide panels)
+//   2. w = L^-T L^-1 b
+//   3. refinement: r = b - A w with A applied EXACTLY in double straight from the factor rows
+//      (A w = HH w + lambda w + alpha sum_i h_i (h_i . w): 2 k flops per entry instead of k^2), w += L^-T L^-1 r,
+//      until |r| <= 1e-10 |b| (at most SV_MAX_REFINE steps). The fp32 rounding of G~ therefore only slows convergence;
+//      the solution is the double-precision one as long as cond(A) * 1e-6 < 1.
+constexpr int SV_THREADS = 256;
+constexpr int SV_NB = 16;
+constexpr int SV_LD = 17;
+constexpr int SV_BLK = SV_NB * SV_LD;
+constexpr int SV_MAX_REFINE = 3;
+
+struct SolveArgs {
+    const uint32_t* row_ptr; const int32_t* cols; const int32_t* order; int32_t q_lo, q_hi;
+    const float* G; const double* bsum; const double* HH;   // HH [k][k] fp64
+    const float* H;                                         // the fixed factor matrix (refinement gathers it again)
+    double alpha, reg;
+    int32_t k;
+    float* W;                                               // [*, k] the factor matrix being solved
+};
+
+__device__ __forceinline__ double* sv_blk(double* L, int bi, int bj) { return L + (size_t)(bi * (bi + 1) / 2 + bj) * SV_BLK; }
+
+// x <- L^-1 x (forward) for the vector x[0 .. kp), blocked; all threads of the CTA call it
+__device__ __forceinline__ void sv_forward(double* L, const double* rdiag, double* x, int np)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int p = 0; p < np; p++) {
+        const int j0 = p * SV_NB;
+        if (warp == 0) {
+            const double* D = sv_blk(L, p, p);
+            for (int c = 0; c < SV_NB; c++) {
+                if (lane == c) x[j0 + c] *= rdiag[j0 + c];
+                __syncwarp();
+                const double y = x[j0 + c];
+                if (lane > c && lane < SV_NB) x[j0 + lane] -= D[lane * SV_LD + c] * y;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int i = j0 + SV_NB + tid; i < np * SV_NB; i += SV_THREADS) {
+            const double* B = sv_blk(L, i / SV_NB, p) + (i % SV_NB) * SV_LD;
+            double s = 0.0;
+#pragma unroll
+            for (int t = 0; t < SV_NB; t++) s += B[t] * x[j0 + t];
+            x[i] -= s;
+        }
+        __syncthreads();
+    }
+}
+
+// x <- L^-T x (backward)
+__device__ __forceinline__ void sv_backward(double* L, const double* rdiag, double* x, int np)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int p = np - 1; p >= 0; p--) {
+        const int j0 = p * SV_NB;
+        if (warp == 0) {
+            const double* D = sv_blk(L, p, p);
+            for (int c = SV_NB - 1; c >= 0; c--) {
+                if (lane == c) x[j0 + c] *= rdiag[j0 + c];
+                __syncwarp();
+                const double w = x[j0 + c];
+                if (lane < c) x[j0 + lane] -= D[c * SV_LD + lane] * w;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < j0; j += SV_THREADS) {
+            const double* B = sv_blk(L, p, j / SV_NB) + (j % SV_NB);
+            double s = 0.0;
+#pragma unroll
+            for (int t = 0; t < SV_NB; t++) s += B[t * SV_LD] * x[j0 + t];
+            x[j] -= s;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveArgs a)
+{
+    extern __shared__ double sv_smem[];
+    const int k = a.k, np = (k + SV_NB - 1) / SV_NB, kp = np * SV_NB;
+    const int q = a.q_lo + blockIdx.x;
+    if (q >= a.q_hi) return;
+    const int u = a.order[q];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t beg = a.row_ptr[u], end = a.row_ptr[u + 1];
+    if (beg == end) {                                 // HCp = 0 => w = 0 exactly
+        for (int f = tid; f < k; f += SV_THREADS) a.W[(size_t)u * k + f] = 0.f;
+        return;
+    }
+    const int nblk = np * (np + 1) / 2;
+    double* L = sv_smem;                              // [nblk][16][17]
+    double* b0 = L + (size_t)nblk * SV_BLK;           // [kp] right-hand side
+    double* wv = b0 + kp;                             // [kp] solution
+    double* rv = wv + kp;                             // [kp] residual / correction
+    double* rdiag = rv + kp;                          // [kp] 1 / L[i][i]
+    double* red = rdiag + kp;                         // [8][kp] per-warp partial sums of the refinement gather
+    __shared__ double s_norm[2];
+    const float* G = a.G + (size_t)blockIdx.x * WS_KP * WS_KP;
+    // ---- assemble the lower triangle; padding rows/columns: identity
+    for (int e = tid; e < nblk * 256; e += SV_THREADS) {
+        const int blk = e >> 8, r = (e >> 4) & 15, c = e & 15;
+        int bi = (int)((sqrtf(8.f * blk + 1.f) - 1.f) * 0.5f);
+        while (bi * (bi + 1) / 2 > blk) bi--;
+        while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
+        const int bj = blk - bi * (bi + 1) / 2;
+        const int i = bi * SV_NB + r, j = bj * SV_NB + c;
+        double v = 0.0;
+        if (i < k && j < k && j <= i) v = a.HH[(size_t)i * k + j] + a.alpha * (double)G[(size_t)i * WS_KP + j] + (i == j ? a.reg : 0.0);
+        else if (i == j) v = 1.0;
+        L[(size_t)blk * SV_BLK + r * SV_LD + c] = v;
+    }
+    for (int f = tid; f < kp; f += SV_THREADS) {
+        const double bb = f < k ? a.bsum[(size_t)blockIdx.x * WS_KP + f] * (1.0 + a.alpha) : 0.0;
+        b0[f] = bb; wv[f] = bb;
+    }
+    __syncthreads();
+    // ---- blocked right-looking Cholesky
+    for (int p = 0; p < np; p++) {
+        const int j0 = p * SV_NB;
+        if (warp == 0) {                              // diagonal block, lane l owns row l
+            double* D = sv_blk(L, p, p);
+            for (int c = 0; c < SV_NB; c++) {
+                if (lane == c) { const double d = sqrt(D[c * SV_LD + c]); D[c * SV_LD + c] = d; rdiag[j0 + c] = 1.0 / d; }
+                __syncwarp();
+                const double rd = rdiag[j0 + c];
+                if (lane > c && lane < SV_NB) D[lane * SV_LD + c] *= rd;
+                __syncwarp();
+                if (lane > c && lane < SV_NB) {
+                    const double l = D[lane * SV_LD + c];
+                    for (int c2 = c + 1; c2 <= lane; c2++) D[lane * SV_LD + c2] -= l * D[c2 * SV_LD + c];
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // panel below the diagonal block: X L11^T = A21, one thread per row
+        {
+            const double* D = sv_blk(L, p, p);
+            for (int i = j0 + SV_NB + tid; i < kp; i += SV_THREADS) {
+                double* Ai = sv_blk(L, i / SV_NB, p) + (i % SV_NB) * SV_LD;
+                double x[SV_NB];
+#pragma unroll
+                for (int c = 0; c < SV_NB; c++) {
+                    double sacc = Ai[c];
+#pragma unroll
+                    for (int t = 0; t < c; t++) sacc -= x[t] * D[c * SV_LD + t];
+                    x[c] = sacc * rdiag[j0 + c];
+                }
+#pragma unroll
+                for (int c = 0; c < SV_NB; c++) Ai[c] = x[c];
+            }
+        }
+        __syncthreads();
+        // trailing update: C(bi, bj) -= L(bi, p) L(bj, p)^T for p < bj <= bi; 4 x 4 register tiles, 16 threads per block pair
+        const int mb = np - p - 1;
+        const int npair = mb * (mb + 1) / 2;
+        for (int t = tid; t < npair * 16; t += SV_THREADS) {
+            const int pair = t >> 4, tx = (t >> 2) & 3, ty = t & 3;
+            int xi = (int)((sqrtf(8.f * pair + 1.f) - 1.f) * 0.5f);
+            while (xi * (xi + 1) / 2 > pair) xi--;
+            while ((xi + 1) * (xi + 2) / 2 <= pair) xi++;
+            const int xj = pair - xi * (xi + 1) / 2;
+            const int bi = p + 1 + xi, bj = p + 1 + xj;
+            const double* Ra = sv_blk(L, bi, p) + (4 * tx) * SV_LD;
+            const double* Cb = sv_blk(L, bj, p) + (4 * ty) * SV_LD;
+            double acc[4][4];
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < 4; y++) acc[x][y] = 0.0;
+#pragma unroll 4
+            for (int sidx = 0; sidx < SV_NB; sidx++) {
+                double ra[4], cb[4];
+#pragma unroll
+                for (int x = 0; x < 4; x++) { ra[x] = Ra[x * SV_LD + sidx]; cb[x] = Cb[x * SV_LD + sidx]; }
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+#pragma unroll
+                    for (int y = 0; y < 4; y++) acc[x][y] += ra[x] * cb[y];
+            }
+            double* C = sv_blk(L, bi, bj) + (4 * tx) * SV_LD + 4 * ty;
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < 4; y++) C[x * SV_LD + y] -= acc[x][y];
+        }
+        __syncthreads();
+    }
+    // ---- w = L^-T L^-1 b
+    sv_forward(L, rdiag, wv, np);
+    sv_backward(L, rdiag, wv, np);
+    // ---- refinement against the exact operator
+    for (int iter = 0; iter < SV_MAX_REFINE; iter++) {
+        // r = b - HH w - lambda w   (HH is symmetric: column reads are coalesced)
+        for (int f = tid; f < kp; f += SV_THREADS) {
+            double sacc = 0.0;
+            if (f < k) {
+                sacc = b0[f] - a.reg * wv[f];
+                for (int g = 0; g < k; g++) sacc -= a.HH[(size_t)g * k + f] * wv[g];
+            }
+            rv[f] = sacc;
+        }
+        // - alpha sum_i h_i (h_i . w): a warp per entry, lane l holds factors 4 l .. 4 l + 3
+        double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+        const bool col_ok = 4 * lane < k;
+        double w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        __syncthreads();
+        if (col_ok) { w0 = wv[4 * lane]; w1 = wv[4 * lane + 1]; w2 = wv[4 * lane + 2]; w3 = wv[4 * lane + 3]; }
+        for (uint32_t e = beg + warp; e < end; e += SV_THREADS / 32) {
+            const int32_t id = a.cols[e];
+            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_ok) h = __ldg(reinterpret_cast<const float4*>(a.H + (size_t)id * k) + lane);
+            double d = (double)h.x * w0 + (double)h.y * w1 + (double)h.z * w2 + (double)h.w * w3;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            r0 += d * (double)h.x; r1 += d * (double)h.y; r2 += d * (double)h.z; r3 += d * (double)h.w;
+        }
+        if (col_ok) {
+            double* rw = red + (size_t)warp * kp + 4 * lane;
+            rw[0] = r0; rw[1] = r1; rw[2] = r2; rw[3] = r3;
+        }
+        __syncthreads();
+        double rmax = 0.0, bmax = 0.0;
+        for (int f = tid; f < k; f += SV_THREADS) {
+            double sacc = 0.0;
+            for (int wi = 0; wi < SV_THREADS / 32; wi++) sacc += red[(size_t)wi * kp + f];
+            const double r = rv[f] - a.alpha * sacc;
+            rv[f] = r;
+            rmax = fmax(rmax, fabs(r)); bmax = fmax(bmax, fabs(b0[f]));
+        }
+        // |r|_inf and |b|_inf over the CTA
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o)); bmax = fmax(bmax, __shfl_xor_sync(0xffffffffu, bmax, o)); }
+        if (tid == 0) { s_norm[0] = 0.0; s_norm[1] = 0.0; }
+        __syncthreads();
+        if (lane == 0) {
+            atomicMax(reinterpret_cast<unsigned long long*>(&s_norm[0]), (unsigned long long)__double_as_longlong(rmax));
+            atomicMax(reinterpret_cast<unsigned long long*>(&s_norm[1]), (unsigned long long)__double_as_longlong(bmax));
+        }
+        __syncthreads();
+        if (!(s_norm[0] > 1e-10 * s_norm[1])) break;           // converged (uniform across the CTA)
+        sv_forward(L, rdiag, rv, np);
+        sv_backward(L, rdiag, rv, np);
+        for (int f = tid; f < k; f += SV_THREADS) wv[f] += rv[f];
+        __syncthreads();
+    }
+    for (int f = tid; f < k; f += SV_THREADS) a.W[(size_t)u * k + f] = (float)wv[f];
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------
+bool wrmf_tc_eligible(int32_t k) { return k >= 4 && k <= 128 && (k % 4) == 0; }
+
+struct WrmfTcWork {
+    DevBuf<float> G; DevBuf<double> bsum; DevBuf<uint32_t> err;
+    int32_t cap_rows = 0;
+};
+WrmfTcWork* wrmf_tc_work_create() { return new (std::nothrow) WrmfTcWork(); }
+void wrmf_tc_work_destroy(WrmfTcWork* w) { delete w; }
+
+// One half-sweep's per-row systems: W[u] <- solve for every row of `order`. HH (fp64, k x k) is on the device.
+int32_t wrmf_tc_half_sweep(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_ptr, const int32_t* cols, const int32_t* order, int32_t n_rows,
+                           float* W, const float* H, int32_t k, const double* HH, double alpha, double reg, int64_t* launches,
+                           float* debug_G_row0)
+{
+    cudaStream_t s = ctx->stream;
+    MML_CHECK(work != nullptr, MML_ERR_STATE, "wrmf: no tensor-path workspace");
+    WrmfTcWork& w = *work;
+    const int32_t B = 16384;                                   // rows per batch: G 1 GiB
+    const int32_t cap = std::min(B, std::max(n_rows, 1));
+    if (w.cap_rows < cap) {
+        MML_TRY(w.G.alloc((size_t)cap * WS_KP * WS_KP)); MML_TRY(w.bsum.alloc((size_t)cap * WS_KP));
+        if (!w.err.p) MML_TRY(w.err.alloc(1));
+        w.cap_rows = cap;
+    }
+    MML_CUDA(cudaMemsetAsync(w.err.p, 0, sizeof(uint32_t), s));
+    const size_t smem_syrk = (size_t)WS_STAGES * 2 * WS_TILE + 1024;
+    MML_CUDA(cudaFuncSetAttribute((const void*)wrmf_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_syrk));
+    const int np = (k + SV_NB - 1) / SV_NB, kp = np * SV_NB;
+    const size_t smem_solve = sizeof(double) * ((size_t)np * (np + 1) / 2 * SV_BLK + (size_t)kp * (4 + SV_THREADS / 32));
+    MML_CUDA(cudaFuncSetAttribute((const void*)wrmf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+    for (int32_t q_lo = 0; q_lo < n_rows; q_lo += B) {
+        const int32_t q_hi = std::min(n_rows, q_lo + B), nb = q_hi - q_lo;
+        MML_CUDA(cudaMemsetAsync(w.bsum.p, 0, sizeof(double) * (size_t)nb * WS_KP, s));
+        SyrkArgs sa{};
+        sa.row_ptr = row_ptr; sa.cols = cols; sa.order = order; sa.q_lo = q_lo; sa.q_hi = q_hi; sa.H = H; sa.k = k;
+        sa.G = w.G.p; sa.bsum = w.bsum.p; sa.err = w.err.p;
+        wrmf_syrk_kernel<<<std::min(nb, ctx->sm_count), WS_THREADS, smem_syrk, s>>>(sa);
+        MML_CUDA(cudaGetLastError());
+        if (debug_G_row0 && q_lo == 0)
+            MML_CUDA(cudaMemcpyAsync(debug_G_row0, w.G.p, sizeof(float) * WS_KP * WS_KP, cudaMemcpyDeviceToHost, s));
+        SolveArgs va{};
+        va.row_ptr = row_ptr; va.cols = cols; va.order = order; va.q_lo = q_lo; va.q_hi = q_hi; va.G = w.G.p; va.bsum = w.bsum.p; va.HH = HH;
+        va.H = H; va.alpha = alpha; va.reg = reg; va.k = k; va.W = W;
+        wrmf_solve_kernel<<<nb, SV_THREADS, smem_solve, s>>>(va);
+        MML_CUDA(cudaGetLastError());
+        if (launches) *launches += 2;
+    }
+    uint32_t h_err = 0;
+    MML_CUDA(cudaMemcpyAsync(&h_err, w.err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    MML_CUDA(cudaStreamSynchronize(s));
+    MML_CHECK(h_err == 0, MML_ERR_CUDA, "wrmf: tcgen05 pipeline timed out");
+    return MML_OK;
+}
+
+}  // namespace mml

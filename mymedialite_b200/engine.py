@@ -101,7 +101,8 @@ class DeviceRatings:
 
     def close(self):
         if self.h:
-            self.lib.mml_ratings_destroy(self.h)
+            if self.ctx.h:                      # the context owns the device state: nothing to release once it is gone
+                self.lib.mml_ratings_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -223,7 +224,8 @@ class SgdModel:
 
     def close(self):
         if self.h:
-            self.lib.mml_sgd_destroy(self.h)
+            if self.ctx.h:
+                self.lib.mml_sgd_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -302,7 +304,8 @@ class DeviceFeedback:
 
     def close(self):
         if self.h:
-            self.lib.mml_feedback_destroy(self.h)
+            if self.ctx.h:
+                self.lib.mml_feedback_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -310,6 +313,11 @@ class DeviceFeedback:
             self.close()
         except Exception:
             pass
+
+
+def wrmf_set_mode(mode):
+    """_capi.WRMF_AUTO (default) / WRMF_FP64 (all-double CUDA-core kernels) / WRMF_TENSOR (tcgen05 Gram sums or error)."""
+    check(_capi.load().mml_wrmf_set_mode(int(mode)))
 
 
 class WrmfModel:
@@ -339,6 +347,13 @@ class WrmfModel:
     def iterate(self):
         check(self.lib.mml_wrmf_iterate(self.h))
 
+    def debug_gram(self):
+        """(user, G) with G = sum of h_i h_i^T over that user's items as the tensor-core kernel computed it."""
+        G = np.zeros((128, 128), np.float32)
+        u = C.c_int32()
+        check(self.lib.mml_wrmf_debug_gram(self.h, G, C.byref(u)))
+        return u.value, G
+
     def stats(self):
         n, ms = C.c_int64(), C.c_float()
         check(self.lib.mml_wrmf_stats(self.h, C.byref(n), C.byref(ms)))
@@ -355,7 +370,8 @@ class WrmfModel:
 
     def close(self):
         if self.h:
-            self.lib.mml_wrmf_destroy(self.h)
+            if self.ctx.h:
+                self.lib.mml_wrmf_destroy(self.h)
             self.h = None
 
     def __del__(self):

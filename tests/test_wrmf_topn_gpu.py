@@ -80,6 +80,60 @@ def test_wrmf_iterate_matches_oracle(eng, k, alpha, reg):
     assert empty.size > 0 and np.all(Ug[empty] == 0)                     # HCp = 0 => the row is exactly zero
 
 
+@pytest.mark.parametrize("k", [64, 128, 20])
+def test_tensor_core_gram_sum_is_fp32_accurate(eng, k):
+    """The tcgen05 kernel's sum_{i in S_u} h_i h_i^T (3 x TF32 split) against a float64 sum: relative error ~1e-6,
+    i.e. fp32 level, for the user with the longest item list."""
+    engine, ctx = eng
+    nu, ni = 300, 500
+    rs = np.random.RandomState(k)
+    u = rs.randint(0, nu, 20000).astype(np.int32); i = rs.randint(0, ni, 20000).astype(np.int32)     # ~65 distinct items per user
+    f = engine.DeviceFeedback(ctx, u, i, max_user=nu - 1, max_item=ni - 1)
+    U = (rs.randn(nu, k) * 0.1).astype(np.float32); V = (rs.randn(ni, k) * 0.3).astype(np.float32)
+    m = engine.WrmfModel(ctx, f, k)
+    m.set_model(U, V)
+    user, G = m.debug_gram()
+    ptr, cols = f.csr(False)
+    items = cols[ptr[user]:ptr[user + 1]]
+    assert items.size == np.diff(ptr).max() and items.size > 32          # spans several 32-row stages
+    Vd = V[items].astype(np.float64)
+    want = Vd.T @ Vd
+    assert np.all(G[k:, :] == 0) and np.all(G[:, k:] == 0)
+    err = np.abs(G[:k, :k] - want).max() / np.abs(want).max()
+    assert err < 5e-6, err
+    Ug, Vg = m.get_model()
+    assert np.array_equal(Ug, U) and np.array_equal(Vg, V)              # the diagnostic leaves the model alone
+
+
+@pytest.mark.parametrize("mode", ["fp64", "tensor"])
+def test_wrmf_paths_agree_on_a_larger_set(eng, mode):
+    """Both device paths against the oracle on 3000 x 1200, k = 64 (rows up to ~1000 entries, empty rows, 2 epochs)."""
+    engine, ctx = eng
+    nu, ni, k = 3000, 1200, 64
+    u, i = events(nu - 5, ni, 90000, 77)
+    f = engine.DeviceFeedback(ctx, u, i, max_user=nu - 1, max_item=ni - 1)
+    rng = O.Random(5)
+    U = rng.init_normal(nu * k).reshape(nu, k); V = rng.init_normal(ni * k).reshape(ni, k)
+    engine.wrmf_set_mode(engine._capi.WRMF_FP64 if mode == "fp64" else engine._capi.WRMF_TENSOR)
+    try:
+        m = engine.WrmfModel(ctx, f, k)
+        m.set_model(U, V)
+        for _ in range(2):
+            m.iterate()
+        Ug, Vg = m.get_model()
+    finally:
+        engine.wrmf_set_mode(engine._capi.WRMF_AUTO)
+    uptr, ucols = O.feedback_csr(u, i, nu - 1)
+    iptr, irows = O.feedback_csr(i, u, ni - 1)
+    Uo, Vo = U.copy(), V.copy()
+    for _ in range(2):
+        O.wrmf_optimize(uptr, ucols, Uo, Vo, 1.0, 0.015)
+        O.wrmf_optimize(iptr, irows, Vo, Uo, 1.0, 0.015)
+    for got, want in ((Ug, Uo), (Vg, Vo)):
+        scale = np.abs(want).max(axis=1, keepdims=True) + 1e-12
+        assert (np.abs(got - want) / scale).max() < 1e-4
+
+
 def _oracle_lists(U, V, users, n, candidates, ignore_lists):
     out = []
     for b, usr in enumerate(users):
