@@ -117,21 +117,20 @@ def make_data(name, rank=0, world=1):
     user % world == rank, the reference's block rule) over the shared item catalogue."""
     from mymedialite_b200 import synthetic
     nu, ni, n, levels, k, seed, desc = WORKLOADS[name]
-    cache = os.path.join("/tmp", "mmlb200_%s_%d_of_%d.npz" % (name, rank, world))
-    if os.path.exists(cache):
-        z = np.load(cache)
-        d = dict(train=(z["u"], z["i"], z["v"]), test=(z["tu"], z["ti"], z["tv"]))
-    else:
-        # n ratings in the TRAINING set (the shape the metric is quoted on) + 10 % test ratings on top
-        d = synthetic.ratings(nu, ni, int(n / 0.9), levels, seed + 1000 * rank, item_seed=seed)
-        u, i, v = d["train"]
-        if u.size > n:
-            u, i, v = u[:n], i[:n], v[:n]
-        d["train"] = (u, i, v)
-        try:
-            np.savez(cache, u=u, i=i, v=v, tu=d["test"][0], ti=d["test"][1], tv=d["test"][2])
-        except Exception:
-            pass
+    # n ratings in the TRAINING set (the shape the metric is quoted on) + 10 % test ratings on top; generated on the
+    # rank's GPU when there is one (the numpy generator needs minutes for 10^8 ratings)
+    gen, kw = synthetic.ratings, {}
+    try:
+        import torch
+        if torch.cuda.is_available():
+            gen, kw = synthetic.ratings_cuda, {"device": "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))}
+    except ImportError:
+        pass
+    d = gen(nu, ni, int(n / 0.9) + 1024, levels, seed + 1000 * rank, item_seed=seed, **kw)
+    u, i, v = d["train"]
+    if u.size > n:
+        u, i, v = u[:n], i[:n], v[:n]
+    d["train"] = (u, i, v)
     if world > 1:
         d["train"] = ((d["train"][0] * world + rank).astype(np.int32), d["train"][1], d["train"][2])
         d["test"] = ((d["test"][0] * world + rank).astype(np.int32), d["test"][1], d["test"][2])
@@ -329,10 +328,10 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ml10m", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="netflix", choices=sorted(WORKLOADS))
     ap.add_argument("--groups", type=int, default=0)
     ap.add_argument("--subgroups", type=int, default=16)
     ap.add_argument("--persistent", type=int, default=-1)

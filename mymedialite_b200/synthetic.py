@@ -78,6 +78,58 @@ def ratings(n_users, n_items, n, levels="half", seed=1, test_fraction=0.1, item_
                 n_users=n_users, n_items=n_items)
 
 
+def ratings_cuda(n_users, n_items, n, levels="half", seed=1, test_fraction=0.1, item_seed=None, device="cuda"):
+    """Same planted model and laws as ratings(), generated with torch on the GPU (the 10^8-rating shapes take minutes in
+    numpy, seconds here). Deterministic for a given seed on a given torch build; NOT the same stream as ratings().
+    Benchmark plumbing only: the arrays it returns feed the engine and the CPU oracle alike."""
+    import torch
+    dev = torch.device(device)
+    g = torch.Generator(device=dev); g.manual_seed(int(seed))
+    gi = torch.Generator(device=dev); gi.manual_seed(int(item_seed if item_seed is not None else seed) + 7919)
+    act = torch.exp(torch.randn(n_users, generator=g, device=dev, dtype=torch.float64))
+    pop = 1.0 / torch.arange(1, n_items + 1, device=dev, dtype=torch.float64) ** 0.8
+    pop = pop[torch.randperm(n_items, generator=gi, device=dev)]
+    cdf = torch.cumsum(pop / pop.sum(), 0); cdf[-1] = 1.0
+    ucdf = torch.cumsum(act / act.sum(), 0); ucdf[-1] = 1.0
+    # every user and item once, then draws by the activity / popularity laws, de-duplicated
+    ar_u = torch.arange(n_users, device=dev, dtype=torch.int64); ar_i = torch.arange(n_items, device=dev, dtype=torch.int64)
+    keys = torch.unique(torch.cat([ar_u * n_items + torch.randint(0, n_items, (n_users,), generator=g, device=dev),
+                                   torch.randint(0, n_users, (n_items,), generator=g, device=dev) * n_items + ar_i]))
+    while keys.numel() < n:
+        draw = int((n - keys.numel()) * 1.15) + 1024
+        uu = torch.searchsorted(ucdf, torch.rand(draw, generator=g, device=dev, dtype=torch.float64), right=True).clamp_(max=n_users - 1)
+        ii = torch.searchsorted(cdf, torch.rand(draw, generator=g, device=dev, dtype=torch.float64), right=True).clamp_(max=n_items - 1)
+        keys = torch.unique(torch.cat([keys, uu * n_items + ii]))
+        del uu, ii
+    if keys.numel() > n:
+        keep = torch.randperm(keys.numel(), generator=g, device=dev)[:n]
+        keys = keys[keep]
+    else:
+        keys = keys[torch.randperm(keys.numel(), generator=g, device=dev)]
+    u = torch.div(keys, n_items, rounding_mode="floor"); i = keys - u * n_items
+    del keys
+    rank = 16
+    Pu = 0.35 * torch.randn(n_users, rank, generator=g, device=dev); Qi = 0.35 * torch.randn(n_items, rank, generator=gi, device=dev)
+    bu = 0.3 * torch.randn(n_users, generator=g, device=dev); bi = 0.3 * torch.randn(n_items, generator=gi, device=dev)
+    v = torch.empty(u.numel(), device=dev, dtype=torch.float32)
+    step = 1 << 24
+    for s0 in range(0, u.numel(), step):
+        uu, ii = u[s0:s0 + step], i[s0:s0 + step]
+        v[s0:s0 + step] = 3.6 + bu[uu] + bi[ii] + (Pu[uu] * Qi[ii]).sum(1) + 0.5 * torch.randn(uu.numel(), generator=g, device=dev)
+    if levels == "half":
+        v = torch.clamp(torch.round(v * 2) / 2, 0.5, 5.0)
+    elif levels == "int":
+        v = torch.clamp(torch.round(v), 1.0, 5.0)
+    is_test = torch.rand(u.numel(), generator=g, device=dev) < test_fraction
+    out = {}
+    for name, m in (("train", ~is_test), ("test", is_test)):
+        out[name] = (u[m].to(torch.int32).cpu().numpy(), i[m].to(torch.int32).cpu().numpy(), v[m].cpu().numpy())
+    out["n_users"], out["n_items"] = n_users, n_items
+    del u, i, v, is_test
+    torch.cuda.empty_cache()
+    return out
+
+
 def implicit(n_users, n_items, n, seed=1):
     rng = np.random.Generator(np.random.PCG64(seed))
     return _pairs(rng, n_users, n_items, n)
