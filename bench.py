@@ -34,6 +34,8 @@ WORKLOADS = {
                 "BiasedMatrixFactorization k=128 DSGD, synthetic Netflix shape (480k x 17.8k, 100M ratings)"),
     "netflix10": (48_000, 17_800, 10_000_000, "int", 128, 20260104,
                   "BiasedMatrixFactorization k=128 DSGD, 1/10 of the synthetic Netflix shape (48k x 17.8k, 10M ratings)"),
+    "nf_sub8": (480_000, 2_225, 12_500_000, "int", 128, 20260104,
+                "one GPU-level sub-epoch of the Netflix shape at 8 GPUs (480k users x 1/8 of the items, 12.5M ratings), diagnostic"),
     "tiny": (3_000, 800, 300_000, "half", 64, 7, "debug-sized"),
 }
 
@@ -112,7 +114,7 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def make_data(name, rank=0, world=1):
+def make_data(name, rank=0, world=1, pop_offset=None):
     """The rank's user shard: n_users users of its own (global id = local * world + rank, so that
     user % world == rank, the reference's block rule) over the shared item catalogue."""
     from mymedialite_b200 import synthetic
@@ -126,7 +128,7 @@ def make_data(name, rank=0, world=1):
             gen, kw = synthetic.ratings_cuda, {"device": "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))}
     except ImportError:
         pass
-    d = gen(nu, ni, int(n / 0.9) + 1024, levels, seed + 1000 * rank, item_seed=seed, **kw)
+    d = gen(nu, ni, int(n / 0.9) + 1024, levels, seed + 1000 * rank, item_seed=seed, pop_offset=pop_offset, **kw)
     u, i, v = d["train"]
     if u.size > n:
         u, i, v = u[:n], i[:n], v[:n]
@@ -167,7 +169,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    d, k, desc = make_data(args.workload, rank, world)
+    d, k, desc = make_data(args.workload, rank, world, args.pop_offset)
     u, i, v = d["train"]; tu, ti, tv = d["test"]
     n = int(u.size)
     ctx = engine.Context(local_rank, rank, world, uid)
@@ -295,7 +297,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as O
-    d, k, desc = make_data(args.workload)
+    d, k, desc = make_data(args.workload, pop_offset=args.pop_offset)
     u, i, v = d["train"]
     cores = os.cpu_count() or 1
     m = min(u.size, args.cpu_sample)
@@ -341,6 +343,8 @@ def main():
     ap.add_argument("--intra", type=int, default=1, help="0 = conflict-free rounds, 1 = async (default)")
     ap.add_argument("--cpu-sample", type=int, default=10_000_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--pop-offset", type=float, default=None,
+                    help="item popularity (i + offset)^-0.8; default synthetic.POP_OFFSET = 30, 0 = the pure Zipf law")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.cpu_sample == 10_000_000:

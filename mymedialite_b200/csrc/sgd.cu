@@ -751,25 +751,44 @@ __device__ __forceinline__ void red_add_f(float* p, float x)
 // the reference's lock-free NaiveParallelization mode (BiasedMatrixFactorization.cs:136-141, :201-204), but
 // confined to a block: blocks of a sub-epoch stay disjoint as in the reference's DSGD mode. A popular item's
 // chain of updates is serialised by the L2 atomic unit, not by the SM. No barriers inside the block.
-template <int L, int KPL, bool BIASED>
-__device__ __forceinline__ void sgd_block_async(const SgdArgs& a, const int j, const int slot)
+// The read-only head of a worker's slice of block (j, slot): its entry range and first two entries. It does not depend on
+// the model, so the persistent kernel fetches it one sub-epoch ahead (three dependent global-memory latencies off the
+// critical path of every block hand-over).
+struct AsyncHead {
+    uint32_t e0, e1;
+    int u1, i1, u2, i2;
+    float v1, v2;
+};
+
+template <int L>
+__device__ __forceinline__ AsyncHead async_head(const SgdArgs& a, const int j, const int slot)
 {
-    constexpr int KP = L * KPL;
     constexpr int WPW = 32 / L;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sl = lane % L;
     const int wid = warp * WPW + lane / L;
-    const int n_workers = a.n_workers;                 // <= workers in the CTA; the rest idle (1 = serial, for tests)
+    const int n_workers = a.n_workers;
+    AsyncHead h;
+    h.u1 = 0; h.i1 = 0; h.u2 = 0; h.i2 = 0; h.v1 = 0.f; h.v2 = 0.f;
+    const uint32_t* wp = a.wptr + (size_t)(j * a.G + slot) * (n_workers + 1) + min(wid, n_workers - 1);
+    h.e0 = wid < n_workers ? wp[0] : 0u; h.e1 = wid < n_workers ? wp[1] : 0u;
+    if (h.e0 < h.e1) { h.u1 = a.ent_u[h.e0]; h.i1 = a.ent_i[h.e0]; h.v1 = a.ent_v[h.e0]; }
+    if (h.e0 + 1 < h.e1) { h.u2 = a.ent_u[h.e0 + 1]; h.i2 = a.ent_i[h.e0 + 1]; h.v2 = a.ent_v[h.e0 + 1]; }
+    return h;
+}
+
+template <int L, int KPL, bool BIASED>
+__device__ __forceinline__ void sgd_block_async(const SgdArgs& a, const int j, const int slot, const AsyncHead& head)
+{
+    constexpr int KP = L * KPL;
+    const int lane = threadIdx.x & 31;
+    const int sl = lane % L;
     int b = slot + j; if (b >= a.G) b -= a.G;
     const int i_lo = a.item_ptr[b];
     float* Qg = a.Q + (size_t)i_lo * KP;
     float* Bg = a.bi + i_lo;
-    const uint32_t* wp = a.wptr + (size_t)(j * a.G + slot) * (n_workers + 1) + min(wid, n_workers - 1);
-    const uint32_t e0 = wid < n_workers ? wp[0] : 0u, e1 = wid < n_workers ? wp[1] : 0u;
+    const uint32_t e0 = head.e0, e1 = head.e1;
     // entries two ahead, user row and item row one ahead
-    int u1 = 0, i1 = 0, u2 = 0, i2 = 0; float v1 = 0.f, v2 = 0.f;
-    if (e0 < e1) { u1 = a.ent_u[e0]; i1 = a.ent_i[e0]; v1 = a.ent_v[e0]; }
-    if (e0 + 1 < e1) { u2 = a.ent_u[e0 + 1]; i2 = a.ent_i[e0 + 1]; v2 = a.ent_v[e0 + 1]; }
+    int u1 = head.u1, i1 = head.i1, u2 = head.u2, i2 = head.i2; float v1 = head.v1, v2 = head.v2;
     float p[KPL], pn[KPL], qn[KPL];
     float bu_v = 0.f, bun = 0.f, bin = 0.f, regu = a.reg_u, regun = a.reg_u;
 #pragma unroll
@@ -852,7 +871,7 @@ template <int L, int KPL, bool BIASED, bool STAGE, bool ASYNC>
 __global__ void __launch_bounds__(512) sgd_slot_kernel(const SgdArgs a, const int slot)
 {
     extern __shared__ float4 smem4[];
-    if (ASYNC) sgd_block_async<L, KPL, BIASED>(a, blockIdx.x, slot);
+    if (ASYNC) sgd_block_async<L, KPL, BIASED>(a, blockIdx.x, slot, async_head<L>(a, blockIdx.x, slot));
     else sgd_block<L, KPL, BIASED, STAGE>(a, blockIdx.x, slot, reinterpret_cast<float*>(smem4));
 }
 
@@ -864,8 +883,12 @@ __global__ void __launch_bounds__(512) sgd_epoch_kernel(const SgdArgs a)
 {
     extern __shared__ float4 smem4[];
     const int j = blockIdx.x;
+    AsyncHead head;
+    if (ASYNC) head = async_head<L>(a, j, a.seq[0]);
     for (int t = 0; t < a.G; t++) {
         const int slot = a.seq[t];
+        AsyncHead next = head;
+        if (ASYNC && t + 1 < a.G) next = async_head<L>(a, j, a.seq[t + 1]);
         if (t > 0) {
             // item group b = (slot + j) % G was held in sub-epoch t-1 by CTA jp with (seq[t-1] + jp) % G == b
             int b = slot + j; if (b >= a.G) b -= a.G;
@@ -877,8 +900,9 @@ __global__ void __launch_bounds__(512) sgd_epoch_kernel(const SgdArgs a)
             }
             __syncthreads();
         }
-        if (ASYNC) sgd_block_async<L, KPL, BIASED>(a, j, slot);
+        if (ASYNC) sgd_block_async<L, KPL, BIASED>(a, j, slot, head);
         else sgd_block<L, KPL, BIASED, STAGE>(a, j, slot, reinterpret_cast<float*>(smem4));
+        head = next;
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) st_release_u32(a.flags + j, a.epoch_base + (uint32_t)t + 1u);
@@ -1371,9 +1395,13 @@ static int32_t run_dsgd_epoch(Sgd& m, const int32_t* h_seq)
     // block (factor rows + biases) to rank - 1 and takes the next one from rank + 1 -- the reference's block
     // schedule (BiasedMatrixFactorization.cs:213-214) with GPUs in place of threads. After R sub-epochs every
     // block is back on its home rank. R = 1: one pass, no exchange.
+    static const bool trace = [] { const char* e = getenv("MMLB200_TRACE"); return e && *e && *e != '0'; }();
+    std::vector<cudaEvent_t> tev;
+    if (trace && m.R > 1) { tev.resize((size_t)3 * m.R); for (auto& e : tev) cudaEventCreate(&e); }
     for (int S = 0; S < m.R; S++) {
         const int B = (S + m.rank) % m.R;
         SgdArgs a = make_args(m, B);
+        if (!tev.empty()) cudaEventRecord(tev[3 * S], s);
         if (m.p.persistent) {
             DevBuf<int32_t>& dseq = m.d_index;   // reuse: serial index cache is unused in DSGD mode
             if ((int64_t)dseq.n < m.G) MML_TRY(dseq.alloc(m.G));
@@ -1390,6 +1418,7 @@ static int32_t run_dsgd_epoch(Sgd& m, const int32_t* h_seq)
             }
             MML_CUDA(cudaGetLastError());
         }
+        if (!tev.empty()) cudaEventRecord(tev[3 * S + 1], s);
         if (m.R > 1) {
             const int Bn = (B + 1) % m.R;
             const int32_t s_lo = m.h_item_ptr[(size_t)B * m.G], s_hi = m.h_item_ptr[(size_t)(B + 1) * m.G];
@@ -1399,6 +1428,19 @@ static int32_t run_dsgd_epoch(Sgd& m, const int32_t* h_seq)
                                        m.Q.p + (size_t)r_lo * m.kp, (size_t)(r_hi - r_lo) * m.kp, m.bi.p + r_lo, (size_t)(r_hi - r_lo),
                                        (m.rank + 1) % m.R));
         }
+        if (!tev.empty()) cudaEventRecord(tev[3 * S + 2], s);
+    }
+    if (!tev.empty()) {
+        cudaStreamSynchronize(s);
+        float tk = 0.f, tx = 0.f, tg = 0.f;
+        for (int S = 0; S < m.R; S++) {
+            float x = 0.f;
+            cudaEventElapsedTime(&x, tev[3 * S], tev[3 * S + 1]); tk += x;
+            cudaEventElapsedTime(&x, tev[3 * S + 1], tev[3 * S + 2]); tx += x;
+            if (S + 1 < m.R) { cudaEventElapsedTime(&x, tev[3 * S + 2], tev[3 * S + 3]); tg += x; }
+        }
+        fprintf(stderr, "[mmlb200 sgd rank %d] epoch: kernels %.3f ms, ring exchanges %.3f ms, gaps %.3f ms\n", m.rank, tk, tx, tg);
+        for (auto& e : tev) cudaEventDestroy(e);
     }
     if (m.R > 1) m.items_dirty = true;
     return MML_OK;

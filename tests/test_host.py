@@ -69,10 +69,11 @@ def test_synthetic_is_deterministic_and_dense():
 
 
 def test_shards_share_the_item_catalogue():
-    a = synthetic.ratings(800, 200, 20000, "int", 11, item_seed=5)
-    b = synthetic.ratings(800, 200, 20000, "int", 12, item_seed=5)
-    ca, cb = np.bincount(a["train"][1], minlength=200), np.bincount(b["train"][1], minlength=200)
-    assert np.corrcoef(ca, cb)[0, 1] > 0.95
+    a = synthetic.ratings(800, 200, 60000, "int", 11, item_seed=5)
+    b = synthetic.ratings(800, 200, 60000, "int", 12, item_seed=5)
+    c = synthetic.ratings(800, 200, 60000, "int", 12, item_seed=6)
+    ca, cb, cc = (np.bincount(x["train"][1], minlength=200) for x in (a, b, c))
+    assert np.corrcoef(ca, cb)[0, 1] > 0.9 > np.corrcoef(ca, cc)[0, 1]          # same popularity law iff same item_seed
     assert not np.array_equal(a["train"][0], b["train"][0])
 
 
