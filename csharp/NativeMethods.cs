@@ -15,7 +15,7 @@ namespace MyMediaLite.Native
 		public int frequency_regularization, loss, bold_driver, max_threads;
 		public int schedule, num_groups, num_subgroups, group_rule, persistent;
 		public float hot_item_factor;
-		public int hot_copies, intra_block, hot_merge_average, async_workers;
+		public int hot_copies, intra_block, hot_merge_average, async_workers, ctas_per_group, prefetch_distance;
 	}
 
 	/// <summary>mml_wrmf_params of include/mmlb200.h</summary>
@@ -109,6 +109,7 @@ namespace MyMediaLite.Native
 		[DllImport(LIB)] public static extern int mml_wrmf_get_model(IntPtr model, [Out] float[] user_factors, [Out] float[] item_factors);
 		[DllImport(LIB)] public static extern int mml_wrmf_iterate(IntPtr model);
 		[DllImport(LIB)] public static extern int mml_wrmf_stats(IntPtr model, out long kernel_launches, out float last_iterate_ms);
+		[DllImport(LIB)] public static extern int mml_wrmf_shard(IntPtr model, int by_item, [Out] int[] ranges);
 		[DllImport(LIB)] public static extern int mml_wrmf_recommend(IntPtr model, int[] users, long n_users, int n, int[] candidates, long n_cand, long[] ignore_ptr, int[] ignore_idx,
 			[Out] int[] out_items, [Out] float[] out_scores, [Out] int[] out_counts);
 

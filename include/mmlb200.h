@@ -130,6 +130,12 @@ typedef struct mml_mf_params {
     int32_t hot_merge_average;    /* hot-item copies are merged by averaging (1, default) or summing (0) their steps */
     int32_t async_workers;        /* async mode: workers per worker group that take part; 0 = all, 1 = serial
                                      inside a block (deterministic; used by the parity tests) */
+    int32_t ctas_per_group;       /* async mode: CTAs that make up one worker group and share its blocks
+                                     (num_groups = 0 then means SMs / ctas_per_group groups); 0 = 1.
+                                     num_groups = 1 makes the whole GPU one worker group: no block hand-over,
+                                     the reference's NaiveParallelization inside the GPU */
+    int32_t prefetch_distance;    /* async mode: user rows are pulled into the L2 this many ratings ahead of their use
+                                     (the user matrix does not fit the L2 at the Netflix shape); 0 = default, -1 = off */
 } mml_mf_params;
 
 void mml_mf_params_default(mml_mf_params* p);
@@ -238,6 +244,11 @@ int32_t mml_wrmf_get_model(mml_wrmf* m, float* user_factors, float* item_factors
 /* WRMF.Iterate (WRMF.cs:68-73): user half-sweep then item half-sweep. */
 int32_t mml_wrmf_iterate(mml_wrmf* m);
 int32_t mml_wrmf_stats(mml_wrmf* m, int64_t* kernel_launches, float* last_iterate_ms);
+/* Multi-GPU contexts (mml_ctx_create_dist): every rank passes the same feedback and model; in each half-sweep
+ * (WRMF.cs:79-92, a Parallel.For over independent rows) rank r solves the contiguous rows
+ * [ranges[r], ranges[r + 1]) -- balanced by events per row -- and the ranks all-gather the solved rows (NCCL), so
+ * every rank holds the whole model after mml_wrmf_iterate. ranges receives world + 1 entries. */
+int32_t mml_wrmf_shard(mml_wrmf* m, int32_t by_item, int32_t* ranges);
 /* Engine knob: AUTO = per-row Gram sums sum_{i in S_u} h_i h_i^T on the tcgen05 tensor cores (3 x TF32 split, fp32-accurate)
  * with HH, the assembly and the blocked Cholesky solve in double (num_factors a multiple of 4, <= 128), the all-double
  * CUDA-core kernels otherwise; FP64 / TENSOR force one of them. */

@@ -76,6 +76,8 @@ struct Ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host -> device staging that may overlap kernels on `stream`
+    cudaEvent_t copy_done = nullptr;
     int n_gpus = 1;              // world size: one process (context) per GPU
     int rank = 0;
     void* comm = nullptr;        // ncclComm_t when n_gpus > 1

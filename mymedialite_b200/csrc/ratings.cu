@@ -136,6 +136,8 @@ int32_t ctx_create_on_device(int dev, mml_ctx** out)
     MML_CUDA(cudaGetDeviceProperties(&prop, dev));
     c->c.sm_count = prop.multiProcessorCount;
     MML_CUDA(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking));
+    MML_CUDA(cudaStreamCreateWithFlags(&c->c.copy_stream, cudaStreamNonBlocking));
+    MML_CUDA(cudaEventCreateWithFlags(&c->c.copy_done, cudaEventDisableTiming));
     *out = c;
     return MML_OK;
 }
@@ -155,6 +157,8 @@ extern "C" int32_t mml_ctx_destroy(mml_ctx* ctx)
     cudaSetDevice(ctx->c.device);
     dist_destroy(&ctx->c);
     if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
+    if (ctx->c.copy_stream) cudaStreamDestroy(ctx->c.copy_stream);
+    if (ctx->c.copy_done) cudaEventDestroy(ctx->c.copy_done);
     if (ctx->c.flush_buf) cudaFree(ctx->c.flush_buf);
     delete ctx;
     return MML_OK;

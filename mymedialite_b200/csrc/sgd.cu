@@ -471,7 +471,9 @@ struct SgdArgs {
     const int32_t* seq;             // persistent kernel: sub-epoch sequence [G] (device)
     uint32_t epoch_base;
     int32_t G, C;                   // worker groups, copies per hot item
-    int32_t n_workers;              // async mode: workers per CTA the slices were cut for
+    int32_t n_workers;              // async mode: workers per worker group the slices were cut for
+    int32_t cpg;                    // async mode: CTAs per worker group (they share the group's blocks)
+    int32_t pf_dist;                // async mode: user rows are prefetched into L2 this many entries ahead (0 = off)
     float hot_scale;                // merge of hot-item copies: 1 = sum of the chains' steps, 1/C = average
     float lr, gb, minr, range, reg_u, reg_i, blr, breg;
     int32_t loss;
@@ -549,6 +551,46 @@ __device__ __forceinline__ void sgd_update(const SgdArgs& a, float (&p)[KPL], fl
         p[f] = pf + a.lr * (gc * qf - regu * pf);
         q[f] = qf + a.lr * (gc * pf - regi * qf);
     }
+}
+
+// The same update for the async mode, which applies the item step as an atomic add: returns the item row's step
+// dq = lr (g p - reg_i q) (and dbi for the bias) instead of the new row, and folds the learn rate into the
+// coefficients: p <- (1 - lr reg_u) p + (lr g) q -- two instructions per factor and row instead of three.
+template <int L, int KPL, bool BIASED>
+__device__ __forceinline__ void sgd_update_delta(const SgdArgs& a, float (&p)[KPL], const float (&q)[KPL], float (&dq)[KPL],
+                                                 float& bu, const float bi, float& dbi, float v, float regu, float regi)
+{
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int f = 0; f < KPL; f += 2) { d0 = fmaf(p[f], q[f], d0); d1 = fmaf(p[f + 1], q[f + 1], d1); }
+    const float dot = worker_sum<L>(d0 + d1);
+    float gc;
+    dbi = 0.f;
+    if (BIASED) {
+        const float score = ((a.gb + bu) + bi) + dot;
+        const float sig = __fdividef(1.f, 1.f + __expf(-score));
+        const float err = v - (a.minr + sig * a.range);
+        if (a.loss == MML_LOSS_RMSE) gc = err * sig * (1.f - sig) * a.range;
+        else if (a.loss == MML_LOSS_MAE) gc = (err > 0.f ? 1.f : (err < 0.f ? -1.f : 0.f)) * sig * (1.f - sig) * a.range;
+        else gc = err;
+        const float step = a.blr * a.lr;
+        bu += step * (gc - a.breg * regu * bu);
+        dbi = step * (gc - a.breg * regi * bi);
+    } else {
+        gc = v - (a.gb + dot);
+    }
+    const float lg = a.lr * gc, cu = fmaf(-a.lr, regu, 1.f), ci = a.lr * regi;
+#pragma unroll
+    for (int f = 0; f < KPL; f++) {
+        const float pf = p[f], qf = q[f];
+        p[f] = fmaf(lg, qf, cu * pf);
+        dq[f] = fmaf(lg, pf, -(ci * qf));
+    }
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
 }
 
 // =================================================================================================
@@ -761,11 +803,11 @@ struct AsyncHead {
 };
 
 template <int L>
-__device__ __forceinline__ AsyncHead async_head(const SgdArgs& a, const int j, const int slot)
+__device__ __forceinline__ AsyncHead async_head(const SgdArgs& a, const int j, const int sub, const int slot)
 {
     constexpr int WPW = 32 / L;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wid = warp * WPW + lane / L;
+    const int wid = sub * (int)(blockDim.x >> 5) * WPW + warp * WPW + lane / L;   // worker inside the group
     const int n_workers = a.n_workers;
     AsyncHead h;
     h.u1 = 0; h.i1 = 0; h.u2 = 0; h.i2 = 0; h.v1 = 0.f; h.v2 = 0.f;
@@ -804,12 +846,21 @@ __device__ __forceinline__ void sgd_block_async(const SgdArgs& a, const int j, c
 #pragma unroll
     for (int d = L; d < 32; d <<= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, d));
     int cur_u = -1;
+    // user rows come from HBM (the user matrix is larger than the L2): lanes 0..3 of the worker pull the four
+    // 128-byte lines of the row pf_dist entries ahead into the L2 (the entry is read one iteration before its use)
+    const uint32_t pfd = (uint32_t)a.pf_dist;
+    int u_far = (pfd && e0 + pfd < e1) ? a.ent_u[e0 + pfd] : -1, u_far_prev = -1;
     for (uint32_t t = 0; t < len; t++) {
         const uint32_t e = e0 + t;
         const bool active = e < e1;
         const int u = u1, i = i1; const float v = v1;
         u1 = u2; i1 = i2; v1 = v2;
         if (e + 2 < e1) { u2 = a.ent_u[e + 2]; i2 = a.ent_i[e + 2]; v2 = a.ent_v[e + 2]; }
+        if (pfd) {
+            if (u_far >= 0 && u_far != u_far_prev && sl * 32 < KP) prefetch_l2(a.P + (size_t)u_far * KP + sl * 32);
+            u_far_prev = u_far;
+            u_far = (e + 1 + pfd < e1) ? a.ent_u[e + 1 + pfd] : -1;
+        }
         if (active && u != cur_u) {   // new user run: flush the previous row, adopt the fetched one
             if (cur_u >= 0) {
                 Row<L, KPL>::store(p, a.P + (size_t)cur_u * KP, sl);
@@ -820,10 +871,9 @@ __device__ __forceinline__ void sgd_block_async(const SgdArgs& a, const int j, c
             bu_v = bun; regu = regun;
             cur_u = u;
         }
-        float q[KPL], q0[KPL];
+        float q[KPL];
 #pragma unroll
-        for (int f = 0; f < KPL; f++) { q[f] = qn[f]; q0[f] = qn[f]; }
-        float bi_v = bin;
+        for (int f = 0; f < KPL; f++) q[f] = qn[f];
         const float bi0 = bin;
         const bool same_item = active && e + 1 < e1 && i1 == i;   // next rating hits the same item: forward the new row
         if (e + 1 < e1) {   // next entry: its item row, and its user row if a new run starts (runs are contiguous)
@@ -838,11 +888,11 @@ __device__ __forceinline__ void sgd_block_async(const SgdArgs& a, const int j, c
             }
         }
         const float regi = a.regw_i ? a.regw_i[i_lo + (active ? i : 0)] : a.reg_i;
-        float pw[KPL];
+        float pw[KPL], dq[KPL];
 #pragma unroll
         for (int f = 0; f < KPL; f++) pw[f] = p[f];
-        float buw = bu_v;
-        sgd_update<L, KPL, BIASED>(a, pw, q, buw, bi_v, v, regu, regi);
+        float buw = bu_v, dbi;
+        sgd_update_delta<L, KPL, BIASED>(a, pw, q, dq, buw, bi0, dbi, v, regu, regi);
         if (active) {
 #pragma unroll
             for (int f = 0; f < KPL; f++) p[f] = pw[f];
@@ -850,13 +900,12 @@ __device__ __forceinline__ void sgd_block_async(const SgdArgs& a, const int j, c
             float* qrow = Qg + (size_t)i * KP;
 #pragma unroll
             for (int vv = 0; vv < KPL / 4; vv++)
-                red_add_f4(qrow + 4 * (vv * L + sl), q[4 * vv] - q0[4 * vv], q[4 * vv + 1] - q0[4 * vv + 1],
-                           q[4 * vv + 2] - q0[4 * vv + 2], q[4 * vv + 3] - q0[4 * vv + 3]);
-            if (BIASED && sl == 0) red_add_f(Bg + i, bi_v - bi0);
+                red_add_f4(qrow + 4 * (vv * L + sl), dq[4 * vv], dq[4 * vv + 1], dq[4 * vv + 2], dq[4 * vv + 3]);
+            if (BIASED && sl == 0) red_add_f(Bg + i, dbi);
             if (same_item) {
 #pragma unroll
-                for (int f = 0; f < KPL; f++) qn[f] = q[f];
-                bin = bi_v;
+                for (int f = 0; f < KPL; f++) qn[f] = q[f] + dq[f];
+                bin = bi0 + dbi;
             }
         }
     }
@@ -871,31 +920,37 @@ template <int L, int KPL, bool BIASED, bool STAGE, bool ASYNC>
 __global__ void __launch_bounds__(512) sgd_slot_kernel(const SgdArgs a, const int slot)
 {
     extern __shared__ float4 smem4[];
-    if (ASYNC) sgd_block_async<L, KPL, BIASED>(a, blockIdx.x, slot, async_head<L>(a, blockIdx.x, slot));
+    if (ASYNC) {
+        const int j = blockIdx.x / a.cpg, sub = blockIdx.x % a.cpg;
+        sgd_block_async<L, KPL, BIASED>(a, j, slot, async_head<L>(a, j, sub, slot));
+    }
     else sgd_block<L, KPL, BIASED, STAGE>(a, blockIdx.x, slot, reinterpret_cast<float*>(smem4));
 }
 
-// One cooperative launch per epoch: CTA j walks the sub-epoch sequence; before it takes item group b
-// it waits (acquire) until the CTA that held b in the previous sub-epoch has published it (release).
-// All G CTAs are co-resident (cooperative launch), so the waits cannot deadlock.
+// One cooperative launch per epoch. A worker group is cpg CTAs (cpg = 1 unless async mode asks for more); group j
+// walks the sub-epoch sequence; before it takes item group b every one of its CTAs waits (acquire) until all cpg
+// CTAs of the group that held b in the previous sub-epoch have published it (release) -- one progress counter
+// per CTA. All G * cpg CTAs are co-resident (cooperative launch), so the waits cannot deadlock. G = 1: no
+// hand-over at all, the GPU is one worker group (the reference's lock-free NaiveParallelization inside the GPU).
 template <int L, int KPL, bool BIASED, bool STAGE, bool ASYNC>
 __global__ void __launch_bounds__(512) sgd_epoch_kernel(const SgdArgs a)
 {
     extern __shared__ float4 smem4[];
-    const int j = blockIdx.x;
+    const int cpg = ASYNC ? a.cpg : 1;
+    const int j = blockIdx.x / cpg, sub = blockIdx.x % cpg;
     AsyncHead head;
-    if (ASYNC) head = async_head<L>(a, j, a.seq[0]);
+    if (ASYNC) head = async_head<L>(a, j, sub, a.seq[0]);
     for (int t = 0; t < a.G; t++) {
         const int slot = a.seq[t];
         AsyncHead next = head;
-        if (ASYNC && t + 1 < a.G) next = async_head<L>(a, j, a.seq[t + 1]);
+        if (ASYNC && t + 1 < a.G) next = async_head<L>(a, j, sub, a.seq[t + 1]);
         if (t > 0) {
-            // item group b = (slot + j) % G was held in sub-epoch t-1 by CTA jp with (seq[t-1] + jp) % G == b
+            // item group b = (slot + j) % G was held in sub-epoch t-1 by group jp with (seq[t-1] + jp) % G == b
             int b = slot + j; if (b >= a.G) b -= a.G;
             int jp = b - a.seq[t - 1]; if (jp < 0) jp += a.G;
-            if (threadIdx.x == 0) {
+            if ((int)threadIdx.x < cpg) {
                 const uint32_t want = a.epoch_base + (uint32_t)t;
-                while ((int32_t)(ld_relaxed_u32(a.flags + jp) - want) < 0) __nanosleep(20);
+                while ((int32_t)(ld_relaxed_u32(a.flags + jp * cpg + threadIdx.x) - want) < 0) __nanosleep(20);
                 __threadfence();   // acquire
             }
             __syncthreads();
@@ -903,9 +958,11 @@ __global__ void __launch_bounds__(512) sgd_epoch_kernel(const SgdArgs a)
         if (ASYNC) sgd_block_async<L, KPL, BIASED>(a, j, slot, head);
         else sgd_block<L, KPL, BIASED, STAGE>(a, j, slot, reinterpret_cast<float*>(smem4));
         head = next;
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) st_release_u32(a.flags + j, a.epoch_base + (uint32_t)t + 1u);
+        if (a.G > 1) {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) st_release_u32(a.flags + blockIdx.x, a.epoch_base + (uint32_t)t + 1u);
+        }
     }
 }
 
@@ -1191,7 +1248,7 @@ static SgdArgs make_args(Sgd& m, int32_t B)
     a.regw_u = m.p.frequency_regularization ? m.regw_u.p : nullptr;
     a.regw_i = m.p.frequency_regularization ? m.regw_i.p : nullptr;
     a.flags = m.flags.p; a.seq = nullptr; a.epoch_base = m.epoch_base;
-    a.G = m.G; a.C = m.hot_copies; a.n_workers = m.n_workers;
+    a.G = m.G; a.C = m.hot_copies; a.n_workers = m.n_workers; a.cpg = std::max(m.cpg, 1); a.pf_dist = m.pf_dist;
     a.hot_scale = m.p.hot_merge_average ? 1.f / (float)m.hot_copies : 1.f;
     a.lr = m.lr; a.gb = m.global_bias; a.minr = m.min_rating; a.range = m.range;
     if (m.p.biased) { a.reg_u = m.p.reg_u; a.reg_i = m.p.reg_i; }
@@ -1408,12 +1465,12 @@ static int32_t run_dsgd_epoch(Sgd& m, const int32_t* h_seq)
             MML_CUDA(cudaMemcpyAsync(dseq.p, seq.data(), sizeof(int32_t) * m.G, cudaMemcpyHostToDevice, s));
             a.seq = dseq.p;
             void* kargs[] = { (void*)&a };
-            MML_CUDA(cudaLaunchCooperativeKernel((const void*)ef, dim3(m.G), dim3(threads), kargs, m.stage_bytes, s));
+            MML_CUDA(cudaLaunchCooperativeKernel((const void*)ef, dim3(m.G * m.cpg), dim3(threads), kargs, m.stage_bytes, s));
             m.epoch_base += (uint32_t)m.G + 1u;
             m.launches++;
         } else {
             for (int t = 0; t < m.G; t++) {
-                sf<<<m.G, threads, m.stage_bytes, s>>>(a, seq[t]);
+                sf<<<m.G * m.cpg, threads, m.stage_bytes, s>>>(a, seq[t]);
                 m.launches++;
             }
             MML_CUDA(cudaGetLastError());
@@ -1504,14 +1561,17 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
     do {
         // group shape: G worker groups (CTAs), W warps per CTA, C private copies per hot item
         if (p->schedule == MML_SCHEDULE_DSGD) {
-            int32_t G = p->num_groups > 0 ? p->num_groups : ctx->sm_count;
+            // async mode: a worker group may be several CTAs (ctas_per_group) sharing the group's blocks
+            m.cpg = (p->intra_block == MML_INTRA_ASYNC && p->ctas_per_group > 0) ? std::min(p->ctas_per_group, ctx->sm_count) : 1;
+            int32_t G = p->num_groups > 0 ? p->num_groups : ctx->sm_count / m.cpg;
             G = std::min(G, std::min(r->n_users(), r->n_items()));
             m.G = std::max(G, 1);
+            m.pf_dist = p->prefetch_distance < 0 ? 0 : (p->prefetch_distance > 0 ? std::min(p->prefetch_distance, 64) : 0);
             int32_t W = p->num_subgroups > 0 ? p->num_subgroups : 8;
             m.W = std::max(1, std::min(W, 16));
             m.hot_copies = p->hot_copies > 0 ? std::min(p->hot_copies, 64) : 8;
         } else {
-            m.G = 1; m.W = 1; m.hot_copies = 1;
+            m.G = 1; m.W = 1; m.hot_copies = 1; m.cpg = 1;
         }
         // counts -> host (group balancing, zero rows)
         // item counts, rating sum and scale are global quantities: reduce them over the ranks
@@ -1608,7 +1668,7 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
         // strata
         if (p->schedule == MML_SCHEDULE_DSGD) {
             if (m.p.intra_block == MML_INTRA_ASYNC) {
-                const int32_t nw = p->async_workers > 0 ? std::min(p->async_workers, n_workers) : n_workers;
+                const int32_t nw = p->async_workers > 0 ? std::min(p->async_workers, n_workers * m.cpg) : n_workers * m.cpg;
                 if ((st = build_strata_async(m, nw))) break;
             }
             else if ((st = build_strata(m, nu_max, (int32_t)std::max<int64_t>(max_rows, 1)))) break;
@@ -1622,9 +1682,9 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
                 if ((st = get_kernels(m, &sf, &ef))) break;
                 int per_sm = 0;
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)ef, m.W * 32, m.stage_bytes) != cudaSuccess) per_sm = 0;
-                if ((int64_t)per_sm * ctx->sm_count < m.G) m.p.persistent = 0;
+                if ((int64_t)per_sm * ctx->sm_count < (int64_t)m.G * m.cpg) m.p.persistent = 0;
             }
-            if ((st = m.flags.alloc(m.G))) break;
+            if ((st = m.flags.alloc((size_t)m.G * m.cpg))) break;
             cudaMemsetAsync(m.flags.p, 0, m.flags.bytes(), s);
             m.epoch_base = 0;
         }
@@ -1866,9 +1926,14 @@ extern "C" int32_t mml_sgd_evaluate(mml_sgd* h, const int32_t* users, const int3
     if (du.n < (size_t)n) MML_TRY(du.alloc(n));
     if (di.n < (size_t)n) MML_TRY(di.alloc(n));
     if (dv.n < (size_t)n) MML_TRY(dv.alloc(n));
-    MML_CUDA(cudaMemcpyAsync(du.p, users, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
-    MML_CUDA(cudaMemcpyAsync(di.p, items, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
-    MML_CUDA(cudaMemcpyAsync(dv.p, values, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+    // The test ratings travel on the copy stream: in the find-iter loop (Iterate(); Evaluate(test)) the upload runs
+    // under the epoch kernel still in flight on `s`; the scratch buffers are free (the previous Evaluate synchronised).
+    cudaStream_t cs = m.ctx->copy_stream;
+    MML_CUDA(cudaMemcpyAsync(du.p, users, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
+    MML_CUDA(cudaMemcpyAsync(di.p, items, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
+    MML_CUDA(cudaMemcpyAsync(dv.p, values, sizeof(float) * n, cudaMemcpyHostToDevice, cs));
+    MML_CUDA(cudaEventRecord(m.ctx->copy_done, cs));
+    MML_CUDA(cudaStreamWaitEvent(s, m.ctx->copy_done, 0));
     double sums[5];
     MML_TRY(evaluate_device(m, du.p, di.p, dv.p, n, sums));
     sums[4] = (double)n;

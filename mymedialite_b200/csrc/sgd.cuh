@@ -23,7 +23,9 @@ struct Sgd {
     mml_mf_params p{};
     int32_t k = 0, kp = 0, kpl = 0;    // factors, padded row length (32 * kpl), floats per lane
     int32_t R = 1, rank = 0;           // GPU-level blocks (world size) and own block
-    int32_t G = 1, W = 1;              // worker groups (CTAs) and warps per CTA
+    int32_t G = 1, W = 1;              // worker groups and warps per CTA
+    int32_t cpg = 1;                   // CTAs per worker group (async mode; 1 otherwise)
+    int32_t pf_dist = 0;               // async mode: L2 prefetch distance of user rows, in entries (0 = off)
     int32_t hot_copies = 1;            // private copies of a hot item row inside a block
     GroupMap users, items;
     std::vector<int32_t> h_item_ptr;   // [R * G + 1] internal item row range of CTA-level item group (B, b)
@@ -44,7 +46,7 @@ struct Sgd {
     // strata: entries ordered by (block = (B, j, slot), round), see sgd.cu
     int32_t n_blk = 0;                 // R * G * G blocks
     int64_t n_rounds = 0;
-    int32_t n_workers = 0;             // async mode: workers per CTA the slices were cut for
+    int32_t n_workers = 0;             // async mode: workers per worker group the slices were cut for
     DevBuf<uint32_t> wptr;             // async mode: [n_blk][n_workers + 1]
     DevBuf<uint32_t> round_ptr;        // [n_rounds + 1] first entry of each round
     DevBuf<uint32_t> blk_round_ptr;    // [n_blk + 1] first round of each block

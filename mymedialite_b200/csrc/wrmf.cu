@@ -20,6 +20,8 @@
 #include <algorithm>
 #include <cmath>
 #include <new>
+#include <numeric>
+#include <vector>
 
 namespace mml {
 
@@ -40,7 +42,9 @@ struct Wrmf {
     double alpha = 1.0, reg = 0.015;
     DevBuf<float> U, V;                    // [n_users x k], [n_items x k] row-major, as the reference's Matrix<float>
     DevBuf<double> HH, HH_part;
-    DevBuf<int32_t> order_u, order_i;      // rows by descending nnz (work queue order)
+    DevBuf<int32_t> order_u, order_i;      // this rank's rows by descending nnz (work queue order)
+    int32_t n_local_u = 0, n_local_i = 0;  // rows this rank solves in each half-sweep
+    std::vector<int32_t> range_u, range_i; // [world + 1] multi-GPU: rank r solves rows [range[r], range[r + 1])
     DevBuf<unsigned> counter;
     bool has_model = false;
     int64_t launches = 0;
@@ -142,6 +146,38 @@ static int32_t rows_by_nnz(Ctx* ctx, const uint32_t* ptr, int32_t n_rows, DevBuf
     MML_TRY(radix_sort_pairs(key.p, val.p, t1.p, t2.p, n_rows, 32, s));
     MML_CUDA(cudaMemcpyAsync(out.p, val.p, sizeof(int32_t) * (size_t)n_rows, cudaMemcpyDeviceToDevice, s));
     MML_CUDA(cudaStreamSynchronize(s));
+    return MML_OK;
+}
+
+// Multi-GPU: rows of a half-sweep are independent given the other factor matrix, so rank r solves the
+// contiguous row range [range[r], range[r + 1]) and the ranks all-gather the solved rows. Ranges are balanced by
+// cost = nnz + row_cost (row_cost stands for the solve, which every row pays, empty ones included: WRMF.cs:79-92
+// solves all rows). out = the rank's rows in descending nnz order.
+static int32_t shard_rows(Ctx* ctx, const uint32_t* d_ptr, int32_t n_rows, int64_t row_cost, std::vector<int32_t>& range,
+                          DevBuf<int32_t>& out, int32_t* n_local)
+{
+    cudaStream_t s = ctx->stream;
+    const int R = std::max(ctx->n_gpus, 1);
+    std::vector<uint32_t> ptr((size_t)n_rows + 1);
+    MML_CUDA(cudaMemcpyAsync(ptr.data(), d_ptr, sizeof(uint32_t) * ptr.size(), cudaMemcpyDeviceToHost, s));
+    MML_CUDA(cudaStreamSynchronize(s));
+    const int64_t total = (int64_t)ptr[n_rows] + row_cost * n_rows;
+    range.assign((size_t)R + 1, n_rows);
+    range[0] = 0;
+    int64_t cum = 0;
+    int r = 1;
+    for (int32_t row = 0; row < n_rows && r < R; row++) {
+        cum += (int64_t)(ptr[row + 1] - ptr[row]) + row_cost;
+        while (r < R && cum * R >= total * r) range[r++] = row + 1;
+    }
+    const int32_t lo = range[ctx->rank], hi = range[ctx->rank + 1];
+    std::vector<int32_t> rows((size_t)(hi - lo));
+    std::iota(rows.begin(), rows.end(), lo);
+    std::stable_sort(rows.begin(), rows.end(), [&](int32_t a, int32_t b) { return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b]; });
+    MML_TRY(out.alloc(std::max<size_t>(rows.size(), 1)));
+    if (!rows.empty()) MML_CUDA(cudaMemcpyAsync(out.p, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, s));
+    MML_CUDA(cudaStreamSynchronize(s));
+    *n_local = hi - lo;
     return MML_OK;
 }
 
@@ -434,8 +470,16 @@ extern "C" int32_t mml_wrmf_create(mml_ctx* hctx, mml_feedback* hf, const mml_wr
     do {
         if ((st = m.U.alloc((size_t)m.fb->n_users() * m.k)) || (st = m.V.alloc((size_t)m.fb->n_items() * m.k))) break;
         if ((st = m.HH.alloc((size_t)m.k * m.k)) || (st = m.counter.alloc(1))) break;
-        if ((st = rows_by_nnz(ctx, m.fb->user_ptr.p, m.fb->n_users(), m.order_u))) break;
-        if ((st = rows_by_nnz(ctx, m.fb->item_ptr.p, m.fb->n_items(), m.order_i))) break;
+        if (ctx->n_gpus > 1) {
+            const int64_t row_cost = 8 * (int64_t)m.k;   // measured at k = 128: one solve costs about as much as 1100 Gram-sum entries
+            if ((st = shard_rows(ctx, m.fb->user_ptr.p, m.fb->n_users(), row_cost, m.range_u, m.order_u, &m.n_local_u))) break;
+            if ((st = shard_rows(ctx, m.fb->item_ptr.p, m.fb->n_items(), row_cost, m.range_i, m.order_i, &m.n_local_i))) break;
+        } else {
+            if ((st = rows_by_nnz(ctx, m.fb->user_ptr.p, m.fb->n_users(), m.order_u))) break;
+            if ((st = rows_by_nnz(ctx, m.fb->item_ptr.p, m.fb->n_items(), m.order_i))) break;
+            m.n_local_u = m.fb->n_users(); m.n_local_i = m.fb->n_items();
+            m.range_u = {0, m.n_local_u}; m.range_i = {0, m.n_local_i};
+        }
         if (cudaEventCreate(&m.ev0) != cudaSuccess || cudaEventCreate(&m.ev1) != cudaSuccess) { set_error("cudaEventCreate failed"); st = MML_ERR_CUDA; break; }
     } while (0);
     if (st) { delete h; return st; }
@@ -511,6 +555,25 @@ extern "C" int32_t mml_wrmf_get_model(mml_wrmf* h, float* user_factors, float* i
     return MML_OK;
 }
 
+// All-gather of the solved rows: every rank's range is broadcast from it (ranges differ in length), one grouped call.
+static int32_t gather_rows(Wrmf& m, float* W, const std::vector<int32_t>& range)
+{
+    if (m.ctx->n_gpus <= 1) return MML_OK;
+    MML_TRY(dist_group_start());
+    for (int r = 0; r < m.ctx->n_gpus; r++)
+        MML_TRY(dist_broadcast_f32(m.ctx, W + (size_t)range[r] * m.k, (size_t)(range[r + 1] - range[r]) * m.k, r));
+    MML_TRY(dist_group_end());
+    return MML_OK;
+}
+
+extern "C" int32_t mml_wrmf_shard(mml_wrmf* h, int32_t by_item, int32_t* ranges)
+{
+    MML_CHECK(h && ranges, MML_ERR_ARG, "NULL argument");
+    const std::vector<int32_t>& r = by_item ? h->m.range_i : h->m.range_u;
+    for (size_t t = 0; t < r.size(); t++) ranges[t] = r[t];
+    return MML_OK;
+}
+
 // WRMF.Iterate (WRMF.cs:68-73): user half-sweep, then item half-sweep
 extern "C" int32_t mml_wrmf_iterate(mml_wrmf* h)
 {
@@ -521,8 +584,10 @@ extern "C" int32_t mml_wrmf_iterate(mml_wrmf* h)
     cudaStream_t s = m.ctx->stream;
     Feedback& f = *m.fb;
     MML_CUDA(cudaEventRecord(m.ev0, s));
-    MML_TRY(half_sweep(m, f.user_ptr.p, f.user_cols.p, m.order_u.p, f.n_users(), m.U.p, m.V.p, f.n_items()));
-    MML_TRY(half_sweep(m, f.item_ptr.p, f.item_rows.p, m.order_i.p, f.n_items(), m.V.p, m.U.p, f.n_users()));
+    MML_TRY(half_sweep(m, f.user_ptr.p, f.user_cols.p, m.order_u.p, m.n_local_u, m.U.p, m.V.p, f.n_items()));
+    MML_TRY(gather_rows(m, m.U.p, m.range_u));
+    MML_TRY(half_sweep(m, f.item_ptr.p, f.item_rows.p, m.order_i.p, m.n_local_i, m.V.p, m.U.p, f.n_users()));
+    MML_TRY(gather_rows(m, m.V.p, m.range_i));
     MML_CUDA(cudaEventRecord(m.ev1, s));
     m.timed = true;
     return MML_OK;

@@ -266,22 +266,23 @@ struct SolveArgs {
 
 __device__ __forceinline__ double* sv_blk(double* L, int bi, int bj) { return L + (size_t)(bi * (bi + 1) / 2 + bj) * SV_BLK; }
 
-// x <- L^-1 x (forward) for the vector x[0 .. kp), blocked; all threads of the CTA call it
-__device__ __forceinline__ void sv_forward(double* L, const double* rdiag, double* x, int np)
+// Triangular solves with the blocked factor. The 16 x 16 diagonal blocks are applied through their explicit inverses
+// Dinv[p] = L(p,p)^-1 (computed once per factorisation), so a panel step is a small matrix-vector product instead of a
+// 16-step dependent chain: 2 barriers per panel.
+// x <- L^-1 x (forward) for the vector x[0 .. kp); all threads of the CTA call it
+__device__ __forceinline__ void sv_forward(double* L, const double* Dinv, double* x, int np)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     for (int p = 0; p < np; p++) {
         const int j0 = p * SV_NB;
-        if (warp == 0) {
-            const double* D = sv_blk(L, p, p);
-            for (int c = 0; c < SV_NB; c++) {
-                if (lane == c) x[j0 + c] *= rdiag[j0 + c];
-                __syncwarp();
-                const double y = x[j0 + c];
-                if (lane > c && lane < SV_NB) x[j0 + lane] -= D[lane * SV_LD + c] * y;
-                __syncwarp();
-            }
+        double y = 0.0;
+        if (tid < SV_NB) {
+            const double* D = Dinv + (size_t)p * SV_BLK + tid * SV_LD;
+#pragma unroll
+            for (int t = 0; t < SV_NB; t++) y += (t <= tid) ? D[t] * x[j0 + t] : 0.0;
         }
+        if (tid < 32) __syncwarp();
+        if (tid < SV_NB) x[j0 + tid] = y;
         __syncthreads();
         for (int i = j0 + SV_NB + tid; i < np * SV_NB; i += SV_THREADS) {
             const double* B = sv_blk(L, i / SV_NB, p) + (i % SV_NB) * SV_LD;
@@ -295,21 +296,19 @@ __device__ __forceinline__ void sv_forward(double* L, const double* rdiag, doubl
 }
 
 // x <- L^-T x (backward)
-__device__ __forceinline__ void sv_backward(double* L, const double* rdiag, double* x, int np)
+__device__ __forceinline__ void sv_backward(double* L, const double* Dinv, double* x, int np)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     for (int p = np - 1; p >= 0; p--) {
         const int j0 = p * SV_NB;
-        if (warp == 0) {
-            const double* D = sv_blk(L, p, p);
-            for (int c = SV_NB - 1; c >= 0; c--) {
-                if (lane == c) x[j0 + c] *= rdiag[j0 + c];
-                __syncwarp();
-                const double w = x[j0 + c];
-                if (lane < c) x[j0 + lane] -= D[c * SV_LD + lane] * w;
-                __syncwarp();
-            }
+        double y = 0.0;
+        if (tid < SV_NB) {
+            const double* D = Dinv + (size_t)p * SV_BLK + tid;
+#pragma unroll
+            for (int t = 0; t < SV_NB; t++) y += (t >= tid) ? D[t * SV_LD] * x[j0 + t] : 0.0;
         }
+        if (tid < 32) __syncwarp();
+        if (tid < SV_NB) x[j0 + tid] = y;
         __syncthreads();
         for (int j = tid; j < j0; j += SV_THREADS) {
             const double* B = sv_blk(L, p, j / SV_NB) + (j % SV_NB);
@@ -342,6 +341,7 @@ __global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveAr
     double* rv = wv + kp;                             // [kp] residual / correction
     double* rdiag = rv + kp;                          // [kp] 1 / L[i][i]
     double* red = rdiag + kp;                         // [8][kp] per-warp partial sums of the refinement gather
+    double* Dinv = red + (size_t)(SV_THREADS / 32) * kp;   // [np][16][17] inverses of the diagonal blocks
     __shared__ double s_norm[2];
     const float* G = a.G + (size_t)blockIdx.x * WS_KP * WS_KP;
     // ---- assemble the lower triangle; padding rows/columns: identity
@@ -379,20 +379,36 @@ __global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveAr
                 }
                 __syncwarp();
             }
-        }
-        __syncthreads();
-        // panel below the diagonal block: X L11^T = A21, one thread per row
-        {
-            const double* D = sv_blk(L, p, p);
-            for (int i = j0 + SV_NB + tid; i < kp; i += SV_THREADS) {
-                double* Ai = sv_blk(L, i / SV_NB, p) + (i % SV_NB) * SV_LD;
+            // explicit inverse of the diagonal block: lane c solves L11 x = e_c (column c of L11^-1)
+            double* Di = Dinv + (size_t)p * SV_BLK;
+            if (lane < SV_NB) {
                 double x[SV_NB];
 #pragma unroll
-                for (int c = 0; c < SV_NB; c++) {
-                    double sacc = Ai[c];
+                for (int r = 0; r < SV_NB; r++) {
+                    double sacc = (r == lane) ? 1.0 : 0.0;
 #pragma unroll
-                    for (int t = 0; t < c; t++) sacc -= x[t] * D[c * SV_LD + t];
-                    x[c] = sacc * rdiag[j0 + c];
+                    for (int t = 0; t < r; t++) sacc -= D[r * SV_LD + t] * x[t];
+                    x[r] = (r >= lane) ? sacc * rdiag[j0 + r] : 0.0;
+                }
+#pragma unroll
+                for (int r = 0; r < SV_NB; r++) Di[r * SV_LD + lane] = x[r];
+            }
+        }
+        __syncthreads();
+        // panel below the diagonal block: X = A21 L11^-T, i.e. X[i][c] = sum_{t <= c} A21[i][t] Dinv[c][t]; one thread per row
+        {
+            const double* Di = Dinv + (size_t)p * SV_BLK;
+            for (int i = j0 + SV_NB + tid; i < kp; i += SV_THREADS) {
+                double* Ai = sv_blk(L, i / SV_NB, p) + (i % SV_NB) * SV_LD;
+                double ar[SV_NB], x[SV_NB];
+#pragma unroll
+                for (int t = 0; t < SV_NB; t++) ar[t] = Ai[t];
+#pragma unroll
+                for (int c = 0; c < SV_NB; c++) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int t = 0; t <= c; t++) sacc += ar[t] * Di[c * SV_LD + t];
+                    x[c] = sacc;
                 }
 #pragma unroll
                 for (int c = 0; c < SV_NB; c++) Ai[c] = x[c];
@@ -435,8 +451,8 @@ __global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveAr
         __syncthreads();
     }
     // ---- w = L^-T L^-1 b
-    sv_forward(L, rdiag, wv, np);
-    sv_backward(L, rdiag, wv, np);
+    sv_forward(L, Dinv, wv, np);
+    sv_backward(L, Dinv, wv, np);
     // ---- refinement against the exact operator
     for (int iter = 0; iter < SV_MAX_REFINE; iter++) {
         // r = b - HH w - lambda w   (HH is symmetric: column reads are coalesced)
@@ -486,9 +502,9 @@ __global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveAr
             atomicMax(reinterpret_cast<unsigned long long*>(&s_norm[1]), (unsigned long long)__double_as_longlong(bmax));
         }
         __syncthreads();
-        if (!(s_norm[0] > 1e-10 * s_norm[1])) break;           // converged (uniform across the CTA)
-        sv_forward(L, rdiag, rv, np);
-        sv_backward(L, rdiag, rv, np);
+        if (!(s_norm[0] > 1e-9 * s_norm[1])) break;            // converged (uniform across the CTA)
+        sv_forward(L, Dinv, rv, np);
+        sv_backward(L, Dinv, rv, np);
         for (int f = tid; f < k; f += SV_THREADS) wv[f] += rv[f];
         __syncthreads();
     }
@@ -524,7 +540,7 @@ int32_t wrmf_tc_half_sweep(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_ptr, 
     const size_t smem_syrk = (size_t)WS_STAGES * 2 * WS_TILE + 1024;
     MML_CUDA(cudaFuncSetAttribute((const void*)wrmf_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_syrk));
     const int np = (k + SV_NB - 1) / SV_NB, kp = np * SV_NB;
-    const size_t smem_solve = sizeof(double) * ((size_t)np * (np + 1) / 2 * SV_BLK + (size_t)kp * (4 + SV_THREADS / 32));
+    const size_t smem_solve = sizeof(double) * ((size_t)np * (np + 1) / 2 * SV_BLK + (size_t)kp * (4 + SV_THREADS / 32) + (size_t)np * SV_BLK);
     MML_CUDA(cudaFuncSetAttribute((const void*)wrmf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
     for (int32_t q_lo = 0; q_lo < n_rows; q_lo += B) {
         const int32_t q_hi = std::min(n_rows, q_lo + B), nb = q_hi - q_lo;

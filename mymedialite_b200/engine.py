@@ -347,6 +347,12 @@ class WrmfModel:
     def iterate(self):
         check(self.lib.mml_wrmf_iterate(self.h))
 
+    def shard(self, by_item=False):
+        """Multi-GPU: row ranges [ranges[r], ranges[r + 1]) each rank solves in the user (item) half-sweep."""
+        r = (C.c_int32 * (self.ctx.world + 1))()
+        check(self.lib.mml_wrmf_shard(self.h, int(by_item), r))
+        return np.array(list(r), np.int32)
+
     def debug_gram(self):
         """(user, G) with G = sum of h_i h_i^T over that user's items as the tensor-core kernel computed it."""
         G = np.zeros((128, 128), np.float32)

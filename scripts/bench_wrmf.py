@@ -21,7 +21,15 @@ def main():
     ap.add_argument("--epochs", type=int, default=3)
     args = ap.parse_args()
     from mymedialite_b200 import engine, synthetic
-    ctx = engine.Context(0)
+    from mymedialite_b200 import dist as mdist
+    rank, world, local = mdist.env_rank()
+    tdist = None
+    if world > 1:        # strong scaling: same problem, rows of each half-sweep sharded over the ranks
+        import torch
+        import torch.distributed as tdist
+        torch.cuda.set_device(local)
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = mdist.create_context(local)
     t0 = time.time()
     u, i = synthetic.implicit(args.users, args.items, args.events, 20260103)
     gen_s = time.time() - t0
@@ -33,13 +41,27 @@ def main():
     build_s = time.time() - t0
     ms = []
     for _ in range(args.epochs):
+        ctx.synchronize()
+        if tdist is not None:
+            tdist.barrier()
         m.iterate()
-        ms.append(m.stats()[1])
+        x = m.stats()[1]
+        if tdist is not None:
+            import torch
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+            x = float(t.item())
+        ms.append(x)
     nnz = f.nnz
     flop = 2.0 * args.k * args.k * (2.0 * nnz + args.users + args.items)
-    print(json.dumps({"shape": {"users": args.users, "items": args.items, "events": int(u.size), "nnz": int(nnz), "k": args.k},
-                      "epoch_ms": [round(x, 2) for x in ms], "gen_s": round(gen_s, 1), "build_s": round(build_s, 2),
-                      "tflops_algorithmic": flop / (min(ms) * 1e-3) / 1e12}))
+    if rank == 0:
+        print(json.dumps({"shape": {"users": args.users, "items": args.items, "events": int(u.size), "nnz": int(nnz), "k": args.k},
+                          "n_gpus": world, "epoch_ms": [round(x, 2) for x in ms], "gen_s": round(gen_s, 1), "build_s": round(build_s, 2),
+                          "user_ranges": m.shard(False).tolist(), "item_ranges": m.shard(True).tolist(),
+                          "tflops_algorithmic": flop / (min(ms) * 1e-3) / 1e12}), flush=True)
+    if tdist is not None:
+        tdist.barrier()
+        tdist.destroy_process_group()
 
 
 if __name__ == "__main__":

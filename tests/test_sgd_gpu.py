@@ -137,6 +137,27 @@ def test_dsgd_epoch_equals_oracle_replay(eng, k, biased, G, W, persistent, loss,
     assert_model_close(gm, om, biased, 5e-5 if intra == "rounds" else 3e-4)
 
 
+@pytest.mark.parametrize("k,G,cpg,W,persistent", [(64, 3, 2, 4, 1), (128, 4, 3, 2, 1), (32, 2, 4, 2, 0), (128, 1, 6, 4, 1)])
+def test_dsgd_multi_cta_groups_equal_oracle_replay(eng, k, G, cpg, W, persistent):
+    """A worker group made of several CTAs (ctas_per_group): with one active worker per group the epoch is
+    still a serial pass in the dumped order; the hand-over waits on every CTA of the previous holder."""
+    engine, ctx = eng
+    d = small_data()
+    u, i, v = d["train"]
+    om = oracle_model(u, i, v, True, k)
+    r, gm = gpu_model(eng, u, i, v, True, k, om, num_groups=G, ctas_per_group=cpg, num_subgroups=W, persistent=persistent,
+                      intra_block=engine._capi.INTRA_ASYNC, async_workers=1)
+    assert gm.strata_info()["G"] == G
+    rs = np.random.RandomState(4)
+    for epoch in range(2):
+        seq = rs.permutation(G).astype(np.int32)
+        order = gm.schedule(seq)
+        assert np.array_equal(np.sort(order), np.arange(u.size))
+        gm.iterate(subepoch_sequence=seq)
+        om.iterate_indices(order)
+    assert_model_close(gm, om, True, 3e-4)
+
+
 def _emulate_epoch(model, u, i, v, order, block, copy, W, hp, average=False):
     """fp32 numpy restatement of the kernel's semantics INCLUDING hot-item copies: inside a block a hot item's
     entries update private copies (all starting from the row at block start); at block end
@@ -253,7 +274,7 @@ def test_dsgd_rounds_are_matchings(eng):
         pos += sz
 
 
-@pytest.mark.parametrize("intra", ["async", "rounds"])
+@pytest.mark.parametrize("intra", ["async", "rounds", "async_4x4", "async_1x16"])
 def test_dsgd_rmse_tracks_single_threaded_oracle(eng, intra):
     """north_star gate: per-epoch train/test RMSE within 0.5 % of the reference's own (MaxThreads=1) run, for the
     default lock-free intra-block mode and for the conflict-free rounds."""
@@ -265,8 +286,12 @@ def test_dsgd_rmse_tracks_single_threaded_oracle(eng, intra):
     rng = O.Random(1)
     om = O.Model(u, i, v, biased=True, num_factors=k)
     om.init(rng)
-    r, gm = gpu_model(eng, u, i, v, True, k, om, num_groups=16, num_subgroups=4, hot_item_factor=0.0,
-                      intra_block=engine._capi.INTRA_ASYNC if intra == "async" else engine._capi.INTRA_ROUNDS)
+    shape = dict(num_groups=16)
+    if "x" in intra:     # worker groups of several CTAs; 1 x 16 = the whole grid is one lock-free group
+        g, c = intra.split("_")[1].split("x")
+        shape = dict(num_groups=int(g), ctas_per_group=int(c))
+    r, gm = gpu_model(eng, u, i, v, True, k, om, num_subgroups=4, hot_item_factor=0.0,
+                      intra_block=engine._capi.INTRA_ROUNDS if intra == "rounds" else engine._capi.INTRA_ASYNC, **shape)
     for epoch in range(8):
         om.iterate(rng)
         gm.iterate()
