@@ -180,7 +180,7 @@ def run_ours(args):
     ratings = engine.DeviceRatings(ctx, u, i, v, max_user=d["n_users"] - 1, max_item=d["n_items"] - 1)
     params = engine.default_params(biased=1, num_factors=k, num_groups=args.groups, num_subgroups=args.subgroups,
                                    persistent=args.persistent, hot_item_factor=args.hot, hot_copies=args.copies,
-                                   intra_block=args.intra, hot_merge_average=args.hot_avg, ctas_per_group=args.cpg, prefetch_distance=args.pf)
+                                   intra_block=args.intra, hot_merge_average=args.hot_avg, ctas_per_group=args.cpg)
     model = engine.SgdModel(ctx, ratings, params)
     model.init_model(1, 0.0, 0.1)
     ctx.synchronize()
@@ -242,7 +242,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc + (" per GPU (users sharded, item catalogue shared)" if world > 1 else ""),
                    "n_ratings": n_total, "num_factors": k,
-                   "schedule": "DSGD G=%d x %d CTAs, W=%d %s%s%s" % (info["G"], max(args.cpg, 1), info["W"], "async" if args.intra else "rounds",
+                   "schedule": "DSGD G=%d x %d CTAs, W=%d %s%s%s" % (info["G"], info["cpg"], info["W"], "async" if args.intra else "rounds",
                                                           " persistent" if params.persistent != 0 else "",
                                                           (", item-block ring over %d GPUs" % world) if world > 1 else ""),
                    "l2": "flushed before every timed epoch (384 MB memset)", "strata_build_s": round(build_s, 3)},
@@ -336,7 +336,6 @@ def main():
     ap.add_argument("--workload", default="netflix", choices=sorted(WORKLOADS))
     ap.add_argument("--groups", type=int, default=0)
     ap.add_argument("--cpg", type=int, default=0, help="CTAs per worker group (async mode); groups default to SMs / cpg")
-    ap.add_argument("--pf", type=int, default=0, help="L2 prefetch distance of user rows (async mode); 0 = library default, -1 = off")
     ap.add_argument("--subgroups", type=int, default=16)
     ap.add_argument("--persistent", type=int, default=-1)
     ap.add_argument("--hot", type=float, default=0.0)

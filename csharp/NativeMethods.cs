@@ -15,7 +15,7 @@ namespace MyMediaLite.Native
 		public int frequency_regularization, loss, bold_driver, max_threads;
 		public int schedule, num_groups, num_subgroups, group_rule, persistent;
 		public float hot_item_factor;
-		public int hot_copies, intra_block, hot_merge_average, async_workers, ctas_per_group, prefetch_distance;
+		public int hot_copies, intra_block, hot_merge_average, async_workers, ctas_per_group;
 	}
 
 	/// <summary>mml_wrmf_params of include/mmlb200.h</summary>
@@ -88,6 +88,7 @@ namespace MyMediaLite.Native
 		[DllImport(LIB)] public static extern int mml_sgd_stats(IntPtr model, out long kernel_launches, out float last_iterate_ms);
 		[DllImport(LIB)] public static extern int mml_sgd_strata_info(IntPtr model, out int G, out int W, out long n_rounds, out long staged_bytes);
 		[DllImport(LIB)] public static extern int mml_sgd_hot_items(IntPtr model, out long n_hot);
+		[DllImport(LIB)] public static extern int mml_sgd_grid(IntPtr model, out int G, out int ctas_per_group);
 		[DllImport(LIB)] public static extern int mml_sgd_schedule_dump(IntPtr model, int[] subepoch_sequence, [Out] int[] order, [Out] int[] block, [Out] int[] copy, [Out] int[] round);
 
 		// top-N

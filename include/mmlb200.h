@@ -115,7 +115,7 @@ typedef struct mml_mf_params {
                                      multi-threaded semantics (learn rate updated twice per epoch, :216/:221) */
     /* engine knobs (not reference options) */
     int32_t schedule;             /* MML_SCHEDULE_* */
-    int32_t num_groups;           /* G: DSGD worker groups on this GPU (one CTA each); 0 = one per SM */
+    int32_t num_groups;           /* G: DSGD worker groups on this GPU; 0 = SMs / ctas_per_group */
     int32_t num_subgroups;        /* warps per worker group (a warp runs 32/L ratings of a round at once); 0 = 8 */
     int32_t group_rule;           /* MML_GROUPS_* */
     int32_t persistent;           /* 1 = one cooperative launch per epoch with neighbour flags instead of
@@ -131,11 +131,10 @@ typedef struct mml_mf_params {
     int32_t async_workers;        /* async mode: workers per worker group that take part; 0 = all, 1 = serial
                                      inside a block (deterministic; used by the parity tests) */
     int32_t ctas_per_group;       /* async mode: CTAs that make up one worker group and share its blocks
-                                     (num_groups = 0 then means SMs / ctas_per_group groups); 0 = 1.
+                                     (num_groups = 0 then means SMs / ctas_per_group groups); 0 = 4 when
+                                     num_groups is 0 too, else 1.
                                      num_groups = 1 makes the whole GPU one worker group: no block hand-over,
                                      the reference's NaiveParallelization inside the GPU */
-    int32_t prefetch_distance;    /* async mode: user rows are pulled into the L2 this many ratings ahead of their use
-                                     (the user matrix does not fit the L2 at the Netflix shape); 0 = default, -1 = off */
 } mml_mf_params;
 
 void mml_mf_params_default(mml_mf_params* p);
@@ -184,6 +183,8 @@ int32_t mml_sgd_objective(mml_sgd* m, double* out);
 int32_t mml_sgd_stats(mml_sgd* m, int64_t* kernel_launches, float* last_iterate_ms);
 /* Strata shape: G, warps per group, number of rounds, staged item block bytes (0 = item rows stay in global memory). */
 int32_t mml_sgd_strata_info(mml_sgd* m, int32_t* G, int32_t* W, int64_t* n_rounds, int64_t* staged_bytes);
+/* Grid of the DSGD epoch kernel: G worker groups x ctas_per_group CTAs (as resolved from the params' defaults). */
+int32_t mml_sgd_grid(mml_sgd* m, int32_t* G, int32_t* ctas_per_group);
 /* Strata shape: ..., number of hot items. */
 int32_t mml_sgd_hot_items(mml_sgd* m, int64_t* n_hot);
 /* The serial-equivalent order of one DSGD epoch with the given sub-epoch sequence (NULL = 0..G-1):

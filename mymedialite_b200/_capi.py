@@ -34,7 +34,7 @@ class MFParams(C.Structure):
         ("reg_u", C.c_float), ("reg_i", C.c_float), ("frequency_regularization", C.c_int32),
         ("loss", C.c_int32), ("bold_driver", C.c_int32), ("max_threads", C.c_int32),
         ("schedule", C.c_int32), ("num_groups", C.c_int32), ("num_subgroups", C.c_int32),
-        ("group_rule", C.c_int32), ("persistent", C.c_int32), ("hot_item_factor", C.c_float), ("hot_copies", C.c_int32), ("intra_block", C.c_int32), ("hot_merge_average", C.c_int32), ("async_workers", C.c_int32), ("ctas_per_group", C.c_int32), ("prefetch_distance", C.c_int32),
+        ("group_rule", C.c_int32), ("persistent", C.c_int32), ("hot_item_factor", C.c_float), ("hot_copies", C.c_int32), ("intra_block", C.c_int32), ("hot_merge_average", C.c_int32), ("async_workers", C.c_int32), ("ctas_per_group", C.c_int32),
     ]
 
 
@@ -93,6 +93,7 @@ SIGNATURES = {
     "mml_sgd_stats": (C.c_int32, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "mml_sgd_strata_info": (C.c_int32, [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mml_sgd_hot_items": (C.c_int32, [vp, C.POINTER(C.c_int64)]),
+    "mml_sgd_grid": (C.c_int32, [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mml_topn_mf": (C.c_int32, [vp, f32p, C.c_int32, f32p, C.c_int32, C.c_int32, oi32p, C.c_int64, C.c_int32,
                                 oi32p, C.c_int64, oi64p, oi32p, i32p, f32p, i32p]),
     "mml_topn_set_mode": (C.c_int32, [C.c_int32]),

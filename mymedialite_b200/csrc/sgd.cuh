@@ -25,7 +25,6 @@ struct Sgd {
     int32_t R = 1, rank = 0;           // GPU-level blocks (world size) and own block
     int32_t G = 1, W = 1;              // worker groups and warps per CTA
     int32_t cpg = 1;                   // CTAs per worker group (async mode; 1 otherwise)
-    int32_t pf_dist = 0;               // async mode: L2 prefetch distance of user rows, in entries (0 = off)
     int32_t hot_copies = 1;            // private copies of a hot item row inside a block
     GroupMap users, items;
     std::vector<int32_t> h_item_ptr;   // [R * G + 1] internal item row range of CTA-level item group (B, b)

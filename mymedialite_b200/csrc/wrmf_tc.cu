@@ -365,20 +365,30 @@ __global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveAr
     // ---- blocked right-looking Cholesky
     for (int p = 0; p < np; p++) {
         const int j0 = p * SV_NB;
-        if (warp == 0) {                              // diagonal block, lane l owns row l
+        if (warp == 0) {                              // diagonal block in registers: lane l owns row l
             double* D = sv_blk(L, p, p);
+            const int row = lane & (SV_NB - 1);       // lanes 16..31 mirror 0..15 (their results are discarded)
+            double rr[SV_NB];
+#pragma unroll
+            for (int c = 0; c < SV_NB; c++) rr[c] = (c <= row) ? D[row * SV_LD + c] : 0.0;
+#pragma unroll
             for (int c = 0; c < SV_NB; c++) {
-                if (lane == c) { const double d = sqrt(D[c * SV_LD + c]); D[c * SV_LD + c] = d; rdiag[j0 + c] = 1.0 / d; }
-                __syncwarp();
-                const double rd = rdiag[j0 + c];
-                if (lane > c && lane < SV_NB) D[lane * SV_LD + c] *= rd;
-                __syncwarp();
-                if (lane > c && lane < SV_NB) {
-                    const double l = D[lane * SV_LD + c];
-                    for (int c2 = c + 1; c2 <= lane; c2++) D[lane * SV_LD + c2] -= l * D[c2 * SV_LD + c];
+                const double dcc = __shfl_sync(0xffffffffu, rr[c], c);
+                const double rd = rsqrt(dcc);         // 1 / L[c][c]
+                const double lc = rr[c] * rd;          // L[row][c] for row >= c (row == c: sqrt(dcc))
+                rr[c] = lc;
+                if (lane == c) rdiag[j0 + c] = rd;
+#pragma unroll
+                for (int c2 = c + 1; c2 < SV_NB; c2++) {
+                    const double l2 = __shfl_sync(0xffffffffu, lc, c2);
+                    if (row >= c2) rr[c2] -= lc * l2;
                 }
-                __syncwarp();
             }
+            if (lane < SV_NB) {
+#pragma unroll
+                for (int c = 0; c < SV_NB; c++) if (c <= row) D[row * SV_LD + c] = rr[c];
+            }
+            __syncwarp();
             // explicit inverse of the diagonal block: lane c solves L11 x = e_c (column c of L11^-1)
             double* Di = Dinv + (size_t)p * SV_BLK;
             if (lane < SV_NB) {

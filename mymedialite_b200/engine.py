@@ -196,7 +196,9 @@ class SgdModel:
     def strata_info(self):
         G, W, ns, sb = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
         check(self.lib.mml_sgd_strata_info(self.h, C.byref(G), C.byref(W), C.byref(ns), C.byref(sb)))
-        return dict(G=G.value, W=W.value, n_rounds=ns.value, staged_bytes=sb.value)
+        cpg = C.c_int32()
+        check(self.lib.mml_sgd_grid(self.h, C.byref(G), C.byref(cpg)))
+        return dict(G=G.value, W=W.value, n_rounds=ns.value, staged_bytes=sb.value, cpg=cpg.value)
 
     def schedule(self, subepoch_sequence=None, detail=False, rounds=False):
         n = self.ratings.n

@@ -26,7 +26,6 @@ def main():
     ap.add_argument("--shapes", default="148x1,74x2,37x4,18x8,9x16,4x37,2x74,1x148")
     ap.add_argument("--subgroups", type=int, default=16)
     ap.add_argument("--pop-offset", type=float, default=None)
-    ap.add_argument("--pf", default="0", help="comma list of L2 prefetch distances to sweep")
     args = ap.parse_args()
     from mymedialite_b200 import engine
     d, k, desc = bench.make_data(args.workload, 0, 1, args.pop_offset)
@@ -57,11 +56,10 @@ def main():
         th.start()
 
     results = []
-    for shape, pf in [(s_, int(p_)) for s_ in args.shapes.split(",") for p_ in args.pf.split(",")]:
+    for shape in args.shapes.split(","):
         G, cpg = (int(x) for x in shape.split("x"))
         t0 = time.time()
-        params = engine.default_params(biased=1, num_factors=k, num_groups=G, ctas_per_group=cpg, num_subgroups=args.subgroups,
-                                       prefetch_distance=pf)
+        params = engine.default_params(biased=1, num_factors=k, num_groups=G, ctas_per_group=cpg, num_subgroups=args.subgroups)
         model = engine.SgdModel(ctx, ratings, params)
         if U0 is not None:
             model.set_model(U0, V0)
@@ -76,7 +74,7 @@ def main():
             model.iterate(rs.permutation(model.strata_info()["G"]).astype(np.int32))
             ms.append(model.stats()[1])
             tr.append(model.evaluate_train()["RMSE"]); te.append(model.evaluate(tu, ti, tv)["RMSE"])
-        r = {"shape": shape, "pf": pf, "G": G, "cpg": cpg, "build_s": round(build_s, 2), "ms": [round(x, 3) for x in ms],
+        r = {"shape": shape, "G": G, "cpg": cpg, "build_s": round(build_s, 2), "ms": [round(x, 3) for x in ms],
              "ms_med": float(np.median(ms)), "gratings_s": n / float(np.median(ms)) / 1e6,
              "train": [round(x, 5) for x in tr], "test": [round(x, 5) for x in te]}
         results.append(r)
