@@ -1548,11 +1548,12 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
         if (p->schedule == MML_SCHEDULE_DSGD) {
             // async mode: a worker group may be several CTAs (ctas_per_group) sharing the group's blocks
             // Default (both 0): groups of 4 CTAs, SMs / 4 groups -- on the measured shapes within 5 % of the best grid
-            // (37 x 4 on 148 SMs: config 4 16.7 ms vs 19.7 ms with 148 x 1).
+            // (37 x 4 on 148 SMs: config 4 16.7 ms vs 19.7 ms with 148 x 1); 18 x 8 when the
+            // item matrix is split over several GPUs (one GPU-level sub-epoch of config 4 at 8 GPUs: 2.80 vs 2.91 ms).
             m.cpg = 1;
             if (p->intra_block == MML_INTRA_ASYNC) {
                 if (p->ctas_per_group > 0) m.cpg = std::min(p->ctas_per_group, ctx->sm_count);
-                else if (p->num_groups <= 0 && ctx->sm_count >= 8) m.cpg = 4;
+                else if (p->num_groups <= 0 && ctx->sm_count >= 16) m.cpg = m.R > 1 ? 8 : 4;   // multi-GPU: a launch sees 1/R of the items
             }
             int32_t G = p->num_groups > 0 ? p->num_groups : ctx->sm_count / m.cpg;
             G = std::min(G, std::min(r->n_users(), r->n_items()));

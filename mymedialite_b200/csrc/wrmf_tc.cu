@@ -344,18 +344,20 @@ __global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveAr
     double* Dinv = red + (size_t)(SV_THREADS / 32) * kp;   // [np][16][17] inverses of the diagonal blocks
     __shared__ double s_norm[2];
     const float* G = a.G + (size_t)blockIdx.x * WS_KP * WS_KP;
-    // ---- assemble the lower triangle; padding rows/columns: identity
-    for (int e = tid; e < nblk * 256; e += SV_THREADS) {
-        const int blk = e >> 8, r = (e >> 4) & 15, c = e & 15;
-        int bi = (int)((sqrtf(8.f * blk + 1.f) - 1.f) * 0.5f);
-        while (bi * (bi + 1) / 2 > blk) bi--;
-        while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
-        const int bj = blk - bi * (bi + 1) / 2;
-        const int i = bi * SV_NB + r, j = bj * SV_NB + c;
-        double v = 0.0;
-        if (i < k && j < k && j <= i) v = a.HH[(size_t)i * k + j] + a.alpha * (double)G[(size_t)i * WS_KP + j] + (i == j ? a.reg : 0.0);
-        else if (i == j) v = 1.0;
-        L[(size_t)blk * SV_BLK + r * SV_LD + c] = v;
+    // ---- assemble the lower triangle; padding rows/columns: identity. One 16 x 16 block per step (256 threads = its
+    //      256 entries), block indices advanced incrementally; loads of four blocks are in flight at a time.
+    {
+        const int r = tid >> 4, c = tid & 15;
+        int bi = 0, bj = 0;
+#pragma unroll 4
+        for (int blk = 0; blk < nblk; blk++) {
+            const int i = bi * SV_NB + r, j = bj * SV_NB + c;
+            double v = 0.0;
+            if (i < k && j < k && j <= i) v = a.HH[(size_t)i * k + j] + a.alpha * (double)G[(size_t)i * WS_KP + j] + (i == j ? a.reg : 0.0);
+            else if (i == j) v = 1.0;
+            L[(size_t)blk * SV_BLK + r * SV_LD + c] = v;
+            if (++bj > bi) { bi++; bj = 0; }
+        }
     }
     for (int f = tid; f < kp; f += SV_THREADS) {
         const double bb = f < k ? a.bsum[(size_t)blockIdx.x * WS_KP + f] * (1.0 + a.alpha) : 0.0;
@@ -374,22 +376,29 @@ __global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveAr
 #pragma unroll
             for (int c = 0; c < SV_NB; c++) {
                 const double dcc = __shfl_sync(0xffffffffu, rr[c], c);
-                const double rd = rsqrt(dcc);         // 1 / L[c][c]
-                const double lc = rr[c] * rd;          // L[row][c] for row >= c (row == c: sqrt(dcc))
+                // 1 / sqrt(dcc): single-precision seed, two Newton steps in double (2^-22 -> 2^-43 -> full precision)
+                double rd = (double)rsqrtf((float)dcc);
+                rd = rd * fma(-0.5 * dcc, rd * rd, 1.5);
+                rd = rd * fma(-0.5 * dcc, rd * rd, 1.5);
+                const double lc = rr[c] * rd;         // L[row][c] for row >= c (row == c: sqrt(dcc))
                 rr[c] = lc;
                 if (lane == c) rdiag[j0 + c] = rd;
 #pragma unroll
                 for (int c2 = c + 1; c2 < SV_NB; c2++) {
                     const double l2 = __shfl_sync(0xffffffffu, lc, c2);
-                    if (row >= c2) rr[c2] -= lc * l2;
+                    rr[c2] = fma(-lc, (row >= c2) ? l2 : 0.0, rr[c2]);
                 }
             }
             if (lane < SV_NB) {
 #pragma unroll
                 for (int c = 0; c < SV_NB; c++) if (c <= row) D[row * SV_LD + c] = rr[c];
             }
-            __syncwarp();
-            // explicit inverse of the diagonal block: lane c solves L11 x = e_c (column c of L11^-1)
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // explicit inverse of the diagonal block for the triangular solves (not needed by the factorisation itself, so
+            // it runs beside the panel): lane c solves L11 x = e_c (column c of L11^-1)
+            const double* D = sv_blk(L, p, p);
             double* Di = Dinv + (size_t)p * SV_BLK;
             if (lane < SV_NB) {
                 double x[SV_NB];
@@ -403,22 +412,18 @@ __global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveAr
 #pragma unroll
                 for (int r = 0; r < SV_NB; r++) Di[r * SV_LD + lane] = x[r];
             }
-        }
-        __syncthreads();
-        // panel below the diagonal block: X = A21 L11^-T, i.e. X[i][c] = sum_{t <= c} A21[i][t] Dinv[c][t]; one thread per row
-        {
-            const double* Di = Dinv + (size_t)p * SV_BLK;
-            for (int i = j0 + SV_NB + tid; i < kp; i += SV_THREADS) {
+        } else {
+            // panel below the diagonal block: X L11^T = A21 by substitution, one thread of warps 1..7 per row
+            const double* D = sv_blk(L, p, p);
+            for (int i = j0 + SV_NB + (tid - 32); i < kp; i += SV_THREADS - 32) {
                 double* Ai = sv_blk(L, i / SV_NB, p) + (i % SV_NB) * SV_LD;
-                double ar[SV_NB], x[SV_NB];
-#pragma unroll
-                for (int t = 0; t < SV_NB; t++) ar[t] = Ai[t];
+                double x[SV_NB];
 #pragma unroll
                 for (int c = 0; c < SV_NB; c++) {
-                    double sacc = 0.0;
+                    double sacc = Ai[c];
 #pragma unroll
-                    for (int t = 0; t <= c; t++) sacc += ar[t] * Di[c * SV_LD + t];
-                    x[c] = sacc;
+                    for (int t = 0; t < c; t++) sacc -= x[t] * D[c * SV_LD + t];
+                    x[c] = sacc * rdiag[j0 + c];
                 }
 #pragma unroll
                 for (int c = 0; c < SV_NB; c++) Ai[c] = x[c];
