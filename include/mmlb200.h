@@ -251,9 +251,11 @@ int32_t mml_wrmf_stats(mml_wrmf* m, int64_t* kernel_launches, float* last_iterat
  * every rank holds the whole model after mml_wrmf_iterate. ranges receives world + 1 entries. */
 int32_t mml_wrmf_shard(mml_wrmf* m, int32_t by_item, int32_t* ranges);
 /* Engine knob: AUTO = per-row Gram sums sum_{i in S_u} h_i h_i^T on the tcgen05 tensor cores (3 x TF32 split, fp32-accurate)
- * with HH, the assembly and the blocked Cholesky solve in double (num_factors a multiple of 4, <= 128), the all-double
- * CUDA-core kernels otherwise; FP64 / TENSOR force one of them. */
-enum { MML_WRMF_AUTO = 0, MML_WRMF_FP64 = 1, MML_WRMF_TENSOR = 2 };
+ * with HH and the assembly in double, a blocked Cholesky factor in single precision used as the preconditioner of an
+ * iterative refinement against the exact double-precision operator (num_factors a multiple of 4, <= 128; a half-sweep
+ * with a row that does not converge is repeated with the double-precision factor), the all-double CUDA-core kernels
+ * otherwise; FP64 / TENSOR force one of them, TENSOR_F64 = TENSOR with the double-precision factor. */
+enum { MML_WRMF_AUTO = 0, MML_WRMF_FP64 = 1, MML_WRMF_TENSOR = 2, MML_WRMF_TENSOR_F64 = 3 };
 int32_t mml_wrmf_set_mode(int32_t mode);
 /* Diagnostic for the parity tests: the tensor-core Gram sum (128 x 128 floats, zero beyond num_factors) of the user with
  * the most events, and that user's id. The model is not modified. */

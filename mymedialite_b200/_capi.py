@@ -117,7 +117,7 @@ SIGNATURES = {
 }
 
 TOPN_AUTO, TOPN_EXACT, TOPN_TENSOR = 0, 1, 2
-WRMF_AUTO, WRMF_FP64, WRMF_TENSOR = 0, 1, 2
+WRMF_AUTO, WRMF_FP64, WRMF_TENSOR, WRMF_TENSOR_F64 = 0, 1, 2, 3
 
 _lib = None
 

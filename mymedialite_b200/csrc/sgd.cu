@@ -40,7 +40,8 @@ namespace mml {
 // host: group maps
 // =================================================================================================
 // Deals ids to n_blocks * G * W groups and numbers them group-major.
-//   level 0 (GPU block)  : perm[id] % R          (the reference rule, MultiCore.cs:64)
+//   level 0 (GPU block)  : perm[id] % R          (the reference rule, MultiCore.cs:64; users always: the host shards
+//                          the ratings by it) -- items under the BALANCED rule: balanced like the levels below
 //   level 1/2, PERM_MOD  : (perm[id] / R) % (G*W) -> g = x % G, w = x / G
 //   level 1/2, BALANCED  : ids of a block in descending rating count, each to the lightest group so far
 // Hot ids (items only, hot_min > 0): an id with at least hot_min ratings would serialise its whole
@@ -60,11 +61,28 @@ static void build_group_map(GroupMap& m, int32_t n_ext, const uint32_t* counts, 
     m.grp.assign(n_ext, -1);
     if (hot_cnt) hot_cnt->assign((size_t)m.n_blocks * G, 0);
     std::vector<std::vector<int32_t>> by_block(m.n_blocks);
-    for (int32_t id = 0; id < n_ext; id++) {
-        const int32_t pid = perm ? perm[id] : id;
-        const int32_t blk = pid % R;
-        if (only_block >= 0 && blk != only_block) continue;
-        by_block[only_block >= 0 ? 0 : blk].push_back(id);
+    if (only_block < 0 && R > 1 && rule == MML_GROUPS_BALANCED) {
+        // Items under the BALANCED rule: the GPU-level blocks are balanced too -- ids in descending rating count, each to
+        // the lightest block so far, so the R hottest items land in R different blocks. A ring step lasts as long as its
+        // slowest rank, and a block's time grows with the popularity of its hottest rows (their atomics queue up at the L2),
+        // so blocks of equal size AND equal hotness keep the ranks in step. Every rank computes the same map (global counts).
+        std::vector<int32_t> ids(n_ext);
+        std::iota(ids.begin(), ids.end(), 0);
+        std::stable_sort(ids.begin(), ids.end(), [&](int32_t a, int32_t b) { return counts[a] > counts[b]; });
+        std::vector<int64_t> bload(R, 0);
+        for (int32_t id : ids) {
+            int32_t best = 0;
+            for (int32_t b = 1; b < R; b++) if (bload[b] < bload[best]) best = b;
+            bload[best] += std::max<uint32_t>(counts[id], 1u);
+            by_block[best].push_back(id);
+        }
+    } else {
+        for (int32_t id = 0; id < n_ext; id++) {
+            const int32_t pid = perm ? perm[id] : id;
+            const int32_t blk = pid % R;
+            if (only_block >= 0 && blk != only_block) continue;
+            by_block[only_block >= 0 ? 0 : blk].push_back(id);
+        }
     }
     for (int32_t bi = 0; bi < m.n_blocks; bi++) {
         auto& ids = by_block[bi];
@@ -1111,27 +1129,64 @@ struct PredArgs {
     float gb, minr, maxr, range;
 };
 
-// BiasedMatrixFactorization.cs:313-325 / MatrixFactorization.cs:205-217,251-259 -- one warp per pair
-__device__ __forceinline__ float predict_pair(const PredArgs& a, int32_t u, int32_t i, int lane)
+// BiasedMatrixFactorization.cs:313-325 / MatrixFactorization.cs:205-217,251-259.
+// A warp takes 32 pairs at a time: the ids are read coalesced (lane = pair), the 32 dot products are formed by the
+// whole warp four pairs at a time (8 independent row loads in flight per lane; per pair: lane-partial sums over
+// f = lane, lane + 32, ... then a butterfly), and the scalar part -- the double-precision link, clipping and, in
+// evaluate_kernel, the logarithms of the measures -- runs once per pair on the pair's own lane instead of 32 times.
+struct PairDots {
+    int32_t urow, irow;     // internal rows of this lane's pair or -1 (unknown id)
+    float dot;              // p_u . q_i of this lane's pair (0 unless both rows are known)
+};
+
+__device__ __forceinline__ PairDots pair_dots(const PredArgs& a, const int32_t* __restrict__ users,
+                                              const int32_t* __restrict__ items, int64_t base, int64_t n, int lane)
 {
-    const bool ku = u >= 0 && u < a.n_users_ext && a.user_int[u] >= 0;
-    const bool ki = i >= 0 && i < a.n_items_ext && a.item_int[i] >= 0;
-    float dot = 0.f;
-    if (ku && ki) {
-        const float* prow = a.P + (size_t)a.user_int[u] * a.kp;
-        const float* qrow = a.Q + (size_t)a.item_int[i] * a.kp;
-        for (int f = lane; f < a.kp; f += 32) dot = fmaf(prow[f], qrow[f], dot);
-        dot = warp_sum(dot);
+    PairDots r;
+    r.urow = -1; r.irow = -1; r.dot = 0.f;
+    if (base + lane < n) {
+        const int32_t u = users[base + lane], i = items[base + lane];
+        if (u >= 0 && u < a.n_users_ext) r.urow = a.user_int[u];
+        if (i >= 0 && i < a.n_items_ext) r.irow = a.item_int[i];
     }
+    const int cnt = (int)min((int64_t)32, n - base);
+    for (int j0 = 0; j0 < cnt; j0 += 4) {
+        const float* pr[4]; const float* qr[4]; bool ok[4];
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            const int32_t ur = __shfl_sync(0xffffffffu, r.urow, (j0 + x) & 31), ir = __shfl_sync(0xffffffffu, r.irow, (j0 + x) & 31);
+            ok[x] = j0 + x < cnt && ur >= 0 && ir >= 0;
+            pr[x] = a.P + (size_t)(ok[x] ? ur : 0) * a.kp;
+            qr[x] = a.Q + (size_t)(ok[x] ? ir : 0) * a.kp;
+        }
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int f = lane; f < a.kp; f += 32) {
+#pragma unroll
+            for (int x = 0; x < 4; x++) d[x] = fmaf(pr[x][f], qr[x][f], d[x]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int x = 0; x < 4; x++) d[x] += __shfl_xor_sync(0xffffffffu, d[x], o);
+        }
+#pragma unroll
+        for (int x = 0; x < 4; x++) if (lane == j0 + x && ok[x]) r.dot = d[x];
+    }
+    return r;
+}
+
+__device__ __forceinline__ float predict_from_dot(const PredArgs& a, const PairDots& r)
+{
+    const bool ku = r.urow >= 0, ki = r.irow >= 0;
     if (a.biased) {
         double score = a.gb;
-        if (ku) score += a.bu[a.user_int[u]];
-        if (ki) score += a.bi[a.item_int[i]];
-        if (ku && ki) score += dot;
+        if (ku) score += a.bu[r.urow];
+        if (ki) score += a.bi[r.irow];
+        if (ku && ki) score += r.dot;
         return (float)((double)a.minr + (1.0 / (1.0 + exp(-score))) * (double)a.range);
     }
     if (!ku || !ki) return a.gb;
-    float res = a.gb + dot;
+    float res = a.gb + r.dot;
     if (res > a.maxr) res = a.maxr;
     if (res < a.minr) res = a.minr;
     return res;
@@ -1141,11 +1196,11 @@ __global__ void predict_kernel(const PredArgs a, const int32_t* __restrict__ use
                                int64_t n, float* __restrict__ out)
 {
     const int lane = threadIdx.x & 31;
-    int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (; t < n; t += stride) {
-        const float pr = predict_pair(a, users[t], items[t], lane);
-        if (lane == 0) out[t] = pr;
+    int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+    const int64_t stride = (((int64_t)gridDim.x * blockDim.x) >> 5) * 32;
+    for (; base < n; base += stride) {
+        const PairDots r = pair_dots(a, users, items, base, n, lane);
+        if (base + lane < n) out[base + lane] = predict_from_dot(a, r);
     }
 }
 
@@ -1157,11 +1212,13 @@ __global__ void evaluate_kernel(const PredArgs a, const int32_t* __restrict__ us
     __shared__ double sh[EV_THREADS / 32][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (; t < n; t += stride) {
-        const float pr = predict_pair(a, users[t], items[t], lane);
-        const float r = values[t];
+    int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+    const int64_t stride = (((int64_t)gridDim.x * blockDim.x) >> 5) * 32;
+    for (; base < n; base += stride) {
+        const PairDots pd = pair_dots(a, users, items, base, n, lane);
+        if (base + lane >= n) continue;
+        const float pr = predict_from_dot(a, pd);
+        const float r = values[base + lane];
         const float err = __fsub_rn(pr, r);
         s0 += (double)__fmul_rn(err, err);
         s1 += (double)fabsf(err);
@@ -1176,6 +1233,12 @@ __global__ void evaluate_kernel(const PredArgs a, const int32_t* __restrict__ us
             s3 -= an * log(pl);
             s3 -= (1.0 - an) * log(1.0 - pl);
         }
+    }
+    // lanes hold their own pairs' sums: butterfly over the warp, then over the block's warps in a fixed order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
     }
     if (lane == 0) { sh[warp][0] = s0; sh[warp][1] = s1; sh[warp][2] = s2; sh[warp][3] = s3; }
     __syncthreads();
@@ -1548,12 +1611,12 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
         if (p->schedule == MML_SCHEDULE_DSGD) {
             // async mode: a worker group may be several CTAs (ctas_per_group) sharing the group's blocks
             // Default (both 0): groups of 4 CTAs, SMs / 4 groups -- on the measured shapes within 5 % of the best grid
-            // (37 x 4 on 148 SMs: config 4 16.7 ms vs 19.7 ms with 148 x 1); 18 x 8 when the
-            // item matrix is split over several GPUs (one GPU-level sub-epoch of config 4 at 8 GPUs: 2.80 vs 2.91 ms).
+            // (37 x 4 on 148 SMs: config 4 16.7 ms vs 19.7 ms with 148 x 1), also under the
+            // 8-GPU ring (30.8 ms per epoch against 31.3 ms with 18 x 8).
             m.cpg = 1;
             if (p->intra_block == MML_INTRA_ASYNC) {
                 if (p->ctas_per_group > 0) m.cpg = std::min(p->ctas_per_group, ctx->sm_count);
-                else if (p->num_groups <= 0 && ctx->sm_count >= 16) m.cpg = m.R > 1 ? 8 : 4;   // multi-GPU: a launch sees 1/R of the items
+                else if (p->num_groups <= 0 && ctx->sm_count >= 16) m.cpg = 4;
             }
             int32_t G = p->num_groups > 0 ? p->num_groups : ctx->sm_count / m.cpg;
             G = std::min(G, std::min(r->n_users(), r->n_items()));

@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <new>
 
 namespace mml {
@@ -241,19 +243,26 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wrmf_syrk_kernel(const SyrkArgs
 }
 
 // ---- assembly + blocked Cholesky solve + iterative refinement, one CTA per row --------------------------------------
-// A_u is held as its lower triangle in 16 x 16 blocks (rows padded to 17 doubles: conflict-free row and column access),
-// block (bi, bj), bj <= bi, at index bi (bi + 1) / 2 + bj: 78 KB at k = 128, so two rows are in flight per SM.
+// A_u is held as its lower triangle in 16 x 16 blocks (rows padded to 17 elements: conflict-free row and column access),
+// block (bi, bj), bj <= bi, at index bi (bi + 1) / 2 + bj.
 //   1. A~ = HH + alpha G~ + lambda I with the tensor cores' fp32-accurate G~;   A~ = L L^T (right-looking, 16-wide panels)
 //   2. w = L^-T L^-1 b
 //   3. refinement: r = b - A w with A applied EXACTLY in double straight from the factor rows
 //      (A w = HH w + lambda w + alpha sum_i h_i (h_i . w): 2 k flops per entry instead of k^2), w += L^-T L^-1 r,
-//      until |r| <= 1e-10 |b| (at most SV_MAX_REFINE steps). The fp32 rounding of G~ therefore only slows convergence;
-//      the solution is the double-precision one as long as cond(A) * 1e-6 < 1.
+//      until |r| <= 1e-9 |b|. The factor is therefore only a preconditioner: its rounding -- and that of G~ -- slows the
+//      convergence but does not enter the result, which is the double-precision solution.
+// T = float (default): the factor, its block inverses and the triangular solves are single precision -- 39 KB for the
+// factor at k = 128, three rows in flight per SM, one shuffle per exchanged value, hardware rsqrt; on WRMF systems
+// (cond(A) ~ 10..100, lambda I keeps them far from singular) it converges in the same two residual evaluations as the
+// double factor. A row that has not converged after SV_MAX_REFINE<T> steps raises *fail and the host repeats the
+// half-sweep with T = double (78 KB, two rows per SM).
 constexpr int SV_THREADS = 256;
 constexpr int SV_NB = 16;
 constexpr int SV_LD = 17;
 constexpr int SV_BLK = SV_NB * SV_LD;
-constexpr int SV_MAX_REFINE = 3;
+template <typename T> struct SvCfg;
+template <> struct SvCfg<double> { static constexpr int max_refine = 3; static constexpr int ctas = 2; };
+template <> struct SvCfg<float> { static constexpr int max_refine = 8; static constexpr int ctas = 3; };
 
 struct SolveArgs {
     const uint32_t* row_ptr; const int32_t* cols; const int32_t* order; int32_t q_lo, q_hi;
@@ -262,31 +271,46 @@ struct SolveArgs {
     double alpha, reg;
     int32_t k;
     float* W;                                               // [*, k] the factor matrix being solved
+    uint32_t* fail;                                         // rows whose refinement did not converge
 };
 
-__device__ __forceinline__ double* sv_blk(double* L, int bi, int bj) { return L + (size_t)(bi * (bi + 1) / 2 + bj) * SV_BLK; }
+template <typename T>
+__device__ __forceinline__ T* sv_blk(T* L, int bi, int bj) { return L + (size_t)(bi * (bi + 1) / 2 + bj) * SV_BLK; }
+
+__device__ __forceinline__ double sv_rsqrt(double d)
+{   // single-precision seed, two Newton steps in double (2^-22 -> 2^-43 -> full precision)
+    double rd = (double)rsqrtf((float)d);
+    rd = rd * fma(-0.5 * d, rd * rd, 1.5);
+    return rd * fma(-0.5 * d, rd * rd, 1.5);
+}
+__device__ __forceinline__ float sv_rsqrt(float d)
+{
+    const float rd = rsqrtf(d);
+    return rd * fmaf(-0.5f * d, rd * rd, 1.5f);
+}
 
 // Triangular solves with the blocked factor. The 16 x 16 diagonal blocks are applied through their explicit inverses
 // Dinv[p] = L(p,p)^-1 (computed once per factorisation), so a panel step is a small matrix-vector product instead of a
 // 16-step dependent chain: 2 barriers per panel.
 // x <- L^-1 x (forward) for the vector x[0 .. kp); all threads of the CTA call it
-__device__ __forceinline__ void sv_forward(double* L, const double* Dinv, double* x, int np)
+template <typename T>
+__device__ __forceinline__ void sv_forward(T* L, const T* Dinv, T* x, int np)
 {
     const int tid = threadIdx.x;
     for (int p = 0; p < np; p++) {
         const int j0 = p * SV_NB;
-        double y = 0.0;
+        T y = 0;
         if (tid < SV_NB) {
-            const double* D = Dinv + (size_t)p * SV_BLK + tid * SV_LD;
+            const T* D = Dinv + (size_t)p * SV_BLK + tid * SV_LD;
 #pragma unroll
-            for (int t = 0; t < SV_NB; t++) y += (t <= tid) ? D[t] * x[j0 + t] : 0.0;
+            for (int t = 0; t < SV_NB; t++) y += (t <= tid) ? D[t] * x[j0 + t] : (T)0;
         }
         if (tid < 32) __syncwarp();
         if (tid < SV_NB) x[j0 + tid] = y;
         __syncthreads();
         for (int i = j0 + SV_NB + tid; i < np * SV_NB; i += SV_THREADS) {
-            const double* B = sv_blk(L, i / SV_NB, p) + (i % SV_NB) * SV_LD;
-            double s = 0.0;
+            const T* B = sv_blk(L, i / SV_NB, p) + (i % SV_NB) * SV_LD;
+            T s = 0;
 #pragma unroll
             for (int t = 0; t < SV_NB; t++) s += B[t] * x[j0 + t];
             x[i] -= s;
@@ -296,23 +320,24 @@ __device__ __forceinline__ void sv_forward(double* L, const double* Dinv, double
 }
 
 // x <- L^-T x (backward)
-__device__ __forceinline__ void sv_backward(double* L, const double* Dinv, double* x, int np)
+template <typename T>
+__device__ __forceinline__ void sv_backward(T* L, const T* Dinv, T* x, int np)
 {
     const int tid = threadIdx.x;
     for (int p = np - 1; p >= 0; p--) {
         const int j0 = p * SV_NB;
-        double y = 0.0;
+        T y = 0;
         if (tid < SV_NB) {
-            const double* D = Dinv + (size_t)p * SV_BLK + tid;
+            const T* D = Dinv + (size_t)p * SV_BLK + tid;
 #pragma unroll
-            for (int t = 0; t < SV_NB; t++) y += (t >= tid) ? D[t * SV_LD] * x[j0 + t] : 0.0;
+            for (int t = 0; t < SV_NB; t++) y += (t >= tid) ? D[t * SV_LD] * x[j0 + t] : (T)0;
         }
         if (tid < 32) __syncwarp();
         if (tid < SV_NB) x[j0 + tid] = y;
         __syncthreads();
         for (int j = tid; j < j0; j += SV_THREADS) {
-            const double* B = sv_blk(L, p, j / SV_NB) + (j % SV_NB);
-            double s = 0.0;
+            const T* B = sv_blk(L, p, j / SV_NB) + (j % SV_NB);
+            T s = 0;
 #pragma unroll
             for (int t = 0; t < SV_NB; t++) s += B[t * SV_LD] * x[j0 + t];
             x[j] -= s;
@@ -321,7 +346,16 @@ __device__ __forceinline__ void sv_backward(double* L, const double* Dinv, doubl
     }
 }
 
-__global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveArgs a)
+// shared memory of one row: doubles first (alignment), then the T-typed factor
+template <typename T>
+__host__ __device__ inline size_t sv_smem_bytes(int np)
+{
+    const size_t kp = (size_t)np * SV_NB, nblk = (size_t)np * (np + 1) / 2;
+    return sizeof(double) * kp * (3 + SV_THREADS / 32) + sizeof(T) * (nblk * SV_BLK + (size_t)np * SV_BLK + 2 * kp);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SV_THREADS, SvCfg<T>::ctas) wrmf_solve_kernel(const SolveArgs a)
 {
     extern __shared__ double sv_smem[];
     const int k = a.k, np = (k + SV_NB - 1) / SV_NB, kp = np * SV_NB;
@@ -335,17 +369,18 @@ __global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveAr
         return;
     }
     const int nblk = np * (np + 1) / 2;
-    double* L = sv_smem;                              // [nblk][16][17]
-    double* b0 = L + (size_t)nblk * SV_BLK;           // [kp] right-hand side
+    double* b0 = sv_smem;                             // [kp] right-hand side
     double* wv = b0 + kp;                             // [kp] solution
-    double* rv = wv + kp;                             // [kp] residual / correction
-    double* rdiag = rv + kp;                          // [kp] 1 / L[i][i]
-    double* red = rdiag + kp;                         // [8][kp] per-warp partial sums of the refinement gather
-    double* Dinv = red + (size_t)(SV_THREADS / 32) * kp;   // [np][16][17] inverses of the diagonal blocks
+    double* rv = wv + kp;                             // [kp] residual
+    double* red = rv + kp;                            // [8][kp] per-warp partial sums of the refinement gather
+    T* L = reinterpret_cast<T*>(red + (size_t)(SV_THREADS / 32) * kp);   // [nblk][16][17]
+    T* Dinv = L + (size_t)nblk * SV_BLK;              // [np][16][17] inverses of the diagonal blocks
+    T* rdiag = Dinv + (size_t)np * SV_BLK;            // [kp] 1 / L[i][i]
+    T* xs = rdiag + kp;                               // [kp] right-hand side / solution of a triangular solve
     __shared__ double s_norm[2];
     const float* G = a.G + (size_t)blockIdx.x * WS_KP * WS_KP;
-    // ---- assemble the lower triangle; padding rows/columns: identity. One 16 x 16 block per step (256 threads = its
-    //      256 entries), block indices advanced incrementally; loads of four blocks are in flight at a time.
+    // ---- assemble the lower triangle (in double, rounded to T); padding rows/columns: identity. One 16 x 16 block per
+    //      step (256 threads = its 256 entries), block indices advanced incrementally; four blocks' loads in flight.
     {
         const int r = tid >> 4, c = tid & 15;
         int bi = 0, bj = 0;
@@ -355,38 +390,35 @@ __global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveAr
             double v = 0.0;
             if (i < k && j < k && j <= i) v = a.HH[(size_t)i * k + j] + a.alpha * (double)G[(size_t)i * WS_KP + j] + (i == j ? a.reg : 0.0);
             else if (i == j) v = 1.0;
-            L[(size_t)blk * SV_BLK + r * SV_LD + c] = v;
+            L[(size_t)blk * SV_BLK + r * SV_LD + c] = (T)v;
             if (++bj > bi) { bi++; bj = 0; }
         }
     }
     for (int f = tid; f < kp; f += SV_THREADS) {
         const double bb = f < k ? a.bsum[(size_t)blockIdx.x * WS_KP + f] * (1.0 + a.alpha) : 0.0;
-        b0[f] = bb; wv[f] = bb;
+        b0[f] = bb; xs[f] = (T)bb;
     }
     __syncthreads();
     // ---- blocked right-looking Cholesky
     for (int p = 0; p < np; p++) {
         const int j0 = p * SV_NB;
         if (warp == 0) {                              // diagonal block in registers: lane l owns row l
-            double* D = sv_blk(L, p, p);
+            T* D = sv_blk(L, p, p);
             const int row = lane & (SV_NB - 1);       // lanes 16..31 mirror 0..15 (their results are discarded)
-            double rr[SV_NB];
+            T rr[SV_NB];
 #pragma unroll
-            for (int c = 0; c < SV_NB; c++) rr[c] = (c <= row) ? D[row * SV_LD + c] : 0.0;
+            for (int c = 0; c < SV_NB; c++) rr[c] = (c <= row) ? D[row * SV_LD + c] : (T)0;
 #pragma unroll
             for (int c = 0; c < SV_NB; c++) {
-                const double dcc = __shfl_sync(0xffffffffu, rr[c], c);
-                // 1 / sqrt(dcc): single-precision seed, two Newton steps in double (2^-22 -> 2^-43 -> full precision)
-                double rd = (double)rsqrtf((float)dcc);
-                rd = rd * fma(-0.5 * dcc, rd * rd, 1.5);
-                rd = rd * fma(-0.5 * dcc, rd * rd, 1.5);
-                const double lc = rr[c] * rd;         // L[row][c] for row >= c (row == c: sqrt(dcc))
+                const T dcc = __shfl_sync(0xffffffffu, rr[c], c);
+                const T rd = sv_rsqrt(dcc);           // 1 / L[c][c]
+                const T lc = rr[c] * rd;              // L[row][c] for row >= c (row == c: sqrt(dcc))
                 rr[c] = lc;
                 if (lane == c) rdiag[j0 + c] = rd;
 #pragma unroll
                 for (int c2 = c + 1; c2 < SV_NB; c2++) {
-                    const double l2 = __shfl_sync(0xffffffffu, lc, c2);
-                    rr[c2] = fma(-lc, (row >= c2) ? l2 : 0.0, rr[c2]);
+                    const T l2 = __shfl_sync(0xffffffffu, lc, c2);
+                    rr[c2] -= lc * ((row >= c2) ? l2 : (T)0);
                 }
             }
             if (lane < SV_NB) {
@@ -398,29 +430,29 @@ __global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveAr
         if (warp == 0) {
             // explicit inverse of the diagonal block for the triangular solves (not needed by the factorisation itself, so
             // it runs beside the panel): lane c solves L11 x = e_c (column c of L11^-1)
-            const double* D = sv_blk(L, p, p);
-            double* Di = Dinv + (size_t)p * SV_BLK;
+            const T* D = sv_blk(L, p, p);
+            T* Di = Dinv + (size_t)p * SV_BLK;
             if (lane < SV_NB) {
-                double x[SV_NB];
+                T x[SV_NB];
 #pragma unroll
                 for (int r = 0; r < SV_NB; r++) {
-                    double sacc = (r == lane) ? 1.0 : 0.0;
+                    T sacc = (r == lane) ? (T)1 : (T)0;
 #pragma unroll
                     for (int t = 0; t < r; t++) sacc -= D[r * SV_LD + t] * x[t];
-                    x[r] = (r >= lane) ? sacc * rdiag[j0 + r] : 0.0;
+                    x[r] = (r >= lane) ? sacc * rdiag[j0 + r] : (T)0;
                 }
 #pragma unroll
                 for (int r = 0; r < SV_NB; r++) Di[r * SV_LD + lane] = x[r];
             }
         } else {
             // panel below the diagonal block: X L11^T = A21 by substitution, one thread of warps 1..7 per row
-            const double* D = sv_blk(L, p, p);
+            const T* D = sv_blk(L, p, p);
             for (int i = j0 + SV_NB + (tid - 32); i < kp; i += SV_THREADS - 32) {
-                double* Ai = sv_blk(L, i / SV_NB, p) + (i % SV_NB) * SV_LD;
-                double x[SV_NB];
+                T* Ai = sv_blk(L, i / SV_NB, p) + (i % SV_NB) * SV_LD;
+                T x[SV_NB];
 #pragma unroll
                 for (int c = 0; c < SV_NB; c++) {
-                    double sacc = Ai[c];
+                    T sacc = Ai[c];
 #pragma unroll
                     for (int t = 0; t < c; t++) sacc -= x[t] * D[c * SV_LD + t];
                     x[c] = sacc * rdiag[j0 + c];
@@ -440,16 +472,16 @@ __global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveAr
             while ((xi + 1) * (xi + 2) / 2 <= pair) xi++;
             const int xj = pair - xi * (xi + 1) / 2;
             const int bi = p + 1 + xi, bj = p + 1 + xj;
-            const double* Ra = sv_blk(L, bi, p) + (4 * tx) * SV_LD;
-            const double* Cb = sv_blk(L, bj, p) + (4 * ty) * SV_LD;
-            double acc[4][4];
+            const T* Ra = sv_blk(L, bi, p) + (4 * tx) * SV_LD;
+            const T* Cb = sv_blk(L, bj, p) + (4 * ty) * SV_LD;
+            T acc[4][4];
 #pragma unroll
             for (int x = 0; x < 4; x++)
 #pragma unroll
-                for (int y = 0; y < 4; y++) acc[x][y] = 0.0;
+                for (int y = 0; y < 4; y++) acc[x][y] = 0;
 #pragma unroll 4
             for (int sidx = 0; sidx < SV_NB; sidx++) {
-                double ra[4], cb[4];
+                T ra[4], cb[4];
 #pragma unroll
                 for (int x = 0; x < 4; x++) { ra[x] = Ra[x * SV_LD + sidx]; cb[x] = Cb[x * SV_LD + sidx]; }
 #pragma unroll
@@ -457,7 +489,7 @@ __global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveAr
 #pragma unroll
                     for (int y = 0; y < 4; y++) acc[x][y] += ra[x] * cb[y];
             }
-            double* C = sv_blk(L, bi, bj) + (4 * tx) * SV_LD + 4 * ty;
+            T* C = sv_blk(L, bi, bj) + (4 * tx) * SV_LD + 4 * ty;
 #pragma unroll
             for (int x = 0; x < 4; x++)
 #pragma unroll
@@ -466,10 +498,13 @@ __global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveAr
         __syncthreads();
     }
     // ---- w = L^-T L^-1 b
-    sv_forward(L, Dinv, wv, np);
-    sv_backward(L, Dinv, wv, np);
+    sv_forward(L, Dinv, xs, np);
+    sv_backward(L, Dinv, xs, np);
+    for (int f = tid; f < kp; f += SV_THREADS) wv[f] = (double)xs[f];
+    __syncthreads();
     // ---- refinement against the exact operator
-    for (int iter = 0; iter < SV_MAX_REFINE; iter++) {
+    bool converged = false;
+    for (int iter = 0; iter <= SvCfg<T>::max_refine; iter++) {
         // r = b - HH w - lambda w   (HH is symmetric: column reads are coalesced)
         for (int f = tid; f < kp; f += SV_THREADS) {
             double sacc = 0.0;
@@ -517,12 +552,16 @@ __global__ void __launch_bounds__(SV_THREADS, 2) wrmf_solve_kernel(const SolveAr
             atomicMax(reinterpret_cast<unsigned long long*>(&s_norm[1]), (unsigned long long)__double_as_longlong(bmax));
         }
         __syncthreads();
-        if (!(s_norm[0] > 1e-9 * s_norm[1])) break;            // converged (uniform across the CTA)
-        sv_forward(L, Dinv, rv, np);
-        sv_backward(L, Dinv, rv, np);
-        for (int f = tid; f < k; f += SV_THREADS) wv[f] += rv[f];
+        if (!(s_norm[0] > 1e-9 * s_norm[1])) { converged = true; break; }   // uniform across the CTA
+        if (iter == SvCfg<T>::max_refine) break;
+        for (int f = tid; f < kp; f += SV_THREADS) xs[f] = (T)rv[f];
+        __syncthreads();
+        sv_forward(L, Dinv, xs, np);
+        sv_backward(L, Dinv, xs, np);
+        for (int f = tid; f < k; f += SV_THREADS) wv[f] += (double)xs[f];
         __syncthreads();
     }
+    if (!converged && tid == 0) atomicAdd(a.fail, 1u);
     for (int f = tid; f < k; f += SV_THREADS) a.W[(size_t)u * k + f] = (float)wv[f];
 }
 
@@ -537,9 +576,9 @@ WrmfTcWork* wrmf_tc_work_create() { return new (std::nothrow) WrmfTcWork(); }
 void wrmf_tc_work_destroy(WrmfTcWork* w) { delete w; }
 
 // One half-sweep's per-row systems: W[u] <- solve for every row of `order`. HH (fp64, k x k) is on the device.
-int32_t wrmf_tc_half_sweep(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_ptr, const int32_t* cols, const int32_t* order, int32_t n_rows,
-                           float* W, const float* H, int32_t k, const double* HH, double alpha, double reg, int64_t* launches,
-                           float* debug_G_row0)
+static int32_t half_sweep_impl(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_ptr, const int32_t* cols, const int32_t* order, int32_t n_rows,
+                               float* W, const float* H, int32_t k, const double* HH, double alpha, double reg, int64_t* launches,
+                               float* debug_G_row0, const bool f64, uint32_t* not_converged)
 {
     cudaStream_t s = ctx->stream;
     MML_CHECK(work != nullptr, MML_ERR_STATE, "wrmf: no tensor-path workspace");
@@ -548,15 +587,16 @@ int32_t wrmf_tc_half_sweep(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_ptr, 
     const int32_t cap = std::min(B, std::max(n_rows, 1));
     if (w.cap_rows < cap) {
         MML_TRY(w.G.alloc((size_t)cap * WS_KP * WS_KP)); MML_TRY(w.bsum.alloc((size_t)cap * WS_KP));
-        if (!w.err.p) MML_TRY(w.err.alloc(1));
+        if (!w.err.p) MML_TRY(w.err.alloc(2));
         w.cap_rows = cap;
     }
-    MML_CUDA(cudaMemsetAsync(w.err.p, 0, sizeof(uint32_t), s));
+    MML_CUDA(cudaMemsetAsync(w.err.p, 0, 2 * sizeof(uint32_t), s));
     const size_t smem_syrk = (size_t)WS_STAGES * 2 * WS_TILE + 1024;
     MML_CUDA(cudaFuncSetAttribute((const void*)wrmf_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_syrk));
-    const int np = (k + SV_NB - 1) / SV_NB, kp = np * SV_NB;
-    const size_t smem_solve = sizeof(double) * ((size_t)np * (np + 1) / 2 * SV_BLK + (size_t)kp * (4 + SV_THREADS / 32) + (size_t)np * SV_BLK);
-    MML_CUDA(cudaFuncSetAttribute((const void*)wrmf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+    const int np = (k + SV_NB - 1) / SV_NB;
+    const size_t smem_solve = f64 ? sv_smem_bytes<double>(np) : sv_smem_bytes<float>(np);
+    void (*solve_fn)(const SolveArgs) = f64 ? wrmf_solve_kernel<double> : wrmf_solve_kernel<float>;
+    MML_CUDA(cudaFuncSetAttribute((const void*)solve_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
     for (int32_t q_lo = 0; q_lo < n_rows; q_lo += B) {
         const int32_t q_hi = std::min(n_rows, q_lo + B), nb = q_hi - q_lo;
         MML_CUDA(cudaMemsetAsync(w.bsum.p, 0, sizeof(double) * (size_t)nb * WS_KP, s));
@@ -569,15 +609,36 @@ int32_t wrmf_tc_half_sweep(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_ptr, 
             MML_CUDA(cudaMemcpyAsync(debug_G_row0, w.G.p, sizeof(float) * WS_KP * WS_KP, cudaMemcpyDeviceToHost, s));
         SolveArgs va{};
         va.row_ptr = row_ptr; va.cols = cols; va.order = order; va.q_lo = q_lo; va.q_hi = q_hi; va.G = w.G.p; va.bsum = w.bsum.p; va.HH = HH;
-        va.H = H; va.alpha = alpha; va.reg = reg; va.k = k; va.W = W;
-        wrmf_solve_kernel<<<nb, SV_THREADS, smem_solve, s>>>(va);
+        va.H = H; va.alpha = alpha; va.reg = reg; va.k = k; va.W = W; va.fail = w.err.p + 1;
+        solve_fn<<<nb, SV_THREADS, smem_solve, s>>>(va);
         MML_CUDA(cudaGetLastError());
         if (launches) *launches += 2;
     }
-    uint32_t h_err = 0;
-    MML_CUDA(cudaMemcpyAsync(&h_err, w.err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    uint32_t h_err[2] = {0, 0};
+    MML_CUDA(cudaMemcpyAsync(h_err, w.err.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     MML_CUDA(cudaStreamSynchronize(s));
-    MML_CHECK(h_err == 0, MML_ERR_CUDA, "wrmf: tcgen05 pipeline timed out");
+    MML_CHECK(h_err[0] == 0, MML_ERR_CUDA, "wrmf: tcgen05 pipeline timed out");
+    *not_converged = h_err[1];
+    return MML_OK;
+}
+
+int32_t wrmf_tc_half_sweep(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_ptr, const int32_t* cols, const int32_t* order, int32_t n_rows,
+                           float* W, const float* H, int32_t k, const double* HH, double alpha, double reg, int64_t* launches,
+                           float* debug_G_row0, bool factor_f64)
+{
+    // factor_f64 (mode MML_WRMF_TENSOR_F64) or MMLB200_WRMF_FACTOR=fp64 forces the double-precision Cholesky factor (the
+    // default single-precision one is a preconditioner of the same double-precision refinement)
+    static const bool env64 = [] { const char* e = getenv("MMLB200_WRMF_FACTOR"); return e && strcmp(e, "fp64") == 0; }();
+    const bool force64 = env64 || factor_f64;
+    uint32_t bad = 0;
+    if (!force64) {
+        MML_TRY(half_sweep_impl(ctx, work, row_ptr, cols, order, n_rows, W, H, k, HH, alpha, reg, launches, debug_G_row0, false, &bad));
+        if (bad == 0) return MML_OK;
+        // some row's refinement did not converge with the single-precision factor (cond(A) beyond ~1e6): redo the
+        // half-sweep with the double-precision factor (W is output only and H is untouched, so a repeat is safe)
+    }
+    MML_TRY(half_sweep_impl(ctx, work, row_ptr, cols, order, n_rows, W, H, k, HH, alpha, reg, launches, debug_G_row0, true, &bad));
+    MML_CHECK(bad == 0, MML_ERR_CUDA, "wrmf: %u rows did not converge (system too ill-conditioned for the 1e-9 residual bound)", bad);
     return MML_OK;
 }
 

@@ -19,6 +19,22 @@ def shard_by_user(users, items, values, rank, world, user_perm=None):
     return users[idx], np.asarray(items)[idx], (None if values is None else np.asarray(values)[idx]), idx
 
 
+def balanced_row_ranges(row_ptr, world, row_cost):
+    """Host restatement of the library's WRMF row sharding (csrc/wrmf.cu shard_rows): contiguous row ranges whose cost
+    = events + row_cost per row is balanced; rank r solves rows [ranges[r], ranges[r + 1]) of a half-sweep."""
+    row_ptr = np.asarray(row_ptr, dtype=np.int64)
+    n = row_ptr.size - 1
+    cum = (row_ptr[1:] - row_ptr[0]) + row_cost * np.arange(1, n + 1, dtype=np.int64)
+    total = int(cum[-1]) if n else 0
+    ranges = np.full(world + 1, n, dtype=np.int32)
+    ranges[0] = 0
+    for r in range(1, world):
+        # first row count whose cumulative cost reaches r / world of the total
+        hit = np.flatnonzero(cum * world >= total * r)
+        ranges[r] = (int(hit[0]) + 1) if hit.size else n
+    return ranges
+
+
 def broadcast_bytes(buf, src=0):
     """Hands `buf` (uint8 array, valid on rank `src`) to every rank through torch.distributed; works with gloo and
     nccl process groups."""

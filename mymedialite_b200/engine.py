@@ -318,7 +318,8 @@ class DeviceFeedback:
 
 
 def wrmf_set_mode(mode):
-    """_capi.WRMF_AUTO (default) / WRMF_FP64 (all-double CUDA-core kernels) / WRMF_TENSOR (tcgen05 Gram sums or error)."""
+    """_capi.WRMF_AUTO (default) / WRMF_FP64 (all-double CUDA-core kernels) / WRMF_TENSOR (tcgen05 Gram sums or error) /
+    WRMF_TENSOR_F64 (the same with the double-precision Cholesky factor instead of the single-precision preconditioner)."""
     check(_capi.load().mml_wrmf_set_mode(int(mode)))
 
 

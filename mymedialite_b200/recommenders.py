@@ -260,12 +260,17 @@ class BiasedMatrixFactorization(MatrixFactorization):
     def _params(self):
         # MaxThreads > 1 selects the reference's DSGD block schedule (:178-184); on the GPU the worker groups are CTAs
         dsgd = self.MaxThreads > 1 or self.Schedule == "dsgd"
-        return engine.default_params(
+        shape = {}
+        if dsgd and self.NaiveParallelization:
+            # :136-141, :201-204: lock-free Parallel.For over index lists, no block exclusivity -> the whole GPU is one
+            # worker group (no hand-over); the library clamps ctas_per_group to the SM count
+            shape = dict(num_groups=1, ctas_per_group=1 << 16)
+        return engine.default_params(**shape, **dict(
             biased=1, num_factors=int(self.NumFactors), learn_rate=float(self.LearnRate), decay=float(self.Decay),
             regularization=float(self.Regularization), bias_learn_rate=float(self.BiasLearnRate), bias_reg=float(self.BiasReg),
             reg_u=float(self.RegU), reg_i=float(self.RegI), frequency_regularization=int(bool(self.FrequencyRegularization)),
             loss=self._LOSS[self.Loss], bold_driver=int(bool(self.BoldDriver)), max_threads=int(self.MaxThreads),
-            schedule=_capi.SCHEDULE_DSGD if dsgd else _capi.SCHEDULE_SERIAL)
+            schedule=_capi.SCHEDULE_DSGD if dsgd else _capi.SCHEDULE_SERIAL))
 
     def Iterate(self):
         if self.MaxThreads > 1 or self.Schedule == "dsgd":

@@ -35,8 +35,12 @@ def main():
         ru, ri = m.shard(False), m.shard(True)
         assert ru[0] == 0 and ru[-1] == n_users and np.all(np.diff(ru) > 0), ru
         assert ri[0] == 0 and ri[-1] == n_items and np.all(np.diff(ri) > 0), ri
-        # balance: events per rank within 25 % of the mean on this shape
+        # the ranges are the documented rule (events + 8 k per row, contiguous), restated on the host
         uptr, _ = fb.csr(False)
+        iptr_, _ = fb.csr(True)
+        assert np.array_equal(ru, mdist.balanced_row_ranges(uptr, world, 8 * k)), (ru, mdist.balanced_row_ranges(uptr, world, 8 * k))
+        assert np.array_equal(ri, mdist.balanced_row_ranges(iptr_, world, 8 * k))
+        # balance: events per rank within 25 % of the mean on this shape
         per = np.diff(uptr[ru])
         assert per.max() < 1.25 * per.mean(), per
         uptr, ucols = O.feedback_csr(u, i, n_users - 1)

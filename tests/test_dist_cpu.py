@@ -30,6 +30,21 @@ def _worker(rank, world, port, q):
         tdist.destroy_process_group()
 
 
+def test_balanced_row_ranges_cover_and_balance():
+    """WRMF row sharding rule (mirrors csrc/wrmf.cu): contiguous, covering, cost-balanced ranges."""
+    sys.path.insert(0, ROOT)
+    from mymedialite_b200 import dist
+    rs = np.random.RandomState(3)
+    nnz = (rs.zipf(1.6, 5000) % 400).astype(np.int64)
+    ptr = np.concatenate([[0], np.cumsum(nnz)])
+    for world in (1, 2, 3, 8):
+        r = dist.balanced_row_ranges(ptr, world, 64)
+        assert r[0] == 0 and r[-1] == 5000 and np.all(np.diff(r) >= 0)
+        cost = np.array([ptr[r[t + 1]] - ptr[r[t]] + 64 * (r[t + 1] - r[t]) for t in range(world)])
+        assert cost.max() <= cost.mean() + nnz.max() + 64          # no rank exceeds its share by more than one row
+    assert list(dist.balanced_row_ranges(np.array([0, 0, 0, 0]), 2, 1)) == [0, 2, 3]
+
+
 @pytest.mark.timeout(180)
 def test_two_rank_gloo_plumbing():
     import torch.multiprocessing as mp

@@ -92,3 +92,17 @@ def test_shard_by_user_partitions_the_ratings():
 def test_merge_schedules_orders_by_subepoch_then_rank():
     parts = [(np.array([10, 11, 12, 13]), np.array([0, 0, 1, 1])), (np.array([20, 21, 22]), np.array([0, 1, 1]))]
     assert list(dist.merge_schedules(parts, 2)) == [10, 11, 20, 12, 13, 21, 22]
+
+
+def test_parallel_options_map_to_the_engine_grid():
+    """MaxThreads > 1 selects the DSGD block schedule (BiasedMatrixFactorization.cs:178-184); NaiveParallelization
+    (:136-141, :201-204) drops the block exclusivity: one worker group spanning the GPU."""
+    from mymedialite_b200 import recommenders as R, _capi
+    m = R.BiasedMatrixFactorization()
+    assert m._params().schedule == _capi.SCHEDULE_SERIAL
+    m.MaxThreads = 8
+    p = m._params()
+    assert p.schedule == _capi.SCHEDULE_DSGD and p.num_groups == 0 and p.ctas_per_group == 0 and p.max_threads == 8
+    m.NaiveParallelization = True
+    p = m._params()
+    assert p.schedule == _capi.SCHEDULE_DSGD and p.num_groups == 1 and p.ctas_per_group >= 148

@@ -105,16 +105,18 @@ def test_tensor_core_gram_sum_is_fp32_accurate(eng, k):
     assert np.array_equal(Ug, U) and np.array_equal(Vg, V)              # the diagnostic leaves the model alone
 
 
-@pytest.mark.parametrize("mode", ["fp64", "tensor"])
+@pytest.mark.parametrize("mode", ["fp64", "tensor", "tensor_f64"])
 def test_wrmf_paths_agree_on_a_larger_set(eng, mode):
-    """Both device paths against the oracle on 3000 x 1200, k = 64 (rows up to ~1000 entries, empty rows, 2 epochs)."""
+    """The device paths (all-double CUDA cores; tcgen05 Gram sums with the single- or the double-precision Cholesky
+    factor) against the oracle on 3000 x 1200, k = 64 (rows up to ~1000 entries, empty rows, 2 epochs)."""
     engine, ctx = eng
     nu, ni, k = 3000, 1200, 64
     u, i = events(nu - 5, ni, 90000, 77)
     f = engine.DeviceFeedback(ctx, u, i, max_user=nu - 1, max_item=ni - 1)
     rng = O.Random(5)
     U = rng.init_normal(nu * k).reshape(nu, k); V = rng.init_normal(ni * k).reshape(ni, k)
-    engine.wrmf_set_mode(engine._capi.WRMF_FP64 if mode == "fp64" else engine._capi.WRMF_TENSOR)
+    engine.wrmf_set_mode(dict(fp64=engine._capi.WRMF_FP64, tensor=engine._capi.WRMF_TENSOR,
+                              tensor_f64=engine._capi.WRMF_TENSOR_F64)[mode])
     try:
         m = engine.WrmfModel(ctx, f, k)
         m.set_model(U, V)
