@@ -28,12 +28,15 @@ extern "C" {
 #define MML_ERR_STATE     3   /* call order violated (e.g. iterate before a model exists) */
 #define MML_ERR_NCCL      4
 #define MML_ERR_UNSUPPORTED 5
+#define MML_ERR_FORMAT    6   /* malformed input line: the reference's FormatException */
+#define MML_ERR_IO        7   /* file cannot be opened / mapped */
 
 typedef struct mml_ctx     mml_ctx;      /* device, stream (and NCCL communicator when n_gpus > 1) */
 typedef struct mml_ratings mml_ratings;  /* COO rating set resident in HBM */
 typedef struct mml_sgd     mml_sgd;      /* MatrixFactorization / BiasedMatrixFactorization model */
 typedef struct mml_feedback mml_feedback;/* implicit feedback (CSR by user and by item) in HBM */
 typedef struct mml_wrmf    mml_wrmf;     /* WRMF model */
+typedef struct mml_ingest  mml_ingest;   /* a parsed rating / feedback file: COO in pinned host memory + id tables */
 
 const char* mml_last_error(void);
 /* Library build info: "mmlb200 <version> sm_100a". */
@@ -54,6 +57,43 @@ int32_t mml_ctx_synchronize(mml_ctx* ctx);
 int32_t mml_ctx_flush_l2(mml_ctx* ctx);
 /* SM count of the device (used by hosts to pick the number of worker groups). */
 int32_t mml_ctx_sm_count(mml_ctx* ctx, int32_t* out);
+
+/* ---- ingest: text file -> id mapping -> COO in pinned host memory (host threads; the step before the path) ------- */
+enum {
+    MML_FILE_RATINGS = 0,          /* user item rating [...]   IO/StaticRatingData.cs:74-117, IO/RatingData.cs:57-88 */
+    MML_FILE_RATINGS_NO_VALUE = 1, /* user item [...]          TestRatingFileFormat.WITHOUT_RATINGS (value 0) */
+    MML_FILE_FEEDBACK = 2          /* user item [...]          IO/ItemData.cs:59-93 */
+};
+enum {
+    MML_MAP_IDENTITY = 0,          /* internal id = int.Parse(token)               Data/IdentityMapping.cs:62-67 */
+    MML_MAP_FIRST_SEEN = 1         /* internal id = order of first appearance      Data/Mapping.cs:75-85 */
+};
+/* Parses `path` as the reference's readers do: lines end at "\n", "\r" or "\r\n"; empty lines are skipped (feedback
+ * files: lines that are empty after Trim()); every other line is split at tab, space and comma (IO/Constants.cs:25, empty
+ * tokens kept) and must have at least 3 (2) columns, else MML_ERR_FORMAT with the reference's message; column 2 is read as
+ * float.Parse(InvariantCulture) does. `prior` (may be NULL) is an earlier ingest whose id tables this one continues -- the
+ * reference passes the same IMapping objects to the training and the test file reader. n_threads = 0: all host threads.
+ * The result is independent of n_threads (first-seen ids are assigned in file order). */
+int32_t mml_ingest_file(const char* path, int32_t kind, int32_t user_mapping, int32_t item_mapping,
+                        int32_t ignore_first_line, int32_t n_threads, const mml_ingest* prior, mml_ingest** out);
+/* Same on a buffer already in memory (TextReader overloads, StaticRatingData.cs:82-117). */
+int32_t mml_ingest_text(const char* text, int64_t len, int32_t kind, int32_t user_mapping, int32_t item_mapping,
+                        int32_t ignore_first_line, int32_t n_threads, const mml_ingest* prior, mml_ingest** out);
+int32_t mml_ingest_destroy(mml_ingest* h);
+/* Count, MaxUserID, MaxItemID (of this data set), sizes of the id tables (0 for identity mappings), and whether the
+ * COO arrays live in cudaHostAlloc'ed memory. Any output pointer may be NULL. */
+int32_t mml_ingest_info(const mml_ingest* h, int64_t* n, int32_t* max_user, int32_t* max_item,
+                        int32_t* n_user_ids, int32_t* n_item_ids, int32_t* pinned);
+/* Copies the triples out (any pointer may be NULL; values only for MML_FILE_RATINGS). */
+int32_t mml_ingest_copy(const mml_ingest* h, int32_t* users, int32_t* items, float* values);
+/* Mapping.ToOriginalID (Data/Mapping.cs:63-69) for internal ids first .. first+count-1 of the user (which = 0) or item
+ * (which = 1) table: the strings are written back to back into buf, offsets[count + 1] delimit them; *needed = bytes
+ * required (call with buf = offsets = NULL to size the buffer). */
+int32_t mml_ingest_original_ids(const mml_ingest* h, int32_t which, int32_t first, int32_t count,
+                                char* buf, int64_t buf_len, int64_t* offsets, int64_t* needed);
+/* mml_ratings_create / mml_feedback_create straight from the pinned COO arrays. */
+int32_t mml_ingest_to_ratings(mml_ctx* ctx, const mml_ingest* h, mml_ratings** out);
+int32_t mml_ingest_to_feedback(mml_ctx* ctx, const mml_ingest* h, mml_feedback** out);
 
 /* ---- rating matrix build -------------------------------------------------------------------- */
 /* Replaces StaticRatings/Ratings storage (Data/StaticRatings.cs:47-84, Data/Ratings.cs:150-190):

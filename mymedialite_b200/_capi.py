@@ -17,6 +17,9 @@ LOSS_RMSE, LOSS_MAE, LOSS_LOGISTIC = 0, 1, 2
 SCHEDULE_SERIAL, SCHEDULE_DSGD = 0, 1
 GROUPS_PERM_MOD, GROUPS_BALANCED = 0, 1
 INTRA_ROUNDS, INTRA_ASYNC = 0, 1
+FILE_RATINGS, FILE_RATINGS_NO_VALUE, FILE_FEEDBACK = 0, 1, 2
+MAP_IDENTITY, MAP_FIRST_SEEN = 0, 1
+ERR_CUDA, ERR_ARG, ERR_STATE, ERR_NCCL, ERR_UNSUPPORTED, ERR_FORMAT, ERR_IO = 1, 2, 3, 4, 5, 6, 7
 
 
 class MmlError(RuntimeError):
@@ -68,6 +71,16 @@ SIGNATURES = {
     "mml_ctx_synchronize": (C.c_int32, [vp]),
     "mml_ctx_flush_l2": (C.c_int32, [vp]),
     "mml_ctx_sm_count": (C.c_int32, [vp, C.POINTER(C.c_int32)]),
+    "mml_ingest_file": (C.c_int32, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, PP]),
+    "mml_ingest_text": (C.c_int32, [C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, PP]),
+    "mml_ingest_destroy": (C.c_int32, [vp]),
+    "mml_ingest_info": (C.c_int32, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "mml_ingest_copy": (C.c_int32, [vp, oi32p, oi32p, of32p]),
+    "mml_ingest_original_ids": (C.c_int32, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_int64, oi64p,
+                                            C.POINTER(C.c_int64)]),
+    "mml_ingest_to_ratings": (C.c_int32, [vp, vp, PP]),
+    "mml_ingest_to_feedback": (C.c_int32, [vp, vp, PP]),
     "mml_ratings_create": (C.c_int32, [vp, oi32p, oi32p, of32p, C.c_int64, C.c_int32, C.c_int32, PP]),
     "mml_ratings_destroy": (C.c_int32, [vp]),
     "mml_ratings_counts": (C.c_int32, [vp, C.c_int32, i32p]),

@@ -5,6 +5,7 @@ cpu_baseline / --impl reference legs -- never from mymedialite_b200/ (the produc
 """
 import ctypes as C
 import os
+import re
 import subprocess
 
 import numpy as np
@@ -349,3 +350,114 @@ def recommend_model(model, user, n=-1, candidates=None, ignore=None):
     os_ = np.empty(max(candidates.size, 1), dtype=np.float32)
     cnt = lib().mo_recommend_model(model.h, int(user), int(n), candidates, candidates.size, ignore, ignore.size, oi, os_)
     return oi[:cnt].copy(), os_[:cnt].copy()
+
+
+# ---- file readers (test infrastructure for csrc/ingest.cu) ----------------------------------------------------------
+_INT_RE = re.compile(r"^[\t-\r ]*[+-]?[0-9]+[\t-\r ]*$")
+_FLOAT_RE = re.compile(r"^[\t-\r ]*[+-]?([0-9]+\.?[0-9]*|\.[0-9]+)([eE][+-]?[0-9]+)?[\t-\r ]*$")
+
+
+class FormatException(Exception):
+    """System.FormatException raised by the reference's readers."""
+
+
+def _net_int_parse(tok):
+    """int.Parse(string), NumberStyles.Integer (Data/IdentityMapping.cs:64)."""
+    if not _INT_RE.match(tok):
+        raise FormatException("Input string was not in a correct format.")
+    v = int(tok.strip("\t\n\v\f\r "))
+    if not -2 ** 31 <= v < 2 ** 31:
+        raise FormatException("Value was either too large or too small for an Int32.")
+    return v
+
+
+def _net_single_parse(tok):
+    """float.Parse(string, InvariantCulture) of the .NET Framework / Mono: parse to double, cast to float
+    (IO/StaticRatingData.cs:112)."""
+    t = tok.strip("\t\n\v\f\r ")
+    if t == "NaN":
+        return np.float32(np.nan)
+    if t in ("Infinity", "-Infinity"):
+        return np.float32(np.inf if t[0] != "-" else -np.inf)
+    if not _FLOAT_RE.match(tok):
+        raise FormatException("Input string was not in a correct format.")
+    with np.errstate(over="ignore"):
+        f = np.float32(float(t))
+    if np.isinf(f):
+        raise FormatException("Value was either too large or too small for a Single.")
+    return f
+
+
+class FirstSeenMapping:
+    """Data/Mapping.cs:75-85."""
+
+    def __init__(self):
+        self.original_to_internal = {}
+        self.internal_to_original = []
+
+    def to_internal(self, tok):
+        if tok in self.original_to_internal:
+            return self.original_to_internal[tok]
+        i = len(self.original_to_internal)
+        self.original_to_internal[tok] = i
+        self.internal_to_original.append(tok)
+        return i
+
+
+class IdentityMapping:
+    """Data/IdentityMapping.cs:62-67."""
+
+    def to_internal(self, tok):
+        return _net_int_parse(tok)
+
+
+def read_lines(text):
+    """TextReader.ReadLine: a line ends at \\n, \\r or \\r\\n; a trailing terminator does not start another line."""
+    parts = re.split(r"\r\n|\n|\r", text)
+    if parts and parts[-1] == "":
+        parts.pop()
+    return parts
+
+
+def read_rating_text(text, user_mapping=None, item_mapping=None, with_ratings=True, ignore_first_line=False):
+    """IO/StaticRatingData.cs:82-117 (IO/RatingData.cs:57-88 has the same line handling)."""
+    um = user_mapping if user_mapping is not None else IdentityMapping()
+    im = item_mapping if item_mapping is not None else IdentityMapping()
+    lines = read_lines(text)
+    if ignore_first_line:
+        lines = lines[1:]
+    users, items, values = [], [], []
+    for line in lines:
+        if len(line) == 0:
+            continue
+        tokens = re.split(r"[\t ,]", line)                      # string.Split(char[]) keeps empty tokens
+        if with_ratings and len(tokens) < 3:
+            raise FormatException("Expected at least 3 columns: " + line)
+        if not with_ratings and len(tokens) < 2:
+            raise FormatException("Expected at least 2 columns: " + line)
+        users.append(um.to_internal(tokens[0]))
+        items.append(im.to_internal(tokens[1]))
+        values.append(_net_single_parse(tokens[2]) if with_ratings else np.float32(0))
+    return np.array(users, np.int32), np.array(items, np.int32), np.array(values, np.float32)
+
+
+def read_feedback_text(text, user_mapping=None, item_mapping=None, ignore_first_line=False):
+    """IO/ItemData.cs:59-93."""
+    um = user_mapping if user_mapping is not None else IdentityMapping()
+    im = item_mapping if item_mapping is not None else IdentityMapping()
+    lines = read_lines(text)
+    if ignore_first_line:
+        lines = lines[1:]
+    users, items = [], []
+    for line in lines:
+        if len(line.strip("\t\n\v\f\r ")) == 0:
+            continue
+        tokens = re.split(r"[\t ,]", line)
+        if len(tokens) < 2:
+            raise FormatException("Expected at least 2 columns: " + line)
+        try:
+            users.append(um.to_internal(tokens[0]))
+            items.append(im.to_internal(tokens[1]))
+        except FormatException:
+            raise FormatException("Could not read line '%s'" % line)
+    return np.array(users, np.int32), np.array(items, np.int32)

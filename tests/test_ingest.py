@@ -1,0 +1,164 @@
+"""The native parallel reader (csrc/ingest.cu, host threads -- runs without a GPU) against the oracle's restatement of
+IO/StaticRatingData.cs:82-117 / IO/ItemData.cs:59-93 and against the reference's own reader tests
+(src/Tests/IO/StaticRatingDataTest.cs:29-62, src/Tests/IO/ItemDataTest.cs:29-62) and example files."""
+import os
+
+import numpy as np
+import pytest
+
+from mymedialite_b200 import ingest
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+REF_TEST_RATINGS = """5951,50,5,2001-01-01
+5951,223,5,2001-01-01
+5951,260,5,2001-01-01
+5951,293,5,2001-01-01
+5951,356,4,2001-01-01
+5951,364,3,2001-01-01
+5951,457,3,2001-01-01
+"""
+
+
+def test_reference_reader_known_answers():
+    """StaticRatingDataTest.TestRead / TestReadIgnoreLine and ItemDataTest.TestRead / TestReadIgnoreLine: 7 entries."""
+    p = ingest.StaticRatingData.ReadText(REF_TEST_RATINGS)
+    assert p.Count == 7 and p.MaxUserID == 5951 and p.MaxItemID == 457
+    u, i, v = p.arrays()
+    assert u.tolist() == [5951] * 7 and i.tolist() == [50, 223, 260, 293, 356, 364, 457]
+    assert v.tolist() == [5, 5, 5, 5, 4, 3, 3]
+    with_time = "# first line\n" + REF_TEST_RATINGS.replace("2001-01-01", "2001-01-01 00:00:00")
+    assert ingest.StaticRatingData.ReadText(with_time, ignore_first_line=True).Count == 7
+    assert ingest.ItemData.ReadText(REF_TEST_RATINGS.replace(",2001-01-01", "")).Count == 7
+    assert ingest.ItemData.ReadText("# first line\n" + REF_TEST_RATINGS, ignore_first_line=True).Count == 7
+
+
+@pytest.mark.parametrize("name", ["example.train", "example.test"])
+def test_example_files(name):
+    """The reference's tests/example.* (config 1 inputs) through the file entry point."""
+    path = os.path.join(GOLDEN, name)
+    p = ingest.StaticRatingData.Read(path)
+    u, i, v = p.arrays()
+    ou, oi, ov = O.read_rating_text(open(path).read())
+    assert np.array_equal(u, ou) and np.array_equal(i, oi) and np.array_equal(v.view(np.uint32), ov.view(np.uint32))
+    assert p.MaxUserID == ou.max() and p.MaxItemID == oi.max()
+
+
+def _random_file(rng, n, string_ids, seps="\t ,", newline="\n", blanks=True):
+    lines = []
+    for _ in range(n):
+        u, i = int(rng.integers(0, 5000)), int(rng.integers(0, 900))
+        if string_ids:
+            u, i = "u%x" % (u * 7919 % 5000), "item-%d" % (i * 31 % 900)
+        r = rng.choice(["1", "2.5", "3.0", "4", "5", "0.5", "3.14159274", "1e0", "+2", "-1.5", ".5", "4.", "1.17549435E-38",
+                        "0.1", "16777217"])
+        s = seps[int(rng.integers(0, len(seps)))]
+        extra = (s + "978300760") if rng.random() < 0.3 else ""
+        lines.append("%s%s%s%s%s%s" % (u, s, i, s, r, extra))
+        if blanks and rng.random() < 0.02:
+            lines.append("")
+    return newline.join(lines) + (newline if rng.random() < 0.5 else "")
+
+
+@pytest.mark.parametrize("newline", ["\n", "\r\n", "\r"])
+@pytest.mark.parametrize("string_ids", [False, True])
+def test_matches_the_oracle_reader(newline, string_ids):
+    rng = np.random.default_rng(5 + len(newline) + 10 * string_ids)
+    text = _random_file(rng, 60000, string_ids, newline=newline)          # > 64 KiB: several chunks
+    maps = (lambda: (ingest.Mapping(), ingest.Mapping())) if string_ids else (lambda: (None, None))
+    omaps = (O.FirstSeenMapping(), O.FirstSeenMapping()) if string_ids else (None, None)
+    ou, oi, ov = O.read_rating_text(text, *omaps)
+    for threads in (1, 3, 8):
+        um, im = maps()
+        p = ingest.StaticRatingData.ReadText(text, um, im, n_threads=threads)
+        u, i, v = p.arrays()
+        assert np.array_equal(u, ou) and np.array_equal(i, oi), threads
+        assert np.array_equal(v.view(np.uint32), ov.view(np.uint32)), threads
+        if string_ids:
+            assert um.OriginalIDs == omaps[0].internal_to_original
+            assert im.OriginalIDs == omaps[1].internal_to_original
+            assert um.ToOriginalID(int(u[17])) == omaps[0].internal_to_original[ou[17]]
+
+
+def test_mapping_continues_into_the_test_file():
+    """The reference hands the same IMapping objects to the train and the test reader: known ids keep their number,
+    new ones are appended (Data/Mapping.cs:75-85)."""
+    train = "alice\tmatrix\t5\nbob\tmatrix\t3\nalice\theat\t4\n"
+    test = "carol\theat\t2\nbob\talien\t1\n"
+    um, im = ingest.Mapping(), ingest.Mapping()
+    a = ingest.StaticRatingData.ReadText(train, um, im)
+    b = ingest.StaticRatingData.ReadText(test, um, im)
+    assert a.arrays()[0].tolist() == [0, 1, 0] and a.arrays()[1].tolist() == [0, 0, 1]
+    assert b.arrays()[0].tolist() == [2, 1] and b.arrays()[1].tolist() == [1, 2]
+    assert um.OriginalIDs == ["alice", "bob", "carol"] and im.OriginalIDs == ["matrix", "heat", "alien"]
+    assert b.MaxUserID == 2 and a.MaxUserID == 1
+    with pytest.raises(ValueError):
+        um.ToOriginalID(3)
+    om, oim = O.FirstSeenMapping(), O.FirstSeenMapping()
+    O.read_rating_text(train, om, oim)
+    ou, oi, _ = O.read_rating_text(test, om, oim)
+    assert ou.tolist() == [2, 1] and oi.tolist() == [1, 2]
+
+
+def test_feedback_and_no_value_formats():
+    text = "1 2\n \n3,4,extra\n\t\n5\t6\n"
+    u, i = ingest.ItemData.ReadText(text).arrays(values=False)
+    ou, oi = O.read_feedback_text(text)
+    assert np.array_equal(u, ou) and np.array_equal(i, oi) and u.tolist() == [1, 3, 5]
+    p = ingest.StaticRatingData.ReadText("1 2\n3 4\n", test_rating_format=ingest.WITHOUT_RATINGS)
+    assert p.Count == 2
+    ou, oi, ov = O.read_rating_text("1 2\n3 4\n", with_ratings=False)
+    assert p.arrays(values=False)[1].tolist() == oi.tolist() == [2, 4] and ov.tolist() == [0, 0]
+
+
+@pytest.mark.parametrize("text,msg", [
+    ("1\t2\n", "Expected at least 3 columns: 1\t2"),
+    ("1 2 3\n \n", "Expected at least 3 columns:  "),          # a blank line is not empty for the rating reader
+    ("1 2 3\nx 2 3\n", None),
+    ("1 2 three\n", None),
+    ("1  2 3\n", None),                                         # two separators: token 1 is empty -> int.Parse fails
+    ("1 2 1e\n", None),
+    ("1 99999999999 1\n", None),
+    ("1 2 1e60\n", None),
+])
+def test_malformed_lines_raise_like_the_reference(text, msg):
+    with pytest.raises(O.FormatException):
+        O.read_rating_text(text)
+    with pytest.raises(ingest.FormatError) as e:
+        ingest.StaticRatingData.ReadText(text)
+    if msg is not None:
+        assert str(e.value) == msg
+
+
+def test_first_bad_line_wins_and_feedback_message():
+    rng = np.random.default_rng(3)
+    good = _random_file(rng, 40000, False, blanks=False)
+    lines = good.split("\n")
+    lines[30000] = "7 8"
+    lines[10000] = "bad"
+    with pytest.raises(ingest.FormatError) as e:
+        ingest.StaticRatingData.ReadText("\n".join(lines), n_threads=8)
+    assert str(e.value) == "Expected at least 3 columns: bad"
+    with pytest.raises(ingest.FormatError) as e:
+        ingest.ItemData.ReadText("1 2\nx y\n")
+    assert str(e.value) == "Could not read line 'x y'"
+    with pytest.raises(IOError):
+        ingest.StaticRatingData.Read("/nonexistent/ratings.txt")
+
+
+def test_empty_inputs():
+    for text in ("", "\n\n", "# only a header\n"):
+        p = ingest.StaticRatingData.ReadText(text, ignore_first_line=text.startswith("#"))
+        assert p.Count == 0 and p.MaxUserID == -1 and p.MaxItemID == -1
+        assert p.arrays()[0].shape == (0,)
+
+
+def test_float_parse_is_double_then_single():
+    """Number.ParseSingle of the .NET Framework / Mono rounds twice (decimal -> double -> float)."""
+    toks = ["16777217", "0.1", "3.4028234e38", "1.17549435E-38", "1e-50", "7.038531e-26", "1.00000017881393432617187499"]
+    text = "".join("0 0 %s\n" % t for t in toks)
+    v = ingest.StaticRatingData.ReadText(text).arrays()[2]
+    want = np.array([np.float32(float(t)) for t in toks], np.float32)
+    assert np.array_equal(v.view(np.uint32), want.view(np.uint32))
