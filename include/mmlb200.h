@@ -237,6 +237,28 @@ int32_t mml_sgd_hot_items(mml_sgd* m, int64_t* n_hot);
 int32_t mml_sgd_schedule_dump(mml_sgd* m, const int32_t* subepoch_sequence, int32_t* order,
                               int32_t* block, int32_t* copy, int32_t* round);
 
+/* ---- fold-in and incremental updates (IFoldInRatingPredictor / IncrementalRatingPredictor) -------------------------- */
+/* FoldIn (MatrixFactorization.cs:323-347, BiasedMatrixFactorization.cs:445-492) for a batch of users described by
+ * ratings, one warp per user, the reference's arithmetic operation by operation. rated_ptr[n_users + 1] delimits each
+ * user's (item, rating) pairs in rated_items / rated_values, in the order AFTER rated_items.Shuffle() (the host's RNG draws
+ * it, as it draws init_factors[n_users x num_factors] = the InitNormal vector of each user). num_iter = NumIter.
+ * out_vectors: n_users x num_factors for MatrixFactorization; n_users x (num_factors + 1) for the biased model, entry 0
+ * the user bias (FOLD_IN_BIAS_INDEX = 0, FOLD_IN_FACTORS_START = 1, BiasedMatrixFactorization.cs:80-82).
+ * A rated item outside the model is MML_ERR_ARG (the reference throws from the matrix indexer). Model unchanged. */
+int32_t mml_sgd_fold_in(mml_sgd* m, const int64_t* rated_ptr, const int32_t* rated_items, const float* rated_values,
+                        int64_t n_users, const float* init_factors, int32_t num_iter, float* out_vectors);
+/* Predict(float[] user_vector, int item_id) (MatrixFactorization.cs:223-241, BiasedMatrixFactorization.cs:328-336) for
+ * every fold-in vector and every candidate -- the scoring half of ScoreItems (MatrixFactorization.cs:350-363).
+ * out_scores: n_users x n_cand, row-major. */
+int32_t mml_sgd_score_items(mml_sgd* m, const float* user_vectors, int64_t n_users,
+                            const int32_t* candidates, int64_t n_cand, float* out_scores);
+/* Overwrites the factor rows (and biases; either pointer may be NULL = unchanged) of the given users (by_item = 0) or
+ * items (1): the row re-initialisation of RetrainUser / RetrainItem (MatrixFactorization.cs:141-160,
+ * BiasedMatrixFactorization.cs:419-431; the host draws RowInitNormal and then calls mml_sgd_iterate_indices on
+ * ByUser[u] / ByItem[i] with update_user / update_item set accordingly) and the zeroing of RemoveUser / RemoveItem
+ * (MatrixFactorization.cs:300-316, BiasedMatrixFactorization.cs:433-445). factors: n x num_factors. */
+int32_t mml_sgd_set_rows(mml_sgd* m, int32_t by_item, const int32_t* ids, int64_t n, const float* factors, const float* biases);
+
 /* ---- Top-N Recommend() ---------------------------------------------------------------------- */
 /* Recommender.Recommend (Recommender.cs:52-103) for a batch of users on an item-MF model
  * (score = RowScalarProduct, ItemRecommendation/MF.cs:151-157): for every user the top n

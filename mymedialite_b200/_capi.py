@@ -100,6 +100,9 @@ SIGNATURES = {
     "mml_sgd_invalidate_index": (C.c_int32, [vp]),
     "mml_sgd_iterate_indices": (C.c_int32, [vp, oi32p, C.c_int64, C.c_int32, C.c_int32]),
     "mml_sgd_predict": (C.c_int32, [vp, oi32p, oi32p, C.c_int64, of32p]),
+    "mml_sgd_fold_in": (C.c_int32, [vp, oi64p, oi32p, of32p, C.c_int64, of32p, C.c_int32, of32p]),
+    "mml_sgd_score_items": (C.c_int32, [vp, of32p, C.c_int64, oi32p, C.c_int64, of32p]),
+    "mml_sgd_set_rows": (C.c_int32, [vp, C.c_int32, oi32p, C.c_int64, of32p, of32p]),
     "mml_sgd_evaluate": (C.c_int32, [vp, oi32p, oi32p, of32p, C.c_int64, f32p]),
     "mml_sgd_evaluate_train": (C.c_int32, [vp, f32p]),
     "mml_sgd_objective": (C.c_int32, [vp, C.POINTER(C.c_double)]),

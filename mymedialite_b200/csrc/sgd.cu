@@ -2114,3 +2114,250 @@ extern "C" int32_t mml_sgd_schedule_dump(mml_sgd* h, const int32_t* subepoch_seq
     MML_CHECK(pos == n, MML_ERR_STATE, "schedule covers %lld of %lld ratings", (long long)pos, (long long)n);
     return MML_OK;
 }
+
+// =================================================================================================
+// fold-in / incremental operations
+// =================================================================================================
+namespace mml {
+
+struct FoldArgs {
+    int32_t k, num_iter, freq_reg, loss;
+    float learn_rate, decay, reg, blr, breg;
+};
+
+// FoldIn for a batch of users that are not part of the model, one warp per user (the users are independent; inside a
+// user the reference's loop is a serial chain over its ratings). Arithmetic follows MatrixFactorization.cs:323-347 /
+// BiasedMatrixFactorization.cs:445-492 operation by operation: sequential fp32 dot (mul then add), double link, the
+// per-factor step as an fp32 expression widened to double, `+= (float)`. Lane l holds factors l, l + 32, ...
+template <bool BIASED>
+__global__ void __launch_bounds__(128) fold_in_kernel(const PredArgs a, const FoldArgs fa,
+                                                      const int64_t* __restrict__ rated_ptr,
+                                                      const int32_t* __restrict__ rated_items,
+                                                      const float* __restrict__ rated_values, int64_t n_users,
+                                                      const float* __restrict__ init, float* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_users) return;
+    const int k = fa.k, nslot = a.kp / 32;
+    float pv[8], qv[8], prod[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        const int f = s * 32 + lane;
+        pv[s] = (s < nslot && f < k) ? init[w * k + f] : 0.f;
+    }
+    const int64_t lo = rated_ptr[w], hi = rated_ptr[w + 1];
+    float regw = fa.reg;
+    if (BIASED && fa.freq_reg) regw = (float)((double)fa.reg / sqrt((double)(hi - lo)));   // :453
+    float ub = 0.f;
+    double lr = (double)fa.learn_rate;
+    for (int it = 0; it < fa.num_iter; it++) {
+        for (int64_t t = lo; t < hi; t++) {
+            const int32_t row = a.item_int[rated_items[t]];
+            const float r = rated_values[t];
+            const float* qrow = a.Q + (size_t)row * a.kp;
+#pragma unroll
+            for (int s = 0; s < 8; s++)
+                if (s < nslot) { qv[s] = qrow[s * 32 + lane]; prod[s] = __fmul_rn(qv[s], pv[s]); }
+            float dot = 0.f;
+#pragma unroll
+            for (int s = 0; s < 8; s++)
+                if (s < nslot) {
+                    const int cnt = min(32, k - s * 32);
+                    for (int j = 0; j < cnt; j++) dot = __fadd_rn(dot, __shfl_sync(0xffffffffu, prod[s], j));
+                }
+            if (BIASED) {
+                const double score = (double)__fadd_rn(__fadd_rn(__fadd_rn(a.gb, ub), a.bi[row]), dot);
+                const double sig = 1.0 / (1.0 + exp(-score));
+                const double pred = (double)a.minr + sig * (double)a.range;
+                const double err = (double)r - pred;
+                float gc;
+                if (fa.loss == MML_LOSS_RMSE) gc = (float)(err * sig * (1.0 - sig) * (double)a.range);
+                else if (fa.loss == MML_LOSS_MAE) gc = (float)((err > 0 ? 1.0 : (err < 0 ? -1.0 : 0.0)) * sig * (1.0 - sig) * (double)a.range);
+                else gc = (float)err;
+                ub = __fadd_rn(ub, __fmul_rn(__fmul_rn(fa.blr, fa.learn_rate), __fsub_rn(gc, __fmul_rn(__fmul_rn(fa.breg, regw), ub))));
+#pragma unroll
+                for (int s = 0; s < 8; s++)
+                    if (s < nslot) {
+                        const float d = __fsub_rn(__fmul_rn(gc, qv[s]), __fmul_rn(regw, pv[s]));
+                        pv[s] = __fadd_rn(pv[s], (float)((double)fa.learn_rate * (double)d));
+                    }
+            } else {
+                const float err = __fsub_rn(r, __fadd_rn(a.gb, dot));                    // Predict(vector, item, false)
+#pragma unroll
+                for (int s = 0; s < 8; s++)
+                    if (s < nslot) {
+                        const float d = __fsub_rn(__fmul_rn(err, qv[s]), __fmul_rn(regw, pv[s]));
+                        pv[s] = __fadd_rn(pv[s], (float)(lr * (double)d));
+                    }
+            }
+        }
+        lr *= (double)fa.decay;                                                          // MatrixFactorization.cs:345
+    }
+    const int stride = BIASED ? k + 1 : k;
+    float* o = out + w * stride + (BIASED ? 1 : 0);                                      // FOLD_IN_FACTORS_START
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        const int f = s * 32 + lane;
+        if (s < nslot && f < k) o[f] = pv[s];
+    }
+    if (BIASED && lane == 0) out[w * stride] = ub;                                       // FOLD_IN_BIAS_INDEX
+}
+
+// Predict(float[] user_vector, int item_id) for every (vector, candidate) pair, one thread per pair, sequential fp32 dot.
+// MatrixFactorization.cs:223-241 (clipped to the rating scale), BiasedMatrixFactorization.cs:328-336 (item terms only for
+// items the model knows).
+__global__ void score_vectors_kernel(const PredArgs a, int32_t k, const float* __restrict__ vectors, int64_t n_users,
+                                     const int32_t* __restrict__ cand, int64_t n_cand, float* __restrict__ out)
+{
+    const int64_t total = n_users * n_cand;
+    const int stride = a.biased ? k + 1 : k;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t u = t / n_cand;
+        const int32_t item = cand[t - u * n_cand];
+        const float* v = vectors + u * stride;
+        const bool known = item >= 0 && item < a.n_items_ext && a.item_int[item] >= 0;
+        const int32_t row = known ? a.item_int[item] : 0;
+        const float* q = a.Q + (size_t)row * a.kp;
+        const float* vf = v + (a.biased ? 1 : 0);
+        float dot = 0.f;
+        for (int f = 0; f < k; f++) dot = __fadd_rn(dot, __fmul_rn(q[f], vf[f]));
+        float res;
+        if (a.biased) {
+            double score = (double)__fadd_rn(a.gb, v[0]);
+            if (known) score += (double)__fadd_rn(a.bi[row], dot);
+            res = (float)((double)a.minr + 1.0 / (1.0 + exp(-score)) * (double)a.range);
+        } else {
+            res = __fadd_rn(a.gb, dot);
+            if (res > a.maxr) res = a.maxr;
+            if (res < a.minr) res = a.minr;
+        }
+        out[t] = res;
+    }
+}
+
+// rows[ids[j]] = given row (padded with zeros to kp), bias likewise; ids this rank does not hold are skipped
+__global__ void set_rows_kernel(const int32_t* __restrict__ ids, int64_t n, const int32_t* __restrict__ to_int,
+                                const float* __restrict__ rows, const float* __restrict__ biases,
+                                int32_t k, int32_t kp, float* __restrict__ dst, float* __restrict__ dst_bias)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n) return;
+    const int32_t r = to_int[ids[w]];
+    if (r < 0) return;
+    if (rows)
+        for (int f = lane; f < kp; f += 32) dst[(size_t)r * kp + f] = f < k ? rows[w * k + f] : 0.f;
+    if (biases && dst_bias && lane == 0) dst_bias[r] = biases[w];
+}
+
+}  // namespace mml
+
+extern "C" int32_t mml_sgd_fold_in(mml_sgd* h, const int64_t* rated_ptr, const int32_t* rated_items,
+                                   const float* rated_values, int64_t n_users, const float* init_factors,
+                                   int32_t num_iter, float* out_vectors)
+{
+    MML_CHECK(h && (n_users == 0 || (rated_ptr && init_factors && out_vectors)), MML_ERR_ARG, "mml_sgd_fold_in: NULL argument");
+    Sgd& m = h->m;
+    MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_fold_in: no model");
+    MML_CHECK(num_iter >= 0 && n_users >= 0, MML_ERR_ARG, "mml_sgd_fold_in: negative count");
+    MML_CUDA(cudaSetDevice(m.ctx->device));
+    MML_TRY(sync_items(m));
+    if (n_users == 0) return MML_OK;
+    MML_CHECK(rated_ptr[0] == 0, MML_ERR_ARG, "mml_sgd_fold_in: rated_ptr[0] must be 0");
+    for (int64_t u = 0; u < n_users; u++)
+        MML_CHECK(rated_ptr[u + 1] >= rated_ptr[u], MML_ERR_ARG, "mml_sgd_fold_in: rated_ptr is not ascending at %lld", (long long)u);
+    const int64_t nnz = rated_ptr[n_users];
+    MML_CHECK(nnz == 0 || (rated_items && rated_values), MML_ERR_ARG, "mml_sgd_fold_in: NULL rated arrays");
+    for (int64_t t = 0; t < nnz; t++)   // the reference indexes item_factors with the id: out of range throws there
+        MML_CHECK(rated_items[t] >= 0 && rated_items[t] < m.items.n_ext && m.items.to_int[rated_items[t]] >= 0, MML_ERR_ARG,
+                  "mml_sgd_fold_in: rated item %d is not part of the model", rated_items[t]);
+    cudaStream_t s = m.ctx->stream;
+    const int stride = m.p.biased ? m.k + 1 : m.k;
+    DevBuf<int64_t> d_ptr; DevBuf<int32_t> d_it; DevBuf<float> d_val, d_init, d_out;
+    MML_TRY(d_ptr.alloc(n_users + 1)); MML_TRY(d_it.alloc(nnz)); MML_TRY(d_val.alloc(nnz));
+    MML_TRY(d_init.alloc((size_t)n_users * m.k)); MML_TRY(d_out.alloc((size_t)n_users * stride));
+    MML_CUDA(cudaMemcpyAsync(d_ptr.p, rated_ptr, sizeof(int64_t) * (n_users + 1), cudaMemcpyHostToDevice, s));
+    if (nnz > 0) {
+        MML_CUDA(cudaMemcpyAsync(d_it.p, rated_items, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, s));
+        MML_CUDA(cudaMemcpyAsync(d_val.p, rated_values, sizeof(float) * nnz, cudaMemcpyHostToDevice, s));
+    }
+    MML_CUDA(cudaMemcpyAsync(d_init.p, init_factors, sizeof(float) * (size_t)n_users * m.k, cudaMemcpyHostToDevice, s));
+    FoldArgs fa{};
+    fa.k = m.k; fa.num_iter = num_iter; fa.freq_reg = m.p.biased ? m.p.frequency_regularization : 0; fa.loss = m.p.loss;
+    fa.learn_rate = m.p.learn_rate; fa.decay = m.p.decay;
+    fa.reg = m.p.biased ? m.p.reg_u : m.p.regularization;
+    fa.blr = m.p.bias_learn_rate; fa.breg = m.p.bias_reg;
+    const int blocks = (int)ceil_div(n_users * 32, 128);
+    if (m.p.biased) fold_in_kernel<true><<<blocks, 128, 0, s>>>(make_pred_args(m), fa, d_ptr.p, d_it.p, d_val.p, n_users, d_init.p, d_out.p);
+    else fold_in_kernel<false><<<blocks, 128, 0, s>>>(make_pred_args(m), fa, d_ptr.p, d_it.p, d_val.p, n_users, d_init.p, d_out.p);
+    MML_CUDA(cudaGetLastError());
+    m.launches++;
+    MML_CUDA(cudaMemcpyAsync(out_vectors, d_out.p, sizeof(float) * (size_t)n_users * stride, cudaMemcpyDeviceToHost, s));
+    MML_CUDA(cudaStreamSynchronize(s));
+    return MML_OK;
+}
+
+extern "C" int32_t mml_sgd_score_items(mml_sgd* h, const float* user_vectors, int64_t n_users,
+                                       const int32_t* candidates, int64_t n_cand, float* out_scores)
+{
+    MML_CHECK(h, MML_ERR_ARG, "mml_sgd_score_items: NULL argument");
+    Sgd& m = h->m;
+    MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_score_items: no model");
+    MML_CHECK(n_users >= 0 && n_cand >= 0, MML_ERR_ARG, "mml_sgd_score_items: negative count");
+    MML_CUDA(cudaSetDevice(m.ctx->device));
+    MML_TRY(sync_items(m));
+    if (n_users == 0 || n_cand == 0) return MML_OK;
+    MML_CHECK(user_vectors && candidates && out_scores, MML_ERR_ARG, "mml_sgd_score_items: NULL argument");
+    if (!m.p.biased)   // MatrixFactorization.Predict(vector, item) has no range check: RowScalarProduct throws
+        for (int64_t c = 0; c < n_cand; c++)
+            MML_CHECK(candidates[c] >= 0 && candidates[c] < m.items.n_ext && m.items.to_int[candidates[c]] >= 0, MML_ERR_ARG,
+                      "i too big: %d, dim1 is %d", candidates[c], m.items.n_ext);
+    cudaStream_t s = m.ctx->stream;
+    const int stride = m.p.biased ? m.k + 1 : m.k;
+    DevBuf<float> d_vec, d_out; DevBuf<int32_t> d_cand;
+    MML_TRY(d_vec.alloc((size_t)n_users * stride)); MML_TRY(d_cand.alloc(n_cand)); MML_TRY(d_out.alloc((size_t)n_users * n_cand));
+    MML_CUDA(cudaMemcpyAsync(d_vec.p, user_vectors, sizeof(float) * (size_t)n_users * stride, cudaMemcpyHostToDevice, s));
+    MML_CUDA(cudaMemcpyAsync(d_cand.p, candidates, sizeof(int32_t) * n_cand, cudaMemcpyHostToDevice, s));
+    const int64_t total = n_users * n_cand;
+    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)m.ctx->sm_count * 32);
+    score_vectors_kernel<<<blocks, 256, 0, s>>>(make_pred_args(m), m.k, d_vec.p, n_users, d_cand.p, n_cand, d_out.p);
+    MML_CUDA(cudaGetLastError());
+    m.launches++;
+    MML_CUDA(cudaMemcpyAsync(out_scores, d_out.p, sizeof(float) * (size_t)total, cudaMemcpyDeviceToHost, s));
+    MML_CUDA(cudaStreamSynchronize(s));
+    return MML_OK;
+}
+
+extern "C" int32_t mml_sgd_set_rows(mml_sgd* h, int32_t by_item, const int32_t* ids, int64_t n,
+                                    const float* factors, const float* biases)
+{
+    MML_CHECK(h && (n == 0 || ids), MML_ERR_ARG, "mml_sgd_set_rows: NULL argument");
+    Sgd& m = h->m;
+    MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_set_rows: no model");
+    MML_CUDA(cudaSetDevice(m.ctx->device));
+    MML_TRY(sync_items(m));
+    if (n <= 0 || (!factors && !biases)) return MML_OK;
+    GroupMap& gm = by_item ? m.items : m.users;
+    for (int64_t j = 0; j < n; j++)
+        MML_CHECK(ids[j] >= 0 && ids[j] < gm.n_ext, MML_ERR_ARG, "mml_sgd_set_rows: id %d out of range", ids[j]);
+    cudaStream_t s = m.ctx->stream;
+    DevBuf<int32_t> d_ids; DevBuf<float> d_rows, d_b;
+    MML_TRY(d_ids.alloc(n));
+    MML_CUDA(cudaMemcpyAsync(d_ids.p, ids, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+    if (factors) {
+        MML_TRY(d_rows.alloc((size_t)n * m.k));
+        MML_CUDA(cudaMemcpyAsync(d_rows.p, factors, sizeof(float) * (size_t)n * m.k, cudaMemcpyHostToDevice, s));
+    }
+    if (biases) {
+        MML_TRY(d_b.alloc(n));
+        MML_CUDA(cudaMemcpyAsync(d_b.p, biases, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+    }
+    set_rows_kernel<<<(int)ceil_div(n * 32, 256), 256, 0, s>>>(d_ids.p, n, gm.d_to_int.p, factors ? d_rows.p : nullptr,
+                                                              biases ? d_b.p : nullptr, m.k, m.kp,
+                                                              by_item ? m.Q.p : m.P.p, by_item ? m.bi.p : m.bu.p);
+    MML_CUDA(cudaGetLastError());
+    m.launches++;
+    MML_CUDA(cudaStreamSynchronize(s));
+    return MML_OK;
+}

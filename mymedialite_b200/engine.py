@@ -166,6 +166,32 @@ class SgdModel:
         idx = _i32(indices)
         check(self.lib.mml_sgd_iterate_indices(self.h, idx, idx.shape[0], int(update_user), int(update_item)))
 
+    def fold_in(self, rated_items, rated_values, init_factors, num_iter):
+        """Batch FoldIn: rated_items / rated_values are per-user sequences (already shuffled), init_factors [n, k]."""
+        n = len(rated_items)
+        ptr = np.zeros(n + 1, np.int64)
+        ptr[1:] = np.cumsum([len(x) for x in rated_items])
+        it = _i32(np.concatenate([np.asarray(x, np.int32) for x in rated_items]) if ptr[-1] else np.zeros(1, np.int32))
+        va = _f32(np.concatenate([np.asarray(x, np.float32) for x in rated_values]) if ptr[-1] else np.zeros(1, np.float32))
+        init = _f32(np.asarray(init_factors, np.float32).reshape(max(n, 1), -1))
+        stride = self.k + 1 if self.params.biased else self.k
+        out = np.zeros((max(n, 1), stride), np.float32)
+        check(self.lib.mml_sgd_fold_in(self.h, ptr, it, va, n, init, int(num_iter), out))
+        return out[:n]
+
+    def score_items(self, user_vectors, candidates):
+        v = _f32(np.atleast_2d(np.asarray(user_vectors, np.float32)))
+        cand = _i32(candidates)
+        out = np.zeros((max(v.shape[0], 1), max(cand.shape[0], 1)), np.float32)
+        check(self.lib.mml_sgd_score_items(self.h, v, v.shape[0], cand, cand.shape[0], out))
+        return out[:v.shape[0], :cand.shape[0]]
+
+    def set_rows(self, ids, factors=None, biases=None, by_item=False):
+        ids = _i32(np.atleast_1d(ids))
+        f = None if factors is None else _f32(np.asarray(factors, np.float32).reshape(ids.shape[0], -1))
+        b = None if biases is None else _f32(np.atleast_1d(biases))
+        check(self.lib.mml_sgd_set_rows(self.h, 1 if by_item else 0, ids, ids.shape[0], f, b))
+
     def predict(self, users, items):
         users, items = _i32(users), _i32(items)
         out = np.zeros(users.shape[0], np.float32)

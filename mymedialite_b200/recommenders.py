@@ -187,6 +187,69 @@ class MatrixFactorization(_Recommender):
     def ComputeObjective(self):
         return self._model.objective()
 
+    # -- IncrementalRatingPredictor / IFoldInRatingPredictor ---------------------------------------------------
+    UpdateUsers = True
+    UpdateItems = True
+
+    def _retrain(self, entity_id, by_item):
+        """RetrainUser / RetrainItem (MatrixFactorization.cs:141-160, BiasedMatrixFactorization.cs:419-431): the row is
+        re-drawn (RowInitNormal, host RNG), the bias zeroed (biased model), then one pass over ByUser[u] / ByItem[i]
+        in ascending rating-index order updating that side only (LearnFactors -> Iterate(list, ...))."""
+        row = sysrandom.get_instance().init_normal(1, int(self.NumFactors), self.InitMean, self.InitStdDev)
+        self._model.set_rows([entity_id], row, [0.0] if self._biased else None, by_item=by_item)
+        ids = self.Ratings.Items if by_item else self.Ratings.Users
+        idx = np.nonzero(ids == entity_id)[0].astype(np.int32)
+        self._model.iterate_indices(idx, update_user=not by_item, update_item=by_item)
+
+    def RetrainUser(self, user_id):
+        if self.UpdateUsers:
+            self._retrain(user_id, False)
+
+    def RetrainItem(self, item_id):
+        if self.UpdateItems:
+            self._retrain(item_id, True)
+
+    def RemoveUser(self, user_id):
+        """MatrixFactorization.cs:300-306 / BiasedMatrixFactorization.cs:433-438: the row (and bias) is set to zero."""
+        self._model.set_rows([user_id], np.zeros((1, int(self.NumFactors)), np.float32), [0.0] if self._biased else None)
+
+    def RemoveItem(self, item_id):
+        self._model.set_rows([item_id], np.zeros((1, int(self.NumFactors)), np.float32), [0.0] if self._biased else None,
+                             by_item=True)
+
+    def FoldInMany(self, rated_items_per_user):
+        """FoldIn (MatrixFactorization.cs:323-347, BiasedMatrixFactorization.cs:445-492) for several new users in one
+        launch. The RNG draws happen user by user in the reference's order: the InitNormal vector, then the shuffle."""
+        rng = sysrandom.get_instance()
+        k = int(self.NumFactors)
+        init = np.zeros((len(rated_items_per_user), k), np.float32)
+        items, values = [], []
+        for j, rated in enumerate(rated_items_per_user):
+            init[j] = rng.init_normal(1, k, self.InitMean, self.InitStdDev)[0]
+            order = rng.shuffle(np.arange(len(rated)))
+            items.append([rated[t][0] for t in order])
+            values.append([rated[t][1] for t in order])
+        return self._model.fold_in(items, values, init, int(self.NumIter))
+
+    def FoldIn(self, rated_items):
+        return self.FoldInMany([rated_items])[0]
+
+    def ScoreItems(self, rated_items, candidate_items=None):
+        """MatrixFactorization.cs:350-363; candidates default as FoldInRatingPredictorExtensions.cs:64 (0..MaxItemID-2)."""
+        if candidate_items is None:
+            candidate_items = np.arange(0, max(self.MaxItemID - 1, 0), dtype=np.int32)
+        cand = np.ascontiguousarray(candidate_items, np.int32)
+        scores = self._model.score_items(self.FoldIn(rated_items), cand)[0]
+        return [(int(i), float(s)) for i, s in zip(cand, scores)]
+
+    def RecommendItems(self, rated_items, candidate_items=None, n=-1):
+        """FoldInRatingPredictorExtensions.cs:35-51: OrderByDescending (stable) then Take(n)."""
+        scored = self.ScoreItems(rated_items, candidate_items)
+        order = np.argsort(-np.array([s for _, s in scored], np.float32), kind="stable")
+        if n >= 0:
+            order = order[:n]
+        return [scored[t] for t in order]
+
     # -- model files ------------------------------------------------------------------------------------------
     def SaveModel(self, filename):
         m = self._model.get_model()

@@ -490,6 +490,72 @@ void mo_model_iterate_indices(mo_model* m, const int32_t* idx, int64_t n_idx, in
     else mo_mf_iterate_list(m, idx, n_idx, update_user, update_item);
 }
 
+/* FoldIn: MatrixFactorization.cs:323-347 (plain; out has k entries) and BiasedMatrixFactorization.cs:445-492
+ * (biased; out[0] = user bias, out[1..k] = factors: FOLD_IN_BIAS_INDEX / FOLD_IN_FACTORS_START, :80-82).
+ * `items`/`values` are rated_items AFTER rated_items.Shuffle(), `init` is the vector InitNormal drew -- both draws belong
+ * to the caller's RNG stream (vector first, then the shuffle). The model is not modified. */
+void mo_model_fold_in(const mo_model* m, const int32_t* items, const float* values, int64_t n, const float* init, float* out)
+{
+    const int32_t k = m->p.num_factors;
+    if (!m->biased) {
+        float* user_vector = out;
+        memcpy(user_vector, init, sizeof(float) * (size_t)k);
+        const float reg = m->p.regularization;
+        double lr = m->p.learn_rate;
+        for (int32_t it = 0; it < m->p.num_iter; it++) {
+            for (int64_t t = 0; t < n; t++) {
+                const float* qi = m->V + (int64_t)items[t] * k;
+                float err = values[t] - (m->global_bias + mo_row_scalar_product(qi, user_vector, k));  /* Predict(v, i, false) */
+                for (int32_t f = 0; f < k; f++) {
+                    float u_f = user_vector[f], i_f = qi[f];
+                    double delta_u = err * i_f - reg * u_f;       /* fp32 expression widened */
+                    user_vector[f] += (float)(lr * delta_u);
+                }
+            }
+            lr *= m->p.decay;
+        }
+        return;
+    }
+    float user_bias = 0;
+    float* factors = out + 1;
+    memcpy(factors, init, sizeof(float) * (size_t)k);
+    const float reg_weight = m->p.frequency_regularization ? (float)(m->p.reg_u / sqrt((double)n)) : m->p.reg_u;
+    const float lrate = m->p.learn_rate;                          /* LearnRate, not current_learnrate (:466,:477) */
+    for (int32_t it = 0; it < m->p.num_iter; it++)
+        for (int64_t t = 0; t < n; t++) {
+            const int32_t item_id = items[t];
+            const float* qi = m->V + (int64_t)item_id * k;
+            double score = m->global_bias + user_bias + m->bi[item_id] + mo_row_scalar_product(qi, factors, k);
+            double sig_score = 1 / (1 + exp(-score));
+            double prediction = m->min_rating + sig_score * m->rating_range_size;
+            double err = values[t] - prediction;
+            float gradient_common = mo_gradient_common(m->p.loss, sig_score, err, m->rating_range_size);
+            user_bias += m->p.bias_learn_rate * lrate * (gradient_common - m->p.bias_reg * reg_weight * user_bias);
+            for (int32_t f = 0; f < k; f++) {
+                float u_f = factors[f], i_f = qi[f];
+                double delta_u = gradient_common * i_f - reg_weight * u_f;   /* fp32 expression widened (:474-476) */
+                factors[f] += (float)(lrate * delta_u);
+            }
+        }
+    out[0] = user_bias;
+}
+
+/* Predict(float[] user_vector, int item_id): MatrixFactorization.cs:223-241 (bounded), BiasedMatrixFactorization.cs:328-336 */
+float mo_model_predict_vector(const mo_model* m, const float* user_vector, int32_t item_id)
+{
+    const int32_t k = m->p.num_factors;
+    if (!m->biased) {
+        float result = m->global_bias + mo_row_scalar_product(m->V + (int64_t)item_id * k, user_vector, k);
+        if (result > m->max_rating) return m->max_rating;
+        if (result < m->min_rating) return m->min_rating;
+        return result;
+    }
+    double score = m->global_bias + user_vector[0];
+    if (item_id <= m->max_item)
+        score += m->bi[item_id] + mo_row_scalar_product(m->V + (int64_t)item_id * k, user_vector + 1, k);
+    return (float)(m->min_rating + 1 / (1 + exp(-score)) * m->rating_range_size);
+}
+
 /* MatrixFactorization.cs:99-116 ; BiasedMatrixFactorization.cs:161-190 */
 void mo_model_init(mo_model* m, mo_rng* r)
 {

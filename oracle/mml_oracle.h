@@ -124,6 +124,8 @@ float* mo_model_item_bias(mo_model* m);
 const int32_t* mo_model_random_index(mo_model* m);  /* NULL until built */
 /* One pass of Iterate(IList<int>,bool,bool) over an explicit index list (no lr update for BMF;
  * plain MF applies its UpdateLearnRate as the reference does, MatrixFactorization.cs:195). */
+void  mo_model_fold_in(const mo_model* m, const int32_t* items, const float* values, int64_t n, const float* init, float* out);
+float mo_model_predict_vector(const mo_model* m, const float* user_vector, int32_t item_id);
 void  mo_model_iterate_indices(mo_model* m, const int32_t* idx, int64_t n_idx, int update_user, int update_item);
 /* Mini-batch replay of the GPU stratum schedule, used ONLY to check the CUDA kernel's arithmetic:
  * ratings (user,value) of one item run are consumed `batch` at a time against the same q_i/b_i. */

@@ -92,6 +92,8 @@ def lib():
         "mo_model_item_bias": (C.POINTER(C.c_float), [vp]),
         "mo_model_random_index": (C.POINTER(C.c_int32), [vp]),
         "mo_model_iterate_indices": (None, [vp, i32p, C.c_int64, C.c_int, C.c_int]),
+        "mo_model_fold_in": (None, [vp, i32p, f32p, C.c_int64, f32p, f32p]),
+        "mo_model_predict_vector": (C.c_float, [vp, f32p, C.c_int32]),
         "mo_bmf_replay_runs": (None, [vp, i32p, i64p, C.c_int64, i32p, f32p, C.c_int32]),
         "mo_wrmf_optimize": (None, [i64p, i32p, C.c_int32, f32p, f32p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int]),
         "mo_wrmf_gram": (None, [f32p, C.c_int32, C.c_int32, f64p]),
@@ -198,6 +200,18 @@ class Model:
         ent_user = np.ascontiguousarray(ent_user, dtype=np.int32)
         ent_value = np.ascontiguousarray(ent_value, dtype=np.float32)
         lib().mo_bmf_replay_runs(self.h, run_item, run_ptr, run_item.size, ent_user, ent_value, int(batch))
+
+    def fold_in(self, items, values, init):
+        """FoldIn on (item, rating) pairs already shuffled; init = the InitNormal vector. Returns the user vector."""
+        items = np.ascontiguousarray(items, np.int32); values = np.ascontiguousarray(values, np.float32)
+        out = np.zeros(self.k + (1 if self.biased else 0), np.float32)
+        lib().mo_model_fold_in(self.h, items if items.size else np.zeros(1, np.int32),
+                               values if values.size else np.zeros(1, np.float32), items.size,
+                               np.ascontiguousarray(init, np.float32), out)
+        return out
+
+    def predict_vector(self, vector, item):
+        return float(lib().mo_model_predict_vector(self.h, np.ascontiguousarray(vector, np.float32), int(item)))
 
     def predict(self, u, i):
         return lib().mo_model_predict(self.h, int(u), int(i))

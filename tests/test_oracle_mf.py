@@ -158,3 +158,72 @@ def test_wrmf_half_sweep_solves_normal_equations():
         b = 2.0 * Hd[S].sum(0)
         assert np.allclose(W[u], np.linalg.solve(A, b), rtol=1e-5, atol=1e-7)
     assert np.allclose(O.wrmf_gram(H), Hd.T @ Hd, rtol=1e-6)
+
+
+# ---- FoldIn (MatrixFactorization.cs:323-347, BiasedMatrixFactorization.cs:445-492) -------------------------------------
+def _fold_in_numpy(m, items, values, init, biased, num_iter):
+    """Second, independent restatement in numpy scalars (float32 for C# float, float for double)."""
+    import math
+    f32 = np.float32
+    V, k = m.item_factors, m.k
+    p = m.params
+    gb = f32(m.global_bias)
+
+    def dot(a, b):
+        r = f32(0)
+        for x, y in zip(a, b):
+            r = f32(r + f32(x * y))
+        return r
+    vec = init.astype(np.float32).copy()
+    if not biased:
+        lr = float(p.learn_rate)
+        for _ in range(num_iter):
+            for it, r in zip(items, values):
+                err = f32(f32(r) - f32(gb + dot(V[it], vec)))
+                for f in range(k):
+                    d = f32(f32(err * V[it, f]) - f32(f32(p.regularization) * vec[f]))
+                    vec[f] = f32(vec[f] + f32(lr * float(d)))
+            lr *= float(f32(p.decay))
+        return vec
+    mn, rng_size = f32(m.values.min()), f32(f32(m.values.max()) - f32(m.values.min()))
+    ub = f32(0)
+    regw = f32(p.reg_u)
+    for _ in range(num_iter):
+        for it, r in zip(items, values):
+            score = float(f32(f32(f32(gb + ub) + m.item_bias[it]) + dot(V[it], vec)))
+            sig = 1 / (1 + math.exp(-score))
+            err = float(f32(r)) - (float(mn) + sig * float(rng_size))
+            gc = f32(err * sig * (1 - sig) * float(rng_size))
+            ub = f32(ub + f32(f32(f32(p.bias_learn_rate) * f32(p.learn_rate)) * f32(gc - f32(f32(f32(p.bias_reg) * regw) * ub))))
+            for f in range(k):
+                d = f32(f32(gc * V[it, f]) - f32(regw * vec[f]))
+                vec[f] = f32(vec[f] + f32(float(f32(p.learn_rate)) * float(d)))
+    return np.concatenate([[ub], vec]).astype(np.float32)
+
+
+@pytest.mark.parametrize("biased", [True, False])
+def test_fold_in_two_restatements_agree(biased):
+    rng = np.random.default_rng(2)
+    n_users, n_items, n = 40, 25, 600
+    u = rng.integers(0, n_users, n).astype(np.int32); i = rng.integers(0, n_items, n).astype(np.int32)
+    u[:n_users] = np.arange(n_users); i[:n_items] = np.arange(n_items)
+    v = (rng.integers(1, 11, n) / 2).astype(np.float32)
+    m = O.Model(u, i, v, biased=biased, num_factors=7, num_iter=4, decay=0.95 if not biased else 1.0)
+    m.init(O.Random(5))
+    m.iterate(O.Random(6))
+    items = rng.integers(0, n_items, 9).astype(np.int32)
+    values = (rng.integers(1, 11, 9) / 2).astype(np.float32)
+    init = (rng.standard_normal(7) * 0.1).astype(np.float32)
+    with np.errstate(over="ignore"):
+        want = _fold_in_numpy(m, items, values, init, biased, 4)
+    got = m.fold_in(items, values, init)
+    if biased:
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)   # libm exp vs math.exp: at most a last-bit difference
+    else:
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # no ratings: the vector is the drawn one
+    empty = m.fold_in([], [], init)
+    assert np.array_equal(empty[-7:], init) and (not biased or empty[0] == 0)
+    # Predict(vector, item): clipped for the plain model, sigmoid link for the biased one
+    s = m.predict_vector(got, 3)
+    assert v.min() <= s <= v.max()

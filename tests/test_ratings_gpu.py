@@ -100,3 +100,30 @@ def test_shuffle_apply_adversarial_targets(eng):
         got = np.arange(n, dtype=np.int32)
         engine._capi.check(ctx.lib.mml_shuffle_apply(ctx.h, got, H, n))
         assert np.array_equal(got, want)
+
+
+def test_ingest_feeds_the_device_from_pinned_memory(eng, tmp_path):
+    """Text file -> native parallel reader -> pinned COO -> mml_ratings_create / mml_feedback_create (no copy through the
+    host language): same counts, CSR and statistics as uploading the arrays by hand."""
+    from mymedialite_b200 import ingest
+    engine, ctx = eng
+    rng = np.random.default_rng(12)
+    n = 300_000
+    u = rng.integers(0, 4000, n).astype(np.int32); i = rng.integers(0, 1500, n).astype(np.int32)
+    v = (rng.integers(1, 11, n) / 2).astype(np.float32)
+    path = tmp_path / "ratings.tsv"
+    with open(path, "w") as w:
+        w.write("".join("%d\t%d\t%s\n" % (a, b, c) for a, b, c in zip(u, i, v)))
+    parsed = ingest.StaticRatingData.Read(str(path))
+    assert parsed.pinned and parsed.Count == n
+    r = parsed.to_device_ratings(ctx)
+    ref = engine.DeviceRatings(ctx, u, i, v)
+    assert np.array_equal(r.counts(False), ref.counts(False)) and np.array_equal(r.counts(True), ref.counts(True))
+    for by_item in (False, True):
+        a, b = r.csr(by_item), ref.csr(by_item)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert r.stats() == ref.stats()
+    fb = ingest.ItemData.Read(str(path)).to_device_feedback(ctx)
+    want = engine.DeviceFeedback(ctx, u, i)
+    assert fb.nnz == want.nnz
+    assert all(np.array_equal(x, y) for x, y in zip(fb.csr(), want.csr()))
