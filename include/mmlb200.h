@@ -284,6 +284,24 @@ int32_t mml_topn_set_mode(int32_t mode);
 /* Users served by each path in the last Recommend() call of this process and the device time of the tensor path. */
 int32_t mml_topn_last_stats(int64_t* users_tensor_path, int64_t* users_exact_path, float* tensor_path_ms);
 
+/* ---- item-ranking evaluation ------------------------------------------------------------------------------ */
+/* Eval.Items.Evaluate (Eval/Items.cs:126-209) for an item-MF model: for every test user the ranking of `candidates`
+ * (distinct ids; the host draws Items.Candidates' shuffle) without the user's ignore row (its training items, NULL =
+ * RepeatedEvents.Yes), cut to the n best (n = -1: whole list), is compared with the user's test row. The list is never
+ * materialised: the ranks of the test items are counted from the exact score rows (score desc, candidate position asc).
+ * test_ptr[n_test_users + 1] / test_idx: test_user_matrix rows aligned with test_users; ignore_ptr / ignore_idx likewise.
+ * out_measures: n_test_users x 8 = {AUC, MAP, NDCG, MRR, prec@5, prec@10, recall@5, recall@10} as the (float) values the
+ * reference adds up (Eval/Measures/AUC.cs, PrecisionAndRecall.cs, NDCG.cs, ReciprocalRank.cs); out_used[u] = 1 when the
+ * user counts (num_users), 0 when the reference skips it (no test item among the candidates, or nothing but test items).
+ * The host sums the rows with out_used = 1 and divides by their number. */
+int32_t mml_items_evaluate_mf(mml_ctx* ctx, const float* user_factors, int32_t n_model_users,
+                              const float* item_factors, int32_t n_model_items, int32_t k,
+                              const int32_t* test_users, int64_t n_test_users,
+                              const int32_t* candidates, int64_t n_cand,
+                              const int64_t* test_ptr, const int32_t* test_idx,
+                              const int64_t* ignore_ptr, const int32_t* ignore_idx, int32_t n,
+                              float* out_measures, int32_t* out_used);
+
 /* ---- WRMF ------------------------------------------------------------------------------------- */
 /* PosOnlyFeedback.UserMatrix / ItemMatrix (Data/PosOnlyFeedback.cs:35-83): duplicates collapse. */
 int32_t mml_feedback_create(mml_ctx* ctx, const int32_t* users, const int32_t* items, int64_t n,
@@ -322,6 +340,12 @@ int32_t mml_wrmf_set_mode(int32_t mode);
 /* Diagnostic for the parity tests: the tensor-core Gram sum (128 x 128 floats, zero beyond num_factors) of the user with
  * the most events, and that user's id. The model is not modified. */
 int32_t mml_wrmf_debug_gram(mml_wrmf* m, float* out_gram, int32_t* out_user);
+/* mml_items_evaluate_mf on the device-resident model (no factor upload). */
+int32_t mml_wrmf_evaluate(mml_wrmf* m, const int32_t* test_users, int64_t n_test_users,
+                          const int32_t* candidates, int64_t n_cand,
+                          const int64_t* test_ptr, const int32_t* test_idx,
+                          const int64_t* ignore_ptr, const int32_t* ignore_idx, int32_t n,
+                          float* out_measures, int32_t* out_used);
 /* mml_topn_mf on the device-resident model (no factor upload). */
 int32_t mml_wrmf_recommend(mml_wrmf* m, const int32_t* users, int64_t n_users, int32_t n,
                            const int32_t* candidates, int64_t n_cand,

@@ -112,6 +112,10 @@ SIGNATURES = {
     "mml_sgd_grid": (C.c_int32, [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mml_topn_mf": (C.c_int32, [vp, f32p, C.c_int32, f32p, C.c_int32, C.c_int32, oi32p, C.c_int64, C.c_int32,
                                 oi32p, C.c_int64, oi64p, oi32p, i32p, f32p, i32p]),
+    "mml_items_evaluate_mf": (C.c_int32, [vp, f32p, C.c_int32, f32p, C.c_int32, C.c_int32, oi32p, C.c_int64, oi32p, C.c_int64,
+                                          oi64p, oi32p, oi64p, oi32p, C.c_int32, of32p, oi32p]),
+    "mml_wrmf_evaluate": (C.c_int32, [vp, oi32p, C.c_int64, oi32p, C.c_int64, oi64p, oi32p, oi64p, oi32p, C.c_int32,
+                                      of32p, oi32p]),
     "mml_topn_set_mode": (C.c_int32, [C.c_int32]),
     "mml_topn_last_stats": (C.c_int32, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "mml_feedback_create": (C.c_int32, [vp, oi32p, oi32p, C.c_int64, C.c_int32, C.c_int32, PP]),

@@ -399,6 +399,195 @@ int32_t topn_device(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
     return MML_OK;
 }
 
+// =================================================================================================
+// Eval.Items.Evaluate on the device: ranking measures straight from the score rows
+// =================================================================================================
+// Reference: Eval/Items.cs:126-209 and Eval/Measures/{AUC,PrecisionAndRecall,NDCG,ReciprocalRank}.cs. For one test user
+// the reference builds Recommend(user, candidates, n, ignore = training items) and walks that list once per measure.
+// Every measure only needs the ranks of the user's correct items (test items among the candidates) in that list, so
+// the list is never materialised: the correct items are ordered by (score desc, candidate position asc), every
+// listed candidate finds by binary search how many correct items precede it, and a prefix sum over those counts gives
+// each correct item's rank. One CTA per user; scores are the exact ones of score_tile_kernel.
+struct EvalArgs {
+    const float* scores; int64_t n_cand; int32_t n;          // scores: [batch][n_cand], -inf = ignored, -FLT_MAX = dropped
+    const int32_t* pos_of; int32_t n_pos_of;                 // item -> candidate position or -1
+    const int64_t* test_ptr; const int32_t* test_idx;        // correct-item rows of ALL test users
+    int64_t b_lo;                                            // first test user of this batch
+    float* c_score; int32_t* c_pos;                          // scratch, one slot per test entry: listed correct items
+    float* s_score; int32_t* s_pos;                          //   ... sorted by rank
+    uint32_t* bucket;                                        // scratch [test nnz + users]: bucket of user u starts at test_ptr[u] + u
+    float* out; int32_t* used;                               // [users][8], [users]
+};
+
+__device__ __forceinline__ bool ranks_before(float sa, int32_t pa, float sb, int32_t pb)
+{
+    return sa > sb || (sa == sb && pa < pb);                 // OrderByDescending is stable: ties keep candidate order
+}
+
+constexpr int EVAL_T = 256;
+__global__ void __launch_bounds__(EVAL_T) items_eval_kernel(const EvalArgs a)
+{
+    __shared__ int sh_m, sh_ncorrect, sh_listed, sh_ignored;
+    const int b = blockIdx.x;
+    const int64_t u = a.b_lo + b;
+    const float* row = a.scores + (size_t)b * a.n_cand;
+    const int64_t lo = a.test_ptr[u], hi = a.test_ptr[u + 1];
+    float* cs = a.c_score + lo; int32_t* cp = a.c_pos + lo;
+    float* ss = a.s_score + lo; int32_t* sp = a.s_pos + lo;
+    uint32_t* bucket = a.bucket + lo + u;
+    if (threadIdx.x == 0) { sh_m = 0; sh_ncorrect = 0; sh_listed = 0; sh_ignored = 0; }
+    __syncthreads();
+    // correct_items = test row  intersected with the candidates (Items.cs:152-153); those with a listed score are ranked
+    for (int64_t e = lo + threadIdx.x; e < hi; e += EVAL_T) {
+        const int32_t item = a.test_idx[e];
+        const int32_t pos = (item >= 0 && item < a.n_pos_of) ? a.pos_of[item] : -1;
+        if (pos < 0) continue;
+        atomicAdd(&sh_ncorrect, 1);
+        const float sc = row[pos];
+        if (sc > -FLT_MAX) { const int slot = atomicAdd(&sh_m, 1); cs[slot] = sc; cp[slot] = pos; }
+    }
+    __syncthreads();
+    const int m = sh_m;
+    for (int i = threadIdx.x; i < m; i += EVAL_T) {
+        int r = 0;
+        const float si = cs[i]; const int32_t pi = cp[i];
+        for (int j = 0; j < m; j++) r += ranks_before(cs[j], cp[j], si, pi) ? 1 : 0;
+        ss[r] = si; sp[r] = pi;
+    }
+    for (int i = threadIdx.x; i <= m; i += EVAL_T) bucket[i] = 0u;
+    __syncthreads();
+    int listed = 0, ignored = 0;
+    for (int64_t c = threadIdx.x; c < a.n_cand; c += EVAL_T) {
+        const float sc = row[c];
+        if (sc == -INFINITY) { ignored++; continue; }
+        if (!(sc > -FLT_MAX)) continue;                      // Recommender.cs:70: only scores > float.MinValue are listed
+        listed++;
+        if (m == 0) continue;
+        int l = 0, h = m;                                    // first correct item that does not precede candidate c
+        while (l < h) {
+            const int mid = (l + h) >> 1;
+            if (ranks_before(ss[mid], sp[mid], sc, (int32_t)c)) l = mid + 1; else h = mid;
+        }
+        atomicAdd(&bucket[l], 1u);
+    }
+    atomicAdd(&sh_listed, listed); atomicAdd(&sh_ignored, ignored);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const int64_t L = sh_listed;
+    const int64_t n_correct = sh_ncorrect;
+    const int64_t num_cand_user = a.n_cand - sh_ignored;     // Items.cs:161-162
+    float* o = a.out + (size_t)u * 8;
+    for (int x = 0; x < 8; x++) o[x] = 0.f;
+    if (n_correct == 0 || n_correct == num_cand_user) { a.used[u] = 0; return; }   // :154-155, :163-164
+    const int64_t Lp = (a.n > 0) ? min((int64_t)a.n, L) : L; // prediction.Count
+    const int64_t dropped = num_cand_user - Lp;              // :169
+    int64_t hits = 0, h5 = 0, h10 = 0, after_sum = 0;
+    double ap = 0.0, dcg = 0.0, rr = 0.0;
+    int64_t rank = 0;
+    const double ln2 = log(2.0);
+    for (int t = 0; t < m; t++) {
+        rank += bucket[t];                                   // listed candidates that do not come after correct item t
+        if (rank > Lp) break;
+        hits++;
+        ap += (double)hits / (double)rank;                   // PrecisionAndRecall.AP
+        dcg += 1.0 / (log((double)(rank + 1)) / ln2);        // NDCG: 1 / Math.Log(rank + 1, 2)
+        if (hits == 1) rr = 1.0 / (double)rank;              // ReciprocalRank
+        if (rank <= 5) h5++;
+        if (rank <= 10) h10++;
+        after_sum += Lp - rank;                              // list entries after this hit (relevant ones removed below)
+    }
+    double idcg = 0.0;
+    for (int64_t i = 0; i < n_correct; i++) idcg += 1.0 / (log((double)(i + 2)) / ln2);
+    // AUC.Compute: pairs (relevant, non-relevant) in the right order
+    const int64_t missing = n_correct - hits;
+    const int64_t eval_pairs = (num_cand_user - hits) * hits;
+    double auc;
+    if (eval_pairs == 0) auc = 0.5;                          // AUC.cs: checked before the consistency test below
+    else if (dropped - missing < 0) { a.used[u] = -1; return; }   // the reference throws "Should not happen."
+    else {
+        const int64_t correct_pairs = after_sum - hits * (hits - 1) / 2 + hits * (dropped - missing);
+        auc = (double)correct_pairs / (double)eval_pairs;
+    }
+    o[0] = (float)auc;
+    o[1] = (float)(hits ? ap / (double)n_correct : 0.0);
+    o[2] = (float)(dcg / idcg);
+    o[3] = (float)rr;
+    o[4] = (float)((double)h5 / 5.0);  o[5] = (float)((double)h10 / 10.0);
+    o[6] = (float)((double)h5 / (double)n_correct); o[7] = (float)((double)h10 / (double)n_correct);
+    a.used[u] = 1;
+}
+
+// d_U / d_V on the device, everything else on the host. out_measures: n_users x 8 = {AUC, MAP, NDCG, MRR, prec@5,
+// prec@10, recall@5, recall@10} of each user; out_used: 1 = counted, 0 = skipped by the reference's rules.
+int32_t items_eval_device(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
+                          const int32_t* users, int64_t n_users, const int32_t* candidates, int64_t n_cand,
+                          const int64_t* test_ptr, const int32_t* test_idx,
+                          const int64_t* ignore_ptr, const int32_t* ignore_idx, int32_t n,
+                          float* out_measures, int32_t* out_used, int64_t* launches)
+{
+    cudaStream_t s = ctx->stream;
+    if (n_users == 0) return MML_OK;
+    MML_CHECK(n_cand > 0 && n_cand < ((int64_t)1 << 31), MML_ERR_ARG, "items_evaluate: bad candidate count");
+    int32_t max_id = n_model_items - 1;
+    for (int64_t c = 0; c < n_cand; c++) max_id = std::max(max_id, candidates[c]);
+    const int32_t n_pos_of = max_id + 1;
+    std::vector<int32_t> pos_of((size_t)std::max(n_pos_of, 1), -1), next((size_t)n_cand, -1);
+    for (int64_t c = 0; c < n_cand; c++) {
+        const int32_t item = candidates[c];
+        MML_CHECK(item >= 0, MML_ERR_ARG, "items_evaluate: negative candidate id");
+        MML_CHECK(pos_of[item] < 0, MML_ERR_ARG, "items_evaluate: candidate %d is listed twice", item);
+        pos_of[item] = (int32_t)c;
+    }
+    const int64_t n_test = test_ptr[n_users];
+    const int64_t n_ign = (ignore_ptr && ignore_idx) ? ignore_ptr[n_users] : 0;
+    DevBuf<int32_t> d_cand, d_pos_of, d_next, d_users, d_ign_idx, d_test_idx, d_cp, d_sp, d_used;
+    DevBuf<int64_t> d_ign_ptr, d_test_ptr;
+    DevBuf<float> d_cs, d_ss, d_out;
+    DevBuf<uint32_t> d_bucket;
+    MML_TRY(d_cand.alloc(n_cand)); MML_TRY(d_pos_of.alloc(pos_of.size())); MML_TRY(d_next.alloc(n_cand));
+    MML_TRY(d_users.alloc(n_users)); MML_TRY(d_test_ptr.alloc(n_users + 1)); MML_TRY(d_test_idx.alloc(n_test));
+    MML_TRY(d_cp.alloc(n_test)); MML_TRY(d_sp.alloc(n_test)); MML_TRY(d_cs.alloc(n_test)); MML_TRY(d_ss.alloc(n_test));
+    MML_TRY(d_bucket.alloc(n_test + n_users)); MML_TRY(d_out.alloc((size_t)n_users * 8)); MML_TRY(d_used.alloc(n_users));
+    MML_CUDA(cudaMemcpyAsync(d_cand.p, candidates, sizeof(int32_t) * n_cand, cudaMemcpyHostToDevice, s));
+    MML_CUDA(cudaMemcpyAsync(d_pos_of.p, pos_of.data(), sizeof(int32_t) * pos_of.size(), cudaMemcpyHostToDevice, s));
+    MML_CUDA(cudaMemcpyAsync(d_next.p, next.data(), sizeof(int32_t) * n_cand, cudaMemcpyHostToDevice, s));
+    MML_CUDA(cudaMemcpyAsync(d_users.p, users, sizeof(int32_t) * n_users, cudaMemcpyHostToDevice, s));
+    MML_CUDA(cudaMemcpyAsync(d_test_ptr.p, test_ptr, sizeof(int64_t) * (n_users + 1), cudaMemcpyHostToDevice, s));
+    if (n_test > 0) MML_CUDA(cudaMemcpyAsync(d_test_idx.p, test_idx, sizeof(int32_t) * n_test, cudaMemcpyHostToDevice, s));
+    if (n_ign > 0) {
+        MML_TRY(d_ign_ptr.alloc(n_users + 1)); MML_TRY(d_ign_idx.alloc(n_ign));
+        MML_CUDA(cudaMemcpyAsync(d_ign_ptr.p, ignore_ptr, sizeof(int64_t) * (n_users + 1), cudaMemcpyHostToDevice, s));
+        MML_CUDA(cudaMemcpyAsync(d_ign_idx.p, ignore_idx, sizeof(int32_t) * n_ign, cudaMemcpyHostToDevice, s));
+    }
+    int64_t B = std::max<int64_t>(1, ((int64_t)1 << 28) / n_cand);      // score buffer <= 1 GiB
+    B = std::min<int64_t>(std::min<int64_t>(B, n_users), 65535 * (int64_t)TS);
+    DevBuf<float> d_scores;
+    MML_TRY(d_scores.alloc((size_t)B * n_cand));
+    EvalArgs a{};
+    a.scores = d_scores.p; a.n_cand = n_cand; a.n = n; a.pos_of = d_pos_of.p; a.n_pos_of = n_pos_of;
+    a.test_ptr = d_test_ptr.p; a.test_idx = d_test_idx.p;
+    a.c_score = d_cs.p; a.c_pos = d_cp.p; a.s_score = d_ss.p; a.s_pos = d_sp.p; a.bucket = d_bucket.p;
+    a.out = d_out.p; a.used = d_used.p;
+    for (int64_t b_lo = 0; b_lo < n_users; b_lo += B) {
+        const int32_t nb = (int32_t)std::min<int64_t>(B, n_users - b_lo);
+        dim3 grid((unsigned)ceil_div(n_cand, TS), (unsigned)ceil_div(nb, TS));
+        score_tile_kernel<<<grid, 256, 0, s>>>(d_U, n_model_users, d_V, n_model_items, k, d_users.p + b_lo, nb, d_cand.p, n_cand, d_scores.p);
+        if (n_ign > 0)
+            mask_ignored_kernel<<<nb, 128, 0, s>>>(d_ign_ptr.p, d_ign_idx.p, (int32_t)b_lo, nb, d_pos_of.p, n_pos_of, d_next.p, n_cand, d_scores.p);
+        a.b_lo = b_lo;
+        items_eval_kernel<<<nb, EVAL_T, 0, s>>>(a);
+        MML_CUDA(cudaGetLastError());
+        if (launches) *launches += 3;
+    }
+    MML_CUDA(cudaMemcpyAsync(out_measures, d_out.p, sizeof(float) * (size_t)n_users * 8, cudaMemcpyDeviceToHost, s));
+    MML_CUDA(cudaMemcpyAsync(out_used, d_used.p, sizeof(int32_t) * n_users, cudaMemcpyDeviceToHost, s));
+    MML_CUDA(cudaStreamSynchronize(s));
+    for (int64_t u = 0; u < n_users; u++)
+        MML_CHECK(out_used[u] >= 0, MML_ERR_ARG, "items_evaluate: user %d has test items among its ignored (training) items "
+                  "(AUC.Compute throws \"Should not happen.\")", users[u]);
+    return MML_OK;
+}
+
 }  // namespace mml
 
 using namespace mml;
@@ -438,4 +627,28 @@ extern "C" int32_t mml_topn_mf(mml_ctx* hctx, const float* user_factors, int32_t
     MML_CUDA(cudaMemcpyAsync(dV.p, item_factors, sizeof(float) * (size_t)n_model_items * k, cudaMemcpyHostToDevice, s));
     return topn_device(ctx, dU.p, n_model_users, dV.p, n_model_items, k, users, n_users, n, candidates, n_cand,
                        ignore_ptr, ignore_idx, out_items, out_scores, out_counts, nullptr);
+}
+
+extern "C" int32_t mml_items_evaluate_mf(mml_ctx* hctx, const float* user_factors, int32_t n_model_users,
+                                         const float* item_factors, int32_t n_model_items, int32_t k,
+                                         const int32_t* test_users, int64_t n_test_users,
+                                         const int32_t* candidates, int64_t n_cand,
+                                         const int64_t* test_ptr, const int32_t* test_idx,
+                                         const int64_t* ignore_ptr, const int32_t* ignore_idx, int32_t n,
+                                         float* out_measures, int32_t* out_used)
+{
+    MML_CHECK(hctx && user_factors && item_factors && candidates && test_ptr &&
+              (n_test_users == 0 || (test_users && out_measures && out_used)), MML_ERR_ARG, "mml_items_evaluate_mf: NULL argument");
+    MML_CHECK(k >= 1 && n_model_users >= 0 && n_model_items >= 0 && n_test_users >= 0 && (n > 0 || n == -1), MML_ERR_ARG,
+              "mml_items_evaluate_mf: bad sizes (n must be > 0 or -1)");
+    MML_CHECK(test_ptr[n_test_users] == 0 || test_idx, MML_ERR_ARG, "mml_items_evaluate_mf: NULL test_idx");
+    Ctx* ctx = ctx_of(hctx);
+    MML_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    DevBuf<float> dU, dV;
+    MML_TRY(dU.alloc((size_t)n_model_users * k)); MML_TRY(dV.alloc((size_t)n_model_items * k));
+    MML_CUDA(cudaMemcpyAsync(dU.p, user_factors, sizeof(float) * (size_t)n_model_users * k, cudaMemcpyHostToDevice, s));
+    MML_CUDA(cudaMemcpyAsync(dV.p, item_factors, sizeof(float) * (size_t)n_model_items * k, cudaMemcpyHostToDevice, s));
+    return items_eval_device(ctx, dU.p, n_model_users, dV.p, n_model_items, k, test_users, n_test_users, candidates, n_cand,
+                             test_ptr, test_idx, ignore_ptr, ignore_idx, n, out_measures, out_used, nullptr);
 }

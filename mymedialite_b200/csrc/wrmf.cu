@@ -394,6 +394,11 @@ static int32_t half_sweep(Wrmf& m, const uint32_t* row_ptr, const int32_t* cols,
 }
 
 Feedback* feedback_of(mml_feedback* h);
+int32_t items_eval_device(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
+                          const int32_t* users, int64_t n_users, const int32_t* candidates, int64_t n_cand,
+                          const int64_t* test_ptr, const int32_t* test_idx,
+                          const int64_t* ignore_ptr, const int32_t* ignore_idx, int32_t n,
+                          float* out_measures, int32_t* out_used, int64_t* launches);
 int32_t topn_device(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
                     const int32_t* users, int64_t n_users, int32_t n, const int32_t* candidates, int64_t n_cand,
                     const int64_t* ignore_ptr, const int32_t* ignore_idx,
@@ -640,6 +645,24 @@ extern "C" int32_t mml_wrmf_stats(mml_wrmf* h, int64_t* kernel_launches, float* 
 }
 
 // Recommend() on the device-resident WRMF model (Recommender.cs:52-103 with ItemRecommendation/MF.cs:151-157 scores)
+extern "C" int32_t mml_wrmf_evaluate(mml_wrmf* h, const int32_t* test_users, int64_t n_test_users,
+                                     const int32_t* candidates, int64_t n_cand,
+                                     const int64_t* test_ptr, const int32_t* test_idx,
+                                     const int64_t* ignore_ptr, const int32_t* ignore_idx, int32_t n,
+                                     float* out_measures, int32_t* out_used)
+{
+    MML_CHECK(h && candidates && test_ptr && (n_test_users == 0 || (test_users && out_measures && out_used)), MML_ERR_ARG,
+              "mml_wrmf_evaluate: NULL argument");
+    MML_CHECK((n > 0 || n == -1) && n_test_users >= 0, MML_ERR_ARG, "mml_wrmf_evaluate: n must be > 0 or -1");
+    MML_CHECK(test_ptr[n_test_users] == 0 || test_idx, MML_ERR_ARG, "mml_wrmf_evaluate: NULL test_idx");
+    Wrmf& m = h->m;
+    MML_CHECK(m.has_model, MML_ERR_STATE, "mml_wrmf_evaluate: no model");
+    MML_CUDA(cudaSetDevice(m.ctx->device));
+    return items_eval_device(m.ctx, m.U.p, m.fb->n_users(), m.V.p, m.fb->n_items(), m.k, test_users, n_test_users,
+                             candidates, n_cand, test_ptr, test_idx, ignore_ptr, ignore_idx, n, out_measures, out_used,
+                             &m.launches);
+}
+
 extern "C" int32_t mml_wrmf_recommend(mml_wrmf* h, const int32_t* users, int64_t n_users, int32_t n,
                                       const int32_t* candidates, int64_t n_cand,
                                       const int64_t* ignore_ptr, const int32_t* ignore_idx,

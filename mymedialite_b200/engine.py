@@ -304,6 +304,32 @@ def topn_mf(ctx, U, V, users, n=-1, candidates=None, ignore_lists=None):
     return [(oi[b, :oc[b]].copy(), os_[b, :oc[b]].copy()) for b in range(users.shape[0])]
 
 
+ITEM_MEASURES = ["AUC", "MAP", "NDCG", "MRR", "prec@5", "prec@10", "recall@5", "recall@10"]   # Eval/Items.cs:37-49
+
+
+def _rows_csr(rows, n_users):
+    """Rows given either as a list of per-user id sequences or as a ready (ptr, idx) pair."""
+    if rows is None:
+        return None, None
+    if isinstance(rows, tuple) and len(rows) == 2 and isinstance(rows[0], np.ndarray):
+        ptr, idx = np.ascontiguousarray(rows[0], np.int64), _i32(rows[1])
+        return ptr, (idx if idx.size else np.zeros(1, np.int32))
+    return _ignore_csr(rows, n_users)
+
+
+def items_evaluate_mf(ctx, U, V, test_users, candidates, test_rows, ignore_rows=None, n=-1):
+    """Per-user ranking measures (mml_items_evaluate_mf). Returns (measures [n_users, 8] float32, used [n_users] int32)."""
+    U, V = _f32(U), _f32(V)
+    users, cand = _i32(test_users), _i32(candidates)
+    tp, ti = _rows_csr(test_rows, users.shape[0])
+    ip, ii = _rows_csr(ignore_rows, users.shape[0])
+    out = np.zeros((max(users.shape[0], 1), 8), np.float32)
+    used = np.zeros(max(users.shape[0], 1), np.int32)
+    check(ctx.lib.mml_items_evaluate_mf(ctx.h, U, U.shape[0], V, V.shape[0], U.shape[1], users, users.shape[0], cand,
+                                        cand.shape[0], tp, ti, ip, ii, int(n), out, used))
+    return out[:users.shape[0]], used[:users.shape[0]]
+
+
 class DeviceFeedback:
     """PosOnlyFeedback resident in HBM: user and item matrices as CSR, duplicate events collapsed."""
 
@@ -402,6 +428,16 @@ class WrmfModel:
         ptr, idx = _ignore_csr(ignore_lists, users.shape[0])
         check(self.lib.mml_wrmf_recommend(self.h, users, users.shape[0], int(n), cand, n_cand, ptr, idx, oi, os_, oc))
         return [(oi[b, :oc[b]].copy(), os_[b, :oc[b]].copy()) for b in range(users.shape[0])]
+
+    def evaluate(self, test_users, candidates, test_rows, ignore_rows=None, n=-1):
+        """mml_wrmf_evaluate on the device-resident model; see items_evaluate_mf."""
+        users, cand = _i32(test_users), _i32(candidates)
+        tp, ti = _rows_csr(test_rows, users.shape[0])
+        ip, ii = _rows_csr(ignore_rows, users.shape[0])
+        out = np.zeros((max(users.shape[0], 1), 8), np.float32)
+        used = np.zeros(max(users.shape[0], 1), np.int32)
+        check(self.lib.mml_wrmf_evaluate(self.h, users, users.shape[0], cand, cand.shape[0], tp, ti, ip, ii, int(n), out, used))
+        return out[:users.shape[0]], used[:users.shape[0]]
 
     def close(self):
         if self.h:

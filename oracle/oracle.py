@@ -475,3 +475,145 @@ def read_feedback_text(text, user_mapping=None, item_mapping=None, ignore_first_
         except FormatException:
             raise FormatException("Could not read line '%s'" % line)
     return np.array(users, np.int32), np.array(items, np.int32)
+
+
+# ---- ranking measures and Eval.Items.Evaluate (test infrastructure for items_eval_kernel) -----------------------------
+def auc_compute(ranked_items, relevant_items, num_dropped_items):
+    """Eval/Measures/AUC.cs:39-69."""
+    relevant = set(relevant_items)
+    num_relevant_items = len(relevant & set(ranked_items))
+    num_eval_items = len(ranked_items) + num_dropped_items
+    num_eval_pairs = (num_eval_items - num_relevant_items) * num_relevant_items
+    if num_eval_pairs < 0:
+        raise Exception("num_eval_pairs cannot be less than 0")
+    if num_eval_pairs == 0:
+        return 0.5
+    num_correct_pairs = 0
+    hit_count = 0
+    for item_id in ranked_items:
+        if item_id not in relevant:
+            num_correct_pairs += hit_count
+        else:
+            hit_count += 1
+    missing_relevant_items = len(relevant - set(ranked_items))
+    if num_dropped_items - missing_relevant_items < 0:
+        raise Exception("Should not happen.")
+    num_correct_pairs += hit_count * (num_dropped_items - missing_relevant_items)
+    return num_correct_pairs / num_eval_pairs
+
+
+def ap_compute(ranked_items, correct_items):
+    """Eval/Measures/PrecisionAndRecall.cs AP."""
+    correct = set(correct_items)
+    hit_count, avg_prec_sum = 0, 0.0
+    for i, item_id in enumerate(ranked_items):
+        if item_id in correct:
+            hit_count += 1
+            avg_prec_sum += hit_count / (i + 1)
+    return avg_prec_sum / len(correct) if hit_count != 0 else 0.0
+
+
+def hits_at(ranked_items, correct_items, n):
+    """PrecisionAndRecall.HitsAt."""
+    if n < 1:
+        raise ValueError("n must be at least 1.")
+    correct = set(correct_items)
+    hit_count = 0
+    for i, item_id in enumerate(ranked_items):
+        if item_id not in correct:
+            continue
+        if i < n:
+            hit_count += 1
+        else:
+            break
+    return hit_count
+
+
+def precision_at(ranked_items, correct_items, n):
+    return hits_at(ranked_items, correct_items, n) / n
+
+
+def recall_at(ranked_items, correct_items, n):
+    return hits_at(ranked_items, correct_items, n) / len(set(correct_items))
+
+
+def ndcg_compute(ranked_items, correct_items):
+    """Eval/Measures/NDCG.cs (Math.Log(x, 2) = Log(x) / Log(2))."""
+    import math
+    correct = set(correct_items)
+    dcg = 0.0
+    idcg = 0.0
+    for i in range(len(correct)):
+        idcg += 1 / (math.log(i + 2) / math.log(2))
+    for i, item_id in enumerate(ranked_items):
+        if item_id not in correct:
+            continue
+        dcg += 1 / (math.log(i + 2) / math.log(2))
+    return dcg / idcg
+
+
+def reciprocal_rank(ranked_items, correct_items):
+    """Eval/Measures/ReciprocalRank.cs."""
+    correct = set(correct_items)
+    for pos, item_id in enumerate(ranked_items):
+        if item_id in correct:
+            return 1.0 / (pos + 1)
+    return 0.0
+
+
+ITEM_MEASURES = ["AUC", "MAP", "NDCG", "MRR", "prec@5", "prec@10", "recall@5", "recall@10"]
+
+
+def first_seen(ids):
+    """HashSet<int> filled in order and copied out (Data/DataSet.cs:112-131): distinct ids in order of first appearance."""
+    seen, out = set(), []
+    for x in ids:
+        x = int(x)
+        if x not in seen:
+            seen.add(x)
+            out.append(x)
+    return out
+
+
+def items_evaluate(recommend, test_users_ids, test_items_ids, train_users_ids, train_items_ids, test_users=None,
+                   candidate_items=None, repeated_events=False, n=-1):
+    """Eval/Items.cs:126-209 with the candidate list already fixed by the caller (Items.Candidates + its shuffle).
+    recommend(user, n, ignore_items, candidate_items) -> [(item, score)] as Recommender.Recommend.
+    Returns (results dict, per-user rows) -- the sums are float32 additions in test_users order (single-threaded order)."""
+    test_rows, train_rows = {}, {}
+    for u, i in zip(test_users_ids, test_items_ids):
+        test_rows.setdefault(int(u), set()).add(int(i))
+    for u, i in zip(train_users_ids, train_items_ids):
+        train_rows.setdefault(int(u), set()).add(int(i))
+    if test_users is None:
+        test_users = first_seen(test_users_ids)
+    cand_set = set(int(c) for c in candidate_items)
+    sums = {m: np.float32(0) for m in ITEM_MEASURES}
+    rows = {}
+    num_users = 0
+    for user_id in test_users:
+        correct_items = test_rows.get(user_id, set()) & cand_set
+        if len(correct_items) == 0:
+            continue
+        ignore = set() if repeated_events else set(train_rows.get(user_id, set()))
+        ignore &= cand_set
+        num_candidates_for_this_user = len(candidate_items) - len(ignore)
+        if len(correct_items) == num_candidates_for_this_user:
+            continue
+        prediction = recommend(user_id, n, ignore, candidate_items)
+        prediction_list = [t[0] for t in prediction]
+        num_dropped_items = num_candidates_for_this_user - len(prediction)
+        row = [auc_compute(prediction_list, correct_items, num_dropped_items), ap_compute(prediction_list, correct_items),
+               ndcg_compute(prediction_list, correct_items), reciprocal_rank(prediction_list, correct_items),
+               precision_at(prediction_list, correct_items, 5), precision_at(prediction_list, correct_items, 10),
+               recall_at(prediction_list, correct_items, 5), recall_at(prediction_list, correct_items, 10)]
+        num_users += 1
+        rows[user_id] = np.array(row, np.float32)
+        for m, x in zip(ITEM_MEASURES, row):
+            sums[m] = np.float32(sums[m] + np.float32(x))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        result = {m: np.float32(sums[m] / np.float32(num_users)) for m in ITEM_MEASURES}
+    result["num_users"] = num_users
+    result["num_lists"] = num_users
+    result["num_items"] = len(candidate_items)
+    return result, rows
