@@ -265,15 +265,16 @@ def run_ours(args):
         except Exception:
             pass
     if not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(args, d, k)
+        out["cpu_baseline"], out["rmse_vs_ref"] = cpu_baseline(args, d, k, ctx)
     print(json.dumps(out), flush=True)
     if dist is not None:
         dist.barrier()
 
 
-def cpu_baseline(args, d, k):
+def cpu_baseline(args, d, k, ctx=None):
     """The oracle's restatement of BiasedMatrixFactorization.Iterate timed on this box's host cores:
-    single-threaded (MaxThreads=1) over a bounded prefix of the workload."""
+    single-threaded (MaxThreads=1) over a bounded prefix of the workload. The same prefix, from the same initial
+    factors, then runs one epoch of the GPU's default schedule: "test RMSE vs ref" of the metric (gate 0.5 %)."""
     from oracle import oracle as O
     u, i, v = d["train"]
     m = min(u.size, args.cpu_sample)
@@ -281,13 +282,32 @@ def cpu_baseline(args, d, k):
     om = O.Model(us, is_, vs, biased=True, num_factors=k, max_user=int(us.max()), max_item=d["n_items"] - 1)
     rng = O.Random(1)
     om.init(rng)
+    U0, V0 = om.user_factors.copy(), om.item_factors.copy()
     t0 = time.time()
     om.iterate(rng)
     dt = time.time() - t0
-    return {"value": m / dt, "unit": "ratings/s", "cores": 1, "kind": "port",
+    base = {"value": m / dt, "unit": "ratings/s", "cores": 1, "kind": "port",
             "sample": "one single-threaded epoch (MaxThreads=1 order) over the first %d ratings of the workload; "
                       "C restatement of the reference loop (no Mono/.NET in this image)" % m,
             "seconds": round(dt, 2)}
+    check = None
+    if ctx is not None:
+        from mymedialite_b200 import engine
+        tu, ti, tv = d["test"]
+        mt = min(tu.size, max(m // 9, 1))
+        tu, ti, tv = tu[:mt], ti[:mt], tv[:mt]
+        r = engine.DeviceRatings(ctx, us, is_, vs, max_user=int(us.max()), max_item=d["n_items"] - 1)
+        gm = engine.SgdModel(ctx, r, engine.default_params(biased=1, num_factors=k, num_subgroups=args.subgroups))
+        gm.set_model(U0, V0)
+        gm.iterate(np.random.RandomState(2).permutation(gm.strata_info()["G"]).astype(np.int32))
+        g_tr, g_te = gm.evaluate_train()["RMSE"], gm.evaluate(tu, ti, tv)["RMSE"]
+        o_tr, o_te = om.evaluate(us, is_, vs)["RMSE"], om.evaluate(tu, ti, tv)["RMSE"]
+        check = {"gpu": {"train": g_tr, "test": g_te}, "ref": {"train": o_tr, "test": o_te},
+                 "rel_diff": {"train": abs(g_tr - o_tr) / o_tr, "test": abs(g_te - o_te) / o_te}, "gate": 0.005,
+                 "sample": "one epoch from identical initial factors on the cpu_baseline prefix (%d ratings), %d test ratings; "
+                           "GPU: default parallel schedule, ref: oracle in the reference's single-threaded order" % (m, mt)}
+        gm.close(); r.close()
+    return base, check
 
 
 def run_reference(args):

@@ -18,7 +18,7 @@ using MyMediaLite.Native;
 namespace MyMediaLite.RatingPrediction
 {
 	/// <summary>MatrixFactorization on the GPU: r = global_bias + p_u . q_i, SGD (MatrixFactorization.cs:166-196)</summary>
-	public class CudaMatrixFactorization : RatingPredictor, IIterativeModel
+	public class CudaMatrixFactorization : RatingPredictor, IIterativeModel, IFoldInRatingPredictor
 	{
 		/// <summary>the device model; shared by clones, replaced (never mutated in place) by Train()</summary>
 		protected MmlHandle model, dev_ratings;
@@ -120,6 +120,88 @@ namespace MyMediaLite.RatingPrediction
 			return (float) v;
 		}
 
+		/// <summary>length of a fold-in vector: the biased model puts the user bias in front (BiasedMatrixFactorization.cs:80-82)</summary>
+		protected int FoldInStride { get { return (int) NumFactors + (Biased ? 1 : 0); } }
+
+		/// <summary>RetrainUser (MatrixFactorization.cs:141-149, BiasedMatrixFactorization.cs:419-424): re-draw the row, zero the bias,
+		/// one pass over ByUser[user_id] updating the user side only</summary>
+		public virtual void RetrainUser(int user_id) { Retrain(user_id, false, ratings.ByUser[user_id]); }
+
+		/// <summary>RetrainItem (MatrixFactorization.cs:152-160, BiasedMatrixFactorization.cs:426-431)</summary>
+		public virtual void RetrainItem(int item_id) { Retrain(item_id, true, ratings.ByItem[item_id]); }
+
+		void Retrain(int id, bool by_item, IList<int> indices)
+		{
+			lock (gate)
+			{
+				var row = new float[NumFactors];
+				row.InitNormal(InitMean, InitStdDev);
+				Mml.Check(Mml.mml_sgd_set_rows(model.DangerousGetHandle(), by_item ? 1 : 0, new int[] { id }, 1, row, Biased ? new float[] { 0 } : null));
+				var idx = indices.ToArray();
+				Mml.Check(Mml.mml_sgd_iterate_indices(model.DangerousGetHandle(), idx, idx.Length, by_item ? 0 : 1, by_item ? 1 : 0));
+			}
+		}
+
+		/// <summary>FoldIn (MatrixFactorization.cs:323-347, BiasedMatrixFactorization.cs:445-492): the vector and the shuffle are drawn
+		/// here (same RNG order as the reference), the SGD passes run on the device</summary>
+		protected virtual float[] FoldIn(IList<Tuple<int, float>> rated_items)
+		{
+			var init = new float[NumFactors];
+			init.InitNormal(InitMean, InitStdDev);
+			rated_items.Shuffle();
+			var items = rated_items.Select(t => t.Item1).ToArray();
+			var values = rated_items.Select(t => t.Item2).ToArray();
+			var result = new float[FoldInStride];
+			Mml.Check(Mml.mml_sgd_fold_in(model.DangerousGetHandle(), new long[] { 0, items.Length }, items, values, 1, init, (int) NumIter, result));
+			return result;
+		}
+
+		/// <summary>ScoreItems (MatrixFactorization.cs:350-363)</summary>
+		public IList<Tuple<int, float>> ScoreItems(IList<Tuple<int, float>> rated_items, IList<int> candidate_items)
+		{
+			var user_vector = FoldIn(rated_items);
+			var cand = candidate_items.ToArray();
+			var scores = new float[cand.Length];
+			Mml.Check(Mml.mml_sgd_score_items(model.DangerousGetHandle(), user_vector, 1, cand, cand.Length, scores));
+			var result = new Tuple<int, float>[cand.Length];
+			for (int i = 0; i < cand.Length; i++) result[i] = Tuple.Create(cand[i], scores[i]);
+			return result;
+		}
+
+		/// <summary>LoadModel (MatrixFactorization.cs:386-408): the factors go to a fresh device model</summary>
+		public override void LoadModel(string filename)
+		{
+			using (StreamReader reader = Model.GetReader(filename, this.GetType()))
+			{
+				var bias = float.Parse(reader.ReadLine(), CultureInfo.InvariantCulture);
+				var user_factors = (Matrix<float>) reader.ReadMatrix(new Matrix<float>(0, 0));
+				var item_factors = (Matrix<float>) reader.ReadMatrix(new Matrix<float>(0, 0));
+				if (user_factors.NumberOfColumns != item_factors.NumberOfColumns)
+					throw new IOException(string.Format("Number of user and item factors must match: {0} != {1}", user_factors.NumberOfColumns, item_factors.NumberOfColumns));
+				Adopt(user_factors, item_factors, null, null, bias, MinRating, MaxRating);
+			}
+		}
+
+		/// <summary>a model without training data: one pseudo rating per id keeps every row (InitModel zeroes rows without ratings)</summary>
+		protected void Adopt(Matrix<float> U, Matrix<float> V, float[] bu, float[] bi, float bias, float min, float max)
+		{
+			lock (gate)
+			{
+				MaxUserID = U.NumberOfRows - 1; MaxItemID = V.NumberOfRows - 1; NumFactors = (uint) U.NumberOfColumns;
+				int n = Math.Max(U.NumberOfRows, V.NumberOfRows);
+				var uu = new int[n]; var ii = new int[n]; var vv = new float[n];
+				for (int t = 0; t < n; t++) { uu[t] = t % U.NumberOfRows; ii[t] = t % V.NumberOfRows; vv[t] = min; }
+				IntPtr ctx = Mml.Context(), r, m;
+				Mml.Check(Mml.mml_ratings_create(ctx, uu, ii, vv, n, MaxUserID, MaxItemID, out r));
+				dev_ratings = new MmlHandle(r, Mml.mml_ratings_destroy);
+				var p = Params(); p.schedule = Mml.SCHEDULE_SERIAL;
+				Mml.Check(Mml.mml_sgd_create(ctx, r, ref p, null, null, out m));
+				model = new MmlHandle(m, Mml.mml_sgd_destroy);
+				Mml.Check(Mml.mml_sgd_set_model(m, U.data, V.data, bu, bi));
+				Mml.Check(Mml.mml_sgd_set_scale(m, min, max, bias));
+			}
+		}
+
 		public override void SaveModel(string filename)
 		{
 			var U = new float[(MaxUserID + 1) * NumFactors]; var V = new float[(MaxItemID + 1) * NumFactors];
@@ -202,6 +284,27 @@ namespace MyMediaLite.RatingPrediction
 				writer.WriteMatrix(new Matrix<float>(nu, k) { data = U });
 				writer.WriteVector(bi);
 				writer.WriteMatrix(new Matrix<float>(ni, k) { data = V });
+			}
+		}
+
+		/// <summary>LoadModel (BiasedMatrixFactorization.cs:353-402)</summary>
+		public override void LoadModel(string filename)
+		{
+			using (StreamReader reader = Model.GetReader(filename, this.GetType()))
+			{
+				var bias = float.Parse(reader.ReadLine(), CultureInfo.InvariantCulture);
+				var min = float.Parse(reader.ReadLine(), CultureInfo.InvariantCulture);
+				var max = float.Parse(reader.ReadLine(), CultureInfo.InvariantCulture);
+				var bu = reader.ReadVector();
+				var user_factors = (Matrix<float>) reader.ReadMatrix(new Matrix<float>(0, 0));
+				var bi = reader.ReadVector();
+				var item_factors = (Matrix<float>) reader.ReadMatrix(new Matrix<float>(0, 0));
+				if (user_factors.NumberOfColumns != item_factors.NumberOfColumns)
+					throw new IOException(string.Format("Number of user and item factors must match: {0} != {1}", user_factors.NumberOfColumns, item_factors.NumberOfColumns));
+				if (bu.Count != user_factors.dim1 || bi.Count != item_factors.dim1)
+					throw new IOException("Number of biases must match the number of factor rows");
+				min_rating = min; max_rating = max;
+				Adopt(user_factors, item_factors, bu.ToArray(), bi.ToArray(), bias, min, max);
 			}
 		}
 

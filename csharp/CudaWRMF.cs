@@ -9,6 +9,7 @@ using System.Linq;
 using MyMediaLite.Data;
 using MyMediaLite.DataType;
 using MyMediaLite.IO;
+using MyMediaLite.Eval;
 using MyMediaLite.Native;
 
 namespace MyMediaLite.ItemRecommendation
@@ -62,6 +63,40 @@ namespace MyMediaLite.ItemRecommendation
 		public virtual void Iterate()
 		{
 			lock (gate) Mml.Check(Mml.mml_wrmf_iterate(model.DangerousGetHandle()));
+		}
+
+		/// <summary>RetrainUser / RetrainItem (WRMF.cs:159-170): Gram matrix of the other side + Optimize() for the one row</summary>
+		public void RetrainUser(int user_id) { lock (gate) Mml.Check(Mml.mml_wrmf_retrain(model.DangerousGetHandle(), 0, new int[] { user_id }, 1)); }
+		public void RetrainItem(int item_id) { lock (gate) Mml.Check(Mml.mml_wrmf_retrain(model.DangerousGetHandle(), 1, new int[] { item_id }, 1)); }
+
+		/// <summary>Eval.Items.Evaluate (Eval/Items.cs:126-209) in one device call: candidate selection (with its shuffle), the skip
+		/// rules' bookkeeping and the averaging stay here, ranking and measures run on the device without materialising the lists</summary>
+		public ItemRecommendationEvaluationResults Evaluate(IPosOnlyFeedback test, IPosOnlyFeedback training, IList<int> test_users = null,
+			IList<int> candidate_items = null, CandidateItems candidate_item_mode = CandidateItems.OVERLAP,
+			RepeatedEvents repeated_events = RepeatedEvents.No, int n = -1)
+		{
+			if (test_users == null) test_users = test.AllUsers;
+			var cand = Items.Candidates(candidate_items, candidate_item_mode, test, training).ToArray();
+			var users = test_users.ToArray();
+			Func<IPosOnlyFeedback, long[]> ptr_of = fb => { var p = new long[users.Length + 1]; for (int b = 0; b < users.Length; b++) p[b + 1] = p[b] + (users[b] <= fb.MaxUserID ? fb.UserMatrix[users[b]].Count : 0); return p; };
+			Func<IPosOnlyFeedback, long[], int[]> idx_of = (fb, p) => { var x = new int[Math.Max(p[users.Length], 1)]; for (int b = 0; b < users.Length; b++) if (users[b] <= fb.MaxUserID) fb.UserMatrix[users[b]].CopyTo(x, (int) p[b]); return x; };
+			var test_ptr = ptr_of(test); var test_idx = idx_of(test, test_ptr);
+			long[] ign_ptr = null; int[] ign_idx = null;
+			if (repeated_events == RepeatedEvents.No) { ign_ptr = ptr_of(training); ign_idx = idx_of(training, ign_ptr); }
+			var rows = new float[Math.Max(users.Length * 8, 1)]; var used = new int[Math.Max(users.Length, 1)];
+			lock (gate) Mml.Check(Mml.mml_wrmf_evaluate(model.DangerousGetHandle(), users, users.Length, cand, cand.Length, test_ptr, test_idx, ign_ptr, ign_idx, n, rows, used));
+			var result = new ItemRecommendationEvaluationResults();
+			string[] names = { "AUC", "MAP", "NDCG", "MRR", "prec@5", "prec@10", "recall@5", "recall@10" };
+			int num_users = 0;
+			for (int b = 0; b < users.Length; b++)
+			{
+				if (used[b] != 1) continue;
+				num_users++;
+				for (int j = 0; j < 8; j++) result[names[j]] += rows[b * 8 + j];
+			}
+			foreach (string measure in Items.Measures) result[measure] /= num_users;
+			result["num_users"] = num_users; result["num_lists"] = num_users; result["num_items"] = cand.Length;
+			return result;
 		}
 
 		public override float Predict(int user_id, int item_id)

@@ -60,6 +60,26 @@ namespace MyMediaLite.Native
 		[DllImport(LIB)] public static extern int mml_ctx_flush_l2(IntPtr ctx);
 		[DllImport(LIB)] public static extern int mml_ctx_sm_count(IntPtr ctx, out int sm_count);
 
+		// ingest (text file -> id mapping -> COO in pinned host memory)
+		public const int FILE_RATINGS = 0, FILE_RATINGS_NO_VALUE = 1, FILE_FEEDBACK = 2;
+		public const int MAP_IDENTITY = 0, MAP_FIRST_SEEN = 1;
+		public const int ERR_FORMAT = 6, ERR_IO = 7;
+		[DllImport(LIB)] public static extern int mml_ingest_file(string path, int kind, int user_mapping, int item_mapping, int ignore_first_line, int n_threads, IntPtr prior, out IntPtr ingest);
+		[DllImport(LIB)] public static extern int mml_ingest_text(byte[] text, long len, int kind, int user_mapping, int item_mapping, int ignore_first_line, int n_threads, IntPtr prior, out IntPtr ingest);
+		[DllImport(LIB)] public static extern int mml_ingest_destroy(IntPtr ingest);
+		[DllImport(LIB)] public static extern int mml_ingest_info(IntPtr ingest, out long n, out int max_user, out int max_item, out int n_user_ids, out int n_item_ids, out int pinned);
+		[DllImport(LIB)] public static extern int mml_ingest_copy(IntPtr ingest, [Out] int[] users, [Out] int[] items, [Out] float[] values);
+		[DllImport(LIB)] public static extern int mml_ingest_original_ids(IntPtr ingest, int which, int first, int count, [Out] byte[] buf, long buf_len, [Out] long[] offsets, out long needed);
+		[DllImport(LIB)] public static extern int mml_ingest_to_ratings(IntPtr ctx, IntPtr ingest, out IntPtr ratings);
+		[DllImport(LIB)] public static extern int mml_ingest_to_feedback(IntPtr ctx, IntPtr ingest, out IntPtr feedback);
+		/// <summary>MML_ERR_FORMAT -> FormatException with the reference's message, MML_ERR_IO -> IOException</summary>
+		public static void CheckIngest(int status)
+		{
+			if (status == ERR_FORMAT) throw new FormatException(LastError());
+			if (status == ERR_IO) throw new System.IO.IOException(LastError());
+			Check(status);
+		}
+
 		// rating matrix build
 		[DllImport(LIB)] public static extern int mml_ratings_create(IntPtr ctx, int[] users, int[] items, float[] values, long n, int max_user, int max_item, out IntPtr ratings);
 		[DllImport(LIB)] public static extern int mml_ratings_destroy(IntPtr ratings);
@@ -82,6 +102,9 @@ namespace MyMediaLite.Native
 		[DllImport(LIB)] public static extern int mml_sgd_invalidate_index(IntPtr model);
 		[DllImport(LIB)] public static extern int mml_sgd_iterate_indices(IntPtr model, int[] indices, long n, int update_user, int update_item);
 		[DllImport(LIB)] public static extern int mml_sgd_predict(IntPtr model, int[] users, int[] items, long n, [Out] float[] result);
+		[DllImport(LIB)] public static extern int mml_sgd_fold_in(IntPtr model, long[] rated_ptr, int[] rated_items, float[] rated_values, long n_users, float[] init_factors, int num_iter, [Out] float[] out_vectors);
+		[DllImport(LIB)] public static extern int mml_sgd_score_items(IntPtr model, float[] user_vectors, long n_users, int[] candidates, long n_cand, [Out] float[] out_scores);
+		[DllImport(LIB)] public static extern int mml_sgd_set_rows(IntPtr model, int by_item, int[] ids, long n, float[] factors, float[] biases);
 		[DllImport(LIB)] public static extern int mml_sgd_evaluate(IntPtr model, int[] users, int[] items, float[] values, long n, [Out] float[] out4);
 		[DllImport(LIB)] public static extern int mml_sgd_evaluate_train(IntPtr model, [Out] float[] out4);
 		[DllImport(LIB)] public static extern int mml_sgd_objective(IntPtr model, out double objective);
@@ -95,6 +118,9 @@ namespace MyMediaLite.Native
 		[DllImport(LIB)] public static extern int mml_topn_mf(IntPtr ctx, float[] user_factors, int n_model_users, float[] item_factors, int n_model_items, int k,
 			int[] users, long n_users, int n, int[] candidates, long n_cand, long[] ignore_ptr, int[] ignore_idx,
 			[Out] int[] out_items, [Out] float[] out_scores, [Out] int[] out_counts);
+		[DllImport(LIB)] public static extern int mml_items_evaluate_mf(IntPtr ctx, float[] user_factors, int n_model_users, float[] item_factors, int n_model_items, int k,
+			int[] test_users, long n_test_users, int[] candidates, long n_cand, long[] test_ptr, int[] test_idx, long[] ignore_ptr, int[] ignore_idx, int n,
+			[Out] float[] out_measures, [Out] int[] out_used);
 		[DllImport(LIB)] public static extern int mml_topn_set_mode(int mode);
 		[DllImport(LIB)] public static extern int mml_topn_last_stats(out long users_tensor_path, out long users_exact_path, out float tensor_path_ms);
 
@@ -109,6 +135,11 @@ namespace MyMediaLite.Native
 		[DllImport(LIB)] public static extern int mml_wrmf_init_model(IntPtr model, ulong seed, double init_mean, double init_stddev);
 		[DllImport(LIB)] public static extern int mml_wrmf_get_model(IntPtr model, [Out] float[] user_factors, [Out] float[] item_factors);
 		[DllImport(LIB)] public static extern int mml_wrmf_iterate(IntPtr model);
+		[DllImport(LIB)] public static extern int mml_wrmf_retrain(IntPtr model, int by_item, int[] ids, long n);
+		[DllImport(LIB)] public static extern int mml_wrmf_set_mode(int mode);
+		[DllImport(LIB)] public static extern int mml_wrmf_debug_gram(IntPtr model, [Out] float[] out_gram, out int out_user);
+		[DllImport(LIB)] public static extern int mml_wrmf_evaluate(IntPtr model, int[] test_users, long n_test_users, int[] candidates, long n_cand,
+			long[] test_ptr, int[] test_idx, long[] ignore_ptr, int[] ignore_idx, int n, [Out] float[] out_measures, [Out] int[] out_used);
 		[DllImport(LIB)] public static extern int mml_wrmf_stats(IntPtr model, out long kernel_launches, out float last_iterate_ms);
 		[DllImport(LIB)] public static extern int mml_wrmf_shard(IntPtr model, int by_item, [Out] int[] ranges);
 		[DllImport(LIB)] public static extern int mml_wrmf_recommend(IntPtr model, int[] users, long n_users, int n, int[] candidates, long n_cand, long[] ignore_ptr, int[] ignore_idx,

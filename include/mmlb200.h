@@ -325,6 +325,10 @@ int32_t mml_wrmf_get_model(mml_wrmf* m, float* user_factors, float* item_factors
 /* WRMF.Iterate (WRMF.cs:68-73): user half-sweep then item half-sweep. */
 int32_t mml_wrmf_iterate(mml_wrmf* m);
 int32_t mml_wrmf_stats(mml_wrmf* m, int64_t* kernel_launches, float* last_iterate_ms);
+/* RetrainUser / RetrainItem (WRMF.cs:159-170): the Gram matrix of the other side, then Optimize() for each given row --
+ * a half-sweep restricted to `ids` (users when by_item = 0, items when 1). On a multi-GPU context every rank solves the
+ * given rows itself (the model is replicated), no collective. */
+int32_t mml_wrmf_retrain(mml_wrmf* m, int32_t by_item, const int32_t* ids, int64_t n);
 /* Multi-GPU contexts (mml_ctx_create_dist): every rank passes the same feedback and model; in each half-sweep
  * (WRMF.cs:79-92, a Parallel.For over independent rows) rank r solves the contiguous rows
  * [ranges[r], ranges[r + 1]) -- balanced by events per row -- and the ranks all-gather the solved rows (NCCL), so

@@ -128,6 +128,7 @@ SIGNATURES = {
     "mml_wrmf_init_model": (C.c_int32, [vp, C.c_uint64, C.c_double, C.c_double]),
     "mml_wrmf_get_model": (C.c_int32, [vp, of32p, of32p]),
     "mml_wrmf_iterate": (C.c_int32, [vp]),
+    "mml_wrmf_retrain": (C.c_int32, [vp, C.c_int32, oi32p, C.c_int64]),
     "mml_wrmf_stats": (C.c_int32, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "mml_wrmf_shard": (C.c_int32, [vp, C.c_int32, C.POINTER(C.c_int32)]),
     "mml_wrmf_set_mode": (C.c_int32, [C.c_int32]),

@@ -599,6 +599,28 @@ extern "C" int32_t mml_wrmf_iterate(mml_wrmf* h)
     return MML_OK;
 }
 
+extern "C" int32_t mml_wrmf_retrain(mml_wrmf* h, int32_t by_item, const int32_t* ids, int64_t n)
+{
+    MML_CHECK(h && (n == 0 || ids), MML_ERR_ARG, "mml_wrmf_retrain: NULL argument");
+    Wrmf& m = h->m;
+    MML_CHECK(m.has_model, MML_ERR_STATE, "mml_wrmf_retrain: no model");
+    MML_CHECK(n >= 0 && n < ((int64_t)1 << 31), MML_ERR_ARG, "mml_wrmf_retrain: bad count");
+    if (n == 0) return MML_OK;
+    Feedback& f = *m.fb;
+    const int32_t n_rows = by_item ? f.n_items() : f.n_users();
+    for (int64_t t = 0; t < n; t++)
+        MML_CHECK(ids[t] >= 0 && ids[t] < n_rows, MML_ERR_ARG, "mml_wrmf_retrain: id %d out of range", ids[t]);
+    MML_CUDA(cudaSetDevice(m.ctx->device));
+    DevBuf<int32_t> d_ids;
+    MML_TRY(d_ids.alloc(n));
+    MML_CUDA(cudaMemcpyAsync(d_ids.p, ids, sizeof(int32_t) * n, cudaMemcpyHostToDevice, m.ctx->stream));
+    // WRMF.cs:159-170: ComputeSquareMatrix of the other side, then Optimize for the row -- a half-sweep over the given rows
+    if (by_item) MML_TRY(half_sweep(m, f.item_ptr.p, f.item_rows.p, d_ids.p, (int32_t)n, m.V.p, m.U.p, f.n_users()));
+    else MML_TRY(half_sweep(m, f.user_ptr.p, f.user_cols.p, d_ids.p, (int32_t)n, m.U.p, m.V.p, f.n_items()));
+    MML_CUDA(cudaStreamSynchronize(m.ctx->stream));
+    return MML_OK;
+}
+
 extern "C" int32_t mml_wrmf_set_mode(int32_t mode)
 {
     MML_CHECK(mode >= MML_WRMF_AUTO && mode <= MML_WRMF_TENSOR_F64, MML_ERR_ARG, "mml_wrmf_set_mode: unknown mode %d", mode);

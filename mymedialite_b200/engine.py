@@ -402,6 +402,11 @@ class WrmfModel:
     def iterate(self):
         check(self.lib.mml_wrmf_iterate(self.h))
 
+    def retrain(self, ids, by_item=False):
+        """RetrainUser / RetrainItem for a batch of rows (mml_wrmf_retrain)."""
+        ids = _i32(np.atleast_1d(ids))
+        check(self.lib.mml_wrmf_retrain(self.h, 1 if by_item else 0, ids, ids.shape[0]))
+
     def shard(self, by_item=False):
         """Multi-GPU: row ranges [ranges[r], ranges[r + 1]) each rank solves in the user (item) half-sweep."""
         r = (C.c_int32 * (self.ctx.world + 1))()

@@ -436,6 +436,14 @@ class WRMF(_Recommender):
         items, scores = self._model.recommend([user_id], n, candidate_items, ign)[0]
         return [(int(i), float(s)) for i, s in zip(items, scores)]
 
+    def RetrainUser(self, user_id):
+        """WRMF.cs:159-163."""
+        self._model.retrain([user_id], by_item=False)
+
+    def RetrainItem(self, item_id):
+        """WRMF.cs:166-170."""
+        self._model.retrain([item_id], by_item=True)
+
     def RecommendMany(self, users, n, ignore_lists=None, candidate_items=None):
         """The all-users loop of ItemRecommendation/Extensions.WritePredictions (:65-128) in one device call."""
         return self._model.recommend(users, n, candidate_items, ignore_lists)

@@ -76,3 +76,23 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "libmmloracle" not in text and "mml_oracle" not in text, f
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+
+
+def test_csharp_binding_declares_every_entry_point():
+    """csharp/NativeMethods.cs (the P/Invoke side a maintainer adds to MyMediaLite.dll) is not compiled here -- no .NET
+    toolchain -- so at least its DllImport list is held against the header: same names, same argument counts."""
+    cs = open(os.path.join(ROOT, "csharp", "NativeMethods.cs")).read()
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "mmlb200.h")).read(), flags=re.S)
+    imported = {}
+    for m in re.finditer(r"\[DllImport\(LIB\)\]\s*(?:public\s+)?static\s+extern\s+\w+\s+(mml_\w+)\s*\((.*?)\)\s*;", cs, flags=re.S):
+        args = re.sub(r"\[[^\]]*\]", "", m.group(2))            # drop [Out] / [In, Out] attributes
+        imported[m.group(1)] = 0 if not args.strip() else args.count(",") + 1
+    declared = {}
+    for m in re.finditer(r"\b(mml_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        args = m.group(2).strip()
+        declared[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    assert sorted(declared) == declared_functions()
+    missing = sorted(set(declared) - set(imported))
+    assert not missing, missing
+    wrong = {n: (imported[n], declared[n]) for n in declared if imported[n] != declared[n]}
+    assert not wrong, wrong

@@ -187,3 +187,36 @@ def test_wrmf_recommend_after_training(eng):
     for b, ((gi, gs), (wi, ws)) in enumerate(zip(got, want)):
         assert np.array_equal(gi, wi) and np.array_equal(gs.view(np.uint32), ws.view(np.uint32))
         assert not set(gi) & set(ign[b])
+
+
+@pytest.mark.parametrize("k", [12, 128])
+def test_wrmf_retrain_rows_match_oracle(eng, k):
+    """RetrainUser / RetrainItem (WRMF.cs:159-170): only the given rows change, to the reference's optimum given the
+    other side (rows are independent, so the oracle's full half-sweep on a copy supplies the expected rows)."""
+    engine, ctx = eng
+    nu, ni = 3000, 2500                                                   # both sides >= 16 k rows: tensor path at k = 128
+    u, i = events(nu, ni, 40000, 7 + k)
+    f = engine.DeviceFeedback(ctx, u, i, max_user=nu - 1, max_item=ni - 1)
+    rng = O.Random(5)
+    U = rng.init_normal(nu * k).reshape(nu, k); V = rng.init_normal(ni * k).reshape(ni, k)
+    m = engine.WrmfModel(ctx, f, k, 1.0, 0.015)
+    m.set_model(U, V)
+    uptr, ucols = O.feedback_csr(u, i, nu - 1)
+    iptr, irows = O.feedback_csr(i, u, ni - 1)
+    users = np.array([0, 17, 2999, 400], np.int32)
+    m.retrain(users, by_item=False)
+    Uo = U.copy()
+    O.wrmf_optimize(uptr, ucols, Uo, V, 1.0, 0.015)
+    Ug, Vg = m.get_model()
+    untouched = np.setdiff1d(np.arange(nu), users)
+    assert np.array_equal(Ug[untouched], U[untouched]) and np.array_equal(Vg, V)
+    scale = np.abs(Uo[users]).max(axis=1, keepdims=True) + 1e-12
+    assert (np.abs(Ug[users] - Uo[users]) / scale).max() < 1e-4
+    items = np.array([3, 1], np.int32)
+    m.retrain(items, by_item=True)
+    Vo = V.copy()
+    O.wrmf_optimize(iptr, irows, Vo, Ug, 1.0, 0.015)
+    _, Vg2 = m.get_model()
+    assert np.array_equal(np.delete(Vg2, items, axis=0), np.delete(V, items, axis=0))
+    scale = np.abs(Vo[items]).max(axis=1, keepdims=True) + 1e-12
+    assert (np.abs(Vg2[items] - Vo[items]) / scale).max() < 1e-4
