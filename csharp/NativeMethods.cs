@@ -122,6 +122,7 @@ namespace MyMediaLite.Native
 			int[] test_users, long n_test_users, int[] candidates, long n_cand, long[] test_ptr, int[] test_idx, long[] ignore_ptr, int[] ignore_idx, int n,
 			[Out] float[] out_measures, [Out] int[] out_used);
 		[DllImport(LIB)] public static extern int mml_topn_set_mode(int mode);
+		[DllImport(LIB)] public static extern int mml_topn_set_filter(int kind);
 		[DllImport(LIB)] public static extern int mml_topn_last_stats(out long users_tensor_path, out long users_exact_path, out float tensor_path_ms);
 
 		// WRMF

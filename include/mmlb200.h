@@ -281,6 +281,11 @@ int32_t mml_topn_mf(mml_ctx* ctx, const float* user_factors, int32_t n_model_use
  * Both paths return bit-identical results; EXACT / TENSOR force one of them (tests, benchmarks). */
 enum { MML_TOPN_AUTO = 0, MML_TOPN_EXACT = 1, MML_TOPN_TENSOR = 2 };
 int32_t mml_topn_set_mode(int32_t mode);
+/* Engine knob: operand precision of the tensor-core filter GEMM: TF32 (default) or BF16 (MMAs at twice the rate on half
+ * the operand bytes; its wider error bound, 0.0045 |u| max|v| against 0.0025, lengthens the list of finalists that are
+ * re-scored exactly). The results are the same bits either way. */
+enum { MML_TOPN_FILTER_BF16 = 0, MML_TOPN_FILTER_TF32 = 1 };
+int32_t mml_topn_set_filter(int32_t kind);
 /* Users served by each path in the last Recommend() call of this process and the device time of the tensor path. */
 int32_t mml_topn_last_stats(int64_t* users_tensor_path, int64_t* users_exact_path, float* tensor_path_ms);
 

@@ -117,6 +117,7 @@ SIGNATURES = {
     "mml_wrmf_evaluate": (C.c_int32, [vp, oi32p, C.c_int64, oi32p, C.c_int64, oi64p, oi32p, oi64p, oi32p, C.c_int32,
                                       of32p, oi32p]),
     "mml_topn_set_mode": (C.c_int32, [C.c_int32]),
+    "mml_topn_set_filter": (C.c_int32, [C.c_int32]),
     "mml_topn_last_stats": (C.c_int32, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "mml_feedback_create": (C.c_int32, [vp, oi32p, oi32p, C.c_int64, C.c_int32, C.c_int32, PP]),
     "mml_feedback_destroy": (C.c_int32, [vp]),
@@ -138,6 +139,7 @@ SIGNATURES = {
 }
 
 TOPN_AUTO, TOPN_EXACT, TOPN_TENSOR = 0, 1, 2
+TOPN_FILTER_BF16, TOPN_FILTER_TF32 = 0, 1
 WRMF_AUTO, WRMF_FP64, WRMF_TENSOR, WRMF_TENSOR_F64 = 0, 1, 2, 3
 
 _lib = None

@@ -314,6 +314,7 @@ static int32_t topn_exact_device(Ctx* ctx, const float* d_U, int32_t n_model_use
 }
 
 bool topn_tc_eligible(int32_t k, int32_t n, int64_t n_cand);
+void topn_tc_set_filter(int kind);
 int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
                     const int32_t* users, int64_t n_users, int32_t n, int32_t n_out, const int32_t* d_cand, int32_t n_cand,
                     bool has_invalid_cand, const int64_t* ignore_ptr, const int32_t* ignore_idx,
@@ -596,6 +597,13 @@ extern "C" int32_t mml_topn_set_mode(int32_t mode)
 {
     MML_CHECK(mode >= MML_TOPN_AUTO && mode <= MML_TOPN_TENSOR, MML_ERR_ARG, "mml_topn_set_mode: unknown mode %d", mode);
     g_topn_mode = mode;
+    return MML_OK;
+}
+
+extern "C" int32_t mml_topn_set_filter(int32_t kind)
+{
+    MML_CHECK(kind == MML_TOPN_FILTER_BF16 || kind == MML_TOPN_FILTER_TF32, MML_ERR_ARG, "mml_topn_set_filter: unknown kind %d", kind);
+    topn_tc_set_filter(kind);
     return MML_OK;
 }
 

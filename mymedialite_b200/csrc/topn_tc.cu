@@ -18,6 +18,7 @@
 // Results are therefore bit-identical to the exact path, whatever the tensor cores round.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <algorithm>
 #include <cfloat>
 #include <chrono>
@@ -27,13 +28,18 @@ namespace mml {
 
 constexpr int TC_ROWS = 256;                  // users per CTA: two 128-row MMA tiles sharing every V tile
 constexpr int TC_N = 128;                     // candidates per MMA tile
-constexpr int TC_KC = 32;                     // floats per K chunk = one 128-byte swizzle atom
+constexpr int TC_KC = 32;                     // TF32 filter: floats per K chunk = one 128-byte swizzle atom
+constexpr int TC_KC_BF16 = 64;                // BF16 filter: elements per K chunk (same 128 bytes)
 constexpr int TC_CHUNK_BYTES = 128 * 128;     // 128 rows x 128 bytes
 constexpr int TC_CAP = 128;                   // candidates collected per epilogue thread (2 threads per user and candidate split) before the user goes to the exact path
 constexpr int TC_SAMPLE = 16384;              // target size of the candidate sample the threshold comes from
 constexpr int TC_MAX_N = 16;                  // largest n served by this path
 constexpr int TC_THREADS = 576;               // warp 0: TMA, warp 1: MMA issue + TMEM, warps 2-17: epilogue (2 threads per user row)
 constexpr float TC_ERR_C = 0.0025f;           // |tf32 score - exact| <= TC_ERR_C * |u| * |v| (2^-9 truncation + slack)
+// BF16 filter: both operands are rounded to nearest bf16 (relative error <= 2^-9 each), so every product is off by at most
+// (2^-8 + 2^-18) |u_f v_f|; the fp32 accumulation of <= 128 products and the fp32 rounding of the exact sequential sum add
+// < 4e-5 sum|u_f v_f|; with Cauchy-Schwarz |approx - exact| <= 0.00395 |u| |v|. Slack on top:
+constexpr float TC_ERR_C_BF16 = 0.0045f;
 constexpr int TC_MAX_SPLITS = 32;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
@@ -78,6 +84,12 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
@@ -103,11 +115,15 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr)
 }
 // Instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128.
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((128u >> 4) << 24);
+// The same with A = B = BF16 (kind::f16; K = 16 per instruction = the same 32 bytes of a swizzled row as 8 TF32 values).
+constexpr uint32_t TC_IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((128u >> 4) << 24);
 
 struct TcArgs {
     int32_t n_rows;                 // users in the batch
     int32_t stride;                 // column j of the V panel is candidate position j * stride (1 when collecting)
-    int32_t kc;                     // K chunks (kp / 32)
+    int32_t kc;                     // K chunks (kp / elements per chunk)
+    int32_t epc;                    // elements per K chunk: 32 (TF32 panels) or 64 (BF16 panels)
+    int32_t bf16;                   // operand panels hold bf16 (kind::f16 MMAs) instead of fp32 (kind::tf32)
     int32_t stages;                 // V ring depth
     int32_t list_off;               // byte offset of the sampling lists behind the aligned operand area
     int32_t n_tiles, tiles_per_split, splits;
@@ -175,13 +191,13 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
             mbar_expect_tx(bar_u, 2u * a.kc * TC_CHUNK_BYTES);
             for (int h = 0; h < 2; h++)
                 for (int c = 0; c < a.kc; c++)
-                    tma_load_2d(smem_u + (uint32_t)(h * a.kc + c) * TC_CHUNK_BYTES, &map_u, bar_u, c * TC_KC, row0 + h * 128);
+                    tma_load_2d(smem_u + (uint32_t)(h * a.kc + c) * TC_CHUNK_BYTES, &map_u, bar_u, c * a.epc, row0 + h * 128);
             int stage = 0; uint32_t phase = 0;
             for (int t = t_begin; t < t_end; t++)
                 for (int c = 0; c < a.kc; c++) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u, a.err);
                     mbar_expect_tx(bar_full + 8 * stage, TC_CHUNK_BYTES);
-                    tma_load_2d(smem_v + (uint32_t)stage * TC_CHUNK_BYTES, &map_v, bar_full + 8 * stage, c * TC_KC, t * TC_N);
+                    tma_load_2d(smem_v + (uint32_t)stage * TC_CHUNK_BYTES, &map_v, bar_full + 8 * stage, c * a.epc, t * TC_N);
                     if (++stage == a.stages) { stage = 0; phase ^= 1u; }
                 }
         }
@@ -205,9 +221,15 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
                         const uint32_t ub = smem_u + (uint32_t)(h * a.kc + c) * TC_CHUNK_BYTES;
                         const uint32_t d = tmem_base + (uint32_t)((buf * 2 + h) * TC_N);
                         if (a.dbg & 2) continue;
+                        if (a.bf16) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; kk++)
-                            tc_mma_tf32(d, tc_smem_desc(ub + kk * 32), tc_smem_desc(vb + kk * 32), TC_IDESC, (c | kk) != 0 ? 1u : 0u);
+                            for (int kk = 0; kk < 4; kk++)
+                                tc_mma_bf16(d, tc_smem_desc(ub + kk * 32), tc_smem_desc(vb + kk * 32), TC_IDESC_BF16, (c | kk) != 0 ? 1u : 0u);
+                        } else {
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++)
+                                tc_mma_tf32(d, tc_smem_desc(ub + kk * 32), tc_smem_desc(vb + kk * 32), TC_IDESC, (c | kk) != 0 ? 1u : 0u);
+                        }
                     }
                     tc_commit(bar_empty + 8 * stage);          // frees the V chunk when these MMAs have read it
                     if (++stage == a.stages) { stage = 0; phase ^= 1u; }
@@ -319,18 +341,18 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * ((gi >> 1) & 1));
             }
         };
+        // n_groups is even (two groups per tile and thread). A tile's TMEM buffer is handed back as soon as its second
+        // group sits in registers -- before this warp blocks on the next tile's accumulators and before it examines the
+        // group -- so that the MMAs of tile t + 2 start while the second half of tile t is still being examined.
         if (n_groups > 0) fetch(0, va);
         for (int gi = 0; gi < n_groups; gi += 2) {
-            tc_ld_wait();                                   // va holds group gi
-            if (gi + 1 < n_groups) fetch(gi + 1, vb);
+            tc_ld_wait();                                   // va holds group gi (first group of its tile)
+            fetch(gi + 1, vb);                              // same tile: no barrier
             examine(gi, va);
-            release(gi);
-            if (gi + 1 < n_groups) {
-                tc_ld_wait();                               // vb holds group gi + 1
-                if (gi + 2 < n_groups) fetch(gi + 2, va);
-                examine(gi + 1, vb);
-                release(gi + 1);
-            }
+            tc_ld_wait();                                   // vb holds group gi + 1: the tile's buffer has been read
+            release(gi + 1);
+            if (gi + 2 < n_groups) fetch(gi + 2, va);       // waits for the next tile's MMAs
+            examine(gi + 1, vb);
         }
         if (MODE == 0) {
             // the user's two threads hold the m best of their halves of the sample (sorted): m-th best of the union
@@ -365,8 +387,9 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
 __global__ void tc_stage_rows_kernel(const float* __restrict__ src, int32_t n_src_rows, int32_t k,
                                      const int32_t* __restrict__ ids, int32_t id_stride, int32_t n, int32_t kp,
                                      float* __restrict__ dst, float* __restrict__ norm, uint8_t* __restrict__ ok,
-                                     uint32_t* __restrict__ max_norm_bits, uint32_t* __restrict__ bad)
+                                     uint32_t* __restrict__ max_norm_bits, uint32_t* __restrict__ bad, int bf16)
 {
+    __nv_bfloat16* dst16 = reinterpret_cast<__nv_bfloat16*>(dst);      // bf16 panels: kp elements of 2 bytes per row
     const int lane = threadIdx.x & 31;
     int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -376,7 +399,8 @@ __global__ void tc_stage_rows_kernel(const float* __restrict__ src, int32_t n_sr
         float ss = 0.f;
         for (int f = lane; f < kp; f += 32) {
             const float x = (valid && f < k) ? src[(size_t)id * k + f] : 0.f;
-            dst[(size_t)r * kp + f] = x;
+            if (bf16) dst16[(size_t)r * kp + f] = __float2bfloat16_rn(x);
+            else dst[(size_t)r * kp + f] = x;
             ss = fmaf(x, x, ss);
         }
 #pragma unroll
@@ -424,7 +448,7 @@ __global__ void tc_ignore_sorted_kernel(const int64_t* __restrict__ ptr, const u
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; t < total; t += stride)
-        if (t + 1 < ptr[row_of[t] + 1] && pos[t] > pos[t + 1]) atomicExch(unsorted, 1u);
+        if (t + 1 < ptr[row_of[t] + 1] && pos[t] > pos[t + 1]) *unsorted = 1u;   // every writer stores the same value
 }
 
 __global__ void tc_copy_u32_kernel(const uint32_t* __restrict__ src, int64_t total, uint32_t* __restrict__ dst)
@@ -434,13 +458,13 @@ __global__ void tc_copy_u32_kernel(const uint32_t* __restrict__ src, int64_t tot
     for (; t < total; t += stride) dst[t] = src[t];
 }
 
-// thr[b] = (m-th best sampled score) - 2 d, d2[b] = 2 d, d = TC_ERR_C * |u_b| * max|v| (+ underflow slack)
+// thr[b] = (m-th best sampled score) - 2 d, d2[b] = 2 d, d = err_c * |u_b| * max|v| (+ underflow slack)
 __global__ void tc_threshold_kernel(float* __restrict__ thr, float* __restrict__ d2, const float* __restrict__ unorm,
-                                    const uint32_t* __restrict__ vmax_bits, int32_t n_rows)
+                                    const uint32_t* __restrict__ vmax_bits, int32_t n_rows, float err_c)
 {
     const int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_rows) return;
-    const float dd = 2.f * (TC_ERR_C * unorm[b] * __uint_as_float(*vmax_bits) + 1e-30f);
+    const float dd = 2.f * (err_c * unorm[b] * __uint_as_float(*vmax_bits) + 1e-30f);
     d2[b] = dd;
     thr[b] = (dd < INFINITY) ? thr[b] - dd : -INFINITY;
 }
@@ -536,7 +560,7 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int32_t make_panel_map(CUtensorMap* map, float* base, int64_t rows, int32_t kp)
+static int32_t make_panel_map(CUtensorMap* map, float* base, int64_t rows, int32_t kp, bool bf16)
 {
     static encode_tiled_fn fn = nullptr;
     if (!fn) {
@@ -547,10 +571,10 @@ static int32_t make_panel_map(CUtensorMap* map, float* base, int64_t rows, int32
         fn = (encode_tiled_fn)p;
     }
     const cuuint64_t dims[2] = { (cuuint64_t)kp, (cuuint64_t)rows };
-    const cuuint64_t strides[1] = { (cuuint64_t)kp * sizeof(float) };
-    const cuuint32_t box[2] = { TC_KC, 128 };
+    const cuuint64_t strides[1] = { (cuuint64_t)kp * (bf16 ? 2 : 4) };
+    const cuuint32_t box[2] = { (cuuint32_t)(bf16 ? TC_KC_BF16 : TC_KC), 128 };
     const cuuint32_t estr[2] = { 1, 1 };
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MML_CHECK(r == CUDA_SUCCESS, MML_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return MML_OK;
@@ -561,6 +585,21 @@ static inline int tc_grid(int64_t n, int threads = 256)
     return (int)std::min<int64_t>(std::max<int64_t>(ceil_div(n, threads), 1), 148 * 16);
 }
 
+// Operand precision of the filter GEMM: TF32 (default) or BF16 (twice the tensor rate, half the operand bytes; the wider
+// error bound lengthens the exactly re-scored candidate list and sends more users to the exact path). Measured on config 5
+// (gpurun_out/pp_topn.csv, qq_topn_trace.log): the collecting pass is bound by operand staging, not by the MMA rate, so
+// BF16 gains 6 % there and loses it again in the finalize kernel. mml_topn_set_filter / MMLB200_TC_FILTER=bf16|tf32.
+static int g_tc_filter = -1;
+void topn_tc_set_filter(int kind) { g_tc_filter = kind; }
+bool topn_tc_filter_bf16()
+{
+    if (g_tc_filter < 0) {
+        const char* e = getenv("MMLB200_TC_FILTER");
+        g_tc_filter = (e && strcmp(e, "bf16") == 0) ? MML_TOPN_FILTER_BF16 : MML_TOPN_FILTER_TF32;
+    }
+    return g_tc_filter == MML_TOPN_FILTER_BF16;
+}
+
 bool topn_tc_eligible(int32_t k, int32_t n, int64_t n_cand)
 {
     return n >= 1 && n <= TC_MAX_N && k >= 1 && k <= 128 && n_cand >= 1 && n_cand < ((int64_t)1 << 30);
@@ -569,6 +608,8 @@ bool topn_tc_eligible(int32_t k, int32_t n, int64_t n_cand)
 // Candidate-side state of one Recommend() call, shared by all user batches.
 struct TcCandidates {
     int32_t n_cand = 0, kp = 0, kc = 0, stride = 1, n_samp = 0;
+    bool bf16 = false;                    // panels hold bf16 (kp elements of 2 bytes per row) instead of fp32
+    size_t row_floats() const { return bf16 ? (size_t)kp / 2 : (size_t)kp; }      // panel row length in 4-byte units
     int64_t cand_pad = 0, samp_pad = 0;
     bool has_bad = false;                 // some candidate id lies outside the model
     DevBuf<float> Vb, Vs;                 // all candidates / the strided sample, zero padded panels
@@ -582,20 +623,22 @@ static int32_t tc_prepare_candidates(Ctx* ctx, TcCandidates& c, const float* d_V
 {
     cudaStream_t s = ctx->stream;
     c.n_cand = n_cand; c.has_bad = has_invalid;
-    c.kp = (int32_t)ceil_div(k, TC_KC) * TC_KC; c.kc = c.kp / TC_KC;
+    const int32_t epc = c.bf16 ? TC_KC_BF16 : TC_KC;
+    c.kp = (int32_t)ceil_div(k, epc) * epc; c.kc = c.kp / epc;
+    const size_t rf = c.row_floats();
     c.cand_pad = ceil_div(n_cand, TC_N) * TC_N;
     // sample: every stride-th position; about n * stride candidates reach the threshold it yields
     c.stride = (int32_t)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_cand, TC_SAMPLE), std::max(1, 96 / n)));
     c.n_samp = (int32_t)ceil_div(n_cand, c.stride);
     c.samp_pad = ceil_div(c.n_samp, TC_N) * TC_N;
-    MML_TRY(c.Vb.alloc((size_t)c.cand_pad * c.kp)); MML_TRY(c.Vs.alloc((size_t)c.samp_pad * c.kp));
+    MML_TRY(c.Vb.alloc((size_t)c.cand_pad * rf)); MML_TRY(c.Vs.alloc((size_t)c.samp_pad * rf));
     MML_TRY(c.bad_b.alloc((size_t)c.cand_pad / 32)); MML_TRY(c.bad_s.alloc((size_t)c.samp_pad / 32)); MML_TRY(c.vmax.alloc(1));
     MML_CUDA(cudaMemsetAsync(c.bad_b.p, 0, c.bad_b.bytes(), s)); MML_CUDA(cudaMemsetAsync(c.bad_s.p, 0, c.bad_s.bytes(), s));
     MML_CUDA(cudaMemsetAsync(c.vmax.p, 0, sizeof(uint32_t), s));
-    if (c.cand_pad > n_cand) MML_CUDA(cudaMemsetAsync(c.Vb.p + (size_t)n_cand * c.kp, 0, sizeof(float) * (size_t)(c.cand_pad - n_cand) * c.kp, s));
-    if (c.samp_pad > c.n_samp) MML_CUDA(cudaMemsetAsync(c.Vs.p + (size_t)c.n_samp * c.kp, 0, sizeof(float) * (size_t)(c.samp_pad - c.n_samp) * c.kp, s));
-    tc_stage_rows_kernel<<<tc_grid((int64_t)n_cand * 32), 256, 0, s>>>(d_V, n_model_items, k, d_cand, 1, n_cand, c.kp, c.Vb.p, nullptr, nullptr, c.vmax.p, c.bad_b.p);
-    tc_stage_rows_kernel<<<tc_grid((int64_t)c.n_samp * 32), 256, 0, s>>>(d_V, n_model_items, k, d_cand, c.stride, c.n_samp, c.kp, c.Vs.p, nullptr, nullptr, nullptr, c.bad_s.p);
+    if (c.cand_pad > n_cand) MML_CUDA(cudaMemsetAsync(c.Vb.p + (size_t)n_cand * rf, 0, sizeof(float) * (size_t)(c.cand_pad - n_cand) * rf, s));
+    if (c.samp_pad > c.n_samp) MML_CUDA(cudaMemsetAsync(c.Vs.p + (size_t)c.n_samp * rf, 0, sizeof(float) * (size_t)(c.samp_pad - c.n_samp) * rf, s));
+    tc_stage_rows_kernel<<<tc_grid((int64_t)n_cand * 32), 256, 0, s>>>(d_V, n_model_items, k, d_cand, 1, n_cand, c.kp, c.Vb.p, nullptr, nullptr, c.vmax.p, c.bad_b.p, c.bf16 ? 1 : 0);
+    tc_stage_rows_kernel<<<tc_grid((int64_t)c.n_samp * 32), 256, 0, s>>>(d_V, n_model_items, k, d_cand, c.stride, c.n_samp, c.kp, c.Vs.p, nullptr, nullptr, nullptr, c.bad_s.p, c.bf16 ? 1 : 0);
     if (d_cand) {
         MML_TRY(c.pos_of.alloc(std::max(n_model_items, 1)));
         MML_CUDA(cudaMemsetAsync(c.pos_of.p, 0xff, c.pos_of.bytes(), s));
@@ -603,8 +646,8 @@ static int32_t tc_prepare_candidates(Ctx* ctx, TcCandidates& c, const float* d_V
     }
     MML_CUDA(cudaGetLastError());
     if (launches) *launches += 3;
-    MML_TRY(make_panel_map(&c.map_b, c.Vb.p, c.cand_pad, c.kp));
-    MML_TRY(make_panel_map(&c.map_s, c.Vs.p, c.samp_pad, c.kp));
+    MML_TRY(make_panel_map(&c.map_b, c.Vb.p, c.cand_pad, c.kp, c.bf16));
+    MML_TRY(make_panel_map(&c.map_s, c.Vs.p, c.samp_pad, c.kp, c.bf16));
     return MML_OK;
 }
 
@@ -630,7 +673,7 @@ static int32_t tc_alloc_work(Ctx* ctx, TcWork& w, const TcCandidates& c, int32_t
     splits = std::max(splits, 1);
     w.tps = (int)ceil_div(n_tiles, splits);
     w.splits = (int)ceil_div(n_tiles, w.tps);
-    MML_TRY(w.Ub.alloc((size_t)rows_pad * c.kp));
+    MML_TRY(w.Ub.alloc((size_t)rows_pad * c.row_floats()));
     MML_TRY(w.unorm.alloc(cap_users)); MML_TRY(w.thr.alloc(cap_users)); MML_TRY(w.d2.alloc(cap_users));
     MML_TRY(w.row_ok.alloc(cap_users)); MML_TRY(w.redo.alloc(cap_users)); MML_TRY(w.err.alloc(1));
     MML_TRY(w.buf_s.alloc((size_t)cap_users * w.splits * 2 * TC_CAP)); MML_TRY(w.buf_p.alloc((size_t)cap_users * w.splits * 2 * TC_CAP));
@@ -667,8 +710,9 @@ static int32_t topn_tc_batch(Ctx* ctx, TcCandidates& c, TcWork& w, const float* 
     const int32_t kp = c.kp, kc = c.kc;
     const int64_t rows_pad = ceil_div(n_users, TC_ROWS) * TC_ROWS;
     MML_CUDA(cudaMemsetAsync(w.err.p, 0, sizeof(uint32_t), s));
-    if (rows_pad > n_users) MML_CUDA(cudaMemsetAsync(w.Ub.p + (size_t)n_users * kp, 0, sizeof(float) * (size_t)(rows_pad - n_users) * kp, s));
-    tc_stage_rows_kernel<<<tc_grid((int64_t)n_users * 32), 256, 0, s>>>(d_U, n_model_users, k, w.users.p, 1, n_users, kp, w.Ub.p, w.unorm.p, w.row_ok.p, nullptr, nullptr);
+    const size_t rf = c.row_floats();
+    if (rows_pad > n_users) MML_CUDA(cudaMemsetAsync(w.Ub.p + (size_t)n_users * rf, 0, sizeof(float) * (size_t)(rows_pad - n_users) * rf, s));
+    tc_stage_rows_kernel<<<tc_grid((int64_t)n_users * 32), 256, 0, s>>>(d_U, n_model_users, k, w.users.p, 1, n_users, kp, w.Ub.p, w.unorm.p, w.row_ok.p, nullptr, nullptr, c.bf16 ? 1 : 0);
     MML_CUDA(cudaGetLastError());
     if (launches) *launches += 1;
     // ignore_items as candidate positions, ascending inside a row (the epilogue walks them with a cursor)
@@ -694,10 +738,11 @@ static int32_t topn_tc_batch(Ctx* ctx, TcCandidates& c, TcWork& w, const float* 
         }
     }
     CUtensorMap map_u;
-    MML_TRY(make_panel_map(&map_u, w.Ub.p, rows_pad, kp));
+    MML_TRY(make_panel_map(&map_u, w.Ub.p, rows_pad, kp, c.bf16));
     const int row_tiles = (int)(rows_pad / TC_ROWS);
     TcArgs a{};
     a.n_rows = n_users; a.kc = kc; a.m = n;
+    a.bf16 = c.bf16 ? 1 : 0; a.epc = c.bf16 ? TC_KC_BF16 : TC_KC;
     { const char* e = getenv("MMLB200_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
     a.row_ok = w.row_ok.p; a.ign_ptr = have_ign ? w.ign_ptr.p : nullptr; a.ign_pos = w.ign_idx.p;
     a.thr = w.thr.p; a.err = w.err.p;
@@ -707,7 +752,7 @@ static int32_t topn_tc_batch(Ctx* ctx, TcCandidates& c, TcWork& w, const float* 
     a.n_cols = c.n_samp; a.bad = c.has_bad ? c.bad_s.p : nullptr;
     score_select_kernel<0><<<dim3(row_tiles, 1), TC_THREADS, w.smem0, s>>>(map_u, c.map_s, a);
     MML_CUDA(cudaGetLastError());
-    tc_threshold_kernel<<<(unsigned)ceil_div(n_users, 256), 256, 0, s>>>(w.thr.p, w.d2.p, w.unorm.p, c.vmax.p, n_users);
+    tc_threshold_kernel<<<(unsigned)ceil_div(n_users, 256), 256, 0, s>>>(w.thr.p, w.d2.p, w.unorm.p, c.vmax.p, n_users, c.bf16 ? TC_ERR_C_BF16 : TC_ERR_C);
     MML_CUDA(cudaGetLastError());
     // pass 2: collect every candidate that reaches it
     MML_CUDA(cudaMemsetAsync(w.buf_n.p, 0, sizeof(int32_t) * (size_t)n_users * w.splits * 2, s));
@@ -754,6 +799,7 @@ int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
     cudaStream_t s = ctx->stream;
     TcPhase ph(s);
     TcCandidates c;
+    c.bf16 = topn_tc_filter_bf16();
     MML_TRY(tc_prepare_candidates(ctx, c, d_V, n_model_items, k, d_cand, n_cand, has_invalid_cand, n, launches));
     ph.mark("candidate panels");
     const int64_t n_ign = (ignore_ptr && ignore_idx) ? ignore_ptr[n_users] : 0;

@@ -285,6 +285,11 @@ def topn_set_mode(mode):
     check(_capi.load().mml_topn_set_mode(int(mode)))
 
 
+def topn_set_filter(kind):
+    """_capi.TOPN_FILTER_TF32 (default) / TOPN_FILTER_BF16: operand precision of the tensor-core filter GEMM."""
+    check(_capi.load().mml_topn_set_filter(int(kind)))
+
+
 def topn_last_stats():
     a, b, ms = C.c_int64(), C.c_int64(), C.c_float()
     check(_capi.load().mml_topn_last_stats(C.byref(a), C.byref(b), C.byref(ms)))

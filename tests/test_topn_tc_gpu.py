@@ -1,4 +1,4 @@
-"""Recommend() on the tcgen05 path (TF32 scoring + fused top-k + exact re-scoring of the finalists) against the CPU
+"""Recommend() on the tcgen05 path (BF16 / TF32 scoring + fused top-k + exact re-scoring of the finalists) against the CPU
 oracle and against the exact CUDA-core path: item ids, order and fp32 scores must be bit-identical
 (Recommender.cs:52-103, ItemRecommendation/MF.cs:151-157, DataType/MatrixExtensions.cs:224-241)."""
 import numpy as np
@@ -9,12 +9,16 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def eng():
+@pytest.fixture(scope="module", params=["bf16", "tf32"])
+def eng(request):
+    """Every test runs under both operand precisions of the filter GEMM (mml_topn_set_filter): the results must be the
+    same bits either way, only the number of exactly re-scored finalists differs."""
     from mymedialite_b200 import engine
     ctx = engine.Context(0)
+    engine.topn_set_filter(engine._capi.TOPN_FILTER_BF16 if request.param == "bf16" else engine._capi.TOPN_FILTER_TF32)
     yield engine, ctx
     engine.topn_set_mode(engine._capi.TOPN_AUTO)
+    engine.topn_set_filter(engine._capi.TOPN_FILTER_TF32)
     ctx.close()
 
 
