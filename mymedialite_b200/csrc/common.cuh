@@ -83,7 +83,15 @@ struct Ctx {
     void* comm = nullptr;        // ncclComm_t when n_gpus > 1
     void* flush_buf = nullptr;   // mml_ctx_flush_l2
     int flush_val = 0;
+    // Every ABI call on this context or on a handle created from it holds this lock for its duration: the handles share the
+    // context's streams and their own grow-only scratch buffers, and the reference calls Predict / Recommend concurrently from
+    // TPL threads on one object (Eval/Items.cs:147-164). Recursive: some entry points are built on others.
+    std::recursive_mutex mu;
 };
+
+#define MML_LOCK(ctxptr)                                                                       \
+    std::unique_lock<std::recursive_mutex> _mml_lock;                                          \
+    do { mml::Ctx* _lc = (ctxptr); if (_lc) _mml_lock = std::unique_lock<std::recursive_mutex>(_lc->mu); } while (0)
 
 struct Ratings {
     Ctx* ctx = nullptr;

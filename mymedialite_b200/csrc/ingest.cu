@@ -468,6 +468,7 @@ int32_t mml_ingest_original_ids(const mml_ingest* h, int32_t which, int32_t firs
 
 int32_t mml_ingest_to_ratings(mml_ctx* ctx, const mml_ingest* h, mml_ratings** out)
 {
+    MML_LOCK(mml::ctx_of(ctx));
     MML_CHECK(h != nullptr, MML_ERR_ARG, "mml_ingest_to_ratings: NULL handle");
     const Ingest* g = ingest_of(h);
     MML_CHECK(g->kind != MML_FILE_FEEDBACK, MML_ERR_STATE, "mml_ingest_to_ratings: the handle holds a feedback file");
@@ -480,6 +481,7 @@ int32_t mml_ingest_to_ratings(mml_ctx* ctx, const mml_ingest* h, mml_ratings** o
 
 int32_t mml_ingest_to_feedback(mml_ctx* ctx, const mml_ingest* h, mml_feedback** out)
 {
+    MML_LOCK(mml::ctx_of(ctx));
     MML_CHECK(h != nullptr, MML_ERR_ARG, "mml_ingest_to_feedback: NULL handle");
     const Ingest* g = ingest_of(h);
     return mml_feedback_create(ctx, g->users, g->items, g->n, g->max_id[0], g->max_id[1], out);

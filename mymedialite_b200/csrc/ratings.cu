@@ -166,6 +166,7 @@ extern "C" int32_t mml_ctx_destroy(mml_ctx* ctx)
 
 extern "C" int32_t mml_ctx_synchronize(mml_ctx* ctx)
 {
+    MML_LOCK(mml::ctx_of(ctx));
     MML_CHECK(ctx != nullptr, MML_ERR_ARG, "ctx is NULL");
     MML_CUDA(cudaStreamSynchronize(ctx->c.stream));
     return MML_OK;
@@ -174,6 +175,7 @@ extern "C" int32_t mml_ctx_synchronize(mml_ctx* ctx)
 /* Writes a buffer larger than the 126 MB L2 so that the next timed kernel starts cold. */
 extern "C" int32_t mml_ctx_flush_l2(mml_ctx* ctx)
 {
+    MML_LOCK(mml::ctx_of(ctx));
     MML_CHECK(ctx != nullptr, MML_ERR_ARG, "ctx is NULL");
     MML_CUDA(cudaSetDevice(ctx->c.device));
     const size_t bytes = (size_t)384 << 20;
@@ -186,6 +188,7 @@ extern "C" int32_t mml_ctx_flush_l2(mml_ctx* ctx)
 
 extern "C" int32_t mml_ctx_sm_count(mml_ctx* ctx, int32_t* out)
 {
+    MML_LOCK(mml::ctx_of(ctx));
     MML_CHECK(ctx != nullptr && out != nullptr, MML_ERR_ARG, "NULL argument");
     *out = ctx->c.sm_count;
     return MML_OK;
@@ -195,6 +198,7 @@ extern "C" int32_t mml_ctx_sm_count(mml_ctx* ctx, int32_t* out)
 extern "C" int32_t mml_ratings_create(mml_ctx* ctx, const int32_t* users, const int32_t* items, const float* values,
                                       int64_t n, int32_t max_user, int32_t max_item, mml_ratings** out)
 {
+    MML_LOCK(mml::ctx_of(ctx));
     MML_CHECK(ctx && out, MML_ERR_ARG, "mml_ratings_create: NULL argument");
     MML_CHECK(n >= 0 && n < ((int64_t)1 << 31), MML_ERR_ARG, "mml_ratings_create: n=%lld out of range", (long long)n);
     MML_CHECK(n == 0 || (users && items && values), MML_ERR_ARG, "mml_ratings_create: NULL data");
@@ -239,6 +243,7 @@ extern "C" int32_t mml_ratings_create(mml_ctx* ctx, const int32_t* users, const 
 
 extern "C" int32_t mml_ratings_destroy(mml_ratings* r)
 {
+    MML_LOCK((r ? mml::ratings_of(r)->ctx : nullptr));
     if (!r) return MML_OK;
     cudaSetDevice(r->r.ctx->device);
     delete r;
@@ -247,6 +252,7 @@ extern "C" int32_t mml_ratings_destroy(mml_ratings* r)
 
 extern "C" int32_t mml_ratings_counts(mml_ratings* h, int32_t by_item, int32_t* counts_out)
 {
+    MML_LOCK((h ? mml::ratings_of(h)->ctx : nullptr));
     MML_CHECK(h && counts_out, MML_ERR_ARG, "mml_ratings_counts: NULL argument");
     Ratings& r = h->r;
     MML_CUDA(cudaSetDevice(r.ctx->device));
@@ -259,6 +265,7 @@ extern "C" int32_t mml_ratings_counts(mml_ratings* h, int32_t by_item, int32_t* 
 
 extern "C" int32_t mml_ratings_csr(mml_ratings* h, int32_t by_item, int64_t* row_ptr, int32_t* idx)
 {
+    MML_LOCK((h ? mml::ratings_of(h)->ctx : nullptr));
     MML_CHECK(h && row_ptr && idx, MML_ERR_ARG, "mml_ratings_csr: NULL argument");
     Ratings& r = h->r;
     MML_CUDA(cudaSetDevice(r.ctx->device));
@@ -272,6 +279,7 @@ extern "C" int32_t mml_ratings_csr(mml_ratings* h, int32_t by_item, int64_t* row
 
 extern "C" int32_t mml_ratings_stats(mml_ratings* h, float* average, float* min_rating, float* max_rating)
 {
+    MML_LOCK((h ? mml::ratings_of(h)->ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "mml_ratings_stats: NULL argument");
     if (average) *average = h->r.average;
     if (min_rating) *min_rating = h->r.min_rating;
@@ -282,6 +290,7 @@ extern "C" int32_t mml_ratings_stats(mml_ratings* h, float* average, float* min_
 extern "C" int32_t mml_partition_blocks(mml_ratings* h, const int32_t* user_perm, const int32_t* item_perm, int32_t g,
                                         int64_t* block_ptr, int32_t* idx)
 {
+    MML_LOCK((h ? mml::ratings_of(h)->ctx : nullptr));
     MML_CHECK(h && user_perm && item_perm && block_ptr && idx, MML_ERR_ARG, "mml_partition_blocks: NULL argument");
     Ratings& r = h->r;
     MML_CHECK(g >= 1 && (int64_t)g * g < ((int64_t)1 << 31), MML_ERR_ARG, "mml_partition_blocks: bad g=%d", g);

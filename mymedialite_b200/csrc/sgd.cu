@@ -1590,6 +1590,7 @@ extern "C" void mml_mf_params_default(mml_mf_params* p)
 extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_params* p,
                                   const int32_t* user_perm, const int32_t* item_perm, mml_sgd** out)
 {
+    MML_LOCK(mml::ctx_of(hctx));
     MML_CHECK(hctx && hr && p && out, MML_ERR_ARG, "mml_sgd_create: NULL argument");
     Ctx* ctx = ctx_of(hctx); Ratings* r = ratings_of(hr);
     MML_CHECK(p->num_factors >= 1 && p->num_factors <= 256, MML_ERR_UNSUPPORTED,
@@ -1756,6 +1757,7 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
 
 extern "C" int32_t mml_sgd_destroy(mml_sgd* h)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     if (!h) return MML_OK;
     cudaSetDevice(h->m.ctx->device);
     cudaStreamSynchronize(h->m.ctx->stream);
@@ -1806,6 +1808,7 @@ static int32_t after_init(Sgd& m)
 extern "C" int32_t mml_sgd_set_model(mml_sgd* h, const float* user_factors, const float* item_factors,
                                      const float* user_bias, const float* item_bias)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && user_factors && item_factors, MML_ERR_ARG, "mml_sgd_set_model: NULL argument");
     Sgd& m = h->m;
     MML_CUDA(cudaSetDevice(m.ctx->device));
@@ -1819,6 +1822,7 @@ extern "C" int32_t mml_sgd_set_model(mml_sgd* h, const float* user_factors, cons
 
 extern "C" int32_t mml_sgd_init_model(mml_sgd* h, uint64_t seed, double init_mean, double init_stddev)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "mml_sgd_init_model: NULL argument");
     Sgd& m = h->m;
     MML_CUDA(cudaSetDevice(m.ctx->device));
@@ -1838,6 +1842,7 @@ extern "C" int32_t mml_sgd_init_model(mml_sgd* h, uint64_t seed, double init_mea
 extern "C" int32_t mml_sgd_get_model(mml_sgd* h, float* user_factors, float* item_factors,
                                      float* user_bias, float* item_bias, float* global_bias, float* current_learnrate)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "mml_sgd_get_model: NULL argument");
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_get_model: no model (call set_model / init_model first)");
@@ -1876,6 +1881,7 @@ extern "C" int32_t mml_sgd_get_model(mml_sgd* h, float* user_factors, float* ite
 
 extern "C" int32_t mml_sgd_set_learnrate(mml_sgd* h, float lr)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
     h->m.lr = lr;
     return MML_OK;
@@ -1883,6 +1889,7 @@ extern "C" int32_t mml_sgd_set_learnrate(mml_sgd* h, float lr)
 
 extern "C" int32_t mml_sgd_set_scale(mml_sgd* h, float min_rating, float max_rating, float global_bias)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
     h->m.min_rating = min_rating; h->m.max_rating = max_rating; h->m.range = max_rating - min_rating;
     h->m.global_bias = global_bias;
@@ -1891,6 +1898,7 @@ extern "C" int32_t mml_sgd_set_scale(mml_sgd* h, float min_rating, float max_rat
 
 extern "C" int32_t mml_sgd_invalidate_index(mml_sgd* h)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
     h->m.n_index = -1;
     return MML_OK;
@@ -1898,6 +1906,7 @@ extern "C" int32_t mml_sgd_invalidate_index(mml_sgd* h)
 
 extern "C" int32_t mml_sgd_iterate(mml_sgd* h, const int32_t* subepoch_sequence, const int32_t* random_index, int64_t n_index)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "mml_sgd_iterate: NULL argument");
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_iterate: no model (call set_model / init_model first)");
@@ -1930,6 +1939,7 @@ extern "C" int32_t mml_sgd_iterate(mml_sgd* h, const int32_t* subepoch_sequence,
 
 extern "C" int32_t mml_sgd_iterate_indices(mml_sgd* h, const int32_t* indices, int64_t n, int32_t update_user, int32_t update_item)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && (indices || n == 0), MML_ERR_ARG, "mml_sgd_iterate_indices: NULL argument");
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_iterate_indices: no model");
@@ -1947,6 +1957,7 @@ extern "C" int32_t mml_sgd_iterate_indices(mml_sgd* h, const int32_t* indices, i
 
 extern "C" int32_t mml_sgd_predict(mml_sgd* h, const int32_t* users, const int32_t* items, int64_t n, float* out)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && (n == 0 || (users && items && out)), MML_ERR_ARG, "mml_sgd_predict: NULL argument");
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_predict: no model");
@@ -1970,6 +1981,7 @@ extern "C" int32_t mml_sgd_predict(mml_sgd* h, const int32_t* users, const int32
 
 extern "C" int32_t mml_sgd_evaluate(mml_sgd* h, const int32_t* users, const int32_t* items, const float* values, int64_t n, float* out4)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && out4 && (n == 0 || (users && items && values)), MML_ERR_ARG, "mml_sgd_evaluate: NULL argument");
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_evaluate: no model");
@@ -1999,6 +2011,7 @@ extern "C" int32_t mml_sgd_evaluate(mml_sgd* h, const int32_t* users, const int3
 
 extern "C" int32_t mml_sgd_evaluate_train(mml_sgd* h, float* out4)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && out4, MML_ERR_ARG, "mml_sgd_evaluate_train: NULL argument");
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_evaluate_train: no model");
@@ -2014,6 +2027,7 @@ extern "C" int32_t mml_sgd_evaluate_train(mml_sgd* h, float* out4)
 
 extern "C" int32_t mml_sgd_objective(mml_sgd* h, double* out)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && out, MML_ERR_ARG, "mml_sgd_objective: NULL argument");
     MML_CHECK(h->m.has_model, MML_ERR_STATE, "mml_sgd_objective: no model");
     MML_CUDA(cudaSetDevice(h->m.ctx->device));
@@ -2022,6 +2036,7 @@ extern "C" int32_t mml_sgd_objective(mml_sgd* h, double* out)
 
 extern "C" int32_t mml_sgd_stats(mml_sgd* h, int64_t* kernel_launches, float* last_iterate_ms)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
     Sgd& m = h->m;
     if (kernel_launches) *kernel_launches = m.launches;
@@ -2038,6 +2053,7 @@ extern "C" int32_t mml_sgd_stats(mml_sgd* h, int64_t* kernel_launches, float* la
 
 extern "C" int32_t mml_sgd_strata_info(mml_sgd* h, int32_t* G, int32_t* W, int64_t* n_rounds, int64_t* staged_bytes)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
     if (G) *G = h->m.G;
     if (W) *W = h->m.W;
@@ -2048,6 +2064,7 @@ extern "C" int32_t mml_sgd_strata_info(mml_sgd* h, int32_t* G, int32_t* W, int64
 
 extern "C" int32_t mml_sgd_grid(mml_sgd* h, int32_t* G, int32_t* ctas_per_group)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
     if (G) *G = h->m.G;
     if (ctas_per_group) *ctas_per_group = h->m.cpg;
@@ -2056,6 +2073,7 @@ extern "C" int32_t mml_sgd_grid(mml_sgd* h, int32_t* G, int32_t* ctas_per_group)
 
 extern "C" int32_t mml_sgd_hot_items(mml_sgd* h, int64_t* n_hot)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && n_hot, MML_ERR_ARG, "NULL argument");
     *n_hot = h->m.n_hot;
     return MML_OK;
@@ -2064,6 +2082,7 @@ extern "C" int32_t mml_sgd_hot_items(mml_sgd* h, int64_t* n_hot)
 extern "C" int32_t mml_sgd_schedule_dump(mml_sgd* h, const int32_t* subepoch_sequence, int32_t* order,
                                         int32_t* block, int32_t* copy, int32_t* round)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && order, MML_ERR_ARG, "mml_sgd_schedule_dump: NULL argument");
     Sgd& m = h->m;
     MML_CHECK(m.p.schedule == MML_SCHEDULE_DSGD, MML_ERR_STATE, "mml_sgd_schedule_dump: not a DSGD model");
@@ -2257,6 +2276,7 @@ extern "C" int32_t mml_sgd_fold_in(mml_sgd* h, const int64_t* rated_ptr, const i
                                    const float* rated_values, int64_t n_users, const float* init_factors,
                                    int32_t num_iter, float* out_vectors)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && (n_users == 0 || (rated_ptr && init_factors && out_vectors)), MML_ERR_ARG, "mml_sgd_fold_in: NULL argument");
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_fold_in: no model");
@@ -2301,6 +2321,7 @@ extern "C" int32_t mml_sgd_fold_in(mml_sgd* h, const int64_t* rated_ptr, const i
 extern "C" int32_t mml_sgd_score_items(mml_sgd* h, const float* user_vectors, int64_t n_users,
                                        const int32_t* candidates, int64_t n_cand, float* out_scores)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "mml_sgd_score_items: NULL argument");
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_score_items: no model");
@@ -2332,6 +2353,7 @@ extern "C" int32_t mml_sgd_score_items(mml_sgd* h, const float* user_vectors, in
 extern "C" int32_t mml_sgd_set_rows(mml_sgd* h, int32_t by_item, const int32_t* ids, int64_t n,
                                     const float* factors, const float* biases)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && (n == 0 || ids), MML_ERR_ARG, "mml_sgd_set_rows: NULL argument");
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_set_rows: no model");

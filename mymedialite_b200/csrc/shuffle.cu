@@ -97,6 +97,7 @@ using namespace mml;
 
 extern "C" int32_t mml_shuffle_apply(mml_ctx* hctx, int32_t* perm, const int32_t* H, int64_t n)
 {
+    MML_LOCK(mml::ctx_of(hctx));
     MML_CHECK(hctx && (n == 0 || (perm && H)), MML_ERR_ARG, "mml_shuffle_apply: NULL argument");
     MML_CHECK(n >= 0 && n < ((int64_t)1 << 31), MML_ERR_ARG, "mml_shuffle_apply: n out of range");
     Ctx* ctx = ctx_of(hctx);

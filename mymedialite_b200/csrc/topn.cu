@@ -622,6 +622,7 @@ extern "C" int32_t mml_topn_mf(mml_ctx* hctx, const float* user_factors, int32_t
                                const int64_t* ignore_ptr, const int32_t* ignore_idx,
                                int32_t* out_items, float* out_scores, int32_t* out_counts)
 {
+    MML_LOCK(mml::ctx_of(hctx));
     MML_CHECK(hctx && user_factors && item_factors && (n_users == 0 || (users && out_items && out_scores && out_counts)),
               MML_ERR_ARG, "mml_topn_mf: NULL argument");
     MML_CHECK(k >= 1 && n_model_users >= 0 && n_model_items >= 0 && n_users >= 0 && (n > 0 || n == -1), MML_ERR_ARG,
@@ -645,6 +646,7 @@ extern "C" int32_t mml_items_evaluate_mf(mml_ctx* hctx, const float* user_factor
                                          const int64_t* ignore_ptr, const int32_t* ignore_idx, int32_t n,
                                          float* out_measures, int32_t* out_used)
 {
+    MML_LOCK(mml::ctx_of(hctx));
     MML_CHECK(hctx && user_factors && item_factors && candidates && test_ptr &&
               (n_test_users == 0 || (test_users && out_measures && out_used)), MML_ERR_ARG, "mml_items_evaluate_mf: NULL argument");
     MML_CHECK(k >= 1 && n_model_users >= 0 && n_model_items >= 0 && n_test_users >= 0 && (n > 0 || n == -1), MML_ERR_ARG,

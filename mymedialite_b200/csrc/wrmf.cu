@@ -415,6 +415,7 @@ namespace mml { Feedback* feedback_of(mml_feedback* h) { return h ? &h->f : null
 extern "C" int32_t mml_feedback_create(mml_ctx* hctx, const int32_t* users, const int32_t* items, int64_t n,
                                        int32_t max_user, int32_t max_item, mml_feedback** out)
 {
+    MML_LOCK(mml::ctx_of(hctx));
     MML_CHECK(hctx && out && (n == 0 || (users && items)), MML_ERR_ARG, "mml_feedback_create: NULL argument");
     MML_CHECK(n >= 0 && n < ((int64_t)1 << 31), MML_ERR_ARG, "mml_feedback_create: n out of range");
     for (int64_t t = 0; t < n; t++)
@@ -433,6 +434,7 @@ extern "C" int32_t mml_feedback_create(mml_ctx* hctx, const int32_t* users, cons
 
 extern "C" int32_t mml_feedback_destroy(mml_feedback* f)
 {
+    MML_LOCK((f ? f->f.ctx : nullptr));
     if (!f) return MML_OK;
     cudaSetDevice(f->f.ctx->device);
     delete f;
@@ -441,6 +443,7 @@ extern "C" int32_t mml_feedback_destroy(mml_feedback* f)
 
 extern "C" int32_t mml_feedback_nnz(mml_feedback* f, int64_t* nnz)
 {
+    MML_LOCK((f ? f->f.ctx : nullptr));
     MML_CHECK(f && nnz, MML_ERR_ARG, "NULL argument");
     *nnz = f->f.nnz;
     return MML_OK;
@@ -448,6 +451,7 @@ extern "C" int32_t mml_feedback_nnz(mml_feedback* f, int64_t* nnz)
 
 extern "C" int32_t mml_feedback_csr(mml_feedback* h, int32_t by_item, int64_t* row_ptr, int32_t* cols)
 {
+    MML_LOCK((h ? h->f.ctx : nullptr));
     MML_CHECK(h && row_ptr && cols, MML_ERR_ARG, "NULL argument");
     Feedback& f = h->f;
     MML_CUDA(cudaSetDevice(f.ctx->device));
@@ -464,6 +468,7 @@ extern "C" int32_t mml_feedback_csr(mml_feedback* h, int32_t by_item, int64_t* r
 
 extern "C" int32_t mml_wrmf_create(mml_ctx* hctx, mml_feedback* hf, const mml_wrmf_params* p, mml_wrmf** out)
 {
+    MML_LOCK(mml::ctx_of(hctx));
     MML_CHECK(hctx && hf && p && out, MML_ERR_ARG, "mml_wrmf_create: NULL argument");
     MML_CHECK(p->num_factors >= 1 && p->num_factors <= 160, MML_ERR_UNSUPPORTED, "mml_wrmf_create: num_factors=%d not in [1,160]", p->num_factors);
     Ctx* ctx = ctx_of(hctx);
@@ -495,6 +500,7 @@ extern "C" int32_t mml_wrmf_create(mml_ctx* hctx, mml_feedback* hf, const mml_wr
 
 extern "C" int32_t mml_wrmf_destroy(mml_wrmf* h)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     if (!h) return MML_OK;
     cudaSetDevice(h->m.ctx->device);
     cudaStreamSynchronize(h->m.ctx->stream);
@@ -507,6 +513,7 @@ extern "C" int32_t mml_wrmf_destroy(mml_wrmf* h)
 
 extern "C" int32_t mml_wrmf_set_model(mml_wrmf* h, const float* user_factors, const float* item_factors)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && user_factors && item_factors, MML_ERR_ARG, "mml_wrmf_set_model: NULL argument");
     Wrmf& m = h->m;
     MML_CUDA(cudaSetDevice(m.ctx->device));
@@ -534,6 +541,7 @@ __global__ void wrmf_init_kernel(float* __restrict__ rows, int64_t n, uint64_t s
 
 extern "C" int32_t mml_wrmf_init_model(mml_wrmf* h, uint64_t seed, double init_mean, double init_stddev)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
     Wrmf& m = h->m;
     MML_CUDA(cudaSetDevice(m.ctx->device));
@@ -550,6 +558,7 @@ extern "C" int32_t mml_wrmf_init_model(mml_wrmf* h, uint64_t seed, double init_m
 
 extern "C" int32_t mml_wrmf_get_model(mml_wrmf* h, float* user_factors, float* item_factors)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
     Wrmf& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_wrmf_get_model: no model");
@@ -574,6 +583,7 @@ static int32_t gather_rows(Wrmf& m, float* W, const std::vector<int32_t>& range)
 
 extern "C" int32_t mml_wrmf_shard(mml_wrmf* h, int32_t by_item, int32_t* ranges)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && ranges, MML_ERR_ARG, "NULL argument");
     const std::vector<int32_t>& r = by_item ? h->m.range_i : h->m.range_u;
     for (size_t t = 0; t < r.size(); t++) ranges[t] = r[t];
@@ -583,6 +593,7 @@ extern "C" int32_t mml_wrmf_shard(mml_wrmf* h, int32_t by_item, int32_t* ranges)
 // WRMF.Iterate (WRMF.cs:68-73): user half-sweep, then item half-sweep
 extern "C" int32_t mml_wrmf_iterate(mml_wrmf* h)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
     Wrmf& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_wrmf_iterate: no model (call set_model / init_model first)");
@@ -601,6 +612,7 @@ extern "C" int32_t mml_wrmf_iterate(mml_wrmf* h)
 
 extern "C" int32_t mml_wrmf_retrain(mml_wrmf* h, int32_t by_item, const int32_t* ids, int64_t n)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && (n == 0 || ids), MML_ERR_ARG, "mml_wrmf_retrain: NULL argument");
     Wrmf& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_wrmf_retrain: no model");
@@ -632,6 +644,7 @@ extern "C" int32_t mml_wrmf_set_mode(int32_t mode)
 // sum_{i in S_u} h_i h_i^T of the user with the most feedback events (the first row of the work queue).
 extern "C" int32_t mml_wrmf_debug_gram(mml_wrmf* h, float* out_gram, int32_t* out_user)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && out_gram && out_user, MML_ERR_ARG, "NULL argument");
     Wrmf& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_wrmf_debug_gram: no model");
@@ -652,6 +665,7 @@ extern "C" int32_t mml_wrmf_debug_gram(mml_wrmf* h, float* out_gram, int32_t* ou
 
 extern "C" int32_t mml_wrmf_stats(mml_wrmf* h, int64_t* kernel_launches, float* last_iterate_ms)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
     Wrmf& m = h->m;
     if (kernel_launches) *kernel_launches = m.launches;
@@ -673,6 +687,7 @@ extern "C" int32_t mml_wrmf_evaluate(mml_wrmf* h, const int32_t* test_users, int
                                      const int64_t* ignore_ptr, const int32_t* ignore_idx, int32_t n,
                                      float* out_measures, int32_t* out_used)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && candidates && test_ptr && (n_test_users == 0 || (test_users && out_measures && out_used)), MML_ERR_ARG,
               "mml_wrmf_evaluate: NULL argument");
     MML_CHECK((n > 0 || n == -1) && n_test_users >= 0, MML_ERR_ARG, "mml_wrmf_evaluate: n must be > 0 or -1");
@@ -690,6 +705,7 @@ extern "C" int32_t mml_wrmf_recommend(mml_wrmf* h, const int32_t* users, int64_t
                                       const int64_t* ignore_ptr, const int32_t* ignore_idx,
                                       int32_t* out_items, float* out_scores, int32_t* out_counts)
 {
+    MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && (n_users == 0 || (users && out_items && out_scores && out_counts)), MML_ERR_ARG, "mml_wrmf_recommend: NULL argument");
     MML_CHECK(n > 0 || n == -1, MML_ERR_ARG, "mml_wrmf_recommend: n must be > 0 or -1");
     Wrmf& m = h->m;
