@@ -268,6 +268,8 @@ int32_t ingest_text(const char* text, int64_t len, int32_t kind, int32_t user_ma
 
     const char* begin = text;
     const char* end = text + len;
+    // StreamReader(filename) detects and drops a UTF-8 byte order mark
+    if (len >= 3 && (unsigned char)begin[0] == 0xEF && (unsigned char)begin[1] == 0xBB && (unsigned char)begin[2] == 0xBF) begin += 3;
     if (ignore_first_line) {                                                      // reader.ReadLine() once
         while (begin < end && *begin != '\n' && *begin != '\r') begin++;
         if (begin < end) begin += (*begin == '\r' && begin + 1 < end && begin[1] == '\n') ? 2 : 1;

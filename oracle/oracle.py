@@ -427,6 +427,8 @@ class IdentityMapping:
 
 def read_lines(text):
     """TextReader.ReadLine: a line ends at \\n, \\r or \\r\\n; a trailing terminator does not start another line."""
+    if text.startswith("\ufeff"):       # StreamReader drops the byte order mark
+        text = text[1:]
     parts = re.split(r"\r\n|\n|\r", text)
     if parts and parts[-1] == "":
         parts.pop()
