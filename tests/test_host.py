@@ -106,3 +106,34 @@ def test_parallel_options_map_to_the_engine_grid():
     m.NaiveParallelization = True
     p = m._params()
     assert p.schedule == _capi.SCHEDULE_DSGD and p.num_groups == 1 and p.ctas_per_group >= 148
+
+
+# ---- Eval.Items host logic (candidate selection, test rows) -- no device needed ---------------------------------------
+def test_items_candidates_modes_follow_the_reference():
+    """Items.Candidates (Eval/Items.cs:62-95): AllItems are first-seen distinct ids; Intersect / Union keep the order of the
+    first sequence; the result is shuffled with MyMediaLite.Random (one Next(i + 1) per element, i = n-1 .. 0)."""
+    from mymedialite_b200 import evalitems as E, recommenders as R, sysrandom
+    from oracle import oracle as O
+    training = R.PosOnlyFeedback([0, 0, 1, 2, 2], [5, 3, 3, 9, 5])
+    test = R.PosOnlyFeedback([0, 1, 1, 3], [9, 7, 5, 7])
+    expect = {E.TRAINING: [5, 3, 9], E.TEST: [9, 7, 5], E.OVERLAP: [9, 5], E.UNION: [9, 7, 5, 3]}
+    for mode, base in expect.items():
+        sysrandom.seed(4)
+        got = E.Candidates(None, mode, test, training)
+        want = O.Random(4).shuffle(np.array(base, np.int32))
+        assert got.tolist() == want.tolist(), mode
+    sysrandom.seed(4)
+    assert sorted(E.Candidates([4, 2, 8], E.EXPLICIT, test, training).tolist()) == [2, 4, 8]
+    with pytest.raises(ValueError):
+        E.Candidates(None, E.EXPLICIT, test, training)
+    with pytest.raises(ValueError):
+        E.Candidates(None, "SOMETHING", test, training)
+
+
+def test_items_rows_are_sets_aligned_with_the_test_users():
+    from mymedialite_b200 import evalitems as E
+    ptr, idx = E._rows([2, 0, 2, 2, 5], [7, 1, 3, 7, 0], np.array([2, 4, 0, 5], np.int32))
+    rows = [idx[ptr[b]:ptr[b + 1]].tolist() for b in range(4)]
+    assert rows == [[3, 7], [], [1], [0]]          # duplicates collapse (SparseBooleanMatrix rows), unknown users are empty
+    ptr, idx = E._rows([], [], np.array([1], np.int32))
+    assert ptr.tolist() == [0, 0] and idx.size == 0
