@@ -264,7 +264,7 @@ def run_ours(args):
                 out["roofline"]["traffic"] = json.load(f).get(args.workload)
         except Exception:
             pass
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:      # rank 0 at N = 1 only: the check model must not enter the ring collectives alone
         out["cpu_baseline"], out["rmse_vs_ref"] = cpu_baseline(args, d, k, ctx)
     print(json.dumps(out), flush=True)
     if dist is not None:
