@@ -1798,8 +1798,15 @@ static int32_t after_init(Sgd& m)
 {
     m.lr = m.p.learn_rate;
     m.has_model = true;
-    if (m.p.biased && m.p.bold_driver) {   // BiasedMatrixFactorization.cs:168-169
-        MML_TRY(objective(m, &m.last_loss));
+    if (m.p.biased && m.p.bold_driver) {
+        // BiasedMatrixFactorization.cs:168-169: InitModel computes last_loss BEFORE Train() sets rating_range_size and
+        // global_bias (:186-190), i.e. with both still 0 -- every prediction is min_rating. Same here, so that the first
+        // bold-driver decision compares against the number the reference compares against.
+        const float gb = m.global_bias, range = m.range;
+        m.global_bias = 0.f; m.range = 0.f;
+        const int32_t st = objective(m, &m.last_loss);
+        m.global_bias = gb; m.range = range;
+        MML_TRY(st);
         m.last_loss = (double)(float)m.last_loss;
     }
     return MML_OK;

@@ -227,3 +227,25 @@ def test_fold_in_two_restatements_agree(biased):
     # Predict(vector, item): clipped for the plain model, sigmoid link for the biased one
     s = m.predict_vector(got, 3)
     assert v.min() <= s <= v.max()
+
+
+def test_bold_driver_rule_in_the_oracle():
+    """BiasedMatrixFactorization.cs:225-244: lr * 0.5 when the objective grew, * 1.05 when it shrank; the first comparison
+    is against the loss of InitModel, computed while rating_range_size and global_bias are still 0 (:161-170 vs :186-190)."""
+    rng = np.random.default_rng(3)
+    n_users, n_items, n = 60, 30, 2500
+    u = rng.integers(0, n_users, n).astype(np.int32); i = rng.integers(0, n_items, n).astype(np.int32)
+    v = (rng.integers(1, 11, n) / 2).astype(np.float32)
+    for lr0, expect_halving in ((0.01, False), (0.9, True)):
+        m = O.Model(u, i, v, biased=True, num_factors=6, bold_driver=1, learn_rate=lr0)
+        r = O.Random(1)
+        m.init(r)
+        seq = [np.float32(lr0)]
+        for _ in range(8):
+            m.iterate(r)
+            seq.append(np.float32(m.learnrate))
+        ratios = {round(float(b / a), 4) for a, b in zip(seq[:-1], seq[1:])}
+        assert ratios <= {0.5, 1.05}, seq
+        assert (0.5 in ratios) == expect_halving, seq
+        if not expect_halving:
+            assert round(float(seq[1] / seq[0]), 4) == 1.05   # a sane first epoch beats "every prediction = min_rating"
