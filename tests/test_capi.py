@@ -96,3 +96,11 @@ def test_csharp_binding_declares_every_entry_point():
     assert not missing, missing
     wrong = {n: (imported[n], declared[n]) for n in declared if imported[n] != declared[n]}
     assert not wrong, wrong
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/mmlb200.h is the FFI contract: it must compile as C99 on its own (no C++ types, no torch, no CUDA headers)."""
+    import subprocess
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "mmlb200.h"\nint main(void) { mml_mf_params p; (void)p; return MML_OK; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
