@@ -124,7 +124,7 @@ namespace MyMediaLite.RatingPrediction
 		protected int FoldInStride { get { return (int) NumFactors + (Biased ? 1 : 0); } }
 
 		/// <summary>RetrainUser (MatrixFactorization.cs:141-149, BiasedMatrixFactorization.cs:419-424): re-draw the row, zero the bias,
-		/// one pass over ByUser[user_id] updating the user side only</summary>
+		/// LearnFactors (:198-202) = NumIter passes over ByUser[user_id] updating the user side only</summary>
 		public virtual void RetrainUser(int user_id) { Retrain(user_id, false, ratings.ByUser[user_id]); }
 
 		/// <summary>RetrainItem (MatrixFactorization.cs:152-160, BiasedMatrixFactorization.cs:426-431)</summary>
@@ -138,7 +138,8 @@ namespace MyMediaLite.RatingPrediction
 				row.InitNormal(InitMean, InitStdDev);
 				Mml.Check(Mml.mml_sgd_set_rows(model.DangerousGetHandle(), by_item ? 1 : 0, new int[] { id }, 1, row, Biased ? new float[] { 0 } : null));
 				var idx = indices.ToArray();
-				Mml.Check(Mml.mml_sgd_iterate_indices(model.DangerousGetHandle(), idx, idx.Length, by_item ? 0 : 1, by_item ? 1 : 0));
+				// LearnFactors (MatrixFactorization.cs:198-202): NumIter passes over the list
+				Mml.Check(Mml.mml_sgd_learn_factors(model.DangerousGetHandle(), idx, idx.Length, by_item ? 0 : 1, by_item ? 1 : 0, (int) NumIter));
 			}
 		}
 

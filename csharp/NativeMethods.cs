@@ -101,6 +101,7 @@ namespace MyMediaLite.Native
 		[DllImport(LIB)] public static extern int mml_sgd_iterate(IntPtr model, int[] subepoch_sequence, int[] random_index, long n_index);
 		[DllImport(LIB)] public static extern int mml_sgd_invalidate_index(IntPtr model);
 		[DllImport(LIB)] public static extern int mml_sgd_iterate_indices(IntPtr model, int[] indices, long n, int update_user, int update_item);
+		[DllImport(LIB)] public static extern int mml_sgd_learn_factors(IntPtr model, int[] indices, long n, int update_user, int update_item, int num_iter);
 		[DllImport(LIB)] public static extern int mml_sgd_predict(IntPtr model, int[] users, int[] items, long n, [Out] float[] result);
 		[DllImport(LIB)] public static extern int mml_sgd_fold_in(IntPtr model, long[] rated_ptr, int[] rated_items, float[] rated_values, long n_users, float[] init_factors, int num_iter, [Out] float[] out_vectors);
 		[DllImport(LIB)] public static extern int mml_sgd_score_items(IntPtr model, float[] user_vectors, long n_users, int[] candidates, long n_cand, [Out] float[] out_scores);

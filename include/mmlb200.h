@@ -211,6 +211,11 @@ int32_t mml_sgd_invalidate_index(mml_sgd* m);
  * in the reference's exact order and mixed precision; no learn-rate update for the biased model,
  * plain MF decays as the reference does (:195). */
 int32_t mml_sgd_iterate_indices(mml_sgd* m, const int32_t* indices, int64_t n, int32_t update_user, int32_t update_item);
+/* LearnFactors (MatrixFactorization.cs:198-202): num_iter (= NumIter) passes of Iterate(list, update_user, update_item) --
+ * what RetrainUser / RetrainItem run over ByUser[u] / ByItem[i] after re-drawing the row (:141-160). Plain MF decays the
+ * learn rate after every pass (:195), the biased model leaves it alone. */
+int32_t mml_sgd_learn_factors(mml_sgd* m, const int32_t* indices, int64_t n, int32_t update_user, int32_t update_item,
+                              int32_t num_iter);
 /* Predict (BiasedMatrixFactorization.cs:313-325 / MatrixFactorization.cs:251-259), batched. */
 int32_t mml_sgd_predict(mml_sgd* m, const int32_t* users, const int32_t* items, int64_t n, float* out);
 /* Eval.Ratings.Evaluate (Eval/Ratings.cs:96-139): out4 = {RMSE, MAE, NMAE, CBD}. */

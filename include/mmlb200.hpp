@@ -494,7 +494,8 @@ protected:
         std::vector<int32_t> idx;                      // ByUser[u] / ByItem[i]: rating indices in ascending order
         const std::vector<int32_t>& ids = by_item ? ratings->Items : ratings->Users;
         for (int64_t t = 0; t < ratings->Count(); t++) if (ids[(size_t)t] == id) idx.push_back((int32_t)t);
-        Check(mml_sgd_iterate_indices(Model(), idx.data(), (int64_t)idx.size(), by_item ? 0 : 1, by_item ? 1 : 0));
+        // LearnFactors (MatrixFactorization.cs:198-202): NumIter passes over the list
+        Check(mml_sgd_learn_factors(Model(), idx.data(), (int64_t)idx.size(), by_item ? 0 : 1, by_item ? 1 : 0, (int32_t)NumIter));
     }
     // a model without training data: one pseudo rating per id keeps every row (InitModel zeroes rows without ratings only)
     void Adopt(const std::vector<float>& U, int64_t nu, int64_t ku, const std::vector<float>& V, int64_t ni, int64_t ki,

@@ -99,6 +99,7 @@ SIGNATURES = {
     "mml_sgd_iterate": (C.c_int32, [vp, oi32p, oi32p, C.c_int64]),
     "mml_sgd_invalidate_index": (C.c_int32, [vp]),
     "mml_sgd_iterate_indices": (C.c_int32, [vp, oi32p, C.c_int64, C.c_int32, C.c_int32]),
+    "mml_sgd_learn_factors": (C.c_int32, [vp, oi32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "mml_sgd_predict": (C.c_int32, [vp, oi32p, oi32p, C.c_int64, of32p]),
     "mml_sgd_fold_in": (C.c_int32, [vp, oi64p, oi32p, of32p, C.c_int64, of32p, C.c_int32, of32p]),
     "mml_sgd_score_items": (C.c_int32, [vp, of32p, C.c_int64, oi32p, C.c_int64, of32p]),

@@ -202,14 +202,15 @@ __global__ void strata_block_kernel(const int32_t* __restrict__ users, const int
     }
 }
 
-// Per entry (in block order): user row local to its group, item row inside the staged image of its group
+// Per entry (in block order): internal user row, item row inside the staged image of its group (absolute_rows: the internal
+// item row itself -- what the async mode and the evaluation of the training set index Q with)
 // (cold items and copy 0 of hot items: internal row - first row of the group; copy c >= 1 of hot item x:
 // n_it + x * (C - 1) + (c - 1)), value, source index, copy.
 __global__ void strata_entries_kernel(const uint32_t* __restrict__ order, const int32_t* __restrict__ users,
                                       const int32_t* __restrict__ items, const float* __restrict__ values, int64_t n,
                                       const int32_t* __restrict__ user_int, const int32_t* __restrict__ item_int,
                                       const int32_t* __restrict__ item_grp, const int32_t* __restrict__ item_ptr,
-                                      int32_t C, int32_t* __restrict__ ent_u, int32_t* __restrict__ ent_i,
+                                      int32_t C, bool absolute_rows, int32_t* __restrict__ ent_u, int32_t* __restrict__ ent_i,
                                       float* __restrict__ ent_v, int32_t* __restrict__ ent_idx, int8_t* __restrict__ ent_copy)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -220,7 +221,7 @@ __global__ void strata_entries_kernel(const uint32_t* __restrict__ order, const 
         const int32_t ig = item_grp[it];
         const int32_t Bb = ig & ~HOT_BIT;
         const int32_t i_lo = item_ptr[Bb], n_it = item_ptr[Bb + 1] - i_lo;
-        int32_t row = item_int[it] - i_lo;
+        int32_t row = item_int[it] - (absolute_rows ? 0 : i_lo);   // async mode: item rows stay in global memory
         int8_t copy = -1;
         if (ig & HOT_BIT) {
             const int32_t c = (int32_t)(mix32(src) % (uint32_t)C);
@@ -383,7 +384,7 @@ static int32_t build_strata_async(Sgd& m, int32_t n_workers)
     MML_TRY(m.ent_copy.alloc(n));
     strata_entries_kernel<<<grid_n(n), 256, 0, s>>>(vals.p, r.users.p, r.items.p, r.values.p, n,
                                                     m.users.d_to_int.p, m.items.d_to_int.p, m.items.d_grp.p, m.d_item_ptr.p,
-                                                    1, m.ent_u.p, m.ent_i.p, m.ent_v.p, m.ent_idx.p, m.ent_copy.p);
+                                                    1, true, m.ent_u.p, m.ent_i.p, m.ent_v.p, m.ent_idx.p, m.ent_copy.p);
     MML_CUDA(cudaGetLastError());
     MML_TRY(m.wptr.alloc((size_t)n_blk * (n_workers + 1)));
     const int64_t nt = (int64_t)n_blk * (n_workers + 1);
@@ -426,7 +427,7 @@ static int32_t build_strata(Sgd& m, int32_t nu_max, int32_t nr_max)
     MML_TRY(u0.alloc(n)); MML_TRY(i0.alloc(n)); MML_TRY(x0.alloc(n)); MML_TRY(v0.alloc(n)); MML_TRY(c0.alloc(n));
     strata_entries_kernel<<<grid_n(n), 256, 0, s>>>(vals.p, r.users.p, r.items.p, r.values.p, n,
                                                     m.users.d_to_int.p, m.items.d_to_int.p, m.items.d_grp.p, m.d_item_ptr.p,
-                                                    m.hot_copies, u0.p, i0.p, v0.p, x0.p, c0.p);
+                                                    m.hot_copies, false, u0.p, i0.p, v0.p, x0.p, c0.p);
     MML_CUDA(cudaGetLastError());
     // 2. rounds: greedy edge colouring per block
     {
@@ -836,10 +837,8 @@ __device__ __forceinline__ void sgd_block_async(const SgdArgs& a, const int j, c
     constexpr int KP = L * KPL;
     const int lane = threadIdx.x & 31;
     const int sl = lane % L;
-    int b = slot + j; if (b >= a.G) b -= a.G;
-    const int i_lo = a.item_ptr[b];
-    float* Qg = a.Q + (size_t)i_lo * KP;
-    float* Bg = a.bi + i_lo;
+    float* Qg = a.Q;            // entries hold internal item rows (strata_entries_kernel, absolute_rows)
+    float* Bg = a.bi;
     const uint32_t e0 = head.e0, e1 = head.e1;
     // entries two ahead, user row and item row one ahead
     int u1 = head.u1, i1 = head.i1, u2 = head.u2, i2 = head.i2; float v1 = head.v1, v2 = head.v2;
@@ -890,7 +889,7 @@ __device__ __forceinline__ void sgd_block_async(const SgdArgs& a, const int j, c
                 if (a.regw_u) regun = a.regw_u[u1];
             }
         }
-        const float regi = a.regw_i ? a.regw_i[i_lo + (active ? i : 0)] : a.reg_i;
+        const float regi = a.regw_i ? a.regw_i[active ? i : 0] : a.reg_i;
         float pw[KPL], dq[KPL];
 #pragma unroll
         for (int f = 0; f < KPL; f++) pw[f] = p[f];
@@ -914,6 +913,154 @@ __device__ __forceinline__ void sgd_block_async(const SgdArgs& a, const int j, c
     }
     if (cur_u >= 0) {
         Row<L, KPL>::store(p, a.P + (size_t)cur_u * KP, sl);
+        if (BIASED) a.bu[cur_u] = bu_v;
+    }
+}
+
+// ---- the async block, second form ------------------------------------------------------------------------------------------
+// Same schedule and semantics as sgd_block_async; what changed is the instruction stream (ncu of round 1: ~200 warp
+// instructions per warp iteration, 16 warps per SM, issue slots half idle on scoreboard waits):
+//   * factor arithmetic on packed pairs (fma.rn.f32x2 / mul.f32x2 of sm_100: one instruction per two factors);
+//   * a worker past the end of its slice keeps running with zero coefficients (p <- 1 p + 0 q, no stores) instead of
+//     computing into copies that are committed under a predicate;
+//   * no forwarding of a just-updated item row to the next rating (the next rating of a user run never has the same item,
+//     and across runs the row comes back from the L2 like everybody else's steps);
+//   * PREF = false: the next user's row is not held in registers ahead of time (8 + 2 registers less: two CTAs per SM).
+template <int KPL>
+struct Row2 {
+    float2 r[KPL / 2];
+};
+
+template <int L, int KPL>
+__device__ __forceinline__ void row2_load(Row2<KPL>& d, const float* row, int sl)
+{
+#pragma unroll
+    for (int v = 0; v < KPL / 4; v++) {
+        const float4 x = reinterpret_cast<const float4*>(row)[v * L + sl];
+        d.r[2 * v] = make_float2(x.x, x.y); d.r[2 * v + 1] = make_float2(x.z, x.w);
+    }
+}
+template <int L, int KPL>
+__device__ __forceinline__ void row2_load_cg(Row2<KPL>& d, const float* row, int sl)
+{
+#pragma unroll
+    for (int v = 0; v < KPL / 4; v++) {
+        const float4 x = ld_cg_f4(reinterpret_cast<const float4*>(row) + (v * L + sl));
+        d.r[2 * v] = make_float2(x.x, x.y); d.r[2 * v + 1] = make_float2(x.z, x.w);
+    }
+}
+template <int L, int KPL>
+__device__ __forceinline__ void row2_store(const Row2<KPL>& d, float* row, int sl)
+{
+#pragma unroll
+    for (int v = 0; v < KPL / 4; v++)
+        reinterpret_cast<float4*>(row)[v * L + sl] = make_float4(d.r[2 * v].x, d.r[2 * v].y, d.r[2 * v + 1].x, d.r[2 * v + 1].y);
+}
+
+template <int L, int KPL, bool BIASED, bool PREF>
+__device__ __forceinline__ void sgd_block_async2(const SgdArgs& a, const AsyncHead& head)
+{
+    constexpr int KP = L * KPL;
+    const int lane = threadIdx.x & 31;
+    const int sl = lane % L;
+    float* const Qg = a.Q;
+    float* const Bg = a.bi;
+    const uint32_t e0 = head.e0, e1 = head.e1;
+    int u1 = head.u1, i1 = head.i1, u2 = head.u2, i2 = head.i2; float v1 = head.v1, v2 = head.v2;
+    Row2<KPL> p, pn, qn;
+    float bu_v = 0.f, bun = 0.f, bin = 0.f, regu = a.reg_u, regun = a.reg_u;
+#pragma unroll
+    for (int f = 0; f < KPL / 2; f++) { p.r[f] = make_float2(0.f, 0.f); pn.r[f] = p.r[f]; qn.r[f] = p.r[f]; }
+    if (e0 < e1) {
+        if (PREF) {
+            row2_load<L, KPL>(pn, a.P + (size_t)u1 * KP, sl);
+            if (BIASED) bun = a.bu[u1];
+            if (a.regw_u) regun = a.regw_u[u1];
+        }
+        row2_load_cg<L, KPL>(qn, Qg + (size_t)i1 * KP, sl);
+        if (BIASED) bin = ld_cg_f(Bg + i1);
+    }
+    uint32_t len = e1 - e0;
+#pragma unroll
+    for (int d = L; d < 32; d <<= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, d));
+    int cur_u = -1;
+    for (uint32_t t = 0; t < len; t++) {
+        const uint32_t e = e0 + t;
+        const bool active = e < e1;
+        const int u = u1, i = i1; const float v = v1;
+        u1 = u2; i1 = i2; v1 = v2;
+        if (e + 2 < e1) { u2 = a.ent_u[e + 2]; i2 = a.ent_i[e + 2]; v2 = a.ent_v[e + 2]; }
+        if (active && u != cur_u) {   // new user run: flush the previous row, take the next one
+            if (cur_u >= 0) {
+                row2_store<L, KPL>(p, a.P + (size_t)cur_u * KP, sl);
+                if (BIASED) a.bu[cur_u] = bu_v;
+            }
+            if (PREF) {
+#pragma unroll
+                for (int f = 0; f < KPL / 2; f++) p.r[f] = pn.r[f];
+                bu_v = bun; regu = regun;
+            } else {
+                row2_load<L, KPL>(p, a.P + (size_t)u * KP, sl);
+                if (BIASED) bu_v = a.bu[u];
+                if (a.regw_u) regu = a.regw_u[u];
+            }
+            cur_u = u;
+        }
+        Row2<KPL> q;
+#pragma unroll
+        for (int f = 0; f < KPL / 2; f++) q.r[f] = qn.r[f];
+        const float bi0 = bin;
+        if (e + 1 < e1) {   // next entry: its item row, and its user row if a new run starts
+            row2_load_cg<L, KPL>(qn, Qg + (size_t)i1 * KP, sl);
+            if (BIASED) bin = ld_cg_f(Bg + i1);
+            if (PREF && u1 != cur_u) {
+                row2_load<L, KPL>(pn, a.P + (size_t)u1 * KP, sl);
+                if (BIASED) bun = a.bu[u1];
+                if (a.regw_u) regun = a.regw_u[u1];
+            }
+        }
+        const float regi = a.regw_i ? a.regw_i[active ? i : 0] : a.reg_i;
+        // dot product on packed pairs
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int f = 0; f < KPL / 2; f++) acc = __ffma2_rn(p.r[f], q.r[f], acc);
+        const float dot = worker_sum<L>(acc.x + acc.y);
+        float gc, dbi = 0.f, bu_new = bu_v;
+        if (BIASED) {
+            const float score = ((a.gb + bu_v) + bi0) + dot;
+            const float sig = __fdividef(1.f, 1.f + __expf(-score));
+            const float err = v - (a.minr + sig * a.range);
+            if (a.loss == MML_LOSS_RMSE) gc = err * sig * (1.f - sig) * a.range;
+            else if (a.loss == MML_LOSS_MAE) gc = (err > 0.f ? 1.f : (err < 0.f ? -1.f : 0.f)) * sig * (1.f - sig) * a.range;
+            else gc = err;
+            const float step = a.blr * a.lr;
+            bu_new = bu_v + step * (gc - a.breg * regu * bu_v);
+            dbi = step * (gc - a.breg * regi * bi0);
+        } else {
+            gc = v - (a.gb + dot);
+        }
+        // p <- cu p + lg q ; dq = lg p - ci q   (pre-update p). Inactive workers: cu = 1, lg = 0 leave p as it is.
+        const float lg = active ? a.lr * gc : 0.f;
+        const float cu = active ? fmaf(-a.lr, regu, 1.f) : 1.f;
+        const float nci = -(a.lr * regi);
+        const float2 lg2 = make_float2(lg, lg), cu2 = make_float2(cu, cu), nci2 = make_float2(nci, nci);
+        Row2<KPL> dq;
+#pragma unroll
+        for (int f = 0; f < KPL / 2; f++) {
+            dq.r[f] = __ffma2_rn(lg2, p.r[f], __fmul2_rn(nci2, q.r[f]));
+            p.r[f] = __ffma2_rn(lg2, q.r[f], __fmul2_rn(cu2, p.r[f]));
+        }
+        if (active) {
+            bu_v = bu_new;
+            float* qrow = Qg + (size_t)i * KP;
+#pragma unroll
+            for (int vv = 0; vv < KPL / 4; vv++)
+                red_add_f4(qrow + 4 * (vv * L + sl), dq.r[2 * vv].x, dq.r[2 * vv].y, dq.r[2 * vv + 1].x, dq.r[2 * vv + 1].y);
+            if (BIASED && sl == 0) red_add_f(Bg + i, dbi);
+        }
+    }
+    if (cur_u >= 0) {
+        row2_store<L, KPL>(p, a.P + (size_t)cur_u * KP, sl);
         if (BIASED) a.bu[cur_u] = bu_v;
     }
 }
@@ -951,15 +1098,57 @@ __global__ void __launch_bounds__(512) sgd_epoch_kernel(const SgdArgs a)
             // item group b = (slot + j) % G was held in sub-epoch t-1 by group jp with (seq[t-1] + jp) % G == b
             int b = slot + j; if (b >= a.G) b -= a.G;
             int jp = b - a.seq[t - 1]; if (jp < 0) jp += a.G;
-            if ((int)threadIdx.x < cpg) {
-                const uint32_t want = a.epoch_base + (uint32_t)t;
-                while ((int32_t)(ld_relaxed_u32(a.flags + jp * cpg + threadIdx.x) - want) < 0) __nanosleep(20);
+            // ... and, with several CTAs per group, by any CTA of this group: the worker slices of a block are cut by entry
+            // count, so a user row this CTA takes now may have belonged to a sister CTA in the previous sub-epoch.
+            const uint32_t want = a.epoch_base + (uint32_t)t;
+            for (int x = (int)threadIdx.x; x < (cpg > 1 ? 2 * cpg : cpg); x += (int)blockDim.x) {
+                const uint32_t* f = a.flags + (x < cpg ? jp * cpg + x : j * cpg + (x - cpg));
+                while ((int32_t)(ld_relaxed_u32(f) - want) < 0) __nanosleep(20);
                 __threadfence();   // acquire
             }
             __syncthreads();
         }
         if (ASYNC) sgd_block_async<L, KPL, BIASED>(a, j, slot, head);
         else sgd_block<L, KPL, BIASED, STAGE>(a, j, slot, reinterpret_cast<float*>(smem4));
+        head = next;
+        if (a.G > 1) {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) st_release_u32(a.flags + blockIdx.x, a.epoch_base + (uint32_t)t + 1u);
+        }
+    }
+}
+
+// The same two kernels on sgd_block_async2 (async mode only). MINB = CTAs per SM the register budget is cut for.
+template <int L, int KPL, bool BIASED, bool PREF, int MINB>
+__global__ void __launch_bounds__(512, MINB) sgd_slot2_kernel(const SgdArgs a, const int slot)
+{
+    const int j = blockIdx.x / a.cpg, sub = blockIdx.x % a.cpg;
+    sgd_block_async2<L, KPL, BIASED, PREF>(a, async_head<L>(a, j, sub, slot));
+}
+
+template <int L, int KPL, bool BIASED, bool PREF, int MINB>
+__global__ void __launch_bounds__(512, MINB) sgd_epoch2_kernel(const SgdArgs a)
+{
+    const int cpg = a.cpg;
+    const int j = blockIdx.x / cpg, sub = blockIdx.x % cpg;
+    AsyncHead head = async_head<L>(a, j, sub, a.seq[0]);
+    for (int t = 0; t < a.G; t++) {
+        const int slot = a.seq[t];
+        AsyncHead next = head;
+        if (t + 1 < a.G) next = async_head<L>(a, j, sub, a.seq[t + 1]);
+        if (t > 0) {   // hand-over: see sgd_epoch_kernel
+            int b = slot + j; if (b >= a.G) b -= a.G;
+            int jp = b - a.seq[t - 1]; if (jp < 0) jp += a.G;
+            const uint32_t want = a.epoch_base + (uint32_t)t;
+            for (int x = (int)threadIdx.x; x < (cpg > 1 ? 2 * cpg : cpg); x += (int)blockDim.x) {
+                const uint32_t* f = a.flags + (x < cpg ? jp * cpg + x : j * cpg + (x - cpg));
+                while ((int32_t)(ld_relaxed_u32(f) - want) < 0) __nanosleep(20);
+                __threadfence();   // acquire
+            }
+            __syncthreads();
+        }
+        sgd_block_async2<L, KPL, BIASED, PREF>(a, head);
         head = next;
         if (a.G > 1) {
             __threadfence();
@@ -1130,47 +1319,66 @@ struct PredArgs {
 };
 
 // BiasedMatrixFactorization.cs:313-325 / MatrixFactorization.cs:205-217,251-259.
-// A warp takes 32 pairs at a time: the ids are read coalesced (lane = pair), the 32 dot products are formed by the
-// whole warp four pairs at a time (8 independent row loads in flight per lane; per pair: lane-partial sums over
-// f = lane, lane + 32, ... then a butterfly), and the scalar part -- the double-precision link, clipping and, in
-// evaluate_kernel, the logarithms of the measures -- runs once per pair on the pair's own lane instead of 32 times.
+// A warp takes 32 pairs at a time: the ids are read coalesced (lane = pair); the 32 dot products are formed by sub-warps of
+// L lanes, each lane moving V 128-bit pieces of either row (a whole row is requested by one or two instructions per lane, so
+// the 512 bytes of a k = 128 row reach the memory system together), two steps (2 * 32 / L pairs) in flight; and the scalar
+// part -- the double-precision link, clipping and, in evaluate_kernel, the logarithms of the measures -- runs once per pair on
+// the pair's own lane instead of L times. ROWS = true: users[] / items[] already hold internal factor rows (the strata
+// entries, sorted by block and user: consecutive pairs share their user row, which then comes from the L1).
 struct PairDots {
     int32_t urow, irow;     // internal rows of this lane's pair or -1 (unknown id)
     float dot;              // p_u . q_i of this lane's pair (0 unless both rows are known)
 };
 
+template <int L, int V, bool ROWS>
 __device__ __forceinline__ PairDots pair_dots(const PredArgs& a, const int32_t* __restrict__ users,
                                               const int32_t* __restrict__ items, int64_t base, int64_t n, int lane)
 {
+    constexpr int NP = 32 / L;          // pairs per step
+    constexpr int KP = 4 * L * V;
     PairDots r;
     r.urow = -1; r.irow = -1; r.dot = 0.f;
     if (base + lane < n) {
         const int32_t u = users[base + lane], i = items[base + lane];
-        if (u >= 0 && u < a.n_users_ext) r.urow = a.user_int[u];
-        if (i >= 0 && i < a.n_items_ext) r.irow = a.item_int[i];
+        if (ROWS) { r.urow = u; r.irow = i; }
+        else {
+            if (u >= 0 && u < a.n_users_ext) r.urow = a.user_int[u];
+            if (i >= 0 && i < a.n_items_ext) r.irow = a.item_int[i];
+        }
     }
     const int cnt = (int)min((int64_t)32, n - base);
-    for (int j0 = 0; j0 < cnt; j0 += 4) {
-        const float* pr[4]; const float* qr[4]; bool ok[4];
+    const int sl = lane % L, g = lane / L;
+    const int steps = (cnt + NP - 1) / NP;
+    for (int s = 0; s < steps; s += 2) {
+        float4 pa[2][V], qa[2][V];
 #pragma unroll
-        for (int x = 0; x < 4; x++) {
-            const int32_t ur = __shfl_sync(0xffffffffu, r.urow, (j0 + x) & 31), ir = __shfl_sync(0xffffffffu, r.irow, (j0 + x) & 31);
-            ok[x] = j0 + x < cnt && ur >= 0 && ir >= 0;
-            pr[x] = a.P + (size_t)(ok[x] ? ur : 0) * a.kp;
-            qr[x] = a.Q + (size_t)(ok[x] ? ir : 0) * a.kp;
-        }
-        float d[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int f = lane; f < a.kp; f += 32) {
+        for (int x = 0; x < 2; x++) {
+            const int pi = (s + x) * NP + g;                 // the pair this sub-warp takes in step s + x
+            const int32_t ur = __shfl_sync(0xffffffffu, r.urow, pi & 31), ir = __shfl_sync(0xffffffffu, r.irow, pi & 31);
+            const bool ok = pi < cnt && ur >= 0 && ir >= 0;
+            const float4* pr = reinterpret_cast<const float4*>(a.P + (size_t)(ok ? ur : 0) * KP);
+            const float4* qr = reinterpret_cast<const float4*>(a.Q + (size_t)(ok ? ir : 0) * KP);
 #pragma unroll
-            for (int x = 0; x < 4; x++) d[x] = fmaf(pr[x][f], qr[x][f], d[x]);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int x = 0; x < 4; x++) d[x] += __shfl_xor_sync(0xffffffffu, d[x], o);
+            for (int v = 0; v < V; v++) {
+                pa[x][v] = ok ? pr[v * L + sl] : make_float4(0.f, 0.f, 0.f, 0.f);
+                qa[x][v] = ok ? qr[v * L + sl] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
 #pragma unroll
-        for (int x = 0; x < 4; x++) if (lane == j0 + x && ok[x]) r.dot = d[x];
+        for (int x = 0; x < 2; x++) {
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+                d0 = fmaf(pa[x][v].x, qa[x][v].x, d0); d1 = fmaf(pa[x][v].y, qa[x][v].y, d1);
+                d0 = fmaf(pa[x][v].z, qa[x][v].z, d0); d1 = fmaf(pa[x][v].w, qa[x][v].w, d1);
+            }
+            float d = d0 + d1;
+#pragma unroll
+            for (int o = L / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            // pair l was taken in step l / NP by sub-warp l % NP
+            const float t = __shfl_sync(0xffffffffu, d, (lane % NP) * L);
+            if (lane / NP == s + x && r.urow >= 0 && r.irow >= 0) r.dot = t;
+        }
     }
     return r;
 }
@@ -1192,6 +1400,7 @@ __device__ __forceinline__ float predict_from_dot(const PredArgs& a, const PairD
     return res;
 }
 
+template <int L, int V>
 __global__ void predict_kernel(const PredArgs a, const int32_t* __restrict__ users, const int32_t* __restrict__ items,
                                int64_t n, float* __restrict__ out)
 {
@@ -1199,15 +1408,17 @@ __global__ void predict_kernel(const PredArgs a, const int32_t* __restrict__ use
     int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
     const int64_t stride = (((int64_t)gridDim.x * blockDim.x) >> 5) * 32;
     for (; base < n; base += stride) {
-        const PairDots r = pair_dots(a, users, items, base, n, lane);
+        const PairDots r = pair_dots<L, V, false>(a, users, items, base, n, lane);
         if (base + lane < n) out[base + lane] = predict_from_dot(a, r);
     }
 }
 
 // Eval/Ratings.cs:96-162. part[blk*4 + {0,1,2,3}] = sum err^2, sum |err|, sum CBD, sum objective loss
 constexpr int EV_THREADS = 256;
-__global__ void evaluate_kernel(const PredArgs a, const int32_t* __restrict__ users, const int32_t* __restrict__ items,
-                                const float* __restrict__ values, int64_t n, int32_t loss, double* __restrict__ part)
+template <int L, int V, bool ROWS>
+__global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(const PredArgs a, const int32_t* __restrict__ users,
+                                                              const int32_t* __restrict__ items, const float* __restrict__ values,
+                                                              int64_t n, int32_t loss, double* __restrict__ part)
 {
     __shared__ double sh[EV_THREADS / 32][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1215,7 +1426,7 @@ __global__ void evaluate_kernel(const PredArgs a, const int32_t* __restrict__ us
     int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
     const int64_t stride = (((int64_t)gridDim.x * blockDim.x) >> 5) * 32;
     for (; base < n; base += stride) {
-        const PairDots pd = pair_dots(a, users, items, base, n, lane);
+        const PairDots pd = pair_dots<L, V, ROWS>(a, users, items, base, n, lane);
         if (base + lane >= n) continue;
         const float pr = predict_from_dot(a, pd);
         const float r = values[base + lane];
@@ -1229,9 +1440,15 @@ __global__ void evaluate_kernel(const PredArgs a, const int32_t* __restrict__ us
         if (loss == MML_LOSS_MAE) s3 += (double)fabsf(err);
         else if (loss == MML_LOSS_RMSE) { const double d = (double)err; s3 += d * d; }
         else {
-            double pl = pn < 0.0 ? 0.0 : (pn > 1.0 ? 1.0 : pn);
-            s3 -= an * log(pl);
-            s3 -= (1.0 - an) * log(1.0 - pl);
+            // Eval/Measures/LogisticLoss.cs:37-57 divides by rating_range_size as the model holds it: 0 while InitModel
+            // computes the bold driver's first last_loss (BiasedMatrixFactorization.cs:168-169 runs before :186), which makes
+            // that loss NaN and the first UpdateLearnRate comparison a no-op -- kept by using a.range, not max - min
+            double pl = ((double)pr - (double)a.minr) / (double)a.range;
+            const double al = ((double)r - (double)a.minr) / (double)a.range;
+            if (pl < 0.0) pl = 0.0;
+            if (pl > 1.0) pl = 1.0;
+            s3 -= al * log(pl);
+            s3 -= (1.0 - al) * log(1.0 - pl);
         }
     }
     // lanes hold their own pairs' sums: butterfly over the warp, then over the block's warps in a fixed order
@@ -1327,10 +1544,48 @@ static void pick_kernels(bool async, bool biased, bool stage, slot_fn_t* sf, epo
     else pick_kernels2<L, KPL, false>(biased, stage, sf, ef);
 }
 
+template <int L, int KPL, bool PREF, int MINB>
+static void pick_kernels_v2(bool biased, slot_fn_t* sf, epoch_fn_t* ef)
+{
+    if (biased) { *sf = sgd_slot2_kernel<L, KPL, true, PREF, MINB>; *ef = sgd_epoch2_kernel<L, KPL, true, PREF, MINB>; }
+    else { *sf = sgd_slot2_kernel<L, KPL, false, PREF, MINB>; *ef = sgd_epoch2_kernel<L, KPL, false, PREF, MINB>; }
+}
+
+// Lanes per worker of the async kernels for padded row length kp under kernel variant `variant` (see Sgd::variant)
+static int async_lanes(int kp, int variant)
+{
+    const int base = kp <= 64 ? 8 : (kp == 128 ? 16 : 32);
+    return (variant == 2 || variant == 4) ? base / 2 : base;
+}
+
 // kp = 32: 8 lanes x 4 floats (4 ratings per warp) ; 64: 8 x 8 ; 128: 16 x 8 (2 per warp) ; 256: 32 x 8
 static int32_t get_kernels(Sgd& m, slot_fn_t* sf, epoch_fn_t* ef)
 {
     const bool stage = m.stage_bytes > 0, async = m.p.intra_block == MML_INTRA_ASYNC;
+    if (async && m.variant > 0) {
+        const bool b = m.p.biased != 0;
+        const int key = m.kp * 10 + m.variant;
+        switch (key) {
+            case 321: pick_kernels_v2<8, 4, true, 1>(b, sf, ef); break;
+            case 641: pick_kernels_v2<8, 8, true, 1>(b, sf, ef); break;
+            case 1281: pick_kernels_v2<16, 8, true, 1>(b, sf, ef); break;
+            case 2561: pick_kernels_v2<32, 8, true, 1>(b, sf, ef); break;
+            case 322: pick_kernels_v2<4, 8, true, 1>(b, sf, ef); break;
+            case 642: pick_kernels_v2<4, 16, true, 1>(b, sf, ef); break;
+            case 1282: pick_kernels_v2<8, 16, true, 1>(b, sf, ef); break;
+            case 2562: pick_kernels_v2<16, 16, true, 1>(b, sf, ef); break;
+            case 323: pick_kernels_v2<8, 4, false, 2>(b, sf, ef); break;
+            case 643: pick_kernels_v2<8, 8, false, 2>(b, sf, ef); break;
+            case 1283: pick_kernels_v2<16, 8, false, 2>(b, sf, ef); break;
+            case 2563: pick_kernels_v2<32, 8, false, 2>(b, sf, ef); break;
+            case 324: pick_kernels_v2<4, 8, false, 1>(b, sf, ef); break;
+            case 644: pick_kernels_v2<4, 16, false, 1>(b, sf, ef); break;
+            case 1284: pick_kernels_v2<8, 16, false, 1>(b, sf, ef); break;
+            case 2564: pick_kernels_v2<16, 16, false, 1>(b, sf, ef); break;
+            default: set_error("unsupported kernel variant %d for kp=%d", m.variant, m.kp); return MML_ERR_UNSUPPORTED;
+        }
+        return MML_OK;
+    }
     switch (m.kp) {
         case 32: pick_kernels<8, 4>(async, m.p.biased != 0, stage, sf, ef); break;
         case 64: pick_kernels<8, 8>(async, m.p.biased != 0, stage, sf, ef); break;
@@ -1372,14 +1627,30 @@ static PredArgs make_pred_args(Sgd& m)
 }
 
 // sums of evaluate_kernel over device-resident (users, items, values)
-static int32_t evaluate_device(Sgd& m, const int32_t* d_u, const int32_t* d_i, const float* d_v, int64_t n, double* sums4)
+template <bool ROWS>
+static void launch_evaluate(Sgd& m, int blocks, const int32_t* d_u, const int32_t* d_i, const float* d_v, int64_t n, double* part)
+{
+    cudaStream_t s = m.ctx->stream;
+    const PredArgs a = make_pred_args(m);
+    switch (m.kp) {
+        case 32: evaluate_kernel<8, 1, ROWS><<<blocks, EV_THREADS, 0, s>>>(a, d_u, d_i, d_v, n, m.p.loss, part); break;
+        case 64: evaluate_kernel<16, 1, ROWS><<<blocks, EV_THREADS, 0, s>>>(a, d_u, d_i, d_v, n, m.p.loss, part); break;
+        case 128: evaluate_kernel<16, 2, ROWS><<<blocks, EV_THREADS, 0, s>>>(a, d_u, d_i, d_v, n, m.p.loss, part); break;
+        default: evaluate_kernel<32, 2, ROWS><<<blocks, EV_THREADS, 0, s>>>(a, d_u, d_i, d_v, n, m.p.loss, part); break;
+    }
+}
+
+// rows = true: d_u / d_i hold internal factor rows (the async strata entries) instead of ids
+static int32_t evaluate_device(Sgd& m, const int32_t* d_u, const int32_t* d_i, const float* d_v, int64_t n, double* sums4,
+                               bool rows = false)
 {
     cudaStream_t s = m.ctx->stream;
     MML_TRY(sync_items(m));
     const int blocks = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(n * 32, EV_THREADS * 4), 1), 148 * 8);
     DevBuf<double>& part = m.scr_part;
     if (part.n < (size_t)blocks * 4) MML_TRY(part.alloc((size_t)148 * 8 * 4));
-    evaluate_kernel<<<blocks, EV_THREADS, 0, s>>>(make_pred_args(m), d_u, d_i, d_v, n, m.p.loss, part.p);
+    if (rows) launch_evaluate<true>(m, blocks, d_u, d_i, d_v, n, part.p);
+    else launch_evaluate<false>(m, blocks, d_u, d_i, d_v, n, part.p);
     MML_CUDA(cudaGetLastError());
     m.launches++;
     std::vector<double> h((size_t)blocks * 4);
@@ -1388,6 +1659,15 @@ static int32_t evaluate_device(Sgd& m, const int32_t* d_u, const int32_t* d_i, c
     for (int c = 0; c < 4; c++) sums4[c] = 0;
     for (int b = 0; b < blocks; b++) for (int c = 0; c < 4; c++) sums4[c] += h[(size_t)b * 4 + c];
     return MML_OK;
+}
+
+// The training set: through the async strata entries when there are any -- (internal user row, internal item row, value)
+// sorted by block and user, i.e. no id translation and a user row shared by consecutive pairs -- else in COO order.
+static int32_t evaluate_train_device(Sgd& m, double* sums4)
+{
+    const bool rows = m.p.schedule == MML_SCHEDULE_DSGD && m.p.intra_block == MML_INTRA_ASYNC && m.ent_u.p != nullptr;
+    if (rows) return evaluate_device(m, m.ent_u.p, m.ent_i.p, m.ent_v.p, m.ratings->n, sums4, true);
+    return evaluate_device(m, m.ratings->users.p, m.ratings->items.p, m.ratings->values.p, m.ratings->n, sums4);
 }
 
 // Sum over ranks of per-rank partial sums (and of the rating count n)
@@ -1441,7 +1721,7 @@ static int32_t regterm(Sgd& m, bool user_side, double* out)
 static int32_t objective(Sgd& m, double* out)
 {
     double sums[4];
-    MML_TRY(evaluate_device(m, m.ratings->users.p, m.ratings->items.p, m.ratings->values.p, m.ratings->n, sums));
+    MML_TRY(evaluate_train_device(m, sums));
     double ru = 0, ri = 0;
     MML_TRY(regterm(m, true, &ru));
     MML_TRY(regterm(m, false, &ri));
@@ -1664,7 +1944,12 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
         // fall back step by step when that does not fit.
         int max_optin = 0;
         cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-        const int lanes = m.kp <= 64 ? 8 : (m.kp == 128 ? 16 : 32);
+        {   // experiment knob: instruction-stream variant of the async epoch kernel (0 = round-1 loop)
+            const char* ev = getenv("MMLB200_SGD_VARIANT");
+            m.variant = ev && *ev ? atoi(ev) : 0;
+            if (m.variant < 0 || m.variant > 4) m.variant = 0;
+        }
+        const int lanes = async_lanes(m.kp, m.variant);
         const int n_workers = m.W * (32 / lanes);
         int64_t hot_min = 0;
         const bool async = dsgd && p->intra_block == MML_INTRA_ASYNC;
@@ -1962,6 +2247,30 @@ extern "C" int32_t mml_sgd_iterate_indices(mml_sgd* h, const int32_t* indices, i
     return MML_OK;
 }
 
+extern "C" int32_t mml_sgd_learn_factors(mml_sgd* h, const int32_t* indices, int64_t n, int32_t update_user, int32_t update_item,
+                                         int32_t num_iter)
+{
+    MML_LOCK((h ? h->m.ctx : nullptr));
+    MML_CHECK(h && (indices || n == 0), MML_ERR_ARG, "mml_sgd_learn_factors: NULL argument");
+    MML_CHECK(num_iter >= 0, MML_ERR_ARG, "mml_sgd_learn_factors: num_iter = %d", num_iter);
+    Sgd& m = h->m;
+    MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_learn_factors: no model");
+    MML_CUDA(cudaSetDevice(m.ctx->device));
+    for (int64_t t = 0; t < n; t++)
+        MML_CHECK(indices[t] >= 0 && indices[t] < m.ratings->n, MML_ERR_ARG, "indices[%lld] out of range", (long long)t);
+    DevBuf<int32_t> d;
+    MML_TRY(d.alloc(n));
+    if (n > 0) MML_CUDA(cudaMemcpyAsync(d.p, indices, sizeof(int32_t) * n, cudaMemcpyHostToDevice, m.ctx->stream));
+    // MatrixFactorization.cs:198-202: NumIter passes of Iterate(list, ...); plain MF's Iterate(list) ends with UpdateLearnRate
+    // (:195), the biased override (BiasedMatrixFactorization.cs:264-310) does not touch the learn rate
+    for (int32_t it = 0; it < num_iter; it++) {
+        MML_TRY(run_serial(m, d.p, n, update_user, update_item));
+        if (!m.p.biased) MML_TRY(update_learnrate(m));
+    }
+    MML_CUDA(cudaStreamSynchronize(m.ctx->stream));
+    return MML_OK;
+}
+
 extern "C" int32_t mml_sgd_predict(mml_sgd* h, const int32_t* users, const int32_t* items, int64_t n, float* out)
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
@@ -1978,7 +2287,16 @@ extern "C" int32_t mml_sgd_predict(mml_sgd* h, const int32_t* users, const int32
     if (dout.n < (size_t)n) MML_TRY(dout.alloc(n));
     MML_CUDA(cudaMemcpyAsync(du.p, users, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
     MML_CUDA(cudaMemcpyAsync(di.p, items, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
-    predict_kernel<<<grid_n(n * 32), 256, 0, s>>>(make_pred_args(m), du.p, di.p, n, dout.p);
+    {
+        const PredArgs a = make_pred_args(m);
+        const int g = grid_n(n * 32);
+        switch (m.kp) {
+            case 32: predict_kernel<8, 1><<<g, 256, 0, s>>>(a, du.p, di.p, n, dout.p); break;
+            case 64: predict_kernel<16, 1><<<g, 256, 0, s>>>(a, du.p, di.p, n, dout.p); break;
+            case 128: predict_kernel<16, 2><<<g, 256, 0, s>>>(a, du.p, di.p, n, dout.p); break;
+            default: predict_kernel<32, 2><<<g, 256, 0, s>>>(a, du.p, di.p, n, dout.p); break;
+        }
+    }
     MML_CUDA(cudaGetLastError());
     m.launches++;
     MML_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
@@ -2025,7 +2343,7 @@ extern "C" int32_t mml_sgd_evaluate_train(mml_sgd* h, float* out4)
     MML_CHECK(m.ratings->n > 0 || m.R > 1, MML_ERR_ARG, "mml_sgd_evaluate_train: empty training set");
     MML_CUDA(cudaSetDevice(m.ctx->device));
     double sums[5];
-    MML_TRY(evaluate_device(m, m.ratings->users.p, m.ratings->items.p, m.ratings->values.p, m.ratings->n, sums));
+    MML_TRY(evaluate_train_device(m, sums));
     sums[4] = (double)m.ratings->n;
     MML_TRY(reduce_over_ranks(m, sums, 5));
     sums_to_measures(m, sums, (int64_t)sums[4], out4);

@@ -166,6 +166,11 @@ class SgdModel:
         idx = _i32(indices)
         check(self.lib.mml_sgd_iterate_indices(self.h, idx, idx.shape[0], int(update_user), int(update_item)))
 
+    def learn_factors(self, indices, num_iter, update_user=True, update_item=True):
+        """LearnFactors (MatrixFactorization.cs:198-202): num_iter passes of Iterate(indices, update_user, update_item)."""
+        idx = _i32(indices)
+        check(self.lib.mml_sgd_learn_factors(self.h, idx, idx.shape[0], int(update_user), int(update_item), int(num_iter)))
+
     def fold_in(self, rated_items, rated_values, init_factors, num_iter):
         """Batch FoldIn: rated_items / rated_values are per-user sequences (already shuffled), init_factors [n, k]."""
         n = len(rated_items)

@@ -193,13 +193,14 @@ class MatrixFactorization(_Recommender):
 
     def _retrain(self, entity_id, by_item):
         """RetrainUser / RetrainItem (MatrixFactorization.cs:141-160, BiasedMatrixFactorization.cs:419-431): the row is
-        re-drawn (RowInitNormal, host RNG), the bias zeroed (biased model), then one pass over ByUser[u] / ByItem[i]
-        in ascending rating-index order updating that side only (LearnFactors -> Iterate(list, ...))."""
+        re-drawn (RowInitNormal, host RNG), the bias zeroed (biased model), then LearnFactors (:198-202): NumIter passes
+        over ByUser[u] / ByItem[i] in ascending rating-index order updating that side only; plain MF decays the learn
+        rate after every pass (:195)."""
         row = sysrandom.get_instance().init_normal(1, int(self.NumFactors), self.InitMean, self.InitStdDev)
         self._model.set_rows([entity_id], row, [0.0] if self._biased else None, by_item=by_item)
         ids = self.Ratings.Items if by_item else self.Ratings.Users
         idx = np.nonzero(ids == entity_id)[0].astype(np.int32)
-        self._model.iterate_indices(idx, update_user=not by_item, update_item=by_item)
+        self._model.learn_factors(idx, int(self.NumIter), update_user=not by_item, update_item=by_item)
 
     def RetrainUser(self, user_id):
         if self.UpdateUsers:

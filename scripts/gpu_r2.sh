@@ -1,0 +1,24 @@
+#!/bin/bash
+# One parameterised runner for the round-2 GPU calls: scripts/gpu_r2.sh <tag> <step> [<step> ...]; every step logs to
+# gpurun_out/<tag>_<step>.log with its exit code on the last line. Steps:
+#   pytest | smoke | bench | benchref | bolddiag | variants | sanitizer | hosttest | <anything else>: run as a command
+tag=$1; shift
+mkdir -p gpurun_out
+for step in "$@"; do
+  log=gpurun_out/${tag}_${step//[^a-zA-Z0-9]/_}.log
+  case "$step" in
+    pytest)   ( time timeout 1500 python -m pytest tests -m gpu -x -q -s ) > $log 2>&1 ;;
+    smoke)    ( time timeout 300 python -c "import __graft_entry__ as g; g.smoke()" ) > $log 2>&1 ;;
+    bench)    ( time timeout 900 python bench.py ) > $log 2>&1 ;;
+    benchref) ( time timeout 600 python bench.py --impl reference ) > $log 2>&1 ;;
+    bolddiag) ( timeout 300 python scripts/diag_bold_driver.py 0.01 0.6 ) > $log 2>&1 ;;
+    variants) ( timeout 600 python scripts/sweep_groups.py --workload netflix --epochs 6 --variants 0,1,2,4 --shapes 37x4 &&
+                timeout 300 python scripts/sweep_groups.py --workload netflix --epochs 6 --variants 3 --shapes 37x8,74x4 &&
+                timeout 300 python scripts/sweep_groups.py --workload ml10m --epochs 6 --variants 0,1,2,4 --shapes 37x4,9x16 &&
+                timeout 300 python scripts/sweep_groups.py --workload ml10m --epochs 6 --variants 3 --shapes 37x8,18x16 ) > $log 2>&1 ;;
+    hosttest) ( LD_LIBRARY_PATH=/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/cuda_runtime/lib:$LD_LIBRARY_PATH timeout 60 tests/cpp/build/host_test gpu tests/golden/example.train tests/golden/example.test gpurun_out ) > $log 2>&1 ;;
+    *)        ( eval "timeout 900 $step" ) > $log 2>&1 ;;
+  esac
+  echo "rc=$?" >> $log
+  echo "== $step: $(tail -n 1 $log)"; tail -n 4 $log | head -n 3
+done

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--shapes", default="148x1,74x2,37x4,18x8,9x16,4x37,2x74,1x148")
     ap.add_argument("--subgroups", type=int, default=16)
     ap.add_argument("--pop-offset", type=float, default=None)
+    ap.add_argument("--variants", default="", help="comma list of MMLB200_SGD_VARIANT values; every shape runs under each")
     args = ap.parse_args()
     from mymedialite_b200 import engine
     d, k, desc = bench.make_data(args.workload, 0, 1, args.pop_offset)
@@ -56,11 +57,19 @@ def main():
         th.start()
 
     results = []
-    for shape in args.shapes.split(","):
+    variants = [v for v in args.variants.split(",") if v != ""] or [None]
+    for variant, shape in [(v, s) for v in variants for s in args.shapes.split(",")]:
         G, cpg = (int(x) for x in shape.split("x"))
+        if variant is not None:
+            os.environ["MMLB200_SGD_VARIANT"] = variant
+            shape = "v%s:%s" % (variant, shape)
         t0 = time.time()
         params = engine.default_params(biased=1, num_factors=k, num_groups=G, ctas_per_group=cpg, num_subgroups=args.subgroups)
-        model = engine.SgdModel(ctx, ratings, params)
+        try:
+            model = engine.SgdModel(ctx, ratings, params)
+        except Exception as ex:          # e.g. a grid the variant's register budget cannot keep co-resident
+            print(json.dumps({"shape": shape, "error": str(ex)}), flush=True)
+            continue
         if U0 is not None:
             model.set_model(U0, V0)
         else:
@@ -86,7 +95,7 @@ def main():
         for r in results:
             dtr = max(abs(a - b) / b for a, b in zip(r["train"], oracle_out["train"]))
             dte = max(abs(a - b) / b for a, b in zip(r["test"], oracle_out["test"]))
-            print("%-8s %8.3f ms  max rel dev train %.4f test %.4f" % (r["shape"], r["ms_med"], dtr, dte), flush=True)
+            print("%-12s %8.3f ms  max rel dev train %.4f test %.4f" % (r["shape"], r["ms_med"], dtr, dte), flush=True)
 
 
 if __name__ == "__main__":

@@ -102,9 +102,11 @@ def test_fold_in_rejects_unknown_items(eng):
 
 @pytest.mark.parametrize("biased", [True, False])
 def test_retrain_user_and_item_match_oracle(eng, biased):
-    """RetrainUser / RetrainItem: row re-drawn by the host RNG, bias zeroed, one pass over ByUser / ByItem updating that
-    side only; RemoveUser zeroes the row."""
+    """RetrainUser / RetrainItem (MatrixFactorization.cs:141-160): row re-drawn by the host RNG, bias zeroed, then
+    LearnFactors (:198-202) = NumIter passes over ByUser / ByItem updating that side only (plain MF decays the learn rate
+    after every pass, :195); RemoveUser zeroes the row."""
     k = 16
+    num_iter = 7
     (u, i, v), om, gm, r = trained_pair(eng, biased, k)
     rng = np.random.default_rng(4)
     for ent, by_item in ((5, False), (17, True), (0, False)):
@@ -120,8 +122,9 @@ def test_retrain_user_and_item_match_oracle(eng, biased):
                 om.user_bias[ent] = 0
             idx = np.nonzero(u == ent)[0].astype(np.int32)
         gm.set_rows([ent], row, [0.0] if biased else None, by_item=by_item)
-        om.iterate_indices(idx, update_user=not by_item, update_item=by_item)
-        gm.iterate_indices(idx, update_user=not by_item, update_item=by_item)
+        for _ in range(num_iter):
+            om.iterate_indices(idx, update_user=not by_item, update_item=by_item)
+        gm.learn_factors(idx, num_iter, update_user=not by_item, update_item=by_item)
     g = gm.get_model()
     np.testing.assert_allclose(g["U"], om.user_factors, rtol=5e-5, atol=5e-5)
     np.testing.assert_allclose(g["V"], om.item_factors, rtol=5e-5, atol=5e-5)
