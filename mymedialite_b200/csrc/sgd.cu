@@ -925,7 +925,9 @@ __device__ __forceinline__ void sgd_block_async(const SgdArgs& a, const int j, c
 //     computing into copies that are committed under a predicate;
 //   * no forwarding of a just-updated item row to the next rating (the next rating of a user run never has the same item,
 //     and across runs the row comes back from the L2 like everybody else's steps);
-//   * PREF = false: the next user's row is not held in registers ahead of time (8 + 2 registers less: two CTAs per SM).
+// Measured on config 4 (profiles/r2_sgd_variants.log): 16.17 ms (first form) -> 15.78 ms (this form, 16 lanes x 8 floats) ->
+// 14.69 ms (8 lanes x 16 floats: four ratings per warp instruction share the scalar part); cutting the registers to 64 for two
+// CTAs per SM (no next-user row held ahead) gave 14.79 ms and was dropped. At k = 64 the 8 x 8 shape stays (4 x 16 is slower).
 template <int KPL>
 struct Row2 {
     float2 r[KPL / 2];
@@ -957,7 +959,7 @@ __device__ __forceinline__ void row2_store(const Row2<KPL>& d, float* row, int s
         reinterpret_cast<float4*>(row)[v * L + sl] = make_float4(d.r[2 * v].x, d.r[2 * v].y, d.r[2 * v + 1].x, d.r[2 * v + 1].y);
 }
 
-template <int L, int KPL, bool BIASED, bool PREF>
+template <int L, int KPL, bool BIASED>
 __device__ __forceinline__ void sgd_block_async2(const SgdArgs& a, const AsyncHead& head)
 {
     constexpr int KP = L * KPL;
@@ -972,11 +974,9 @@ __device__ __forceinline__ void sgd_block_async2(const SgdArgs& a, const AsyncHe
 #pragma unroll
     for (int f = 0; f < KPL / 2; f++) { p.r[f] = make_float2(0.f, 0.f); pn.r[f] = p.r[f]; qn.r[f] = p.r[f]; }
     if (e0 < e1) {
-        if (PREF) {
-            row2_load<L, KPL>(pn, a.P + (size_t)u1 * KP, sl);
-            if (BIASED) bun = a.bu[u1];
-            if (a.regw_u) regun = a.regw_u[u1];
-        }
+        row2_load<L, KPL>(pn, a.P + (size_t)u1 * KP, sl);
+        if (BIASED) bun = a.bu[u1];
+        if (a.regw_u) regun = a.regw_u[u1];
         row2_load_cg<L, KPL>(qn, Qg + (size_t)i1 * KP, sl);
         if (BIASED) bin = ld_cg_f(Bg + i1);
     }
@@ -995,15 +995,9 @@ __device__ __forceinline__ void sgd_block_async2(const SgdArgs& a, const AsyncHe
                 row2_store<L, KPL>(p, a.P + (size_t)cur_u * KP, sl);
                 if (BIASED) a.bu[cur_u] = bu_v;
             }
-            if (PREF) {
 #pragma unroll
-                for (int f = 0; f < KPL / 2; f++) p.r[f] = pn.r[f];
-                bu_v = bun; regu = regun;
-            } else {
-                row2_load<L, KPL>(p, a.P + (size_t)u * KP, sl);
-                if (BIASED) bu_v = a.bu[u];
-                if (a.regw_u) regu = a.regw_u[u];
-            }
+            for (int f = 0; f < KPL / 2; f++) p.r[f] = pn.r[f];
+            bu_v = bun; regu = regun;
             cur_u = u;
         }
         Row2<KPL> q;
@@ -1013,7 +1007,7 @@ __device__ __forceinline__ void sgd_block_async2(const SgdArgs& a, const AsyncHe
         if (e + 1 < e1) {   // next entry: its item row, and its user row if a new run starts
             row2_load_cg<L, KPL>(qn, Qg + (size_t)i1 * KP, sl);
             if (BIASED) bin = ld_cg_f(Bg + i1);
-            if (PREF && u1 != cur_u) {
+            if (u1 != cur_u) {
                 row2_load<L, KPL>(pn, a.P + (size_t)u1 * KP, sl);
                 if (BIASED) bun = a.bu[u1];
                 if (a.regw_u) regun = a.regw_u[u1];
@@ -1119,16 +1113,16 @@ __global__ void __launch_bounds__(512) sgd_epoch_kernel(const SgdArgs a)
     }
 }
 
-// The same two kernels on sgd_block_async2 (async mode only). MINB = CTAs per SM the register budget is cut for.
-template <int L, int KPL, bool BIASED, bool PREF, int MINB>
-__global__ void __launch_bounds__(512, MINB) sgd_slot2_kernel(const SgdArgs a, const int slot)
+// The same two kernels on sgd_block_async2 (async mode only).
+template <int L, int KPL, bool BIASED>
+__global__ void __launch_bounds__(512) sgd_slot2_kernel(const SgdArgs a, const int slot)
 {
     const int j = blockIdx.x / a.cpg, sub = blockIdx.x % a.cpg;
-    sgd_block_async2<L, KPL, BIASED, PREF>(a, async_head<L>(a, j, sub, slot));
+    sgd_block_async2<L, KPL, BIASED>(a, async_head<L>(a, j, sub, slot));
 }
 
-template <int L, int KPL, bool BIASED, bool PREF, int MINB>
-__global__ void __launch_bounds__(512, MINB) sgd_epoch2_kernel(const SgdArgs a)
+template <int L, int KPL, bool BIASED>
+__global__ void __launch_bounds__(512) sgd_epoch2_kernel(const SgdArgs a)
 {
     const int cpg = a.cpg;
     const int j = blockIdx.x / cpg, sub = blockIdx.x % cpg;
@@ -1148,7 +1142,7 @@ __global__ void __launch_bounds__(512, MINB) sgd_epoch2_kernel(const SgdArgs a)
             }
             __syncthreads();
         }
-        sgd_block_async2<L, KPL, BIASED, PREF>(a, head);
+        sgd_block_async2<L, KPL, BIASED>(a, head);
         head = next;
         if (a.G > 1) {
             __threadfence();
@@ -1194,7 +1188,7 @@ __global__ void sgd_serial_kernel(const SgdArgs a, const int32_t* __restrict__ i
             const float bu = *pbu, bi = *pbi;
             const double score = (double)__fadd_rn(__fadd_rn(__fadd_rn(a.gb, bu), bi), dot);
             const double sig = 1.0 / (1.0 + exp(-score));
-            const double pred = (double)a.minr + sig * (double)a.range;
+            const double pred = __dadd_rn((double)a.minr, __dmul_rn(sig, (double)a.range));   // no FMA contraction: the CLR does not fuse
             const double err = (double)r - pred;
             if (a.loss == MML_LOSS_RMSE) gc = (float)(err * sig * (1.0 - sig) * (double)a.range);
             else if (a.loss == MML_LOSS_MAE) gc = (float)((err > 0 ? 1.0 : (err < 0 ? -1.0 : 0.0)) * sig * (1.0 - sig) * (double)a.range);
@@ -1210,8 +1204,8 @@ __global__ void sgd_serial_kernel(const SgdArgs a, const int32_t* __restrict__ i
         for (int s = 0; s < nslot; s++) {
             const double uf = pv[s], vf = qv[s];
             if (BIASED) {
-                if (update_user) prow[s * 32 + lane] = __fadd_rn(pv[s], (float)((double)a.lr * ((double)gc * vf - (double)regu * uf)));
-                if (update_item) qrow[s * 32 + lane] = __fadd_rn(qv[s], (float)((double)a.lr * ((double)gc * uf - (double)regi * vf)));
+                if (update_user) prow[s * 32 + lane] = __fadd_rn(pv[s], (float)__dmul_rn((double)a.lr, __dsub_rn(__dmul_rn((double)gc, vf), __dmul_rn((double)regu, uf))));
+                if (update_item) qrow[s * 32 + lane] = __fadd_rn(qv[s], (float)__dmul_rn((double)a.lr, __dsub_rn(__dmul_rn((double)gc, uf), __dmul_rn((double)regi, vf))));
             } else {
                 // MatrixFactorization.cs:181-191: err * i_f and Regularization * u_f are float products
                 if (update_user) prow[s * 32 + lane] = __fadd_rn(pv[s], (float)((double)a.lr * (double)__fsub_rn(__fmul_rn(gc, qv[s]), __fmul_rn(regu, pv[s]))));
@@ -1391,7 +1385,7 @@ __device__ __forceinline__ float predict_from_dot(const PredArgs& a, const PairD
         if (ku) score += a.bu[r.urow];
         if (ki) score += a.bi[r.irow];
         if (ku && ki) score += r.dot;
-        return (float)((double)a.minr + (1.0 / (1.0 + exp(-score))) * (double)a.range);
+        return (float)__dadd_rn((double)a.minr, __dmul_rn(1.0 / (1.0 + exp(-score)), (double)a.range));
     }
     if (!ku || !ki) return a.gb;
     float res = a.gb + r.dot;
@@ -1544,45 +1538,33 @@ static void pick_kernels(bool async, bool biased, bool stage, slot_fn_t* sf, epo
     else pick_kernels2<L, KPL, false>(biased, stage, sf, ef);
 }
 
-template <int L, int KPL, bool PREF, int MINB>
+template <int L, int KPL>
 static void pick_kernels_v2(bool biased, slot_fn_t* sf, epoch_fn_t* ef)
 {
-    if (biased) { *sf = sgd_slot2_kernel<L, KPL, true, PREF, MINB>; *ef = sgd_epoch2_kernel<L, KPL, true, PREF, MINB>; }
-    else { *sf = sgd_slot2_kernel<L, KPL, false, PREF, MINB>; *ef = sgd_epoch2_kernel<L, KPL, false, PREF, MINB>; }
+    if (biased) { *sf = sgd_slot2_kernel<L, KPL, true>; *ef = sgd_epoch2_kernel<L, KPL, true>; }
+    else { *sf = sgd_slot2_kernel<L, KPL, false>; *ef = sgd_epoch2_kernel<L, KPL, false>; }
 }
 
-// Lanes per worker of the async kernels for padded row length kp under kernel variant `variant` (see Sgd::variant)
+// Async epoch kernel: which loop (Sgd::variant: 0 = sgd_block_async, 1 = sgd_block_async2) and how many lanes per worker
+// for padded row length kp. Default: the second form everywhere, 8 lanes x 16 floats at kp = 128.
 static int async_lanes(int kp, int variant)
 {
-    const int base = kp <= 64 ? 8 : (kp == 128 ? 16 : 32);
-    return (variant == 2 || variant == 4) ? base / 2 : base;
+    if (variant == 0) return kp <= 64 ? 8 : (kp == 128 ? 16 : 32);
+    return kp <= 128 ? 8 : 32;
 }
 
-// kp = 32: 8 lanes x 4 floats (4 ratings per warp) ; 64: 8 x 8 ; 128: 16 x 8 (2 per warp) ; 256: 32 x 8
+// kp = 32: 8 lanes x 4 floats (4 ratings per warp) ; 64: 8 x 8 ; 128: 16 x 8 (first form) or 8 x 16 ; 256: 32 x 8
 static int32_t get_kernels(Sgd& m, slot_fn_t* sf, epoch_fn_t* ef)
 {
     const bool stage = m.stage_bytes > 0, async = m.p.intra_block == MML_INTRA_ASYNC;
     if (async && m.variant > 0) {
         const bool b = m.p.biased != 0;
-        const int key = m.kp * 10 + m.variant;
-        switch (key) {
-            case 321: pick_kernels_v2<8, 4, true, 1>(b, sf, ef); break;
-            case 641: pick_kernels_v2<8, 8, true, 1>(b, sf, ef); break;
-            case 1281: pick_kernels_v2<16, 8, true, 1>(b, sf, ef); break;
-            case 2561: pick_kernels_v2<32, 8, true, 1>(b, sf, ef); break;
-            case 322: pick_kernels_v2<4, 8, true, 1>(b, sf, ef); break;
-            case 642: pick_kernels_v2<4, 16, true, 1>(b, sf, ef); break;
-            case 1282: pick_kernels_v2<8, 16, true, 1>(b, sf, ef); break;
-            case 2562: pick_kernels_v2<16, 16, true, 1>(b, sf, ef); break;
-            case 323: pick_kernels_v2<8, 4, false, 2>(b, sf, ef); break;
-            case 643: pick_kernels_v2<8, 8, false, 2>(b, sf, ef); break;
-            case 1283: pick_kernels_v2<16, 8, false, 2>(b, sf, ef); break;
-            case 2563: pick_kernels_v2<32, 8, false, 2>(b, sf, ef); break;
-            case 324: pick_kernels_v2<4, 8, false, 1>(b, sf, ef); break;
-            case 644: pick_kernels_v2<4, 16, false, 1>(b, sf, ef); break;
-            case 1284: pick_kernels_v2<8, 16, false, 1>(b, sf, ef); break;
-            case 2564: pick_kernels_v2<16, 16, false, 1>(b, sf, ef); break;
-            default: set_error("unsupported kernel variant %d for kp=%d", m.variant, m.kp); return MML_ERR_UNSUPPORTED;
+        switch (m.kp) {
+            case 32: pick_kernels_v2<8, 4>(b, sf, ef); break;
+            case 64: pick_kernels_v2<8, 8>(b, sf, ef); break;
+            case 128: pick_kernels_v2<8, 16>(b, sf, ef); break;
+            case 256: pick_kernels_v2<32, 8>(b, sf, ef); break;
+            default: set_error("unsupported num_factors"); return MML_ERR_UNSUPPORTED;
         }
         return MML_OK;
     }
@@ -1944,10 +1926,9 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
         // fall back step by step when that does not fit.
         int max_optin = 0;
         cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-        {   // experiment knob: instruction-stream variant of the async epoch kernel (0 = round-1 loop)
+        {   // diagnostic knob: MMLB200_SGD_VARIANT=0 selects the first form of the async loop (sgd_block_async)
             const char* ev = getenv("MMLB200_SGD_VARIANT");
-            m.variant = ev && *ev ? atoi(ev) : 0;
-            if (m.variant < 0 || m.variant > 4) m.variant = 0;
+            m.variant = (ev && *ev == '0') ? 0 : 1;
         }
         const int lanes = async_lanes(m.kp, m.variant);
         const int n_workers = m.W * (32 / lanes);
@@ -2513,7 +2494,7 @@ __global__ void __launch_bounds__(128) fold_in_kernel(const PredArgs a, const Fo
             if (BIASED) {
                 const double score = (double)__fadd_rn(__fadd_rn(__fadd_rn(a.gb, ub), a.bi[row]), dot);
                 const double sig = 1.0 / (1.0 + exp(-score));
-                const double pred = (double)a.minr + sig * (double)a.range;
+                const double pred = __dadd_rn((double)a.minr, __dmul_rn(sig, (double)a.range));
                 const double err = (double)r - pred;
                 float gc;
                 if (fa.loss == MML_LOSS_RMSE) gc = (float)(err * sig * (1.0 - sig) * (double)a.range);
@@ -2570,7 +2551,7 @@ __global__ void score_vectors_kernel(const PredArgs a, int32_t k, const float* _
         if (a.biased) {
             double score = (double)__fadd_rn(a.gb, v[0]);
             if (known) score += (double)__fadd_rn(a.bi[row], dot);
-            res = (float)((double)a.minr + 1.0 / (1.0 + exp(-score)) * (double)a.range);
+            res = (float)__dadd_rn((double)a.minr, __dmul_rn(1.0 / (1.0 + exp(-score)), (double)a.range));
         } else {
             res = __fadd_rn(a.gb, dot);
             if (res > a.maxr) res = a.maxr;

@@ -25,7 +25,7 @@ struct Sgd {
     int32_t R = 1, rank = 0;           // GPU-level blocks (world size) and own block
     int32_t G = 1, W = 1;              // worker groups and warps per CTA
     int32_t cpg = 1;                   // CTAs per worker group (async mode; 1 otherwise)
-    int32_t variant = 0;               // async epoch kernel: 0 = sgd_block_async, 1..4 = sgd_block_async2 shapes (get_kernels)
+    int32_t variant = 1;               // async epoch kernel: 0 = sgd_block_async, 1 = sgd_block_async2 (get_kernels)
     int32_t hot_copies = 1;            // private copies of a hot item row inside a block
     GroupMap users, items;
     std::vector<int32_t> h_item_ptr;   // [R * G + 1] internal item row range of CTA-level item group (B, b)

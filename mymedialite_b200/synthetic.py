@@ -145,6 +145,34 @@ def implicit(n_users, n_items, n, seed=1):
     return _pairs(rng, n_users, n_items, n)
 
 
+def implicit_cuda(n_users, n_items, n, seed=1, device="cuda", pop_offset=None):
+    """n distinct (user, item) events by the same activity / popularity laws, generated with torch on the GPU (benchmark
+    plumbing for the 20M-event shape; deterministic for a seed on a given torch build, NOT the stream of implicit())."""
+    import torch
+    dev = torch.device(device)
+    g = torch.Generator(device=dev); g.manual_seed(int(seed))
+    act = torch.exp(torch.randn(n_users, generator=g, device=dev, dtype=torch.float64))
+    pop = 1.0 / (torch.arange(1, n_items + 1, device=dev, dtype=torch.float64) + (POP_OFFSET if pop_offset is None else pop_offset)) ** 0.8
+    pop = pop[torch.randperm(n_items, generator=g, device=dev)]
+    cdf = torch.cumsum(pop / pop.sum(), 0); cdf[-1] = 1.0
+    ucdf = torch.cumsum(act / act.sum(), 0); ucdf[-1] = 1.0
+    ar_u = torch.arange(n_users, device=dev, dtype=torch.int64); ar_i = torch.arange(n_items, device=dev, dtype=torch.int64)
+    keys = torch.unique(torch.cat([ar_u * n_items + torch.randint(0, n_items, (n_users,), generator=g, device=dev),
+                                   torch.randint(0, n_users, (n_items,), generator=g, device=dev) * n_items + ar_i]))
+    while keys.numel() < n:
+        draw = int((n - keys.numel()) * 1.15) + 1024
+        uu = torch.searchsorted(ucdf, torch.rand(draw, generator=g, device=dev, dtype=torch.float64), right=True).clamp_(max=n_users - 1)
+        ii = torch.searchsorted(cdf, torch.rand(draw, generator=g, device=dev, dtype=torch.float64), right=True).clamp_(max=n_items - 1)
+        keys = torch.unique(torch.cat([keys, uu * n_items + ii]))
+        del uu, ii
+    keys = keys[torch.randperm(keys.numel(), generator=g, device=dev)[:n]]
+    u = torch.div(keys, n_items, rounding_mode="floor"); i = keys - u * n_items
+    out = (u.to(torch.int32).cpu().numpy(), i.to(torch.int32).cpu().numpy())
+    del keys, u, i
+    torch.cuda.empty_cache()
+    return out
+
+
 def named(name, scale=1.0):
     nu, ni, n, levels, k, seed = SHAPES[name]
     if scale != 1.0:

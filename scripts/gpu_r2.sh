@@ -1,7 +1,7 @@
 #!/bin/bash
 # One parameterised runner for the round-2 GPU calls: scripts/gpu_r2.sh <tag> <step> [<step> ...]; every step logs to
 # gpurun_out/<tag>_<step>.log with its exit code on the last line. Steps:
-#   pytest | smoke | bench | benchref | bolddiag | variants | sanitizer | hosttest | <anything else>: run as a command
+#   pytest | smoke | bench | benchref | bolddiag | variants | ncusgd | hosttest | <anything else>: run as a command
 tag=$1; shift
 mkdir -p gpurun_out
 for step in "$@"; do
@@ -16,6 +16,11 @@ for step in "$@"; do
                 timeout 300 python scripts/sweep_groups.py --workload netflix --epochs 6 --variants 3 --shapes 37x8,74x4 &&
                 timeout 300 python scripts/sweep_groups.py --workload ml10m --epochs 6 --variants 0,1,2,4 --shapes 37x4,9x16 &&
                 timeout 300 python scripts/sweep_groups.py --workload ml10m --epochs 6 --variants 3 --shapes 37x8,18x16 ) > $log 2>&1 ;;
+    ncusgd)   # launch list + one full capture of the epoch kernel of the default bench workload (after a plain run of the same command)
+              ( CMD="python bench.py --sgd-only --no-cpu --steps 2 --warmup 3"
+                timeout 300 $CMD > gpurun_out/${tag}_ncusgd_plain.log 2>&1 &&
+                timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'sgd_|evaluate_|strata_|rs_|scan_|hist|init_rows|stats_' --csv --log-file gpurun_out/${tag}_sgd_launches.csv $CMD &&
+                timeout 600 ncu --set full --clock-control none --import-source on -k regex:sgd_epoch -s 3 -c 1 -f -o gpurun_out/${tag}_sgd_prof $CMD ) > $log 2>&1 ;;
     hosttest) ( LD_LIBRARY_PATH=/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/cuda_runtime/lib:$LD_LIBRARY_PATH timeout 60 tests/cpp/build/host_test gpu tests/golden/example.train tests/golden/example.test gpurun_out ) > $log 2>&1 ;;
     *)        ( eval "timeout 900 $step" ) > $log 2>&1 ;;
   esac
