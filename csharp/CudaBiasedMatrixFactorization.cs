@@ -58,18 +58,34 @@ namespace MyMediaLite.RatingPrediction
 			Mml.mml_mf_params_default(out p);
 			p.biased = Biased ? 1 : 0;
 			p.num_factors = (int) NumFactors; p.learn_rate = LearnRate; p.decay = Decay; p.regularization = Regularization;
-			p.schedule = Mml.SCHEDULE_SERIAL;
+			p.schedule = Parallel ? Mml.SCHEDULE_DSGD : Mml.SCHEDULE_SERIAL;
 			return p;
 		}
+
+		/// <summary>threads the reference would use: 1 for plain MF, MaxThreads for the biased model</summary>
+		protected virtual int Threads { get { return 1; } }
+
+		/// <summary>whether Iterate() runs the parallel epoch kernel (Mml.Order); several GPUs always do</summary>
+		protected bool Parallel
+		{
+			get
+			{
+				if (NumGpus > 1 || Mml.Order == Mml.EngineOrder.Parallel) return true;
+				if (Mml.Order == Mml.EngineOrder.Reference) return Threads > 1;
+				return Threads > 1 || (ratings != null && ratings.Count >= Mml.SerialBelow);
+			}
+		}
+		bool parallel_model;
 
 		/// <summary>InitModel (MatrixFactorization.cs:99-116): draws come from MyMediaLite.Random in the reference's order</summary>
 		protected internal virtual void InitModel()
 		{
-			IntPtr ctx = Mml.Context(), r, m;
+			IntPtr ctx = Mml.Context(NumGpus), r, m;
 			int n = ratings.Count;
 			Mml.Check(Mml.mml_ratings_create(ctx, AsArray(ratings.Users, n), AsArray(ratings.Items, n), AsArray(ratings.Values, n), n, MaxUserID, MaxItemID, out r));
 			dev_ratings = new MmlHandle(r, Mml.mml_ratings_destroy);
 			var p = Params();
+			parallel_model = p.schedule == Mml.SCHEDULE_DSGD;
 			Mml.Check(Mml.mml_sgd_create(ctx, r, ref p, null, null, out m));
 			model = new MmlHandle(m, Mml.mml_sgd_destroy);
 			var user_factors = new Matrix<float>(MaxUserID + 1, (int) NumFactors);
@@ -92,6 +108,15 @@ namespace MyMediaLite.RatingPrediction
 		{
 			lock (gate)
 			{
+				if (parallel_model)
+				{
+					int G, W; long rounds, staged;
+					Mml.Check(Mml.mml_sgd_strata_info(model.DangerousGetHandle(), out G, out W, out rounds, out staged));
+					var subepoch_sequence = new List<int>(Enumerable.Range(0, G));
+					subepoch_sequence.Shuffle();                            // BiasedMatrixFactorization.cs:210-211
+					Mml.Check(Mml.mml_sgd_iterate(model.DangerousGetHandle(), subepoch_sequence.ToArray(), null, 0));
+					return;
+				}
 				var index = AsArray(ratings.RandomIndex, ratings.Count);
 				Mml.Check(Mml.mml_sgd_iterate(model.DangerousGetHandle(), null, index, index.Length));
 			}
@@ -252,23 +277,14 @@ namespace MyMediaLite.RatingPrediction
 			p.frequency_regularization = FrequencyRegularization ? 1 : 0;
 			p.loss = Loss == OptimizationTarget.MAE ? Mml.LOSS_MAE : (Loss == OptimizationTarget.LogisticLoss ? Mml.LOSS_LOGISTIC : Mml.LOSS_RMSE);
 			p.bold_driver = BoldDriver ? 1 : 0; p.max_threads = MaxThreads;
-			// MaxThreads > 1 selects the reference's DSGD block schedule (:178-184); on the GPU the worker groups are CTAs
-			p.schedule = MaxThreads > 1 ? Mml.SCHEDULE_DSGD : Mml.SCHEDULE_SERIAL;
+			// MaxThreads > 1 selects the reference's DSGD block schedule (:178-184); on the GPU the worker groups are CTAs, and the
+			// parallel kernel is also what MaxThreads = 1 runs unless the engine order says Reference (base.Params, Mml.Order).
+			// NaiveParallelization (:136-141, :201-204): no block exclusivity -- the whole GPU is one worker group
+			if (p.schedule == Mml.SCHEDULE_DSGD && NaiveParallelization) { p.num_groups = 1; p.ctas_per_group = 1 << 16; }
 			return p;
 		}
 
-		public override void Iterate()
-		{
-			if (MaxThreads <= 1) { base.Iterate(); return; }
-			lock (gate)
-			{
-				int G, W; long rounds, staged;
-				Mml.Check(Mml.mml_sgd_strata_info(model.DangerousGetHandle(), out G, out W, out rounds, out staged));
-				var subepoch_sequence = Enumerable.Range(0, G).ToList();
-				subepoch_sequence.Shuffle();   // :210-211
-				Mml.Check(Mml.mml_sgd_iterate(model.DangerousGetHandle(), subepoch_sequence.ToArray(), null, 0));
-			}
-		}
+		protected override int Threads { get { return MaxThreads; } }
 
 		public override void SaveModel(string filename)
 		{

@@ -34,7 +34,8 @@ namespace MyMediaLite.ItemRecommendation
 
 		protected virtual void InitModel()
 		{
-			IntPtr ctx = Mml.Context(), f, m;
+			IntPtr ctx = Mml.Context(NumGpus), f, m;
+			cache = null;
 			int n = Feedback.Count;
 			var users = new int[n]; var items = new int[n];
 			for (int t = 0; t < n; t++) { users[t] = Feedback.Users[t]; items[t] = Feedback.Items[t]; }
@@ -62,12 +63,12 @@ namespace MyMediaLite.ItemRecommendation
 		/// <summary>WRMF.Iterate (WRMF.cs:68-73): user half-sweep, then item half-sweep</summary>
 		public virtual void Iterate()
 		{
-			lock (gate) Mml.Check(Mml.mml_wrmf_iterate(model.DangerousGetHandle()));
+			lock (gate) { Mml.Check(Mml.mml_wrmf_iterate(model.DangerousGetHandle())); cache = null; }
 		}
 
 		/// <summary>RetrainUser / RetrainItem (WRMF.cs:159-170): Gram matrix of the other side + Optimize() for the one row</summary>
-		public void RetrainUser(int user_id) { lock (gate) Mml.Check(Mml.mml_wrmf_retrain(model.DangerousGetHandle(), 0, new int[] { user_id }, 1)); }
-		public void RetrainItem(int item_id) { lock (gate) Mml.Check(Mml.mml_wrmf_retrain(model.DangerousGetHandle(), 1, new int[] { item_id }, 1)); }
+		public void RetrainUser(int user_id) { lock (gate) { Mml.Check(Mml.mml_wrmf_retrain(model.DangerousGetHandle(), 0, new int[] { user_id }, 1)); cache = null; } }
+		public void RetrainItem(int item_id) { lock (gate) { Mml.Check(Mml.mml_wrmf_retrain(model.DangerousGetHandle(), 1, new int[] { item_id }, 1)); cache = null; } }
 
 		/// <summary>Eval.Items.Evaluate (Eval/Items.cs:126-209) in one device call: candidate selection (with its shuffle), the skip
 		/// rules' bookkeeping and the averaging stay here, ranking and measures run on the device without materialising the lists</summary>
@@ -106,9 +107,32 @@ namespace MyMediaLite.ItemRecommendation
 			return r.Count > 0 ? r[0].Item2 : float.MinValue;
 		}
 
-		/// <summary>Recommender.Recommend (Recommender.cs:52-103) for one user</summary>
+		/// <summary>all-users lists of the current model for one (n, candidates) pair, ignore rows = the training feedback</summary>
+		sealed class ListCache { public int n; public int[] cand; public IList<Tuple<int, float>>[] lists; }
+		ListCache cache;
+
+		/// <summary>Recommender.Recommend (Recommender.cs:52-103) for one user. Eval.Items.Evaluate (Eval/Items.cs:147-164) and
+		/// WritePredictions (ItemRecommendation/Extensions.cs:65-128) call this once per user with ignore_items = the user's training
+		/// items, from TPL threads: the first such call after the model changed computes the lists of ALL users in one device call
+		/// and keeps them; later calls with the same n and candidates whose ignore list is the user's training row are lookups.</summary>
 		public override IList<Tuple<int, float>> Recommend(int user_id, int n = -1, ICollection<int> ignore_items = null, ICollection<int> candidate_items = null)
 		{
+			if (n > 0 && user_id >= 0 && user_id <= MaxUserID && ignore_items != null && Feedback != null
+			    && ignore_items.Count == Feedback.UserMatrix[user_id].Count && Feedback.UserMatrix[user_id].IsSupersetOf(ignore_items))
+			{
+				lock (gate)
+				{
+					int[] cand = candidate_items == null ? Enumerable.Range(0, Math.Max(MaxItemID - 1, 0)).ToArray() : candidate_items.ToArray();
+					if (cache == null || cache.n != n || !cache.cand.SequenceEqual(cand))
+					{
+						var all_users = Enumerable.Range(0, MaxUserID + 1).ToArray();
+						var rows = new ICollection<int>[all_users.Length];
+						for (int u = 0; u < rows.Length; u++) rows[u] = Feedback.UserMatrix[u];
+						cache = new ListCache { n = n, cand = cand, lists = RecommendMany(all_users, n, rows, cand) };
+					}
+					return cache.lists[user_id];
+				}
+			}
 			return RecommendMany(new int[] { user_id }, n, ignore_items == null ? null : new ICollection<int>[] { ignore_items }, candidate_items)[0];
 		}
 

@@ -148,16 +148,35 @@ namespace MyMediaLite.Native
 			[Out] int[] out_items, [Out] float[] out_scores, [Out] int[] out_counts);
 
 		static readonly object ctx_lock = new object();
-		static IntPtr shared_ctx = IntPtr.Zero;
-		/// <summary>One library context per process and device 0 (NumGpus = 1). Throws without a CUDA device: there is no CPU path.</summary>
-		public static IntPtr Context()
+		static readonly Dictionary<uint, IntPtr> shared_ctx = new Dictionary<uint, IntPtr>();
+		/// <summary>One library context per process and GPU count: GPUs 0 .. n_gpus - 1, all driven from this process
+		/// (mml_ctx_create with n_gpus > 1 = the NumGpus property). Throws without a CUDA device: there is no CPU path.</summary>
+		public static IntPtr Context(uint n_gpus = 1)
 		{
 			lock (ctx_lock)
 			{
-				if (shared_ctx == IntPtr.Zero)
-					Check(mml_ctx_create(1, null, out shared_ctx));
-				return shared_ctx;
+				if (n_gpus < 1) n_gpus = 1;
+				IntPtr ctx;
+				if (!shared_ctx.TryGetValue(n_gpus, out ctx))
+				{
+					Check(mml_ctx_create((int) n_gpus, null, out ctx));
+					shared_ctx[n_gpus] = ctx;
+				}
+				return ctx;
 			}
+		}
+
+		/// <summary>The one engine knob (process-wide; the option set of the classes stays the reference's + NumGpus).
+		/// Auto (default): Iterate() runs the parallel epoch kernel whatever MaxThreads says (MaxThreads keeps its other meaning,
+		/// UpdateLearnRate twice per epoch when > 1), except on data sets below SerialBelow ratings, where the exact
+		/// single-threaded order costs nothing. Reference: MaxThreads = 1 walks RandomIndex in the reference's order on one warp
+		/// (parity runs). Parallel: always the parallel kernel. Environment: MMLB200_ORDER = auto | reference | parallel.</summary>
+		public enum EngineOrder { Auto, Reference, Parallel }
+		public const int SerialBelow = 20000;
+		public static EngineOrder Order = ParseOrder(Environment.GetEnvironmentVariable("MMLB200_ORDER"));
+		static EngineOrder ParseOrder(string v)
+		{
+			return v == "reference" ? EngineOrder.Reference : (v == "parallel" ? EngineOrder.Parallel : EngineOrder.Auto);
 		}
 	}
 }

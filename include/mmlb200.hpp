@@ -27,7 +27,9 @@
 #include <ctime>
 #include <fstream>
 #include <limits>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -140,16 +142,53 @@ public:
     }
 };
 
-// ---- library context: one per process and device (mml_ctx); throws without a CUDA device (there is no CPU path) ---------
+// ---- library context: one per process and GPU count (mml_ctx); throws without a CUDA device (there is no CPU path) -----
 class Context {
     mml_ctx* h_ = nullptr;
 public:
-    explicit Context(int device = 0) { int32_t d = device; Check(mml_ctx_create(1, &d, &h_)); }
+    // GPUs 0 .. n_gpus - 1 driven from this process (mml_ctx_create with n_gpus > 1 = the NumGpus property of the classes)
+    explicit Context(int n_gpus = 1) { Check(mml_ctx_create((int32_t)std::max(n_gpus, 1), nullptr, &h_)); }
     ~Context() { if (h_) mml_ctx_destroy(h_); }
     Context(const Context&) = delete;
     Context& operator=(const Context&) = delete;
     mml_ctx* get() const { return h_; }
-    static Context& Default() { static Context c(0); return c; }
+    static Context& Default() { return ForGpus(1); }
+    static Context& ForGpus(uint32_t n_gpus)
+    {
+        static std::map<uint32_t, std::unique_ptr<Context>> all;
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lock(mu);
+        auto& c = all[std::max<uint32_t>(n_gpus, 1)];
+        if (!c) c.reset(new Context((int)std::max<uint32_t>(n_gpus, 1)));
+        return *c;
+    }
+};
+
+// ---- the one engine knob (process-wide; not a recommender option: the option set stays the reference's + NumGpus) -------
+//   Order::Auto (default)  Iterate() runs the parallel epoch kernel (the DSGD block schedule) whatever MaxThreads says --
+//                          MaxThreads keeps its other meaning, UpdateLearnRate twice per epoch when > 1 -- except on data
+//                          sets below SerialBelow ratings, where the exact single-threaded order costs nothing;
+//   Order::Reference       MaxThreads = 1 walks RandomIndex in the reference's order on one warp (parity runs);
+//   Order::Parallel        always the parallel kernel.
+//   DeviceInit             InitModel draws on the device (counter-based) instead of MyMediaLite.Random on the host.
+// Environment: MMLB200_ORDER = auto | reference | parallel, MMLB200_INIT = host | device.
+struct Engine {
+    enum class Order { Auto, Reference, Parallel };
+    static constexpr int64_t SerialBelow = 20000;
+    static Order& order()
+    {
+        static Order o = [] {
+            const char* e = std::getenv("MMLB200_ORDER");
+            const std::string v = e ? e : "auto";
+            return v == "reference" ? Order::Reference : (v == "parallel" ? Order::Parallel : Order::Auto);
+        }();
+        return o;
+    }
+    static bool& device_init()
+    {
+        static bool d = [] { const char* e = std::getenv("MMLB200_INIT"); return e && std::string(e) == "device"; }();
+        return d;
+    }
 };
 
 // ---- data sets -------------------------------------------------------------------------------------------------------------
@@ -340,12 +379,17 @@ public:
         if (!ratings) throw std::invalid_argument("Ratings is not set");
         Release();
         MaxUserID = ratings->MaxUserID; MaxItemID = ratings->MaxItemID;
-        mml_ctx* ctx = Context::Default().get();
+        mml_ctx* ctx = Context::ForGpus(NumGpus).get();
         Check(mml_ratings_create(ctx, ratings->Users.data(), ratings->Items.data(), ratings->Values.data(), ratings->Count(),
                                  MaxUserID, MaxItemID, &dev_ratings_));
         if (ratings->Count() > 0) { float avg; Check(mml_ratings_stats(dev_ratings_, &avg, &MinRating, &MaxRating)); }
         mml_mf_params p = Params();
+        parallel_ = p.schedule == MML_SCHEDULE_DSGD;
         Check(mml_sgd_create(ctx, dev_ratings_, &p, nullptr, nullptr, &model_));
+        if (Engine::device_init()) {
+            Check(mml_sgd_init_model(model_, (uint64_t)Random::GetInstance().Next(), InitMean, InitStdDev));
+            return;
+        }
         Random& rng = Random::GetInstance();           // user matrix first, then the item matrix
         const std::vector<float> U = rng.InitNormal((int64_t)(MaxUserID + 1) * NumFactors, InitMean, InitStdDev);
         const std::vector<float> V = rng.InitNormal((int64_t)(MaxItemID + 1) * NumFactors, InitMean, InitStdDev);
@@ -358,8 +402,25 @@ public:
     }
     virtual void Iterate()
     {
+        if (parallel_) {
+            int32_t G = 0, W = 0; int64_t rounds = 0, staged = 0;
+            Check(mml_sgd_strata_info(Model(), &G, &W, &rounds, &staged));
+            std::vector<int32_t> subepoch_sequence((size_t)G);
+            for (int32_t g = 0; g < G; g++) subepoch_sequence[(size_t)g] = g;
+            Random::GetInstance().Shuffle(subepoch_sequence);                       // BiasedMatrixFactorization.cs:210-211
+            Check(mml_sgd_iterate(Model(), subepoch_sequence.data(), nullptr, 0));
+            return;
+        }
         const std::vector<int32_t>& index = ratings->RandomIndex();
         Check(mml_sgd_iterate(Model(), nullptr, index.data(), (int64_t)index.size()));
+    }
+    // whether Iterate() runs the parallel epoch kernel (see Engine above); several GPUs always do
+    virtual int32_t Threads() const { return 1; }
+    bool Parallel() const
+    {
+        if (NumGpus > 1 || Engine::order() == Engine::Order::Parallel) return true;
+        if (Engine::order() == Engine::Order::Reference) return Threads() > 1;
+        return Threads() > 1 || (ratings && ratings->Count() >= Engine::SerialBelow);
     }
     float Predict(int32_t user_id, int32_t item_id) const
     {
@@ -466,6 +527,7 @@ public:
 protected:
     mml_ratings* dev_ratings_ = nullptr;
     mml_sgd* model_ = nullptr;
+    bool parallel_ = false;
 
     virtual bool Biased() const { return false; }
     mml_sgd* Model() const
@@ -483,7 +545,7 @@ protected:
         mml_mf_params p;
         mml_mf_params_default(&p);
         p.biased = 0; p.num_factors = (int32_t)NumFactors; p.learn_rate = LearnRate; p.decay = Decay; p.regularization = Regularization;
-        p.schedule = MML_SCHEDULE_SERIAL;
+        p.schedule = Parallel() ? MML_SCHEDULE_DSGD : MML_SCHEDULE_SERIAL;
         return p;
     }
     void Retrain(int32_t id, bool by_item)
@@ -514,6 +576,7 @@ protected:
         Check(mml_ratings_create(ctx, uu.data(), ii.data(), vv.data(), n, MaxUserID, MaxItemID, &dev_ratings_));
         mml_mf_params p = Params();
         p.schedule = MML_SCHEDULE_SERIAL;
+        parallel_ = false;
         Check(mml_sgd_create(ctx, dev_ratings_, &p, nullptr, nullptr, &model_));
         Check(mml_sgd_set_model(model_, U.data(), V.data(), bu ? bu->data() : nullptr, bi ? bi->data() : nullptr));
         Check(mml_sgd_set_scale(model_, min_rating, max_rating, bias));
@@ -535,16 +598,7 @@ public:
     std::string TypeName() const override { return "MyMediaLite.RatingPrediction.CudaBiasedMatrixFactorization"; }
     std::string ClassName() const override { return "BiasedMatrixFactorization"; }
 
-    void Iterate() override
-    {
-        if (MaxThreads <= 1) { MatrixFactorization::Iterate(); return; }
-        int32_t G = 0, W = 0; int64_t rounds = 0, staged = 0;
-        Check(mml_sgd_strata_info(Model(), &G, &W, &rounds, &staged));
-        std::vector<int32_t> subepoch_sequence((size_t)G);
-        for (int32_t g = 0; g < G; g++) subepoch_sequence[(size_t)g] = g;
-        Random::GetInstance().Shuffle(subepoch_sequence);                           // :210-211
-        Check(mml_sgd_iterate(Model(), subepoch_sequence.data(), nullptr, 0));
-    }
+    int32_t Threads() const override { return MaxThreads; }
     void SaveModel(const std::string& filename) const override
     {
         const int64_t nu = MaxUserID + 1, ni = MaxItemID + 1;
@@ -600,9 +654,9 @@ protected:
         p.frequency_regularization = FrequencyRegularization ? 1 : 0;
         p.loss = Loss == OptimizationTarget::MAE ? MML_LOSS_MAE : (Loss == OptimizationTarget::LogisticLoss ? MML_LOSS_LOGISTIC : MML_LOSS_RMSE);
         p.bold_driver = BoldDriver ? 1 : 0; p.max_threads = MaxThreads;
-        // MaxThreads > 1 selects the reference's DSGD block schedule (:178-184); on the GPU the worker groups are CTAs
-        p.schedule = MaxThreads > 1 ? MML_SCHEDULE_DSGD : MML_SCHEDULE_SERIAL;
-        if (MaxThreads > 1 && NaiveParallelization) { p.num_groups = 1; p.ctas_per_group = 1 << 16; }   // :136-141, :201-204
+        // MaxThreads > 1 selects the reference's DSGD block schedule (:178-184); on the GPU the worker groups are CTAs, and the
+        // parallel kernel is also what MaxThreads = 1 runs unless the engine order says Reference (Engine above)
+        if (p.schedule == MML_SCHEDULE_DSGD && NaiveParallelization) { p.num_groups = 1; p.ctas_per_group = 1 << 16; }   // :136-141, :201-204
         return p;
     }
 };
@@ -639,9 +693,9 @@ public:
         InitModel();
         for (uint32_t it = 0; it < NumIter; it++) Iterate();
     }
-    void Iterate() { Check(mml_wrmf_iterate(Model())); }          // WRMF.cs:68-73
-    void RetrainUser(int32_t user_id) { Check(mml_wrmf_retrain(Model(), 0, &user_id, 1)); }   // WRMF.cs:159-163
-    void RetrainItem(int32_t item_id) { Check(mml_wrmf_retrain(Model(), 1, &item_id, 1)); }   // WRMF.cs:166-170
+    void Iterate() { Check(mml_wrmf_iterate(Model())); cache_.valid = false; }          // WRMF.cs:68-73
+    void RetrainUser(int32_t user_id) { Check(mml_wrmf_retrain(Model(), 0, &user_id, 1)); cache_.valid = false; }   // WRMF.cs:159-163
+    void RetrainItem(int32_t item_id) { Check(mml_wrmf_retrain(Model(), 1, &item_id, 1)); cache_.valid = false; }   // WRMF.cs:166-170
 
     float Predict(int32_t user_id, int32_t item_id) const          // MF.cs:151-157
     {
@@ -653,6 +707,12 @@ public:
     std::vector<std::pair<int32_t, float>> Recommend(int32_t user_id, int n = -1, const std::vector<int32_t>* ignore_items = nullptr,
                                                      const std::vector<int32_t>* candidate_items = nullptr) const
     {
+        // Eval.Items.Evaluate (Eval/Items.cs:147-164) and WritePredictions (ItemRecommendation/Extensions.cs:65-128) call this
+        // once per user with ignore_items = the user's training items, from several threads. The first such call after the
+        // model changed computes the lists of ALL users in one device call and keeps them; later calls with the same n and
+        // candidates whose ignore list is the user's training row are lookups.
+        std::vector<std::pair<int32_t, float>> hit;
+        if (FromCache(user_id, n, ignore_items, candidate_items, &hit)) return hit;
         std::vector<std::vector<int32_t>> ign;
         if (ignore_items) ign.push_back(*ignore_items);
         return RecommendMany({user_id}, n, ignore_items ? &ign : nullptr, candidate_items)[0];
@@ -716,6 +776,58 @@ public:
     }
 
 private:
+    struct ListCache {
+        bool valid = false;
+        int n = 0;
+        std::vector<int32_t> cand;
+        std::vector<int64_t> ptr; std::vector<int32_t> idx;      // training rows (sets, ascending) of all users
+        std::vector<int32_t> items, counts; std::vector<float> scores;
+    };
+    mutable ListCache cache_;
+    mutable std::mutex cache_mu_;
+
+    bool FromCache(int32_t user_id, int n, const std::vector<int32_t>* ignore_items, const std::vector<int32_t>* candidate_items,
+                   std::vector<std::pair<int32_t, float>>* out) const
+    {
+        if (n <= 0 || user_id < 0 || user_id > MaxUserID || !Feedback || Feedback->Users.empty()) return false;
+        std::lock_guard<std::mutex> lock(cache_mu_);
+        std::vector<int32_t> cand;
+        if (candidate_items) cand = *candidate_items;
+        else for (int32_t i = 0; i < MaxItemID - 1; i++) cand.push_back(i);
+        ListCache& c = cache_;
+        if (c.ptr.empty()) {                                     // training rows: the user matrix is a set
+            const size_t nu = (size_t)MaxUserID + 1;
+            std::vector<std::pair<int32_t, int32_t>> ev(Feedback->Users.size());
+            for (size_t t = 0; t < ev.size(); t++) ev[t] = {Feedback->Users[t], Feedback->Items[t]};
+            std::sort(ev.begin(), ev.end());
+            ev.erase(std::unique(ev.begin(), ev.end()), ev.end());
+            c.ptr.assign(nu + 1, 0);
+            for (auto& e : ev) c.ptr[(size_t)e.first + 1]++;
+            for (size_t u = 0; u < nu; u++) c.ptr[u + 1] += c.ptr[u];
+            c.idx.resize(std::max<size_t>(ev.size(), 1));
+            for (size_t t = 0; t < ev.size(); t++) c.idx[t] = ev[t].second;
+        }
+        std::vector<int32_t> given = ignore_items ? *ignore_items : std::vector<int32_t>();
+        std::sort(given.begin(), given.end());
+        given.erase(std::unique(given.begin(), given.end()), given.end());
+        const int64_t lo = c.ptr[(size_t)user_id], hi = c.ptr[(size_t)user_id + 1];
+        if ((int64_t)given.size() != hi - lo || !std::equal(given.begin(), given.end(), c.idx.begin() + lo)) return false;
+        const int64_t n_out = std::min<int64_t>(n, (int64_t)cand.size());
+        if (!c.valid || c.n != n || c.cand != cand) {
+            const size_t nu = (size_t)MaxUserID + 1;
+            std::vector<int32_t> users(nu);
+            for (size_t u = 0; u < nu; u++) users[u] = (int32_t)u;
+            c.items.assign(std::max<size_t>(nu * (size_t)n_out, 1), 0); c.scores.assign(c.items.size(), 0.f); c.counts.assign(nu, 0);
+            Check(mml_wrmf_recommend(Model(), users.data(), (int64_t)nu, n, cand.data(), (int64_t)cand.size(), c.ptr.data(), c.idx.data(),
+                                     c.items.data(), c.scores.data(), c.counts.data()));
+            c.valid = true; c.n = n; c.cand = cand;
+        }
+        out->clear();
+        for (int32_t r = 0; r < c.counts[(size_t)user_id]; r++)
+            out->emplace_back(c.items[(size_t)user_id * (size_t)n_out + r], c.scores[(size_t)user_id * (size_t)n_out + r]);
+        return true;
+    }
+
     mml_feedback* fb_ = nullptr;
     mml_wrmf* model_ = nullptr;
     mml_wrmf* Model() const
@@ -731,7 +843,8 @@ private:
     void NewModel(int32_t n_users, int32_t n_items, const std::vector<int32_t>& users, const std::vector<int32_t>& items)
     {
         Release();
-        mml_ctx* ctx = Context::Default().get();
+        cache_ = ListCache();
+        mml_ctx* ctx = Context::ForGpus(NumGpus).get();
         Check(mml_feedback_create(ctx, users.data(), items.data(), (int64_t)users.size(), n_users - 1, n_items - 1, &fb_));
         mml_wrmf_params p;
         p.num_factors = (int32_t)NumFactors; p.alpha = Alpha; p.regularization = Regularization;

@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 #include <mutex>
+#include <functional>
+#include <algorithm>
 
 #include "../../include/mmlb200.h"
 
@@ -51,7 +53,29 @@ struct DevBuf {
         n = count;
         return MML_OK;
     }
+    // grow-only: keeps the buffer when it already holds `count` elements (no cudaFree / cudaMalloc on the hot path)
+    int32_t ensure(size_t count) { return (p && n >= std::max<size_t>(count, 1)) ? MML_OK : alloc(count); }
     size_t bytes() const { return n * sizeof(T); }
+};
+
+// ---- a page-locked host buffer (staging for asynchronous copies), grow-only ---------------------
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    PinBuf() = default;
+    PinBuf(const PinBuf&) = delete;
+    PinBuf& operator=(const PinBuf&) = delete;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    int32_t ensure(size_t count) {
+        if (count == 0) count = 1;
+        if (p && n >= count) return MML_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0;
+        MML_CUDA(cudaHostAlloc((void**)&p, count * sizeof(T), cudaHostAllocDefault));
+        n = count;
+        return MML_OK;
+    }
 };
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -83,6 +107,14 @@ struct Ctx {
     void* comm = nullptr;        // ncclComm_t when n_gpus > 1
     void* flush_buf = nullptr;   // mml_ctx_flush_l2
     int flush_val = 0;
+    void* topn_cache = nullptr;  // Recommend() workspace of this context, grow-only (topn_tc.cu); freed by topn_cache_destroy
+    cudaStream_t out_stream = nullptr;    // device -> host result staging that may overlap the next batch's kernels
+    // One-process multi-GPU (mml_ctx_create with n_gpus > 1, the NumGpus property of the host classes): this context is
+    // then only the root of `peers`, one ordinary rank context per GPU (rank r of n_gpus, NCCL communicators from
+    // ncclCommInitAll); every entry point on the root or on a handle created from it fans out to the peers, one host
+    // thread per GPU (on_ranks), exactly the calls a one-process-per-GPU host would make.
+    std::vector<mml_ctx*> peers;
+    bool is_root() const { return !peers.empty(); }
     // Every ABI call on this context or on a handle created from it holds this lock for its duration: the handles share the
     // context's streams and their own grow-only scratch buffers, and the reference calls Predict / Recommend concurrently from
     // TPL threads on one object (Eval/Items.cs:147-164). Recursive: some entry points are built on others.
@@ -101,12 +133,14 @@ struct Ratings {
     DevBuf<float> values;
     DevBuf<uint32_t> count_by_user, count_by_item;
     float average = 0.f, min_rating = 0.f, max_rating = 0.f;
+    std::vector<mml_ratings*> shards;   // root of a one-process multi-GPU rating set: shard r holds the users with u % N == r
     int32_t n_users() const { return max_user + 1; }
     int32_t n_items() const { return max_item + 1; }
 };
 
 Ratings* ratings_of(mml_ratings* h);
 int32_t dist_destroy(Ctx* c);
+void topn_cache_destroy(Ctx* c);
 int32_t dist_allreduce_u32(Ctx* c, uint32_t* d_buf, size_t n);
 int32_t dist_allreduce_f64(Ctx* c, double* d_buf, size_t n);
 int32_t dist_allreduce_f64_max(Ctx* c, double* d_buf, size_t n);
@@ -116,5 +150,20 @@ int32_t dist_broadcast_f32(Ctx* c, float* d_buf, size_t n, int root);
 int32_t dist_group_start();
 int32_t dist_group_end();
 Ctx* ctx_of(mml_ctx* h);
+
+// Runs fn(r) for r = 0..n-1, one host thread per rank (each thread drives one GPU: collectives inside fn meet their
+// peers), joins, and returns the first non-zero status with that thread's error message made the caller's.
+int32_t on_ranks(int n, const std::function<int32_t(int)>& fn);
+// ncclCommInitAll for the peers of a root context (dist.cu)
+int32_t dist_init_all(std::vector<Ctx*>& peers);
+
+// Fan-out of an entry point on a root handle: `call` is evaluated once per shard with `s` bound to shard r's handle.
+#define MML_FORWARD_ALL(handle, call)                                                          \
+    do {                                                                                       \
+        if ((handle) && !(handle)->shards.empty()) {                                           \
+            auto& _sh = (handle)->shards;                                                      \
+            return mml::on_ranks((int)_sh.size(), [&](int _r) -> int32_t { auto* s = _sh[_r]; (void)s; return (call); }); \
+        }                                                                                      \
+    } while (0)
 
 }  // namespace mml

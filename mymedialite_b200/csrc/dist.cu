@@ -56,6 +56,18 @@ extern "C" int32_t mml_ctx_create_dist(int32_t rank, int32_t world, int32_t devi
 
 namespace mml {
 
+// One process, several GPUs: all communicators at once (ncclCommInitAll), rank r = position in `peers`.
+int32_t dist_init_all(std::vector<Ctx*>& peers)
+{
+    const int n = (int)peers.size();
+    std::vector<int> devs((size_t)n);
+    for (int r = 0; r < n; r++) devs[(size_t)r] = peers[(size_t)r]->device;
+    std::vector<ncclComm_t> comms((size_t)n);
+    MML_NCCL(ncclCommInitAll(comms.data(), n, devs.data()));
+    for (int r = 0; r < n; r++) { peers[(size_t)r]->comm = (void*)comms[(size_t)r]; peers[(size_t)r]->rank = r; peers[(size_t)r]->n_gpus = n; }
+    return MML_OK;
+}
+
 int32_t dist_destroy(Ctx* c)
 {
     if (c->comm) { ncclCommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }

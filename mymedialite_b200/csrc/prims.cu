@@ -5,6 +5,7 @@
 // (Data/DataSet.cs:134-191 count / index build, MultiCore.cs:58-66 block bucketing).
 #include "common.cuh"
 #include <cstdarg>
+#include <thread>
 
 namespace mml {
 
@@ -19,6 +20,24 @@ void set_error(const char* fmt, ...)
     va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+int32_t on_ranks(int n, const std::function<int32_t(int)>& fn)
+{
+    if (n == 1) return fn(0);
+    std::vector<int32_t> st((size_t)n, MML_OK);
+    std::vector<std::string> msg((size_t)n);
+    std::vector<std::thread> th;
+    th.reserve((size_t)n);
+    for (int r = 0; r < n; r++)
+        th.emplace_back([&, r] {
+            st[(size_t)r] = fn(r);
+            if (st[(size_t)r] != MML_OK) msg[(size_t)r] = last_error();
+        });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < n; r++)
+        if (st[(size_t)r] != MML_OK) { set_error("[gpu %d of %d] %s", r, n, msg[(size_t)r].c_str()); return st[(size_t)r]; }
+    return MML_OK;
+}
 
 int bits_for(uint32_t max_value)
 {

@@ -137,6 +137,7 @@ int32_t ctx_create_on_device(int dev, mml_ctx** out)
     c->c.sm_count = prop.multiProcessorCount;
     MML_CUDA(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking));
     MML_CUDA(cudaStreamCreateWithFlags(&c->c.copy_stream, cudaStreamNonBlocking));
+    MML_CUDA(cudaStreamCreateWithFlags(&c->c.out_stream, cudaStreamNonBlocking));
     MML_CUDA(cudaEventCreateWithFlags(&c->c.copy_done, cudaEventDisableTiming));
     *out = c;
     return MML_OK;
@@ -146,16 +147,45 @@ int32_t ctx_create_on_device(int dev, mml_ctx** out)
 extern "C" int32_t mml_ctx_create(int32_t n_gpus, const int32_t* device_ids, mml_ctx** out)
 {
     MML_CHECK(out != nullptr, MML_ERR_ARG, "mml_ctx_create: out is NULL");
-    MML_CHECK(n_gpus == 1, MML_ERR_UNSUPPORTED,
-              "mml_ctx_create: one context drives one GPU (one process per GPU; use mml_ctx_create_dist); got n_gpus=%d", n_gpus);
-    return ctx_create_on_device(device_ids ? device_ids[0] : 0, out);
+    MML_CHECK(n_gpus >= 1 && n_gpus <= 64, MML_ERR_ARG, "mml_ctx_create: n_gpus=%d", n_gpus);
+    if (n_gpus == 1) return ctx_create_on_device(device_ids ? device_ids[0] : 0, out);
+    // One process, n_gpus GPUs (the NumGpus property of the host classes): a root context over one rank context per GPU.
+    int count = 0;
+    MML_CUDA(cudaGetDeviceCount(&count));
+    MML_CHECK(count >= n_gpus, MML_ERR_CUDA, "mml_ctx_create: %d GPUs asked for, %d visible (no CPU fallback)", n_gpus, count);
+    mml_ctx* root = new (std::nothrow) mml_ctx();
+    MML_CHECK(root != nullptr, MML_ERR_ARG, "out of host memory");
+    root->c.device = device_ids ? device_ids[0] : 0;
+    root->c.n_gpus = n_gpus;
+    int32_t st = MML_OK;
+    for (int r = 0; r < n_gpus && st == MML_OK; r++) {
+        mml_ctx* p = nullptr;
+        st = ctx_create_on_device(device_ids ? device_ids[r] : r, &p);
+        if (st == MML_OK) root->c.peers.push_back(p);
+    }
+    if (st == MML_OK) {
+        std::vector<Ctx*> pc;
+        for (mml_ctx* p : root->c.peers) pc.push_back(&p->c);
+        st = dist_init_all(pc);
+        root->c.sm_count = pc[0]->sm_count;
+    }
+    if (st != MML_OK) { mml_ctx_destroy(root); return st; }
+    *out = root;
+    return MML_OK;
 }
 
 extern "C" int32_t mml_ctx_destroy(mml_ctx* ctx)
 {
     if (!ctx) return MML_OK;
+    if (ctx->c.is_root()) {
+        for (mml_ctx* p : ctx->c.peers) mml_ctx_destroy(p);
+        delete ctx;
+        return MML_OK;
+    }
     cudaSetDevice(ctx->c.device);
     dist_destroy(&ctx->c);
+    topn_cache_destroy(&ctx->c);
+    if (ctx->c.out_stream) cudaStreamDestroy(ctx->c.out_stream);
     if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
     if (ctx->c.copy_stream) cudaStreamDestroy(ctx->c.copy_stream);
     if (ctx->c.copy_done) cudaEventDestroy(ctx->c.copy_done);
@@ -168,6 +198,11 @@ extern "C" int32_t mml_ctx_synchronize(mml_ctx* ctx)
 {
     MML_LOCK(mml::ctx_of(ctx));
     MML_CHECK(ctx != nullptr, MML_ERR_ARG, "ctx is NULL");
+    if (ctx->c.is_root()) {
+        for (mml_ctx* p : ctx->c.peers) MML_TRY(mml_ctx_synchronize(p));
+        return MML_OK;
+    }
+    MML_CUDA(cudaSetDevice(ctx->c.device));
     MML_CUDA(cudaStreamSynchronize(ctx->c.stream));
     return MML_OK;
 }
@@ -177,6 +212,10 @@ extern "C" int32_t mml_ctx_flush_l2(mml_ctx* ctx)
 {
     MML_LOCK(mml::ctx_of(ctx));
     MML_CHECK(ctx != nullptr, MML_ERR_ARG, "ctx is NULL");
+    if (ctx->c.is_root()) {
+        for (mml_ctx* p : ctx->c.peers) MML_TRY(mml_ctx_flush_l2(p));
+        return MML_OK;
+    }
     MML_CUDA(cudaSetDevice(ctx->c.device));
     const size_t bytes = (size_t)384 << 20;
     if (ctx->c.flush_buf == nullptr) MML_CUDA(cudaMalloc(&ctx->c.flush_buf, bytes));
@@ -203,6 +242,40 @@ extern "C" int32_t mml_ratings_create(mml_ctx* ctx, const int32_t* users, const 
     MML_CHECK(n >= 0 && n < ((int64_t)1 << 31), MML_ERR_ARG, "mml_ratings_create: n=%lld out of range", (long long)n);
     MML_CHECK(n == 0 || (users && items && values), MML_ERR_ARG, "mml_ratings_create: NULL data");
     MML_CHECK(max_user >= -1 && max_item >= -1, MML_ERR_ARG, "mml_ratings_create: bad max ids");
+    if (ctx->c.is_root()) {
+        // one shard per GPU: the users with u % N == r (the reference's block rule, MultiCore.cs:64, lifted to GPUs), with
+        // the whole id space; Average and the scale are those of the whole set
+        const int N = (int)ctx->c.peers.size();
+        mml_ratings* root = new (std::nothrow) mml_ratings();
+        MML_CHECK(root != nullptr, MML_ERR_ARG, "out of host memory");
+        root->r.ctx = &ctx->c; root->r.n = n; root->r.max_user = max_user; root->r.max_item = max_item;
+        root->r.shards.assign((size_t)N, nullptr);
+        std::vector<double> sums((size_t)N, 0.0);
+        const int32_t st = on_ranks(N, [&](int r) -> int32_t {
+            std::vector<int32_t> su, si; std::vector<float> sv;
+            su.reserve((size_t)(n / N + 1024)); si.reserve((size_t)(n / N + 1024)); sv.reserve((size_t)(n / N + 1024));
+            for (int64_t t = 0; t < n; t++)
+                if (users[t] >= 0 && users[t] % N == r) { su.push_back(users[t]); si.push_back(items[t]); sv.push_back(values[t]); }
+                else if (users[t] < 0 && r == 0) { set_error("mml_ratings_create: rating %lld has a negative user id", (long long)t); return MML_ERR_ARG; }
+            double sum = 0;
+            for (float x : sv) sum += (double)x;
+            sums[(size_t)r] = sum;
+            return mml_ratings_create(ctx->c.peers[(size_t)r], su.data(), si.data(), sv.data(), (int64_t)su.size(), max_user, max_item,
+                                      &root->r.shards[(size_t)r]);
+        });
+        if (st != MML_OK) { mml_ratings_destroy(root); return st; }
+        double sum = 0; float mn = FLT_MAX, mx = -FLT_MAX;
+        for (int r = 0; r < N; r++) {
+            sum += sums[(size_t)r];
+            if (root->r.shards[(size_t)r]->r.n > 0) {
+                mn = std::min(mn, root->r.shards[(size_t)r]->r.min_rating); mx = std::max(mx, root->r.shards[(size_t)r]->r.max_rating);
+            }
+        }
+        root->r.average = n > 0 ? (float)sum / (float)n : 0.f;
+        root->r.min_rating = mn; root->r.max_rating = mx;
+        *out = root;
+        return MML_OK;
+    }
     MML_CUDA(cudaSetDevice(ctx->c.device));
     mml_ratings* h = new (std::nothrow) mml_ratings();
     MML_CHECK(h != nullptr, MML_ERR_ARG, "out of host memory");
@@ -245,6 +318,11 @@ extern "C" int32_t mml_ratings_destroy(mml_ratings* r)
 {
     MML_LOCK((r ? mml::ratings_of(r)->ctx : nullptr));
     if (!r) return MML_OK;
+    if (!r->r.shards.empty() || r->r.ctx->is_root()) {
+        for (mml_ratings* s : r->r.shards) mml_ratings_destroy(s);
+        delete r;
+        return MML_OK;
+    }
     cudaSetDevice(r->r.ctx->device);
     delete r;
     return MML_OK;
@@ -255,6 +333,16 @@ extern "C" int32_t mml_ratings_counts(mml_ratings* h, int32_t by_item, int32_t* 
     MML_LOCK((h ? mml::ratings_of(h)->ctx : nullptr));
     MML_CHECK(h && counts_out, MML_ERR_ARG, "mml_ratings_counts: NULL argument");
     Ratings& r = h->r;
+    if (!r.shards.empty()) {   // every shard counts over the whole id space: add them up
+        const int32_t rows = by_item ? r.n_items() : r.n_users();
+        std::vector<int32_t> part((size_t)rows);
+        for (int32_t t = 0; t < rows; t++) counts_out[t] = 0;
+        for (mml_ratings* s : r.shards) {
+            MML_TRY(mml_ratings_counts(s, by_item, part.data()));
+            for (int32_t t = 0; t < rows; t++) counts_out[t] += part[(size_t)t];
+        }
+        return MML_OK;
+    }
     MML_CUDA(cudaSetDevice(r.ctx->device));
     DevBuf<uint32_t>& c = by_item ? r.count_by_item : r.count_by_user;
     const int32_t rows = by_item ? r.n_items() : r.n_users();
@@ -268,6 +356,7 @@ extern "C" int32_t mml_ratings_csr(mml_ratings* h, int32_t by_item, int64_t* row
     MML_LOCK((h ? mml::ratings_of(h)->ctx : nullptr));
     MML_CHECK(h && row_ptr && idx, MML_ERR_ARG, "mml_ratings_csr: NULL argument");
     Ratings& r = h->r;
+    MML_CHECK(r.shards.empty(), MML_ERR_UNSUPPORTED, "mml_ratings_csr: not available on a multi-GPU context (the shards index their own ratings)");
     MML_CUDA(cudaSetDevice(r.ctx->device));
     const int32_t rows = by_item ? r.n_items() : r.n_users();
     DevBuf<uint32_t> key;
@@ -293,6 +382,7 @@ extern "C" int32_t mml_partition_blocks(mml_ratings* h, const int32_t* user_perm
     MML_LOCK((h ? mml::ratings_of(h)->ctx : nullptr));
     MML_CHECK(h && user_perm && item_perm && block_ptr && idx, MML_ERR_ARG, "mml_partition_blocks: NULL argument");
     Ratings& r = h->r;
+    MML_CHECK(r.shards.empty(), MML_ERR_UNSUPPORTED, "mml_partition_blocks: not available on a multi-GPU context");
     MML_CHECK(g >= 1 && (int64_t)g * g < ((int64_t)1 << 31), MML_ERR_ARG, "mml_partition_blocks: bad g=%d", g);
     MML_CUDA(cudaSetDevice(r.ctx->device));
     cudaStream_t s = r.ctx->stream;

@@ -1820,7 +1820,18 @@ using namespace mml;
 // =================================================================================================
 // C ABI
 // =================================================================================================
-struct mml_sgd { Sgd m; };
+// A model on a one-process multi-GPU context is a root over one ordinary model per GPU (shards[r] on rank r's context,
+// created from shard r of the ratings): every entry point below fans out to the shards, one host thread per GPU, which is
+// exactly what the ranks of a one-process-per-GPU host would call.
+struct mml_sgd { Sgd m; std::vector<mml_sgd*> shards; };
+
+// pairs (users[t], items[t]) dealt to the rank that owns the user (u % N; ids outside the model go to rank 0)
+static void deal_pairs(int N, const int32_t* users, int64_t n, std::vector<std::vector<int64_t>>& pos)
+{
+    pos.assign((size_t)N, std::vector<int64_t>());
+    for (auto& p : pos) p.reserve((size_t)(n / N + 16));
+    for (int64_t t = 0; t < n; t++) pos[(size_t)(users[t] >= 0 ? users[t] % N : 0)].push_back(t);
+}
 
 extern "C" void mml_mf_params_default(mml_mf_params* p)
 {
@@ -1858,6 +1869,23 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
     MML_CHECK(p->num_factors >= 1 && p->num_factors <= 256, MML_ERR_UNSUPPORTED,
               "mml_sgd_create: num_factors=%d not in [1,256]", p->num_factors);
     MML_CHECK(r->n_users() > 0 && r->n_items() > 0, MML_ERR_ARG, "mml_sgd_create: empty id space");
+    if (ctx->is_root()) {
+        MML_CHECK(r->shards.size() == ctx->peers.size(), MML_ERR_ARG, "mml_sgd_create: the ratings were not created on this multi-GPU context");
+        MML_CHECK(p->schedule == MML_SCHEDULE_DSGD, MML_ERR_UNSUPPORTED,
+                  "mml_sgd_create: the serial (MaxThreads = 1 order) schedule runs on one GPU; a multi-GPU context needs MML_SCHEDULE_DSGD");
+        MML_CHECK(user_perm == nullptr, MML_ERR_UNSUPPORTED,
+                  "mml_sgd_create: a multi-GPU context shards users by id (u %% N) when the ratings are created; user_perm must be NULL");
+        mml_sgd* root = new (std::nothrow) mml_sgd();
+        MML_CHECK(root != nullptr, MML_ERR_ARG, "out of host memory");
+        root->m.ctx = ctx; root->m.ratings = r; root->m.p = *p; root->m.k = p->num_factors;
+        root->shards.assign(ctx->peers.size(), nullptr);
+        const int32_t st = on_ranks((int)ctx->peers.size(), [&](int x) -> int32_t {
+            return mml_sgd_create(ctx->peers[(size_t)x], r->shards[(size_t)x], p, nullptr, item_perm, &root->shards[(size_t)x]);
+        });
+        if (st != MML_OK) { mml_sgd_destroy(root); return st; }
+        *out = root;
+        return MML_OK;
+    }
     MML_CUDA(cudaSetDevice(ctx->device));
     mml_sgd* h = new (std::nothrow) mml_sgd();
     MML_CHECK(h != nullptr, MML_ERR_ARG, "out of host memory");
@@ -2025,6 +2053,11 @@ extern "C" int32_t mml_sgd_destroy(mml_sgd* h)
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     if (!h) return MML_OK;
+    if (h->m.ctx->is_root()) {
+        for (mml_sgd* s : h->shards) mml_sgd_destroy(s);
+        delete h;
+        return MML_OK;
+    }
     cudaSetDevice(h->m.ctx->device);
     cudaStreamSynchronize(h->m.ctx->stream);
     if (h->m.ev0) cudaEventDestroy(h->m.ev0);
@@ -2083,6 +2116,7 @@ extern "C" int32_t mml_sgd_set_model(mml_sgd* h, const float* user_factors, cons
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && user_factors && item_factors, MML_ERR_ARG, "mml_sgd_set_model: NULL argument");
+    MML_FORWARD_ALL(h, mml_sgd_set_model(s, user_factors, item_factors, user_bias, item_bias));   // every shard keeps its own user rows
     Sgd& m = h->m;
     MML_CUDA(cudaSetDevice(m.ctx->device));
     MML_TRY(rows_from_host(m, m.users, m.ratings->count_by_user.p, user_factors, m.P.p));
@@ -2097,6 +2131,7 @@ extern "C" int32_t mml_sgd_init_model(mml_sgd* h, uint64_t seed, double init_mea
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "mml_sgd_init_model: NULL argument");
+    MML_FORWARD_ALL(h, mml_sgd_init_model(s, seed, init_mean, init_stddev));   // counter-based: a row's values do not depend on the shard
     Sgd& m = h->m;
     MML_CUDA(cudaSetDevice(m.ctx->device));
     cudaStream_t s = m.ctx->stream;
@@ -2117,6 +2152,25 @@ extern "C" int32_t mml_sgd_get_model(mml_sgd* h, float* user_factors, float* ite
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "mml_sgd_get_model: NULL argument");
+    if (!h->shards.empty()) {
+        // user rows and biases come from the shard that owns the user (u % N), the item side from shard 0 (every shard
+        // holds all item rows after the home blocks were broadcast, which get_model does on every shard: a collective)
+        const int N = (int)h->shards.size();
+        const int64_t nu = h->m.ratings->n_users(), k = h->m.k;
+        return on_ranks(N, [&](int x) -> int32_t {
+            std::vector<float> U, bu;
+            if (user_factors) U.assign((size_t)(nu * k), 0.f);
+            if (user_bias) bu.assign((size_t)nu, 0.f);
+            MML_TRY(mml_sgd_get_model(h->shards[(size_t)x], user_factors ? U.data() : nullptr, x == 0 ? item_factors : nullptr,
+                                      user_bias ? bu.data() : nullptr, x == 0 ? item_bias : nullptr,
+                                      x == 0 ? global_bias : nullptr, x == 0 ? current_learnrate : nullptr));
+            for (int64_t u = x; u < nu; u += N) {
+                if (user_factors) memcpy(user_factors + u * k, U.data() + u * k, sizeof(float) * (size_t)k);
+                if (user_bias) user_bias[u] = bu[(size_t)u];
+            }
+            return MML_OK;
+        });
+    }
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_get_model: no model (call set_model / init_model first)");
     MML_CUDA(cudaSetDevice(m.ctx->device));
@@ -2156,6 +2210,7 @@ extern "C" int32_t mml_sgd_set_learnrate(mml_sgd* h, float lr)
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
+    for (mml_sgd* s : h->shards) s->m.lr = lr;
     h->m.lr = lr;
     return MML_OK;
 }
@@ -2164,6 +2219,7 @@ extern "C" int32_t mml_sgd_set_scale(mml_sgd* h, float min_rating, float max_rat
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
+    for (mml_sgd* s : h->shards) MML_TRY(mml_sgd_set_scale(s, min_rating, max_rating, global_bias));
     h->m.min_rating = min_rating; h->m.max_rating = max_rating; h->m.range = max_rating - min_rating;
     h->m.global_bias = global_bias;
     return MML_OK;
@@ -2173,6 +2229,7 @@ extern "C" int32_t mml_sgd_invalidate_index(mml_sgd* h)
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
+    for (mml_sgd* s : h->shards) s->m.n_index = -1;
     h->m.n_index = -1;
     return MML_OK;
 }
@@ -2181,6 +2238,7 @@ extern "C" int32_t mml_sgd_iterate(mml_sgd* h, const int32_t* subepoch_sequence,
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "mml_sgd_iterate: NULL argument");
+    MML_FORWARD_ALL(h, mml_sgd_iterate(s, subepoch_sequence, random_index, n_index));
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_iterate: no model (call set_model / init_model first)");
     MML_CUDA(cudaSetDevice(m.ctx->device));
@@ -2214,6 +2272,7 @@ extern "C" int32_t mml_sgd_iterate_indices(mml_sgd* h, const int32_t* indices, i
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && (indices || n == 0), MML_ERR_ARG, "mml_sgd_iterate_indices: NULL argument");
+    MML_CHECK(h->shards.empty(), MML_ERR_UNSUPPORTED, "mml_sgd_iterate_indices: rating indices are per GPU on a multi-GPU context");
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_iterate_indices: no model");
     MML_CUDA(cudaSetDevice(m.ctx->device));
@@ -2234,6 +2293,7 @@ extern "C" int32_t mml_sgd_learn_factors(mml_sgd* h, const int32_t* indices, int
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && (indices || n == 0), MML_ERR_ARG, "mml_sgd_learn_factors: NULL argument");
     MML_CHECK(num_iter >= 0, MML_ERR_ARG, "mml_sgd_learn_factors: num_iter = %d", num_iter);
+    MML_CHECK(h->shards.empty(), MML_ERR_UNSUPPORTED, "mml_sgd_learn_factors: rating indices are per GPU on a multi-GPU context");
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_learn_factors: no model");
     MML_CUDA(cudaSetDevice(m.ctx->device));
@@ -2256,6 +2316,18 @@ extern "C" int32_t mml_sgd_predict(mml_sgd* h, const int32_t* users, const int32
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && (n == 0 || (users && items && out)), MML_ERR_ARG, "mml_sgd_predict: NULL argument");
+    if (!h->shards.empty()) {   // every pair is predicted by the GPU that owns the user's row
+        std::vector<std::vector<int64_t>> pos;
+        deal_pairs((int)h->shards.size(), users, n, pos);
+        return on_ranks((int)h->shards.size(), [&](int x) -> int32_t {
+            const std::vector<int64_t>& p = pos[(size_t)x];
+            std::vector<int32_t> su(p.size()), si(p.size()); std::vector<float> so(p.size());
+            for (size_t t = 0; t < p.size(); t++) { su[t] = users[p[t]]; si[t] = items[p[t]]; }
+            MML_TRY(mml_sgd_predict(h->shards[(size_t)x], su.data(), si.data(), (int64_t)p.size(), so.data()));
+            for (size_t t = 0; t < p.size(); t++) out[p[t]] = so[t];
+            return MML_OK;
+        });
+    }
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_predict: no model");
     MML_CUDA(cudaSetDevice(m.ctx->device));
@@ -2289,6 +2361,20 @@ extern "C" int32_t mml_sgd_evaluate(mml_sgd* h, const int32_t* users, const int3
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && out4 && (n == 0 || (users && items && values)), MML_ERR_ARG, "mml_sgd_evaluate: NULL argument");
+    if (!h->shards.empty()) {   // every GPU evaluates the pairs of its own users; the sums are all-reduced inside
+        const int N = (int)h->shards.size();
+        std::vector<std::vector<int64_t>> pos;
+        deal_pairs(N, users, n, pos);
+        std::vector<float> res((size_t)N * 4, 0.f);
+        MML_TRY(on_ranks(N, [&](int x) -> int32_t {
+            const std::vector<int64_t>& p = pos[(size_t)x];
+            std::vector<int32_t> su(p.size() + 1), si(p.size() + 1); std::vector<float> sv(p.size() + 1);
+            for (size_t t = 0; t < p.size(); t++) { su[t] = users[p[t]]; si[t] = items[p[t]]; sv[t] = values[p[t]]; }
+            return mml_sgd_evaluate(h->shards[(size_t)x], su.data(), si.data(), sv.data(), (int64_t)p.size(), res.data() + 4 * x);
+        }));
+        for (int c = 0; c < 4; c++) out4[c] = res[(size_t)c];
+        return MML_OK;
+    }
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_evaluate: no model");
     MML_CHECK(n > 0 || m.R > 1, MML_ERR_ARG, "mml_sgd_evaluate: empty test set");   // Eval/Ratings.cs:98-99 returns null
@@ -2319,6 +2405,13 @@ extern "C" int32_t mml_sgd_evaluate_train(mml_sgd* h, float* out4)
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && out4, MML_ERR_ARG, "mml_sgd_evaluate_train: NULL argument");
+    if (!h->shards.empty()) {
+        const int N = (int)h->shards.size();
+        std::vector<float> res((size_t)N * 4, 0.f);
+        MML_TRY(on_ranks(N, [&](int x) -> int32_t { return mml_sgd_evaluate_train(h->shards[(size_t)x], res.data() + 4 * x); }));
+        for (int c = 0; c < 4; c++) out4[c] = res[(size_t)c];
+        return MML_OK;
+    }
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_evaluate_train: no model");
     MML_CHECK(m.ratings->n > 0 || m.R > 1, MML_ERR_ARG, "mml_sgd_evaluate_train: empty training set");
@@ -2335,6 +2428,13 @@ extern "C" int32_t mml_sgd_objective(mml_sgd* h, double* out)
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && out, MML_ERR_ARG, "mml_sgd_objective: NULL argument");
+    if (!h->shards.empty()) {
+        const int N = (int)h->shards.size();
+        std::vector<double> res((size_t)N, 0.0);
+        MML_TRY(on_ranks(N, [&](int x) -> int32_t { return mml_sgd_objective(h->shards[(size_t)x], &res[(size_t)x]); }));
+        *out = res[0];
+        return MML_OK;
+    }
     MML_CHECK(h->m.has_model, MML_ERR_STATE, "mml_sgd_objective: no model");
     MML_CUDA(cudaSetDevice(h->m.ctx->device));
     return objective(h->m, out);
@@ -2344,6 +2444,17 @@ extern "C" int32_t mml_sgd_stats(mml_sgd* h, int64_t* kernel_launches, float* la
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
+    if (!h->shards.empty()) {   // launches of all GPUs, device time of the slowest
+        int64_t total = 0; float worst = 0.f;
+        for (mml_sgd* s : h->shards) {
+            int64_t l = 0; float ms = 0.f;
+            MML_TRY(mml_sgd_stats(s, &l, &ms));
+            total += l; worst = std::max(worst, ms);
+        }
+        if (kernel_launches) *kernel_launches = total;
+        if (last_iterate_ms) *last_iterate_ms = worst;
+        return MML_OK;
+    }
     Sgd& m = h->m;
     if (kernel_launches) *kernel_launches = m.launches;
     if (last_iterate_ms) {
@@ -2361,6 +2472,7 @@ extern "C" int32_t mml_sgd_strata_info(mml_sgd* h, int32_t* G, int32_t* W, int64
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
+    if (!h->shards.empty()) return mml_sgd_strata_info(h->shards[0], G, W, n_rounds, staged_bytes);
     if (G) *G = h->m.G;
     if (W) *W = h->m.W;
     if (n_rounds) *n_rounds = h->m.n_rounds;
@@ -2372,6 +2484,7 @@ extern "C" int32_t mml_sgd_grid(mml_sgd* h, int32_t* G, int32_t* ctas_per_group)
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
+    if (!h->shards.empty()) return mml_sgd_grid(h->shards[0], G, ctas_per_group);
     if (G) *G = h->m.G;
     if (ctas_per_group) *ctas_per_group = h->m.cpg;
     return MML_OK;
@@ -2381,6 +2494,7 @@ extern "C" int32_t mml_sgd_hot_items(mml_sgd* h, int64_t* n_hot)
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && n_hot, MML_ERR_ARG, "NULL argument");
+    if (!h->shards.empty()) return mml_sgd_hot_items(h->shards[0], n_hot);
     *n_hot = h->m.n_hot;
     return MML_OK;
 }
@@ -2390,6 +2504,7 @@ extern "C" int32_t mml_sgd_schedule_dump(mml_sgd* h, const int32_t* subepoch_seq
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && order, MML_ERR_ARG, "mml_sgd_schedule_dump: NULL argument");
+    MML_CHECK(h->shards.empty(), MML_ERR_UNSUPPORTED, "mml_sgd_schedule_dump: per GPU on a multi-GPU context");
     Sgd& m = h->m;
     MML_CHECK(m.p.schedule == MML_SCHEDULE_DSGD, MML_ERR_STATE, "mml_sgd_schedule_dump: not a DSGD model");
     MML_CUDA(cudaSetDevice(m.ctx->device));
@@ -2584,6 +2699,12 @@ extern "C" int32_t mml_sgd_fold_in(mml_sgd* h, const int64_t* rated_ptr, const i
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && (n_users == 0 || (rated_ptr && init_factors && out_vectors)), MML_ERR_ARG, "mml_sgd_fold_in: NULL argument");
+    if (!h->shards.empty()) {   // needs the item side only: every GPU synchronises its item rows (a collective), GPU 0 answers
+        return on_ranks((int)h->shards.size(), [&](int x) -> int32_t {
+            if (x == 0) return mml_sgd_fold_in(h->shards[0], rated_ptr, rated_items, rated_values, n_users, init_factors, num_iter, out_vectors);
+            return mml_sgd_fold_in(h->shards[(size_t)x], nullptr, nullptr, nullptr, 0, nullptr, num_iter, nullptr);
+        });
+    }
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_fold_in: no model");
     MML_CHECK(num_iter >= 0 && n_users >= 0, MML_ERR_ARG, "mml_sgd_fold_in: negative count");
@@ -2629,6 +2750,12 @@ extern "C" int32_t mml_sgd_score_items(mml_sgd* h, const float* user_vectors, in
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "mml_sgd_score_items: NULL argument");
+    if (!h->shards.empty()) {
+        return on_ranks((int)h->shards.size(), [&](int x) -> int32_t {
+            if (x == 0) return mml_sgd_score_items(h->shards[0], user_vectors, n_users, candidates, n_cand, out_scores);
+            return mml_sgd_score_items(h->shards[(size_t)x], nullptr, 0, nullptr, 0, nullptr);
+        });
+    }
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_score_items: no model");
     MML_CHECK(n_users >= 0 && n_cand >= 0, MML_ERR_ARG, "mml_sgd_score_items: negative count");
@@ -2661,6 +2788,7 @@ extern "C" int32_t mml_sgd_set_rows(mml_sgd* h, int32_t by_item, const int32_t* 
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && (n == 0 || ids), MML_ERR_ARG, "mml_sgd_set_rows: NULL argument");
+    MML_FORWARD_ALL(h, mml_sgd_set_rows(s, by_item, ids, n, factors, biases));   // a shard skips the user rows it does not hold
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_set_rows: no model");
     MML_CUDA(cudaSetDevice(m.ctx->device));

@@ -101,6 +101,7 @@ extern "C" int32_t mml_shuffle_apply(mml_ctx* hctx, int32_t* perm, const int32_t
     MML_CHECK(hctx && (n == 0 || (perm && H)), MML_ERR_ARG, "mml_shuffle_apply: NULL argument");
     MML_CHECK(n >= 0 && n < ((int64_t)1 << 31), MML_ERR_ARG, "mml_shuffle_apply: n out of range");
     Ctx* ctx = ctx_of(hctx);
+    if (ctx->is_root()) return mml_shuffle_apply(ctx->peers[0], perm, H, n);   // one permutation: one GPU
     for (int64_t i = 0; i < n; i++)
         MML_CHECK(H[i] >= 0 && H[i] <= i, MML_ERR_ARG, "mml_shuffle_apply: H[%lld]=%d is not in [0,%lld]", (long long)i, H[i], (long long)i);
     if (n == 0) return MML_OK;

@@ -321,8 +321,8 @@ int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
                     int32_t* out_items, float* out_scores, int32_t* out_counts, std::vector<int64_t>& redo_users, int64_t* launches);
 
 static int g_topn_mode = 0;                         // MML_TOPN_AUTO
-static int64_t g_stat_tc = 0, g_stat_exact = 0;     // users served by each path in the last call
-static float g_stat_ms = 0.f;
+static thread_local int64_t g_stat_tc = 0, g_stat_exact = 0;     // users served by each path in this thread's last call
+static thread_local float g_stat_ms = 0.f;
 
 // Recommend() for a user batch. Tensor-core path (topn_tc.cu) when the request qualifies; users whose candidate
 // superset it cannot prove complete, and requests outside its envelope, run on the exact CUDA-core path.
@@ -628,6 +628,21 @@ extern "C" int32_t mml_topn_mf(mml_ctx* hctx, const float* user_factors, int32_t
     MML_CHECK(k >= 1 && n_model_users >= 0 && n_model_items >= 0 && n_users >= 0 && (n > 0 || n == -1), MML_ERR_ARG,
               "mml_topn_mf: bad sizes (n must be > 0 or -1)");
     Ctx* ctx = ctx_of(hctx);
+    if (ctx->is_root()) {   // users sharded over the GPUs (contiguous ranges of the list), factors uploaded to each
+        const int64_t N = (int64_t)ctx->peers.size();
+        const int64_t nc = candidates ? n_cand : n_model_items;
+        const int64_t n_out = n < 0 ? nc : std::min<int64_t>(n, nc);
+        return on_ranks((int)N, [&](int x) -> int32_t {
+            const int64_t lo = n_users * x / N, hi = n_users * (x + 1) / N;
+            if (hi <= lo) return MML_OK;
+            std::vector<int64_t> ip;
+            const bool ign = ignore_ptr && ignore_idx;
+            if (ign) { ip.resize((size_t)(hi - lo + 1)); for (int64_t t = lo; t <= hi; t++) ip[(size_t)(t - lo)] = ignore_ptr[t] - ignore_ptr[lo]; }
+            return mml_topn_mf(ctx->peers[(size_t)x], user_factors, n_model_users, item_factors, n_model_items, k, users + lo, hi - lo, n,
+                               candidates, n_cand, ign ? ip.data() : nullptr, ign ? ignore_idx + ignore_ptr[lo] : nullptr,
+                               out_items + lo * n_out, out_scores + lo * n_out, out_counts + lo);
+        });
+    }
     MML_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     DevBuf<float> dU, dV;
@@ -653,6 +668,9 @@ extern "C" int32_t mml_items_evaluate_mf(mml_ctx* hctx, const float* user_factor
               "mml_items_evaluate_mf: bad sizes (n must be > 0 or -1)");
     MML_CHECK(test_ptr[n_test_users] == 0 || test_idx, MML_ERR_ARG, "mml_items_evaluate_mf: NULL test_idx");
     Ctx* ctx = ctx_of(hctx);
+    if (ctx->is_root())
+        return mml_items_evaluate_mf(ctx->peers[0], user_factors, n_model_users, item_factors, n_model_items, k, test_users, n_test_users,
+                                     candidates, n_cand, test_ptr, test_idx, ignore_ptr, ignore_idx, n, out_measures, out_used);
     MML_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     DevBuf<float> dU, dV;

@@ -631,8 +631,8 @@ static int32_t tc_prepare_candidates(Ctx* ctx, TcCandidates& c, const float* d_V
     c.stride = (int32_t)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_cand, TC_SAMPLE), std::max(1, 96 / n)));
     c.n_samp = (int32_t)ceil_div(n_cand, c.stride);
     c.samp_pad = ceil_div(c.n_samp, TC_N) * TC_N;
-    MML_TRY(c.Vb.alloc((size_t)c.cand_pad * rf)); MML_TRY(c.Vs.alloc((size_t)c.samp_pad * rf));
-    MML_TRY(c.bad_b.alloc((size_t)c.cand_pad / 32)); MML_TRY(c.bad_s.alloc((size_t)c.samp_pad / 32)); MML_TRY(c.vmax.alloc(1));
+    MML_TRY(c.Vb.ensure((size_t)c.cand_pad * rf)); MML_TRY(c.Vs.ensure((size_t)c.samp_pad * rf));
+    MML_TRY(c.bad_b.ensure((size_t)c.cand_pad / 32)); MML_TRY(c.bad_s.ensure((size_t)c.samp_pad / 32)); MML_TRY(c.vmax.ensure(1));
     MML_CUDA(cudaMemsetAsync(c.bad_b.p, 0, c.bad_b.bytes(), s)); MML_CUDA(cudaMemsetAsync(c.bad_s.p, 0, c.bad_s.bytes(), s));
     MML_CUDA(cudaMemsetAsync(c.vmax.p, 0, sizeof(uint32_t), s));
     if (c.cand_pad > n_cand) MML_CUDA(cudaMemsetAsync(c.Vb.p + (size_t)n_cand * rf, 0, sizeof(float) * (size_t)(c.cand_pad - n_cand) * rf, s));
@@ -640,7 +640,7 @@ static int32_t tc_prepare_candidates(Ctx* ctx, TcCandidates& c, const float* d_V
     tc_stage_rows_kernel<<<tc_grid((int64_t)n_cand * 32), 256, 0, s>>>(d_V, n_model_items, k, d_cand, 1, n_cand, c.kp, c.Vb.p, nullptr, nullptr, c.vmax.p, c.bad_b.p, c.bf16 ? 1 : 0);
     tc_stage_rows_kernel<<<tc_grid((int64_t)c.n_samp * 32), 256, 0, s>>>(d_V, n_model_items, k, d_cand, c.stride, c.n_samp, c.kp, c.Vs.p, nullptr, nullptr, nullptr, c.bad_s.p, c.bf16 ? 1 : 0);
     if (d_cand) {
-        MML_TRY(c.pos_of.alloc(std::max(n_model_items, 1)));
+        MML_TRY(c.pos_of.ensure(std::max(n_model_items, 1)));
         MML_CUDA(cudaMemsetAsync(c.pos_of.p, 0xff, c.pos_of.bytes(), s));
         tc_pos_of_kernel<<<(unsigned)ceil_div(n_cand, 256), 256, 0, s>>>(d_cand, n_cand, n_model_items, c.pos_of.p);
     }
@@ -651,17 +651,54 @@ static int32_t tc_prepare_candidates(Ctx* ctx, TcCandidates& c, const float* d_V
     return MML_OK;
 }
 
-// Per-batch buffers of one Recommend() call, allocated once for the largest batch.
+// Per-batch buffers of Recommend(): grow-only members of the context's cache (no cudaMalloc / cudaFree per call -- a fresh
+// 1.3 GB workspace per call cost 3 to 80 ms on round 1's boxes). The per-batch inputs (users, ignore CSR) and outputs
+// (lists, counts, redo flags, the pipeline error word) exist twice: batch b + 1 is uploaded and batch b - 1 downloaded
+// through page-locked staging on the copy streams while batch b's kernels run.
 struct TcWork {
     int32_t cap_users = 0, splits = 1, tps = 1, stages = 2, stages0 = 2;
     size_t smem = 0, smem0 = 0;
-    DevBuf<float> Ub, unorm, thr, d2, buf_s, out_s;
-    DevBuf<uint8_t> row_ok, redo;
-    DevBuf<uint32_t> err;
-    DevBuf<int32_t> buf_p, buf_n, users, out_i, out_c, ign_idx;
-    DevBuf<int64_t> ign_ptr;
-    DevBuf<uint32_t> row_of, flag, key, t1, t2;
+    DevBuf<float> Ub, unorm, thr, d2, buf_s;
+    DevBuf<uint8_t> row_ok;
+    DevBuf<int32_t> buf_p, buf_n;
+    DevBuf<uint32_t> row_of, key, t1, t2;
+    // double-buffered per batch
+    DevBuf<int32_t> users[2], ign_idx[2], out_i[2], out_c[2];
+    DevBuf<int64_t> ign_ptr[2];
+    DevBuf<float> out_s[2];
+    DevBuf<uint8_t> redo[2];
+    DevBuf<uint32_t> err[2];
+    PinBuf<int32_t> h_users[2], h_ign_idx[2], h_out_i[2], h_out_c[2];
+    PinBuf<int64_t> h_ign_ptr[2];
+    PinBuf<float> h_out_s[2];
+    PinBuf<uint8_t> h_redo[2];
+    PinBuf<uint32_t> h_err[2];
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
+
+struct TopnCache {
+    TcCandidates c;
+    TcWork w;
+};
+
+static TopnCache* topn_cache(Ctx* ctx)
+{
+    if (!ctx->topn_cache) ctx->topn_cache = new (std::nothrow) TopnCache();
+    return reinterpret_cast<TopnCache*>(ctx->topn_cache);
+}
+
+void topn_cache_destroy(Ctx* ctx)
+{
+    TopnCache* t = reinterpret_cast<TopnCache*>(ctx->topn_cache);
+    if (!t) return;
+    for (int x = 0; x < 2; x++) {
+        if (t->w.ev_in[x]) cudaEventDestroy(t->w.ev_in[x]);
+        if (t->w.ev_done[x]) cudaEventDestroy(t->w.ev_done[x]);
+        if (t->w.ev_out[x]) cudaEventDestroy(t->w.ev_out[x]);
+    }
+    delete t;
+    ctx->topn_cache = nullptr;
+}
 
 static int32_t tc_alloc_work(Ctx* ctx, TcWork& w, const TcCandidates& c, int32_t cap_users, int32_t n_out, int64_t max_ign)
 {
@@ -673,16 +710,28 @@ static int32_t tc_alloc_work(Ctx* ctx, TcWork& w, const TcCandidates& c, int32_t
     splits = std::max(splits, 1);
     w.tps = (int)ceil_div(n_tiles, splits);
     w.splits = (int)ceil_div(n_tiles, w.tps);
-    MML_TRY(w.Ub.alloc((size_t)rows_pad * c.row_floats()));
-    MML_TRY(w.unorm.alloc(cap_users)); MML_TRY(w.thr.alloc(cap_users)); MML_TRY(w.d2.alloc(cap_users));
-    MML_TRY(w.row_ok.alloc(cap_users)); MML_TRY(w.redo.alloc(cap_users)); MML_TRY(w.err.alloc(1));
-    MML_TRY(w.buf_s.alloc((size_t)cap_users * w.splits * 2 * TC_CAP)); MML_TRY(w.buf_p.alloc((size_t)cap_users * w.splits * 2 * TC_CAP));
-    MML_TRY(w.buf_n.alloc((size_t)cap_users * w.splits * 2));
-    MML_TRY(w.users.alloc(cap_users)); MML_TRY(w.out_i.alloc((size_t)cap_users * n_out)); MML_TRY(w.out_s.alloc((size_t)cap_users * n_out));
-    MML_TRY(w.out_c.alloc(cap_users));
+    MML_TRY(w.Ub.ensure((size_t)rows_pad * c.row_floats()));
+    MML_TRY(w.unorm.ensure(cap_users)); MML_TRY(w.thr.ensure(cap_users)); MML_TRY(w.d2.ensure(cap_users));
+    MML_TRY(w.row_ok.ensure(cap_users));
+    MML_TRY(w.buf_s.ensure((size_t)cap_users * w.splits * 2 * TC_CAP)); MML_TRY(w.buf_p.ensure((size_t)cap_users * w.splits * 2 * TC_CAP));
+    MML_TRY(w.buf_n.ensure((size_t)cap_users * w.splits * 2));
     if (max_ign > 0) {
-        MML_TRY(w.ign_ptr.alloc((size_t)cap_users + 1)); MML_TRY(w.ign_idx.alloc(max_ign));
-        MML_TRY(w.row_of.alloc(max_ign)); MML_TRY(w.flag.alloc(1));
+        MML_TRY(w.row_of.ensure(max_ign)); MML_TRY(w.key.ensure(max_ign)); MML_TRY(w.t1.ensure(max_ign)); MML_TRY(w.t2.ensure(max_ign));
+    }
+    for (int x = 0; x < 2; x++) {
+        MML_TRY(w.users[x].ensure(cap_users)); MML_TRY(w.out_i[x].ensure((size_t)cap_users * n_out)); MML_TRY(w.out_s[x].ensure((size_t)cap_users * n_out));
+        MML_TRY(w.out_c[x].ensure(cap_users)); MML_TRY(w.redo[x].ensure(cap_users)); MML_TRY(w.err[x].ensure(1));
+        MML_TRY(w.h_users[x].ensure(cap_users)); MML_TRY(w.h_out_i[x].ensure((size_t)cap_users * n_out)); MML_TRY(w.h_out_s[x].ensure((size_t)cap_users * n_out));
+        MML_TRY(w.h_out_c[x].ensure(cap_users)); MML_TRY(w.h_redo[x].ensure(cap_users)); MML_TRY(w.h_err[x].ensure(1));
+        if (max_ign > 0) {
+            MML_TRY(w.ign_ptr[x].ensure((size_t)cap_users + 1)); MML_TRY(w.ign_idx[x].ensure(max_ign));
+            MML_TRY(w.h_ign_ptr[x].ensure((size_t)cap_users + 1)); MML_TRY(w.h_ign_idx[x].ensure(max_ign));
+        }
+        if (!w.ev_in[x]) {
+            MML_CUDA(cudaEventCreateWithFlags(&w.ev_in[x], cudaEventDisableTiming));
+            MML_CUDA(cudaEventCreateWithFlags(&w.ev_done[x], cudaEventDisableTiming));
+            MML_CUDA(cudaEventCreateWithFlags(&w.ev_out[x], cudaEventDisableTiming));
+        }
     }
     int max_optin = 0;
     MML_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
@@ -699,43 +748,38 @@ static int32_t tc_alloc_work(Ctx* ctx, TcWork& w, const TcCandidates& c, int32_t
     return MML_OK;
 }
 
-// Top n of a user batch on the tensor-core path; users and the ignore CSR (item ids) are already in w.users / w.ign_*.
-// w.redo[b] = 1 for users whose candidate superset could not be proven complete (caller re-runs them exactly).
-// Results: w.out_i / w.out_s [n_users x n_out], w.out_c [n_users].
-static int32_t topn_tc_batch(Ctx* ctx, TcCandidates& c, TcWork& w, const float* d_U, int32_t n_model_users, const float* d_V,
+// Top n of a user batch on the tensor-core path; users and the ignore CSR (item ids) are already in w.users[x] / w.ign_*[x].
+// w.redo[x][b] = 1 for users whose candidate superset could not be proven complete (caller re-runs them exactly).
+// Results: w.out_i[x] / w.out_s[x] [n_users x n_out], w.out_c[x] [n_users]. Nothing here waits for the device.
+static int32_t topn_tc_batch(Ctx* ctx, TcCandidates& c, TcWork& w, int x, const float* d_U, int32_t n_model_users, const float* d_V,
                              int32_t n_model_items, int32_t k, int32_t n_users, int32_t n, int32_t n_out, const int32_t* d_cand,
                              int64_t n_ign, int64_t* launches)
 {
     cudaStream_t s = ctx->stream;
     const int32_t kp = c.kp, kc = c.kc;
     const int64_t rows_pad = ceil_div(n_users, TC_ROWS) * TC_ROWS;
-    MML_CUDA(cudaMemsetAsync(w.err.p, 0, sizeof(uint32_t), s));
+    MML_CUDA(cudaMemsetAsync(w.err[x].p, 0, sizeof(uint32_t), s));
+    MML_CUDA(cudaMemsetAsync(w.out_i[x].p, 0, sizeof(int32_t) * (size_t)n_users * n_out, s));
+    MML_CUDA(cudaMemsetAsync(w.out_s[x].p, 0, sizeof(float) * (size_t)n_users * n_out, s));
     const size_t rf = c.row_floats();
     if (rows_pad > n_users) MML_CUDA(cudaMemsetAsync(w.Ub.p + (size_t)n_users * rf, 0, sizeof(float) * (size_t)(rows_pad - n_users) * rf, s));
-    tc_stage_rows_kernel<<<tc_grid((int64_t)n_users * 32), 256, 0, s>>>(d_U, n_model_users, k, w.users.p, 1, n_users, kp, w.Ub.p, w.unorm.p, w.row_ok.p, nullptr, nullptr, c.bf16 ? 1 : 0);
+    tc_stage_rows_kernel<<<tc_grid((int64_t)n_users * 32), 256, 0, s>>>(d_U, n_model_users, k, w.users[x].p, 1, n_users, kp, w.Ub.p, w.unorm.p, w.row_ok.p, nullptr, nullptr, c.bf16 ? 1 : 0);
     MML_CUDA(cudaGetLastError());
     if (launches) *launches += 1;
-    // ignore_items as candidate positions, ascending inside a row (the epilogue walks them with a cursor)
+    // ignore_items as candidate positions, ascending inside a row (the epilogue walks them with a cursor): always sorted on
+    // the device by (row, position) -- half a millisecond per 5M entries, and no round trip to the host to ask whether the
+    // caller's lists were already in order
     const bool have_ign = n_ign > 0;
     if (have_ign) {
-        MML_CUDA(cudaMemsetAsync(w.flag.p, 0, sizeof(uint32_t), s));
-        tc_ignore_pos_kernel<<<tc_grid(n_ign), 256, 0, s>>>(w.ign_ptr.p, n_users, w.ign_idx.p, n_ign, d_cand ? c.pos_of.p : nullptr,
+        tc_ignore_pos_kernel<<<tc_grid(n_ign), 256, 0, s>>>(w.ign_ptr[x].p, n_users, w.ign_idx[x].p, n_ign, d_cand ? c.pos_of.p : nullptr,
                                                            n_model_items, c.n_cand, w.row_of.p);
-        tc_ignore_sorted_kernel<<<tc_grid(n_ign), 256, 0, s>>>(w.ign_ptr.p, w.row_of.p, w.ign_idx.p, n_ign, w.flag.p);
+        tc_copy_u32_kernel<<<tc_grid(n_ign), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(w.ign_idx[x].p), n_ign, w.key.p);
         MML_CUDA(cudaGetLastError());
-        uint32_t unsorted = 0;
-        MML_CUDA(cudaMemcpyAsync(&unsorted, w.flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        MML_CUDA(cudaStreamSynchronize(s));
-        if (launches) *launches += 2;
-        if (unsorted) {     // positions are non-negative: plain unsigned radix order
-            if (w.key.n < (size_t)n_ign) { MML_TRY(w.key.alloc(n_ign)); MML_TRY(w.t1.alloc(n_ign)); MML_TRY(w.t2.alloc(n_ign)); }
-            tc_copy_u32_kernel<<<tc_grid(n_ign), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(w.ign_idx.p), n_ign, w.key.p);
-            MML_TRY(radix_sort_pairs(w.key.p, w.row_of.p, w.t1.p, w.t2.p, n_ign, 31, s));                                              // by position
-            MML_TRY(radix_sort_pairs(w.row_of.p, w.key.p, w.t1.p, w.t2.p, n_ign, bits_for((uint32_t)std::max(n_users - 1, 1)), s));   // by row, stable
-            tc_copy_u32_kernel<<<tc_grid(n_ign), 256, 0, s>>>(w.key.p, n_ign, reinterpret_cast<uint32_t*>(w.ign_idx.p));
-            MML_CUDA(cudaGetLastError());
-            if (launches) *launches += 12;
-        }
+        MML_TRY(radix_sort_pairs(w.key.p, w.row_of.p, w.t1.p, w.t2.p, n_ign, 31, s));                                              // by position
+        MML_TRY(radix_sort_pairs(w.row_of.p, w.key.p, w.t1.p, w.t2.p, n_ign, bits_for((uint32_t)std::max(n_users - 1, 1)), s));   // by row, stable
+        tc_copy_u32_kernel<<<tc_grid(n_ign), 256, 0, s>>>(w.key.p, n_ign, reinterpret_cast<uint32_t*>(w.ign_idx[x].p));
+        MML_CUDA(cudaGetLastError());
+        if (launches) *launches += 13;
     }
     CUtensorMap map_u;
     MML_TRY(make_panel_map(&map_u, w.Ub.p, rows_pad, kp, c.bf16));
@@ -743,9 +787,9 @@ static int32_t topn_tc_batch(Ctx* ctx, TcCandidates& c, TcWork& w, const float* 
     TcArgs a{};
     a.n_rows = n_users; a.kc = kc; a.m = n;
     a.bf16 = c.bf16 ? 1 : 0; a.epc = c.bf16 ? TC_KC_BF16 : TC_KC;
-    { const char* e = getenv("MMLB200_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
-    a.row_ok = w.row_ok.p; a.ign_ptr = have_ign ? w.ign_ptr.p : nullptr; a.ign_pos = w.ign_idx.p;
-    a.thr = w.thr.p; a.err = w.err.p;
+    { static const int dbg = [] { const char* e = getenv("MMLB200_TC_DBG"); return e ? atoi(e) : 0; }(); a.dbg = dbg; }
+    a.row_ok = w.row_ok.p; a.ign_ptr = have_ign ? w.ign_ptr[x].p : nullptr; a.ign_pos = w.ign_idx[x].p;
+    a.thr = w.thr.p; a.err = w.err[x].p;
     // pass 1: threshold from the candidate sample
     a.stride = c.stride; a.n_tiles = (int)(c.samp_pad / TC_N); a.tiles_per_split = a.n_tiles; a.splits = 1;
     a.stages = w.stages0; a.list_off = (2 * kc + w.stages0) * TC_CHUNK_BYTES;
@@ -763,10 +807,10 @@ static int32_t topn_tc_batch(Ctx* ctx, TcCandidates& c, TcWork& w, const float* 
     score_select_kernel<1><<<dim3(row_tiles, w.splits), TC_THREADS, w.smem, s>>>(map_u, c.map_b, a);
     MML_CUDA(cudaGetLastError());
     FinArgs f{};
-    f.U = d_U; f.V = d_V; f.k = k; f.users = w.users.p; f.cand = d_cand;
+    f.U = d_U; f.V = d_V; f.k = k; f.users = w.users[x].p; f.cand = d_cand;
     f.buf_s = w.buf_s.p; f.buf_p = w.buf_p.p; f.buf_n = w.buf_n.p; f.thr = w.thr.p; f.d2 = w.d2.p; f.row_ok = w.row_ok.p;
     f.n_rows = n_users; f.splits = w.splits; f.n = n; f.n_out = n_out;
-    f.out_items = w.out_i.p; f.out_scores = w.out_s.p; f.out_counts = w.out_c.p; f.redo = w.redo.p;
+    f.out_items = w.out_i[x].p; f.out_scores = w.out_s[x].p; f.out_counts = w.out_c[x].p; f.redo = w.redo[x].p;
     const size_t per_warp = (size_t)w.splits * 2 * TC_CAP * 12;
     f.warps = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)96 * 1024 / per_warp));
     const size_t fsmem = per_warp * f.warps;
@@ -790,15 +834,21 @@ struct TcPhase {
     }
 };
 
-// All user batches of one Recommend() call. users / ignore CSR / outputs: host. d_cand: device or NULL.
+// All user batches of one Recommend() call. users / ignore CSR / outputs: host (pageable or not). d_cand: device or NULL.
+// Three streams: batch b + 1's inputs go up (copy_stream) and batch b - 1's results come down (out_stream) through
+// page-locked staging while batch b's kernels run (stream); the host only waits for staging it is about to reuse and for
+// results it is about to hand to the caller.
 int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
                     const int32_t* users, int64_t n_users, int32_t n, int32_t n_out, const int32_t* d_cand, int32_t n_cand,
                     bool has_invalid_cand, const int64_t* ignore_ptr, const int32_t* ignore_idx,
                     int32_t* out_items, float* out_scores, int32_t* out_counts, std::vector<int64_t>& redo_users, int64_t* launches)
 {
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = ctx->stream, cs = ctx->copy_stream, os = ctx->out_stream;
     TcPhase ph(s);
-    TcCandidates c;
+    TopnCache* cache = topn_cache(ctx);
+    MML_CHECK(cache != nullptr, MML_ERR_ARG, "out of host memory");
+    TcCandidates& c = cache->c;
+    TcWork& w = cache->w;
     c.bf16 = topn_tc_filter_bf16();
     MML_TRY(tc_prepare_candidates(ctx, c, d_V, n_model_items, k, d_cand, n_cand, has_invalid_cand, n, launches));
     ph.mark("candidate panels");
@@ -808,41 +858,63 @@ int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
     if (n_ign > 0)
         for (int64_t b_lo = 0; b_lo < n_users; b_lo += B)
             max_ign = std::max(max_ign, ignore_ptr[std::min(b_lo + B, n_users)] - ignore_ptr[b_lo]);
-    TcWork w;
     MML_TRY(tc_alloc_work(ctx, w, c, (int32_t)std::min<int64_t>(B, n_users), n_out, max_ign));
-    ph.mark("workspace alloc");
-    std::vector<uint8_t> h_redo;
-    std::vector<int64_t> ptr_local;
-    for (int64_t b_lo = 0; b_lo < n_users; b_lo += B) {
+    ph.mark("workspace");
+    // batch bookkeeping for the retire step
+    struct Pending { int64_t b_lo; int32_t nb; bool live; } pend[2] = {{0, 0, false}, {0, 0, false}};
+    auto retire = [&](int x) -> int32_t {
+        if (!pend[x].live) return MML_OK;
+        MML_CUDA(cudaEventSynchronize(w.ev_out[x]));
+        const int64_t b_lo = pend[x].b_lo; const int32_t nb = pend[x].nb;
+        MML_CHECK(w.h_err[x].p[0] == 0, MML_ERR_CUDA, "topn: tcgen05 pipeline timed out");
+        memcpy(out_items + (size_t)b_lo * n_out, w.h_out_i[x].p, sizeof(int32_t) * (size_t)nb * n_out);
+        memcpy(out_scores + (size_t)b_lo * n_out, w.h_out_s[x].p, sizeof(float) * (size_t)nb * n_out);
+        memcpy(out_counts + b_lo, w.h_out_c[x].p, sizeof(int32_t) * (size_t)nb);
+        const uint8_t* rd = w.h_redo[x].p;
+        for (int32_t t = 0; t < nb; t++) if (rd[t]) redo_users.push_back(b_lo + t);
+        pend[x].live = false;
+        return MML_OK;
+    };
+    int bi = 0;
+    for (int64_t b_lo = 0; b_lo < n_users; b_lo += B, bi++) {
+        const int x = bi & 1;
         const int32_t nb = (int32_t)std::min<int64_t>(B, n_users - b_lo);
-        MML_CUDA(cudaMemcpyAsync(w.users.p, users + b_lo, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s));
-        MML_CUDA(cudaMemsetAsync(w.out_i.p, 0, sizeof(int32_t) * (size_t)nb * n_out, s));
-        MML_CUDA(cudaMemsetAsync(w.out_s.p, 0, sizeof(float) * (size_t)nb * n_out, s));
+        // staging x was last read by the upload of batch bi - 2, device inputs x by its kernels: both finished once its
+        // results were retired (previous iteration)
+        memcpy(w.h_users[x].p, users + b_lo, sizeof(int32_t) * (size_t)nb);
+        MML_CUDA(cudaMemcpyAsync(w.users[x].p, w.h_users[x].p, sizeof(int32_t) * (size_t)nb, cudaMemcpyHostToDevice, cs));
         int64_t nib = 0;
         if (n_ign > 0) {
             const int64_t i_lo = ignore_ptr[b_lo];
             nib = ignore_ptr[b_lo + nb] - i_lo;
-            ptr_local.resize((size_t)nb + 1);
-            for (int32_t t = 0; t <= nb; t++) ptr_local[t] = ignore_ptr[b_lo + t] - i_lo;
-            MML_CUDA(cudaMemcpyAsync(w.ign_ptr.p, ptr_local.data(), sizeof(int64_t) * ((size_t)nb + 1), cudaMemcpyHostToDevice, s));
-            if (nib > 0) MML_CUDA(cudaMemcpyAsync(w.ign_idx.p, ignore_idx + i_lo, sizeof(int32_t) * (size_t)nib, cudaMemcpyHostToDevice, s));
-            MML_CUDA(cudaStreamSynchronize(s));      // ptr_local is reused by the next batch
+            int64_t* pl = w.h_ign_ptr[x].p;
+            for (int32_t t = 0; t <= nb; t++) pl[t] = ignore_ptr[b_lo + t] - i_lo;
+            MML_CUDA(cudaMemcpyAsync(w.ign_ptr[x].p, pl, sizeof(int64_t) * ((size_t)nb + 1), cudaMemcpyHostToDevice, cs));
+            if (nib > 0) {
+                memcpy(w.h_ign_idx[x].p, ignore_idx + i_lo, sizeof(int32_t) * (size_t)nib);
+                MML_CUDA(cudaMemcpyAsync(w.ign_idx[x].p, w.h_ign_idx[x].p, sizeof(int32_t) * (size_t)nib, cudaMemcpyHostToDevice, cs));
+            }
         }
+        MML_CUDA(cudaEventRecord(w.ev_in[x], cs));
+        MML_CUDA(cudaStreamWaitEvent(s, w.ev_in[x], 0));
         ph.mark("batch H2D");
-        MML_TRY(topn_tc_batch(ctx, c, w, d_U, n_model_users, d_V, n_model_items, k, nb, n, n_out, d_cand, nib, launches));
+        MML_TRY(topn_tc_batch(ctx, c, w, x, d_U, n_model_users, d_V, n_model_items, k, nb, n, n_out, d_cand, nib, launches));
+        MML_CUDA(cudaEventRecord(w.ev_done[x], s));
         ph.mark("batch kernels");
-        h_redo.resize(nb);
-        MML_CUDA(cudaMemcpyAsync(out_items + (size_t)b_lo * n_out, w.out_i.p, sizeof(int32_t) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, s));
-        MML_CUDA(cudaMemcpyAsync(out_scores + (size_t)b_lo * n_out, w.out_s.p, sizeof(float) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, s));
-        MML_CUDA(cudaMemcpyAsync(out_counts + b_lo, w.out_c.p, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
-        MML_CUDA(cudaMemcpyAsync(h_redo.data(), w.redo.p, nb, cudaMemcpyDeviceToHost, s));
-        MML_CUDA(cudaStreamSynchronize(s));
-        uint32_t h_err = 0;
-        MML_CUDA(cudaMemcpy(&h_err, w.err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        MML_CHECK(h_err == 0, MML_ERR_CUDA, "topn: tcgen05 pipeline timed out");
-        for (int32_t t = 0; t < nb; t++) if (h_redo[t]) redo_users.push_back(b_lo + t);
-        ph.mark("batch D2H");
+        MML_CUDA(cudaStreamWaitEvent(os, w.ev_done[x], 0));
+        MML_CUDA(cudaMemcpyAsync(w.h_out_i[x].p, w.out_i[x].p, sizeof(int32_t) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, os));
+        MML_CUDA(cudaMemcpyAsync(w.h_out_s[x].p, w.out_s[x].p, sizeof(float) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, os));
+        MML_CUDA(cudaMemcpyAsync(w.h_out_c[x].p, w.out_c[x].p, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, os));
+        MML_CUDA(cudaMemcpyAsync(w.h_redo[x].p, w.redo[x].p, (size_t)nb, cudaMemcpyDeviceToHost, os));
+        MML_CUDA(cudaMemcpyAsync(w.h_err[x].p, w.err[x].p, sizeof(uint32_t), cudaMemcpyDeviceToHost, os));
+        MML_CUDA(cudaEventRecord(w.ev_out[x], os));
+        pend[x] = {b_lo, nb, true};
+        MML_TRY(retire(x ^ 1));      // the previous batch, while this one computes
+        ph.mark("previous batch retired");
     }
+    MML_TRY(retire(bi & 1));            // batches bi - 2 (already retired in the loop: a no-op) and bi - 1
+    MML_TRY(retire((bi & 1) ^ 1));
+    MML_CUDA(cudaStreamSynchronize(s));
     return MML_OK;
 }
 

@@ -408,8 +408,11 @@ int32_t topn_device(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
 
 using namespace mml;
 
-struct mml_feedback { Feedback f; };
-struct mml_wrmf { Wrmf m; };
+// On a one-process multi-GPU context both handles are roots over one ordinary handle per GPU (shards[r] on rank r's
+// context): the feedback and the model are replicated, every half-sweep solves its own row range on every GPU and the rows
+// are all-gathered (as in the one-process-per-GPU mode); Recommend() / Evaluate() split their user lists over the GPUs.
+struct mml_feedback { Feedback f; std::vector<mml_feedback*> shards; };
+struct mml_wrmf { Wrmf m; std::vector<mml_wrmf*> shards; };
 namespace mml { Feedback* feedback_of(mml_feedback* h) { return h ? &h->f : nullptr; } }
 
 extern "C" int32_t mml_feedback_create(mml_ctx* hctx, const int32_t* users, const int32_t* items, int64_t n,
@@ -422,6 +425,19 @@ extern "C" int32_t mml_feedback_create(mml_ctx* hctx, const int32_t* users, cons
         MML_CHECK((uint32_t)users[t] <= (uint32_t)max_user && (uint32_t)items[t] <= (uint32_t)max_item, MML_ERR_ARG,
                   "mml_feedback_create: event %lld has id out of range (user %d, item %d)", (long long)t, users[t], items[t]);
     Ctx* ctx = ctx_of(hctx);
+    if (ctx->is_root()) {
+        mml_feedback* root = new (std::nothrow) mml_feedback();
+        MML_CHECK(root != nullptr, MML_ERR_ARG, "out of host memory");
+        root->f.ctx = ctx; root->f.max_user = max_user; root->f.max_item = max_item; root->f.n_events = n;
+        root->shards.assign(ctx->peers.size(), nullptr);
+        const int32_t st = on_ranks((int)ctx->peers.size(), [&](int x) -> int32_t {
+            return mml_feedback_create(ctx->peers[(size_t)x], users, items, n, max_user, max_item, &root->shards[(size_t)x]);
+        });
+        if (st != MML_OK) { mml_feedback_destroy(root); return st; }
+        root->f.nnz = root->shards[0]->f.nnz;
+        *out = root;
+        return MML_OK;
+    }
     MML_CUDA(cudaSetDevice(ctx->device));
     mml_feedback* h = new (std::nothrow) mml_feedback();
     MML_CHECK(h != nullptr, MML_ERR_ARG, "out of host memory");
@@ -436,6 +452,11 @@ extern "C" int32_t mml_feedback_destroy(mml_feedback* f)
 {
     MML_LOCK((f ? f->f.ctx : nullptr));
     if (!f) return MML_OK;
+    if (f->f.ctx->is_root()) {
+        for (mml_feedback* s : f->shards) mml_feedback_destroy(s);
+        delete f;
+        return MML_OK;
+    }
     cudaSetDevice(f->f.ctx->device);
     delete f;
     return MML_OK;
@@ -453,6 +474,7 @@ extern "C" int32_t mml_feedback_csr(mml_feedback* h, int32_t by_item, int64_t* r
 {
     MML_LOCK((h ? h->f.ctx : nullptr));
     MML_CHECK(h && row_ptr && cols, MML_ERR_ARG, "NULL argument");
+    if (!h->shards.empty()) return mml_feedback_csr(h->shards[0], by_item, row_ptr, cols);
     Feedback& f = h->f;
     MML_CUDA(cudaSetDevice(f.ctx->device));
     cudaStream_t s = f.ctx->stream;
@@ -472,6 +494,19 @@ extern "C" int32_t mml_wrmf_create(mml_ctx* hctx, mml_feedback* hf, const mml_wr
     MML_CHECK(hctx && hf && p && out, MML_ERR_ARG, "mml_wrmf_create: NULL argument");
     MML_CHECK(p->num_factors >= 1 && p->num_factors <= 160, MML_ERR_UNSUPPORTED, "mml_wrmf_create: num_factors=%d not in [1,160]", p->num_factors);
     Ctx* ctx = ctx_of(hctx);
+    if (ctx->is_root()) {
+        MML_CHECK(hf->shards.size() == ctx->peers.size(), MML_ERR_ARG, "mml_wrmf_create: the feedback was not created on this multi-GPU context");
+        mml_wrmf* root = new (std::nothrow) mml_wrmf();
+        MML_CHECK(root != nullptr, MML_ERR_ARG, "out of host memory");
+        root->m.ctx = ctx; root->m.fb = &hf->f; root->m.k = p->num_factors; root->m.alpha = p->alpha; root->m.reg = p->regularization;
+        root->shards.assign(ctx->peers.size(), nullptr);
+        const int32_t st = on_ranks((int)ctx->peers.size(), [&](int x) -> int32_t {
+            return mml_wrmf_create(ctx->peers[(size_t)x], hf->shards[(size_t)x], p, &root->shards[(size_t)x]);
+        });
+        if (st != MML_OK) { mml_wrmf_destroy(root); return st; }
+        *out = root;
+        return MML_OK;
+    }
     MML_CUDA(cudaSetDevice(ctx->device));
     mml_wrmf* h = new (std::nothrow) mml_wrmf();
     MML_CHECK(h != nullptr, MML_ERR_ARG, "out of host memory");
@@ -502,6 +537,11 @@ extern "C" int32_t mml_wrmf_destroy(mml_wrmf* h)
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     if (!h) return MML_OK;
+    if (h->m.ctx->is_root()) {
+        for (mml_wrmf* s : h->shards) mml_wrmf_destroy(s);
+        delete h;
+        return MML_OK;
+    }
     cudaSetDevice(h->m.ctx->device);
     cudaStreamSynchronize(h->m.ctx->stream);
     if (h->m.ev0) cudaEventDestroy(h->m.ev0);
@@ -515,6 +555,7 @@ extern "C" int32_t mml_wrmf_set_model(mml_wrmf* h, const float* user_factors, co
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && user_factors && item_factors, MML_ERR_ARG, "mml_wrmf_set_model: NULL argument");
+    MML_FORWARD_ALL(h, mml_wrmf_set_model(s, user_factors, item_factors));
     Wrmf& m = h->m;
     MML_CUDA(cudaSetDevice(m.ctx->device));
     cudaStream_t s = m.ctx->stream;
@@ -543,6 +584,7 @@ extern "C" int32_t mml_wrmf_init_model(mml_wrmf* h, uint64_t seed, double init_m
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
+    MML_FORWARD_ALL(h, mml_wrmf_init_model(s, seed, init_mean, init_stddev));   // counter-based: the same model on every GPU
     Wrmf& m = h->m;
     MML_CUDA(cudaSetDevice(m.ctx->device));
     cudaStream_t s = m.ctx->stream;
@@ -560,6 +602,7 @@ extern "C" int32_t mml_wrmf_get_model(mml_wrmf* h, float* user_factors, float* i
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
+    if (!h->shards.empty()) return mml_wrmf_get_model(h->shards[0], user_factors, item_factors);   // replicated
     Wrmf& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_wrmf_get_model: no model");
     MML_CUDA(cudaSetDevice(m.ctx->device));
@@ -585,6 +628,7 @@ extern "C" int32_t mml_wrmf_shard(mml_wrmf* h, int32_t by_item, int32_t* ranges)
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && ranges, MML_ERR_ARG, "NULL argument");
+    if (!h->shards.empty()) return mml_wrmf_shard(h->shards[0], by_item, ranges);
     const std::vector<int32_t>& r = by_item ? h->m.range_i : h->m.range_u;
     for (size_t t = 0; t < r.size(); t++) ranges[t] = r[t];
     return MML_OK;
@@ -595,6 +639,7 @@ extern "C" int32_t mml_wrmf_iterate(mml_wrmf* h)
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
+    MML_FORWARD_ALL(h, mml_wrmf_iterate(s));
     Wrmf& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_wrmf_iterate: no model (call set_model / init_model first)");
     MML_CUDA(cudaSetDevice(m.ctx->device));
@@ -614,6 +659,7 @@ extern "C" int32_t mml_wrmf_retrain(mml_wrmf* h, int32_t by_item, const int32_t*
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && (n == 0 || ids), MML_ERR_ARG, "mml_wrmf_retrain: NULL argument");
+    MML_FORWARD_ALL(h, mml_wrmf_retrain(s, by_item, ids, n));   // replicated model: every GPU re-solves the rows itself
     Wrmf& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_wrmf_retrain: no model");
     MML_CHECK(n >= 0 && n < ((int64_t)1 << 31), MML_ERR_ARG, "mml_wrmf_retrain: bad count");
@@ -646,6 +692,7 @@ extern "C" int32_t mml_wrmf_debug_gram(mml_wrmf* h, float* out_gram, int32_t* ou
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && out_gram && out_user, MML_ERR_ARG, "NULL argument");
+    if (!h->shards.empty()) return mml_wrmf_debug_gram(h->shards[0], out_gram, out_user);
     Wrmf& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_wrmf_debug_gram: no model");
     MML_CHECK(wrmf_tc_eligible(m.k), MML_ERR_UNSUPPORTED, "mml_wrmf_debug_gram: num_factors outside the tensor-core path");
@@ -667,6 +714,17 @@ extern "C" int32_t mml_wrmf_stats(mml_wrmf* h, int64_t* kernel_launches, float* 
 {
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h, MML_ERR_ARG, "NULL argument");
+    if (!h->shards.empty()) {   // launches of all GPUs, device time of the slowest
+        int64_t total = 0; float worst = 0.f;
+        for (mml_wrmf* s : h->shards) {
+            int64_t l = 0; float ms = 0.f;
+            MML_TRY(mml_wrmf_stats(s, &l, &ms));
+            total += l; worst = std::max(worst, ms);
+        }
+        if (kernel_launches) *kernel_launches = total;
+        if (last_iterate_ms) *last_iterate_ms = worst;
+        return MML_OK;
+    }
     Wrmf& m = h->m;
     if (kernel_launches) *kernel_launches = m.launches;
     if (last_iterate_ms) {
@@ -692,6 +750,20 @@ extern "C" int32_t mml_wrmf_evaluate(mml_wrmf* h, const int32_t* test_users, int
               "mml_wrmf_evaluate: NULL argument");
     MML_CHECK((n > 0 || n == -1) && n_test_users >= 0, MML_ERR_ARG, "mml_wrmf_evaluate: n must be > 0 or -1");
     MML_CHECK(test_ptr[n_test_users] == 0 || test_idx, MML_ERR_ARG, "mml_wrmf_evaluate: NULL test_idx");
+    if (!h->shards.empty()) {   // contiguous ranges of the test users, one per GPU; rows of the outputs are disjoint
+        const int64_t N = (int64_t)h->shards.size();
+        return on_ranks((int)N, [&](int x) -> int32_t {
+            const int64_t lo = n_test_users * x / N, hi = n_test_users * (x + 1) / N;
+            if (hi <= lo) return MML_OK;
+            std::vector<int64_t> tp((size_t)(hi - lo + 1)), ip;
+            for (int64_t t = lo; t <= hi; t++) tp[(size_t)(t - lo)] = test_ptr[t] - test_ptr[lo];
+            const bool ign = ignore_ptr && ignore_idx;
+            if (ign) { ip.resize((size_t)(hi - lo + 1)); for (int64_t t = lo; t <= hi; t++) ip[(size_t)(t - lo)] = ignore_ptr[t] - ignore_ptr[lo]; }
+            return mml_wrmf_evaluate(h->shards[(size_t)x], test_users + lo, hi - lo, candidates, n_cand, tp.data(),
+                                     test_idx ? test_idx + test_ptr[lo] : nullptr, ign ? ip.data() : nullptr,
+                                     ign ? ignore_idx + ignore_ptr[lo] : nullptr, n, out_measures + lo * 8, out_used + lo);
+        });
+    }
     Wrmf& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_wrmf_evaluate: no model");
     MML_CUDA(cudaSetDevice(m.ctx->device));
@@ -708,6 +780,21 @@ extern "C" int32_t mml_wrmf_recommend(mml_wrmf* h, const int32_t* users, int64_t
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && (n_users == 0 || (users && out_items && out_scores && out_counts)), MML_ERR_ARG, "mml_wrmf_recommend: NULL argument");
     MML_CHECK(n > 0 || n == -1, MML_ERR_ARG, "mml_wrmf_recommend: n must be > 0 or -1");
+    if (!h->shards.empty()) {   // Top-N shards users with no collective: contiguous ranges of the user list, one per GPU
+        const int64_t N = (int64_t)h->shards.size();
+        const int64_t nc = candidates ? n_cand : h->m.fb->n_items();
+        const int64_t n_out = n < 0 ? nc : std::min<int64_t>(n, nc);
+        return on_ranks((int)N, [&](int x) -> int32_t {
+            const int64_t lo = n_users * x / N, hi = n_users * (x + 1) / N;
+            if (hi <= lo) return MML_OK;
+            std::vector<int64_t> ip;
+            const bool ign = ignore_ptr && ignore_idx;
+            if (ign) { ip.resize((size_t)(hi - lo + 1)); for (int64_t t = lo; t <= hi; t++) ip[(size_t)(t - lo)] = ignore_ptr[t] - ignore_ptr[lo]; }
+            return mml_wrmf_recommend(h->shards[(size_t)x], users + lo, hi - lo, n, candidates, n_cand, ign ? ip.data() : nullptr,
+                                      ign ? ignore_idx + ignore_ptr[lo] : nullptr, out_items + lo * n_out, out_scores + lo * n_out,
+                                      out_counts + lo);
+        });
+    }
     Wrmf& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_wrmf_recommend: no model");
     MML_CUDA(cudaSetDevice(m.ctx->device));

@@ -17,19 +17,22 @@ def _f32(a):
 
 
 class Context:
-    """One GPU (one process per GPU). Raises MmlError without a CUDA device: there is no CPU path."""
+    """One GPU of a one-process-per-GPU job (rank / world / unique_id), or -- n_gpus > 1 -- the GPUs device ..
+    device + n_gpus - 1 driven from this one process (mml_ctx_create with n_gpus > 1: the NumGpus property of the host
+    classes). Raises MmlError without a CUDA device: there is no CPU path."""
 
-    def __init__(self, device=0, rank=0, world=1, unique_id=None):
+    def __init__(self, device=0, rank=0, world=1, unique_id=None, n_gpus=1):
         self.lib = _capi.load()
-        self.rank, self.world = rank, world
+        self.rank, self.world, self.n_gpus = rank, world, int(n_gpus)
         h = C.c_void_p()
         if world > 1:
+            assert n_gpus == 1, "one process per GPU and several GPUs per process do not mix"
             uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
             assert uid.size == 128
             check(self.lib.mml_ctx_create_dist(rank, world, device, uid, C.byref(h)))
         else:
-            dev = np.array([device], dtype=np.int32)
-            check(self.lib.mml_ctx_create(1, dev, C.byref(h)))
+            dev = np.arange(device, device + self.n_gpus, dtype=np.int32)
+            check(self.lib.mml_ctx_create(self.n_gpus, dev, C.byref(h)))
         self.h = h
 
     @staticmethod
@@ -435,13 +438,16 @@ class WrmfModel:
         check(self.lib.mml_wrmf_stats(self.h, C.byref(n), C.byref(ms)))
         return n.value, ms.value
 
-    def recommend(self, users, n=-1, candidates=None, ignore_lists=None):
+    def recommend(self, users, n=-1, candidates=None, ignore_lists=None, raw=False):
+        """ignore_lists: per-user id sequences or a ready (ptr, idx) CSR; raw: return the (items, scores, counts) arrays."""
         users = _i32(users)
         cand = _i32(candidates)
         n_cand = self.n_items if cand is None else cand.shape[0]
         oi, os_, oc, n_out = _topn_outputs(users.shape[0], n, n_cand)
-        ptr, idx = _ignore_csr(ignore_lists, users.shape[0])
+        ptr, idx = _rows_csr(ignore_lists, users.shape[0])
         check(self.lib.mml_wrmf_recommend(self.h, users, users.shape[0], int(n), cand, n_cand, ptr, idx, oi, os_, oc))
+        if raw:
+            return oi, os_, oc
         return [(oi[b, :oc[b]].copy(), os_[b, :oc[b]].copy()) for b in range(users.shape[0])]
 
     def evaluate(self, test_users, candidates, test_rows, ignore_rows=None, n=-1):

@@ -15,14 +15,41 @@ import numpy as np
 
 from . import _capi, engine, modelio, sysrandom
 
+import os
+
 _ctx = {}
 
 
-def context(device=0):
-    """One library context per device and process (mml_ctx)."""
-    if device not in _ctx:
-        _ctx[device] = engine.Context(device)
-    return _ctx[device]
+def context(n_gpus=1):
+    """One library context per process and GPU count (mml_ctx): GPUs 0 .. n_gpus - 1, one process driving all of them."""
+    n_gpus = max(int(n_gpus), 1)
+    if n_gpus not in _ctx:
+        _ctx[n_gpus] = engine.Context(0, n_gpus=n_gpus)
+    return _ctx[n_gpus]
+
+
+# The one documented engine knob (process-wide, not a recommender option: the option set stays the reference's + NumGpus).
+#   order: "auto" (default)  -- Iterate() runs the parallel epoch kernel (the DSGD block schedule, whatever MaxThreads says;
+#                               MaxThreads keeps its other meaning, UpdateLearnRate twice per epoch when > 1), except on
+#                               data sets below SERIAL_BELOW ratings, where the exact single-threaded order costs nothing;
+#          "reference"       -- MaxThreads = 1 walks RandomIndex in the reference's order on one warp (parity runs);
+#          "parallel"        -- always the parallel kernel.
+#   init:  "host" (default)  -- InitModel draws from MyMediaLite.Random on the host, in the reference's order;
+#          "device"          -- counter-based generator on the device (large models: no host sampling).
+# Environment: MMLB200_ORDER, MMLB200_INIT.
+ENGINE = {"order": os.environ.get("MMLB200_ORDER", "auto"), "init": os.environ.get("MMLB200_INIT", "host")}
+SERIAL_BELOW = 20000
+
+
+def set_engine(order=None, init=None):
+    if order is not None:
+        if order not in ("auto", "reference", "parallel"):
+            raise ValueError("order must be auto, reference or parallel")
+        ENGINE["order"] = order
+    if init is not None:
+        if init not in ("host", "device"):
+            raise ValueError("init must be host or device")
+        ENGINE["init"] = init
 
 
 class Ratings:
@@ -102,10 +129,9 @@ class MatrixFactorization(_Recommender):
         self.InitStdDev = 0.1
         self.InitMean = 0.0
         self.NumFactors = 10
-        # engine properties (the only additions to the reference's option set)
+        # the one addition to the reference's option set: GPUs this process trains on (mml_ctx_create(n_gpus))
         self.NumGpus = 1
-        self.Schedule = "serial"        # "serial": the reference's single-threaded order; "dsgd": the block schedule
-        self.InitOnDevice = False       # True: counter-based device generator instead of MyMediaLite.Random
+        self._is_parallel = False
         self.MinRating = 1.0
         self.MaxRating = 5.0
         self.Ratings = None
@@ -113,11 +139,20 @@ class MatrixFactorization(_Recommender):
         self._dev_ratings = None
 
     # -- plumbing -----------------------------------------------------------------------------------------------
+    def _parallel(self):
+        """Whether Iterate() runs the parallel epoch kernel (see ENGINE above). Several GPUs always do."""
+        if int(self.NumGpus) > 1 or ENGINE["order"] == "parallel":
+            return True
+        if ENGINE["order"] == "reference":
+            return getattr(self, "MaxThreads", 1) > 1
+        n = self.Ratings.Count if self.Ratings is not None else 0
+        return getattr(self, "MaxThreads", 1) > 1 or n >= SERIAL_BELOW
+
     def _params(self):
         return engine.default_params(
             biased=self._biased, num_factors=int(self.NumFactors), learn_rate=float(self.LearnRate), decay=float(self.Decay),
             regularization=float(self.Regularization),
-            schedule=_capi.SCHEDULE_DSGD if self.Schedule == "dsgd" else _capi.SCHEDULE_SERIAL)
+            schedule=_capi.SCHEDULE_DSGD if self._parallel() else _capi.SCHEDULE_SERIAL)
 
     def _init_model(self):
         """InitModel (MatrixFactorization.cs:99-116): a fresh device model (Train() allocates a new handle, it never
@@ -126,12 +161,13 @@ class MatrixFactorization(_Recommender):
             raise ValueError("Ratings is not set")
         r = self.Ratings
         self.MaxUserID, self.MaxItemID = r.MaxUserID, r.MaxItemID
-        ctx = context()
+        ctx = context(self.NumGpus)
         self._dev_ratings = engine.DeviceRatings(ctx, r.Users, r.Items, r.Values, r.MaxUserID, r.MaxItemID)
         if r.Count:
             _, self.MinRating, self.MaxRating = self._dev_ratings.stats()
         self._model = engine.SgdModel(ctx, self._dev_ratings, self._params())
-        if self.InitOnDevice:
+        self._is_parallel = self._parallel()
+        if ENGINE["init"] == "device":
             self._model.init_model(sysrandom.get_instance().next(), self.InitMean, self.InitStdDev)
         else:
             rng = sysrandom.get_instance()
@@ -152,9 +188,9 @@ class MatrixFactorization(_Recommender):
             self.Iterate()
 
     def Iterate(self):
-        if self.Schedule == "dsgd":
+        if self._is_parallel:
             G = self._model.strata_info()["G"]
-            seq = sysrandom.get_instance().shuffle(np.arange(G))       # :210-211
+            seq = sysrandom.get_instance().shuffle(np.arange(G))       # BiasedMatrixFactorization.cs:210-211
             self._model.iterate(subepoch_sequence=seq)
         else:
             self._model.iterate(random_index=self.Ratings.RandomIndex)
@@ -284,6 +320,7 @@ class MatrixFactorization(_Recommender):
         self._dev_ratings = engine.DeviceRatings(ctx, uu, ii, vv, nu - 1, ni - 1)
         p = self._params()
         p.schedule = _capi.SCHEDULE_SERIAL
+        self._is_parallel = False
         self._model = engine.SgdModel(ctx, self._dev_ratings, p)
         self._model.set_model(U, V, bu, bi)
         _capi.check(ctx.lib.mml_sgd_set_scale(self._model.h, float(self.MinRating), float(self.MaxRating), float(bias)))
@@ -322,8 +359,9 @@ class BiasedMatrixFactorization(MatrixFactorization):
         object.__setattr__(self, name, value)
 
     def _params(self):
-        # MaxThreads > 1 selects the reference's DSGD block schedule (:178-184); on the GPU the worker groups are CTAs
-        dsgd = self.MaxThreads > 1 or self.Schedule == "dsgd"
+        # MaxThreads > 1 selects the reference's DSGD block schedule (:178-184); on the GPU the worker groups are CTAs, and
+        # the parallel kernel is also what MaxThreads = 1 runs unless the engine order says "reference" (ENGINE above)
+        dsgd = self._parallel()
         shape = {}
         if dsgd and self.NaiveParallelization:
             # :136-141, :201-204: lock-free Parallel.For over index lists, no block exclusivity -> the whole GPU is one
@@ -335,14 +373,6 @@ class BiasedMatrixFactorization(MatrixFactorization):
             reg_u=float(self.RegU), reg_i=float(self.RegI), frequency_regularization=int(bool(self.FrequencyRegularization)),
             loss=self._LOSS[self.Loss], bold_driver=int(bool(self.BoldDriver)), max_threads=int(self.MaxThreads),
             schedule=_capi.SCHEDULE_DSGD if dsgd else _capi.SCHEDULE_SERIAL))
-
-    def Iterate(self):
-        if self.MaxThreads > 1 or self.Schedule == "dsgd":
-            G = self._model.strata_info()["G"]
-            seq = sysrandom.get_instance().shuffle(np.arange(G))
-            self._model.iterate(subepoch_sequence=seq)
-        else:
-            self._model.iterate(random_index=self.Ratings.RandomIndex)
 
     def SaveModel(self, filename):
         m = self._model.get_model()
@@ -393,13 +423,13 @@ class WRMF(_Recommender):
         self.InitMean = 0.0
         self.InitStdDev = 0.1
         self.NumGpus = 1
-        self.InitOnDevice = False
         self.Feedback = None
         self._model = None
         self._fb = None
+        self._cache = None          # all-users top-N of the current model: (n, candidate key, train rows, items, scores, counts)
 
     def _new_model(self, n_users, n_items, users, items):
-        ctx = context()
+        ctx = context(self.NumGpus)
         self._fb = engine.DeviceFeedback(ctx, users, items, n_users - 1, n_items - 1)
         self._model = engine.WrmfModel(ctx, self._fb, int(self.NumFactors), float(self.Alpha), float(self.Regularization))
 
@@ -407,7 +437,7 @@ class WRMF(_Recommender):
         f = self.Feedback
         self.MaxUserID, self.MaxItemID = f.MaxUserID, f.MaxItemID
         self._new_model(f.MaxUserID + 1, f.MaxItemID + 1, f.Users, f.Items)
-        if self.InitOnDevice:
+        if ENGINE["init"] == "device":
             self._model.init_model(sysrandom.get_instance().next(), self.InitMean, self.InitStdDev)
         else:
             rng = sysrandom.get_instance()   # MF.cs:56-57: user matrix first, no zeroing of empty rows
@@ -422,6 +452,48 @@ class WRMF(_Recommender):
 
     def Iterate(self):
         self._model.iterate()
+        self._cache = None
+
+    # -- per-user Recommend() served from one batched all-users call ------------------------------------------------------
+    # Eval.Items.Evaluate (Eval/Items.cs:147-164) and WritePredictions (ItemRecommendation/Extensions.cs:65-128) call
+    # Recommend(user, n, ignore = the user's training items, candidates) once per user, from TPL threads. The first such call
+    # after the model changed computes the lists of ALL users in one device call (ignore rows = the training feedback) and
+    # keeps them; every later call with the same n and candidates whose ignore list is the user's training row is a lookup.
+    def _train_rows(self):
+        f = self.Feedback
+        if f is None or f.Count == 0:
+            return None
+        order = np.lexsort((f.Items, f.Users))
+        u, i = f.Users[order], f.Items[order]
+        keep = np.ones(u.size, bool)
+        keep[1:] = (u[1:] != u[:-1]) | (i[1:] != i[:-1])          # the user matrix is a set (PosOnlyFeedback.cs:35-83)
+        u, i = u[keep], i[keep]
+        ptr = np.zeros(self.MaxUserID + 2, np.int64)
+        np.add.at(ptr, u + 1, 1)
+        return np.cumsum(ptr), i.astype(np.int32)
+
+    def _cached(self, user_id, n, ignore_items, cand):
+        if n <= 0 or user_id < 0 or user_id > self.MaxUserID or self.Feedback is None:
+            return None
+        key = (int(n), cand.size, hash(cand.tobytes()))
+        c = self._cache
+        if c is None or c["key"] != key:
+            rows = self._train_rows()
+            if rows is None:
+                return None
+            c = dict(key=key, ptr=rows[0], idx=rows[1], lists=None)
+        ptr, idx = c["ptr"], c["idx"]
+        row = idx[ptr[user_id]:ptr[user_id + 1]]
+        given = np.unique(np.asarray(list(ignore_items) if ignore_items is not None else [], np.int32))
+        if given.size != row.size or not np.array_equal(given, row):
+            return None                       # some other ignore list: answered directly
+        if c["lists"] is None:
+            users = np.arange(self.MaxUserID + 1, dtype=np.int32)
+            c["lists"] = self._model.recommend(users, n, cand, (ptr, idx if idx.size else np.zeros(1, np.int32)), raw=True)
+            self._cache = c
+        oi, os_, oc = c["lists"]
+        k = int(oc[user_id])
+        return [(int(a), float(b)) for a, b in zip(oi[user_id, :k], os_[user_id, :k])]
 
     def Predict(self, user_id, item_id):
         # MF.cs:151-157
@@ -433,17 +505,23 @@ class WRMF(_Recommender):
     def Recommend(self, user_id, n=-1, ignore_items=None, candidate_items=None):
         if candidate_items is None:
             candidate_items = np.arange(0, max(self.MaxItemID - 1, 0), dtype=np.int32)   # Recommender.cs:57-58
+        cand = np.ascontiguousarray(candidate_items, np.int32)
+        hit = self._cached(user_id, n, ignore_items, cand)
+        if hit is not None:
+            return hit
         ign = None if ignore_items is None else [np.asarray(list(ignore_items), np.int32)]
-        items, scores = self._model.recommend([user_id], n, candidate_items, ign)[0]
+        items, scores = self._model.recommend([user_id], n, cand, ign)[0]
         return [(int(i), float(s)) for i, s in zip(items, scores)]
 
     def RetrainUser(self, user_id):
         """WRMF.cs:159-163."""
         self._model.retrain([user_id], by_item=False)
+        self._cache = None
 
     def RetrainItem(self, item_id):
         """WRMF.cs:166-170."""
         self._model.retrain([item_id], by_item=True)
+        self._cache = None
 
     def RecommendMany(self, users, n, ignore_lists=None, candidate_items=None):
         """The all-users loop of ItemRecommendation/Extensions.WritePredictions (:65-128) in one device call."""
@@ -466,6 +544,7 @@ class WRMF(_Recommender):
         self.NumFactors = U.shape[1]
         self._new_model(U.shape[0], V.shape[0], np.zeros(0, np.int32), np.zeros(0, np.int32))
         self._model.set_model(U, V)
+        self._cache = None
 
     def ToString(self):
         return "%s num_factors=%d regularization=%s alpha=%s num_iter=%d" % (

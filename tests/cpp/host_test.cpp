@@ -4,6 +4,11 @@
 //                                 hyper-parameter defaults, and that creating a context without a CUDA device THROWS (no CPU path)
 //   host_test gpu TRAIN TEST DIR  config 1 on the device: prints one "key value..." line per result for the Python test to
 //                                 hold against tests/golden/oracle_config1.json
+//   host_test multi N [RATINGS]   one process, N GPUs (the NumGpus property): BiasedMatrixFactorization on a synthetic set of
+//                                 the config 2 shape (71.5k x 10.7k, RATINGS ratings, default 10M, k = 64) trained with
+//                                 NumGpus = 1 and NumGpus = N from the same initial model; WRMF with NumGpus = N against
+//                                 NumGpus = 1; and 10^4 per-user Recommend() calls served from the cached all-users result
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -141,15 +146,101 @@ static int run_gpu(const char* train_file, const char* test_file, const char* di
     return 0;
 }
 
+// xorshift64*: test data only
+struct Xs {
+    uint64_t s;
+    explicit Xs(uint64_t seed) : s(seed * 0x9E3779B97F4A7C15ull + 1) {}
+    uint64_t next() { s ^= s >> 12; s ^= s << 25; s ^= s >> 27; return s * 0x2545F4914F6CDD1Dull; }
+    double uni() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+    double gauss() { double a = 0; for (int i = 0; i < 6; i++) a += uni(); return (a - 3.0) * 1.41421356; }   // ~N(0,1)
+};
+
+static int run_multi(uint32_t n_gpus, int64_t n_ratings)
+{
+    using clk = std::chrono::steady_clock;
+    Engine::device_init() = true;                        // both runs start from the same counter-based model
+    // planted model of the config 2 shape: skewed user activity and item popularity, half-star levels
+    const int32_t nu = 71500, ni = 10700;
+    Xs g(20260102);
+    std::vector<float> bu((size_t)nu), bi((size_t)ni), pu((size_t)nu * 4), qi((size_t)ni * 4);
+    for (auto& x : bu) x = 0.3f * (float)g.gauss();
+    for (auto& x : bi) x = 0.3f * (float)g.gauss();
+    for (auto& x : pu) x = 0.35f * (float)g.gauss();
+    for (auto& x : qi) x = 0.35f * (float)g.gauss();
+    Ratings train, test;
+    for (int64_t t = 0; t < n_ratings + n_ratings / 10; t++) {
+        const double a = g.uni(), b = g.uni();
+        const int32_t u = std::min<int32_t>(nu - 1, (int32_t)(nu * a * a)), i = std::min<int32_t>(ni - 1, (int32_t)(ni * b * b * b));
+        float v = 3.6f + bu[(size_t)u] + bi[(size_t)i] + 0.5f * (float)g.gauss();
+        for (int f = 0; f < 4; f++) v += pu[(size_t)u * 4 + f] * qi[(size_t)i * 4 + f];
+        v = std::min(5.0f, std::max(0.5f, std::round(v * 2.f) / 2.f));
+        (t < n_ratings ? train : test).Add(u, i, v);
+    }
+    train.MaxUserID = test.MaxUserID = nu - 1; train.MaxItemID = test.MaxItemID = ni - 1;
+    std::printf("multi data %lld %lld\n", (long long)train.Count(), (long long)test.Count());
+    for (uint32_t gpus : {1u, n_gpus}) {
+        Random::Seed(1);
+        BiasedMatrixFactorization rec;
+        rec.NumFactors = 64; rec.NumGpus = gpus; rec.ratings = &train;
+        const auto t0 = clk::now();
+        rec.InitModel();
+        const auto t1 = clk::now();
+        for (int it = 0; it < 6; it++) {
+            rec.Iterate();
+            std::printf("multi epoch %u %d %.6f\n", gpus, it, rec.Evaluate(test).RMSE);
+        }
+        const auto t2 = clk::now();
+        std::printf("multi time %u init_s %.3f epochs_s %.3f predict %.6f\n", gpus, std::chrono::duration<double>(t1 - t0).count(),
+                    std::chrono::duration<double>(t2 - t1).count(), rec.Predict(5, 7));
+    }
+    // WRMF: NumGpus = N against NumGpus = 1 (rows are solved on different GPUs, the arithmetic is the same)
+    Engine::device_init() = false;
+    PosOnlyFeedback fb;
+    const int32_t wu = 20000, wi = 5000;
+    for (int64_t t = 0; t < 1000000; t++) {
+        const double a = g.uni(), b = g.uni();
+        fb.Add(std::min<int32_t>(wu - 1, (int32_t)(wu * a * a)), std::min<int32_t>(wi - 1, (int32_t)(wi * b * b)));
+    }
+    fb.Add(wu - 1, wi - 1);
+    std::vector<std::vector<std::pair<int32_t, float>>> lists[2];
+    std::vector<int32_t> cand;
+    for (int32_t i = 0; i <= fb.MaxItemID; i++) cand.push_back(i);
+    std::vector<std::vector<int32_t>> train_rows((size_t)wu);
+    for (int64_t t = 0; t < fb.Count(); t++) train_rows[(size_t)fb.Users[(size_t)t]].push_back(fb.Items[(size_t)t]);
+    int x = 0;
+    for (uint32_t gpus : {1u, n_gpus}) {
+        Random::Seed(3);
+        WRMF w;
+        w.NumFactors = 32; w.NumIter = 2; w.NumGpus = gpus; w.Feedback = &fb;
+        w.Train();
+        const auto t0 = clk::now();
+        auto first = w.Recommend(0, 10, &train_rows[0], &cand);              // computes and caches the lists of all users
+        const auto t1 = clk::now();
+        lists[x].push_back(first);
+        for (int32_t u = 1; u < 10001; u++) lists[x].push_back(w.Recommend(u, 10, &train_rows[(size_t)u], &cand));
+        const auto t2 = clk::now();
+        std::printf("multi wrmf %u first_call_ms %.2f next_10000_calls_ms %.2f\n", gpus,
+                    std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+        x++;
+    }
+    size_t same = 0;
+    for (size_t u = 0; u < lists[0].size(); u++) same += lists[0][u] == lists[1][u] ? 1 : 0;
+    std::printf("multi wrmf_lists_identical %zu of %zu\n", same, lists[0].size());
+    std::printf("OK\n");
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     try {
         if (argc >= 2 && std::strcmp(argv[1], "cpu") == 0) return run_cpu();
+        if (argc >= 3 && std::strcmp(argv[1], "multi") == 0)
+            return run_multi((uint32_t)std::atoi(argv[2]), argc >= 4 ? std::atoll(argv[3]) : 10000000);
         if (argc >= 5 && std::strcmp(argv[1], "gpu") == 0) return run_gpu(argv[2], argv[3], argv[4]);
     } catch (const std::exception& e) {
         std::printf("EXCEPTION %s\n", e.what());
         return 2;
     }
-    std::printf("usage: host_test cpu | host_test gpu TRAIN TEST DIR\n");
+    std::printf("usage: host_test cpu | host_test gpu TRAIN TEST DIR | host_test multi N [RATINGS]\n");
     return 64;
 }

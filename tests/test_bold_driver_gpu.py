@@ -8,7 +8,7 @@ differences of exp() between the device and the host libm, so a free-running com
 the kernel (round 1: objectives 0.6 % apart after 8 epochs while every learn-rate decision agreed; scripts/diag_bold_driver.py
 prints the per-epoch divergence, kept in profiles/r2_bold_driver_diag.log). What is stable is checked instead: (a) the
 learn-rate decisions of the free run, epoch by epoch, and the objective for as long as the two models agree to 1e-4;
-(b) the overshooting epoch in chunks of 500 ratings, each chunk from the oracle's state ("teacher forcing": rows copied to the
+(b) the overshooting epoch in chunks of 100 ratings, each chunk from the oracle's state ("teacher forcing": rows copied to the
 device before each chunk), where the serial kernel and the objective must match the oracle's at any learn rate."""
 import numpy as np
 import pytest
@@ -72,7 +72,7 @@ def test_overshooting_epoch_in_chunks_from_the_oracle_state(learn_rate, loss):
     """The overshooting regime checked where it is checkable. profiles/r2_bold_driver_diag.log: at LearnRate 0.6 the factors
     reach |x| ~ 10 and ONE free-running epoch (18k sequential updates) already ends 14 apart from the oracle, while at 0.01
     eight epochs end 1e-7 apart -- sensitivity to the last bit of exp(), not a kernel difference. So the epoch is walked in
-    chunks of 500 ratings, every chunk starting from the oracle's state on both sides (rows copied to the device): inside a
+    chunks of 100 ratings, every chunk starting from the oracle's state on both sides (rows copied to the device): inside a
     chunk the per-rating arithmetic has to agree, and the objective is compared on identical models."""
     from mymedialite_b200 import engine
     ctx = engine.Context(0)
@@ -82,8 +82,8 @@ def test_overshooting_epoch_in_chunks_from_the_oracle_state(learn_rate, loss):
         ri = rng.shuffle(np.arange(om.users.size))
         worst = 0.0
         for epoch in range(2):
-            for c0 in range(0, ri.size, 500):
-                chunk = ri[c0:c0 + 500]
+            for c0 in range(0, ri.size, 100):
+                chunk = ri[c0:c0 + 100]
                 gm.set_rows(np.arange(nu), om.user_factors, om.user_bias)
                 gm.set_rows(np.arange(ni), om.item_factors, om.item_bias, by_item=True)
                 om.iterate_indices(chunk)
