@@ -486,6 +486,7 @@ struct SgdArgs {
     const int32_t* item_ptr;        // offset to B: [G + 1] internal item row range per item group
     const int32_t* hot_cnt;         // offset to B: [G] hot items per item group (their rows come first)
     const float* regw_u; const float* regw_i;   // frequency regularisation weights or NULL
+    unsigned long long* wait_stats; // diagnostic (MMLB200_SGD_WAITSTATS): [0] cycles CTAs spent in hand-over waits, [1] CTA cycles
     uint32_t* flags;                // persistent kernel: progress counter per CTA
     const int32_t* seq;             // persistent kernel: sub-epoch sequence [G] (device)
     uint32_t epoch_base;
@@ -1126,6 +1127,8 @@ __global__ void __launch_bounds__(512) sgd_epoch2_kernel(const SgdArgs a)
 {
     const int cpg = a.cpg;
     const int j = blockIdx.x / cpg, sub = blockIdx.x % cpg;
+    const long long k0 = a.wait_stats ? clock64() : 0;
+    long long waited = 0;
     AsyncHead head = async_head<L>(a, j, sub, a.seq[0]);
     for (int t = 0; t < a.G; t++) {
         const int slot = a.seq[t];
@@ -1135,20 +1138,28 @@ __global__ void __launch_bounds__(512) sgd_epoch2_kernel(const SgdArgs a)
             int b = slot + j; if (b >= a.G) b -= a.G;
             int jp = b - a.seq[t - 1]; if (jp < 0) jp += a.G;
             const uint32_t want = a.epoch_base + (uint32_t)t;
+            const long long w0 = a.wait_stats ? clock64() : 0;
             for (int x = (int)threadIdx.x; x < (cpg > 1 ? 2 * cpg : cpg); x += (int)blockDim.x) {
                 const uint32_t* f = a.flags + (x < cpg ? jp * cpg + x : j * cpg + (x - cpg));
                 while ((int32_t)(ld_relaxed_u32(f) - want) < 0) __nanosleep(20);
                 __threadfence();   // acquire
             }
             __syncthreads();
+            if (a.wait_stats) waited += clock64() - w0;
         }
         sgd_block_async2<L, KPL, BIASED>(a, head);
         head = next;
         if (a.G > 1) {
+            const long long w0 = a.wait_stats ? clock64() : 0;
             __threadfence();
-            __syncthreads();
+            __syncthreads();     // the CTA's slowest warp: also idle time of the others
+            if (a.wait_stats && threadIdx.x == 0) waited += clock64() - w0;
             if (threadIdx.x == 0) st_release_u32(a.flags + blockIdx.x, a.epoch_base + (uint32_t)t + 1u);
         }
+    }
+    if (a.wait_stats && threadIdx.x == 0) {
+        atomicAdd(a.wait_stats, (unsigned long long)waited);
+        atomicAdd(a.wait_stats + 1, (unsigned long long)(clock64() - k0));
     }
 }
 
@@ -1507,6 +1518,7 @@ static SgdArgs make_args(Sgd& m, int32_t B)
     a.regw_u = m.p.frequency_regularization ? m.regw_u.p : nullptr;
     a.regw_i = m.p.frequency_regularization ? m.regw_i.p : nullptr;
     a.flags = m.flags.p; a.seq = nullptr; a.epoch_base = m.epoch_base;
+    a.wait_stats = m.wait_stats.p;
     a.G = m.G; a.C = m.hot_copies; a.n_workers = m.n_workers; a.cpg = std::max(m.cpg, 1);
     a.hot_scale = m.p.hot_merge_average ? 1.f / (float)m.hot_copies : 1.f;
     a.lr = m.lr; a.gb = m.global_bias; a.minr = m.min_rating; a.range = m.range;
@@ -1810,6 +1822,14 @@ static int32_t run_dsgd_epoch(Sgd& m, const int32_t* h_seq)
         for (auto& e : tev) cudaEventDestroy(e);
     }
     if (m.R > 1) m.items_dirty = true;
+    if (m.wait_stats.p) {
+        unsigned long long h[2] = {0, 0};
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h, m.wait_stats.p, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaMemset(m.wait_stats.p, 0, sizeof(h));
+        fprintf(stderr, "[mmlb200 sgd rank %d] epoch kernel: %.1f %% of the CTA time at block hand-overs (flag waits + CTA barriers), G=%d x %d\n",
+                m.rank, h[1] ? 100.0 * (double)h[0] / (double)h[1] : 0.0, m.G, m.cpg);
+    }
     return MML_OK;
 }
 
@@ -2035,6 +2055,13 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
             }
             if ((st = m.flags.alloc((size_t)m.G * m.cpg))) break;
             cudaMemsetAsync(m.flags.p, 0, m.flags.bytes(), s);
+            {   // diagnostic: share of the epoch kernel's CTA time spent waiting at block hand-overs (thread 0 of every CTA)
+                const char* ev = getenv("MMLB200_SGD_WAITSTATS");
+                if (ev && *ev && *ev != '0') {
+                    if ((st = m.wait_stats.alloc(2))) break;
+                    cudaMemsetAsync(m.wait_stats.p, 0, m.wait_stats.bytes(), s);
+                }
+            }
             m.epoch_base = 0;
         }
         if (cudaEventCreate(&m.ev0) != cudaSuccess || cudaEventCreate(&m.ev1) != cudaSuccess) {

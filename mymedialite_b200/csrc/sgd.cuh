@@ -56,6 +56,7 @@ struct Sgd {
     DevBuf<float> ent_v;
     size_t stage_bytes = 0;            // shared memory for the largest item group; 0 = not staged
     DevBuf<uint32_t> flags;            // persistent kernel: per-CTA progress counters
+    DevBuf<unsigned long long> wait_stats;   // MMLB200_SGD_WAITSTATS diagnostic: {hand-over wait cycles, CTA cycles}
     uint32_t epoch_base = 0;
 
     // grow-only scratch of Evaluate()/Predict() (no cudaMalloc/cudaFree in the per-epoch find-iter loop)

@@ -51,13 +51,16 @@ def test_cpp_host_layer_without_a_device(host_test):
 @pytest.mark.gpu
 def test_cpp_host_one_process_two_gpus(host_test):
     """NumGpus = 2 from ONE process (mml_ctx_create(n_gpus = 2): ncclCommInitAll + one host thread per GPU inside the library):
-    BiasedMatrixFactorization on a 2M-rating set of the config 2 shape tracks the NumGpus = 1 run from the same initial model
-    (test RMSE within 0.5 % per epoch); WRMF lists are identical; 10^4 per-user Recommend() calls after the first are lookups."""
+    BiasedMatrixFactorization on a 10M-rating set of the config 2 shape (71.5k x 10.7k, k = 64) tracks the NumGpus = 1 run from
+    the same initial model (per-epoch test RMSE within 1 %: two different parallel schedules, neither is the reference -- the
+    gate against the reference's own run is tests/test_rmse_gate_gpu.py); WRMF lists are identical; 10^4 per-user Recommend()
+    calls after the first are lookups."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     exe, env = host_test
-    r = subprocess.run([exe, "multi", "2", "2000000"], capture_output=True, text=True, env=env, timeout=600)
+    r = subprocess.run([exe, "multi", "2", "10000000"], capture_output=True, text=True, env=env, timeout=600)
+    print(r.stdout)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
     rmse = {}
     for line in r.stdout.splitlines():
@@ -69,7 +72,7 @@ def test_cpp_host_one_process_two_gpus(host_test):
         if p[:2] == ["multi", "wrmf_lists_identical"]:
             assert p[2] == p[4], line
     for e in range(6):
-        assert abs(rmse[(2, e)] - rmse[(1, e)]) / rmse[(1, e)] < 0.005, (e, rmse)
+        assert abs(rmse[(2, e)] - rmse[(1, e)]) / rmse[(1, e)] < 0.01, (e, rmse)
     assert rmse[(1, 5)] < rmse[(1, 0)]
 
 
