@@ -58,6 +58,24 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// ---- a stream-ordered temporary (cudaMallocAsync / cudaFreeAsync on `s`): scratch of the primitives, freed in stream order,
+//      so neither the allocation nor the release makes the host wait for the device ---------------
+template <typename T>
+struct StreamBuf {
+    T* p = nullptr;
+    cudaStream_t s = nullptr;
+    StreamBuf() = default;
+    StreamBuf(const StreamBuf&) = delete;
+    StreamBuf& operator=(const StreamBuf&) = delete;
+    ~StreamBuf() { if (p) cudaFreeAsync(p, s); }
+    int32_t alloc(size_t count, cudaStream_t stream) {
+        s = stream;
+        if (count == 0) count = 1;
+        MML_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), s));
+        return MML_OK;
+    }
+};
+
 // ---- a page-locked host buffer (staging for asynchronous copies), grow-only ---------------------
 template <typename T>
 struct PinBuf {

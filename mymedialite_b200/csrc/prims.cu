@@ -207,15 +207,14 @@ int32_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, cudaStr
         return MML_OK;
     }
     int64_t tiles = ceil_div(n + 1, SCAN_TILE);   // +1 so that position n (the total) has an owner tile
-    DevBuf<uint32_t> sums, offsets;
-    MML_TRY(sums.alloc((size_t)tiles));
-    MML_TRY(offsets.alloc((size_t)tiles + 1));
+    StreamBuf<uint32_t> sums, offsets;          // stream-ordered scratch: no host synchronisation in here
+    MML_TRY(sums.alloc((size_t)tiles, s));
+    MML_TRY(offsets.alloc((size_t)tiles + 1, s));
     scan_tile_sums_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(in, n, sums.p);
     MML_CUDA(cudaGetLastError());
     MML_TRY(exclusive_scan_u32(sums.p, offsets.p, tiles, s));
     scan_tile_apply_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(in, n, offsets.p, out);
     MML_CUDA(cudaGetLastError());
-    MML_CUDA(cudaStreamSynchronize(s));   // sums/offsets are freed on return
     return MML_OK;
 }
 
@@ -307,9 +306,9 @@ int32_t radix_sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_tmp, uin
     int passes = (key_bits + 7) / 8;
     if (passes < 1) passes = 1;
     const int nblk = (int)ceil_div(n, RS_TILE);
-    DevBuf<uint32_t> hist, hist_scanned;
-    MML_TRY(hist.alloc((size_t)256 * nblk));
-    MML_TRY(hist_scanned.alloc((size_t)256 * nblk + 1));
+    StreamBuf<uint32_t> hist, hist_scanned;
+    MML_TRY(hist.alloc((size_t)256 * nblk, s));
+    MML_TRY(hist_scanned.alloc((size_t)256 * nblk + 1, s));
     uint32_t *kin = keys, *vin = vals, *kout = keys_tmp, *vout = vals_tmp;
     for (int p = 0; p < passes; p++) {
         const int shift = 8 * p;
@@ -326,7 +325,6 @@ int32_t radix_sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_tmp, uin
         MML_CUDA(cudaMemcpyAsync(keys, kin, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
         MML_CUDA(cudaMemcpyAsync(vals, vin, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
     }
-    MML_CUDA(cudaStreamSynchronize(s));
     return MML_OK;
 }
 

@@ -135,6 +135,13 @@ int32_t ctx_create_on_device(int dev, mml_ctx** out)
     cudaDeviceProp prop;
     MML_CUDA(cudaGetDeviceProperties(&prop, dev));
     c->c.sm_count = prop.multiProcessorCount;
+    {   // the primitives' scratch is stream-ordered (StreamBuf): keep freed blocks in the pool instead of returning them
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     MML_CUDA(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking));
     MML_CUDA(cudaStreamCreateWithFlags(&c->c.copy_stream, cudaStreamNonBlocking));
     MML_CUDA(cudaStreamCreateWithFlags(&c->c.out_stream, cudaStreamNonBlocking));

@@ -924,8 +924,8 @@ __device__ __forceinline__ void sgd_block_async(const SgdArgs& a, const int j, c
 //   * factor arithmetic on packed pairs (fma.rn.f32x2 / mul.f32x2 of sm_100: one instruction per two factors);
 //   * a worker past the end of its slice keeps running with zero coefficients (p <- 1 p + 0 q, no stores) instead of
 //     computing into copies that are committed under a predicate;
-//   * no forwarding of a just-updated item row to the next rating (the next rating of a user run never has the same item,
-//     and across runs the row comes back from the L2 like everybody else's steps);
+//   * a just-updated item row is not forwarded through registers to a next rating on the same item (it only happens at run
+//     boundaries); that rating's row is simply loaded after the step was added instead of one rating ahead;
 // Measured on config 4 (profiles/r2_sgd_variants.log): 16.17 ms (first form) -> 15.78 ms (this form, 16 lanes x 8 floats) ->
 // 14.69 ms (8 lanes x 16 floats: four ratings per warp instruction share the scalar part); cutting the registers to 64 for two
 // CTAs per SM (no next-user row held ahead) gave 14.79 ms and was dropped. At k = 64 the 8 x 8 shape stays (4 x 16 is slower).
@@ -1005,9 +1005,14 @@ __device__ __forceinline__ void sgd_block_async2(const SgdArgs& a, const AsyncHe
 #pragma unroll
         for (int f = 0; f < KPL / 2; f++) q.r[f] = qn.r[f];
         const float bi0 = bin;
+        // the next rating hits the same item row (a run boundary: consecutive users sharing an item): its row is read after
+        // this rating's step has been added (same thread, same address: the red and the load stay in order)
+        const bool same_item = active && e + 1 < e1 && i1 == i;
         if (e + 1 < e1) {   // next entry: its item row, and its user row if a new run starts
-            row2_load_cg<L, KPL>(qn, Qg + (size_t)i1 * KP, sl);
-            if (BIASED) bin = ld_cg_f(Bg + i1);
+            if (!same_item) {
+                row2_load_cg<L, KPL>(qn, Qg + (size_t)i1 * KP, sl);
+                if (BIASED) bin = ld_cg_f(Bg + i1);
+            }
             if (u1 != cur_u) {
                 row2_load<L, KPL>(pn, a.P + (size_t)u1 * KP, sl);
                 if (BIASED) bun = a.bu[u1];
@@ -1052,6 +1057,10 @@ __device__ __forceinline__ void sgd_block_async2(const SgdArgs& a, const AsyncHe
             for (int vv = 0; vv < KPL / 4; vv++)
                 red_add_f4(qrow + 4 * (vv * L + sl), dq.r[2 * vv].x, dq.r[2 * vv].y, dq.r[2 * vv + 1].x, dq.r[2 * vv + 1].y);
             if (BIASED && sl == 0) red_add_f(Bg + i, dbi);
+            if (same_item) {
+                row2_load_cg<L, KPL>(qn, Qg + (size_t)i * KP, sl);
+                if (BIASED) bin = ld_cg_f(Bg + i);
+            }
         }
     }
     if (cur_u >= 0) {

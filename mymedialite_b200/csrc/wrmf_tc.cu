@@ -565,6 +565,130 @@ __global__ void __launch_bounds__(SV_THREADS, SvCfg<T>::ctas) wrmf_solve_kernel(
     for (int f = tid; f < k; f += SV_THREADS) a.W[(size_t)u * k + f] = (float)wv[f];
 }
 
+// ---- conjugate-gradient solve, one CTA of 128 threads per row (the default solver of the tensor path) ----------------------
+// The Cholesky kernel above spends its time in dependent panel steps behind CTA barriers (ncu, round 1: barrier stall 10.7
+// per issue, 86 us per row): 165k rows of config 3 cost 32 ms of a 52 ms epoch. The systems are SPD and well conditioned
+// (HH + lambda I dominates), so an iterative solve does the same work as dense matrix-vector products with no dependent
+// chain longer than a dot product:
+//   * thread t keeps row t of A~ = fl32(HH + alpha G~ + lambda I) in 128 registers (read as column t of the symmetric
+//     inputs: coalesced), the search direction lives in shared memory and is read as broadcast 128-bit loads;
+//   * Jacobi-preconditioned CG in single precision, started from the row's current factors (ALS moves a row less and less
+//     from epoch to epoch), to a relative residual of 1e-6;
+//   * then iterative refinement in double against the stored A~ (r = b - A~ x with double accumulation, correction by a
+//     short CG) until |r| <= 2e-7 |b|: the result is the double-precision solution of the system with the fp32-rounded
+//     matrix, i.e. off the exact one by cond(A) x (6e-8 + the tensor cores' Gram rounding), far inside the 1e-4 gate;
+//   * a row that does not get there in CG_MAX_IT iterations raises *fail and the half-sweep is redone by the Cholesky
+//     kernel with its refinement against the exact operator (which also serves MML_WRMF_TENSOR_F64).
+constexpr int CG_THREADS = 128;
+constexpr int CG_MAX_IT = 400;
+
+// sums v0 and v1 over the CTA; `red` is one of three rotating [2][4] buffers (a barrier separates write and read, two more
+// barriers pass before the buffer is written again)
+__device__ __forceinline__ void cg_sum2(float& v0, float& v1, float (*red)[4], int lane, int warp)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
+    if (lane == 0) { red[0][warp] = v0; red[1][warp] = v1; }
+    __syncthreads();
+    v0 = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+    v1 = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+}
+
+__global__ void __launch_bounds__(CG_THREADS, 2) wrmf_cg_kernel(const SolveArgs a)
+{
+    __shared__ __align__(16) float ps[2][WS_KP];      // search direction, double buffered
+    __shared__ double xd_s[WS_KP];                    // solution (double) for the refinement residual
+    __shared__ float red[3][2][4];
+    __shared__ double redd[2][4];
+    const int k = a.k;
+    const int q = a.q_lo + blockIdx.x;
+    if (q >= a.q_hi) return;
+    const int u = a.order[q];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (a.row_ptr[u] == a.row_ptr[u + 1]) {           // HCp = 0 => w = 0 exactly
+        if (t < k) a.W[(size_t)u * k + t] = 0.f;
+        return;
+    }
+    const float* G = a.G + (size_t)blockIdx.x * WS_KP * WS_KP;
+    const bool row_ok = t < k;
+    // row t of A~ (= column t: coalesced), padding rows / columns: identity
+    float A[WS_KP];
+    float diag = 1.f;
+#pragma unroll
+    for (int j = 0; j < WS_KP; j++) {
+        double v = 0.0;
+        if (row_ok && j < k) v = a.HH[(size_t)j * k + t] + a.alpha * (double)G[(size_t)j * WS_KP + t] + (j == t ? a.reg : 0.0);
+        else if (j == t) v = 1.0;
+        A[j] = (float)v;
+        if (j == t) diag = (float)v;
+    }
+    const float dinv = 1.f / diag;
+    const double bd = row_ok ? a.bsum[(size_t)blockIdx.x * WS_KP + t] * (1.0 + a.alpha) : 0.0;
+    double xd = row_ok ? (double)a.W[(size_t)u * k + t] : 0.0;     // warm start: the row as the last epoch left it
+    // |b|_inf for the stopping tests
+    double bmax = fabs(bd);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bmax = fmax(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+    if (lane == 0) redd[0][warp] = bmax;
+    __syncthreads();
+    bmax = fmax(fmax(redd[0][0], redd[0][1]), fmax(redd[0][2], redd[0][3]));
+    int total_it = 0;
+    bool ok = false;
+    for (int round = 0; round < 6; round++) {
+        // r = b - A~ x in double
+        xd_s[t] = xd;
+        __syncthreads();
+        double rd = bd, rd2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < WS_KP; j += 2) { rd -= (double)A[j] * xd_s[j]; rd2 -= (double)A[j + 1] * xd_s[j + 1]; }   // fully unrolled: A stays in registers
+        rd += rd2;
+        double rmax = fabs(rd);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        if (lane == 0) redd[1][warp] = rmax;
+        __syncthreads();
+        rmax = fmax(fmax(redd[1][0], redd[1][1]), fmax(redd[1][2], redd[1][3]));
+        if (!(rmax > 2e-7 * bmax)) { ok = true; break; }              // uniform across the CTA
+        if (total_it >= CG_MAX_IT) break;
+        // correction d: A~ d = r by preconditioned CG in single precision (r scaled to O(1))
+        const float scale = (float)(1.0 / rmax);
+        float r = (float)rd * scale, x = 0.f;
+        float z = r * dinv, pv = z;
+        float rz = r * z, rr = r * r;
+        cg_sum2(rz, rr, red[0], lane, warp);
+        const float rr0 = rr;
+        int buf = 0;
+        for (int it = 0; it < CG_MAX_IT && total_it < CG_MAX_IT; it++, total_it++) {
+            ps[buf][t] = pv;
+            __syncthreads();
+            const float4* p4 = reinterpret_cast<const float4*>(ps[buf]);
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < WS_KP / 4; j++) {
+                const float4 pj = p4[j];
+                s0 = fmaf(A[4 * j], pj.x, s0); s1 = fmaf(A[4 * j + 1], pj.y, s1);
+                s2 = fmaf(A[4 * j + 2], pj.z, s2); s3 = fmaf(A[4 * j + 3], pj.w, s3);
+            }
+            const float Ap = (s0 + s1) + (s2 + s3);
+            float pAp = pv * Ap, dummy = 0.f;
+            cg_sum2(pAp, dummy, red[1], lane, warp);
+            const float al = rz / pAp;
+            x = fmaf(al, pv, x);
+            r = fmaf(-al, Ap, r);
+            z = r * dinv;
+            float rz_new = r * z, rr_new = r * r;
+            cg_sum2(rz_new, rr_new, red[2], lane, warp);
+            if (!(rr_new > 1e-12f * rr0)) { total_it++; break; }      // |r| <= 1e-6 |r0|
+            pv = fmaf(rz_new / rz, pv, z);
+            rz = rz_new;
+            buf ^= 1;
+        }
+        xd += (double)x * rmax;
+    }
+    if (!ok && t == 0) atomicAdd(a.fail, 1u);
+    if (row_ok) a.W[(size_t)u * k + t] = (float)xd;
+}
+
 // ---- host ---------------------------------------------------------------------------------------------------------
 bool wrmf_tc_eligible(int32_t k) { return k >= 4 && k <= 128 && (k % 4) == 0; }
 
@@ -578,7 +702,7 @@ void wrmf_tc_work_destroy(WrmfTcWork* w) { delete w; }
 // One half-sweep's per-row systems: W[u] <- solve for every row of `order`. HH (fp64, k x k) is on the device.
 static int32_t half_sweep_impl(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_ptr, const int32_t* cols, const int32_t* order, int32_t n_rows,
                                float* W, const float* H, int32_t k, const double* HH, double alpha, double reg, int64_t* launches,
-                               float* debug_G_row0, const bool f64, uint32_t* not_converged)
+                               float* debug_G_row0, const int solver, uint32_t* not_converged)
 {
     cudaStream_t s = ctx->stream;
     MML_CHECK(work != nullptr, MML_ERR_STATE, "wrmf: no tensor-path workspace");
@@ -594,9 +718,11 @@ static int32_t half_sweep_impl(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_p
     const size_t smem_syrk = (size_t)WS_STAGES * 2 * WS_TILE + 1024;
     MML_CUDA(cudaFuncSetAttribute((const void*)wrmf_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_syrk));
     const int np = (k + SV_NB - 1) / SV_NB;
-    const size_t smem_solve = f64 ? sv_smem_bytes<double>(np) : sv_smem_bytes<float>(np);
-    void (*solve_fn)(const SolveArgs) = f64 ? wrmf_solve_kernel<double> : wrmf_solve_kernel<float>;
-    MML_CUDA(cudaFuncSetAttribute((const void*)solve_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+    // solver: 0 = conjugate gradients (default), 1 = Cholesky with the single-precision factor, 2 = with the double one
+    const bool f64 = solver == 2;
+    const size_t smem_solve = solver == 0 ? 0 : (f64 ? sv_smem_bytes<double>(np) : sv_smem_bytes<float>(np));
+    void (*solve_fn)(const SolveArgs) = solver == 0 ? wrmf_cg_kernel : (f64 ? wrmf_solve_kernel<double> : wrmf_solve_kernel<float>);
+    if (solver != 0) MML_CUDA(cudaFuncSetAttribute((const void*)solve_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
     for (int32_t q_lo = 0; q_lo < n_rows; q_lo += B) {
         const int32_t q_hi = std::min(n_rows, q_lo + B), nb = q_hi - q_lo;
         MML_CUDA(cudaMemsetAsync(w.bsum.p, 0, sizeof(double) * (size_t)nb * WS_KP, s));
@@ -610,7 +736,7 @@ static int32_t half_sweep_impl(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_p
         SolveArgs va{};
         va.row_ptr = row_ptr; va.cols = cols; va.order = order; va.q_lo = q_lo; va.q_hi = q_hi; va.G = w.G.p; va.bsum = w.bsum.p; va.HH = HH;
         va.H = H; va.alpha = alpha; va.reg = reg; va.k = k; va.W = W; va.fail = w.err.p + 1;
-        solve_fn<<<nb, SV_THREADS, smem_solve, s>>>(va);
+        solve_fn<<<nb, solver == 0 ? CG_THREADS : SV_THREADS, smem_solve, s>>>(va);
         MML_CUDA(cudaGetLastError());
         if (launches) *launches += 2;
     }
@@ -626,18 +752,22 @@ int32_t wrmf_tc_half_sweep(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_ptr, 
                            float* W, const float* H, int32_t k, const double* HH, double alpha, double reg, int64_t* launches,
                            float* debug_G_row0, bool factor_f64)
 {
-    // factor_f64 (mode MML_WRMF_TENSOR_F64) or MMLB200_WRMF_FACTOR=fp64 forces the double-precision Cholesky factor (the
-    // default single-precision one is a preconditioner of the same double-precision refinement)
-    static const bool env64 = [] { const char* e = getenv("MMLB200_WRMF_FACTOR"); return e && strcmp(e, "fp64") == 0; }();
-    const bool force64 = env64 || factor_f64;
+    // Solver ladder: conjugate gradients (default) -> Cholesky with the single-precision factor -> with the double one, each
+    // tried only if the previous left a row unconverged (W is output only -- the CG kernel reads it as a starting guess, which
+    // affects the iteration count, not the result -- and H is untouched, so a repeat is safe). factor_f64 (mode
+    // MML_WRMF_TENSOR_F64) or MMLB200_WRMF_SOLVER = chol | chol64 start further down the ladder (parity tests, A/B runs).
+    static const int env_first = [] {
+        const char* e = getenv("MMLB200_WRMF_SOLVER");
+        if (e && strcmp(e, "chol64") == 0) return 2;
+        if (e && strcmp(e, "chol") == 0) return 1;
+        const char* f = getenv("MMLB200_WRMF_FACTOR");
+        return (f && strcmp(f, "fp64") == 0) ? 2 : 0;
+    }();
     uint32_t bad = 0;
-    if (!force64) {
-        MML_TRY(half_sweep_impl(ctx, work, row_ptr, cols, order, n_rows, W, H, k, HH, alpha, reg, launches, debug_G_row0, false, &bad));
+    for (int solver = factor_f64 ? 2 : env_first; solver <= 2; solver++) {
+        MML_TRY(half_sweep_impl(ctx, work, row_ptr, cols, order, n_rows, W, H, k, HH, alpha, reg, launches, debug_G_row0, solver, &bad));
         if (bad == 0) return MML_OK;
-        // some row's refinement did not converge with the single-precision factor (cond(A) beyond ~1e6): redo the
-        // half-sweep with the double-precision factor (W is output only and H is untouched, so a repeat is safe)
     }
-    MML_TRY(half_sweep_impl(ctx, work, row_ptr, cols, order, n_rows, W, H, k, HH, alpha, reg, launches, debug_G_row0, true, &bad));
     MML_CHECK(bad == 0, MML_ERR_CUDA, "wrmf: %u rows did not converge (system too ill-conditioned for the 1e-9 residual bound)", bad);
     return MML_OK;
 }

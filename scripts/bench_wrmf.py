@@ -31,7 +31,7 @@ def main():
         tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = mdist.create_context(local)
     t0 = time.time()
-    u, i = synthetic.implicit(args.users, args.items, args.events, 20260103)
+    u, i = synthetic.implicit_cuda(args.users, args.items, args.events, 20260103, device="cuda:%d" % local)
     gen_s = time.time() - t0
     t0 = time.time()
     f = engine.DeviceFeedback(ctx, u, i, max_user=args.users - 1, max_item=args.items - 1)

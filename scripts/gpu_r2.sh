@@ -23,8 +23,12 @@ for step in "$@"; do
                 timeout 600 ncu --set full --clock-control none --import-source on -k regex:sgd_epoch -s 3 -c 1 -f -o gpurun_out/${tag}_sgd_prof $CMD ) > $log 2>&1 ;;
     hostmulti) ( LD_LIBRARY_PATH=/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/cuda_runtime/lib:/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/lib:$LD_LIBRARY_PATH timeout 300 tests/cpp/build/host_test multi 2 10000000 ) > $log 2>&1 ;;
     topntrace) ( MMLB200_TRACE=1 timeout 300 python scripts/bench_topn.py --reps 2 --exact-users 256 ) > $log 2>&1 ;;
-    waitstats) ( for shape in 37x4 18x8 9x16 4x37; do MMLB200_SGD_WAITSTATS=1 timeout 200 python scripts/sweep_groups.py --workload netflix --epochs 3 --shapes $shape 2>&1 | grep -v "^{" | tail -n 1; done
-                 for shape in 37x4 18x8 9x16 4x37 2x74; do MMLB200_SGD_WAITSTATS=1 timeout 200 python scripts/sweep_groups.py --workload nf_sub8 --epochs 3 --shapes $shape 2>&1 | grep -v "^{" | tail -n 1; done ) > $log 2>&1 ;;
+    waitstats) ( for shape in 37x4 18x8 9x16 4x37; do MMLB200_SGD_WAITSTATS=1 timeout 200 python scripts/sweep_groups.py --workload netflix --epochs 3 --shapes $shape 2>&1 | cut -c1-160 | tail -n 2; done
+                 for shape in 37x4 18x8 9x16 4x37 2x74; do MMLB200_SGD_WAITSTATS=1 timeout 200 python scripts/sweep_groups.py --workload nf_sub8 --epochs 3 --shapes $shape 2>&1 | cut -c1-160 | tail -n 2; done ) > $log 2>&1 ;;
+    wrmfdiag) ( timeout 600 python scripts/diag_wrmf_solvers.py --epochs 4 ) > $log 2>&1 ;;
+    wrmfncu)  ( CMD="python scripts/bench_wrmf.py --epochs 2"
+                timeout 300 $CMD > gpurun_out/${tag}_wrmf_plain.log 2>&1 &&
+                timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'wrmf_|gram_' --csv --log-file gpurun_out/${tag}_wrmf_launches.csv $CMD ) > $log 2>&1 ;;
     hosttest) ( LD_LIBRARY_PATH=/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/cuda_runtime/lib:$LD_LIBRARY_PATH timeout 60 tests/cpp/build/host_test gpu tests/golden/example.train tests/golden/example.test gpurun_out ) > $log 2>&1 ;;
     *)        ( eval "timeout 900 $step" ) > $log 2>&1 ;;
   esac
