@@ -279,8 +279,8 @@ namespace MyMediaLite.RatingPrediction
 			p.bold_driver = BoldDriver ? 1 : 0; p.max_threads = MaxThreads;
 			// MaxThreads > 1 selects the reference's DSGD block schedule (:178-184); on the GPU the worker groups are CTAs, and the
 			// parallel kernel is also what MaxThreads = 1 runs unless the engine order says Reference (base.Params, Mml.Order).
-			// NaiveParallelization (:136-141, :201-204): no block exclusivity -- the whole GPU is one worker group
-			if (p.schedule == Mml.SCHEDULE_DSGD && NaiveParallelization) { p.num_groups = 1; p.ctas_per_group = 1 << 16; }
+			// NaiveParallelization (:136-141, :201-204): the list schedule of MultiCore.PartitionIndices (one GPU only)
+			if (p.schedule == Mml.SCHEDULE_DSGD && NaiveParallelization && NumGpus <= 1) p.schedule = Mml.SCHEDULE_NAIVE;
 			return p;
 		}
 

@@ -41,7 +41,7 @@ namespace MyMediaLite.Native
 		const string LIB = "mmlb200";   // libmmlb200.so on the library path
 
 		public const int LOSS_RMSE = 0, LOSS_MAE = 1, LOSS_LOGISTIC = 2;
-		public const int SCHEDULE_SERIAL = 0, SCHEDULE_DSGD = 1;
+		public const int SCHEDULE_SERIAL = 0, SCHEDULE_DSGD = 1, SCHEDULE_NAIVE = 2;
 		public const int TOPN_AUTO = 0, TOPN_EXACT = 1, TOPN_TENSOR = 2;
 
 		[DllImport(LIB)] static extern IntPtr mml_last_error();
@@ -88,6 +88,7 @@ namespace MyMediaLite.Native
 		[DllImport(LIB)] public static extern int mml_ratings_stats(IntPtr ratings, out float average, out float min_rating, out float max_rating);
 		[DllImport(LIB)] public static extern int mml_shuffle_apply(IntPtr ctx, [In, Out] int[] perm, int[] H, long n);
 		[DllImport(LIB)] public static extern int mml_partition_blocks(IntPtr ratings, int[] user_perm, int[] item_perm, int g, [Out] long[] block_ptr, [Out] int[] idx);
+		[DllImport(LIB)] public static extern int mml_partition_indices(IntPtr ctx, int[] random_index, long n, int num_groups, [Out] long[] list_ptr, [Out] int[] idx);
 
 		// MatrixFactorization / BiasedMatrixFactorization
 		[DllImport(LIB)] public static extern void mml_mf_params_default(out MmlMfParams p);

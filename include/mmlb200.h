@@ -119,11 +119,21 @@ int32_t mml_shuffle_apply(mml_ctx* ctx, int32_t* perm, const int32_t* H, int64_t
 int32_t mml_partition_blocks(mml_ratings* r, const int32_t* user_perm, const int32_t* item_perm, int32_t g,
                              int64_t* block_ptr, int32_t* idx);
 
+/* MultiCore.PartitionIndices (MultiCore.cs:79-92): random_index (= DataSet.RandomIndex, n entries) dealt round-robin into
+ * g = min(num_groups, n) lists: list_ptr[num_groups + 1] (lists beyond g are empty), idx[n] = list 0, list 1, ...;
+ * list l holds random_index[l], random_index[l + g], random_index[l + 2 g], ... in that order. */
+int32_t mml_partition_indices(mml_ctx* ctx, const int32_t* random_index, int64_t n, int32_t num_groups,
+                              int64_t* list_ptr, int32_t* idx);
+
 /* ---- MatrixFactorization / BiasedMatrixFactorization ------------------------------------------ */
 enum { MML_LOSS_RMSE = 0, MML_LOSS_MAE = 1, MML_LOSS_LOGISTIC = 2 };
 enum {
     MML_SCHEDULE_SERIAL = 0,   /* MaxThreads = 1: one pass over RandomIndex in the reference's order */
-    MML_SCHEDULE_DSGD   = 1    /* stratified DSGD block schedule (BiasedMatrixFactorization.cs:205-215) */
+    MML_SCHEDULE_DSGD   = 1,   /* stratified DSGD block schedule (BiasedMatrixFactorization.cs:205-215) */
+    MML_SCHEDULE_NAIVE  = 2    /* NaiveParallelization (BiasedMatrixFactorization.cs:136-141, :201-204): RandomIndex dealt round-robin
+                                  into lists (MultiCore.PartitionIndices, MultiCore.cs:79-92), one list per worker, every list walked
+                                  in order, all of them at once with no exclusivity at all -- the reference's lock-free mode; its
+                                  lost updates become atomic adds here (red.global.add on both rows) */
 };
 enum {
     MML_GROUPS_PERM_MOD = 0,   /* group = perm[id] % groups, the reference rule (MultiCore.cs:64) */
@@ -205,6 +215,8 @@ int32_t mml_sgd_set_scale(mml_sgd* m, float min_rating, float max_rating, float 
  * shuffled sub-epoch order of :210-211. Serial schedule: random_index (host, n_index entries) is
  * ratings.RandomIndex; it is uploaded once and cached until a different length is passed or
  * mml_sgd_invalidate_index is called. */
+/* Naive schedule: random_index as for the serial schedule; the lists (one per worker of the GPU) are cut from it on the
+ * device the first time and cached like the serial index. */
 int32_t mml_sgd_iterate(mml_sgd* m, const int32_t* subepoch_sequence, const int32_t* random_index, int64_t n_index);
 int32_t mml_sgd_invalidate_index(mml_sgd* m);
 /* Iterate(IList<int>, bool, bool) (BiasedMatrixFactorization.cs:264-310, MatrixFactorization.cs:166-196)

@@ -656,7 +656,8 @@ protected:
         p.bold_driver = BoldDriver ? 1 : 0; p.max_threads = MaxThreads;
         // MaxThreads > 1 selects the reference's DSGD block schedule (:178-184); on the GPU the worker groups are CTAs, and the
         // parallel kernel is also what MaxThreads = 1 runs unless the engine order says Reference (Engine above)
-        if (p.schedule == MML_SCHEDULE_DSGD && NaiveParallelization) { p.num_groups = 1; p.ctas_per_group = 1 << 16; }   // :136-141, :201-204
+        // NaiveParallelization (:136-141, :201-204): the list schedule of MultiCore.PartitionIndices (one GPU only)
+        if (p.schedule == MML_SCHEDULE_DSGD && NaiveParallelization && NumGpus <= 1) p.schedule = MML_SCHEDULE_NAIVE;
         return p;
     }
 };

@@ -14,7 +14,7 @@ f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 vp = C.c_void_p
 
 LOSS_RMSE, LOSS_MAE, LOSS_LOGISTIC = 0, 1, 2
-SCHEDULE_SERIAL, SCHEDULE_DSGD = 0, 1
+SCHEDULE_SERIAL, SCHEDULE_DSGD, SCHEDULE_NAIVE = 0, 1, 2
 GROUPS_PERM_MOD, GROUPS_BALANCED = 0, 1
 INTRA_ROUNDS, INTRA_ASYNC = 0, 1
 FILE_RATINGS, FILE_RATINGS_NO_VALUE, FILE_FEEDBACK = 0, 1, 2
@@ -88,6 +88,7 @@ SIGNATURES = {
     "mml_ratings_stats": (C.c_int32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "mml_shuffle_apply": (C.c_int32, [vp, i32p, i32p, C.c_int64]),
     "mml_partition_blocks": (C.c_int32, [vp, i32p, i32p, C.c_int32, i64p, i32p]),
+    "mml_partition_indices": (C.c_int32, [vp, i32p, C.c_int64, C.c_int32, i64p, i32p]),
     "mml_mf_params_default": (None, [C.POINTER(MFParams)]),
     "mml_sgd_create": (C.c_int32, [vp, vp, C.POINTER(MFParams), oi32p, oi32p, PP]),
     "mml_sgd_destroy": (C.c_int32, [vp]),

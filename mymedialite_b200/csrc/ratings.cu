@@ -402,6 +402,47 @@ extern "C" int32_t mml_partition_blocks(mml_ratings* h, const int32_t* user_perm
     return sort_indices_by_key(r.ctx, key.p, r.n, (uint32_t)(g * g), block_ptr, idx);
 }
 
+// MultiCore.PartitionIndices (MultiCore.cs:79-92): element t of RandomIndex goes to list t % g, at position t / g
+namespace mml {
+__global__ void partition_indices_kernel(const int32_t* __restrict__ ri, int64_t n, int32_t g, int32_t* __restrict__ idx)
+{
+    const int64_t base = n / g, rem = n % g;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) {
+        const int64_t l = t % g, pos = t / g;
+        idx[l * base + (l < rem ? l : rem) + pos] = ri[t];
+    }
+}
+}
+
+extern "C" int32_t mml_partition_indices(mml_ctx* hctx, const int32_t* random_index, int64_t n, int32_t num_groups,
+                                         int64_t* list_ptr, int32_t* idx)
+{
+    MML_LOCK(mml::ctx_of(hctx));
+    MML_CHECK(hctx && list_ptr && (n == 0 || (random_index && idx)), MML_ERR_ARG, "mml_partition_indices: NULL argument");
+    MML_CHECK(num_groups >= 1 && n >= 0 && n < ((int64_t)1 << 31), MML_ERR_ARG, "mml_partition_indices: bad sizes");
+    Ctx* ctx = ctx_of(hctx);
+    if (ctx->is_root()) return mml_partition_indices(ctx->peers[0], random_index, n, num_groups, list_ptr, idx);
+    const int32_t g = (int32_t)std::min<int64_t>(num_groups, n);          // :81
+    for (int32_t l = 0; l <= num_groups; l++) {
+        if (g == 0) { list_ptr[l] = 0; continue; }
+        const int64_t ll = std::min<int64_t>(l, g), base = n / g, rem = n % g;
+        list_ptr[l] = ll * base + std::min<int64_t>(ll, rem);
+    }
+    if (n == 0) return MML_OK;
+    MML_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    DevBuf<int32_t> d_ri, d_idx;
+    MML_TRY(d_ri.alloc(n)); MML_TRY(d_idx.alloc(n));
+    MML_CUDA(cudaMemcpyAsync(d_ri.p, random_index, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+    partition_indices_kernel<<<grid_n(n), 256, 0, s>>>(d_ri.p, n, g, d_idx.p);
+    MML_CUDA(cudaGetLastError());
+    MML_CUDA(cudaMemcpyAsync(idx, d_idx.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    MML_CUDA(cudaStreamSynchronize(s));
+    return MML_OK;
+}
+
 namespace mml {
 Ratings* ratings_of(mml_ratings* h) { return h ? &h->r : nullptr; }
 Ctx* ctx_of(mml_ctx* h) { return h ? &h->c : nullptr; }

@@ -1069,6 +1069,99 @@ __device__ __forceinline__ void sgd_block_async2(const SgdArgs& a, const AsyncHe
     }
 }
 
+// ---- NaiveParallelization (BiasedMatrixFactorization.cs:136-141, :201-204) -----------------------------------------------------
+// The reference deals RandomIndex round-robin into MaxThreads lists (MultiCore.PartitionIndices) and lets every thread walk
+// its list with no coordination: both rows of a rating may be under update by other threads. Here a list belongs to a worker
+// (L lanes); the GPU runs n_lists = all its workers at once. A rating reads both rows L1-bypassed, and applies BOTH steps as
+// vector atomic adds (the reference's racing read-modify-writes lose updates; the atomics do not). Entries are laid out list
+// after list at build time (naive_entries_kernel), item and user rows as internal row numbers.
+__global__ void naive_entries_kernel(const int32_t* __restrict__ ri, int64_t n, int32_t n_lists,
+                                     const int32_t* __restrict__ users, const int32_t* __restrict__ items, const float* __restrict__ values,
+                                     const int32_t* __restrict__ user_int, const int32_t* __restrict__ item_int,
+                                     int32_t* __restrict__ ent_u, int32_t* __restrict__ ent_i, float* __restrict__ ent_v)
+{
+    const int64_t base = n / n_lists, rem = n % n_lists;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) {
+        const int64_t l = t % n_lists, pos = t / n_lists;           // MultiCore.cs:88-89
+        const int64_t e = l * base + (l < rem ? l : rem) + pos;
+        const int32_t src = ri[t];
+        ent_u[e] = user_int[users[src]]; ent_i[e] = item_int[items[src]]; ent_v[e] = values[src];
+    }
+}
+
+template <int L, int KPL, bool BIASED>
+__global__ void __launch_bounds__(512) sgd_naive_kernel(const SgdArgs a, const int64_t n, const int32_t n_lists)
+{
+    constexpr int KP = L * KPL;
+    const int lane = threadIdx.x & 31, sl = lane % L;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;          // list of this worker
+    const int64_t base = n / n_lists, rem = n % n_lists;
+    int64_t e0 = 0, e1 = 0;
+    if (w < n_lists) { e0 = w * base + (w < rem ? w : rem); e1 = e0 + base + (w < rem ? 1 : 0); }
+    uint32_t len = (uint32_t)(e1 - e0);
+#pragma unroll
+    for (int d = L; d < 32; d <<= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, d));
+    Row2<KPL> pn, qn;
+    int un = 0, in = 0; float vn = 0.f, bun = 0.f, bin = 0.f;
+#pragma unroll
+    for (int f = 0; f < KPL / 2; f++) { pn.r[f] = make_float2(0.f, 0.f); qn.r[f] = pn.r[f]; }
+    if (e0 < e1) {
+        un = a.ent_u[e0]; in = a.ent_i[e0]; vn = a.ent_v[e0];
+        row2_load_cg<L, KPL>(pn, a.P + (size_t)un * KP, sl);
+        row2_load_cg<L, KPL>(qn, a.Q + (size_t)in * KP, sl);
+        if (BIASED) { bun = ld_cg_f(a.bu + un); bin = ld_cg_f(a.bi + in); }
+    }
+    for (uint32_t t = 0; t < len; t++) {
+        const int64_t e = e0 + t;
+        const bool active = e < e1;
+        const int u = un, i = in; const float v = vn;
+        Row2<KPL> p, q;
+#pragma unroll
+        for (int f = 0; f < KPL / 2; f++) { p.r[f] = pn.r[f]; q.r[f] = qn.r[f]; }
+        const float bu0 = bun, bi0 = bin;
+        if (e + 1 < e1) {                                         // the next rating's rows, one rating ahead
+            un = a.ent_u[e + 1]; in = a.ent_i[e + 1]; vn = a.ent_v[e + 1];
+            row2_load_cg<L, KPL>(pn, a.P + (size_t)un * KP, sl);
+            row2_load_cg<L, KPL>(qn, a.Q + (size_t)in * KP, sl);
+            if (BIASED) { bun = ld_cg_f(a.bu + un); bin = ld_cg_f(a.bi + in); }
+        }
+        const float regu = a.regw_u ? a.regw_u[active ? u : 0] : a.reg_u, regi = a.regw_i ? a.regw_i[active ? i : 0] : a.reg_i;
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int f = 0; f < KPL / 2; f++) acc = __ffma2_rn(p.r[f], q.r[f], acc);
+        const float dot = worker_sum<L>(acc.x + acc.y);
+        float gc, dbu = 0.f, dbi = 0.f;
+        if (BIASED) {
+            const float score = ((a.gb + bu0) + bi0) + dot;
+            const float sig = __fdividef(1.f, 1.f + __expf(-score));
+            const float err = v - (a.minr + sig * a.range);
+            if (a.loss == MML_LOSS_RMSE) gc = err * sig * (1.f - sig) * a.range;
+            else if (a.loss == MML_LOSS_MAE) gc = (err > 0.f ? 1.f : (err < 0.f ? -1.f : 0.f)) * sig * (1.f - sig) * a.range;
+            else gc = err;
+            const float step = a.blr * a.lr;
+            dbu = step * (gc - a.breg * regu * bu0);
+            dbi = step * (gc - a.breg * regi * bi0);
+        } else {
+            gc = v - (a.gb + dot);
+        }
+        if (!active) continue;
+        const float lg = a.lr * gc, ncu = -(a.lr * regu), nci = -(a.lr * regi);
+        const float2 lg2 = make_float2(lg, lg), ncu2 = make_float2(ncu, ncu), nci2 = make_float2(nci, nci);
+        float* prow = a.P + (size_t)u * KP;
+        float* qrow = a.Q + (size_t)i * KP;
+#pragma unroll
+        for (int vv = 0; vv < KPL / 4; vv++) {
+            const float2 dp0 = __ffma2_rn(lg2, q.r[2 * vv], __fmul2_rn(ncu2, p.r[2 * vv])), dp1 = __ffma2_rn(lg2, q.r[2 * vv + 1], __fmul2_rn(ncu2, p.r[2 * vv + 1]));
+            const float2 dq0 = __ffma2_rn(lg2, p.r[2 * vv], __fmul2_rn(nci2, q.r[2 * vv])), dq1 = __ffma2_rn(lg2, p.r[2 * vv + 1], __fmul2_rn(nci2, q.r[2 * vv + 1]));
+            red_add_f4(prow + 4 * (vv * L + sl), dp0.x, dp0.y, dp1.x, dp1.y);
+            red_add_f4(qrow + 4 * (vv * L + sl), dq0.x, dq0.y, dq1.x, dq1.y);
+        }
+        if (BIASED && sl == 0) { red_add_f(a.bu + u, dbu); red_add_f(a.bi + i, dbi); }
+    }
+}
+
 // One launch per sub-epoch: grid = G CTAs.
 template <int L, int KPL, bool BIASED, bool STAGE, bool ASYNC>
 __global__ void __launch_bounds__(512) sgd_slot_kernel(const SgdArgs a, const int slot)
@@ -1766,6 +1859,37 @@ static int32_t run_serial(Sgd& m, const int32_t* d_idx, int64_t n, int update_us
     return MML_OK;
 }
 
+// NaiveParallelization epoch: lists cut from RandomIndex (d_index), one per worker of the GPU
+static int32_t run_naive_epoch(Sgd& m, bool rebuild)
+{
+    Ratings& r = *m.ratings;
+    cudaStream_t s = m.ctx->stream;
+    const int64_t n = r.n;
+    if (n <= 0) return MML_OK;
+    const int lanes = async_lanes(m.kp, 1);
+    const int64_t workers = (int64_t)m.ctx->sm_count * (512 / lanes);
+    const int32_t n_lists = (int32_t)std::min<int64_t>(workers, n);           // MultiCore.cs:81: min(num_groups, Count)
+    if (rebuild || m.ent_u.p == nullptr) {
+        MML_TRY(m.ent_u.ensure(n)); MML_TRY(m.ent_i.ensure(n)); MML_TRY(m.ent_v.ensure(n));
+        naive_entries_kernel<<<grid_n(n), 256, 0, s>>>(m.d_index.p, n, n_lists, r.users.p, r.items.p, r.values.p,
+                                                       m.users.d_to_int.p, m.items.d_to_int.p, m.ent_u.p, m.ent_i.p, m.ent_v.p);
+        MML_CUDA(cudaGetLastError());
+        m.launches++;
+    }
+    const SgdArgs a = make_args(m, 0);
+    const int blocks = (int)ceil_div((int64_t)n_lists * lanes, 512);
+    const bool b = m.p.biased != 0;
+    switch (m.kp) {
+        case 32: if (b) sgd_naive_kernel<8, 4, true><<<blocks, 512, 0, s>>>(a, n, n_lists); else sgd_naive_kernel<8, 4, false><<<blocks, 512, 0, s>>>(a, n, n_lists); break;
+        case 64: if (b) sgd_naive_kernel<8, 8, true><<<blocks, 512, 0, s>>>(a, n, n_lists); else sgd_naive_kernel<8, 8, false><<<blocks, 512, 0, s>>>(a, n, n_lists); break;
+        case 128: if (b) sgd_naive_kernel<8, 16, true><<<blocks, 512, 0, s>>>(a, n, n_lists); else sgd_naive_kernel<8, 16, false><<<blocks, 512, 0, s>>>(a, n, n_lists); break;
+        default: if (b) sgd_naive_kernel<32, 8, true><<<blocks, 512, 0, s>>>(a, n, n_lists); else sgd_naive_kernel<32, 8, false><<<blocks, 512, 0, s>>>(a, n, n_lists); break;
+    }
+    MML_CUDA(cudaGetLastError());
+    m.launches++;
+    return MML_OK;
+}
+
 static int32_t run_dsgd_epoch(Sgd& m, const int32_t* h_seq)
 {
     cudaStream_t s = m.ctx->stream;
@@ -1898,6 +2022,7 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
     MML_CHECK(p->num_factors >= 1 && p->num_factors <= 256, MML_ERR_UNSUPPORTED,
               "mml_sgd_create: num_factors=%d not in [1,256]", p->num_factors);
     MML_CHECK(r->n_users() > 0 && r->n_items() > 0, MML_ERR_ARG, "mml_sgd_create: empty id space");
+    MML_CHECK(p->schedule >= MML_SCHEDULE_SERIAL && p->schedule <= MML_SCHEDULE_NAIVE, MML_ERR_ARG, "mml_sgd_create: unknown schedule %d", p->schedule);
     if (ctx->is_root()) {
         MML_CHECK(r->shards.size() == ctx->peers.size(), MML_ERR_ARG, "mml_sgd_create: the ratings were not created on this multi-GPU context");
         MML_CHECK(p->schedule == MML_SCHEDULE_DSGD, MML_ERR_UNSUPPORTED,
@@ -2283,8 +2408,9 @@ extern "C" int32_t mml_sgd_iterate(mml_sgd* h, const int32_t* subepoch_sequence,
     if (m.p.schedule == MML_SCHEDULE_DSGD) {
         MML_TRY(run_dsgd_epoch(m, subepoch_sequence));
     } else {
-        MML_CHECK(n_index == m.ratings->n, MML_ERR_ARG, "mml_sgd_iterate: serial schedule needs RandomIndex of length %lld (got %lld)",
+        MML_CHECK(n_index == m.ratings->n, MML_ERR_ARG, "mml_sgd_iterate: this schedule needs RandomIndex of length %lld (got %lld)",
                   (long long)m.ratings->n, (long long)n_index);
+        const bool fresh_index = m.n_index != n_index;
         if (m.n_index != n_index) {
             MML_CHECK(random_index != nullptr, MML_ERR_ARG, "mml_sgd_iterate: random_index is NULL");
             for (int64_t t = 0; t < n_index; t++)
@@ -2293,7 +2419,8 @@ extern "C" int32_t mml_sgd_iterate(mml_sgd* h, const int32_t* subepoch_sequence,
             MML_CUDA(cudaMemcpyAsync(m.d_index.p, random_index, sizeof(int32_t) * n_index, cudaMemcpyHostToDevice, s));
             m.n_index = n_index;
         }
-        MML_TRY(run_serial(m, m.d_index.p, n_index, 1, 1));
+        if (m.p.schedule == MML_SCHEDULE_NAIVE) MML_TRY(run_naive_epoch(m, fresh_index));
+        else MML_TRY(run_serial(m, m.d_index.p, n_index, 1, 1));
     }
     MML_CUDA(cudaEventRecord(m.ev1, s));
     m.timed = true;
@@ -2329,6 +2456,7 @@ extern "C" int32_t mml_sgd_learn_factors(mml_sgd* h, const int32_t* indices, int
     MML_LOCK((h ? h->m.ctx : nullptr));
     MML_CHECK(h && (indices || n == 0), MML_ERR_ARG, "mml_sgd_learn_factors: NULL argument");
     MML_CHECK(num_iter >= 0, MML_ERR_ARG, "mml_sgd_learn_factors: num_iter = %d", num_iter);
+    MML_CHECK(h->m.p.schedule >= MML_SCHEDULE_SERIAL && h->m.p.schedule <= MML_SCHEDULE_NAIVE, MML_ERR_ARG, "unknown schedule");
     MML_CHECK(h->shards.empty(), MML_ERR_UNSUPPORTED, "mml_sgd_learn_factors: rating indices are per GPU on a multi-GPU context");
     Sgd& m = h->m;
     MML_CHECK(m.has_model, MML_ERR_STATE, "mml_sgd_learn_factors: no model");

@@ -565,128 +565,267 @@ __global__ void __launch_bounds__(SV_THREADS, SvCfg<T>::ctas) wrmf_solve_kernel(
     for (int f = tid; f < k; f += SV_THREADS) a.W[(size_t)u * k + f] = (float)wv[f];
 }
 
-// ---- conjugate-gradient solve, one CTA of 128 threads per row (the default solver of the tensor path) ----------------------
+// ---- preconditioned conjugate gradients + one refinement against the exact operator (the default solver) ------------------
 // The Cholesky kernel above spends its time in dependent panel steps behind CTA barriers (ncu, round 1: barrier stall 10.7
-// per issue, 86 us per row): 165k rows of config 3 cost 32 ms of a 52 ms epoch. The systems are SPD and well conditioned
-// (HH + lambda I dominates), so an iterative solve does the same work as dense matrix-vector products with no dependent
-// chain longer than a dot product:
+// per issue; ~150 barriers and 86 us per row): the 165k rows of config 3 cost 32 ms of a 52 ms epoch. Every system of a
+// half-sweep is the SAME matrix A0 = HH + lambda I plus a row-specific alpha G_u that is a small correction for almost every
+// row (G_u sums a few hundred of the tens of thousands of rows that make up HH). So M = A0^-1, computed once per half-sweep
+// (wrmf_precond_kernel), is a preconditioner under which A_u has its spectrum clustered at 1 + [0, small] and conjugate
+// gradients converge in a handful of iterations, each two dense matrix-vector products and four CTA barriers:
 //   * thread t keeps row t of A~ = fl32(HH + alpha G~ + lambda I) in 128 registers (read as column t of the symmetric
-//     inputs: coalesced), the search direction lives in shared memory and is read as broadcast 128-bit loads;
-//   * Jacobi-preconditioned CG in single precision, started from the row's current factors (ALS moves a row less and less
-//     from epoch to epoch), to a relative residual of 1e-6;
-//   * then iterative refinement in double against the stored A~ (r = b - A~ x with double accumulation, correction by a
-//     short CG) until |r| <= 2e-7 |b|: the result is the double-precision solution of the system with the fp32-rounded
-//     matrix, i.e. off the exact one by cond(A) x (6e-8 + the tensor cores' Gram rounding), far inside the 1e-4 gate;
-//   * a row that does not get there in CG_MAX_IT iterations raises *fail and the half-sweep is redone by the Cholesky
-//     kernel with its refinement against the exact operator (which also serves MML_WRMF_TENSOR_F64).
-constexpr int CG_THREADS = 128;
-constexpr int CG_MAX_IT = 400;
+//     inputs: coalesced); M sits in shared memory (fp32, column access: conflict-free); vectors are exchanged through
+//     shared memory and read as broadcast 128-bit loads;
+//   * w1 = PCG(A~, b); then ONE residual against the exact operator in double, r = b - HH w1 - lambda w1 - alpha sum_i h_i (h_i.w1)
+//     straight from the factor rows (as the Cholesky kernel's refinement), d = PCG(A~, r), w = w1 + d. The fp32 rounding of A~
+//     and of the tensor cores' G~ only enters d, i.e. at relative size |d| / |w| ~ 1e-5 of itself;
+//   * a row whose inner solves do not converge in CG_MAX_IT iterations, or whose correction is not small (|d| > 1e-3 |w|: the
+//     contraction was not what the argument assumes), raises *fail and the half-sweep is redone by the Cholesky kernels.
+// A plain (Jacobi-preconditioned) CG on the same matrices was measured first and rejected: the systems are too
+// ill-conditioned for it (hundreds of iterations; config 3 epoch 58 ms against 52 ms with the Cholesky kernel).
+constexpr int CG_THREADS = 256;           // two threads per matrix row: thread 2 t + h holds columns 64 h .. 64 h + 63 of row t
+constexpr int CG_HALF = WS_KP / 2;
+constexpr int CG_MAX_IT = 60;
+constexpr int CG_WARPS = CG_THREADS / 32;
+constexpr int PRE_THREADS = 128;
 
-// sums v0 and v1 over the CTA; `red` is one of three rotating [2][4] buffers (a barrier separates write and read, two more
-// barriers pass before the buffer is written again)
-__device__ __forceinline__ void cg_sum2(float& v0, float& v1, float (*red)[4], int lane, int warp)
+// M = (HH + lambda I)^-1 as fp32, one CTA: Cholesky in double in shared memory, then column t of the inverse by thread t
+// (forward and backward substitution; the columns live in `scratch`, k x k doubles, [row][t]: coalesced).
+__global__ void __launch_bounds__(PRE_THREADS) wrmf_precond_kernel(const double* __restrict__ HH, double reg, int k,
+                                                                   double* __restrict__ scratch, float* __restrict__ M)
+{
+    extern __shared__ double Lp[];                   // [128][129]
+    constexpr int LD = WS_KP + 1;
+    const int t = threadIdx.x;
+    for (int j = 0; j < WS_KP; j++) {
+        double v = (j == t) ? 1.0 : 0.0;             // padding: identity
+        if (t < k && j < k) v = HH[(size_t)j * k + t] + (j == t ? reg : 0.0);
+        Lp[j * LD + t] = v;                          // column t of row j (symmetric)
+    }
+    __syncthreads();
+    for (int j = 0; j < WS_KP; j++) {
+        if (t == j) Lp[j * LD + j] = sqrt(Lp[j * LD + j]);
+        __syncthreads();
+        if (t > j) Lp[t * LD + j] /= Lp[j * LD + j];
+        __syncthreads();
+        if (t > j) {
+            const double ltj = Lp[t * LD + j];
+            for (int c = j + 1; c <= t; c++) Lp[t * LD + c] -= ltj * Lp[c * LD + j];
+        }
+        __syncthreads();
+    }
+    // column t of the inverse: L y = e_t, L^T x = y
+    double* col = scratch + t;                       // element i at col[i * 128]
+    for (int i = 0; i < WS_KP; i++) {
+        double sacc = (i == t) ? 1.0 : 0.0;
+        for (int c = 0; c < i; c++) sacc -= Lp[i * LD + c] * col[(size_t)c * WS_KP];
+        col[(size_t)i * WS_KP] = sacc / Lp[i * LD + i];
+    }
+    for (int i = WS_KP - 1; i >= 0; i--) {
+        double sacc = col[(size_t)i * WS_KP];
+        for (int c = i + 1; c < WS_KP; c++) sacc -= Lp[c * LD + i] * col[(size_t)c * WS_KP];
+        col[(size_t)i * WS_KP] = sacc / Lp[i * LD + i];
+    }
+    for (int i = 0; i < WS_KP; i++) M[(size_t)i * WS_KP + t] = (float)col[(size_t)i * WS_KP];
+}
+
+struct CgShared {
+    float vec[2][WS_KP];            // the vector being multiplied (search direction / residual)
+    float red[4][2][CG_WARPS];
+    double wd[WS_KP];               // w1 in double (exact residual)
+    double part[CG_WARPS][WS_KP];   // per-warp partial sums of the exact residual's gather
+    double redd[2][CG_WARPS];
+};
+
+// sums v0 and v1 over the CTA (callers zero the contribution of the odd thread of a row pair); `red` is one of four rotating
+// buffers: a barrier separates write and read, three more barriers pass before the buffer is written again
+__device__ __forceinline__ void cg_sum2(float& v0, float& v1, float (*red)[CG_WARPS], int lane, int warp)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
     if (lane == 0) { red[0][warp] = v0; red[1][warp] = v1; }
     __syncthreads();
-    v0 = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
-    v1 = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int x = 0; x < CG_WARPS; x++) { s0 += red[0][x]; s1 += red[1][x]; }
+    v0 = s0; v1 = s1;
 }
 
-__global__ void __launch_bounds__(CG_THREADS, 2) wrmf_cg_kernel(const SolveArgs a)
+__device__ __forceinline__ double cg_max(double v, double* red, int lane, int warp)
 {
-    __shared__ __align__(16) float ps[2][WS_KP];      // search direction, double buffered
-    __shared__ double xd_s[WS_KP];                    // solution (double) for the refinement residual
-    __shared__ float red[3][2][4];
-    __shared__ double redd[2][4];
-    const int k = a.k;
-    const int q = a.q_lo + blockIdx.x;
-    if (q >= a.q_hi) return;
-    const int u = a.order[q];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (a.row_ptr[u] == a.row_ptr[u + 1]) {           // HCp = 0 => w = 0 exactly
-        if (t < k) a.W[(size_t)u * k + t] = 0.f;
-        return;
-    }
-    const float* G = a.G + (size_t)blockIdx.x * WS_KP * WS_KP;
-    const bool row_ok = t < k;
-    // row t of A~ (= column t: coalesced), padding rows / columns: identity
-    float A[WS_KP];
-    float diag = 1.f;
 #pragma unroll
-    for (int j = 0; j < WS_KP; j++) {
-        double v = 0.0;
-        if (row_ok && j < k) v = a.HH[(size_t)j * k + t] + a.alpha * (double)G[(size_t)j * WS_KP + t] + (j == t ? a.reg : 0.0);
-        else if (j == t) v = 1.0;
-        A[j] = (float)v;
-        if (j == t) diag = (float)v;
-    }
-    const float dinv = 1.f / diag;
-    const double bd = row_ok ? a.bsum[(size_t)blockIdx.x * WS_KP + t] * (1.0 + a.alpha) : 0.0;
-    double xd = row_ok ? (double)a.W[(size_t)u * k + t] : 0.0;     // warm start: the row as the last epoch left it
-    // |b|_inf for the stopping tests
-    double bmax = fabs(bd);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) bmax = fmax(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
-    if (lane == 0) redd[0][warp] = bmax;
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) red[warp] = v;
     __syncthreads();
-    bmax = fmax(fmax(redd[0][0], redd[0][1]), fmax(redd[0][2], redd[0][3]));
-    int total_it = 0;
-    bool ok = false;
-    for (int round = 0; round < 6; round++) {
-        // r = b - A~ x in double
-        xd_s[t] = xd;
-        __syncthreads();
-        double rd = bd, rd2 = 0.0;
+    double m = red[0];
 #pragma unroll
-        for (int j = 0; j < WS_KP; j += 2) { rd -= (double)A[j] * xd_s[j]; rd2 -= (double)A[j + 1] * xd_s[j + 1]; }   // fully unrolled: A stays in registers
-        rd += rd2;
-        double rmax = fabs(rd);
+    for (int x = 1; x < CG_WARPS; x++) m = fmax(m, red[x]);
+    return m;
+}
+
+// y[t] = sum_j X[t][j] v[j] with this thread's half of row t in registers (A) or shared memory (M, column access)
+__device__ __forceinline__ float cg_mv_regs(const float (&A)[CG_HALF], const float* v, int h)
+{
+    const float4* v4 = reinterpret_cast<const float4*>(v + CG_HALF * h);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
-        if (lane == 0) redd[1][warp] = rmax;
-        __syncthreads();
-        rmax = fmax(fmax(redd[1][0], redd[1][1]), fmax(redd[1][2], redd[1][3]));
-        if (!(rmax > 2e-7 * bmax)) { ok = true; break; }              // uniform across the CTA
-        if (total_it >= CG_MAX_IT) break;
-        // correction d: A~ d = r by preconditioned CG in single precision (r scaled to O(1))
-        const float scale = (float)(1.0 / rmax);
-        float r = (float)rd * scale, x = 0.f;
-        float z = r * dinv, pv = z;
-        float rz = r * z, rr = r * r;
-        cg_sum2(rz, rr, red[0], lane, warp);
-        const float rr0 = rr;
-        int buf = 0;
-        for (int it = 0; it < CG_MAX_IT && total_it < CG_MAX_IT; it++, total_it++) {
-            ps[buf][t] = pv;
-            __syncthreads();
-            const float4* p4 = reinterpret_cast<const float4*>(ps[buf]);
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-            for (int j = 0; j < WS_KP / 4; j++) {
-                const float4 pj = p4[j];
-                s0 = fmaf(A[4 * j], pj.x, s0); s1 = fmaf(A[4 * j + 1], pj.y, s1);
-                s2 = fmaf(A[4 * j + 2], pj.z, s2); s3 = fmaf(A[4 * j + 3], pj.w, s3);
-            }
-            const float Ap = (s0 + s1) + (s2 + s3);
-            float pAp = pv * Ap, dummy = 0.f;
-            cg_sum2(pAp, dummy, red[1], lane, warp);
-            const float al = rz / pAp;
-            x = fmaf(al, pv, x);
-            r = fmaf(-al, Ap, r);
-            z = r * dinv;
-            float rz_new = r * z, rr_new = r * r;
-            cg_sum2(rz_new, rr_new, red[2], lane, warp);
-            if (!(rr_new > 1e-12f * rr0)) { total_it++; break; }      // |r| <= 1e-6 |r0|
-            pv = fmaf(rz_new / rz, pv, z);
-            rz = rz_new;
-            buf ^= 1;
-        }
-        xd += (double)x * rmax;
+    for (int j = 0; j < CG_HALF / 4; j++) {
+        const float4 x = v4[j];
+        s0 = fmaf(A[4 * j], x.x, s0); s1 = fmaf(A[4 * j + 1], x.y, s1); s2 = fmaf(A[4 * j + 2], x.z, s2); s3 = fmaf(A[4 * j + 3], x.w, s3);
     }
-    if (!ok && t == 0) atomicAdd(a.fail, 1u);
-    if (row_ok) a.W[(size_t)u * k + t] = (float)xd;
+    const float s = (s0 + s1) + (s2 + s3);
+    return s + __shfl_xor_sync(0xffffffffu, s, 1);
+}
+__device__ __forceinline__ float cg_mv_smem(const float* Ms, const float* v, int t, int h)
+{
+    const float4* v4 = reinterpret_cast<const float4*>(v + CG_HALF * h);
+    const float* Mc = Ms + (size_t)(CG_HALF * h) * WS_KP + t;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < CG_HALF / 4; j++) {
+        const float4 x = v4[j];
+        s0 = fmaf(Mc[(4 * j) * WS_KP], x.x, s0); s1 = fmaf(Mc[(4 * j + 1) * WS_KP], x.y, s1);
+        s2 = fmaf(Mc[(4 * j + 2) * WS_KP], x.z, s2); s3 = fmaf(Mc[(4 * j + 3) * WS_KP], x.w, s3);
+    }
+    const float s = (s0 + s1) + (s2 + s3);
+    return s + __shfl_xor_sync(0xffffffffu, s, 1);
+}
+
+// d = PCG(A~, rhs): both threads of row t hold rhs[t] on entry and d[t] on return; false if it did not converge.
+__device__ __forceinline__ bool cg_pcg(const float (&A)[CG_HALF], const float* Ms, CgShared& sh, float rhs, float& x_out,
+                                       int t, int h, int lane, int warp)
+{
+    const float mine = h == 0 ? 1.f : 0.f;          // a row's two threads carry the same vector element: count it once
+    float r = rhs, x = 0.f;
+    if (h == 0) sh.vec[1][t] = r;
+    __syncthreads();
+    float z = cg_mv_smem(Ms, sh.vec[1], t, h);
+    float pv = z;
+    float rz = mine * r * z, rr = mine * r * r;
+    cg_sum2(rz, rr, sh.red[0], lane, warp);
+    const float rr0 = rr;
+    bool ok = !(rr0 > 0.f);
+    for (int it = 0; it < CG_MAX_IT && !ok; it++) {
+        if (h == 0) sh.vec[0][t] = pv;
+        __syncthreads();
+        const float Ap = cg_mv_regs(A, sh.vec[0], h);
+        float pAp = mine * pv * Ap, dummy = 0.f;
+        cg_sum2(pAp, dummy, sh.red[1], lane, warp);
+        const float al = rz / pAp;
+        x = fmaf(al, pv, x);
+        r = fmaf(-al, Ap, r);
+        if (h == 0) sh.vec[1][t] = r;
+        __syncthreads();
+        z = cg_mv_smem(Ms, sh.vec[1], t, h);
+        float rz_new = mine * r * z, rr_new = mine * r * r;
+        cg_sum2(rz_new, rr_new, sh.red[2 + (it & 1)], lane, warp);
+        if (!(rr_new > 1e-10f * rr0)) { ok = true; break; }           // |r| <= 1e-5 |r0|
+        pv = fmaf(rz_new / rz, pv, z);
+        rz = rz_new;
+    }
+    x_out = x;
+    return ok;
+}
+
+__global__ void __launch_bounds__(CG_THREADS, 2) wrmf_pcg_kernel(const SolveArgs a, const float* __restrict__ Mg)
+{
+    extern __shared__ float cg_smem[];
+    float* Ms = cg_smem;                                             // [128][128] fp32
+    CgShared& sh = *reinterpret_cast<CgShared*>(cg_smem + WS_KP * WS_KP);
+    const int k = a.k;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = tid >> 1, h = tid & 1;
+    for (int x = tid; x < WS_KP * WS_KP / 4; x += CG_THREADS) reinterpret_cast<float4*>(Ms)[x] = reinterpret_cast<const float4*>(Mg)[x];
+    __syncthreads();
+    const bool row_ok = t < k;
+    const bool col_ok = 4 * lane < k;
+    for (int qb = blockIdx.x; a.q_lo + qb < a.q_hi; qb += gridDim.x) {
+        const int u = a.order[a.q_lo + qb];
+        const uint32_t beg = a.row_ptr[u], end = a.row_ptr[u + 1];
+        if (beg == end) {                                           // HCp = 0 => w = 0 exactly
+            if (row_ok && h == 0) a.W[(size_t)u * k + t] = 0.f;
+            continue;
+        }
+        const float* G = a.G + (size_t)qb * WS_KP * WS_KP;
+        // this thread's half of row t of A~ (read as column t: the inputs are symmetric), padding rows / columns: identity
+        float A[CG_HALF];
+#pragma unroll
+        for (int jj = 0; jj < CG_HALF; jj++) {
+            const int j = CG_HALF * h + jj;
+            double v = 0.0;
+            if (row_ok && j < k) v = a.HH[(size_t)j * k + t] + a.alpha * (double)G[(size_t)j * WS_KP + t] + (j == t ? a.reg : 0.0);
+            else if (j == t) v = 1.0;
+            A[jj] = (float)v;
+            if ((jj & 15) == 15) asm volatile("" ::: "memory");     // 16 rows of loads in flight at a time, not all 64 (registers)
+        }
+        const double bd = row_ok ? a.bsum[(size_t)qb * WS_KP + t] * (1.0 + a.alpha) : 0.0;
+        const double bmax = cg_max(fabs(bd), sh.redd[0], lane, warp);
+        float x1 = 0.f;
+        bool ok = cg_pcg(A, Ms, sh, (float)(bd / bmax), x1, t, h, lane, warp);
+        const double w1 = (double)x1 * bmax;
+        // r = b - HH w1 - lambda w1 - alpha sum_i h_i (h_i . w1): the exact operator, in double
+        if (h == 0) sh.wd[t] = w1;
+        __syncthreads();
+        double rd = 0.0;
+        if (row_ok) {
+            const int g0 = CG_HALF * h, g1 = min(k, g0 + CG_HALF);
+            for (int g = g0; g < g1; g++) rd -= a.HH[(size_t)g * k + t] * sh.wd[g];
+        }
+        rd += __shfl_xor_sync(0xffffffffu, rd, 1);
+        if (row_ok) rd += bd - a.reg * w1;
+        {
+            double r0 = 0, r1 = 0, r2 = 0, r3 = 0, w0 = 0, w1r = 0, w2 = 0, w3 = 0;
+            if (col_ok) { w0 = sh.wd[4 * lane]; w1r = sh.wd[4 * lane + 1]; w2 = sh.wd[4 * lane + 2]; w3 = sh.wd[4 * lane + 3]; }
+            // a warp per entry, lane l holds factors 4 l .. 4 l + 3; two entries in flight
+            uint32_t e = beg + warp;
+            for (; e + CG_WARPS < end; e += 2 * CG_WARPS) {
+                const int32_t ida = a.cols[e], idb = a.cols[e + CG_WARPS];
+                float4 ha = make_float4(0.f, 0.f, 0.f, 0.f), hb = ha;
+                if (col_ok) {
+                    ha = __ldg(reinterpret_cast<const float4*>(a.H + (size_t)ida * k) + lane);
+                    hb = __ldg(reinterpret_cast<const float4*>(a.H + (size_t)idb * k) + lane);
+                }
+                double da = (double)ha.x * w0 + (double)ha.y * w1r + (double)ha.z * w2 + (double)ha.w * w3;
+                double db = (double)hb.x * w0 + (double)hb.y * w1r + (double)hb.z * w2 + (double)hb.w * w3;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { da += __shfl_xor_sync(0xffffffffu, da, o); db += __shfl_xor_sync(0xffffffffu, db, o); }
+                r0 += da * (double)ha.x + db * (double)hb.x; r1 += da * (double)ha.y + db * (double)hb.y;
+                r2 += da * (double)ha.z + db * (double)hb.z; r3 += da * (double)ha.w + db * (double)hb.w;
+            }
+            for (; e < end; e += CG_WARPS) {
+                const int32_t id = a.cols[e];
+                float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col_ok) hv = __ldg(reinterpret_cast<const float4*>(a.H + (size_t)id * k) + lane);
+                double d = (double)hv.x * w0 + (double)hv.y * w1r + (double)hv.z * w2 + (double)hv.w * w3;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                r0 += d * (double)hv.x; r1 += d * (double)hv.y; r2 += d * (double)hv.z; r3 += d * (double)hv.w;
+            }
+            double* pw = sh.part[warp] + 4 * lane;
+            pw[0] = r0; pw[1] = r1; pw[2] = r2; pw[3] = r3;
+        }
+        __syncthreads();
+        if (row_ok) {
+            double acc = 0.0;
+#pragma unroll
+            for (int x = 0; x < CG_WARPS; x++) acc += sh.part[x][t];
+            rd -= a.alpha * acc;
+        }
+        const double rmax = cg_max(fabs(rd), sh.redd[1], lane, warp);
+        double w = w1;
+        if (rmax > 1e-9 * bmax) {                                   // uniform across the CTA
+            float d1 = 0.f;
+            ok = cg_pcg(A, Ms, sh, (float)(rd / rmax), d1, t, h, lane, warp) && ok;
+            const double dd = (double)d1 * rmax;
+            w = w1 + dd;
+            // the correction must be small next to the solution, or the one-step argument does not hold
+            const double dm = cg_max(fabs(dd), sh.redd[0], lane, warp);
+            const double wm = cg_max(fabs(w), sh.redd[1], lane, warp);
+            if (dm > 1e-3 * wm) ok = false;
+        }
+        if (!ok && tid == 0) atomicAdd(a.fail, 1u);
+        if (row_ok && h == 0) a.W[(size_t)u * k + t] = (float)w;
+        __syncthreads();                                            // shared scratch is reused by the next row
+    }
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------
@@ -694,6 +833,7 @@ bool wrmf_tc_eligible(int32_t k) { return k >= 4 && k <= 128 && (k % 4) == 0; }
 
 struct WrmfTcWork {
     DevBuf<float> G; DevBuf<double> bsum; DevBuf<uint32_t> err;
+    DevBuf<float> M; DevBuf<double> Mscratch;          // preconditioner of the PCG solver and its work space
     int32_t cap_rows = 0;
 };
 WrmfTcWork* wrmf_tc_work_create() { return new (std::nothrow) WrmfTcWork(); }
@@ -718,11 +858,22 @@ static int32_t half_sweep_impl(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_p
     const size_t smem_syrk = (size_t)WS_STAGES * 2 * WS_TILE + 1024;
     MML_CUDA(cudaFuncSetAttribute((const void*)wrmf_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_syrk));
     const int np = (k + SV_NB - 1) / SV_NB;
-    // solver: 0 = conjugate gradients (default), 1 = Cholesky with the single-precision factor, 2 = with the double one
+    // solver: 0 = preconditioned CG + one exact refinement (default), 1 = Cholesky with the single-precision factor, 2 = double
     const bool f64 = solver == 2;
-    const size_t smem_solve = solver == 0 ? 0 : (f64 ? sv_smem_bytes<double>(np) : sv_smem_bytes<float>(np));
-    void (*solve_fn)(const SolveArgs) = solver == 0 ? wrmf_cg_kernel : (f64 ? wrmf_solve_kernel<double> : wrmf_solve_kernel<float>);
-    if (solver != 0) MML_CUDA(cudaFuncSetAttribute((const void*)solve_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+    const size_t smem_solve = solver == 0 ? sizeof(float) * WS_KP * WS_KP + sizeof(CgShared)
+                                          : (f64 ? sv_smem_bytes<double>(np) : sv_smem_bytes<float>(np));
+    void (*chol_fn)(const SolveArgs) = f64 ? wrmf_solve_kernel<double> : wrmf_solve_kernel<float>;
+    if (solver != 0) MML_CUDA(cudaFuncSetAttribute((const void*)chol_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+    else {
+        // the shared preconditioner M = (HH + lambda I)^-1 of this half-sweep
+        MML_TRY(w.M.ensure((size_t)WS_KP * WS_KP)); MML_TRY(w.Mscratch.ensure((size_t)WS_KP * WS_KP));
+        const size_t smem_pre = sizeof(double) * WS_KP * (WS_KP + 1);
+        MML_CUDA(cudaFuncSetAttribute((const void*)wrmf_precond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pre));
+        MML_CUDA(cudaFuncSetAttribute((const void*)wrmf_pcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+        wrmf_precond_kernel<<<1, PRE_THREADS, smem_pre, s>>>(HH, reg, k, w.Mscratch.p, w.M.p);
+        MML_CUDA(cudaGetLastError());
+        if (launches) *launches += 1;
+    }
     for (int32_t q_lo = 0; q_lo < n_rows; q_lo += B) {
         const int32_t q_hi = std::min(n_rows, q_lo + B), nb = q_hi - q_lo;
         MML_CUDA(cudaMemsetAsync(w.bsum.p, 0, sizeof(double) * (size_t)nb * WS_KP, s));
@@ -736,7 +887,8 @@ static int32_t half_sweep_impl(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_p
         SolveArgs va{};
         va.row_ptr = row_ptr; va.cols = cols; va.order = order; va.q_lo = q_lo; va.q_hi = q_hi; va.G = w.G.p; va.bsum = w.bsum.p; va.HH = HH;
         va.H = H; va.alpha = alpha; va.reg = reg; va.k = k; va.W = W; va.fail = w.err.p + 1;
-        solve_fn<<<nb, solver == 0 ? CG_THREADS : SV_THREADS, smem_solve, s>>>(va);
+        if (solver == 0) wrmf_pcg_kernel<<<std::min(nb, 2 * ctx->sm_count), CG_THREADS, smem_solve, s>>>(va, w.M.p);
+        else chol_fn<<<nb, SV_THREADS, smem_solve, s>>>(va);
         MML_CUDA(cudaGetLastError());
         if (launches) *launches += 2;
     }
@@ -752,7 +904,7 @@ int32_t wrmf_tc_half_sweep(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_ptr, 
                            float* W, const float* H, int32_t k, const double* HH, double alpha, double reg, int64_t* launches,
                            float* debug_G_row0, bool factor_f64)
 {
-    // Solver ladder: conjugate gradients (default) -> Cholesky with the single-precision factor -> with the double one, each
+    // Solver ladder: preconditioned conjugate gradients (default) -> Cholesky with the single-precision factor -> with the double one, each
     // tried only if the previous left a row unconverged (W is output only -- the CG kernel reads it as a starting guess, which
     // affects the iteration count, not the result -- and H is untouched, so a repeat is safe). factor_f64 (mode
     // MML_WRMF_TENSOR_F64) or MMLB200_WRMF_SOLVER = chol | chol64 start further down the ladder (parity tests, A/B runs).

@@ -115,6 +115,15 @@ class DeviceRatings:
             pass
 
 
+def partition_indices(ctx, random_index, num_groups):
+    """MultiCore.PartitionIndices (MultiCore.cs:79-92) on the device: (list_ptr int64[num_groups + 1], idx int32[n])."""
+    ri = _i32(random_index)
+    ptr = np.zeros(int(num_groups) + 1, np.int64)
+    idx = np.zeros(max(ri.shape[0], 1), np.int32)
+    check(ctx.lib.mml_partition_indices(ctx.h, ri, ri.shape[0], int(num_groups), ptr, idx))
+    return ptr, idx[:ri.shape[0]]
+
+
 def default_params(**kw):
     p = MFParams()
     _capi.load().mml_mf_params_default(C.byref(p))

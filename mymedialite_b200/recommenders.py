@@ -165,8 +165,9 @@ class MatrixFactorization(_Recommender):
         self._dev_ratings = engine.DeviceRatings(ctx, r.Users, r.Items, r.Values, r.MaxUserID, r.MaxItemID)
         if r.Count:
             _, self.MinRating, self.MaxRating = self._dev_ratings.stats()
-        self._model = engine.SgdModel(ctx, self._dev_ratings, self._params())
-        self._is_parallel = self._parallel()
+        params = self._params()
+        self._model = engine.SgdModel(ctx, self._dev_ratings, params)
+        self._is_parallel = params.schedule == _capi.SCHEDULE_DSGD
         if ENGINE["init"] == "device":
             self._model.init_model(sysrandom.get_instance().next(), self.InitMean, self.InitStdDev)
         else:
@@ -362,17 +363,15 @@ class BiasedMatrixFactorization(MatrixFactorization):
         # MaxThreads > 1 selects the reference's DSGD block schedule (:178-184); on the GPU the worker groups are CTAs, and
         # the parallel kernel is also what MaxThreads = 1 runs unless the engine order says "reference" (ENGINE above)
         dsgd = self._parallel()
-        shape = {}
-        if dsgd and self.NaiveParallelization:
-            # :136-141, :201-204: lock-free Parallel.For over index lists, no block exclusivity -> the whole GPU is one
-            # worker group (no hand-over); the library clamps ctas_per_group to the SM count
-            shape = dict(num_groups=1, ctas_per_group=1 << 16)
-        return engine.default_params(**shape, **dict(
+        # NaiveParallelization (:136-141, :201-204): RandomIndex dealt into lists (MultiCore.PartitionIndices), one per worker,
+        # all walked at once with no exclusivity -- MML_SCHEDULE_NAIVE (one GPU; several GPUs keep the block schedule)
+        naive = dsgd and self.NaiveParallelization and int(self.NumGpus) <= 1
+        return engine.default_params(**dict(
             biased=1, num_factors=int(self.NumFactors), learn_rate=float(self.LearnRate), decay=float(self.Decay),
             regularization=float(self.Regularization), bias_learn_rate=float(self.BiasLearnRate), bias_reg=float(self.BiasReg),
             reg_u=float(self.RegU), reg_i=float(self.RegI), frequency_regularization=int(bool(self.FrequencyRegularization)),
             loss=self._LOSS[self.Loss], bold_driver=int(bool(self.BoldDriver)), max_threads=int(self.MaxThreads),
-            schedule=_capi.SCHEDULE_DSGD if dsgd else _capi.SCHEDULE_SERIAL))
+            schedule=_capi.SCHEDULE_NAIVE if naive else (_capi.SCHEDULE_DSGD if dsgd else _capi.SCHEDULE_SERIAL)))
 
     def SaveModel(self, filename):
         m = self._model.get_model()

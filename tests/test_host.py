@@ -96,7 +96,7 @@ def test_merge_schedules_orders_by_subepoch_then_rank():
 
 def test_parallel_options_map_to_the_engine_grid():
     """MaxThreads > 1 selects the DSGD block schedule (BiasedMatrixFactorization.cs:178-184); NaiveParallelization
-    (:136-141, :201-204) drops the block exclusivity: one worker group spanning the GPU."""
+    (:136-141, :201-204) the list schedule of MultiCore.PartitionIndices (no exclusivity at all)."""
     from mymedialite_b200 import recommenders as R, _capi
     m = R.BiasedMatrixFactorization()
     assert m._params().schedule == _capi.SCHEDULE_SERIAL
@@ -105,7 +105,9 @@ def test_parallel_options_map_to_the_engine_grid():
     assert p.schedule == _capi.SCHEDULE_DSGD and p.num_groups == 0 and p.ctas_per_group == 0 and p.max_threads == 8
     m.NaiveParallelization = True
     p = m._params()
-    assert p.schedule == _capi.SCHEDULE_DSGD and p.num_groups == 1 and p.ctas_per_group >= 148
+    assert p.schedule == _capi.SCHEDULE_NAIVE and p.max_threads == 8
+    m.NumGpus = 2                                   # several GPUs keep the block schedule
+    assert m._params().schedule == _capi.SCHEDULE_DSGD
 
 
 # ---- Eval.Items host logic (candidate selection, test rows) -- no device needed ---------------------------------------

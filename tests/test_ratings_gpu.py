@@ -68,6 +68,19 @@ def test_partition_blocks_match_oracle(eng, g):
     assert np.array_equal(ptr, optr) and np.array_equal(idx, oidx)
 
 
+@pytest.mark.parametrize("n,g", [(10, 3), (10, 50), (1, 1), (1000, 7), (300_000, 4736), (1_000_003, 9472)])
+def test_partition_indices_match_oracle(eng, n, g):
+    """MultiCore.PartitionIndices (MultiCore.cs:79-92): RandomIndex dealt round-robin into min(groups, n) lists --
+    bit-exact with the oracle's restatement (itself held by the known answers of src/Tests/MulticoreTest.cs:27-93)."""
+    engine, ctx = eng
+    ri = O.Random(n).shuffle(np.arange(n))
+    g2, optr, oidx = O.partition_indices(ri, g)
+    ptr, idx = engine.partition_indices(ctx, ri, g)
+    assert np.array_equal(ptr[:g2 + 1], optr[:g2 + 1]) and np.all(ptr[g2:] == n)
+    assert np.array_equal(idx, oidx[:n])
+    assert np.array_equal(np.sort(idx), np.arange(n))
+
+
 def test_empty_rating_set(eng):
     engine, ctx = eng
     e = np.zeros(0, np.int32)

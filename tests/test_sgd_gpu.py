@@ -301,6 +301,31 @@ def test_dsgd_rmse_tracks_single_threaded_oracle(eng, intra):
         assert abs(g_te - o_te) / o_te < 0.005, (epoch, g_te, o_te)
 
 
+@pytest.mark.parametrize("biased,k", [(True, 32), (True, 128), (False, 10)])
+def test_naive_parallelization_tracks_single_threaded_oracle(eng, biased, k):
+    """NaiveParallelization (BiasedMatrixFactorization.cs:136-141, :201-204; lists of MultiCore.PartitionIndices, one per
+    worker of the GPU, walked with no exclusivity): declared non-reproducible by the reference, so the gate is the statistical
+    one -- per-epoch train / test RMSE within 0.5 % of the single-threaded run from the same factors."""
+    engine, ctx = eng
+    from mymedialite_b200 import synthetic
+    d = synthetic.ratings(3000, 800, 300000, "half", 11)
+    u, i, v = d["train"]; tu, ti, tv = d["test"]
+    rng = O.Random(1)
+    om = O.Model(u, i, v, biased=biased, num_factors=k)
+    om.init(rng)
+    r, gm = gpu_model(eng, u, i, v, biased, k, om, schedule=engine._capi.SCHEDULE_NAIVE, max_threads=8)
+    ri = O.Random(5).shuffle(np.arange(u.size))
+    lr0 = gm.learnrate
+    for epoch in range(6):
+        om.iterate(rng)
+        gm.iterate(random_index=ri)
+        o_tr, o_te = om.evaluate(u, i, v)["RMSE"], om.evaluate(tu, ti, tv)["RMSE"]
+        g_tr, g_te = gm.evaluate_train()["RMSE"], gm.evaluate(tu, ti, tv)["RMSE"]
+        assert abs(g_tr - o_tr) / o_tr < 0.005, (epoch, g_tr, o_tr)
+        assert abs(g_te - o_te) / o_te < 0.005, (epoch, g_te, o_te)
+    assert gm.learnrate == lr0                      # Decay = 1: UpdateLearnRate (twice, MaxThreads > 1) leaves it alone
+
+
 def test_predict_evaluate_objective_match_oracle(eng):
     engine, ctx = eng
     d = small_data()
