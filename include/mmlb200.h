@@ -360,8 +360,10 @@ int32_t mml_wrmf_shard(mml_wrmf* m, int32_t by_item, int32_t* ranges);
  * with HH and the assembly in double, a blocked Cholesky factor in single precision used as the preconditioner of an
  * iterative refinement against the exact double-precision operator (num_factors a multiple of 4, <= 128; a half-sweep
  * with a row that does not converge is repeated with the double-precision factor), the all-double CUDA-core kernels
- * otherwise; FP64 / TENSOR force one of them, TENSOR_F64 = TENSOR with the double-precision factor. */
-enum { MML_WRMF_AUTO = 0, MML_WRMF_FP64 = 1, MML_WRMF_TENSOR = 2, MML_WRMF_TENSOR_F64 = 3 };
+ * otherwise; FP64 / TENSOR force one of them, TENSOR_F64 = TENSOR with the double-precision factor, TENSOR_PCG = TENSOR with the
+ * row systems solved by conjugate gradients preconditioned with (HH + lambda I)^-1 and one refinement against the exact operator
+ * (rows within 2e-7 of the double solve at config 3, but 62 ms per epoch against 52 ms: measured, not the default). */
+enum { MML_WRMF_AUTO = 0, MML_WRMF_FP64 = 1, MML_WRMF_TENSOR = 2, MML_WRMF_TENSOR_F64 = 3, MML_WRMF_TENSOR_PCG = 4 };
 int32_t mml_wrmf_set_mode(int32_t mode);
 /* Diagnostic for the parity tests: the tensor-core Gram sum (128 x 128 floats, zero beyond num_factors) of the user with
  * the most events, and that user's id. The model is not modified. */

@@ -142,7 +142,7 @@ SIGNATURES = {
 
 TOPN_AUTO, TOPN_EXACT, TOPN_TENSOR = 0, 1, 2
 TOPN_FILTER_BF16, TOPN_FILTER_TF32 = 0, 1
-WRMF_AUTO, WRMF_FP64, WRMF_TENSOR, WRMF_TENSOR_F64 = 0, 1, 2, 3
+WRMF_AUTO, WRMF_FP64, WRMF_TENSOR, WRMF_TENSOR_F64, WRMF_TENSOR_PCG = 0, 1, 2, 3, 4
 
 _lib = None
 

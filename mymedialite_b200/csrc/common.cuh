@@ -127,6 +127,7 @@ struct Ctx {
     int flush_val = 0;
     void* topn_cache = nullptr;  // Recommend() workspace of this context, grow-only (topn_tc.cu); freed by topn_cache_destroy
     cudaStream_t out_stream = nullptr;    // device -> host result staging that may overlap the next batch's kernels
+    cudaStream_t aux_stream = nullptr;    // a second kernel stream (WRMF: the next batch's Gram sums under this batch's solves)
     // One-process multi-GPU (mml_ctx_create with n_gpus > 1, the NumGpus property of the host classes): this context is
     // then only the root of `peers`, one ordinary rank context per GPU (rank r of n_gpus, NCCL communicators from
     // ncclCommInitAll); every entry point on the root or on a handle created from it fans out to the peers, one host

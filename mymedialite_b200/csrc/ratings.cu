@@ -145,6 +145,7 @@ int32_t ctx_create_on_device(int dev, mml_ctx** out)
     MML_CUDA(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking));
     MML_CUDA(cudaStreamCreateWithFlags(&c->c.copy_stream, cudaStreamNonBlocking));
     MML_CUDA(cudaStreamCreateWithFlags(&c->c.out_stream, cudaStreamNonBlocking));
+    MML_CUDA(cudaStreamCreateWithFlags(&c->c.aux_stream, cudaStreamNonBlocking));
     MML_CUDA(cudaEventCreateWithFlags(&c->c.copy_done, cudaEventDisableTiming));
     *out = c;
     return MML_OK;
@@ -193,6 +194,7 @@ extern "C" int32_t mml_ctx_destroy(mml_ctx* ctx)
     dist_destroy(&ctx->c);
     topn_cache_destroy(&ctx->c);
     if (ctx->c.out_stream) cudaStreamDestroy(ctx->c.out_stream);
+    if (ctx->c.aux_stream) cudaStreamDestroy(ctx->c.aux_stream);
     if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
     if (ctx->c.copy_stream) cudaStreamDestroy(ctx->c.copy_stream);
     if (ctx->c.copy_done) cudaEventDestroy(ctx->c.copy_done);

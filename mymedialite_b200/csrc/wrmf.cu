@@ -340,7 +340,7 @@ void wrmf_tc_work_destroy(WrmfTcWork* w);
 bool wrmf_tc_eligible(int32_t k);
 int32_t wrmf_tc_half_sweep(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_ptr, const int32_t* cols, const int32_t* order, int32_t n_rows,
                            float* W, const float* H, int32_t k, const double* HH, double alpha, double reg, int64_t* launches,
-                           float* debug_G_row0, bool factor_f64);
+                           float* debug_G_row0, int first_solver);
 static int g_wrmf_mode = 0;            // MML_WRMF_AUTO
 static float* g_wrmf_debug_G = nullptr;
 
@@ -374,14 +374,14 @@ static int32_t half_sweep(Wrmf& m, const uint32_t* row_ptr, const int32_t* cols,
     MML_CUDA(cudaGetLastError());
     // AUTO takes the tensor path only when HH sums many more rows than it has columns: with n_h_rows ~ k the system is so
     // ill-conditioned that the fp32-level rounding of the per-row Gram sums shows above the 1e-4 gate (double does not).
-    const bool forced = g_wrmf_mode == MML_WRMF_TENSOR || g_wrmf_mode == MML_WRMF_TENSOR_F64;
+    const bool forced = g_wrmf_mode == MML_WRMF_TENSOR || g_wrmf_mode == MML_WRMF_TENSOR_F64 || g_wrmf_mode == MML_WRMF_TENSOR_PCG;
     const bool tc = g_wrmf_mode != MML_WRMF_FP64 && wrmf_tc_eligible(k) && (forced || (int64_t)n_h_rows >= 16ll * k);
     MML_CHECK(tc || !forced, MML_ERR_UNSUPPORTED, "WRMF: num_factors=%d is outside the tensor-core path (multiple of 4, <= 128)", k);
     if (tc) {
         m.launches += 2;
         if (!m.tc_work) m.tc_work = wrmf_tc_work_create();
         return wrmf_tc_half_sweep(m.ctx, m.tc_work, row_ptr, cols, order, n_rows, W, H, k, m.HH.p, m.alpha, m.reg, &m.launches, g_wrmf_debug_G,
-                                  g_wrmf_mode == MML_WRMF_TENSOR_F64);
+                                  g_wrmf_mode == MML_WRMF_TENSOR_F64 ? 2 : (g_wrmf_mode == MML_WRMF_TENSOR_PCG ? 0 : 1));
     }
     const size_t smem = sizeof(double) * ((size_t)k * k + k) + sizeof(float) * HB * k;
     MML_CUDA(cudaFuncSetAttribute((const void*)af, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -681,7 +681,7 @@ extern "C" int32_t mml_wrmf_retrain(mml_wrmf* h, int32_t by_item, const int32_t*
 
 extern "C" int32_t mml_wrmf_set_mode(int32_t mode)
 {
-    MML_CHECK(mode >= MML_WRMF_AUTO && mode <= MML_WRMF_TENSOR_F64, MML_ERR_ARG, "mml_wrmf_set_mode: unknown mode %d", mode);
+    MML_CHECK(mode >= MML_WRMF_AUTO && mode <= MML_WRMF_TENSOR_PCG, MML_ERR_ARG, "mml_wrmf_set_mode: unknown mode %d", mode);
     g_wrmf_mode = mode;
     return MML_OK;
 }

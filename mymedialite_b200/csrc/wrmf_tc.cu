@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(SV_THREADS, SvCfg<T>::ctas) wrmf_solve_kernel(
     for (int f = tid; f < k; f += SV_THREADS) a.W[(size_t)u * k + f] = (float)wv[f];
 }
 
-// ---- preconditioned conjugate gradients + one refinement against the exact operator (the default solver) ------------------
+// ---- preconditioned conjugate gradients + one refinement against the exact operator (MML_WRMF_TENSOR_PCG) ----------------
 // The Cholesky kernel above spends its time in dependent panel steps behind CTA barriers (ncu, round 1: barrier stall 10.7
 // per issue; ~150 barriers and 86 us per row): the 165k rows of config 3 cost 32 ms of a 52 ms epoch. Every system of a
 // half-sweep is the SAME matrix A0 = HH + lambda I plus a row-specific alpha G_u that is a small correction for almost every
@@ -580,8 +580,11 @@ __global__ void __launch_bounds__(SV_THREADS, SvCfg<T>::ctas) wrmf_solve_kernel(
 //     and of the tensor cores' G~ only enters d, i.e. at relative size |d| / |w| ~ 1e-5 of itself;
 //   * a row whose inner solves do not converge in CG_MAX_IT iterations, or whose correction is not small (|d| > 1e-3 |w|: the
 //     contraction was not what the argument assumes), raises *fail and the half-sweep is redone by the Cholesky kernels.
-// A plain (Jacobi-preconditioned) CG on the same matrices was measured first and rejected: the systems are too
-// ill-conditioned for it (hundreds of iterations; config 3 epoch 58 ms against 52 ms with the Cholesky kernel).
+// Measured at config 3 (profiles/r2_wrmf_solvers.md): rows within 1.2e-7 of the double-precision solve (the Cholesky path:
+// ~1e-6), but 40.7 ms of solves per epoch against 32 ms -- ~30 CG iterations x 5 barrier-separated steps per row are as
+// latency bound as the ~150 barriers of the blocked factorisation -- so the Cholesky kernel stays the default and this one a
+// selectable mode. A plain (Jacobi-preconditioned) CG was measured first and rejected outright: hundreds of iterations
+// (58 ms per epoch) and row errors up to 2e-4 without the exact refinement.
 constexpr int CG_THREADS = 256;           // two threads per matrix row: thread 2 t + h holds columns 64 h .. 64 h + 63 of row t
 constexpr int CG_HALF = WS_KP / 2;
 constexpr int CG_MAX_IT = 60;
@@ -832,12 +835,18 @@ __global__ void __launch_bounds__(CG_THREADS, 2) wrmf_pcg_kernel(const SolveArgs
 bool wrmf_tc_eligible(int32_t k) { return k >= 4 && k <= 128 && (k % 4) == 0; }
 
 struct WrmfTcWork {
-    DevBuf<float> G; DevBuf<double> bsum; DevBuf<uint32_t> err;
+    DevBuf<float> G[2]; DevBuf<double> bsum[2]; DevBuf<uint32_t> err;   // per-batch Gram sums and right-hand sides, double buffered
     DevBuf<float> M; DevBuf<double> Mscratch;          // preconditioner of the PCG solver and its work space
+    cudaEvent_t syrk_done[2] = {nullptr, nullptr}, solve_done[2] = {nullptr, nullptr};
     int32_t cap_rows = 0;
 };
 WrmfTcWork* wrmf_tc_work_create() { return new (std::nothrow) WrmfTcWork(); }
-void wrmf_tc_work_destroy(WrmfTcWork* w) { delete w; }
+void wrmf_tc_work_destroy(WrmfTcWork* w)
+{
+    if (!w) return;
+    for (int x = 0; x < 2; x++) { if (w->syrk_done[x]) cudaEventDestroy(w->syrk_done[x]); if (w->solve_done[x]) cudaEventDestroy(w->solve_done[x]); }
+    delete w;
+}
 
 // One half-sweep's per-row systems: W[u] <- solve for every row of `order`. HH (fp64, k x k) is on the device.
 static int32_t half_sweep_impl(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_ptr, const int32_t* cols, const int32_t* order, int32_t n_rows,
@@ -847,13 +856,23 @@ static int32_t half_sweep_impl(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_p
     cudaStream_t s = ctx->stream;
     MML_CHECK(work != nullptr, MML_ERR_STATE, "wrmf: no tensor-path workspace");
     WrmfTcWork& w = *work;
-    const int32_t B = 16384;                                   // rows per batch: G 1 GiB
+    // Rows per batch: G 1 GiB, twice. The Gram-sum kernel (gather + tensor pipe, one CTA per SM) of batch b + 1 runs on a
+    // second stream UNDER the row solves of batch b (latency bound: barrier-separated panel steps), which leave the SM's
+    // issue slots, L2 path and tensor pipe mostly idle; 129 KB + 2 x 39 KB of shared memory fit one SM together.
+    const int32_t B = 16384;
     const int32_t cap = std::min(B, std::max(n_rows, 1));
     if (w.cap_rows < cap) {
-        MML_TRY(w.G.alloc((size_t)cap * WS_KP * WS_KP)); MML_TRY(w.bsum.alloc((size_t)cap * WS_KP));
+        for (int x = 0; x < 2; x++) { MML_TRY(w.G[x].alloc((size_t)cap * WS_KP * WS_KP)); MML_TRY(w.bsum[x].alloc((size_t)cap * WS_KP)); }
         if (!w.err.p) MML_TRY(w.err.alloc(2));
         w.cap_rows = cap;
     }
+    for (int x = 0; x < 2; x++)
+        if (!w.syrk_done[x]) {
+            MML_CUDA(cudaEventCreateWithFlags(&w.syrk_done[x], cudaEventDisableTiming));
+            MML_CUDA(cudaEventCreateWithFlags(&w.solve_done[x], cudaEventDisableTiming));
+        }
+    cudaStream_t s2 = ctx->aux_stream;
+    static const bool overlap = [] { const char* e = getenv("MMLB200_WRMF_OVERLAP"); return !(e && *e == '0'); }();
     MML_CUDA(cudaMemsetAsync(w.err.p, 0, 2 * sizeof(uint32_t), s));
     const size_t smem_syrk = (size_t)WS_STAGES * 2 * WS_TILE + 1024;
     MML_CUDA(cudaFuncSetAttribute((const void*)wrmf_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_syrk));
@@ -874,22 +893,31 @@ static int32_t half_sweep_impl(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_p
         MML_CUDA(cudaGetLastError());
         if (launches) *launches += 1;
     }
-    for (int32_t q_lo = 0; q_lo < n_rows; q_lo += B) {
+    // everything enqueued on `s` so far (HH, the error words, the preconditioner) precedes the first Gram sums on s2
+    cudaEvent_t ev_start = w.solve_done[0];
+    if (overlap) { MML_CUDA(cudaEventRecord(ev_start, s)); MML_CUDA(cudaStreamWaitEvent(s2, ev_start, 0)); }
+    int bi = 0;
+    for (int32_t q_lo = 0; q_lo < n_rows; q_lo += B, bi++) {
         const int32_t q_hi = std::min(n_rows, q_lo + B), nb = q_hi - q_lo;
-        MML_CUDA(cudaMemsetAsync(w.bsum.p, 0, sizeof(double) * (size_t)nb * WS_KP, s));
+        const int x = bi & 1;
+        cudaStream_t sy = overlap ? s2 : s;
+        if (overlap && bi >= 2) MML_CUDA(cudaStreamWaitEvent(sy, w.solve_done[x], 0));     // buffer x was read by the solves of batch bi - 2
+        MML_CUDA(cudaMemsetAsync(w.bsum[x].p, 0, sizeof(double) * (size_t)nb * WS_KP, sy));
         SyrkArgs sa{};
         sa.row_ptr = row_ptr; sa.cols = cols; sa.order = order; sa.q_lo = q_lo; sa.q_hi = q_hi; sa.H = H; sa.k = k;
-        sa.G = w.G.p; sa.bsum = w.bsum.p; sa.err = w.err.p;
-        wrmf_syrk_kernel<<<std::min(nb, ctx->sm_count), WS_THREADS, smem_syrk, s>>>(sa);
+        sa.G = w.G[x].p; sa.bsum = w.bsum[x].p; sa.err = w.err.p;
+        wrmf_syrk_kernel<<<std::min(nb, ctx->sm_count), WS_THREADS, smem_syrk, sy>>>(sa);
         MML_CUDA(cudaGetLastError());
+        if (overlap) { MML_CUDA(cudaEventRecord(w.syrk_done[x], sy)); MML_CUDA(cudaStreamWaitEvent(s, w.syrk_done[x], 0)); }
         if (debug_G_row0 && q_lo == 0)
-            MML_CUDA(cudaMemcpyAsync(debug_G_row0, w.G.p, sizeof(float) * WS_KP * WS_KP, cudaMemcpyDeviceToHost, s));
+            MML_CUDA(cudaMemcpyAsync(debug_G_row0, w.G[x].p, sizeof(float) * WS_KP * WS_KP, cudaMemcpyDeviceToHost, s));
         SolveArgs va{};
-        va.row_ptr = row_ptr; va.cols = cols; va.order = order; va.q_lo = q_lo; va.q_hi = q_hi; va.G = w.G.p; va.bsum = w.bsum.p; va.HH = HH;
+        va.row_ptr = row_ptr; va.cols = cols; va.order = order; va.q_lo = q_lo; va.q_hi = q_hi; va.G = w.G[x].p; va.bsum = w.bsum[x].p; va.HH = HH;
         va.H = H; va.alpha = alpha; va.reg = reg; va.k = k; va.W = W; va.fail = w.err.p + 1;
         if (solver == 0) wrmf_pcg_kernel<<<std::min(nb, 2 * ctx->sm_count), CG_THREADS, smem_solve, s>>>(va, w.M.p);
         else chol_fn<<<nb, SV_THREADS, smem_solve, s>>>(va);
         MML_CUDA(cudaGetLastError());
+        if (overlap) MML_CUDA(cudaEventRecord(w.solve_done[x], s));
         if (launches) *launches += 2;
     }
     uint32_t h_err[2] = {0, 0};
@@ -902,21 +930,22 @@ static int32_t half_sweep_impl(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_p
 
 int32_t wrmf_tc_half_sweep(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_ptr, const int32_t* cols, const int32_t* order, int32_t n_rows,
                            float* W, const float* H, int32_t k, const double* HH, double alpha, double reg, int64_t* launches,
-                           float* debug_G_row0, bool factor_f64)
+                           float* debug_G_row0, int first_solver)
 {
-    // Solver ladder: preconditioned conjugate gradients (default) -> Cholesky with the single-precision factor -> with the double one, each
-    // tried only if the previous left a row unconverged (W is output only -- the CG kernel reads it as a starting guess, which
-    // affects the iteration count, not the result -- and H is untouched, so a repeat is safe). factor_f64 (mode
-    // MML_WRMF_TENSOR_F64) or MMLB200_WRMF_SOLVER = chol | chol64 start further down the ladder (parity tests, A/B runs).
+    // Solvers: 0 = preconditioned conjugate gradients + one exact refinement (MML_WRMF_TENSOR_PCG), 1 = Cholesky with the
+    // single-precision factor (default), 2 = with the double-precision factor (MML_WRMF_TENSOR_F64). A half-sweep that leaves
+    // a row unconverged is redone by the next solver down the ladder (W is output only -- the PCG kernel does not read it --
+    // and H is untouched, so a repeat is safe). MMLB200_WRMF_SOLVER = pcg | chol | chol64 overrides the first solver.
     static const int env_first = [] {
         const char* e = getenv("MMLB200_WRMF_SOLVER");
         if (e && strcmp(e, "chol64") == 0) return 2;
         if (e && strcmp(e, "chol") == 0) return 1;
+        if (e && strcmp(e, "pcg") == 0) return 0;
         const char* f = getenv("MMLB200_WRMF_FACTOR");
-        return (f && strcmp(f, "fp64") == 0) ? 2 : 0;
+        return (f && strcmp(f, "fp64") == 0) ? 2 : -1;
     }();
     uint32_t bad = 0;
-    for (int solver = factor_f64 ? 2 : env_first; solver <= 2; solver++) {
+    for (int solver = env_first >= 0 ? env_first : first_solver; solver <= 2; solver++) {
         MML_TRY(half_sweep_impl(ctx, work, row_ptr, cols, order, n_rows, W, H, k, HH, alpha, reg, launches, debug_G_row0, solver, &bad));
         if (bad == 0) return MML_OK;
     }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""WRMF config 3 (138k x 27k, 20M events, k = 128): the default conjugate-gradient row solver against the double-precision
-Cholesky solver with refinement against the exact operator (mode WRMF_TENSOR_F64, itself within 1e-6 of the oracle), from
-the same initial model, epoch by epoch: epoch time of both, and the largest relative row error of the CG result
+"""WRMF config 3 (138k x 27k, 20M events, k = 128): the preconditioned-CG row solver (mode WRMF_TENSOR_PCG) against the
+double-precision Cholesky solver with refinement against the exact operator (mode WRMF_TENSOR_F64, itself within 1e-6 of the
+oracle), epoch by epoch: epoch time of both, and the largest relative row error of the CG result
 (max over rows of |w_cg - w_ref|_inf / |w_ref|_inf; gate 1e-4) when both start the epoch from the SAME model.
 usage: python scripts/diag_wrmf_solvers.py [--epochs E] [--scale S]"""
 import argparse
@@ -32,7 +32,7 @@ def main():
         ref.set_model(U, V)            # both solvers start every epoch from the CG run's model
         engine.wrmf_set_mode(_capi.WRMF_TENSOR_F64)
         ref.iterate(); ref_ms = ref.stats()[1]
-        engine.wrmf_set_mode(_capi.WRMF_AUTO)
+        engine.wrmf_set_mode(_capi.WRMF_TENSOR_PCG)
         cg.iterate(); cg_ms = cg.stats()[1]
         U, V = cg.get_model()
         rU, rV = ref.get_model()

@@ -105,10 +105,11 @@ def test_tensor_core_gram_sum_is_fp32_accurate(eng, k):
     assert np.array_equal(Ug, U) and np.array_equal(Vg, V)              # the diagnostic leaves the model alone
 
 
-@pytest.mark.parametrize("mode", ["fp64", "tensor", "tensor_f64"])
+@pytest.mark.parametrize("mode", ["fp64", "tensor", "tensor_f64", "tensor_pcg"])
 def test_wrmf_paths_agree_on_a_larger_set(eng, mode):
     """The device paths (all-double CUDA cores; tcgen05 Gram sums with the single- or the double-precision Cholesky
-    factor) against the oracle on 3000 x 1200, k = 64 (rows up to ~1000 entries, empty rows, 2 epochs)."""
+    factor, or with the preconditioned-CG row solver) against the oracle on 3000 x 1200, k = 64 (rows up to ~1000
+    entries, empty rows, 2 epochs)."""
     engine, ctx = eng
     nu, ni, k = 3000, 1200, 64
     u, i = events(nu - 5, ni, 90000, 77)
@@ -116,7 +117,7 @@ def test_wrmf_paths_agree_on_a_larger_set(eng, mode):
     rng = O.Random(5)
     U = rng.init_normal(nu * k).reshape(nu, k); V = rng.init_normal(ni * k).reshape(ni, k)
     engine.wrmf_set_mode(dict(fp64=engine._capi.WRMF_FP64, tensor=engine._capi.WRMF_TENSOR,
-                              tensor_f64=engine._capi.WRMF_TENSOR_F64)[mode])
+                              tensor_f64=engine._capi.WRMF_TENSOR_F64, tensor_pcg=engine._capi.WRMF_TENSOR_PCG)[mode])
     try:
         m = engine.WrmfModel(ctx, f, k)
         m.set_model(U, V)
