@@ -319,59 +319,20 @@ __global__ void gather_entries_kernel(const uint32_t* __restrict__ perm, int64_t
     }
 }
 
-// head[e] = 1 where a user run starts inside its block (entries are sorted by block, then user)
-__global__ void strata_run_heads_kernel(const uint32_t* __restrict__ blk_sorted, const int32_t* __restrict__ ent_u, int64_t n,
-                                        uint32_t* __restrict__ head)
-{
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; t < n; t += stride) head[t] = (t == 0 || blk_sorted[t] != blk_sorted[t - 1] || ent_u[t] != ent_u[t - 1]) ? 1u : 0u;
-}
-
-// Async mode: the block's entries (sorted by user) are cut into one slice per worker at user boundaries, so that every user
-// row of the block belongs to exactly one worker. The workers of a warp run in lockstep (the warp iterates to its longest
-// slice and every user switch of any of its workers costs the whole warp its instructions), so the cut has two levels:
-// the block goes to the group's warps in pieces of equal COST = entries + run_cost x user runs (a warp's time), and a
-// warp's piece to its wpw workers in equal entry counts. cum_runs = exclusive scan of strata_run_heads_kernel's flags.
-// run_cost4 = 4 x the cost of a run in entries (0: plain equal-entry slices).
-__global__ void strata_split_kernel(const uint32_t* __restrict__ blk_ptr, int32_t n_blk, int32_t n_workers, int32_t wpw,
-                                    const int32_t* __restrict__ ent_u, const uint32_t* __restrict__ cum_runs, uint32_t run_cost4,
-                                    uint32_t* __restrict__ wptr)
+// Async mode: worker w of the CTA gets the w-th of n_workers equal slices of the block's entries (sorted by
+// user), cut at user boundaries so that every user row of the block belongs to exactly one worker.
+// (A two-level cut balancing entries + 2 x user runs per warp was measured and dropped: hand-over waits stayed at 12 % of
+// the CTA time, 14.59 ms against 14.50 ms per epoch -- the waits are not caused by uneven run counts.)
+__global__ void strata_split_kernel(const uint32_t* __restrict__ blk_ptr, int32_t n_blk, int32_t n_workers,
+                                    const int32_t* __restrict__ ent_u, uint32_t* __restrict__ wptr)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)n_blk * (n_workers + 1)) return;
     const int32_t blk = (int32_t)(t / (n_workers + 1)), w = (int32_t)(t % (n_workers + 1));
     const uint32_t beg = blk_ptr[blk], end = blk_ptr[blk + 1];
-    auto boundary = [&](uint32_t cut) {
-        while (cut > beg && cut < end && ent_u[cut] == ent_u[cut - 1]) cut++;
-        return cut;
-    };
-    auto warp_cut = [&](int32_t wi, int32_t n_warps) -> uint32_t {          // start of warp wi's piece
-        if (wi <= 0) return beg;
-        if (wi >= n_warps || beg == end) return end;
-        if (run_cost4 == 0 || cum_runs == nullptr)
-            return boundary(beg + (uint32_t)(((uint64_t)(end - beg) * (uint64_t)wi) / (uint64_t)n_warps));
-        const uint64_t r0 = cum_runs[beg];
-        const uint64_t total = 4ull * (end - beg) + (uint64_t)run_cost4 * (cum_runs[end] - r0);
-        const uint64_t target = total * (uint64_t)wi / (uint64_t)n_warps;
-        uint32_t lo = beg, hi = end;                                        // first e with cost(beg..e) >= target
-        while (lo < hi) {
-            const uint32_t mid = lo + (hi - lo) / 2;
-            const uint64_t c = 4ull * (mid - beg) + (uint64_t)run_cost4 * (cum_runs[mid] - r0);
-            if (c < target) lo = mid + 1; else hi = mid;
-        }
-        return boundary(lo);
-    };
-    const int32_t n_warps = (n_workers + wpw - 1) / wpw;
-    const int32_t wi = w / wpw, x = w % wpw;
-    uint32_t cut;
-    if (w >= n_workers) cut = end;
-    else {
-        const uint32_t a = warp_cut(wi, n_warps), b = warp_cut(wi + 1, n_warps);
-        const int32_t in_warp = min(wpw, n_workers - wi * wpw);
-        cut = x == 0 ? a : boundary(a + (uint32_t)(((uint64_t)(b - a) * (uint64_t)x) / (uint64_t)in_warp));
-        if (cut > b) cut = b;
-    }
+    uint32_t cut = beg + (uint32_t)(((uint64_t)(end - beg) * (uint64_t)w) / (uint64_t)n_workers);
+    if (w == n_workers) cut = end;
+    while (cut > beg && cut < end && ent_u[cut] == ent_u[cut - 1]) cut++;
     wptr[t] = cut;
 }
 
@@ -388,8 +349,6 @@ __global__ void user_key_kernel(const int32_t* __restrict__ users, const int32_t
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; t < n; t += stride) { const int32_t r = user_int[users[t]]; key[t] = r < 0 ? 0u : (uint32_t)r; }
 }
-
-static int async_lanes(int kp, int variant);
 
 static int32_t build_strata_async(Sgd& m, int32_t n_workers)
 {
@@ -431,20 +390,10 @@ static int32_t build_strata_async(Sgd& m, int32_t n_workers)
     MML_CUDA(cudaGetLastError());
     MML_TRY(m.wptr.alloc((size_t)n_blk * (n_workers + 1)));
     const int64_t nt = (int64_t)n_blk * (n_workers + 1);
-    // user runs per block prefix (for the cost-balanced cut); key still holds the sorted block ids
-    static const uint32_t run_cost4 = [] { const char* e = getenv("MMLB200_SGD_RUNCOST"); return e && *e ? (uint32_t)(4.0 * atof(e) + 0.5) : 8u; }();
-    DevBuf<uint32_t> head, cum;
-    const int wpw = 32 / async_lanes(m.kp, m.variant);
-    if (run_cost4 > 0 && n_workers > wpw) {
-        MML_TRY(head.alloc(n)); MML_TRY(cum.alloc((size_t)n + 1));
-        strata_run_heads_kernel<<<grid_n(n), 256, 0, s>>>(key.p, m.ent_u.p, n, head.p);
-        MML_CUDA(cudaGetLastError());
-        MML_TRY(exclusive_scan_u32(head.p, cum.p, n, s));
-    }
-    strata_split_kernel<<<(unsigned)ceil_div(nt, 256), 256, 0, s>>>(blk_ptr.p, n_blk, n_workers, wpw, m.ent_u.p, cum.p, cum.p ? run_cost4 : 0u, m.wptr.p);
+    strata_split_kernel<<<(unsigned)ceil_div(nt, 256), 256, 0, s>>>(blk_ptr.p, n_blk, n_workers, m.ent_u.p, m.wptr.p);
     MML_CUDA(cudaGetLastError());
     MML_CUDA(cudaStreamSynchronize(s));
-    m.launches += 16;
+    m.launches += 14;
     return MML_OK;
 }
 

@@ -17,6 +17,8 @@
 //      Otherwise the user is flagged and the caller re-runs it on the exact CUDA-core path (topn.cu).
 // Results are therefore bit-identical to the exact path, whatever the tensor cores round.
 #include "common.cuh"
+#include <chrono>
+#include <string>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -821,6 +823,19 @@ static int32_t topn_tc_batch(Ctx* ctx, TcCandidates& c, TcWork& w, int x, const 
     return MML_OK;
 }
 
+// MMLB200_TOPN_TIMES=1: host time stamps of one call (no synchronisation added), printed when the call returns
+struct TcTimes {
+    bool on; std::chrono::steady_clock::time_point t0; std::string log;
+    TcTimes() { static const bool e = [] { const char* v = getenv("MMLB200_TOPN_TIMES"); return v && *v && *v != '0'; }(); on = e; t0 = std::chrono::steady_clock::now(); }
+    void mark(const char* what) {
+        if (!on) return;
+        char buf[96];
+        snprintf(buf, sizeof(buf), " %s@%.1f", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        log += buf;
+    }
+    ~TcTimes() { if (on) fprintf(stderr, "[mmlb200 topn host ms]%s\n", log.c_str()); }
+};
+
 static bool tc_trace() { static int t = -1; if (t < 0) { const char* e = getenv("MMLB200_TRACE"); t = (e && *e && *e != '0') ? 1 : 0; } return t == 1; }
 struct TcPhase {
     cudaStream_t s; std::chrono::steady_clock::time_point t0;
@@ -845,6 +860,7 @@ int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
 {
     cudaStream_t s = ctx->stream, cs = ctx->copy_stream, os = ctx->out_stream;
     TcPhase ph(s);
+    TcTimes tt;
     TopnCache* cache = topn_cache(ctx);
     MML_CHECK(cache != nullptr, MML_ERR_ARG, "out of host memory");
     TcCandidates& c = cache->c;
@@ -860,11 +876,14 @@ int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
             max_ign = std::max(max_ign, ignore_ptr[std::min(b_lo + B, n_users)] - ignore_ptr[b_lo]);
     MML_TRY(tc_alloc_work(ctx, w, c, (int32_t)std::min<int64_t>(B, n_users), n_out, max_ign));
     ph.mark("workspace");
+    tt.mark("prepared");
     // batch bookkeeping for the retire step
     struct Pending { int64_t b_lo; int32_t nb; bool live; } pend[2] = {{0, 0, false}, {0, 0, false}};
     auto retire = [&](int x) -> int32_t {
         if (!pend[x].live) return MML_OK;
+        tt.mark("wait");
         MML_CUDA(cudaEventSynchronize(w.ev_out[x]));
+        tt.mark("got");
         const int64_t b_lo = pend[x].b_lo; const int32_t nb = pend[x].nb;
         MML_CHECK(w.h_err[x].p[0] == 0, MML_ERR_CUDA, "topn: tcgen05 pipeline timed out");
         memcpy(out_items + (size_t)b_lo * n_out, w.h_out_i[x].p, sizeof(int32_t) * (size_t)nb * n_out);
@@ -873,6 +892,7 @@ int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
         const uint8_t* rd = w.h_redo[x].p;
         for (int32_t t = 0; t < nb; t++) if (rd[t]) redo_users.push_back(b_lo + t);
         pend[x].live = false;
+        tt.mark("retired");
         return MML_OK;
     };
     int bi = 0;
@@ -898,9 +918,11 @@ int32_t topn_tc_run(Ctx* ctx, const float* d_U, int32_t n_model_users, const flo
         MML_CUDA(cudaEventRecord(w.ev_in[x], cs));
         MML_CUDA(cudaStreamWaitEvent(s, w.ev_in[x], 0));
         ph.mark("batch H2D");
+        tt.mark("staged");
         MML_TRY(topn_tc_batch(ctx, c, w, x, d_U, n_model_users, d_V, n_model_items, k, nb, n, n_out, d_cand, nib, launches));
         MML_CUDA(cudaEventRecord(w.ev_done[x], s));
         ph.mark("batch kernels");
+        tt.mark("issued");
         MML_CUDA(cudaStreamWaitEvent(os, w.ev_done[x], 0));
         MML_CUDA(cudaMemcpyAsync(w.h_out_i[x].p, w.out_i[x].p, sizeof(int32_t) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, os));
         MML_CUDA(cudaMemcpyAsync(w.h_out_s[x].p, w.out_s[x].p, sizeof(float) * (size_t)nb * n_out, cudaMemcpyDeviceToHost, os));

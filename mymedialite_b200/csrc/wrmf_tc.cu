@@ -835,18 +835,12 @@ __global__ void __launch_bounds__(CG_THREADS, 2) wrmf_pcg_kernel(const SolveArgs
 bool wrmf_tc_eligible(int32_t k) { return k >= 4 && k <= 128 && (k % 4) == 0; }
 
 struct WrmfTcWork {
-    DevBuf<float> G[2]; DevBuf<double> bsum[2]; DevBuf<uint32_t> err;   // per-batch Gram sums and right-hand sides, double buffered
+    DevBuf<float> G; DevBuf<double> bsum; DevBuf<uint32_t> err;
     DevBuf<float> M; DevBuf<double> Mscratch;          // preconditioner of the PCG solver and its work space
-    cudaEvent_t syrk_done[2] = {nullptr, nullptr}, solve_done[2] = {nullptr, nullptr};
     int32_t cap_rows = 0;
 };
 WrmfTcWork* wrmf_tc_work_create() { return new (std::nothrow) WrmfTcWork(); }
-void wrmf_tc_work_destroy(WrmfTcWork* w)
-{
-    if (!w) return;
-    for (int x = 0; x < 2; x++) { if (w->syrk_done[x]) cudaEventDestroy(w->syrk_done[x]); if (w->solve_done[x]) cudaEventDestroy(w->solve_done[x]); }
-    delete w;
-}
+void wrmf_tc_work_destroy(WrmfTcWork* w) { delete w; }
 
 // One half-sweep's per-row systems: W[u] <- solve for every row of `order`. HH (fp64, k x k) is on the device.
 static int32_t half_sweep_impl(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_ptr, const int32_t* cols, const int32_t* order, int32_t n_rows,
@@ -856,23 +850,16 @@ static int32_t half_sweep_impl(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_p
     cudaStream_t s = ctx->stream;
     MML_CHECK(work != nullptr, MML_ERR_STATE, "wrmf: no tensor-path workspace");
     WrmfTcWork& w = *work;
-    // Rows per batch: G 1 GiB, twice. The Gram-sum kernel (gather + tensor pipe, one CTA per SM) of batch b + 1 runs on a
-    // second stream UNDER the row solves of batch b (latency bound: barrier-separated panel steps), which leave the SM's
-    // issue slots, L2 path and tensor pipe mostly idle; 129 KB + 2 x 39 KB of shared memory fit one SM together.
+    // Rows per batch: G 1 GiB. (Running the next batch's Gram sums on a second stream under this batch's solves was tried:
+    // the solve kernel's three CTAs per SM hold 61k of the 64k registers, so the Gram kernel's CTAs only get an SM once the
+    // solves have drained -- no overlap, 52.0 ms either way.)
     const int32_t B = 16384;
     const int32_t cap = std::min(B, std::max(n_rows, 1));
     if (w.cap_rows < cap) {
-        for (int x = 0; x < 2; x++) { MML_TRY(w.G[x].alloc((size_t)cap * WS_KP * WS_KP)); MML_TRY(w.bsum[x].alloc((size_t)cap * WS_KP)); }
+        MML_TRY(w.G.alloc((size_t)cap * WS_KP * WS_KP)); MML_TRY(w.bsum.alloc((size_t)cap * WS_KP));
         if (!w.err.p) MML_TRY(w.err.alloc(2));
         w.cap_rows = cap;
     }
-    for (int x = 0; x < 2; x++)
-        if (!w.syrk_done[x]) {
-            MML_CUDA(cudaEventCreateWithFlags(&w.syrk_done[x], cudaEventDisableTiming));
-            MML_CUDA(cudaEventCreateWithFlags(&w.solve_done[x], cudaEventDisableTiming));
-        }
-    cudaStream_t s2 = ctx->aux_stream;
-    static const bool overlap = [] { const char* e = getenv("MMLB200_WRMF_OVERLAP"); return !(e && *e == '0'); }();
     MML_CUDA(cudaMemsetAsync(w.err.p, 0, 2 * sizeof(uint32_t), s));
     const size_t smem_syrk = (size_t)WS_STAGES * 2 * WS_TILE + 1024;
     MML_CUDA(cudaFuncSetAttribute((const void*)wrmf_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_syrk));
@@ -893,31 +880,22 @@ static int32_t half_sweep_impl(Ctx* ctx, WrmfTcWork* work, const uint32_t* row_p
         MML_CUDA(cudaGetLastError());
         if (launches) *launches += 1;
     }
-    // everything enqueued on `s` so far (HH, the error words, the preconditioner) precedes the first Gram sums on s2
-    cudaEvent_t ev_start = w.solve_done[0];
-    if (overlap) { MML_CUDA(cudaEventRecord(ev_start, s)); MML_CUDA(cudaStreamWaitEvent(s2, ev_start, 0)); }
-    int bi = 0;
-    for (int32_t q_lo = 0; q_lo < n_rows; q_lo += B, bi++) {
+    for (int32_t q_lo = 0; q_lo < n_rows; q_lo += B) {
         const int32_t q_hi = std::min(n_rows, q_lo + B), nb = q_hi - q_lo;
-        const int x = bi & 1;
-        cudaStream_t sy = overlap ? s2 : s;
-        if (overlap && bi >= 2) MML_CUDA(cudaStreamWaitEvent(sy, w.solve_done[x], 0));     // buffer x was read by the solves of batch bi - 2
-        MML_CUDA(cudaMemsetAsync(w.bsum[x].p, 0, sizeof(double) * (size_t)nb * WS_KP, sy));
+        MML_CUDA(cudaMemsetAsync(w.bsum.p, 0, sizeof(double) * (size_t)nb * WS_KP, s));
         SyrkArgs sa{};
         sa.row_ptr = row_ptr; sa.cols = cols; sa.order = order; sa.q_lo = q_lo; sa.q_hi = q_hi; sa.H = H; sa.k = k;
-        sa.G = w.G[x].p; sa.bsum = w.bsum[x].p; sa.err = w.err.p;
-        wrmf_syrk_kernel<<<std::min(nb, ctx->sm_count), WS_THREADS, smem_syrk, sy>>>(sa);
+        sa.G = w.G.p; sa.bsum = w.bsum.p; sa.err = w.err.p;
+        wrmf_syrk_kernel<<<std::min(nb, ctx->sm_count), WS_THREADS, smem_syrk, s>>>(sa);
         MML_CUDA(cudaGetLastError());
-        if (overlap) { MML_CUDA(cudaEventRecord(w.syrk_done[x], sy)); MML_CUDA(cudaStreamWaitEvent(s, w.syrk_done[x], 0)); }
         if (debug_G_row0 && q_lo == 0)
-            MML_CUDA(cudaMemcpyAsync(debug_G_row0, w.G[x].p, sizeof(float) * WS_KP * WS_KP, cudaMemcpyDeviceToHost, s));
+            MML_CUDA(cudaMemcpyAsync(debug_G_row0, w.G.p, sizeof(float) * WS_KP * WS_KP, cudaMemcpyDeviceToHost, s));
         SolveArgs va{};
-        va.row_ptr = row_ptr; va.cols = cols; va.order = order; va.q_lo = q_lo; va.q_hi = q_hi; va.G = w.G[x].p; va.bsum = w.bsum[x].p; va.HH = HH;
+        va.row_ptr = row_ptr; va.cols = cols; va.order = order; va.q_lo = q_lo; va.q_hi = q_hi; va.G = w.G.p; va.bsum = w.bsum.p; va.HH = HH;
         va.H = H; va.alpha = alpha; va.reg = reg; va.k = k; va.W = W; va.fail = w.err.p + 1;
         if (solver == 0) wrmf_pcg_kernel<<<std::min(nb, 2 * ctx->sm_count), CG_THREADS, smem_solve, s>>>(va, w.M.p);
         else chol_fn<<<nb, SV_THREADS, smem_solve, s>>>(va);
         MML_CUDA(cudaGetLastError());
-        if (overlap) MML_CUDA(cudaEventRecord(w.solve_done[x], s));
         if (launches) *launches += 2;
     }
     uint32_t h_err[2] = {0, 0};

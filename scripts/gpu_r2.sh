@@ -29,6 +29,8 @@ for step in "$@"; do
     wrmfncu)  ( CMD="python scripts/bench_wrmf.py --epochs 2"
                 timeout 300 $CMD > gpurun_out/${tag}_wrmf_plain.log 2>&1 &&
                 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'wrmf_|gram_' --csv --log-file gpurun_out/${tag}_wrmf_launches.csv $CMD ) > $log 2>&1 ;;
+    memcheck)  ( timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 3 python scripts/sanitize_case.py ) > $log 2>&1 ;;
+    racecheck) ( timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 3 python scripts/sanitize_case.py ) > $log 2>&1 ;;
     hosttest) ( LD_LIBRARY_PATH=/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/cuda_runtime/lib:$LD_LIBRARY_PATH timeout 60 tests/cpp/build/host_test gpu tests/golden/example.train tests/golden/example.test gpurun_out ) > $log 2>&1 ;;
     *)        ( eval "timeout 900 $step" ) > $log 2>&1 ;;
   esac
