@@ -126,6 +126,7 @@ struct Ctx {
     void* flush_buf = nullptr;   // mml_ctx_flush_l2
     int flush_val = 0;
     void* topn_cache = nullptr;  // Recommend() workspace of this context, grow-only (topn_tc.cu); freed by topn_cache_destroy
+    void* topn_exact_cache = nullptr;     // the same for the exact CUDA-core path (topn.cu)
     cudaStream_t out_stream = nullptr;    // device -> host result staging that may overlap the next batch's kernels
     cudaStream_t aux_stream = nullptr;    // a second kernel stream (WRMF: the next batch's Gram sums under this batch's solves)
     // One-process multi-GPU (mml_ctx_create with n_gpus > 1, the NumGpus property of the host classes): this context is
@@ -160,6 +161,7 @@ struct Ratings {
 Ratings* ratings_of(mml_ratings* h);
 int32_t dist_destroy(Ctx* c);
 void topn_cache_destroy(Ctx* c);
+void topn_exact_cache_destroy(Ctx* c);
 int32_t dist_allreduce_u32(Ctx* c, uint32_t* d_buf, size_t n);
 int32_t dist_allreduce_f64(Ctx* c, double* d_buf, size_t n);
 int32_t dist_allreduce_f64_max(Ctx* c, double* d_buf, size_t n);

@@ -193,6 +193,7 @@ extern "C" int32_t mml_ctx_destroy(mml_ctx* ctx)
     cudaSetDevice(ctx->c.device);
     dist_destroy(&ctx->c);
     topn_cache_destroy(&ctx->c);
+    topn_exact_cache_destroy(&ctx->c);
     if (ctx->c.out_stream) cudaStreamDestroy(ctx->c.out_stream);
     if (ctx->c.aux_stream) cudaStreamDestroy(ctx->c.aux_stream);
     if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);

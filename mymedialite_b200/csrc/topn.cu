@@ -224,6 +224,19 @@ __global__ void rank_emit_kernel(const uint32_t* __restrict__ val, const float* 
     if (threadIdx.x == 0) out_counts[b] = s_cnt;     // qualifying entries sort first, so they are rows 0 .. count-1
 }
 
+// Buffers of the exact path, kept by the context between calls (grow-only).
+struct ExactWork {
+    DevBuf<int32_t> d_cand, d_pos_of, d_next, d_users, d_ign_idx, d_out_i, d_out_c;
+    DevBuf<int64_t> d_ign_ptr;
+    DevBuf<float> d_scores, d_out_s;
+};
+void topn_exact_cache_destroy(Ctx* ctx)
+{
+    delete reinterpret_cast<ExactWork*>(ctx->topn_exact_cache);
+    ctx->topn_exact_cache = nullptr;
+}
+
+
 // d_U / d_V: model on the device. All other pointers: host. Exact scoring on the CUDA cores.
 static int32_t topn_exact_device(Ctx* ctx, const float* d_U, int32_t n_model_users, const float* d_V, int32_t n_model_items, int32_t k,
                     const int32_t* users, int64_t n_users, int32_t n,
@@ -237,10 +250,16 @@ static int32_t topn_exact_device(Ctx* ctx, const float* d_U, int32_t n_model_use
     const int32_t n_out = n < 0 ? (int32_t)n_cand : (int32_t)std::min<int64_t>(n, n_cand);
     if (n_cand == 0 || n_out == 0) { for (int64_t b = 0; b < n_users; b++) out_counts[b] = 0; return MML_OK; }
     MML_CHECK(n_cand < ((int64_t)1 << 31), MML_ERR_ARG, "topn: too many candidates");
+    // buffers: grow-only members of the context (the tensor path sends its few undecided users here on every call: a dozen
+    // cudaMalloc / cudaFree pairs per call cost 30-150 ms of wall clock on a busy box against 104 ms of device time)
+    if (!ctx->topn_exact_cache) ctx->topn_exact_cache = new (std::nothrow) ExactWork();
+    MML_CHECK(ctx->topn_exact_cache != nullptr, MML_ERR_ARG, "out of host memory");
+    ExactWork& xw = *reinterpret_cast<ExactWork*>(ctx->topn_exact_cache);
+    DevBuf<int32_t>& d_cand = xw.d_cand; DevBuf<int32_t>& d_pos_of = xw.d_pos_of; DevBuf<int32_t>& d_next = xw.d_next;
+    DevBuf<int32_t>& d_users = xw.d_users; DevBuf<int32_t>& d_ign_idx = xw.d_ign_idx; DevBuf<int64_t>& d_ign_ptr = xw.d_ign_ptr;
     // candidate list and the position maps for ignore_items
-    DevBuf<int32_t> d_cand, d_pos_of, d_next, d_users, d_ign_idx; DevBuf<int64_t> d_ign_ptr;
     if (candidates) {
-        MML_TRY(d_cand.alloc(n_cand));
+        MML_TRY(d_cand.ensure(n_cand));
         MML_CUDA(cudaMemcpyAsync(d_cand.p, candidates, sizeof(int32_t) * n_cand, cudaMemcpyHostToDevice, s));
     }
     int32_t n_pos_of = 0;
@@ -254,15 +273,15 @@ static int32_t topn_exact_device(Ctx* ctx, const float* d_U, int32_t n_model_use
             if (item < 0) continue;
             next[c] = pos_of[item]; pos_of[item] = (int32_t)c;
         }
-        MML_TRY(d_pos_of.alloc(pos_of.size())); MML_TRY(d_next.alloc(n_cand));
-        MML_TRY(d_ign_ptr.alloc((size_t)n_users + 1)); MML_TRY(d_ign_idx.alloc((size_t)ignore_ptr[n_users]));
+        MML_TRY(d_pos_of.ensure(pos_of.size())); MML_TRY(d_next.ensure(n_cand));
+        MML_TRY(d_ign_ptr.ensure((size_t)n_users + 1)); MML_TRY(d_ign_idx.ensure((size_t)ignore_ptr[n_users]));
         MML_CUDA(cudaMemcpyAsync(d_pos_of.p, pos_of.data(), sizeof(int32_t) * pos_of.size(), cudaMemcpyHostToDevice, s));
         MML_CUDA(cudaMemcpyAsync(d_next.p, next.data(), sizeof(int32_t) * n_cand, cudaMemcpyHostToDevice, s));
         MML_CUDA(cudaMemcpyAsync(d_ign_ptr.p, ignore_ptr, sizeof(int64_t) * ((size_t)n_users + 1), cudaMemcpyHostToDevice, s));
         MML_CUDA(cudaMemcpyAsync(d_ign_idx.p, ignore_idx, sizeof(int32_t) * (size_t)ignore_ptr[n_users], cudaMemcpyHostToDevice, s));
         MML_CUDA(cudaStreamSynchronize(s));
     }
-    MML_TRY(d_users.alloc(n_users));
+    MML_TRY(d_users.ensure(n_users));
     MML_CUDA(cudaMemcpyAsync(d_users.p, users, sizeof(int32_t) * n_users, cudaMemcpyHostToDevice, s));
 
     const bool fast = n > 0 && n_out <= MAXN;
@@ -271,10 +290,10 @@ static int32_t topn_exact_device(Ctx* ctx, const float* d_U, int32_t n_model_use
     if (!fast) B = std::max<int64_t>(1, std::min<int64_t>(B, (((int64_t)1 << 31) - 1) / n_cand));
     B = std::min<int64_t>(B, n_users);
     B = std::min<int64_t>(B, 65535 * (int64_t)TS);
-    DevBuf<float> d_scores, d_out_s; DevBuf<int32_t> d_out_i, d_out_c;
-    MML_TRY(d_scores.alloc((size_t)B * n_cand));
-    MML_TRY(d_out_s.alloc((size_t)B * n_out)); MML_TRY(d_out_i.alloc((size_t)B * n_out)); MML_TRY(d_out_c.alloc(B));
-    DevBuf<uint32_t> key, val, k2, v2;
+    DevBuf<float>& d_scores = xw.d_scores; DevBuf<float>& d_out_s = xw.d_out_s; DevBuf<int32_t>& d_out_i = xw.d_out_i; DevBuf<int32_t>& d_out_c = xw.d_out_c;
+    MML_TRY(d_scores.ensure((size_t)B * n_cand));
+    MML_TRY(d_out_s.ensure((size_t)B * n_out)); MML_TRY(d_out_i.ensure((size_t)B * n_out)); MML_TRY(d_out_c.ensure(B));
+    DevBuf<uint32_t> key, val, k2, v2;          // the n = -1 (full ranking) path sorts B x n_cand keys: per call
     if (!fast) { MML_TRY(key.alloc((size_t)B * n_cand)); MML_TRY(val.alloc((size_t)B * n_cand)); MML_TRY(k2.alloc((size_t)B * n_cand)); MML_TRY(v2.alloc((size_t)B * n_cand)); }
     for (int64_t b_lo = 0; b_lo < n_users; b_lo += B) {
         const int32_t nb = (int32_t)std::min<int64_t>(B, n_users - b_lo);

@@ -1,5 +1,8 @@
-"""MyMediaLite's text model format (IO/Model.cs:85-114, IO/MatrixExtensions.cs:31-89, IO/VectorExtensions.cs:40-60), so
-that models trained on the GPU load into stock MyMediaLite and vice versa."""
+"""MyMediaLite's text model format (IO/Model.cs:85-114, IO/MatrixExtensions.cs:31-89, IO/VectorExtensions.cs:40-60): the
+layout after the two header lines is the stock classes' own, so `LoadModel` on an existing instance of the corresponding
+class reads a file either side wrote (Model.cs:100-114 only warns about the type name). The header names the Cuda* class,
+so the by-name route `Model.Load(filename)` (IO/Model.cs:67-83) resolves these files only where the Cuda* classes are
+compiled into MyMediaLite.dll."""
 import math
 
 import numpy as np

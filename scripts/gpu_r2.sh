@@ -32,7 +32,7 @@ for step in "$@"; do
     memcheck)  ( timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 3 python scripts/sanitize_case.py ) > $log 2>&1 ;;
     racecheck) ( timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 3 python scripts/sanitize_case.py ) > $log 2>&1 ;;
     hosttest) ( LD_LIBRARY_PATH=/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/cuda_runtime/lib:$LD_LIBRARY_PATH timeout 60 tests/cpp/build/host_test gpu tests/golden/example.train tests/golden/example.test gpurun_out ) > $log 2>&1 ;;
-    *)        ( eval "timeout 900 $step" ) > $log 2>&1 ;;
+    *)        ( eval "timeout 900 env $step" ) > $log 2>&1 ;;
   esac
   echo "rc=$?" >> $log
   echo "== $step: $(tail -n 1 $log)"; tail -n 4 $log | head -n 3
