@@ -165,7 +165,7 @@ void topn_exact_cache_destroy(Ctx* c);
 int32_t dist_allreduce_u32(Ctx* c, uint32_t* d_buf, size_t n);
 int32_t dist_allreduce_f64(Ctx* c, double* d_buf, size_t n);
 int32_t dist_allreduce_f64_max(Ctx* c, double* d_buf, size_t n);
-int32_t dist_ring_exchange(Ctx* c, const float* send_a, size_t n_send_a, const float* send_b, size_t n_send_b, int to,
+int32_t dist_ring_exchange(Ctx* c, cudaStream_t stream, const float* send_a, size_t n_send_a, const float* send_b, size_t n_send_b, int to,
                            float* recv_a, size_t n_recv_a, float* recv_b, size_t n_recv_b, int from);
 int32_t dist_broadcast_f32(Ctx* c, float* d_buf, size_t n, int root);
 int32_t dist_group_start();

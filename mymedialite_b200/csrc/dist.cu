@@ -97,16 +97,16 @@ int32_t dist_allreduce_f64_max(Ctx* c, double* d_buf, size_t n)
 }
 
 // One ring step: send [send_a, send_b] to `to`, receive into [recv_a, recv_b] from `from`, grouped.
-int32_t dist_ring_exchange(Ctx* c, const float* send_a, size_t n_send_a, const float* send_b, size_t n_send_b, int to,
+int32_t dist_ring_exchange(Ctx* c, cudaStream_t stream, const float* send_a, size_t n_send_a, const float* send_b, size_t n_send_b, int to,
                            float* recv_a, size_t n_recv_a, float* recv_b, size_t n_recv_b, int from)
 {
     if (c->n_gpus <= 1) return MML_OK;
     ncclComm_t comm = (ncclComm_t)c->comm;
     MML_NCCL(ncclGroupStart());
-    if (n_send_a) MML_NCCL(ncclSend(send_a, n_send_a, ncclFloat, to, comm, c->stream));
-    if (n_send_b) MML_NCCL(ncclSend(send_b, n_send_b, ncclFloat, to, comm, c->stream));
-    if (n_recv_a) MML_NCCL(ncclRecv(recv_a, n_recv_a, ncclFloat, from, comm, c->stream));
-    if (n_recv_b) MML_NCCL(ncclRecv(recv_b, n_recv_b, ncclFloat, from, comm, c->stream));
+    if (n_send_a) MML_NCCL(ncclSend(send_a, n_send_a, ncclFloat, to, comm, stream));
+    if (n_send_b) MML_NCCL(ncclSend(send_b, n_send_b, ncclFloat, to, comm, stream));
+    if (n_recv_a) MML_NCCL(ncclRecv(recv_a, n_recv_a, ncclFloat, from, comm, stream));
+    if (n_recv_b) MML_NCCL(ncclRecv(recv_b, n_recv_b, ncclFloat, from, comm, stream));
     MML_NCCL(ncclGroupEnd());
     return MML_OK;
 }

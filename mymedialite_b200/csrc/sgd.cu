@@ -355,7 +355,7 @@ static int32_t build_strata_async(Sgd& m, int32_t n_workers)
     Ratings& r = *m.ratings;
     cudaStream_t s = m.ctx->stream;
     const int64_t n = r.n;
-    const int64_t n_blk64 = (int64_t)m.R * m.G * m.G;
+    const int64_t n_blk64 = (int64_t)m.RB * m.G * m.G;
     MML_CHECK(n_blk64 * (n_workers + 1) < ((int64_t)1 << 31), MML_ERR_ARG, "strata: %lld blocks is too many (G=%d)", (long long)n_blk64, m.G);
     const int32_t n_blk = (int32_t)n_blk64;
     m.n_blk = n_blk;
@@ -402,7 +402,7 @@ static int32_t build_strata(Sgd& m, int32_t nu_max, int32_t nr_max)
     Ratings& r = *m.ratings;
     cudaStream_t s = m.ctx->stream;
     const int64_t n = r.n;
-    const int64_t n_blk64 = (int64_t)m.R * m.G * m.G;
+    const int64_t n_blk64 = (int64_t)m.RB * m.G * m.G;
     MML_CHECK(n_blk64 < ((int64_t)1 << (32 - COLOR_BITS)), MML_ERR_ARG, "strata: %lld blocks is too many (G=%d)", (long long)n_blk64, m.G);
     const int32_t n_blk = (int32_t)n_blk64;
     m.n_blk = n_blk;
@@ -1704,10 +1704,10 @@ static int32_t sync_items(Sgd& m)
 {
     if (m.R <= 1 || !m.items_dirty) return MML_OK;
     MML_TRY(dist_group_start());
-    for (int B = 0; B < m.R; B++) {
+    for (int B = 0; B < m.RB; B++) {        // block B is at home on rank B / split after an epoch
         const int32_t lo = m.h_item_ptr[(size_t)B * m.G], hi = m.h_item_ptr[(size_t)(B + 1) * m.G];
-        MML_TRY(dist_broadcast_f32(m.ctx, m.Q.p + (size_t)lo * m.kp, (size_t)(hi - lo) * m.kp, B));
-        MML_TRY(dist_broadcast_f32(m.ctx, m.bi.p + lo, (size_t)(hi - lo), B));
+        MML_TRY(dist_broadcast_f32(m.ctx, m.Q.p + (size_t)lo * m.kp, (size_t)(hi - lo) * m.kp, B / m.split));
+        MML_TRY(dist_broadcast_f32(m.ctx, m.bi.p + lo, (size_t)(hi - lo), B / m.split));
     }
     MML_TRY(dist_group_end());
     m.items_dirty = false;
@@ -1907,17 +1907,25 @@ static int32_t run_dsgd_epoch(Sgd& m, const int32_t* h_seq)
         seen[seq[t]] = 1;
     }
     const int threads = m.W * 32;
-    // GPU-level sub-epochs: in sub-epoch S this rank works on item block B = (S + rank) mod R, then passes the
-    // block (factor rows + biases) to rank - 1 and takes the next one from rank + 1 -- the reference's block
-    // schedule (BiasedMatrixFactorization.cs:213-214) with GPUs in place of threads. After R sub-epochs every
-    // block is back on its home rank. R = 1: one pass, no exchange.
+    // GPU-level sub-epochs -- the reference's block schedule (BiasedMatrixFactorization.cs:213-214) with GPUs in place of
+    // threads. The item matrix is cut into RB = split x R blocks (split = 2 when R > 1); rank r starts the epoch holding its
+    // home blocks split*r .. split*r + split-1. In sub-epoch S' it trains on block B = (S' + split*r) mod RB (one persistent
+    // launch) and then, ON A SECOND STREAM, sends B to rank r - 1 and receives block B + split from rank r + 1 -- the block it
+    // needs in sub-epoch S' + split, which rank r + 1 has just finished. With split = 2 a block therefore has a whole
+    // sub-epoch to travel (and a late neighbour a whole sub-epoch of slack) while this rank trains on its other block; the
+    // launch of S' + 2 waits for the exchange of S' only. After RB sub-epochs every block is back on its home rank.
+    // (split = 1: the block needed next is finished by the neighbour at the same moment -- the exchange cannot overlap.)
     static const bool trace = [] { const char* e = getenv("MMLB200_TRACE"); return e && *e && *e != '0'; }();
+    const int RB = m.RB, split = m.split;
+    cudaStream_t xs = m.R > 1 ? m.ctx->aux_stream : s;
     std::vector<cudaEvent_t> tev;
-    if (trace && m.R > 1) { tev.resize((size_t)3 * m.R); for (auto& e : tev) cudaEventCreate(&e); }
-    for (int S = 0; S < m.R; S++) {
-        const int B = (S + m.rank) % m.R;
+    if (trace && m.R > 1) { tev.resize((size_t)2 * RB + 1); for (auto& e : tev) cudaEventCreate(&e); }
+    if (!tev.empty()) cudaEventRecord(tev[2 * RB], s);
+    for (int S = 0; S < RB; S++) {
+        const int B = (S + split * m.rank) % RB;
         SgdArgs a = make_args(m, B);
-        if (!tev.empty()) cudaEventRecord(tev[3 * S], s);
+        if (m.R > 1 && S >= split) MML_CUDA(cudaStreamWaitEvent(s, m.ev_xchg[S % split], 0));     // block B has arrived
+        if (!tev.empty()) cudaEventRecord(tev[2 * S], s);
         if (m.p.persistent) {
             DevBuf<int32_t>& dseq = m.d_index;   // reuse: serial index cache is unused in DSGD mode
             if ((int64_t)dseq.n < m.G) MML_TRY(dseq.alloc(m.G));
@@ -1934,28 +1942,33 @@ static int32_t run_dsgd_epoch(Sgd& m, const int32_t* h_seq)
             }
             MML_CUDA(cudaGetLastError());
         }
-        if (!tev.empty()) cudaEventRecord(tev[3 * S + 1], s);
+        if (!tev.empty()) cudaEventRecord(tev[2 * S + 1], s);
         if (m.R > 1) {
-            const int Bn = (B + 1) % m.R;
+            MML_CUDA(cudaEventRecord(m.ev_kern[S % split], s));
+            MML_CUDA(cudaStreamWaitEvent(xs, m.ev_kern[S % split], 0));
+            const int Bn = (B + split) % RB;
             const int32_t s_lo = m.h_item_ptr[(size_t)B * m.G], s_hi = m.h_item_ptr[(size_t)(B + 1) * m.G];
             const int32_t r_lo = m.h_item_ptr[(size_t)Bn * m.G], r_hi = m.h_item_ptr[(size_t)(Bn + 1) * m.G];
-            MML_TRY(dist_ring_exchange(m.ctx, m.Q.p + (size_t)s_lo * m.kp, (size_t)(s_hi - s_lo) * m.kp, m.bi.p + s_lo, (size_t)(s_hi - s_lo),
+            MML_TRY(dist_ring_exchange(m.ctx, xs, m.Q.p + (size_t)s_lo * m.kp, (size_t)(s_hi - s_lo) * m.kp, m.bi.p + s_lo, (size_t)(s_hi - s_lo),
                                        (m.rank + m.R - 1) % m.R,
                                        m.Q.p + (size_t)r_lo * m.kp, (size_t)(r_hi - r_lo) * m.kp, m.bi.p + r_lo, (size_t)(r_hi - r_lo),
                                        (m.rank + 1) % m.R));
+            MML_CUDA(cudaEventRecord(m.ev_xchg[S % split], xs));
         }
-        if (!tev.empty()) cudaEventRecord(tev[3 * S + 2], s);
     }
+    if (m.R > 1)       // the last exchanges bring the home blocks back: the epoch (and its timing) ends when they have landed
+        for (int x = 0; x < split; x++) MML_CUDA(cudaStreamWaitEvent(s, m.ev_xchg[x], 0));
     if (!tev.empty()) {
+        cudaEvent_t e_end;
+        cudaEventCreate(&e_end);
+        cudaEventRecord(e_end, s);
         cudaStreamSynchronize(s);
-        float tk = 0.f, tx = 0.f, tg = 0.f;
-        for (int S = 0; S < m.R; S++) {
-            float x = 0.f;
-            cudaEventElapsedTime(&x, tev[3 * S], tev[3 * S + 1]); tk += x;
-            cudaEventElapsedTime(&x, tev[3 * S + 1], tev[3 * S + 2]); tx += x;
-            if (S + 1 < m.R) { cudaEventElapsedTime(&x, tev[3 * S + 2], tev[3 * S + 3]); tg += x; }
-        }
-        fprintf(stderr, "[mmlb200 sgd rank %d] epoch: kernels %.3f ms, ring exchanges %.3f ms, gaps %.3f ms\n", m.rank, tk, tx, tg);
+        float tk = 0.f, tot = 0.f;
+        for (int S = 0; S < RB; S++) { float x = 0.f; cudaEventElapsedTime(&x, tev[2 * S], tev[2 * S + 1]); tk += x; }
+        cudaEventElapsedTime(&tot, tev[2 * RB], e_end);
+        fprintf(stderr, "[mmlb200 sgd rank %d] epoch %.3f ms: %d sub-epoch kernels %.3f ms, waiting for item blocks %.3f ms\n",
+                m.rank, tot, RB, tk, tot - tk);
+        cudaEventDestroy(e_end);
         for (auto& e : tev) cudaEventDestroy(e);
     }
     if (m.R > 1) m.items_dirty = true;
@@ -2053,6 +2066,11 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
     m.kp = m.k <= 32 ? 32 : (m.k <= 64 ? 64 : (m.k <= 128 ? 128 : 256));
     m.kpl = m.kp / 32;
     m.R = std::max(ctx->n_gpus, 1); m.rank = ctx->rank;
+    {   // item blocks per rank: two, so that the ring step of one overlaps the training of the other (MMLB200_RING_SPLIT=1: one)
+        const char* e = getenv("MMLB200_RING_SPLIT");
+        m.split = m.R > 1 ? ((e && *e == '1') ? 1 : 2) : 1;
+        m.RB = m.R * m.split;
+    }
     cudaStream_t s = ctx->stream;
     int32_t st = MML_OK;
     do {
@@ -2127,11 +2145,11 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
         size_t need = 0;
         int64_t max_rows = 0;
         for (int attempt = 0; attempt < 2; attempt++) {
-            build_group_map(m.items, r->n_items(), ci.data(), dsgd ? item_perm : nullptr, m.R, -1, m.G, 1, rule, hot_min, &m.h_hot_cnt);
+            build_group_map(m.items, r->n_items(), ci.data(), dsgd ? item_perm : nullptr, m.RB, -1, m.G, 1, rule, hot_min, &m.h_hot_cnt);
             m.h_item_ptr.assign(m.items.grp_ptr.begin(), m.items.grp_ptr.end());   // [R * G + 1]
             max_rows = 0;
             m.n_hot = 0;
-            for (int32_t g = 0; g < m.R * m.G; g++) {
+            for (int32_t g = 0; g < m.RB * m.G; g++) {
                 max_rows = std::max<int64_t>(max_rows, (int64_t)(m.h_item_ptr[g + 1] - m.h_item_ptr[g]) + (int64_t)m.h_hot_cnt[g] * m.hot_copies);
                 m.n_hot += m.h_hot_cnt[g];
             }
@@ -2202,6 +2220,10 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
             }
             m.epoch_base = 0;
         }
+        for (int x = 0; x < 2 && m.R > 1; x++)
+            if (cudaEventCreateWithFlags(&m.ev_kern[x], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&m.ev_xchg[x], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate failed"); st = MML_ERR_CUDA; }
+        if (st) break;
         if (cudaEventCreate(&m.ev0) != cudaSuccess || cudaEventCreate(&m.ev1) != cudaSuccess) {
             set_error("cudaEventCreate failed"); st = MML_ERR_CUDA; break;
         }
@@ -2227,6 +2249,7 @@ extern "C" int32_t mml_sgd_destroy(mml_sgd* h)
     cudaStreamSynchronize(h->m.ctx->stream);
     if (h->m.ev0) cudaEventDestroy(h->m.ev0);
     if (h->m.ev1) cudaEventDestroy(h->m.ev1);
+    for (int x = 0; x < 2; x++) { if (h->m.ev_kern[x]) cudaEventDestroy(h->m.ev_kern[x]); if (h->m.ev_xchg[x]) cudaEventDestroy(h->m.ev_xchg[x]); }
     delete h;
     return MML_OK;
 }
@@ -2702,9 +2725,9 @@ extern "C" int32_t mml_sgd_schedule_dump(mml_sgd* h, const int32_t* subepoch_seq
     MML_CUDA(cudaStreamSynchronize(s));
     int64_t pos = 0;
     const int G = m.G;
-    for (int S = 0; S < m.R; S++)           // execution order of the GPU-level sub-epochs on this rank
+    for (int S = 0; S < m.RB; S++)          // execution order of the GPU-level sub-epochs on this rank
         for (int t = 0; t < G; t++) {
-            const int B = (S + m.rank) % m.R;
+            const int B = (S + m.split * m.rank) % m.RB;
             const int slot = subepoch_sequence ? subepoch_sequence[t] : t;
             MML_CHECK(slot >= 0 && slot < G, MML_ERR_ARG, "subepoch_sequence[%d] out of range", t);
             for (int j = 0; j < G; j++) {

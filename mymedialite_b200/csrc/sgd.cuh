@@ -22,7 +22,9 @@ struct Sgd {
     Ratings* ratings = nullptr;
     mml_mf_params p{};
     int32_t k = 0, kp = 0, kpl = 0;    // factors, padded row length (32 * kpl), floats per lane
-    int32_t R = 1, rank = 0;           // GPU-level blocks (world size) and own block
+    int32_t R = 1, rank = 0;           // world size (= GPU-level user blocks) and own rank
+    int32_t split = 1, RB = 1;         // item blocks per rank (2 when R > 1: ring overlap) and GPU-level item blocks R * split
+    cudaEvent_t ev_kern[2] = {nullptr, nullptr}, ev_xchg[2] = {nullptr, nullptr};   // sub-epoch kernel done / its ring exchange done
     int32_t G = 1, W = 1;              // worker groups and warps per CTA
     int32_t cpg = 1;                   // CTAs per worker group (async mode; 1 otherwise)
     int32_t variant = 1;               // async epoch kernel: 0 = sgd_block_async, 1 = sgd_block_async2 (get_kernels)
