@@ -1908,7 +1908,7 @@ static int32_t run_dsgd_epoch(Sgd& m, const int32_t* h_seq)
     }
     const int threads = m.W * 32;
     // GPU-level sub-epochs -- the reference's block schedule (BiasedMatrixFactorization.cs:213-214) with GPUs in place of
-    // threads. The item matrix is cut into RB = split x R blocks (split = 2 when R > 1); rank r starts the epoch holding its
+    // threads. The item matrix is cut into RB = split x R blocks (split = 1, or 2 with MMLB200_RING_SPLIT=2); rank r starts the epoch holding its
     // home blocks split*r .. split*r + split-1. In sub-epoch S' it trains on block B = (S' + split*r) mod RB (one persistent
     // launch) and then, ON A SECOND STREAM, sends B to rank r - 1 and receives block B + split from rank r + 1 -- the block it
     // needs in sub-epoch S' + split, which rank r + 1 has just finished. With split = 2 a block therefore has a whole
@@ -2066,9 +2066,11 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
     m.kp = m.k <= 32 ? 32 : (m.k <= 64 ? 64 : (m.k <= 128 ? 128 : 256));
     m.kpl = m.kp / 32;
     m.R = std::max(ctx->n_gpus, 1); m.rank = ctx->rank;
-    {   // item blocks per rank: two, so that the ring step of one overlaps the training of the other (MMLB200_RING_SPLIT=1: one)
+    {   // item blocks per rank. One by default: with two (MMLB200_RING_SPLIT=2) the ring step of one block overlaps the training
+        // of the other, but the sub-epoch kernels lose more on the halved item blocks (shorter user runs) than the overlap wins
+        // -- 25.2 ms against 17.2 ms per epoch on 2 GPUs (profiles/r2_ring_split_2gpu.log).
         const char* e = getenv("MMLB200_RING_SPLIT");
-        m.split = m.R > 1 ? ((e && *e == '1') ? 1 : 2) : 1;
+        m.split = (m.R > 1 && e && *e == '2') ? 2 : 1;
         m.RB = m.R * m.split;
     }
     cudaStream_t s = ctx->stream;

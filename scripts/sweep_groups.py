@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--subgroups", type=int, default=16)
     ap.add_argument("--pop-offset", type=float, default=None)
     ap.add_argument("--variants", default="", help="comma list of MMLB200_SGD_VARIANT values; every shape runs under each")
+    ap.add_argument("--naive", type=int, default=0, help="1: also time the NaiveParallelization list schedule (shape name 'naive')")
     args = ap.parse_args()
     from mymedialite_b200 import engine
     d, k, desc = bench.make_data(args.workload, 0, 1, args.pop_offset)
@@ -58,13 +59,17 @@ def main():
 
     results = []
     variants = [v for v in args.variants.split(",") if v != ""] or [None]
-    for variant, shape in [(v, s) for v in variants for s in args.shapes.split(",")]:
-        G, cpg = (int(x) for x in shape.split("x"))
+    ri = np.random.RandomState(7).permutation(n).astype(np.int32) if args.naive else None
+    for variant, shape in [(v, s) for v in variants for s in args.shapes.split(",")] + ([(None, "naive")] if args.naive else []):
+        naive = shape == "naive"
+        G, cpg = (0, 0) if naive else (int(x) for x in shape.split("x"))
         if variant is not None:
             os.environ["MMLB200_SGD_VARIANT"] = variant
             shape = "v%s:%s" % (variant, shape)
         t0 = time.time()
         params = engine.default_params(biased=1, num_factors=k, num_groups=G, ctas_per_group=cpg, num_subgroups=args.subgroups)
+        if naive:
+            params = engine.default_params(biased=1, num_factors=k, schedule=engine._capi.SCHEDULE_NAIVE, max_threads=8)
         try:
             model = engine.SgdModel(ctx, ratings, params)
         except Exception as ex:          # e.g. a grid the variant's register budget cannot keep co-resident
@@ -80,7 +85,10 @@ def main():
         ms, tr, te = [], [], []
         for _ in range(args.epochs):
             ctx.flush_l2()
-            model.iterate(rs.permutation(model.strata_info()["G"]).astype(np.int32))
+            if naive:
+                model.iterate(random_index=ri)
+            else:
+                model.iterate(rs.permutation(model.strata_info()["G"]).astype(np.int32))
             ms.append(model.stats()[1])
             tr.append(model.evaluate_train()["RMSE"]); te.append(model.evaluate(tu, ti, tv)["RMSE"])
         r = {"shape": shape, "G": G, "cpg": cpg, "build_s": round(build_s, 2), "ms": [round(x, 3) for x in ms],

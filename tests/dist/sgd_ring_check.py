@@ -4,7 +4,7 @@ against the CPU oracle.
   torchrun --nproc-per-node 2 tests/dist/sgd_ring_check.py
 
 Deterministic part: with the conflict-free `rounds` mode the R-GPU epoch equals a serial pass in the order
-(GPU-level sub-epoch S, rank, that rank's dumped schedule of item block (S + rank) mod R); the oracle replays it.
+(GPU-level sub-epoch S, rank, that rank's dumped schedule of the item block it holds in S); the oracle replays it.
 Statistical part: default async mode, per-epoch RMSE within 0.5 % of the oracle's single-threaded run."""
 import os
 import sys
@@ -51,7 +51,8 @@ def main():
         S_of = block // (G * G)
         parts = [None] * world
         dist.all_gather_object(parts, (local_idx[order], S_of))
-        for S in range(world):
+        n_sub = max(int(s_of.max()) for _, s_of in parts if s_of.size) + 1   # world x item blocks per rank
+        for S in range(n_sub):
             for rk in range(world):
                 idx, s_of = parts[rk]
                 om.iterate_indices(idx[s_of == S].astype(np.int32))
