@@ -931,6 +931,12 @@ __device__ __forceinline__ void sgd_block_async(const SgdArgs& a, const int j, c
 // Measured on config 4 (profiles/r2_sgd_variants.log): 16.17 ms (first form) -> 15.78 ms (this form, 16 lanes x 8 floats) ->
 // 14.69 ms (8 lanes x 16 floats: four ratings per warp instruction share the scalar part); cutting the registers to 64 for two
 // CTAs per SM (no next-user row held ahead) gave 14.79 ms and was dropped. At k = 64 the 8 x 8 shape stays (4 x 16 is slower).
+// A third form was measured and dropped (GPU calls o, p of round 2): rows requested TWO ratings ahead with cp.async.cg into a
+// per-worker ring in shared memory (no row registers held ahead, no scoreboard shared with the entry loads; 96 registers,
+// 198 KB of rings). Parity-green, but 15.27 ms against 14.34 ms on config 4 and 2.93 against 2.60 ms on one GPU-level
+// sub-epoch of the 8-GPU ring: the loop is not waiting for a row that a longer request distance would have brought earlier,
+// it queues on the SM's request path to the L2 (l1tex__m_l1tex2xbar_req_cycles_active 67 % of the whole kernel, hand-overs
+// included), and the staged form adds requests (two 16-byte bias chunks per rating) to it.
 template <int KPL>
 struct Row2 {
     float2 r[KPL / 2];
@@ -962,7 +968,7 @@ __device__ __forceinline__ void row2_store(const Row2<KPL>& d, float* row, int s
         reinterpret_cast<float4*>(row)[v * L + sl] = make_float4(d.r[2 * v].x, d.r[2 * v].y, d.r[2 * v + 1].x, d.r[2 * v + 1].y);
 }
 
-template <int L, int KPL, bool BIASED>
+template <int L, int KPL, bool BIASED, bool FREQW>
 __device__ __forceinline__ void sgd_block_async2(const SgdArgs& a, const AsyncHead& head)
 {
     constexpr int KP = L * KPL;
@@ -979,7 +985,7 @@ __device__ __forceinline__ void sgd_block_async2(const SgdArgs& a, const AsyncHe
     if (e0 < e1) {
         row2_load<L, KPL>(pn, a.P + (size_t)u1 * KP, sl);
         if (BIASED) bun = a.bu[u1];
-        if (a.regw_u) regun = a.regw_u[u1];
+        if (FREQW) regun = a.regw_u[u1];
         row2_load_cg<L, KPL>(qn, Qg + (size_t)i1 * KP, sl);
         if (BIASED) bin = ld_cg_f(Bg + i1);
     }
@@ -1018,10 +1024,12 @@ __device__ __forceinline__ void sgd_block_async2(const SgdArgs& a, const AsyncHe
             if (u1 != cur_u) {
                 row2_load<L, KPL>(pn, a.P + (size_t)u1 * KP, sl);
                 if (BIASED) bun = a.bu[u1];
-                if (a.regw_u) regun = a.regw_u[u1];
+                if (FREQW) regun = a.regw_u[u1];
             }
         }
-        const float regi = a.regw_i ? a.regw_i[active ? i : 0] : a.reg_i;
+        // (a template flag, not a run-time test of the pointer: a predicated-off load still ties its register to the scoreboard
+        // it shares with the row loads above, and the first use of regi then waits for those)
+        const float regi = FREQW ? a.regw_i[active ? i : 0] : a.reg_i;
         // dot product on packed pairs
         float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
@@ -1219,14 +1227,14 @@ __global__ void __launch_bounds__(512) sgd_epoch_kernel(const SgdArgs a)
 }
 
 // The same two kernels on sgd_block_async2 (async mode only).
-template <int L, int KPL, bool BIASED>
+template <int L, int KPL, bool BIASED, bool FREQW>
 __global__ void __launch_bounds__(512) sgd_slot2_kernel(const SgdArgs a, const int slot)
 {
     const int j = blockIdx.x / a.cpg, sub = blockIdx.x % a.cpg;
-    sgd_block_async2<L, KPL, BIASED>(a, async_head<L>(a, j, sub, slot));
+    sgd_block_async2<L, KPL, BIASED, FREQW>(a, async_head<L>(a, j, sub, slot));
 }
 
-template <int L, int KPL, bool BIASED>
+template <int L, int KPL, bool BIASED, bool FREQW>
 __global__ void __launch_bounds__(512) sgd_epoch2_kernel(const SgdArgs a)
 {
     const int cpg = a.cpg;
@@ -1251,7 +1259,7 @@ __global__ void __launch_bounds__(512) sgd_epoch2_kernel(const SgdArgs a)
             __syncthreads();
             if (a.wait_stats) waited += clock64() - w0;
         }
-        sgd_block_async2<L, KPL, BIASED>(a, head);
+        sgd_block_async2<L, KPL, BIASED, FREQW>(a, head);
         head = next;
         if (a.G > 1) {
             const long long w0 = a.wait_stats ? clock64() : 0;
@@ -1655,10 +1663,15 @@ static void pick_kernels(bool async, bool biased, bool stage, slot_fn_t* sf, epo
 }
 
 template <int L, int KPL>
-static void pick_kernels_v2(bool biased, slot_fn_t* sf, epoch_fn_t* ef)
+static void pick_kernels_v2(bool biased, bool freqw, slot_fn_t* sf, epoch_fn_t* ef)
 {
-    if (biased) { *sf = sgd_slot2_kernel<L, KPL, true>; *ef = sgd_epoch2_kernel<L, KPL, true>; }
-    else { *sf = sgd_slot2_kernel<L, KPL, false>; *ef = sgd_epoch2_kernel<L, KPL, false>; }
+    if (biased) {
+        if (freqw) { *sf = sgd_slot2_kernel<L, KPL, true, true>; *ef = sgd_epoch2_kernel<L, KPL, true, true>; }
+        else { *sf = sgd_slot2_kernel<L, KPL, true, false>; *ef = sgd_epoch2_kernel<L, KPL, true, false>; }
+    } else {
+        if (freqw) { *sf = sgd_slot2_kernel<L, KPL, false, true>; *ef = sgd_epoch2_kernel<L, KPL, false, true>; }
+        else { *sf = sgd_slot2_kernel<L, KPL, false, false>; *ef = sgd_epoch2_kernel<L, KPL, false, false>; }
+    }
 }
 
 // Async epoch kernel: which loop (Sgd::variant: 0 = sgd_block_async, 1 = sgd_block_async2) and how many lanes per worker
@@ -1674,12 +1687,12 @@ static int32_t get_kernels(Sgd& m, slot_fn_t* sf, epoch_fn_t* ef)
 {
     const bool stage = m.stage_bytes > 0, async = m.p.intra_block == MML_INTRA_ASYNC;
     if (async && m.variant > 0) {
-        const bool b = m.p.biased != 0;
+        const bool b = m.p.biased != 0, fw = m.p.frequency_regularization != 0;
         switch (m.kp) {
-            case 32: pick_kernels_v2<8, 4>(b, sf, ef); break;
-            case 64: pick_kernels_v2<8, 8>(b, sf, ef); break;
-            case 128: pick_kernels_v2<8, 16>(b, sf, ef); break;
-            case 256: pick_kernels_v2<32, 8>(b, sf, ef); break;
+            case 32: pick_kernels_v2<8, 4>(b, fw, sf, ef); break;
+            case 64: pick_kernels_v2<8, 8>(b, fw, sf, ef); break;
+            case 128: pick_kernels_v2<8, 16>(b, fw, sf, ef); break;
+            case 256: pick_kernels_v2<32, 8>(b, fw, sf, ef); break;
             default: set_error("unsupported num_factors"); return MML_ERR_UNSUPPORTED;
         }
         return MML_OK;
