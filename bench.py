@@ -489,6 +489,23 @@ def run_ours(args):
                            "lts_throughput_pct_ncu": facts.get("lts_throughput_pct"),
                            "what": "item rows are updated by red.global.add.v4.f32 executed in the L2 slices"},
             "source": facts.get("source", ncu_facts().get("_source"))}
+    # the limit that binds, measured live: the rate at which THIS GPU's L2 serves one row read (L1 bypassed) plus one row of
+    # red.global.add.v4.f32 per touch on a table the size of the item matrix -- the epoch kernel's item-row traffic per rating
+    # without its arithmetic (mml_ctx_probe_l2). User rows, entries and biases come on top, so 1.0 is not reachable.
+    try:
+        n_items_tab = int(d["n_items"])
+        rows_rr = ctx.probe_l2(2, n_items_tab, 32 * ((k + 31) // 32), 3)
+        rows_rd = ctx.probe_l2(0, n_items_tab, 32 * ((k + 31) // 32), 3)
+        rows_red = ctx.probe_l2(1, n_items_tab, 32 * ((k + 31) // 32), 3)
+        per_gpu = (n_total / world) / (ms_per_step * 1e-3)
+        roof.setdefault("binding", {})["l2"] = {
+            "achieved_rows_s": per_gpu, "peak_rows_s": rows_rr, "frac": per_gpu / rows_rr,
+            "peak_read_rows_s": rows_rd, "peak_red_rows_s": rows_red, "row_bytes": 4 * 32 * ((k + 31) // 32),
+            "what": "item-row traffic of the epoch kernel (per rating: one row read + one row of vector atomics, executed as "
+                    "read-modify-writes in the L2 slices) against mml_ctx_probe_l2 mode 2 on a %d-row table, measured in this run; "
+                    "at N > 1 the achieved rate includes the ring exchange" % n_items_tab}
+    except Exception as ex:      # a diagnostic: never fails the bench line
+        roof.setdefault("binding", {})["l2"] = {"error": str(ex)}
     out = {
         "metric": "BiasedMF SGD ratings/sec", "value": value, "unit": "ratings/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -58,6 +58,7 @@ namespace MyMediaLite.Native
 		[DllImport(LIB)] public static extern int mml_ctx_destroy(IntPtr ctx);
 		[DllImport(LIB)] public static extern int mml_ctx_synchronize(IntPtr ctx);
 		[DllImport(LIB)] public static extern int mml_ctx_flush_l2(IntPtr ctx);
+		[DllImport(LIB)] public static extern int mml_ctx_probe_l2(IntPtr ctx, int mode, int n_rows, int row_floats, int reps, out double rows_per_s);
 		[DllImport(LIB)] public static extern int mml_ctx_sm_count(IntPtr ctx, out int sm_count);
 
 		// ingest (text file -> id mapping -> COO in pinned host memory)

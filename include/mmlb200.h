@@ -57,6 +57,12 @@ int32_t mml_ctx_synchronize(mml_ctx* ctx);
 int32_t mml_ctx_flush_l2(mml_ctx* ctx);
 /* SM count of the device (used by hosts to pick the number of worker groups). */
 int32_t mml_ctx_sm_count(mml_ctx* ctx, int32_t* out);
+/* Measurement aid for the roofline of the SGD epoch kernel (bench.py): the rate at which this GPU's L2 serves the kernel's
+ * own access pattern on a table of n_rows rows of row_floats floats that fits the L2 -- 8-lane workers touching random rows,
+ * rows read L1-bypassed in 128-bit pieces (mode 0), updated with red.global.add.v4.f32 (mode 1), or read and then updated
+ * (mode 2, what the kernel does to an item row per rating). *rows_per_s = rows touched per second, best of `reps` launches. */
+enum { MML_L2_READ = 0, MML_L2_RED = 1, MML_L2_READ_RED = 2 };
+int32_t mml_ctx_probe_l2(mml_ctx* ctx, int32_t mode, int32_t n_rows, int32_t row_floats, int32_t reps, double* rows_per_s);
 
 /* ---- ingest: text file -> id mapping -> COO in pinned host memory (host threads; the step before the path) ------- */
 enum {

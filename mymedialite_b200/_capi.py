@@ -70,6 +70,7 @@ SIGNATURES = {
     "mml_ctx_destroy": (C.c_int32, [vp]),
     "mml_ctx_synchronize": (C.c_int32, [vp]),
     "mml_ctx_flush_l2": (C.c_int32, [vp]),
+    "mml_ctx_probe_l2": (C.c_int32, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "mml_ctx_sm_count": (C.c_int32, [vp, C.POINTER(C.c_int32)]),
     "mml_ingest_file": (C.c_int32, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, PP]),
     "mml_ingest_text": (C.c_int32, [C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, PP]),

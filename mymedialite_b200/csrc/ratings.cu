@@ -235,6 +235,76 @@ extern "C" int32_t mml_ctx_flush_l2(mml_ctx* ctx)
     return MML_OK;
 }
 
+// ---- L2 probe (mml_ctx_probe_l2): the SGD epoch kernel's item-row traffic without the arithmetic ---------------------------
+namespace mml {
+template <int MODE>
+__global__ void __launch_bounds__(512) l2_probe_kernel(float* __restrict__ tab, const uint32_t n_rows, const int row_f4, const int touches,
+                                                       float* __restrict__ sink)
+{
+    const int lane = threadIdx.x & 7;                                   // lane inside the 8-lane worker
+    const uint32_t worker = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    uint32_t x = worker * 2654435761u + 12345u;
+    float acc = 0.f;
+    const int pieces = row_f4 / 8;                                      // 128-bit pieces per lane
+    for (int t = 0; t < touches; t += 2) {                              // two independent rows in flight per worker
+        x = x * 1664525u + 1013904223u;
+        const uint32_t r0 = (x >> 8) % n_rows;
+        x = x * 1664525u + 1013904223u;
+        const uint32_t r1 = (x >> 8) % n_rows;
+        float4* p0 = reinterpret_cast<float4*>(tab) + (size_t)r0 * row_f4 + lane;
+        float4* p1 = reinterpret_cast<float4*>(tab) + (size_t)r1 * row_f4 + lane;
+        for (int v = 0; v < pieces; v++) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            if (MODE != MML_L2_RED) {
+                asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p0 + 8 * v) : "memory");
+                asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p1 + 8 * v) : "memory");
+                acc += (a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w);
+            }
+            if (MODE != MML_L2_READ) {
+                const float d = MODE == MML_L2_READ_RED ? 1e-30f * a.x : 1e-30f;
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(p0 + 8 * v), "f"(d) : "memory");
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(p1 + 8 * v), "f"(d) : "memory");
+            }
+        }
+    }
+    if (acc == 123.456f) sink[0] = acc;                                 // keeps the loads alive
+}
+}  // namespace mml
+
+extern "C" int32_t mml_ctx_probe_l2(mml_ctx* ctx, int32_t mode, int32_t n_rows, int32_t row_floats, int32_t reps, double* rows_per_s)
+{
+    MML_LOCK(mml::ctx_of(ctx));
+    MML_CHECK(ctx != nullptr && rows_per_s != nullptr, MML_ERR_ARG, "NULL argument");
+    MML_CHECK(mode >= MML_L2_READ && mode <= MML_L2_READ_RED && n_rows > 0 && row_floats >= 32 && row_floats % 32 == 0 && reps > 0,
+              MML_ERR_ARG, "mml_ctx_probe_l2: mode 0..2, row_floats a multiple of 32");
+    if (ctx->c.is_root()) return mml_ctx_probe_l2(ctx->c.peers[0], mode, n_rows, row_floats, reps, rows_per_s);
+    MML_CUDA(cudaSetDevice(ctx->c.device));
+    cudaStream_t s = ctx->c.stream;
+    mml::DevBuf<float> tab, sink;
+    MML_TRY(tab.alloc((size_t)n_rows * row_floats));
+    MML_TRY(sink.alloc(1));
+    MML_CUDA(cudaMemsetAsync(tab.p, 0, tab.bytes(), s));
+    const int touches = 2048, grid = ctx->c.sm_count, threads = 512;
+    cudaEvent_t e0, e1;
+    MML_CUDA(cudaEventCreate(&e0)); MML_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int r = 0; r < reps + 1; r++) {                                // launch 0 warms the L2
+        cudaEventRecord(e0, s);
+        if (mode == MML_L2_READ) mml::l2_probe_kernel<MML_L2_READ><<<grid, threads, 0, s>>>(tab.p, (uint32_t)n_rows, row_floats / 4, touches, sink.p);
+        else if (mode == MML_L2_RED) mml::l2_probe_kernel<MML_L2_RED><<<grid, threads, 0, s>>>(tab.p, (uint32_t)n_rows, row_floats / 4, touches, sink.p);
+        else mml::l2_probe_kernel<MML_L2_READ_RED><<<grid, threads, 0, s>>>(tab.p, (uint32_t)n_rows, row_floats / 4, touches, sink.p);
+        cudaEventRecord(e1, s);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    MML_CUDA(cudaGetLastError());
+    *rows_per_s = (double)grid * (threads / 8) * touches / ((double)best * 1e-3);
+    return MML_OK;
+}
+
 extern "C" int32_t mml_ctx_sm_count(mml_ctx* ctx, int32_t* out)
 {
     MML_LOCK(mml::ctx_of(ctx));
