@@ -977,7 +977,8 @@ __device__ __forceinline__ void row2_store(const Row2<KPL>& d, float* row, int s
 // Measured (GPU call r): parity-green, 14.67 ms against 14.34 ms at config 4, 2.68 against 2.60 ms on a ring sub-epoch -- no
 // gain, so the per-lane atomics stay the default (MMLB200_SGD_VARIANT=2 selects this form): the loop is not bound by the SM's
 // store path either. What binds is the L2 itself: a row read plus a row atomic (read-modify-write in the slice) per rating,
-// see mml_ctx_probe_l2 and bench.py's roofline.binding.
+// see mml_ctx_probe_l2 and bench.py's roofline.binding. (Also measured and dropped, GPU call u: prefetch.global.L2 of the
+// entry arrays 64 ratings ahead and of the next run's user row two ratings ahead -- 14.50 ms with, 14.26 ms without.)
 __device__ __forceinline__ void bulk_red_add_f32(float* dst, uint32_t src_smem, uint32_t bytes)
 {
     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" :: "l"(dst), "r"(src_smem), "r"(bytes) : "memory");
