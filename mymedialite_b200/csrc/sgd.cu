@@ -157,6 +157,51 @@ static void build_group_map(GroupMap& m, int32_t n_ext, const uint32_t* counts, 
     }
 }
 
+// Owned-users mode of the async schedule: inside every user group the users are dealt to the group's `nw` workers, heaviest
+// first, each to the lightest worker so far (a worker's load = the ratings of its users, summed over ALL item groups), and the
+// group's internal rows are renumbered worker-major (ascending id inside a worker). The entries of a block, sorted by user row,
+// then fall into one contiguous slice per worker, and a worker meets the same users in every block of the epoch.
+static void pin_users_to_workers(GroupMap& m, const uint32_t* counts, int32_t G, int32_t nw, std::vector<int32_t>& worker_ptr)
+{
+    worker_ptr.assign((size_t)G * nw + 1, 0);
+    std::vector<int32_t> ids, owner;
+    std::vector<std::pair<int64_t, int32_t>> heap;
+    auto cmp = [](const std::pair<int64_t, int32_t>& a, const std::pair<int64_t, int32_t>& b) { return a > b; };
+    for (int32_t g = 0; g < G; g++) {
+        const int32_t lo = m.grp_ptr[g], hi = m.grp_ptr[g + 1];
+        ids.assign(m.to_ext.begin() + lo, m.to_ext.begin() + hi);
+        std::stable_sort(ids.begin(), ids.end(), [&](int32_t a, int32_t b) { return counts[a] > counts[b]; });
+        heap.resize(nw);
+        for (int32_t w = 0; w < nw; w++) heap[w] = std::make_pair((int64_t)0, w);
+        std::make_heap(heap.begin(), heap.end(), cmp);
+        owner.assign(ids.size(), 0);
+        std::vector<int32_t> n_of(nw, 0);
+        for (size_t x = 0; x < ids.size(); x++) {
+            std::pop_heap(heap.begin(), heap.end(), cmp);
+            auto& top = heap.back();
+            owner[x] = top.second;
+            n_of[top.second]++;
+            top.first += std::max<uint32_t>(counts[ids[x]], 1u);
+            std::push_heap(heap.begin(), heap.end(), cmp);
+        }
+        std::vector<int32_t> first(nw + 1, 0);
+        for (int32_t w = 0; w < nw; w++) first[w + 1] = first[w] + n_of[w];
+        for (int32_t w = 0; w < nw; w++) worker_ptr[(size_t)g * nw + w] = lo + first[w];
+        // worker-major, ascending id inside a worker: walk the ids in ascending order and append to their worker's range
+        std::vector<int32_t> of_id_sorted(ids.size());
+        std::vector<std::pair<int32_t, int32_t>> io(ids.size());
+        for (size_t x = 0; x < ids.size(); x++) io[x] = std::make_pair(ids[x], owner[x]);
+        std::sort(io.begin(), io.end());
+        std::vector<int32_t> cur(first.begin(), first.end() - 1);
+        for (auto& pr : io) {
+            const int32_t r = lo + cur[pr.second]++;
+            m.to_int[pr.first] = r;
+            m.to_ext[r] = pr.first;
+        }
+    }
+    worker_ptr[(size_t)G * nw] = m.grp_ptr[G];
+}
+
 static int32_t upload_group_map(GroupMap& m, cudaStream_t s)
 {
     MML_TRY(m.d_grp.alloc(m.n_ext)); MML_TRY(m.d_to_int.alloc(m.n_ext)); MML_TRY(m.d_to_ext.alloc(m.n_int));
@@ -336,6 +381,25 @@ __global__ void strata_split_kernel(const uint32_t* __restrict__ blk_ptr, int32_
     wptr[t] = cut;
 }
 
+// Owned-users mode: worker w's slice of a block = the entries of its own users = [first entry with user row >= worker_ptr[j nw + w],
+// the same for w + 1) -- binary search in the block's entries (sorted by user row).
+__global__ void strata_split_owned_kernel(const uint32_t* __restrict__ blk_ptr, int32_t n_blk, int32_t G, int32_t n_workers,
+                                          const int32_t* __restrict__ ent_u, const int32_t* __restrict__ worker_ptr, uint32_t* __restrict__ wptr)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n_blk * (n_workers + 1)) return;
+    const int32_t blk = (int32_t)(t / (n_workers + 1)), w = (int32_t)(t % (n_workers + 1));
+    const int32_t j = (blk / G) % G;
+    uint32_t lo = blk_ptr[blk], hi = blk_ptr[blk + 1];
+    if (w == n_workers) { wptr[t] = hi; return; }
+    const int32_t first = worker_ptr[(size_t)j * n_workers + w];
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (ent_u[mid] < first) lo = mid + 1; else hi = mid;
+    }
+    wptr[t] = lo;
+}
+
 __global__ void gather_key_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, int64_t n, uint32_t* __restrict__ out)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -390,9 +454,18 @@ static int32_t build_strata_async(Sgd& m, int32_t n_workers)
     MML_CUDA(cudaGetLastError());
     MML_TRY(m.wptr.alloc((size_t)n_blk * (n_workers + 1)));
     const int64_t nt = (int64_t)n_blk * (n_workers + 1);
-    strata_split_kernel<<<(unsigned)ceil_div(nt, 256), 256, 0, s>>>(blk_ptr.p, n_blk, n_workers, m.ent_u.p, m.wptr.p);
-    MML_CUDA(cudaGetLastError());
-    MML_CUDA(cudaStreamSynchronize(s));
+    if (m.owned) {
+        DevBuf<int32_t> d_wp;
+        MML_TRY(d_wp.alloc(m.h_worker_ptr.size()));
+        MML_CUDA(cudaMemcpyAsync(d_wp.p, m.h_worker_ptr.data(), sizeof(int32_t) * m.h_worker_ptr.size(), cudaMemcpyHostToDevice, s));
+        strata_split_owned_kernel<<<(unsigned)ceil_div(nt, 256), 256, 0, s>>>(blk_ptr.p, n_blk, m.G, n_workers, m.ent_u.p, d_wp.p, m.wptr.p);
+        MML_CUDA(cudaGetLastError());
+        MML_CUDA(cudaStreamSynchronize(s));
+    } else {
+        strata_split_kernel<<<(unsigned)ceil_div(nt, 256), 256, 0, s>>>(blk_ptr.p, n_blk, n_workers, m.ent_u.p, m.wptr.p);
+        MML_CUDA(cudaGetLastError());
+        MML_CUDA(cudaStreamSynchronize(s));
+    }
     m.launches += 14;
     return MML_OK;
 }
@@ -1706,6 +1779,170 @@ static SgdArgs make_args(Sgd& m, int32_t B)
 typedef void (*slot_fn_t)(const SgdArgs, const int);
 typedef void (*epoch_fn_t)(const SgdArgs);
 
+// ---- owned-users epoch: no block hand-overs ------------------------------------------------------------------------------------
+// In sgd_epoch2_kernel 12-14 % of the CTA time (19 % on the short sub-epochs of the multi-GPU ring) goes to the hand-over
+// between sub-epochs: every CTA waits for the CTAs that held its next item group and for its sister CTAs (a user row may
+// move between sister CTAs from block to block), then for its own slowest warp. None of that protects anything the async mode
+// needs: item rows are only ever touched by atomics, so two groups on one item group cost nothing but a little more staleness;
+// what must stay exclusive is a USER row. Here users are pinned to workers for the whole epoch (pin_users_to_workers): worker
+// w of group j owns the same users in every block (j, *), its slices of the G blocks -- taken in the epoch's sub-epoch order --
+// form ONE stream of ratings, and the kernel is a single loop over that stream: no flags, no barriers, no cooperative launch.
+// The groups still walk the item groups in the DSGD order (s + j) mod G, in step only as far as equal loads keep them in step
+// (a worker's load is balanced over the whole epoch, not per block): the "blocks of a sub-epoch are disjoint" of the reference
+// becomes approximate, the per-block run structure (what the RMSE gate is sensitive to) is unchanged.
+// Shared memory: per worker the G slice starts and the G + 1 prefix sums of their lengths.
+template <int L, int KPL, bool BIASED, bool FREQW>
+__global__ void __launch_bounds__(512) sgd_free_kernel(const SgdArgs a)
+{
+    extern __shared__ float4 smem4[];
+    constexpr int KP = L * KPL;
+    constexpr int WPW = 32 / L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sl = lane % L;
+    const int cpg = a.cpg, G = a.G;
+    const int j = blockIdx.x / cpg, sub = blockIdx.x % cpg;
+    const int wl = warp * WPW + lane / L;                                   // worker inside the CTA
+    const int wid = sub * (int)(blockDim.x >> 5) * WPW + wl;                 // worker inside the group
+    uint32_t* tab = reinterpret_cast<uint32_t*>(smem4) + (size_t)wl * (2 * G + 1);
+    uint32_t* cum = tab;                                                     // [G + 1]
+    uint32_t* base = tab + G + 1;                                            // [G]
+    const bool has = wid < a.n_workers;
+    for (int t = sl; t < G; t += L) {
+        const uint32_t* wp = a.wptr + (size_t)(j * G + a.seq[t]) * (a.n_workers + 1) + (has ? wid : 0);
+        const uint32_t b0 = wp[0], b1 = has ? wp[1] : b0;
+        base[t] = b0; cum[t + 1] = b1 - b0;
+    }
+    __syncwarp();
+    if (sl == 0) {
+        uint32_t acc = 0;
+        cum[0] = 0;
+        for (int t = 0; t < G; t++) { acc += cum[t + 1]; cum[t + 1] = acc; }
+    }
+    __syncwarp();
+    const uint32_t total = cum[G];
+    // cursor of the entry fetches (two ratings ahead of the one being computed)
+    int kf = 0;
+    uint32_t c0 = 0, c1 = cum[1], bs = base[0];
+    auto entry_of = [&](uint32_t pos) -> uint32_t {                          // pos < total, non-decreasing from call to call
+        while (pos >= c1) { kf++; c0 = c1; c1 = cum[kf + 1]; bs = base[kf]; }
+        return bs + (pos - c0);
+    };
+    float* const Qg = a.Q;
+    float* const Bg = a.bi;
+    int u1 = 0, i1 = 0, u2 = 0, i2 = 0; float v1 = 0.f, v2 = 0.f;
+    if (0 < total) { const uint32_t e = entry_of(0); u1 = a.ent_u[e]; i1 = a.ent_i[e]; v1 = a.ent_v[e]; }
+    if (1 < total) { const uint32_t e = entry_of(1); u2 = a.ent_u[e]; i2 = a.ent_i[e]; v2 = a.ent_v[e]; }
+    Row2<KPL> p, pn, qn;
+    float bu_v = 0.f, bun = 0.f, bin = 0.f, regu = a.reg_u, regun = a.reg_u;
+#pragma unroll
+    for (int f = 0; f < KPL / 2; f++) { p.r[f] = make_float2(0.f, 0.f); pn.r[f] = p.r[f]; qn.r[f] = p.r[f]; }
+    if (0 < total) {
+        row2_load<L, KPL>(pn, a.P + (size_t)u1 * KP, sl);
+        if (BIASED) bun = a.bu[u1];
+        if (FREQW) regun = a.regw_u[u1];
+        row2_load_cg<L, KPL>(qn, Qg + (size_t)i1 * KP, sl);
+        if (BIASED) bin = ld_cg_f(Bg + i1);
+    }
+    uint32_t len = total;
+#pragma unroll
+    for (int d = L; d < 32; d <<= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, d));
+    int cur_u = -1;
+    for (uint32_t t = 0; t < len; t++) {
+        const bool active = t < total;
+        const int u = u1, i = i1; const float v = v1;
+        u1 = u2; i1 = i2; v1 = v2;
+        if (t + 2 < total) { const uint32_t e = entry_of(t + 2); u2 = a.ent_u[e]; i2 = a.ent_i[e]; v2 = a.ent_v[e]; }
+        if (active && u != cur_u) {   // new user run: flush the previous row, take the next one
+            if (cur_u >= 0) {
+                row2_store<L, KPL>(p, a.P + (size_t)cur_u * KP, sl);
+                if (BIASED) a.bu[cur_u] = bu_v;
+            }
+#pragma unroll
+            for (int f = 0; f < KPL / 2; f++) p.r[f] = pn.r[f];
+            bu_v = bun; regu = regun;
+            cur_u = u;
+        }
+        Row2<KPL> q;
+#pragma unroll
+        for (int f = 0; f < KPL / 2; f++) q.r[f] = qn.r[f];
+        const float bi0 = bin;
+        const bool same_item = active && t + 1 < total && i1 == i;     // see sgd_block_async2
+        if (t + 1 < total) {
+            if (!same_item) {
+                row2_load_cg<L, KPL>(qn, Qg + (size_t)i1 * KP, sl);
+                if (BIASED) bin = ld_cg_f(Bg + i1);
+            }
+            if (u1 != cur_u) {
+                row2_load<L, KPL>(pn, a.P + (size_t)u1 * KP, sl);
+                if (BIASED) bun = a.bu[u1];
+                if (FREQW) regun = a.regw_u[u1];
+            }
+        }
+        const float regi = FREQW ? a.regw_i[active ? i : 0] : a.reg_i;
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int f = 0; f < KPL / 2; f++) acc = __ffma2_rn(p.r[f], q.r[f], acc);
+        const float dot = worker_sum<L>(acc.x + acc.y);
+        float gc, dbi = 0.f, bu_new = bu_v;
+        if (BIASED) {
+            const float score = ((a.gb + bu_v) + bi0) + dot;
+            const float sig = __fdividef(1.f, 1.f + __expf(-score));
+            const float err = v - (a.minr + sig * a.range);
+            if (a.loss == MML_LOSS_RMSE) gc = err * sig * (1.f - sig) * a.range;
+            else if (a.loss == MML_LOSS_MAE) gc = (err > 0.f ? 1.f : (err < 0.f ? -1.f : 0.f)) * sig * (1.f - sig) * a.range;
+            else gc = err;
+            const float step = a.blr * a.lr;
+            bu_new = bu_v + step * (gc - a.breg * regu * bu_v);
+            dbi = step * (gc - a.breg * regi * bi0);
+        } else {
+            gc = v - (a.gb + dot);
+        }
+        const float lg = active ? a.lr * gc : 0.f;
+        const float cu = active ? fmaf(-a.lr, regu, 1.f) : 1.f;
+        const float nci = -(a.lr * regi);
+        const float2 lg2 = make_float2(lg, lg), cu2 = make_float2(cu, cu), nci2 = make_float2(nci, nci);
+        Row2<KPL> dq;
+#pragma unroll
+        for (int f = 0; f < KPL / 2; f++) {
+            dq.r[f] = __ffma2_rn(lg2, p.r[f], __fmul2_rn(nci2, q.r[f]));
+            p.r[f] = __ffma2_rn(lg2, q.r[f], __fmul2_rn(cu2, p.r[f]));
+        }
+        if (active) {
+            bu_v = bu_new;
+            float* qrow = Qg + (size_t)i * KP;
+#pragma unroll
+            for (int vv = 0; vv < KPL / 4; vv++)
+                red_add_f4(qrow + 4 * (vv * L + sl), dq.r[2 * vv].x, dq.r[2 * vv].y, dq.r[2 * vv + 1].x, dq.r[2 * vv + 1].y);
+            if (BIASED && sl == 0) red_add_f(Bg + i, dbi);
+            if (same_item) {
+                row2_load_cg<L, KPL>(qn, Qg + (size_t)i * KP, sl);
+                if (BIASED) bin = ld_cg_f(Bg + i);
+            }
+        }
+    }
+    if (cur_u >= 0) {
+        row2_store<L, KPL>(p, a.P + (size_t)cur_u * KP, sl);
+        if (BIASED) a.bu[cur_u] = bu_v;
+    }
+}
+
+template <int L, int KPL>
+static epoch_fn_t pick_free_kernel(bool biased, bool freqw)
+{
+    if (biased) return freqw ? sgd_free_kernel<L, KPL, true, true> : sgd_free_kernel<L, KPL, true, false>;
+    return freqw ? sgd_free_kernel<L, KPL, false, true> : sgd_free_kernel<L, KPL, false, false>;
+}
+static epoch_fn_t get_free_kernel(const Sgd& m)
+{
+    const bool b = m.p.biased != 0, fw = m.p.frequency_regularization != 0;
+    switch (m.kp) {
+        case 32: return pick_free_kernel<8, 4>(b, fw);
+        case 64: return pick_free_kernel<8, 8>(b, fw);
+        case 128: return pick_free_kernel<8, 16>(b, fw);
+        case 256: return pick_free_kernel<32, 8>(b, fw);
+    }
+    return nullptr;
+}
+
 template <int L, int KPL, bool ASYNC>
 static void pick_kernels2(bool biased, bool stage, slot_fn_t* sf, epoch_fn_t* ef)
 {
@@ -2014,7 +2251,16 @@ static int32_t run_dsgd_epoch(Sgd& m, const int32_t* h_seq)
         SgdArgs a = make_args(m, B);
         if (m.R > 1 && S >= split) MML_CUDA(cudaStreamWaitEvent(s, m.ev_xchg[S % split], 0));     // block B has arrived
         if (!tev.empty()) cudaEventRecord(tev[2 * S], s);
-        if (m.p.persistent) {
+        if (m.owned) {                       // owned-users epoch: one plain launch, no hand-overs
+            DevBuf<int32_t>& dseq = m.d_index;
+            if ((int64_t)dseq.n < m.G) MML_TRY(dseq.alloc(m.G));
+            MML_CUDA(cudaMemcpyAsync(dseq.p, seq.data(), sizeof(int32_t) * m.G, cudaMemcpyHostToDevice, s));
+            a.seq = dseq.p;
+            epoch_fn_t fk = get_free_kernel(m);
+            fk<<<m.G * m.cpg, threads, m.free_smem, s>>>(a);
+            MML_CUDA(cudaGetLastError());
+            m.launches++;
+        } else if (m.p.persistent) {
             DevBuf<int32_t>& dseq = m.d_index;   // reuse: serial index cache is unused in DSGD mode
             if ((int64_t)dseq.n < m.G) MML_TRY(dseq.alloc(m.G));
             MML_CUDA(cudaMemcpyAsync(dseq.p, seq.data(), sizeof(int32_t) * m.G, cudaMemcpyHostToDevice, s));
@@ -2251,6 +2497,22 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
         if (async && m.variant >= 2) m.stage_bytes = (size_t)n_workers * 2 * m.kp * sizeof(float);   // two dq buffers per worker
         int32_t nu_max = 1;
         for (int32_t g = 0; g < m.G; g++) nu_max = std::max(nu_max, m.users.grp_ptr[g + 1] - m.users.grp_ptr[g]);
+        {   // owned-users mode, see sgd_free_kernel. Default for rows of up to 64 factors: there the epoch is bound by the
+            // hand-overs (config 2, k = 64: 1.75 ms against 2.07 ms per epoch); at k = 128 the L2 is the limit either way and
+            // the barrier-free loop's extra bookkeeping costs 5 % (config 4: 15.0 against 14.2 ms; ring sub-epoch 2.86 against
+            // 2.60 ms) -- profiles/r2_sgd_owned_users.log. MMLB200_SGD_OWNED = 0 | 1 overrides.
+            const char* eo = getenv("MMLB200_SGD_OWNED");
+            const bool want = eo && (*eo == '0' || *eo == '1') ? *eo == '1' : m.kp <= 64;
+            m.free_smem = (size_t)n_workers * (2 * (size_t)m.G + 1) * sizeof(uint32_t);
+            m.owned = async && m.variant == 1 && p->async_workers == 0 && p->persistent != 0 && want &&
+                      m.free_smem <= (size_t)max_optin && get_free_kernel(m) != nullptr;
+            if (m.owned) {
+                pin_users_to_workers(m.users, cu.data(), m.G, n_workers * m.cpg, m.h_worker_ptr);
+                if (cudaFuncSetAttribute((const void*)get_free_kernel(m), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.free_smem) != cudaSuccess) {
+                    set_error("mml_sgd_create: cudaFuncSetAttribute failed"); st = MML_ERR_CUDA; break;
+                }
+            }
+        }
         if ((st = upload_group_map(m.users, s)) || (st = upload_group_map(m.items, s))) break;
         if ((st = m.d_item_ptr.alloc(m.h_item_ptr.size())) || (st = m.d_hot_cnt.alloc(m.h_hot_cnt.size())) ||
             (st = m.d_user_ptr.alloc(m.users.grp_ptr.size()))) break;

@@ -50,6 +50,9 @@ struct Sgd {
     int64_t n_rounds = 0;
     int32_t n_workers = 0;             // async mode: workers per worker group the slices were cut for
     DevBuf<uint32_t> wptr;             // async mode: [n_blk][n_workers + 1]
+    bool owned = false;                // async mode: users pinned to workers for the whole epoch (no block hand-overs)
+    std::vector<int32_t> h_worker_ptr; // owned: [G * n_workers + 1] first internal user row of every worker
+    size_t free_smem = 0;              // owned: dynamic shared memory of sgd_free_kernel (the workers' slice tables)
     DevBuf<uint32_t> round_ptr;        // [n_rounds + 1] first entry of each round
     DevBuf<uint32_t> blk_round_ptr;    // [n_blk + 1] first round of each block
     DevBuf<int32_t> d_user_ptr;        // [G + 1] internal user row range of each user group

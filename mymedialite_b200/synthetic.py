@@ -10,6 +10,8 @@ popular of 17.8k items 2.8 % of all ratings, twelve times the share of the real 
 0.23 %, MovieLens-10M 0.35 %); with the offset it is 0.25 %. It matters because SGD on one item row is a sequential
 chain: a 2.8 % item alone bounds the epoch time of ANY schedule that keeps the reference's block exclusivity
 (pop_offset=0 reproduces the pure law; DESIGN.md section 6 has both numbers)."""
+import os
+
 import numpy as np
 
 SHAPES = {
@@ -97,6 +99,8 @@ def ratings_cuda(n_users, n_items, n, levels="half", seed=1, test_fraction=0.1, 
     g = torch.Generator(device=dev); g.manual_seed(int(seed))
     gi = torch.Generator(device=dev); gi.manual_seed(int(item_seed if item_seed is not None else seed) + 7919)
     act = torch.exp(torch.randn(n_users, generator=g, device=dev, dtype=torch.float64))
+    if os.environ.get("MMLB200_SYN_ACT_CLIP"):      # diagnostic: cap the user activity law (how much of an epoch is the heaviest user's chain?)
+        act = torch.clamp(act, max=float(os.environ["MMLB200_SYN_ACT_CLIP"]))
     pop = 1.0 / (torch.arange(1, n_items + 1, device=dev, dtype=torch.float64) + (POP_OFFSET if pop_offset is None else pop_offset)) ** 0.8
     pop = pop[torch.randperm(n_items, generator=gi, device=dev)]
     cdf = torch.cumsum(pop / pop.sum(), 0); cdf[-1] = 1.0
@@ -152,6 +156,8 @@ def implicit_cuda(n_users, n_items, n, seed=1, device="cuda", pop_offset=None):
     dev = torch.device(device)
     g = torch.Generator(device=dev); g.manual_seed(int(seed))
     act = torch.exp(torch.randn(n_users, generator=g, device=dev, dtype=torch.float64))
+    if os.environ.get("MMLB200_SYN_ACT_CLIP"):      # diagnostic: cap the user activity law (how much of an epoch is the heaviest user's chain?)
+        act = torch.clamp(act, max=float(os.environ["MMLB200_SYN_ACT_CLIP"]))
     pop = 1.0 / (torch.arange(1, n_items + 1, device=dev, dtype=torch.float64) + (POP_OFFSET if pop_offset is None else pop_offset)) ** 0.8
     pop = pop[torch.randperm(n_items, generator=g, device=dev)]
     cdf = torch.cumsum(pop / pop.sum(), 0); cdf[-1] = 1.0
