@@ -1050,7 +1050,12 @@ __device__ __forceinline__ void row2_store(const Row2<KPL>& d, float* row, int s
 // Measured (GPU call r): parity-green, 14.67 ms against 14.34 ms at config 4, 2.68 against 2.60 ms on a ring sub-epoch -- no
 // gain, so the per-lane atomics stay the default (MMLB200_SGD_VARIANT=2 selects this form): the loop is not bound by the SM's
 // store path either. What binds is the L2 itself: a row read plus a row atomic (read-modify-write in the slice) per rating,
-// see mml_ctx_probe_l2 and bench.py's roofline.binding. (Also measured and dropped, GPU call u: prefetch.global.L2 of the
+// see mml_ctx_probe_l2 and bench.py's roofline.binding. Of the ~11 L2 requests of a rating two are the 4-byte item-bias read
+// and the 4-byte item-bias atomic (plain MF without biases: 12.6 ms against 14.2 ms, call ab). Keeping the biases of the
+// block's item group in shared memory and adding the CTA's net change at the block end (call ac) gave 12.98 ms -- and a
+// WRONG model (train RMSE of epoch 1 at 10M ratings: 0.814 against 0.735): with 8 CTAs per group every CTA pushes its own
+// copy of a popular item's bias towards the target and the eight net changes are summed. The bias has to be shared by the
+// whole group at every rating, i.e. stay in the L2. (Also measured and dropped, GPU call u: prefetch.global.L2 of the
 // entry arrays 64 ratings ahead and of the next run's user row two ratings ahead -- 14.50 ms with, 14.26 ms without.)
 __device__ __forceinline__ void bulk_red_add_f32(float* dst, uint32_t src_smem, uint32_t bytes)
 {

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--subgroups", type=int, default=16)
     ap.add_argument("--pop-offset", type=float, default=None)
     ap.add_argument("--variants", default="", help="comma list of MMLB200_SGD_VARIANT values; every shape runs under each")
+    ap.add_argument("--biased", type=int, default=1, help="0: plain MatrixFactorization (no bias terms)")
     ap.add_argument("--naive", type=int, default=0, help="1: also time the NaiveParallelization list schedule (shape name 'naive')")
     args = ap.parse_args()
     from mymedialite_b200 import engine
@@ -67,7 +68,7 @@ def main():
             os.environ["MMLB200_SGD_VARIANT"] = variant
             shape = "v%s:%s" % (variant, shape)
         t0 = time.time()
-        params = engine.default_params(biased=1, num_factors=k, num_groups=G, ctas_per_group=cpg, num_subgroups=args.subgroups)
+        params = engine.default_params(biased=args.biased, num_factors=k, num_groups=G, ctas_per_group=cpg, num_subgroups=args.subgroups)
         if naive:
             params = engine.default_params(biased=1, num_factors=k, schedule=engine._capi.SCHEDULE_NAIVE, max_threads=8)
         try:
