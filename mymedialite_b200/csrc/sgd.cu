@@ -2506,11 +2506,25 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
             // hand-overs (config 2, k = 64: 1.75 ms against 2.07 ms per epoch); at k = 128 the L2 is the limit either way and
             // the barrier-free loop's extra bookkeeping costs 5 % (config 4: 15.0 against 14.2 ms; ring sub-epoch 2.86 against
             // 2.60 ms) -- profiles/r2_sgd_owned_users.log. MMLB200_SGD_OWNED = 0 | 1 overrides.
+            // Not when a single user outweighs the average worker several times over: the workers of such users are still
+            // running long after everyone else has finished, and an epoch that ends with a few heavy users alone on the
+            // popular item rows leaves those rows fitted to them -- seen on a set with a 37k-rating user among 10M ratings
+            // (34 x the average worker load; tests/cpp host_test multi): test RMSE jumping between 0.58 and 0.68 from epoch to
+            // epoch. Config 2's heaviest user is ~6 x the average load and stays within 0.05 % of the oracle; the line is drawn at 8.
             const char* eo = getenv("MMLB200_SGD_OWNED");
-            const bool want = eo && (*eo == '0' || *eo == '1') ? *eo == '1' : m.kp <= 64;
+            uint32_t cu_max = 0;
+            for (uint32_t c : cu) cu_max = std::max(cu_max, c);
+            const double avg_load = (double)r->n / std::max<double>((double)m.G * n_workers * m.cpg, 1.0);
+            const bool want = eo && (*eo == '0' || *eo == '1') ? *eo == '1' : (m.kp <= 64 && (double)cu_max <= 8.0 * avg_load);
             m.free_smem = (size_t)n_workers * (2 * (size_t)m.G + 1) * sizeof(uint32_t);
             m.owned = async && m.variant == 1 && p->async_workers == 0 && p->persistent != 0 && want &&
                       m.free_smem <= (size_t)max_optin && get_free_kernel(m) != nullptr;
+            {
+                const char* tr = getenv("MMLB200_TRACE");
+                if (async && tr && *tr && *tr != '0')
+                    fprintf(stderr, "[mmlb200 sgd rank %d] async schedule: %s (heaviest user %u ratings, average worker load %.0f)\n", m.rank,
+                            m.owned ? "owned-users loop" : "block schedule with hand-overs", cu_max, avg_load);
+            }
             if (m.owned) {
                 pin_users_to_workers(m.users, cu.data(), m.G, n_workers * m.cpg, m.h_worker_ptr);
                 if (cudaFuncSetAttribute((const void*)get_free_kernel(m), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.free_smem) != cudaSuccess) {

@@ -326,6 +326,48 @@ def test_naive_parallelization_tracks_single_threaded_oracle(eng, biased, k):
     assert gm.learnrate == lr0                      # Decay = 1: UpdateLearnRate (twice, MaxThreads > 1) leaves it alone
 
 
+@pytest.mark.parametrize("env,k,biased", [({"MMLB200_SGD_OWNED": "1"}, 128, True), ({"MMLB200_SGD_OWNED": "0"}, 32, True),
+                                          ({"MMLB200_SGD_OWNED": "1"}, 10, False), ({"MMLB200_SGD_VARIANT": "2"}, 128, True),
+                                          ({"MMLB200_SGD_VARIANT": "2"}, 64, False)])
+def test_async_loop_forms_track_single_threaded_oracle(eng, monkeypatch, env, k, biased):
+    """The forms of the lock-free block schedule the library does not pick by default for this row length -- the owned-users
+    loop (users pinned to workers, no block hand-overs) forced on at k = 128 and off at k = 32, and the bulk-reduction form of
+    the item step -- against the same gate as the default: every rating visited exactly once, per-epoch train / test RMSE
+    within 0.5 % of the oracle's single-threaded run from the same factors."""
+    engine, ctx = eng
+    from mymedialite_b200 import synthetic
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    d = synthetic.ratings(3000, 800, 300000, "half", 13)
+    u, i, v = d["train"]; tu, ti, tv = d["test"]
+    rng = O.Random(1)
+    om = O.Model(u, i, v, biased=biased, num_factors=k)
+    om.init(rng)
+    r, gm = gpu_model(eng, u, i, v, biased, k, om, num_groups=6, ctas_per_group=3, num_subgroups=4)
+    assert np.array_equal(np.sort(gm.schedule()), np.arange(u.size))
+    for epoch in range(6):
+        om.iterate(rng)
+        gm.iterate()
+        o_tr, o_te = om.evaluate(u, i, v)["RMSE"], om.evaluate(tu, ti, tv)["RMSE"]
+        g_tr, g_te = gm.evaluate_train()["RMSE"], gm.evaluate(tu, ti, tv)["RMSE"]
+        assert abs(g_tr - o_tr) / o_tr < 0.005, (epoch, g_tr, o_tr)
+        assert abs(g_te - o_te) / o_te < 0.005, (epoch, g_te, o_te)
+
+
+def test_l2_probe_reports_rates(eng):
+    """mml_ctx_probe_l2 (the denominator of bench.py's roofline.binding.l2): positive, and a row atomic is dearer than a row read."""
+    engine, ctx = eng
+    rd = ctx.probe_l2(0, 4096, 128, 2)
+    red = ctx.probe_l2(1, 4096, 128, 2)
+    both = ctx.probe_l2(2, 4096, 128, 2)
+    assert rd > 1e9 and red > 1e9 and both > 1e9
+    assert red < rd and both < rd
+    with pytest.raises(Exception):
+        ctx.probe_l2(3, 4096, 128, 2)
+    with pytest.raises(Exception):
+        ctx.probe_l2(0, 4096, 100, 2)
+
+
 def test_predict_evaluate_objective_match_oracle(eng):
     engine, ctx = eng
     d = small_data()
