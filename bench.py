@@ -652,7 +652,7 @@ def main():
     ap.add_argument("--sgd-only", action="store_true", help="skip the zipf0 / strong / train_e2e / wrmf_c3 / topn_c5 sub-objects")
     ap.add_argument("--groups", type=int, default=0)
     ap.add_argument("--cpg", type=int, default=0, help="CTAs per worker group (async mode); groups default to SMs / cpg")
-    ap.add_argument("--subgroups", type=int, default=16)
+    ap.add_argument("--subgroups", type=int, default=0, help="warps per CTA; 0 = the library's default for the row length and GPU count")
     ap.add_argument("--persistent", type=int, default=-1)
     ap.add_argument("--hot", type=float, default=0.0)
     ap.add_argument("--copies", type=int, default=0)

@@ -2421,15 +2421,21 @@ extern "C" int32_t mml_sgd_create(mml_ctx* hctx, mml_ratings* hr, const mml_mf_p
             // Default (both 0): groups of 8 CTAs, SMs / 8 groups (18 x 8 on 148 SMs: with the packed loop config 4 runs 14.50 ms
             // against 14.89 ms at 37 x 4, 15.5 ms at 9 x 16 and 16.2 ms at 4 x 37; one GPU-level sub-epoch of the 8-GPU ring
             // 2.70 / 2.72 / 3.20 / 3.02 ms: profiles/r2_sgd_grid_waits.log); it also leaves four SMs to the ring's transfers.
+            // CTA size (both 0, one GPU, rows of 128+ factors): 4 warps and 32 CTAs per group -- four CTAs per SM, so that an SM
+            // whose CTA waits at a hand-over has three others to run: 13.73 ms against 14.2 ms for 18 x 8 CTAs of 16 warps and
+            // 13.82 ms for 18 x 16 of 8 (profiles/r2_sgd_cta_size.log). Rows of up to 64 factors: 8 warps, 18 x 8 (config 2: 1.66 ms
+            // against 1.75 ms with 16 warps). Ring sub-epochs (several GPUs): 16 warps, 18 x 8 (2.60 against 2.68 ms).
+            const bool all_default = p->num_groups <= 0 && p->ctas_per_group <= 0 && p->num_subgroups <= 0 && ctx->sm_count >= 16;
+            const bool small_ctas = all_default && p->intra_block == MML_INTRA_ASYNC && m.R == 1 && m.kp >= 128;
             m.cpg = 1;
             if (p->intra_block == MML_INTRA_ASYNC) {
                 if (p->ctas_per_group > 0) m.cpg = std::min(p->ctas_per_group, ctx->sm_count);
-                else if (p->num_groups <= 0 && ctx->sm_count >= 16) m.cpg = 8;
+                else if (p->num_groups <= 0 && ctx->sm_count >= 16) m.cpg = small_ctas ? 32 : 8;
             }
-            int32_t G = p->num_groups > 0 ? p->num_groups : ctx->sm_count / m.cpg;
+            int32_t G = p->num_groups > 0 ? p->num_groups : (small_ctas ? ctx->sm_count / 8 : ctx->sm_count / m.cpg);
             G = std::min(G, std::min(r->n_users(), r->n_items()));
             m.G = std::max(G, 1);
-            int32_t W = p->num_subgroups > 0 ? p->num_subgroups : 8;
+            int32_t W = p->num_subgroups > 0 ? p->num_subgroups : (small_ctas ? 4 : (all_default && m.R > 1 ? 16 : 8));
             m.W = std::max(1, std::min(W, 16));
             m.hot_copies = p->hot_copies > 0 ? std::min(p->hot_copies, 64) : 8;
         } else {
