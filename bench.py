@@ -260,6 +260,10 @@ def time_sgd(args, D, ctx, d, k, steps, warmup, e2e=True):
     out = {"n": n, "n_total": int(round(D.sum(n))), "ms": ms, "build_s": build_s, "info": info, "params": params,
            "launches": int(launches1 - launches0), "epochs_run": warmup + steps}
     if e2e:
+        model.iterate(seq())                      # one untimed end-to-end step: the first Evaluate() allocates its device scratch
+        model.evaluate(tu, ti, tv)
+        ctx.synchronize()
+        out["epochs_run"] += 1
         D.barrier(ctx)
         t0 = time.time()
         rmse = None
