@@ -424,8 +424,11 @@ static int32_t build_strata_async(Sgd& m, int32_t n_workers)
     const int32_t n_blk = (int32_t)n_blk64;
     m.n_blk = n_blk;
     m.n_workers = n_workers;
-    DevBuf<uint32_t> blk, key, vals, ktmp, vtmp, cnt, bad, blk_ptr;
-    MML_TRY(blk.alloc(n)); MML_TRY(key.alloc(n)); MML_TRY(vals.alloc(n)); MML_TRY(ktmp.alloc(n)); MML_TRY(vtmp.alloc(n));
+    // the five n-sized temporaries come from the stream-ordered pool (kept between calls: a second Train() in the same
+    // process does not pay cudaMalloc / cudaFree of 2 GB again)
+    StreamBuf<uint32_t> blk, key, vals, ktmp, vtmp;
+    DevBuf<uint32_t> cnt, bad, blk_ptr;
+    MML_TRY(blk.alloc(n, s)); MML_TRY(key.alloc(n, s)); MML_TRY(vals.alloc(n, s)); MML_TRY(ktmp.alloc(n, s)); MML_TRY(vtmp.alloc(n, s));
     MML_TRY(cnt.alloc(n_blk)); MML_TRY(bad.alloc(1)); MML_TRY(blk_ptr.alloc((size_t)n_blk + 1));
     MML_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(uint32_t), s));
     MML_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), s));
