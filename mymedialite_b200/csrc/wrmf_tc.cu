@@ -261,8 +261,10 @@ constexpr int SV_NB = 16;
 constexpr int SV_LD = 17;
 constexpr int SV_BLK = SV_NB * SV_LD;
 template <typename T> struct SvCfg;
-template <> struct SvCfg<double> { static constexpr int max_refine = 3; static constexpr int ctas = 2; };
-template <> struct SvCfg<float> { static constexpr int max_refine = 8; static constexpr int ctas = 3; };
+template <> struct SvCfg<double> { static constexpr int max_refine = 3; static constexpr int ctas = 2; static constexpr int red_bufs = 8; };
+// float: FOUR rows per SM (round 2, late): 64 registers (20 bytes of spill) and 56 KB -- the gather's per-warp partial sums
+// share four buffers, warps 4..7 adding to what warps 0..3 wrote.
+template <> struct SvCfg<float> { static constexpr int max_refine = 8; static constexpr int ctas = 4; static constexpr int red_bufs = 4; };
 
 struct SolveArgs {
     const uint32_t* row_ptr; const int32_t* cols; const int32_t* order; int32_t q_lo, q_hi;
@@ -351,7 +353,7 @@ template <typename T>
 __host__ __device__ inline size_t sv_smem_bytes(int np)
 {
     const size_t kp = (size_t)np * SV_NB, nblk = (size_t)np * (np + 1) / 2;
-    return sizeof(double) * kp * (3 + SV_THREADS / 32) + sizeof(T) * (nblk * SV_BLK + (size_t)np * SV_BLK + 2 * kp);
+    return sizeof(double) * kp * (3 + SvCfg<T>::red_bufs) + sizeof(T) * (nblk * SV_BLK + (size_t)np * SV_BLK + 2 * kp);
 }
 
 template <typename T>
@@ -372,8 +374,9 @@ __global__ void __launch_bounds__(SV_THREADS, SvCfg<T>::ctas) wrmf_solve_kernel(
     double* b0 = sv_smem;                             // [kp] right-hand side
     double* wv = b0 + kp;                             // [kp] solution
     double* rv = wv + kp;                             // [kp] residual
-    double* red = rv + kp;                            // [8][kp] per-warp partial sums of the refinement gather
-    T* L = reinterpret_cast<T*>(red + (size_t)(SV_THREADS / 32) * kp);   // [nblk][16][17]
+    constexpr int RB = SvCfg<T>::red_bufs;
+    double* red = rv + kp;                            // [RB][kp] partial sums of the refinement gather
+    T* L = reinterpret_cast<T*>(red + (size_t)RB * kp);   // [nblk][16][17]
     T* Dinv = L + (size_t)nblk * SV_BLK;              // [np][16][17] inverses of the diagonal blocks
     T* rdiag = Dinv + (size_t)np * SV_BLK;            // [kp] 1 / L[i][i]
     T* xs = rdiag + kp;                               // [kp] right-hand side / solution of a triangular solve
@@ -529,15 +532,22 @@ __global__ void __launch_bounds__(SV_THREADS, SvCfg<T>::ctas) wrmf_solve_kernel(
             for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
             r0 += d * (double)h.x; r1 += d * (double)h.y; r2 += d * (double)h.z; r3 += d * (double)h.w;
         }
-        if (col_ok) {
+        if (col_ok && warp < RB) {
             double* rw = red + (size_t)warp * kp + 4 * lane;
             rw[0] = r0; rw[1] = r1; rw[2] = r2; rw[3] = r3;
         }
         __syncthreads();
+        if (RB < SV_THREADS / 32) {                   // the upper warps add to the buffers of the lower ones
+            if (col_ok && warp >= RB) {
+                double* rw = red + (size_t)(warp - RB) * kp + 4 * lane;
+                rw[0] += r0; rw[1] += r1; rw[2] += r2; rw[3] += r3;
+            }
+            __syncthreads();
+        }
         double rmax = 0.0, bmax = 0.0;
         for (int f = tid; f < k; f += SV_THREADS) {
             double sacc = 0.0;
-            for (int wi = 0; wi < SV_THREADS / 32; wi++) sacc += red[(size_t)wi * kp + f];
+            for (int wi = 0; wi < RB; wi++) sacc += red[(size_t)wi * kp + f];
             const double r = rv[f] - a.alpha * sacc;
             rv[f] = r;
             rmax = fmax(rmax, fabs(r)); bmax = fmax(bmax, fabs(b0[f]));
