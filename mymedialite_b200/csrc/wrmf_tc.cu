@@ -159,8 +159,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wrmf_syrk_kernel(const SyrkArgs
     } else if (warp <= 4) {
         // ===== gather producers: warp pw takes rows pw, pw + 4, ... of every stage =====
         // (Keeping two stages in flight per warp -- rows of stage t + 1 and item ids of stage t + 2 requested while stage t is
-        // split and stored -- was measured: 48.9 against 48.2 ms per epoch at config 3, GPU call ai. The gather's latency is
-        // not what bounds the kernel.)
+        // split and stored -- was measured: 48.9 against 48.2 ms per epoch at config 3, GPU call ai; a ring of FOUR stages in
+        // registers the same, call aj: the stage's fence.proxy.async compiles to MEMBAR.ALL.CTA, which waits for every load the
+        // warp has in flight, so a deeper request queue drains at each stage anyway. Writing the tiles with st.async (async
+        // proxy, bytes counted on the `full` barrier, no fence; needs a launch with a 1 x 1 x 1 cluster attribute -- without
+        // one STAS is an illegal instruction on sm_100a, scripts/probe/st_async_probe.cu) kept the requests in flight but was
+        // slower still: 51.8 ms, call am.)
         const int pw = warp - 1;
         const int j = lane >> 3, c = lane & 7;           // 128-byte block along M/N and 16-byte chunk inside it
         const bool col_ok = 4 * lane < a.k;
