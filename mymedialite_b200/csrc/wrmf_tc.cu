@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wrmf_syrk_kernel(const SyrkArgs
         // warp has in flight, so a deeper request queue drains at each stage anyway. Writing the tiles with st.async (async
         // proxy, bytes counted on the `full` barrier, no fence; needs a launch with a 1 x 1 x 1 cluster attribute -- without
         // one STAS is an illegal instruction on sm_100a, scripts/probe/st_async_probe.cu) kept the requests in flight but was
-        // slower still: 51.8 ms, call am.)
+        // slower still: 51.8 ms, call am. One warp per WHOLE stage (four stages in flight per CTA, each warp's fence draining
+        // only its own loads): 51.9 ms, call an. More requests in flight do not help this kernel.)
         const int pw = warp - 1;
         const int j = lane >> 3, c = lane & 7;           // 128-byte block along M/N and 16-byte chunk inside it
         const bool col_ok = 4 * lane < a.k;
