@@ -346,13 +346,16 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
         // n_groups is even (two groups per tile and thread). A tile's TMEM buffer is handed back as soon as its second
         // group sits in registers -- before this warp blocks on the next tile's accumulators and before it examines the
         // group -- so that the MMAs of tile t + 2 start while the second half of tile t is still being examined.
+        // (Round 2: both groups of a tile are now in registers BEFORE the first is examined -- the hand-back used to wait for
+        // examine(gi), which sat between the second fetch and its wait; with two TMEM buffers the MMAs of tile t + 2 wait for
+        // exactly that hand-back.)
         if (n_groups > 0) fetch(0, va);
         for (int gi = 0; gi < n_groups; gi += 2) {
             tc_ld_wait();                                   // va holds group gi (first group of its tile)
             fetch(gi + 1, vb);                              // same tile: no barrier
-            examine(gi, va);
             tc_ld_wait();                                   // vb holds group gi + 1: the tile's buffer has been read
             release(gi + 1);
+            examine(gi, va);
             if (gi + 2 < n_groups) fetch(gi + 2, va);       // waits for the next tile's MMAs
             examine(gi + 1, vb);
         }
