@@ -92,6 +92,17 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// One lane of a converged warp (elect.sync). The single-thread roles run as WHOLE warps in uniform control flow with the
+// issuing instructions under this predicate: inside `if (lane == 0)` ptxas wraps every tcgen05.mma / TMA instruction (their
+// operands live in uniform registers) in an ELECT / R2UR / BRA.U.ANY loop -- ~16 instructions and ~130 cycles per MMA in the
+// round-1 kernel, i.e. the issuing thread, not the tensor pipe, set the pace (ncu: the issuer busy all the time, 49 % of its
+// samples fixed-latency waits, tensor pipe 38 % active).
+__device__ __forceinline__ bool tc_elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
@@ -189,35 +200,41 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp == 0) {
-        if (lane == 0) {    // ===== TMA producer =====
+        // ===== TMA producer (whole warp, one elected lane issues) =====
+        if (tc_elect_one()) {
             mbar_expect_tx(bar_u, 2u * a.kc * TC_CHUNK_BYTES);
             for (int h = 0; h < 2; h++)
                 for (int c = 0; c < a.kc; c++)
                     tma_load_2d(smem_u + (uint32_t)(h * a.kc + c) * TC_CHUNK_BYTES, &map_u, bar_u, c * a.epc, row0 + h * 128);
-            int stage = 0; uint32_t phase = 0;
-            for (int t = t_begin; t < t_end; t++)
-                for (int c = 0; c < a.kc; c++) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1u, a.err);
+        }
+        __syncwarp();
+        int stage = 0; uint32_t phase = 0;
+        for (int t = t_begin; t < t_end; t++)
+            for (int c = 0; c < a.kc; c++) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1u, a.err);
+                if (tc_elect_one()) {
                     mbar_expect_tx(bar_full + 8 * stage, TC_CHUNK_BYTES);
                     tma_load_2d(smem_v + (uint32_t)stage * TC_CHUNK_BYTES, &map_v, bar_full + 8 * stage, c * a.epc, t * TC_N);
-                    if (++stage == a.stages) { stage = 0; phase ^= 1u; }
                 }
-        }
+                __syncwarp();
+                if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+            }
     } else if (warp == 1) {
-        if (lane == 0) {    // ===== MMA issuer =====
-            mbar_wait(bar_u, 0, a.err);
+        // ===== MMA issuer (whole warp, one elected lane issues) =====
+        mbar_wait(bar_u, 0, a.err);
+        tc_fence_after();
+        int stage = 0; uint32_t phase = 0;
+        int it = 0;
+        for (int t = t_begin; t < t_end; t++, it++) {
+            const int buf = it & 1;
+            const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(bar_tempty + 8 * buf, aphase ^ 1u, a.err);
             tc_fence_after();
-            int stage = 0; uint32_t phase = 0;
-            int it = 0;
-            for (int t = t_begin; t < t_end; t++, it++) {
-                const int buf = it & 1;
-                const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(bar_tempty + 8 * buf, aphase ^ 1u, a.err);
+            for (int c = 0; c < a.kc; c++) {
+                mbar_wait(bar_full + 8 * stage, phase, a.err);
                 tc_fence_after();
-                for (int c = 0; c < a.kc; c++) {
-                    mbar_wait(bar_full + 8 * stage, phase, a.err);
-                    tc_fence_after();
-                    const uint32_t vb = smem_v + (uint32_t)stage * TC_CHUNK_BYTES;
+                const uint32_t vb = smem_v + (uint32_t)stage * TC_CHUNK_BYTES;
+                if (tc_elect_one()) {
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const uint32_t ub = smem_u + (uint32_t)(h * a.kc + c) * TC_CHUNK_BYTES;
@@ -234,9 +251,10 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
                         }
                     }
                     tc_commit(bar_empty + 8 * stage);          // frees the V chunk when these MMAs have read it
-                    if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+                    if (c + 1 == a.kc) tc_commit(bar_tfull + 8 * buf);   // ... and, after the tile's last chunk, its accumulators are complete
                 }
-                tc_commit(bar_tfull + 8 * buf);                // accumulators of this tile complete
+                __syncwarp();
+                if (++stage == a.stages) { stage = 0; phase ^= 1u; }
             }
         }
     } else {

@@ -53,6 +53,12 @@ __device__ __forceinline__ void ws_mbar_wait(uint32_t bar, uint32_t parity, uint
         if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1u); __threadfence(); asm volatile("trap;"); }
     }
 }
+__device__ __forceinline__ bool ws_elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void ws_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void ws_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void ws_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
@@ -126,35 +132,36 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wrmf_syrk_kernel(const SyrkArgs
 
     // every role walks the same row sequence: batch-local rows blockIdx.x, blockIdx.x + gridDim.x, ...; empty rows are skipped
     if (warp == 0) {
-        if (lane == 0) {    // ===== MMA issuer =====
-            int stage = 0; uint32_t phase = 0; int it = 0;
-            for (int q = a.q_lo + blockIdx.x; q < a.q_hi; q += gridDim.x) {
-                const int u = a.order[q];
-                const uint32_t K = a.row_ptr[u + 1] - a.row_ptr[u];
-                if (K == 0) continue;
-                const int buf = it & 3;
-                ws_mbar_wait(bar_tempty + 8 * buf, ((uint32_t)(it >> 2) & 1u) ^ 1u, a.err);
+        // ===== MMA issuer: the whole warp walks the rows in uniform control flow, one elected lane issues (inside
+        //       `if (lane == 0)` ptxas wraps every tcgen05.mma in an ELECT / R2UR / BRA.U.ANY loop: see topn_tc.cu) =====
+        int stage = 0; uint32_t phase = 0; int it = 0;
+        for (int q = a.q_lo + blockIdx.x; q < a.q_hi; q += gridDim.x) {
+            const int u = a.order[q];
+            const uint32_t K = a.row_ptr[u + 1] - a.row_ptr[u];
+            if (K == 0) continue;
+            const int buf = it & 3;
+            ws_mbar_wait(bar_tempty + 8 * buf, ((uint32_t)(it >> 2) & 1u) ^ 1u, a.err);
+            ws_fence_after();
+            const uint32_t d = tmem_base + (uint32_t)(buf * 128);
+            for (uint32_t base = 0; base < K; base += WS_KCH) {
+                ws_mbar_wait(bar_full + 8 * stage, phase, a.err);
                 ws_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(buf * 128);
-                bool first = true;
-                for (uint32_t base = 0; base < K; base += WS_KCH) {
-                    ws_mbar_wait(bar_full + 8 * stage, phase, a.err);
-                    ws_fence_after();
-                    const uint32_t hi = smem0 + (uint32_t)stage * 2 * WS_TILE, lo = hi + WS_TILE;
-                    const int groups = (int)min((uint32_t)4, (K - base + 7) / 8);
+                const uint32_t hi = smem0 + (uint32_t)stage * 2 * WS_TILE, lo = hi + WS_TILE;
+                const int groups = (int)min((uint32_t)4, (K - base + 7) / 8);
+                if (ws_elect_one()) {
                     for (int g = 0; g < groups; g++) {
                         const uint64_t dh = ws_smem_desc(hi + g * 4096), dl = ws_smem_desc(lo + g * 4096);
-                        ws_mma_tf32(d, dh, dh, WS_IDESC, first ? 0u : 1u);
+                        ws_mma_tf32(d, dh, dh, WS_IDESC, (base | (uint32_t)g) != 0u ? 1u : 0u);
                         ws_mma_tf32(d, dh, dl, WS_IDESC, 1u);
                         ws_mma_tf32(d, dl, dh, WS_IDESC, 1u);
-                        first = false;
                     }
                     ws_commit(bar_empty + 8 * stage);
-                    if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
+                    if (base + WS_KCH >= K) ws_commit(bar_tfull + 8 * buf);     // the row's last stage: its accumulators are complete
                 }
-                ws_commit(bar_tfull + 8 * buf);
-                it++;
+                __syncwarp();
+                if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
             }
+            it++;
         }
     } else if (warp <= 4) {
         // ===== gather producers: warp pw takes rows pw, pw + 4, ... of every stage =====
