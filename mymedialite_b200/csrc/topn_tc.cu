@@ -126,6 +126,26 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr)
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// The same descriptor as two words: the low one carries the (address >> 4) field, so the descriptor of the same tile 32 bytes
+// further along K is low + 2; the high word is a constant. The issuing thread builds its descriptors this way: one add per
+// operand and MMA instead of a shift / mask / or chain per descriptor (the issuing thread's instruction stream is what the
+// tensor pipe waits for: ncu after the elect.sync change still showed it busy 90 % of the time at 7 cycles per instruction).
+__device__ __forceinline__ uint32_t tc_desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+constexpr uint32_t TC_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ void tc_mma_tf32_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(TC_DESC_HI) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(TC_DESC_HI) : "memory");
+}
 // Instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128.
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((128u >> 4) << 24);
 // The same with A = B = BF16 (kind::f16; K = 16 per instruction = the same 32 bytes of a swizzled row as 8 TF32 values).
@@ -225,36 +245,40 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
         tc_fence_after();
         int stage = 0; uint32_t phase = 0;
         int it = 0;
+        const int kc = a.kc, n_stages = a.stages;
+        const bool use_bf16 = a.bf16 != 0, no_mma = (a.dbg & 2) != 0;
+        const uint32_t u_lo = tc_desc_lo(smem_u), v_lo = tc_desc_lo(smem_v);
+        const uint32_t half_lo = (uint32_t)kc * (TC_CHUNK_BYTES >> 4);      // descriptor distance of the two row halves of U
         for (int t = t_begin; t < t_end; t++, it++) {
             const int buf = it & 1;
             const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
             mbar_wait(bar_tempty + 8 * buf, aphase ^ 1u, a.err);
             tc_fence_after();
-            for (int c = 0; c < a.kc; c++) {
+            const uint32_t d0 = tmem_base + (uint32_t)(buf * 2 * TC_N), d1 = d0 + (uint32_t)TC_N;
+            for (int c = 0; c < kc; c++) {
                 mbar_wait(bar_full + 8 * stage, phase, a.err);
                 tc_fence_after();
-                const uint32_t vb = smem_v + (uint32_t)stage * TC_CHUNK_BYTES;
                 if (tc_elect_one()) {
+                    const uint32_t a0 = u_lo + (uint32_t)c * (TC_CHUNK_BYTES >> 4), a1 = a0 + half_lo;
+                    const uint32_t b0 = v_lo + (uint32_t)stage * (TC_CHUNK_BYTES >> 4);
+                    if (!no_mma) {
+                        if (use_bf16) {
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const uint32_t ub = smem_u + (uint32_t)(h * a.kc + c) * TC_CHUNK_BYTES;
-                        const uint32_t d = tmem_base + (uint32_t)((buf * 2 + h) * TC_N);
-                        if (a.dbg & 2) continue;
-                        if (a.bf16) {
+                            for (int kk = 0; kk < 4; kk++) tc_mma_bf16_lo(d0, a0 + 2 * kk, b0 + 2 * kk, TC_IDESC_BF16, (c | kk) != 0 ? 1u : 0u);
 #pragma unroll
-                            for (int kk = 0; kk < 4; kk++)
-                                tc_mma_bf16(d, tc_smem_desc(ub + kk * 32), tc_smem_desc(vb + kk * 32), TC_IDESC_BF16, (c | kk) != 0 ? 1u : 0u);
+                            for (int kk = 0; kk < 4; kk++) tc_mma_bf16_lo(d1, a1 + 2 * kk, b0 + 2 * kk, TC_IDESC_BF16, (c | kk) != 0 ? 1u : 0u);
                         } else {
 #pragma unroll
-                            for (int kk = 0; kk < 4; kk++)
-                                tc_mma_tf32(d, tc_smem_desc(ub + kk * 32), tc_smem_desc(vb + kk * 32), TC_IDESC, (c | kk) != 0 ? 1u : 0u);
+                            for (int kk = 0; kk < 4; kk++) tc_mma_tf32_lo(d0, a0 + 2 * kk, b0 + 2 * kk, TC_IDESC, (c | kk) != 0 ? 1u : 0u);
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++) tc_mma_tf32_lo(d1, a1 + 2 * kk, b0 + 2 * kk, TC_IDESC, (c | kk) != 0 ? 1u : 0u);
                         }
                     }
                     tc_commit(bar_empty + 8 * stage);          // frees the V chunk when these MMAs have read it
-                    if (c + 1 == a.kc) tc_commit(bar_tfull + 8 * buf);   // ... and, after the tile's last chunk, its accumulators are complete
+                    if (c + 1 == kc) tc_commit(bar_tfull + 8 * buf);     // ... and, after the tile's last chunk, its accumulators are complete
                 }
                 __syncwarp();
-                if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+                if (++stage == n_stages) { stage = 0; phase ^= 1u; }
             }
         }
     } else {
