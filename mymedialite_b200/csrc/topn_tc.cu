@@ -635,7 +635,9 @@ static inline int tc_grid(int64_t n, int threads = 256)
 // Operand precision of the filter GEMM: TF32 (default) or BF16 (twice the tensor rate, half the operand bytes; the wider
 // error bound lengthens the exactly re-scored candidate list and sends more users to the exact path). Measured on config 5
 // (gpurun_out/pp_topn.csv, qq_topn_trace.log): the collecting pass is bound by operand staging, not by the MMA rate, so
-// BF16 gains 6 % there and loses it again in the finalize kernel. mml_topn_set_filter / MMLB200_TC_FILTER=bf16|tf32.
+// BF16 gains 6 % there and loses it again in the finalize kernel. (Round 2, after the MMA-issuing thread stopped being the
+// bound: 90.9 ms per call with BF16 against 92.0 ms with TF32, 665 instead of 29 users on the exact path -- still no reason to
+// switch.) mml_topn_set_filter / MMLB200_TC_FILTER=bf16|tf32.
 static int g_tc_filter = -1;
 void topn_tc_set_filter(int kind) { g_tc_filter = kind; }
 bool topn_tc_filter_bf16()
